@@ -1,0 +1,24 @@
+"""avr_b200 — B200 (sm_100a) ray-sampling + volume-compositing path of
+yankeesong/adaptive-volume-rendering, behind the reference's own renderer API.
+
+    from avr_b200 import VolumeRenderer, AdaptiveVolumeRenderer, volume_integral, ...
+
+The kernels live in ``csrc/`` and are reached only through the C ABI in
+``include/avr_b200.h`` (``lib/libavr_b200.so``, loaded with ctypes by ``_lib``).
+"""
+from ._lib import AvrError, LIB_PATH, load as load_library  # noqa: F401
+from .renderers import (  # noqa: F401
+    AdaptiveVolumeRenderer,
+    VolumeRenderer,
+    sample_coarse,
+    sample_depth,
+    sample_fine,
+    volume_integral,
+    volume_integral_rgbs,
+)
+from . import ops, geometry  # noqa: F401
+
+__all__ = [
+    "AdaptiveVolumeRenderer", "VolumeRenderer", "sample_coarse", "sample_depth", "sample_fine",
+    "volume_integral", "volume_integral_rgbs", "ops", "geometry", "AvrError", "load_library", "LIB_PATH",
+]

@@ -1,0 +1,96 @@
+"""ctypes binding of libavr_b200.so — the only way the host side reaches the kernels.
+
+There is deliberately no fallback: if the shared library is missing, cannot be
+loaded, or the current device is not an sm_100 part, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libavr_b200.so")
+
+AVR_OK = 0
+ABI_VERSION = 1
+
+_P = c_void_p  # every device pointer crosses as a plain address
+
+# name -> (restype, argtypes); mirrors include/avr_b200.h one to one
+PROTOTYPES = {
+    "avr_abi_version": (c_int, []),
+    "avr_status_string": (c_char_p, [c_int]),
+    "avr_last_cuda_error": (c_char_p, []),
+    "avr_device_check": (c_int, []),
+    "avr_composite_plan": (c_int, [c_int64, c_int, _P, _P]),
+    "avr_set_force_generic": (None, [c_int]),
+    "avr_coarse_sample_fwd": (c_int, [_P, _P, c_int, _P, c_int64, c_int, _P, _P]),
+    "avr_coarse_sample_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
+    "avr_importance_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int,
+                                      c_float, _P, _P, _P, _P, _P]),
+    "avr_sort_rays": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
+    "avr_composite_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P]),
+    "avr_composite_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "avr_composite_fwd_packed": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_float, _P, _P, _P, _P]),
+    "avr_composite_bwd_packed": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_float, _P, _P, _P]),
+    "avr_coarse_sample_fwd_packed": (c_int, [_P, _P, c_int, _P, _P, c_int64, c_int64, _P, _P]),
+    "avr_importance_sample_packed": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int64, c_int, c_int,
+                                             _P, _P, _P]),
+    "avr_composite_fwd_bwd_host": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, c_int64]),
+}
+
+_lib = None
+
+
+class AvrError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (once).  Raises AvrError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AvrError(
+            f"{LIB_PATH} is missing: build it with `python adaptive-volume-rendering_b200/build.py` "
+            "(or __graft_entry__.build()). There is no CPU or eager fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.avr_abi_version() != ABI_VERSION:
+        raise AvrError(f"ABI mismatch: library {lib.avr_abi_version()}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != AVR_OK:
+        lib = load()
+        msg = lib.avr_status_string(status).decode()
+        detail = lib.avr_last_cuda_error().decode()
+        raise AvrError(f"{what}: {msg} ({status})" + (f" [{detail}]" if detail and status in (-2, -3, -5) else ""))
+
+
+def ptr(t) -> int | None:
+    """Device (or host) address of a tensor, None for None."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise AvrError(
+                "avr_b200 ops run on CUDA tensors only (sm_100a kernels; there is no CPU fallback) — "
+                f"got a tensor on {t.device}"
+            )

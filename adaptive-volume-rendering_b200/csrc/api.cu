@@ -1,0 +1,294 @@
+// extern "C" entry points of libavr_b200.so: argument checks and kernel selection.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "avr_common.cuh"
+#include "kernels.h"
+
+namespace avr {
+
+static thread_local char g_last_error[256] = "";
+static std::atomic<int> g_force_generic{0};
+
+void set_last_cuda_error(cudaError_t e) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int check_launch() {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess) return AVR_OK;
+  set_last_cuda_error(e);
+  (void)cudaGetLastError();  // clear the (non-sticky) launch error so the next call starts clean
+  return AVR_ERR_LAUNCH;
+}
+
+static inline cudaStream_t as_stream(avr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace avr
+
+using namespace avr;
+
+extern "C" {
+
+int avr_abi_version(void) { return AVR_B200_ABI_VERSION; }
+
+const char* avr_status_string(int status) {
+  switch (status) {
+    case AVR_OK: return "ok";
+    case AVR_ERR_BAD_ARG: return "bad argument";
+    case AVR_ERR_LAUNCH: return "kernel launch failed";
+    case AVR_ERR_NO_DEVICE: return "no sm_100 device";
+    case AVR_ERR_UNSUPPORTED: return "unsupported shape";
+    case AVR_ERR_RUNTIME: return "cuda runtime call failed";
+    default: return "unknown status";
+  }
+}
+
+const char* avr_last_cuda_error(void) { return g_last_error; }
+
+int avr_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e);
+    (void)cudaGetLastError();
+    return AVR_ERR_NO_DEVICE;
+  }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess || major != 10) {
+    if (e != cudaSuccess) set_last_cuda_error(e);
+    return AVR_ERR_NO_DEVICE;
+  }
+  return AVR_OK;
+}
+
+void avr_set_force_generic(int on) { g_force_generic.store(on ? 1 : 0); }
+
+int avr_composite_plan(int64_t R, int K, const void* rgbs, const void* z) {
+  SpanPlan p;
+  if (g_force_generic.load()) return 0;
+  return span_plan(R, K, rgbs, z, &p) ? 1 : 0;
+}
+
+/* ---------------------------------------------------------------- samplers -- */
+
+int avr_coarse_sample_fwd(const float* near, const float* far, int bound_stride, const float* u, int64_t R,
+                          int K, float* z, avr_stream_t stream) {
+  if (R < 0 || K < 1 || (bound_stride != 0 && bound_stride != 1)) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!near || !far || !u || !z) return AVR_ERR_BAD_ARG;
+  return launch_coarse_fwd(near, far, bound_stride, u, nullptr, R, K, R * K, z, as_stream(stream));
+}
+
+int avr_coarse_sample_fwd_packed(const float* near, const float* far, int bound_stride, const float* u,
+                                 const int64_t* offsets, int64_t R, int64_t S, float* z,
+                                 avr_stream_t stream) {
+  if (R < 0 || S < 0 || (bound_stride != 0 && bound_stride != 1)) return AVR_ERR_BAD_ARG;
+  if (R == 0 || S == 0) return AVR_OK;
+  if (!near || !far || !u || !z || !offsets) return AVR_ERR_BAD_ARG;
+  return launch_coarse_fwd(near, far, bound_stride, u, offsets, R, 0, S, z, as_stream(stream));
+}
+
+int avr_coarse_sample_bwd(const float* g_z, const float* u, int64_t R, int K, float* d_near, float* d_far,
+                          avr_stream_t stream) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!g_z || !u || !d_near || !d_far) return AVR_ERR_BAD_ARG;
+  return launch_coarse_bwd(g_z, u, R, K, d_near, d_far, as_stream(stream));
+}
+
+int avr_importance_sample(const float* weights, const float* z_coarse, const float* u, const float* u2,
+                          const float* normals, const float* near, const float* far, int bound_stride,
+                          int64_t R, int Kc, int n_imp, int n_depth, float depth_std, float* z_fine,
+                          float* z_sorted, float* cdf, int32_t* idx, avr_stream_t stream) {
+  if (R < 0 || Kc < 1 || n_imp < 0 || n_depth < 0 || (bound_stride != 0 && bound_stride != 1))
+    return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!weights || !near || !far) return AVR_ERR_BAD_ARG;
+  if (n_imp > 0 && (!u || !u2)) return AVR_ERR_BAD_ARG;
+  if (z_sorted && !z_coarse) return AVR_ERR_BAD_ARG;
+  if (z_sorted && n_depth > 0 && !normals) return AVR_ERR_BAD_ARG;
+  if (!z_sorted) n_depth = 0;
+  return launch_importance(weights, z_coarse, u, u2, normals, near, far, bound_stride, nullptr, nullptr, R, Kc,
+                           n_imp, n_depth, depth_std, z_fine, z_sorted, cdf, idx, as_stream(stream));
+}
+
+int avr_importance_sample_packed(const float* weights, const float* z_coarse, const float* u, const float* u2,
+                                 const float* near, const float* far, int bound_stride, const int64_t* offsets,
+                                 const int64_t* fine_offsets, int64_t R, int max_coarse, int max_fine,
+                                 float* z_fine, float* z_sorted, avr_stream_t stream) {
+  if (R < 0 || max_coarse < 1 || max_fine < 0 || (bound_stride != 0 && bound_stride != 1))
+    return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!weights || !near || !far || !offsets || !fine_offsets || !u || !u2) return AVR_ERR_BAD_ARG;
+  if (z_sorted && !z_coarse) return AVR_ERR_BAD_ARG;
+  return launch_importance(weights, z_coarse, u, u2, nullptr, near, far, bound_stride, offsets, fine_offsets, R,
+                           max_coarse, max_fine, 0, 0.f, z_fine, z_sorted, nullptr, nullptr, as_stream(stream));
+}
+
+int avr_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, avr_stream_t stream) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!z_in || !z_out) return AVR_ERR_BAD_ARG;
+  return launch_sort_rays(z_in, R, K, z_out, perm, as_stream(stream));
+}
+
+/* ------------------------------------------------------------- compositing -- */
+
+int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int white_back, float infinity,
+                      float* w, float* rgb, float* depth, avr_stream_t stream) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!rgbs || !z || !rgb || !depth || !aligned16(rgbs)) return AVR_ERR_BAD_ARG;
+  cudaStream_t st = as_stream(stream);
+  SpanPlan plan;
+  int64_t done = 0;
+  if (!g_force_generic.load() && span_plan(R, K, rgbs, z, &plan) && (w == nullptr || aligned16(w))) {
+    int rc = launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, st);
+    if (rc != AVR_OK) return rc;
+    done = plan.main_rays;
+  }
+  if (done < R) {
+    return launch_composite_fwd_generic(rgbs + done * K * 4, z + done * K, nullptr, R - done, K, white_back,
+                                        infinity, w ? w + done * K : nullptr, rgb + done * 3, depth + done, st);
+  }
+  return AVR_OK;
+}
+
+int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, const float* g_depth,
+                      const float* g_w, int64_t R, int K, int white_back, float infinity, float* d_rgbs,
+                      float* d_z, avr_stream_t stream) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!rgbs || !z || !d_rgbs || !aligned16(rgbs) || !aligned16(d_rgbs)) return AVR_ERR_BAD_ARG;
+  cudaStream_t st = as_stream(stream);
+  SpanPlan plan;
+  int64_t done = 0;
+  // the span kernel covers the training configuration (no grad into weights or z);
+  // g_w / d_z requests take the generic kernel
+  if (!g_force_generic.load() && !g_w && !d_z && span_plan(R, K, rgbs, z, &plan)) {
+    int rc = launch_composite_bwd_span(plan, rgbs, z, g_rgb, g_depth, K, white_back, infinity, d_rgbs, st);
+    if (rc != AVR_OK) return rc;
+    done = plan.main_rays;
+  }
+  if (done < R) {
+    return launch_composite_bwd_generic(rgbs + done * K * 4, z + done * K, nullptr,
+                                        g_rgb ? g_rgb + done * 3 : nullptr, g_depth ? g_depth + done : nullptr,
+                                        g_w ? g_w + done * K : nullptr, R - done, K, white_back, infinity,
+                                        d_rgbs + done * K * 4, d_z ? d_z + done * K : nullptr, st);
+  }
+  return AVR_OK;
+}
+
+int avr_composite_fwd_packed(const float* rgbs, const float* z, const int64_t* offsets, int64_t R, int64_t S,
+                             int white_back, float infinity, float* w, float* rgb, float* depth,
+                             avr_stream_t stream) {
+  if (R < 0 || S < 0) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!offsets || !rgb || !depth) return AVR_ERR_BAD_ARG;
+  if (S > 0 && (!rgbs || !z || !aligned16(rgbs))) return AVR_ERR_BAD_ARG;
+  return launch_composite_fwd_generic(rgbs, z, offsets, R, 0, white_back, infinity, w, rgb, depth,
+                                      as_stream(stream));
+}
+
+int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* offsets, const float* g_rgb,
+                             const float* g_depth, const float* g_w, int64_t R, int64_t S, int white_back,
+                             float infinity, float* d_rgbs, float* d_z, avr_stream_t stream) {
+  if (R < 0 || S < 0) return AVR_ERR_BAD_ARG;
+  if (R == 0 || S == 0) return AVR_OK;
+  if (!offsets || !rgbs || !z || !d_rgbs || !aligned16(rgbs) || !aligned16(d_rgbs)) return AVR_ERR_BAD_ARG;
+  return launch_composite_bwd_generic(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs,
+                                      d_z, as_stream(stream));
+}
+
+/* ------------------------------------------------ host-buffer (end to end) -- */
+
+#define AVR_RT(call)                  \
+  do {                                \
+    cudaError_t e_ = (call);          \
+    if (e_ != cudaSuccess) {          \
+      set_last_cuda_error(e_);        \
+      rc = AVR_ERR_RUNTIME;           \
+      goto cleanup;                   \
+    }                                 \
+  } while (0)
+
+int avr_composite_fwd_bwd_host(const float* rgbs, const float* z, const float* g_rgb, const float* g_depth,
+                               int64_t R, int K, int white_back, float infinity, float* rgb, float* depth,
+                               float* d_rgbs, int64_t chunk_rays) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!rgbs || !z || !rgb || !depth || !d_rgbs) return AVR_ERR_BAD_ARG;
+  int rc = avr_device_check();
+  if (rc != AVR_OK) return rc;
+
+  // Rays are independent, so the pass is chunked and software-pipelined over three
+  // slots: while chunk c computes, chunk c+1 uploads and chunk c-1 downloads (PCIe is
+  // full duplex).  Chunks are multiples of 96 rays so every chunk start stays aligned
+  // for the span kernels whatever K is.
+  constexpr int kSlots = 3;
+  if (chunk_rays <= 0) {
+    int64_t target = (int64_t)(48ll << 20) / ((int64_t)K * 16);  // ~48 MiB of rgbs per chunk
+    chunk_rays = target < 96 ? 96 : target;
+  }
+  chunk_rays = (chunk_rays + 95) / 96 * 96;
+  if (chunk_rays > R) chunk_rays = R;
+  const int64_t n_chunks = (R + chunk_rays - 1) / chunk_rays;
+
+  struct Slot {
+    float *rgbs, *z, *g_rgb, *g_depth, *rgb, *depth, *d_rgbs;
+    cudaStream_t stream;
+  } slots[kSlots];
+  memset(slots, 0, sizeof(slots));
+  const size_t nk = (size_t)chunk_rays * K;
+  for (int s = 0; s < kSlots && s < n_chunks; ++s) {
+    AVR_RT(cudaStreamCreateWithFlags(&slots[s].stream, cudaStreamNonBlocking));
+    AVR_RT(cudaMalloc(&slots[s].rgbs, nk * 16));
+    AVR_RT(cudaMalloc(&slots[s].z, nk * 4));
+    AVR_RT(cudaMalloc(&slots[s].g_rgb, (size_t)chunk_rays * 12));
+    AVR_RT(cudaMalloc(&slots[s].g_depth, (size_t)chunk_rays * 4));
+    AVR_RT(cudaMalloc(&slots[s].rgb, (size_t)chunk_rays * 12));
+    AVR_RT(cudaMalloc(&slots[s].depth, (size_t)chunk_rays * 4));
+    AVR_RT(cudaMalloc(&slots[s].d_rgbs, nk * 16));
+  }
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    Slot& sl = slots[c % kSlots];
+    const int64_t r0 = c * chunk_rays;
+    const int64_t rn = (R - r0 < chunk_rays) ? R - r0 : chunk_rays;
+    const size_t n = (size_t)rn * K;
+    // stream order inside a slot serialises reuse of its buffers
+    AVR_RT(cudaMemcpyAsync(sl.rgbs, rgbs + r0 * K * 4, n * 16, cudaMemcpyHostToDevice, sl.stream));
+    AVR_RT(cudaMemcpyAsync(sl.z, z + r0 * K, n * 4, cudaMemcpyHostToDevice, sl.stream));
+    if (g_rgb) AVR_RT(cudaMemcpyAsync(sl.g_rgb, g_rgb + r0 * 3, (size_t)rn * 12, cudaMemcpyHostToDevice, sl.stream));
+    if (g_depth) AVR_RT(cudaMemcpyAsync(sl.g_depth, g_depth + r0, (size_t)rn * 4, cudaMemcpyHostToDevice, sl.stream));
+    rc = avr_composite_fwd(sl.rgbs, sl.z, rn, K, white_back, infinity, nullptr, sl.rgb, sl.depth, sl.stream);
+    if (rc != AVR_OK) goto cleanup;
+    rc = avr_composite_bwd(sl.rgbs, sl.z, g_rgb ? sl.g_rgb : nullptr, g_depth ? sl.g_depth : nullptr, nullptr, rn,
+                           K, white_back, infinity, sl.d_rgbs, nullptr, sl.stream);
+    if (rc != AVR_OK) goto cleanup;
+    AVR_RT(cudaMemcpyAsync(rgb + r0 * 3, sl.rgb, (size_t)rn * 12, cudaMemcpyDeviceToHost, sl.stream));
+    AVR_RT(cudaMemcpyAsync(depth + r0, sl.depth, (size_t)rn * 4, cudaMemcpyDeviceToHost, sl.stream));
+    AVR_RT(cudaMemcpyAsync(d_rgbs + r0 * K * 4, sl.d_rgbs, n * 16, cudaMemcpyDeviceToHost, sl.stream));
+  }
+  for (int s = 0; s < kSlots; ++s)
+    if (slots[s].stream) AVR_RT(cudaStreamSynchronize(slots[s].stream));
+cleanup:
+  for (int s = 0; s < kSlots; ++s) {
+    if (slots[s].stream) {
+      if (rc != AVR_OK) cudaStreamSynchronize(slots[s].stream);
+      cudaStreamDestroy(slots[s].stream);
+    }
+    cudaFree(slots[s].rgbs);
+    cudaFree(slots[s].z);
+    cudaFree(slots[s].g_rgb);
+    cudaFree(slots[s].g_depth);
+    cudaFree(slots[s].rgb);
+    cudaFree(slots[s].depth);
+    cudaFree(slots[s].d_rgbs);
+  }
+  return rc;
+}
+
+}  // extern "C"

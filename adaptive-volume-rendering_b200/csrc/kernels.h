@@ -1,0 +1,45 @@
+// Internal launcher declarations (host side).  Each returns an avr_status.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace avr {
+
+// composite_generic.cu — any shape, dense (offsets == nullptr) or packed
+int launch_composite_fwd_generic(const float* rgbs, const float* z, const int64_t* offsets, int64_t R,
+                                 int K, int white_back, float infinity, float* w, float* rgb,
+                                 float* depth, cudaStream_t stream);
+int launch_composite_bwd_generic(const float* rgbs, const float* z, const int64_t* offsets,
+                                 const float* g_rgb, const float* g_depth, const float* g_w, int64_t R,
+                                 int K, int white_back, float infinity, float* d_rgbs, float* d_z,
+                                 cudaStream_t stream);
+
+// composite_span.cu — dense, TMA-staged blocked scan.  `span_plan` says whether a
+// shape is eligible and how many leading rays the span kernel covers (the caller
+// runs the generic kernel on the remaining tail rays).
+struct SpanPlan {
+  int L;              // samples per lane (odd)
+  int rays_per_tile;  // whole rays per warp tile
+  int64_t main_rays;  // rays covered by full tiles
+};
+bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan);
+int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
+                              int white_back, float infinity, float* w, float* rgb, float* depth,
+                              cudaStream_t stream);
+int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
+                              const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
+                              cudaStream_t stream);
+
+// samplers.cu
+int launch_coarse_fwd(const float* near, const float* far, int bound_stride, const float* u,
+                      const int64_t* offsets, int64_t R, int K, int64_t S, float* z, cudaStream_t stream);
+int launch_coarse_bwd(const float* g_z, const float* u, int64_t R, int K, float* d_near, float* d_far,
+                      cudaStream_t stream);
+int launch_importance(const float* weights, const float* z_coarse, const float* u, const float* u2,
+                      const float* normals, const float* near, const float* far, int bound_stride,
+                      const int64_t* offsets, const int64_t* fine_offsets, int64_t R, int Kc, int n_imp,
+                      int n_depth, float depth_std, float* z_fine, float* z_sorted, float* cdf,
+                      int32_t* idx, cudaStream_t stream);
+int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, cudaStream_t stream);
+
+}  // namespace avr

@@ -1,0 +1,350 @@
+// Depth samplers: stratified coarse sampling (+ its gradient), inverse-CDF importance
+// sampling with the per-ray merge sort, and a stand-alone per-ray sort.
+//
+// Reference: sample_coarse renderers.py:4-24, sample_fine :27-54, sample_depth :56-66,
+// clamp/cat/sort :255-258, sort :494.  The samplers reproduce the reference's operation
+// order with explicitly rounded intrinsics (no FMA contraction) so that, given the same
+// draws (and, for the importance sampler, the same CDF), depths are bit-identical to
+// torch-CPU.
+#include <math_constants.h>
+
+#include "avr_common.cuh"
+#include "kernels.h"
+
+namespace avr {
+
+constexpr int kSamplerWarps = 4;
+
+// z = near + (far-near)*(j/K) + (u*(far-near))/K       renderers.py:12-14
+__device__ __forceinline__ float coarse_depth(float near, float far, int j, int K, float u) {
+  const float span = __fsub_rn(far, near);
+  const float bin = __fdiv_rn((float)j, (float)K);
+  const float z = __fadd_rn(near, __fmul_rn(span, bin));
+  return __fadd_rn(z, __fdiv_rn(__fmul_rn(u, span), (float)K));
+}
+
+__global__ void __launch_bounds__(256)
+coarse_fwd_dense_kernel(const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
+                        const float* __restrict__ u, int64_t total, int K, float* __restrict__ z) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / K;
+    const int j = (int)(i - r * K);
+    const int64_t b = bound_stride ? r : 0;
+    z[i] = coarse_depth(near[b], far[b], j, K, u[i]);
+  }
+}
+
+// packed: one warp per ray, each ray stratified over its own count
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+coarse_fwd_packed_kernel(const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
+                         const float* __restrict__ u, const int64_t* __restrict__ offsets, int64_t R,
+                         float* __restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * kSamplerWarps;
+  for (int64_t r = blockIdx.x * (int64_t)kSamplerWarps + (threadIdx.x >> 5); r < R; r += warps) {
+    const int64_t begin = offsets[r];
+    const int cnt = (int)(offsets[r + 1] - begin);
+    const int64_t b = bound_stride ? r : 0;
+    const float nr = near[b], fr = far[b];
+    for (int j = lane; j < cnt; j += 32) z[begin + j] = coarse_depth(nr, fr, j, cnt, u[begin + j]);
+  }
+}
+
+// d_near = sum_j g_j (1 - f_j), d_far = sum_j g_j f_j with f_j = j/K + u_j/K
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+coarse_bwd_kernel(const float* __restrict__ g_z, const float* __restrict__ u, int64_t R, int K,
+                  float* __restrict__ d_near, float* __restrict__ d_far) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * kSamplerWarps;
+  for (int64_t r = blockIdx.x * (int64_t)kSamplerWarps + (threadIdx.x >> 5); r < R; r += warps) {
+    float dn = 0.f, df = 0.f;
+    for (int j = lane; j < K; j += 32) {
+      const float g = g_z[r * K + j];
+      const float f = (float)j / (float)K + u[r * K + j] / (float)K;
+      df += g * f;
+      dn += g * (1.0f - f);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      dn += __shfl_xor_sync(0xffffffffu, dn, d);
+      df += __shfl_xor_sync(0xffffffffu, df, d);
+    }
+    if (lane == 0) {
+      d_near[r] = dn;
+      d_far[r] = df;
+    }
+  }
+}
+
+// ---- warp-synchronous bitonic sort of P (power of two) keys in shared memory --------
+// With `idx` non-null the (key, index) pairs are ordered lexicographically, which makes
+// the result the stable sort of the keys.
+__device__ __forceinline__ void warp_bitonic_sort(float* key, int* idx, int P, int lane) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < (P >> 1); t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));  // index with the `stride` bit clear
+        const int hi = lo + stride;
+        const bool ascending = ((lo & size) == 0);
+        const float a = key[lo], b = key[hi];
+        bool swap;
+        if (idx) {
+          const int ia = idx[lo], ib = idx[hi];
+          const bool a_gt_b = (a > b) || (a == b && ia > ib);
+          swap = (a_gt_b == ascending);
+          if (swap) {
+            idx[lo] = ib;
+            idx[hi] = ia;
+          }
+        } else {
+          swap = ((a > b) == ascending) && (a != b);
+        }
+        if (swap) {
+          key[lo] = b;
+          key[hi] = a;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__host__ __device__ inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ---- importance sampling + merge ----------------------------------------------------
+struct ImportanceArgs {
+  const float* weights;
+  const float* z_coarse;
+  const float* u;
+  const float* u2;
+  const float* normals;
+  const float* near;
+  const float* far;
+  int bound_stride;
+  const int64_t* offsets;       // packed coarse layout or null
+  const int64_t* fine_offsets;  // packed fine layout or null
+  int64_t R;
+  int Kc, n_imp, n_depth;
+  float depth_std;
+  float* z_fine;
+  float* z_sorted;
+  float* cdf;
+  int32_t* idx;
+  int cdf_cap;   // floats reserved per warp for the cdf
+  int sort_cap;  // floats reserved per warp for the sort buffer (power of two)
+};
+
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+importance_kernel(const ImportanceArgs a) {
+  extern __shared__ __align__(16) float fsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* cdf = fsmem + warp * (a.cdf_cap + a.sort_cap);
+  float* sortbuf = cdf + a.cdf_cap;
+  const int64_t warps = (int64_t)gridDim.x * kSamplerWarps;
+
+  for (int64_t r = blockIdx.x * (int64_t)kSamplerWarps + warp; r < a.R; r += warps) {
+    int64_t cbase, fbase;
+    int kc, n;
+    if (a.offsets) {
+      cbase = a.offsets[r];
+      kc = (int)(a.offsets[r + 1] - cbase);
+      fbase = a.fine_offsets[r];
+      n = (int)(a.fine_offsets[r + 1] - fbase);
+    } else {
+      cbase = r * (int64_t)a.Kc;
+      kc = a.Kc;
+      fbase = r * (int64_t)a.n_imp;
+      n = a.n_imp;
+    }
+    const int nd = a.n_depth;
+    const int64_t bi = a.bound_stride ? r : 0;
+    const float near = a.near[bi], far = a.far[bi];
+    const float span = __fsub_rn(far, near);
+
+    // (a) S = sum_j (w_j + 1e-5)                                           renderers.py:36-37
+    float part = 0.f;
+    for (int j = lane; j < kc; j += 32) part += __fadd_rn(a.weights[cbase + j], kPdfEps);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    const float S = part;
+
+    // (b) cdf_0 = 0, cdf_{j+1} = cdf_j + pdf_j: 32-wide shuffle scan with a running carry,
+    // then a running max so the table is non-decreasing by construction (a parallel
+    // prefix sum is not monotone in floating point; the search below requires it).
+    __syncwarp();
+    if (lane == 0) cdf[0] = 0.f;
+    float carry = 0.f, hi = 0.f;
+    for (int j0 = 0; j0 < kc; j0 += 32) {
+      const int j = j0 + lane;
+      float v = (j < kc) ? __fdiv_rn(__fadd_rn(a.weights[cbase + j], kPdfEps), S) : 0.f;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float p = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += p;
+      }
+      v += carry;
+      float m = fmaxf(v, hi);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float p = __shfl_up_sync(0xffffffffu, m, d);
+        if (lane >= d) m = fmaxf(m, p);
+      }
+      if (j < kc) cdf[j + 1] = m;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+      hi = __shfl_sync(0xffffffffu, m, 31);
+    }
+    __syncwarp();
+    if (a.cdf) {
+      float* out = a.cdf + (cbase + r);  // kc+1 entries per ray: dense r*(Kc+1), packed offsets[r]+r
+      for (int j = lane; j <= kc; j += 32) out[j] = cdf[j];
+    }
+
+    // (c) inverse-CDF search + in-bin jitter                              renderers.py:41-46
+    const int total = kc + n + nd;
+    const int P = next_pow2(total);
+    const bool do_sort = (a.z_sorted != nullptr);
+    for (int i = lane; i < n; i += 32) {
+      const float uu = a.u[fbase + i];
+      // number of entries <= u among cdf[0..kc]  (searchsorted right=True)
+      int lo = 0, hi_i = kc + 1;
+      while (lo < hi_i) {
+        const int mid = (lo + hi_i) >> 1;
+        if (cdf[mid] <= uu) lo = mid + 1; else hi_i = mid;
+      }
+      int bin = lo - 1;
+      if (bin < 0) bin = 0;
+      const float t = __fdiv_rn(__fadd_rn((float)bin, a.u2[fbase + i]), (float)kc);
+      const float zf = __fadd_rn(near, __fmul_rn(span, t));
+      if (a.idx) a.idx[fbase + i] = bin;
+      if (a.z_fine) a.z_fine[fbase + i] = zf;
+      if (do_sort) sortbuf[kc + i] = zf;
+    }
+    if (do_sort) {
+      for (int j = lane; j < kc; j += 32) sortbuf[j] = a.z_coarse[cbase + j];
+      // sample_depth + clamp: normals*std (depth NOT added), clamped to [near, far]   :62-66, :255
+      for (int i = lane; i < nd; i += 32) {
+        const float v = __fmul_rn(a.normals[r * (int64_t)nd + i], a.depth_std);
+        sortbuf[kc + n + i] = fminf(fmaxf(v, near), far);
+      }
+      for (int i = total + lane; i < P; i += 32) sortbuf[i] = CUDART_INF_F;
+      warp_bitonic_sort(sortbuf, nullptr, P, lane);
+      float* out = a.z_sorted + (cbase + fbase + r * (int64_t)nd);
+      for (int i = lane; i < total; i += 32) out[i] = sortbuf[i];
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+sort_rays_kernel(const float* __restrict__ z_in, int64_t R, int K, int P, float* __restrict__ z_out,
+                 int32_t* __restrict__ perm) {
+  extern __shared__ __align__(16) float fsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* key = fsmem + warp * 2 * P;
+  int* idx = reinterpret_cast<int*>(key + P);
+  const int64_t warps = (int64_t)gridDim.x * kSamplerWarps;
+  for (int64_t r = blockIdx.x * (int64_t)kSamplerWarps + warp; r < R; r += warps) {
+    for (int i = lane; i < P; i += 32) {
+      key[i] = (i < K) ? z_in[r * K + i] : CUDART_INF_F;
+      idx[i] = i;
+    }
+    warp_bitonic_sort(key, idx, P, lane);
+    for (int i = lane; i < K; i += 32) {
+      z_out[r * K + i] = key[i];
+      if (perm) perm[r * K + i] = idx[i];
+    }
+    __syncwarp();
+  }
+}
+
+// ---- launchers ------------------------------------------------------------------------
+static int grid_for(int64_t work_items, int per_block, int max_blocks) {
+  int64_t b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  return (int)(b < max_blocks ? b : max_blocks);
+}
+
+int launch_coarse_fwd(const float* near, const float* far, int bound_stride, const float* u,
+                      const int64_t* offsets, int64_t R, int K, int64_t S, float* z, cudaStream_t stream) {
+  if (R == 0) return AVR_OK;
+  if (offsets) {
+    coarse_fwd_packed_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 16), kSamplerWarps * 32, 0, stream>>>(
+        near, far, bound_stride, u, offsets, R, z);
+  } else {
+    const int64_t total = R * (int64_t)K;
+    if (total == 0) return AVR_OK;
+    coarse_fwd_dense_kernel<<<grid_for(total, 256, kNumSMs * 8), 256, 0, stream>>>(near, far, bound_stride, u,
+                                                                                 total, K, z);
+  }
+  (void)S;
+  return check_launch();
+}
+
+int launch_coarse_bwd(const float* g_z, const float* u, int64_t R, int K, float* d_near, float* d_far,
+                      cudaStream_t stream) {
+  if (R == 0) return AVR_OK;
+  coarse_bwd_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 16), kSamplerWarps * 32, 0, stream>>>(g_z, u, R, K,
+                                                                                                d_near, d_far);
+  return check_launch();
+}
+
+int launch_importance(const float* weights, const float* z_coarse, const float* u, const float* u2,
+                      const float* normals, const float* near, const float* far, int bound_stride,
+                      const int64_t* offsets, const int64_t* fine_offsets, int64_t R, int Kc, int n_imp,
+                      int n_depth, float depth_std, float* z_fine, float* z_sorted, float* cdf,
+                      int32_t* idx, cudaStream_t stream) {
+  if (R == 0) return AVR_OK;
+  // dense: Kc/n_imp are exact; packed: they are the caller's per-ray maxima
+  const int total_cap = Kc + n_imp + n_depth;
+  if (total_cap > AVR_MAX_SORT) return AVR_ERR_UNSUPPORTED;
+  ImportanceArgs a;
+  a.weights = weights;
+  a.z_coarse = z_coarse;
+  a.u = u;
+  a.u2 = u2;
+  a.normals = normals;
+  a.near = near;
+  a.far = far;
+  a.bound_stride = bound_stride;
+  a.offsets = offsets;
+  a.fine_offsets = fine_offsets;
+  a.R = R;
+  a.Kc = Kc;
+  a.n_imp = n_imp;
+  a.n_depth = n_depth;
+  a.depth_std = depth_std;
+  a.z_fine = z_fine;
+  a.z_sorted = z_sorted;
+  a.cdf = cdf;
+  a.idx = idx;
+  a.cdf_cap = ((Kc + 1) + 3) & ~3;
+  a.sort_cap = z_sorted ? next_pow2(total_cap) : 0;
+  const int smem = kSamplerWarps * (a.cdf_cap + a.sort_cap) * (int)sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(importance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e);
+      return AVR_ERR_LAUNCH;
+    }
+  }
+  importance_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 8), kSamplerWarps * 32, smem, stream>>>(a);
+  return check_launch();
+}
+
+int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, cudaStream_t stream) {
+  if (R == 0 || K == 0) return AVR_OK;
+  if (K > AVR_MAX_SORT) return AVR_ERR_UNSUPPORTED;
+  const int P = next_pow2(K);
+  const int smem = kSamplerWarps * 2 * P * (int)sizeof(float);
+  sort_rays_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 8), kSamplerWarps * 32, smem, stream>>>(z_in, R, K, P,
+                                                                                                z_out, perm);
+  return check_launch();
+}
+
+}  // namespace avr

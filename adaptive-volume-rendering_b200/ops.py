@@ -1,0 +1,317 @@
+"""torch-facing operators over the C ABI: output allocation, stream/device plumbing and
+``torch.autograd.Function`` wrappers.  No arithmetic happens here.
+
+Shapes follow the reference (renderers.py): leading dims are ``(SB, R)``; the kernels
+see them flattened to one ray axis.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous (no copy when it already is — the radiance field's output is)."""
+    if t.dtype != torch.float32:
+        raise _lib.AvrError(f"avr_b200 kernels are fp32 (as the reference); got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _bounds(near: torch.Tensor, far: torch.Tensor, n_rays: int):
+    """(near, far, bound_stride).  The reference hands VolumeRenderer's scalar bounds
+    over as stride-0 expands of a 1-element tensor (renderers.py:169); those stay one
+    element (bound_stride 0), everything else becomes one value per ray."""
+    def scalar(t):
+        return t.numel() == 1 or all(s == 0 for s in t.stride())
+
+    def first(t):
+        return _f32c(t.as_strided((1,), (1,)))
+
+    if scalar(near) and scalar(far):
+        return first(near), first(far), 0
+    near = _f32c(first(near).expand(n_rays) if scalar(near) else near.reshape(-1))
+    far = _f32c(first(far).expand(n_rays) if scalar(far) else far.reshape(-1))
+    if near.numel() != n_rays or far.numel() != n_rays:
+        raise _lib.AvrError(f"near/far must hold 1 or {n_rays} values")
+    return near, far, 1
+
+
+# --------------------------------------------------------------------------- coarse
+def coarse_sample_raw(near, far, bound_stride: int, u: torch.Tensor) -> torch.Tensor:
+    require_cuda(near, far, u)
+    u = _f32c(u)
+    k = u.shape[-1]
+    r = u.numel() // k
+    z = torch.empty_like(u)
+    with torch.cuda.device(u.device):
+        check(_lib.load().avr_coarse_sample_fwd(ptr(near), ptr(far), bound_stride, ptr(u), r, k, ptr(z), _stream(u)),
+              "avr_coarse_sample_fwd")
+    return z
+
+
+class CoarseSample(torch.autograd.Function):
+    """z = sample_coarse(near, far) for per-ray bounds that carry grad (AdaptiveVolumeRenderer,
+    renderers.py:490-494).  u is the explicit uniform draw."""
+
+    @staticmethod
+    def forward(ctx, near, far, u):
+        near_c, far_c, stride = _bounds(near, far, u.numel() // u.shape[-1])
+        ctx.save_for_backward(u)
+        ctx.bshape = (near.shape, far.shape)
+        ctx.stride = stride
+        return coarse_sample_raw(near_c, far_c, stride, u)
+
+    @staticmethod
+    def backward(ctx, g_z):
+        (u,) = ctx.saved_tensors
+        g_z = _f32c(g_z)
+        u = _f32c(u)
+        k = u.shape[-1]
+        r = u.numel() // k
+        d_near = torch.empty(r, dtype=torch.float32, device=u.device)
+        d_far = torch.empty_like(d_near)
+        with torch.cuda.device(u.device):
+            check(_lib.load().avr_coarse_sample_bwd(ptr(g_z), ptr(u), r, k, ptr(d_near), ptr(d_far), _stream(u)),
+                  "avr_coarse_sample_bwd")
+        ns, fs = ctx.bshape
+        # an expanded (stride-0) input still receives a per-ray gradient of its own shape;
+        # autograd's expand backward does the reduction
+        d_near = d_near.reshape(ns) if d_near.numel() == ns.numel() else d_near.sum().reshape(ns)
+        d_far = d_far.reshape(fs) if d_far.numel() == fs.numel() else d_far.sum().reshape(fs)
+        return d_near, d_far, None
+
+
+# ------------------------------------------------------------------------ importance
+def importance_sample(
+    weights: torch.Tensor,              # (..., Kc) or (..., Kc, 1)
+    near: torch.Tensor, far: torch.Tensor,
+    u: torch.Tensor, u2: torch.Tensor,  # (..., n)
+    z_coarse: Optional[torch.Tensor] = None,
+    normals: Optional[torch.Tensor] = None, depth_std: float = 0.0,
+    want_fine: bool = True, want_sorted: bool = False, want_cdf: bool = False, want_idx: bool = False,
+):
+    """sample_fine (+ sample_depth/clamp + cat/sort when ``want_sorted``) in one kernel.
+    Returns a dict with the requested outputs.  Non-differentiable (the reference
+    detaches the weights, renderers.py:36)."""
+    if weights.dim() == u.dim() + 1:
+        weights = weights.squeeze(-1)
+    weights = _f32c(weights.detach())
+    u, u2 = _f32c(u), _f32c(u2)
+    require_cuda(weights, u, u2, near, far)
+    kc, n = weights.shape[-1], u.shape[-1]
+    r = weights.numel() // kc
+    lead = weights.shape[:-1]
+    near_c, far_c, stride = _bounds(near.detach(), far.detach(), r)
+    nd = 0
+    if want_sorted:
+        if z_coarse is None:
+            raise _lib.AvrError("want_sorted needs z_coarse")
+        z_coarse = _f32c(z_coarse.detach())
+        if normals is not None:
+            normals = _f32c(normals)
+            nd = normals.shape[-1]
+    dev = weights.device
+    out = {}
+    z_fine = torch.empty(*lead, n, dtype=torch.float32, device=dev) if want_fine else None
+    z_sorted = torch.empty(*lead, kc + n + nd, dtype=torch.float32, device=dev) if want_sorted else None
+    cdf = torch.empty(*lead, kc + 1, dtype=torch.float32, device=dev) if want_cdf else None
+    idx = torch.empty(*lead, n, dtype=torch.int32, device=dev) if want_idx else None
+    with torch.cuda.device(dev):
+        check(_lib.load().avr_importance_sample(
+            ptr(weights), ptr(z_coarse), ptr(u), ptr(u2), ptr(normals) if nd else None, ptr(near_c), ptr(far_c), stride,
+            r, kc, n, nd, float(depth_std), ptr(z_fine), ptr(z_sorted), ptr(cdf), ptr(idx), _stream(weights)),
+            "avr_importance_sample")
+    out.update(z_fine=z_fine, z_sorted=z_sorted, cdf=cdf, idx=idx)
+    return out
+
+
+class SortRays(torch.autograd.Function):
+    """Ascending per-ray sort that routes gradients (torch.sort at renderers.py:494)."""
+
+    @staticmethod
+    def forward(ctx, z):
+        require_cuda(z)
+        zc = _f32c(z)
+        k = zc.shape[-1]
+        r = zc.numel() // k
+        out = torch.empty_like(zc)
+        perm = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
+        with torch.cuda.device(zc.device):
+            check(_lib.load().avr_sort_rays(ptr(zc), r, k, ptr(out), ptr(perm), _stream(zc)), "avr_sort_rays")
+        ctx.save_for_backward(perm)
+        ctx.mark_non_differentiable(perm)
+        return out, perm
+
+    @staticmethod
+    def backward(ctx, g_out, _g_perm):
+        (perm,) = ctx.saved_tensors
+        g_in = torch.empty_like(g_out)
+        g_in.scatter_(-1, perm.long(), g_out)
+        return g_in
+
+
+# -------------------------------------------------------------------------- composite
+def composite_fwd_raw(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool, infinity: float, want_w: bool = True):
+    require_cuda(rgbs, z)
+    rgbs, z = _f32c(rgbs), _f32c(z)
+    k = z.shape[-1]
+    r = z.numel() // k
+    if rgbs.numel() != z.numel() * 4:
+        raise _lib.AvrError(f"rgbs {tuple(rgbs.shape)} does not match z {tuple(z.shape)}")
+    lead = z.shape[:-1]
+    dev = z.device
+    w = torch.empty(*lead, k, dtype=torch.float32, device=dev) if want_w else None
+    rgb = torch.empty(*lead, 3, dtype=torch.float32, device=dev)
+    depth = torch.empty(*lead, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().avr_composite_fwd(ptr(rgbs), ptr(z), r, k, int(bool(white_back)), float(infinity),
+                                            ptr(w), ptr(rgb), ptr(depth), _stream(z)), "avr_composite_fwd")
+    return rgb, depth, w
+
+
+def composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back: bool, infinity: float, want_dz: bool):
+    rgbs, z = _f32c(rgbs), _f32c(z)
+    k = z.shape[-1]
+    r = z.numel() // k
+    g_rgb = None if g_rgb is None else _f32c(g_rgb)
+    g_depth = None if g_depth is None else _f32c(g_depth)
+    g_w = None if g_w is None else _f32c(g_w)
+    d_rgbs = torch.empty_like(rgbs)
+    d_z = torch.empty_like(z) if want_dz else None
+    with torch.cuda.device(z.device):
+        check(_lib.load().avr_composite_bwd(ptr(rgbs), ptr(z), ptr(g_rgb), ptr(g_depth), ptr(g_w), r, k,
+                                            int(bool(white_back)), float(infinity), ptr(d_rgbs), ptr(d_z), _stream(z)),
+              "avr_composite_bwd")
+    return d_rgbs, d_z
+
+
+class Composite(torch.autograd.Function):
+    """(rgb, depth, w) = volume_integral(z, rgbs) — renderers.py:69-119.
+
+    Saves only its inputs; backward recomputes the transmittance.  ``w`` is returned
+    with shape (..., K) (callers add the trailing 1 the reference has)."""
+
+    @staticmethod
+    def forward(ctx, rgbs, z, white_back: bool, infinity: float, want_w: bool):
+        rgb, depth, w = composite_fwd_raw(rgbs, z, white_back, infinity, want_w)
+        ctx.save_for_backward(rgbs, z)
+        ctx.cfg = (bool(white_back), float(infinity))
+        if w is None:
+            w = rgb.new_empty(0)
+            ctx.mark_non_differentiable(w)
+        return rgb, depth, w
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_w):
+        rgbs, z = ctx.saved_tensors
+        white_back, infinity = ctx.cfg
+        if g_w is not None and g_w.numel() == 0:
+            g_w = None
+        want_dz = ctx.needs_input_grad[1]
+        d_rgbs, d_z = composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back, infinity, want_dz)
+        return (d_rgbs.view_as(rgbs) if ctx.needs_input_grad[0] else None), d_z, None, None, None
+
+
+def composite(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = True, infinity: float = 1.8,
+              want_w: bool = True) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Differentiable compositing of a (..., K, 4) = (r,g,b,sigma) buffer along z (..., K).
+    Returns rgb (...,3), depth (...), w (...,K) or None."""
+    rgb, depth, w = Composite.apply(rgbs, z, white_back, infinity, want_w)
+    return rgb, depth, (w if want_w else None)
+
+
+# ----------------------------------------------------------------- packed (ragged) rays
+def composite_packed_fwd_raw(rgbs, z, offsets, white_back, infinity, want_w=True):
+    require_cuda(rgbs, z, offsets)
+    rgbs, z = _f32c(rgbs), _f32c(z)
+    if offsets.dtype != torch.int64:
+        raise _lib.AvrError("offsets must be int64")
+    offsets = offsets.contiguous()
+    r = offsets.numel() - 1
+    s = z.numel()
+    dev = z.device
+    w = torch.empty(s, dtype=torch.float32, device=dev) if want_w else None
+    rgb = torch.empty(r, 3, dtype=torch.float32, device=dev)
+    depth = torch.empty(r, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().avr_composite_fwd_packed(ptr(rgbs), ptr(z), ptr(offsets), r, s, int(bool(white_back)),
+                                                   float(infinity), ptr(w), ptr(rgb), ptr(depth), _stream(z)),
+              "avr_composite_fwd_packed")
+    return rgb, depth, w
+
+
+class CompositePacked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgbs, z, offsets, white_back, infinity, want_w):
+        rgb, depth, w = composite_packed_fwd_raw(rgbs, z, offsets, white_back, infinity, want_w)
+        ctx.save_for_backward(rgbs, z, offsets)
+        ctx.cfg = (bool(white_back), float(infinity))
+        if w is None:
+            w = rgb.new_empty(0)
+            ctx.mark_non_differentiable(w)
+        return rgb, depth, w
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_w):
+        rgbs, z, offsets = ctx.saved_tensors
+        white_back, infinity = ctx.cfg
+        rgbs_c, z_c = _f32c(rgbs), _f32c(z)
+        if g_w is not None and g_w.numel() == 0:
+            g_w = None
+        g_rgb = None if g_rgb is None else _f32c(g_rgb)
+        g_depth = None if g_depth is None else _f32c(g_depth)
+        g_w = None if g_w is None else _f32c(g_w)
+        want_dz = ctx.needs_input_grad[1]
+        d_rgbs = torch.zeros_like(rgbs_c)
+        d_z = torch.zeros_like(z_c) if want_dz else None
+        r = offsets.numel() - 1
+        with torch.cuda.device(z.device):
+            check(_lib.load().avr_composite_bwd_packed(ptr(rgbs_c), ptr(z_c), ptr(offsets), ptr(g_rgb), ptr(g_depth),
+                                                       ptr(g_w), r, z_c.numel(), int(white_back), float(infinity),
+                                                       ptr(d_rgbs), ptr(d_z), _stream(z)), "avr_composite_bwd_packed")
+        return (d_rgbs.view_as(rgbs) if ctx.needs_input_grad[0] else None), d_z, None, None, None, None
+
+
+def composite_packed(rgbs, z, offsets, white_back=True, infinity=1.8, want_w=True):
+    """Compositing over packed rays: rgbs (S,4), z (S,), offsets (R+1,) int64."""
+    rgb, depth, w = CompositePacked.apply(rgbs, z, offsets, white_back, infinity, want_w)
+    return rgb, depth, (w if want_w else None)
+
+
+def coarse_sample_packed(near, far, u, offsets):
+    """Stratified depths for packed rays; ray r is stratified over its own count."""
+    require_cuda(u, offsets)
+    u = _f32c(u)
+    r = offsets.numel() - 1
+    near_c, far_c, stride = _bounds(near, far, r)
+    z = torch.empty_like(u)
+    with torch.cuda.device(u.device):
+        check(_lib.load().avr_coarse_sample_fwd_packed(ptr(near_c), ptr(far_c), stride, ptr(u), ptr(offsets.contiguous()),
+                                                       r, u.numel(), ptr(z), _stream(u)), "avr_coarse_sample_fwd_packed")
+    return z
+
+
+def importance_sample_packed(weights, z_coarse, near, far, u, u2, offsets, fine_offsets, max_coarse, max_fine,
+                             want_sorted=True):
+    """Packed sample_fine + merge: returns (z_fine (Sf,), z_sorted (S+Sf,) or None)."""
+    require_cuda(weights, u, u2, offsets, fine_offsets)
+    weights, u, u2 = _f32c(weights.detach()), _f32c(u), _f32c(u2)
+    z_coarse = _f32c(z_coarse.detach())
+    r = offsets.numel() - 1
+    near_c, far_c, stride = _bounds(near.detach(), far.detach(), r)
+    z_fine = torch.empty_like(u)
+    z_sorted = torch.empty(weights.numel() + u.numel(), dtype=torch.float32, device=u.device) if want_sorted else None
+    with torch.cuda.device(u.device):
+        check(_lib.load().avr_importance_sample_packed(
+            ptr(weights), ptr(z_coarse), ptr(u), ptr(u2), ptr(near_c), ptr(far_c), stride,
+            ptr(offsets.contiguous()), ptr(fine_offsets.contiguous()), r, int(max_coarse), int(max_fine),
+            ptr(z_fine), ptr(z_sorted), _stream(u)), "avr_importance_sample_packed")
+    return z_fine, z_sorted

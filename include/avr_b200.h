@@ -1,0 +1,179 @@
+/*
+ * avr_b200 — C ABI of the B200 (sm_100a) ray-sampling + volume-compositing path.
+ *
+ * This is the drop-in boundary.  The reference (yankeesong/adaptive-volume-rendering)
+ * has no native layer at all: its hot path is ~30 stock ATen calls in
+ * renderers.py:4-119.  Each entry point below replaces the op sequence of one
+ * reference function (cited per function); the Python host side that mirrors the
+ * reference's own API (`sample_coarse`, `sample_fine`, `sample_depth`,
+ * `volume_integral`, `VolumeRenderer`, `AdaptiveVolumeRenderer`) binds these with
+ * ctypes and nothing else (see INTEGRATION.md for the stub a maintainer adds).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the function name ends in `_host`;
+ *     all floating-point data is fp32, contiguous, row-major;
+ *   - buffers are owned by the caller and must stay alive until the work queued on
+ *     `stream` has completed; the library never allocates device memory in the
+ *     device-pointer entry points, never synchronises, holds no mutable global
+ *     state (safe to call from autograd's backward thread);
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - return value: AVR_OK (0) or a negative AVR_ERR_* code; nothing throws;
+ *   - "rgbs" is the radiance field's output exactly as the reference slices it:
+ *     4 floats per sample in the order (r, g, b, sigma)  [models.py:856-862,
+ *     renderers.py:177-178];
+ *   - dense layout:  R rays x K samples;  packed layout: `offsets[R+1]` (int64,
+ *     offsets[0] == 0, non-decreasing) gives each ray's slice of an S-sample stream;
+ *   - `bound_stride`: 1 if `near`/`far` hold one value per ray, 0 if they hold a
+ *     single value shared by all rays (the reference passes stride-0 expands of a
+ *     1-element tensor, renderers.py:169).
+ */
+#ifndef AVR_B200_H_
+#define AVR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVR_B200_ABI_VERSION 1
+
+typedef void* avr_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define AVR_API __attribute__((visibility("default")))
+#else
+#define AVR_API
+#endif
+
+enum avr_status {
+  AVR_OK = 0,
+  AVR_ERR_BAD_ARG = -1,    /* null / misaligned pointer, negative size, K out of range */
+  AVR_ERR_LAUNCH = -2,     /* cudaPeekAtLastError() after the launch was not cudaSuccess */
+  AVR_ERR_NO_DEVICE = -3,  /* current device is not compute capability 10.x */
+  AVR_ERR_UNSUPPORTED = -4,/* shape outside what the kernels implement (e.g. K > AVR_MAX_SORT) */
+  AVR_ERR_RUNTIME = -5     /* a CUDA runtime call (malloc/memcpy/event) failed; host entry points only */
+};
+
+/* Largest per-ray sample count the merge-sort kernel takes (coarse + fine + depth). */
+#define AVR_MAX_SORT 1024
+
+AVR_API int avr_abi_version(void);
+AVR_API const char* avr_status_string(int status);
+/* Last CUDA error string recorded by the calling thread's most recent failing call. */
+AVR_API const char* avr_last_cuda_error(void);
+/* AVR_OK if the current device can run the kernels (sm_100 family). */
+AVR_API int avr_device_check(void);
+
+/* Which composite kernel family a call will use (for tests/bench): 0 = generic
+ * thread-per-ray, 1 = TMA-staged blocked scan ("span" kernels). */
+AVR_API int avr_composite_plan(int64_t R, int K, const void* rgbs, const void* z);
+/* Force the generic kernels (1) or restore automatic choice (0); process-wide, for tests. */
+AVR_API void avr_set_force_generic(int on);
+
+/* ---------------------------------------------------------------- samplers -- */
+
+/* Replaces sample_coarse, renderers.py:12-14:
+ *   z[r,j] = near_r + (far_r - near_r) * (j / K)  +  (u[r,j] * (far_r - near_r)) / K
+ * evaluated with the reference's operation order (separate mul / add / div, no FMA)
+ * so the result is bit-identical to torch-CPU.  u: [R,K] uniforms in [0,1). */
+AVR_API int avr_coarse_sample_fwd(const float* near, const float* far, int bound_stride,
+                          const float* u, int64_t R, int K, float* z, avr_stream_t stream);
+
+/* Gradient of the above w.r.t. per-ray near / far (AdaptiveVolumeRenderer only,
+ * renderers.py:490-494):  d_near[r] = sum_j g_z[r,j] * (1 - (j + u[r,j]) / K),
+ * d_far[r] = sum_j g_z[r,j] * ((j + u[r,j]) / K). */
+AVR_API int avr_coarse_sample_bwd(const float* g_z, const float* u, int64_t R, int K,
+                          float* d_near, float* d_far, avr_stream_t stream);
+
+/* Replaces sample_fine (renderers.py:27-54), sample_depth + clamp (:56-66, :255) and
+ * cat + sort (:257-258) in one pass per ray.
+ *   weights [R,Kc]   coarse compositing weights (detached by construction)
+ *   z_coarse [R,Kc]  coarse depths to merge in (may be NULL when z_sorted is NULL)
+ *   u, u2 [R,n_imp]  inverse-CDF draws and in-bin jitter
+ *   normals [R,n_depth] N(0,1) draws (may be NULL iff n_depth == 0); the reference's
+ *                    sample_depth returns normals * depth_std WITHOUT the depth added;
+ *                    reproduced, then clamped to [near_r, far_r]
+ * outputs (each may be NULL):
+ *   z_fine  [R,n_imp]            unsorted importance samples (what sample_fine returns)
+ *   z_sorted[R,Kc+n_imp+n_depth] ascending merge of coarse, fine and depth samples
+ *   cdf     [R,Kc+1]             the CDF the search ran on (cdf[r,0] == 0)
+ *   idx     [R,n_imp] int32      bin index in [0, Kc] — bit-exact with
+ *                                clamp_min(searchsorted(cdf, u, right=True) - 1, 0) */
+AVR_API int avr_importance_sample(const float* weights, const float* z_coarse,
+                          const float* u, const float* u2, const float* normals,
+                          const float* near, const float* far, int bound_stride,
+                          int64_t R, int Kc, int n_imp, int n_depth, float depth_std,
+                          float* z_fine, float* z_sorted, float* cdf, int32_t* idx,
+                          avr_stream_t stream);
+
+/* Per-ray ascending sort (torch.sort, renderers.py:494).  perm (int32 [R,K], may be
+ * NULL) receives the source index of each output element (stable), for routing
+ * gradients back (d_in[r, perm[r,k]] = d_out[r,k]). */
+AVR_API int avr_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm,
+                  avr_stream_t stream);
+
+/* ------------------------------------------------------------- compositing -- */
+
+/* Replaces volume_integral, renderers.py:69-119 (fused: deltas, alpha, exclusive
+ * cumprod of (1-alpha)+1e-10, weights, weighted sums, white background).
+ *   rgbs [R,K,4], z [R,K]  ->  w [R,K] (may be NULL), rgb [R,3], depth [R]
+ * `infinity` is the z paired with the last sample in the depth sum (reference
+ * default 1.8, never overridden by its callers). */
+AVR_API int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K,
+                      int white_back, float infinity,
+                      float* w, float* rgb, float* depth, avr_stream_t stream);
+
+/* Gradient of the above; transmittance is recomputed, nothing is saved by forward.
+ *   g_rgb [R,3] (may be NULL = zeros), g_depth [R] (may be NULL), g_w [R,K] (may be NULL)
+ *   d_rgbs [R,K,4] (required), d_z [R,K] (may be NULL: VolumeRenderer's z carries no grad) */
+AVR_API int avr_composite_bwd(const float* rgbs, const float* z,
+                      const float* g_rgb, const float* g_depth, const float* g_w,
+                      int64_t R, int K, int white_back, float infinity,
+                      float* d_rgbs, float* d_z, avr_stream_t stream);
+
+/* Packed (ragged) variants: ray r owns samples [offsets[r], offsets[r+1]) of an
+ * S-sample stream.  rgbs [S,4], z [S], w [S], g_w [S], d_rgbs [S,4], d_z [S].
+ * A ray with zero samples composites to background (rgb = white_back, depth = 0). */
+AVR_API int avr_composite_fwd_packed(const float* rgbs, const float* z, const int64_t* offsets,
+                             int64_t R, int64_t S, int white_back, float infinity,
+                             float* w, float* rgb, float* depth, avr_stream_t stream);
+AVR_API int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* offsets,
+                             const float* g_rgb, const float* g_depth, const float* g_w,
+                             int64_t R, int64_t S, int white_back, float infinity,
+                             float* d_rgbs, float* d_z, avr_stream_t stream);
+
+/* Packed samplers.  counts are implied by offsets; `u` is laid out like z. */
+AVR_API int avr_coarse_sample_fwd_packed(const float* near, const float* far, int bound_stride,
+                                 const float* u, const int64_t* offsets, int64_t R, int64_t S,
+                                 float* z, avr_stream_t stream);
+/* Importance sampling on packed rays: ray r draws n_r = fine_offsets[r+1]-fine_offsets[r]
+ * samples from its Kc_r = offsets[r+1]-offsets[r] coarse weights (Kc_r >= 1 wherever
+ * n_r > 0), and the merge has Kc_r + n_r entries at offsets[r] + fine_offsets[r].
+ * max_coarse / max_fine: upper bounds on Kc_r / n_r over all rays (they size the
+ * per-warp shared-memory tables; max_coarse + max_fine <= AVR_MAX_SORT). */
+AVR_API int avr_importance_sample_packed(const float* weights, const float* z_coarse,
+                                 const float* u, const float* u2,
+                                 const float* near, const float* far, int bound_stride,
+                                 const int64_t* offsets, const int64_t* fine_offsets,
+                                 int64_t R, int max_coarse, int max_fine,
+                                 float* z_fine, float* z_sorted, avr_stream_t stream);
+
+/* ------------------------------------------------ host-buffer (end to end) -- */
+
+/* One forward+backward compositing pass over HOST buffers (pinned for full speed):
+ * chunks the rays, overlaps H2D copies, the two kernels and D2H copies on internal
+ * streams, and returns when every output is on the host.  This is the call `bench.py`
+ * times for the end-to-end figure.  Outputs rgb [R,3], depth [R], d_rgbs [R,K,4];
+ * w is not returned (the fine pass discards it, renderers.py:270).
+ * `chunk_rays` <= 0 picks a default. */
+AVR_API int avr_composite_fwd_bwd_host(const float* rgbs, const float* z,
+                               const float* g_rgb, const float* g_depth,
+                               int64_t R, int K, int white_back, float infinity,
+                               float* rgb, float* depth, float* d_rgbs,
+                               int64_t chunk_rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVR_B200_H_ */

@@ -1,0 +1,289 @@
+"""CPU oracle for the ray-sampling + volume-compositing hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is product code: only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it, and only as the checker (or as the
+reported CPU baseline), never as the thing shipped.  The product path is the
+CUDA library behind ``include/avr_b200.h`` and fails loudly without it.
+
+What this is: a restatement, in plain torch-CPU ops, of the algorithm in the
+reference's ``renderers.py`` (the arithmetic itself lives in PyTorch — pinned
+at 1.13.0 by the reference's ``environment.yml:222-223``; this image has
+2.11.0).  Every function names the reference lines it follows.  Differences
+from the reference are deliberate and limited to the calling convention:
+
+* random draws are *arguments* (``u``, ``u2``, ``normals``) instead of being
+  drawn inside, so the CUDA kernels and the oracle consume identical numbers;
+* the CDF and the bin indices are returned so index parity can be checked
+  bit-exactly;
+* a ``dtype`` switch lets the same code run in fp64 as an accuracy yardstick
+  (constants are still rounded to fp32 first, as the reference creates them
+  with ``torch.Tensor([...])``: 1.8 -> 1.7999999523, 1e10 -> 1e10f).
+
+Pinning: the reference ships no tests or golden vectors,
+so parity is pinned by (a) ``tests/test_oracle_vs_reference.py``, which imports
+the unmodified reference from ``/root/reference`` in the build container and
+checks this file against it bit-for-bit on CPU, and (b) the fixtures under
+``tests/golden/`` that ``oracle/make_golden.py`` produced by *running the
+reference itself*; both the fixtures and the generator are committed.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Tuple
+
+import torch
+
+# fp32-rounded constants, created the way the reference creates them
+# (renderers.py:80, :91, :105 use torch.Tensor([...]) / torch.tensor([...]))
+_LAST_DELTA = 1e10
+_T_EPS = 1e-10
+_PDF_EPS = 1e-5
+
+
+def _f32const(v: float, like: torch.Tensor) -> torch.Tensor:
+    return torch.tensor([v], dtype=torch.float32).to(like.dtype)
+
+
+# --------------------------------------------------------------------------
+# samplers
+# --------------------------------------------------------------------------
+def coarse_z(near: torch.Tensor, far: torch.Tensor, n: int, u: torch.Tensor) -> torch.Tensor:
+    """Stratified depths, one jittered sample per bin.  renderers.py:12-14.
+
+    near, far: (SB, R);  u: (SB, R, n) uniforms in [0,1).  Returns (SB, R, n).
+    """
+    bins = torch.arange(n, dtype=torch.float32).to(u.dtype) / n          # :12
+    span = far - near
+    z = near.unsqueeze(-1) + torch.einsum("bs,j->bsj", span, bins)        # :13
+    z = z + torch.einsum("bsi,bs->bsi", u, span) / n                      # :14
+    return z
+
+
+def cdf_from_weights(weights: torch.Tensor) -> torch.Tensor:
+    """(SB,R,Kc) weights -> (SB,R,Kc+1) cdf with a leading 0.  renderers.py:36-39."""
+    w = weights.detach() + _PDF_EPS                                       # :36
+    pdf = w / torch.sum(w, -1, keepdim=True)                              # :37
+    cdf = torch.cumsum(pdf, -1)                                           # :38
+    return torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)           # :39
+
+
+def cdf_search(cdf: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """Bin index (int64) in [0, Kc] inclusive.  renderers.py:42-43.
+
+    ``searchsorted(right=True) - 1`` = (#entries <= u) - 1; only the lower end
+    is clamped, so u >= cdf[-1] (cdf[-1] can round below 1) yields Kc.
+    """
+    idx = torch.searchsorted(cdf, u.contiguous(), right=True) - 1
+    return torch.clamp_min(idx, 0)
+
+
+def fine_z(
+    near: torch.Tensor,
+    far: torch.Tensor,
+    weights: torch.Tensor,          # (SB, R, Kc, 1) or (SB, R, Kc)
+    u: torch.Tensor,                # (SB, R, n)  inverse-CDF draws
+    u2: torch.Tensor,               # (SB, R, n)  in-bin jitter
+    return_aux: bool = False,
+):
+    """Importance samples from the coarse weights.  renderers.py:27-54.
+
+    Unsorted, non-differentiable (weights are detached at :36).
+    """
+    if weights.dim() == 4:
+        weights = weights.squeeze(-1)
+    kc = weights.shape[-1]
+    cdf = cdf_from_weights(weights)
+    idx = cdf_search(cdf, u)
+    t = (idx.to(u.dtype) + u2) / kc                                       # :45
+    z = near.unsqueeze(-1) + torch.einsum("bs,bsj->bsj", far - near, t)   # :46
+    if return_aux:
+        return z, cdf, idx
+    return z
+
+
+def depth_z(normals: torch.Tensor, depth_std: float, near, far) -> torch.Tensor:
+    """"Depth" samples as the reference actually computes them.
+
+    renderers.py:62-66 returns ``randn * depth_std`` WITHOUT adding the depth,
+    and the caller clamps to [near, far] (:255) — so every entry equals
+    ``near`` for the shipped configs.  Reproduced, not fixed.
+    """
+    return torch.clamp(normals * depth_std, near, far)
+
+
+def merge_sorted(*parts: torch.Tensor) -> torch.Tensor:
+    """Ascending per-ray sort of the concatenated z sets.  renderers.py:257-258."""
+    return torch.sort(torch.cat(parts, dim=-1), dim=-1).values
+
+
+# --------------------------------------------------------------------------
+# compositing
+# --------------------------------------------------------------------------
+def composite(
+    z: torch.Tensor,            # (SB, R, K)
+    sigma: torch.Tensor,        # (SB, R, K, 1)
+    rad: torch.Tensor,          # (SB, R, K, 3)
+    white_back: bool = True,
+    infinity: float = 1.8,
+) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Alpha compositing.  renderers.py:69-119.
+
+    Returns rgb (SB,R,3), depth (SB,R,1), weights (SB,R,K,1).
+    """
+    last = torch.broadcast_to(_f32const(_LAST_DELTA, z), z[..., :1].shape)
+    delta = torch.cat([z[..., 1:] - z[..., :-1], last], -1)               # :78-81
+    alpha = 1.0 - torch.exp(-torch.einsum("brzs,brz->brzs", sigma, delta))  # :86
+    one = torch.broadcast_to(_f32const(1.0, alpha), alpha[..., :1, :].shape)
+    trans = torch.cat([one, torch.cumprod(1.0 - alpha + _T_EPS, -2)[..., :-1, :]], -2)  # :90-93
+    w = alpha * trans                                                     # :96
+    rgb = torch.einsum("brzs,brzs->brs", w, rad)                          # :99
+    inf = torch.broadcast_to(_f32const(infinity, z), z[..., :1].shape)
+    z_next = torch.cat([z[..., 1:], inf], -1)                             # :104-106
+    depth = torch.einsum("brzs,brz->brs", w, z_next)                      # :108
+    if white_back:
+        rgb = rgb + (1.0 - w.sum(dim=-2))                                 # :110-112
+    return rgb, depth, w
+
+
+def composite_rgbs(z: torch.Tensor, rgbs: torch.Tensor, white_back=True, infinity=1.8):
+    """Same, taking the radiance field's (SB, R, K, 4) = (r,g,b,sigma) output the
+    way the renderers slice it (renderers.py:177-178, models.py:856-862)."""
+    return composite(z, rgbs[..., 3:4], rgbs[..., :3], white_back, infinity)
+
+
+def composite_grads(
+    z: torch.Tensor,
+    rgbs: torch.Tensor,
+    g_rgb: Optional[torch.Tensor],
+    g_depth: Optional[torch.Tensor],
+    g_w: Optional[torch.Tensor] = None,
+    white_back: bool = True,
+    infinity: float = 1.8,
+    want_dz: bool = False,
+):
+    """Gradients of ``composite_rgbs`` as torch autograd produces them for the
+    reference (there is no hand-written backward in the reference)."""
+    z = z.detach().clone().requires_grad_(want_dz)
+    rgbs = rgbs.detach().clone().requires_grad_(True)
+    rgb, depth, w = composite_rgbs(z, rgbs, white_back, infinity)
+    outs, grads = [], []
+    for o, g in ((rgb, g_rgb), (depth, g_depth), (w, g_w)):
+        if g is not None:
+            outs.append(o)
+            grads.append(g.reshape(o.shape))
+    torch.autograd.backward(outs, grads)
+    return rgbs.grad, (z.grad if want_dz else None)
+
+
+# --------------------------------------------------------------------------
+# packed (ragged) layout: per-ray sample counts, offsets[R+1]
+# --------------------------------------------------------------------------
+def composite_packed(z, rgbs, offsets, white_back=True, infinity=1.8):
+    """Ragged restatement: bucket rays by sample count and run ``composite`` on
+    each bucket.  Per-ray results of the reference do not depend on batch
+    composition on CPU, so this is the reference's
+    answer for every ray.  z: (S,), rgbs: (S,4), offsets: (R+1,) int64."""
+    offsets = offsets.to(torch.int64)
+    counts = offsets[1:] - offsets[:-1]
+    r_total = counts.numel()
+    rgb = torch.zeros(r_total, 3, dtype=z.dtype)
+    depth = torch.zeros(r_total, dtype=z.dtype)
+    w = torch.zeros_like(z)
+    for k in torch.unique(counts).tolist():
+        rays = torch.nonzero(counts == k).squeeze(-1)
+        if k == 0:
+            # no samples: nothing absorbed; the reference cannot express this
+            # case, the packed layout defines it as pure background.
+            rgb[rays] = 1.0 if white_back else 0.0
+            continue
+        idx = offsets[rays].unsqueeze(-1) + torch.arange(k)
+        o_rgb, o_depth, o_w = composite_rgbs(z[idx].unsqueeze(0), rgbs[idx].unsqueeze(0), white_back, infinity)
+        rgb[rays] = o_rgb[0]
+        depth[rays] = o_depth[0, :, 0]
+        w[idx] = o_w[0, :, :, 0]
+    return rgb, depth, w
+
+
+def bucketed(offsets: torch.Tensor):
+    """Yield (k, ray_ids, sample_index_matrix) for each distinct count."""
+    offsets = offsets.to(torch.int64)
+    counts = offsets[1:] - offsets[:-1]
+    for k in torch.unique(counts).tolist():
+        rays = torch.nonzero(counts == k).squeeze(-1)
+        idx = offsets[rays].unsqueeze(-1) + torch.arange(k)
+        yield k, rays, idx
+
+
+# --------------------------------------------------------------------------
+# geometry either side of the path (adjacent; restated only so the renderer
+# oracle below is self-contained).  utils.py:246-336, 358-361.
+# --------------------------------------------------------------------------
+def world_rays(x_pix, intrinsics, cam2world):
+    """utils.py:315-336 (get_world_rays) incl. the x-flip of unproject (:263-265)."""
+    origin = cam2world[..., :3, -1]
+    pix_h = torch.cat((x_pix, torch.ones_like(x_pix[..., :1])), dim=-1)
+    cam = torch.einsum("...ij,...kj->...ki", intrinsics.inverse(), pix_h)
+    cam = torch.cat((-cam[..., :1], cam[..., 1:]), dim=-1)
+    cam = cam * (-torch.ones_like(x_pix[..., :1]))
+    cam = cam / torch.norm(cam, dim=-1).unsqueeze(-1)
+    dir_h = torch.cat((cam, torch.zeros_like(cam[..., :1])), dim=-1)
+    world = torch.einsum("...ij,...j->...i", cam2world, dir_h)
+    return origin, world[..., :3]
+
+
+def camera_depth(world_pts, cam2world):
+    """utils.py:358-361 (depth_from_world)."""
+    pts_h = torch.cat((world_pts, torch.ones_like(world_pts[..., :1])), dim=-1)
+    cam = torch.einsum("...ij,...j->...i", torch.inverse(cam2world), pts_h)
+    return -cam[..., 2]
+
+
+# --------------------------------------------------------------------------
+# renderer orchestration with explicit draws.  renderers.py:133-277.
+# --------------------------------------------------------------------------
+def render_volume(
+    cam2world, intrinsics, x_pix,
+    radiance_field: Callable,
+    near: float, far: float, n_coarse: int, n_fine: int, n_fine_depth: int,
+    depth_std: float, white_back: bool,
+    draws: Sequence[torch.Tensor],
+):
+    """``VolumeRenderer.forward`` with the four RNG draws passed in, in the
+    order the reference consumes them:
+    u_coarse (SB,R,Kc), u_cdf (SB,R,Ki), u_bin (SB,R,Ki), normals (SB,R,Kd)."""
+    u_c, u_cdf, u_bin, normals = draws
+    sb, r, _ = x_pix.shape
+    ros, rds = world_rays(x_pix, intrinsics, cam2world)                    # :166
+    near_t = torch.tensor([near]).expand_as(ros[..., 0])
+    far_t = torch.tensor([far]).expand_as(ros[..., 0])
+    z_c = coarse_z(near_t, far_t, n_coarse, u_c)                           # :169
+    pts = ros.unsqueeze(-2) + torch.einsum("bsi,bsj->bsji", rds, z_c)      # :171
+    out = radiance_field(pts.reshape(sb, -1, 3),
+                         viewdirs=rds.unsqueeze(-2).expand(sb, r, n_coarse, -1).reshape(sb, -1, 3),
+                         coarse=True)                                      # :173
+    out = out.view(sb, r, n_coarse, 4)
+    rgb_c, dist_c, w_c = composite_rgbs(z_c, out, white_back)              # :180
+    z_f = fine_z(near_t, far_t, w_c, u_cdf, u_bin)                         # :252
+    z_d = depth_z(normals, depth_std, torch.tensor([near]), torch.tensor([far]))  # :254-255
+    z_s = merge_sorted(z_c, z_f, z_d)                                      # :257-258
+    k = n_coarse + n_fine
+    pts = ros.unsqueeze(-2) + torch.einsum("bsi,bsj->bsji", rds, z_s)      # :260
+    out = radiance_field(pts.reshape(sb, -1, 3),
+                         viewdirs=rds.unsqueeze(-2).expand(sb, r, k, -1).reshape(sb, -1, 3),
+                         coarse=False)                                     # :263
+    out = out.view(sb, r, k, 4)
+    rgb_f, dist_f, _ = composite_rgbs(z_s, out, white_back)                # :270
+    depth = camera_depth(ros + rds * dist_f, cam2world)                    # :274-275
+    return rgb_c, rgb_f, depth, depth
+
+
+def draw_volume_randoms(sb, r, n_coarse, n_fine, n_fine_depth, generator=None, device="cpu"):
+    """The reference's draw order (renderers.py:14, :41, :45, :63)."""
+    ki = n_fine - n_fine_depth
+    kw = dict(dtype=torch.float32, device=device, generator=generator)
+    return (
+        torch.rand(sb, r, n_coarse, **kw),
+        torch.rand(sb, r, ki, **kw),
+        torch.rand(sb, r, ki, **kw),
+        torch.randn(sb, r, n_fine_depth, **kw),
+    )

@@ -1,0 +1,249 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (build container only).
+
+    python oracle/make_golden.py
+
+Every array named ``ref_*`` in the fixtures is an output of the unmodified
+functions/classes in /root/reference/renderers.py (imported through
+``oracle/ref_shim.py``) on CPU fp32 (and fp64 where noted); everything else is
+an input.  The reference draws its random numbers internally, so each case
+seeds torch, runs the reference, then re-seeds and replays the same draw calls
+in the reference's order (renderers.py:14, :41, :45, :63; :413 for the
+adaptive renderer) to record the numbers it consumed.
+
+TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+from fields import TinyField, TinyFeatureField, camera_setup  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    conv = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        conv[k] = np.asarray(v)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **conv)
+    print(f"{name}: {os.path.getsize(path)/1024:.1f} KiB")
+
+
+def synth_rgbs(gen, shape_rk, sparse=True):
+    """(…,K,4) rgbσ like the MLP's output: sigmoid colours, ReLU density with exact zeros."""
+    rgb = torch.sigmoid(torch.randn(*shape_rk, 3, generator=gen))
+    if sparse:
+        sig = torch.relu(torch.randn(*shape_rk, 1, generator=gen)) * 30.0
+    else:
+        sig = torch.rand(*shape_rk, 1, generator=gen) * 5.0
+    return torch.cat([rgb, sig], -1).contiguous()
+
+
+def synth_z(gen, shape_rk, near=0.8, dup=0):
+    z = near + torch.rand(*shape_rk, generator=gen)
+    if dup:
+        z[..., :dup] = near
+    return torch.sort(z, -1).values.contiguous()
+
+
+def case_coarse(ref):
+    g = torch.Generator().manual_seed(11)
+    sb, r = 2, 37
+    out = {}
+    # VolumeRenderer style: scalar near/far expanded with stride 0 (renderers.py:169)
+    near = torch.tensor([0.8]).expand(sb, r)
+    far = torch.tensor([1.8]).expand(sb, r)
+    for k in (64, 20, 1):
+        torch.manual_seed(100 + k)
+        z = ref.sample_coarse(near, far, k, device="cpu")
+        torch.manual_seed(100 + k)
+        u = torch.rand(sb, r, k)
+        out[f"u_k{k}"] = u
+        out[f"ref_z_k{k}"] = z
+    # AdaptiveVolumeRenderer style: per-ray interval d -/+ eps (renderers.py:492)
+    d = 0.9 + 0.8 * torch.rand(sb, r, generator=g)
+    torch.manual_seed(7)
+    z = ref.sample_coarse(d - 0.15, d + 0.15, 20, device="cpu")
+    torch.manual_seed(7)
+    out["avr_u"] = torch.rand(sb, r, 20)
+    out["avr_d"] = d
+    out["ref_avr_z"] = z
+    save("coarse", **out)
+
+
+def case_composite(ref):
+    g = torch.Generator().manual_seed(22)
+    out = {}
+    cases = {
+        # name: (SB, R, K, dup, sparse, white_back)
+        "k96": (1, 96, 96, 16, True, True),      # fine pass incl. the 16 duplicate z=near (renderers.py:255)
+        "k64": (2, 48, 64, 0, True, True),       # coarse pass
+        "k192": (1, 40, 192, 0, True, True),
+        "k20": (1, 64, 20, 0, False, True),      # adaptive renderer
+        "k20_noback": (1, 64, 20, 0, True, False),
+        "k1": (1, 32, 1, 0, False, True),
+        "k7": (1, 33, 7, 0, True, True),         # odd K, ragged-ish tail
+        "dense_pos": (1, 64, 96, 0, False, True),  # all-positive sigma for strict gradient checks
+    }
+    for name, (sb, r, k, dup, sparse, wb) in cases.items():
+        z = synth_z(g, (sb, r, k), dup=dup)
+        rgbs = synth_rgbs(g, (sb, r, k), sparse=sparse)
+        g_rgb = torch.randn(sb, r, 3, generator=g)
+        g_depth = torch.randn(sb, r, 1, generator=g)
+        g_w = torch.randn(sb, r, k, 1, generator=g)
+        for dt, tag in ((torch.float32, ""), (torch.float64, "64")):
+            zz = z.to(dt).clone().requires_grad_(True)
+            xx = rgbs.to(dt).clone().requires_grad_(True)
+            rgb, depth, w = ref.volume_integral(zz, xx[..., 3:4], xx[..., :3], white_back=wb)
+            # loss as utils.py:364-377 touches it: rgb and depth only
+            torch.autograd.backward([rgb, depth], [g_rgb.to(dt), g_depth.to(dt)], retain_graph=True)
+            out[f"{name}_ref{tag}_rgb"] = rgb
+            out[f"{name}_ref{tag}_depth"] = depth
+            out[f"{name}_ref{tag}_w"] = w
+            out[f"{name}_ref{tag}_d_rgbs"] = xx.grad.clone()
+            out[f"{name}_ref{tag}_d_z"] = zz.grad.clone()
+            xx.grad = None
+            zz.grad = None
+            torch.autograd.backward([rgb, depth, w], [g_rgb.to(dt), g_depth.to(dt), g_w.to(dt)])
+            out[f"{name}_ref{tag}_d_rgbs_gw"] = xx.grad.clone()
+            out[f"{name}_ref{tag}_d_z_gw"] = zz.grad.clone()
+        out[f"{name}_z"] = z
+        out[f"{name}_rgbs"] = rgbs
+        out[f"{name}_g_rgb"] = g_rgb
+        out[f"{name}_g_depth"] = g_depth
+        out[f"{name}_g_w"] = g_w
+        out[f"{name}_white_back"] = np.array(wb)
+    # known-answer rows
+    z = synth_z(g, (1, 8, 16))
+    x = synth_rgbs(g, (1, 8, 16))
+    x[0, 0, :, 3] = 0.0                # empty ray -> rgb = 1, depth = 0
+    x[0, 1, :, 3] = 1e4                # very opaque: weights run through denormals
+    x[0, 2, :, 3] = 0.0
+    x[0, 2, 5, 3] = 1e6                # single opaque sample -> one-hot weights
+    rgb, depth, w = ref.volume_integral(z, x[..., 3:4], x[..., :3])
+    out.update(kat_z=z, kat_rgbs=x, kat_ref_rgb=rgb, kat_ref_depth=depth, kat_ref_w=w)
+    save("composite", **out)
+
+
+def case_fine(ref):
+    g = torch.Generator().manual_seed(33)
+    sb, r, kc, n = 1, 200, 64, 128
+    near = torch.tensor([0.8]).expand(sb, r)
+    far = torch.tensor([1.8]).expand(sb, r)
+    w = (torch.rand(sb, r, kc, 1, generator=g) ** 6)
+    w[0, 0] = 0.0                       # all-zero weights -> uniform pdf
+    w[0, 1] = 1.0                       # uniform weights
+    w[0, 2] = 0.0
+    w[0, 2, 17] = 1.0                   # one spike
+    torch.manual_seed(3)
+    z = ref.sample_fine(near, far, n, w, device="cpu")
+    torch.manual_seed(3)
+    u = torch.rand(sb, r, n)
+    u2 = torch.rand(sb, r, n)
+    out = dict(w=w, u=u, u2=u2, ref_z=z)
+    # adversarial draws cannot be injected into the reference (it draws inside), so
+    # monkeypatch torch.rand for one call: still the reference's code doing the work.
+    ua = u.clone()
+    ua[:, :, 0] = 0.0
+    ua[:, :, 1] = 2.0 ** -24
+    ua[:, :, 2] = 1.0 - 2.0 ** -24
+    ua[:, :, 3] = 0.5
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: ua.clone()
+    try:
+        torch.manual_seed(4)
+        z_adv = ref.sample_fine(near, far, n, w, device="cpu")
+        torch.manual_seed(4)
+        u2_adv = torch.rand_like(ua)
+    finally:
+        torch.rand = real_rand
+    out.update(u_adv=ua, u2_adv=u2_adv, ref_z_adv=z_adv)
+    # per-ray near/far
+    d = 0.9 + 0.8 * torch.rand(sb, r, generator=g)
+    torch.manual_seed(5)
+    z_pr = ref.sample_fine(d - 0.15, d + 0.15, 16, w, device="cpu")
+    torch.manual_seed(5)
+    out.update(pr_d=d, pr_u=torch.rand(sb, r, 16), pr_u2=torch.rand(sb, r, 16), ref_pr_z=z_pr)
+    # the merge step as VolumeRenderer does it (renderers.py:254-258)
+    torch.manual_seed(6)
+    zc = ref.sample_coarse(near, far, kc, device="cpu")
+    zd = torch.clamp(ref.sample_depth(torch.zeros(sb, r, 1), 16, 0.01), torch.tensor([0.8]), torch.tensor([1.8]))
+    torch.manual_seed(6)
+    uc = torch.rand(sb, r, kc)
+    nrm = torch.randn(sb, r, 16)
+    zs, _ = torch.sort(torch.cat([zc, z, zd], -1), -1)
+    out.update(merge_uc=uc, merge_normals=nrm, ref_merge_zc=zc, ref_merge_zd=zd, ref_merge_sorted=zs)
+    save("fine", **out)
+
+
+def case_volume_renderer(ref):
+    sb, r = 2, 64
+    cam2world, intrinsics, x_pix = camera_setup(sb, r, seed=1)
+    for name, (kc, nf, nd, wb) in {"default": (64, 32, 16, True), "small": (32, 16, 8, False)}.items():
+        field = TinyField(seed=2)
+        ren = ref.VolumeRenderer(0.8, 1.8, kc, nf, nd, 0.01, white_back=wb)
+        ren.near, ren.far = ren.near.cpu(), ren.far.cpu()
+        torch.manual_seed(40)
+        with torch.no_grad():
+            rc, rf, d0, d1 = ren(cam2world, intrinsics, x_pix, field)
+        torch.manual_seed(40)
+        ki = nf - nd
+        draws = [torch.rand(sb, r, kc), torch.rand(sb, r, ki), torch.rand(sb, r, ki), torch.randn(sb, r, nd)]
+        # gradients w.r.t. the field's parameters through the whole renderer (loss = utils.py:364-377 style)
+        torch.manual_seed(40)
+        field.zero_grad()
+        rc2, rf2, d2, _ = ren(cam2world, intrinsics, x_pix, field)
+        loss = ((rc2 - 0.3) ** 2).mean() + ((rf2 - 0.3) ** 2).mean() + 0.1 * d2.mean()
+        loss.backward()
+        grads = {f"{name}_ref_grad_{i}": p.grad.clone() for i, p in enumerate(field.parameters())}
+        save(f"volume_renderer_{name}", cam2world=cam2world, intrinsics=intrinsics, x_pix=x_pix,
+             u_coarse=draws[0], u_cdf=draws[1], u_bin=draws[2], normals=draws[3],
+             ref_rgb_coarse=rc, ref_rgb_fine=rf, ref_depth=d0, ref_loss=loss.detach(),
+             cfg=np.array([kc, nf, nd, int(wb)]), **grads)
+
+
+def case_adaptive_renderer(ref):
+    sb, r, ch = 1, 48, 32
+    cam2world, intrinsics, x_pix = camera_setup(sb, r, seed=3)
+    phi = TinyFeatureField(ch, seed=4)
+    torch.manual_seed(9)
+    ren = ref.AdaptiveVolumeRenderer(ch, raymarch_steps=3, epsilon=0.15, n_coarse=20, white_back=True)
+    state = {k: v.clone() for k, v in ren.state_dict().items()}
+    torch.manual_seed(50)
+    rc, rgb, dc, depth = ren(cam2world, intrinsics, x_pix, phi)
+    loss = ((rgb - 0.3) ** 2).mean() + 0.1 * depth.mean() + ((rc - 0.2) ** 2).mean()
+    loss.backward()
+    torch.manual_seed(50)
+    init = torch.zeros((sb, r, 1)).normal_(mean=0.8, std=5e-2)      # renderers.py:413
+    u = torch.rand(sb, r, 20)                                      # renderers.py:14 via :492
+    save("adaptive_renderer", cam2world=cam2world, intrinsics=intrinsics, x_pix=x_pix,
+         init_distance=init, u_coarse=u,
+         ref_rgb_coarse=rc, ref_rgb=rgb, ref_depth_coarse=dc, ref_depth=depth,
+         **{"state_" + k.replace(".", "__"): v for k, v in state.items()},
+         **{"ref_grad_" + k.replace(".", "__"): p.grad.clone() for k, p in ren.named_parameters()},
+         **{f"ref_phi_grad_{i}": p.grad.clone() for i, p in enumerate(phi.parameters())})
+
+
+def main():
+    ref = ref_shim.load()
+    torch.set_num_threads(1)   # one thread: reductions are order-stable across machines
+    case_coarse(ref)
+    case_composite(ref)
+    case_fine(ref)
+    case_volume_renderer(ref)
+    case_adaptive_renderer(ref)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,93 @@
+"""The oracle against the committed fixtures, which hold outputs of the reference itself
+(oracle/make_golden.py).  Runs anywhere (CPU).  Tolerance is a few ulp rather than exact
+because torch-CPU's exp/sum kernels are ISA-dependent across machines."""
+import pytest
+import torch
+
+import avr_oracle as O
+from conftest import assert_close, load_golden
+
+TIGHT = dict(rtol=2e-6, atol=2e-7)
+
+
+def test_coarse_golden():
+    g = load_golden("coarse")
+    near = torch.tensor([0.8]).expand(2, 37)
+    far = torch.tensor([1.8]).expand(2, 37)
+    for k in (64, 20, 1):
+        assert torch.equal(O.coarse_z(near, far, k, g[f"u_k{k}"]), g[f"ref_z_k{k}"])
+    d = g["avr_d"]
+    assert torch.equal(O.coarse_z(d - 0.15, d + 0.15, 20, g["avr_u"]), g["ref_avr_z"])
+
+
+COMPOSITE_CASES = ["k96", "k64", "k192", "k20", "k20_noback", "k1", "k7", "dense_pos"]
+
+
+@pytest.mark.parametrize("name", COMPOSITE_CASES)
+def test_composite_golden(name):
+    g = load_golden("composite")
+    wb = bool(g[f"{name}_white_back"])
+    z, x = g[f"{name}_z"], g[f"{name}_rgbs"]
+    rgb, depth, w = O.composite_rgbs(z, x, wb)
+    assert_close(rgb, g[f"{name}_ref_rgb"], what="rgb", **TIGHT)
+    assert_close(depth, g[f"{name}_ref_depth"], what="depth", **TIGHT)
+    assert_close(w, g[f"{name}_ref_w"], what="w", **TIGHT)
+    # fp64 run of the reference is the accuracy yardstick: fp32 sits well inside the parity bar
+    assert_close(rgb, g[f"{name}_ref64_rgb"].float(), what="rgb vs fp64")
+    dx, dz = O.composite_grads(z, x, g[f"{name}_g_rgb"], g[f"{name}_g_depth"], None, wb, want_dz=True)
+    ref_dx = g[f"{name}_ref_d_rgbs"]
+    scale = ref_dx.abs().max().item()
+    assert_close(dx / scale, ref_dx / scale, what="d_rgbs", **TIGHT)
+    ref_dz = g[f"{name}_ref_d_z"]
+    assert_close(dz / ref_dz.abs().max().clamp_min(1.0), ref_dz / ref_dz.abs().max().clamp_min(1.0), what="d_z", **TIGHT)
+
+
+def test_composite_known_answers():
+    g = load_golden("composite")
+    rgb, depth, w = O.composite_rgbs(g["kat_z"], g["kat_rgbs"])
+    assert_close(rgb, g["kat_ref_rgb"], what="rgb", **TIGHT)
+    # empty ray: pure white background, depth 0
+    assert torch.equal(rgb[0, 0], torch.ones(3)) and depth[0, 0, 0] == 0 and w[0, 0].abs().sum() == 0
+    # very opaque ray: weights fall by 1e-10 per sample through the denormals
+    assert w[0, 1, 0, 0] == 1.0 and 0 < w[0, 1, 3, 0] < 1e-29
+    # one opaque sample: one-hot weights
+    assert w[0, 2, 5, 0] == 1.0 and w[0, 2].sum() == 1.0
+
+
+def test_fine_golden():
+    g = load_golden("fine")
+    r = g["w"].shape[1]
+    near = torch.tensor([0.8]).expand(1, r)
+    far = torch.tensor([1.8]).expand(1, r)
+    z, cdf, idx = O.fine_z(near, far, g["w"], g["u"], g["u2"], return_aux=True)
+    assert_close(z, g["ref_z"], what="z_fine", **TIGHT)
+    assert idx.min() >= 0 and idx.max() <= 64
+    # uniform weights: cdf_j = j/K and the bin is floor(u*K) (up to rounding of the cdf)
+    assert (idx[0, 1] - torch.floor(g["u"][0, 1] * 64).long()).abs().max() <= 1
+    z_adv, _, idx_adv = O.fine_z(near, far, g["w"], g["u_adv"], g["u2_adv"], return_aux=True)
+    assert_close(z_adv, g["ref_z_adv"], what="z_fine adversarial", **TIGHT)
+    assert (idx_adv[..., 0] == 0).all()                 # u = 0 -> first bin
+    assert (idx_adv[..., 2] >= 63).all()                # u = 1 - 2^-24 -> last bin, or one past it
+    d = g["pr_d"]
+    assert_close(O.fine_z(d - 0.15, d + 0.15, g["w"], g["pr_u"], g["pr_u2"]), g["ref_pr_z"], what="per-ray bounds", **TIGHT)
+    zc = O.coarse_z(near, far, 64, g["merge_uc"])
+    zd = O.depth_z(g["merge_normals"], 0.01, torch.tensor([0.8]), torch.tensor([1.8]))
+    assert torch.equal(zc, g["ref_merge_zc"]) and torch.equal(zd, g["ref_merge_zd"])
+    assert (zd == 0.8).all()                            # the sample_depth quirk: all clamp to near
+    assert_close(O.merge_sorted(zc, z, zd), g["ref_merge_sorted"], what="merged", **TIGHT)
+
+
+@pytest.mark.parametrize("name", ["default", "small"])
+def test_volume_renderer_golden(name):
+    from fields import TinyField
+
+    g = load_golden(f"volume_renderer_{name}")
+    kc, nf, nd, wb = [int(v) for v in g["cfg"]]
+    field = TinyField(seed=2)
+    draws = (g["u_coarse"], g["u_cdf"], g["u_bin"], g["normals"])
+    with torch.no_grad():
+        rc, rf, d, _ = O.render_volume(g["cam2world"], g["intrinsics"], g["x_pix"], field, 0.8, 1.8, kc, nf, nd, 0.01,
+                                       bool(wb), draws)
+    assert_close(rc, g["ref_rgb_coarse"], what="rgb_coarse", rtol=1e-5, atol=1e-6)
+    assert_close(rf, g["ref_rgb_fine"], what="rgb_fine", rtol=1e-4, atol=1e-5)
+    assert_close(d, g["ref_depth"], what="depth", rtol=1e-4, atol=1e-5)
