@@ -24,6 +24,8 @@ PROTOTYPES = {
     "avr_last_cuda_error": (c_char_p, []),
     "avr_device_check": (c_int, []),
     "avr_composite_plan": (c_int, [c_int64, c_int, _P, _P]),
+    "avr_composite_plan_info": (c_int, [c_int64, c_int, _P, _P, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                        ctypes.POINTER(c_int64)]),
     "avr_set_force_generic": (None, [c_int]),
     "avr_coarse_sample_fwd": (c_int, [_P, _P, c_int, _P, c_int64, c_int, _P, _P]),
     "avr_coarse_sample_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
@@ -37,7 +39,9 @@ PROTOTYPES = {
     "avr_coarse_sample_fwd_packed": (c_int, [_P, _P, c_int, _P, _P, c_int64, c_int64, _P, _P]),
     "avr_importance_sample_packed": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int64, c_int, c_int,
                                              _P, _P, _P]),
-    "avr_composite_fwd_bwd_host": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, c_int64]),
+    "avr_host_workspace_create": (c_int, [c_int, c_int64, ctypes.POINTER(c_void_p)]),
+    "avr_host_workspace_destroy": (c_int, [_P]),
+    "avr_composite_fwd_bwd_host": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
 }
 
 _lib = None

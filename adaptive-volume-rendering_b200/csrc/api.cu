@@ -72,6 +72,16 @@ int avr_composite_plan(int64_t R, int K, const void* rgbs, const void* z) {
   return span_plan(R, K, rgbs, z, &p) ? 1 : 0;
 }
 
+int avr_composite_plan_info(int64_t R, int K, const void* rgbs, const void* z, int* samples_per_lane,
+                            int* rays_per_tile, int64_t* main_rays) {
+  SpanPlan p{};
+  const bool ok = !g_force_generic.load() && span_plan(R, K, rgbs, z, &p);
+  if (samples_per_lane) *samples_per_lane = ok ? p.L : 0;
+  if (rays_per_tile) *rays_per_tile = ok ? p.rays_per_tile : 0;
+  if (main_rays) *main_rays = ok ? p.main_rays : 0;
+  return ok ? 1 : 0;
+}
+
 /* ---------------------------------------------------------------- samplers -- */
 
 int avr_coarse_sample_fwd(const float* near, const float* far, int bound_stride, const float* u, int64_t R,
@@ -205,90 +215,132 @@ int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* o
 
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
-#define AVR_RT(call)                  \
-  do {                                \
-    cudaError_t e_ = (call);          \
-    if (e_ != cudaSuccess) {          \
-      set_last_cuda_error(e_);        \
-      rc = AVR_ERR_RUNTIME;           \
-      goto cleanup;                   \
-    }                                 \
+}  // extern "C"
+
+// Rays are independent, so the pass is chunked and software-pipelined over three slots:
+// while chunk c computes, chunk c+1 uploads and chunk c-1 downloads (PCIe is full duplex).
+// Stream order inside a slot serialises the reuse of its buffers.
+struct avr_host_workspace {
+  static constexpr int kSlots = 3;
+  struct Slot {
+    float *rgbs = nullptr, *z = nullptr, *g_rgb = nullptr, *g_depth = nullptr;
+    float *rgb = nullptr, *depth = nullptr, *d_rgbs = nullptr;
+    cudaStream_t stream = nullptr;
+  } slots[kSlots];
+  int K = 0;
+  int64_t chunk_rays = 0;
+  int device = 0;
+};
+
+static void free_workspace(avr_host_workspace* ws) {
+  for (auto& sl : ws->slots) {
+    if (sl.stream) {
+      cudaStreamSynchronize(sl.stream);
+      cudaStreamDestroy(sl.stream);
+    }
+    cudaFree(sl.rgbs);
+    cudaFree(sl.z);
+    cudaFree(sl.g_rgb);
+    cudaFree(sl.g_depth);
+    cudaFree(sl.rgb);
+    cudaFree(sl.depth);
+    cudaFree(sl.d_rgbs);
+  }
+  delete ws;
+}
+
+#define AVR_RT(call)            \
+  do {                          \
+    cudaError_t e_ = (call);    \
+    if (e_ != cudaSuccess) {    \
+      set_last_cuda_error(e_);  \
+      (void)cudaGetLastError(); \
+      return AVR_ERR_RUNTIME;   \
+    }                           \
   } while (0)
 
-int avr_composite_fwd_bwd_host(const float* rgbs, const float* z, const float* g_rgb, const float* g_depth,
-                               int64_t R, int K, int white_back, float infinity, float* rgb, float* depth,
-                               float* d_rgbs, int64_t chunk_rays) {
-  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
-  if (R == 0) return AVR_OK;
-  if (!rgbs || !z || !rgb || !depth || !d_rgbs) return AVR_ERR_BAD_ARG;
-  int rc = avr_device_check();
-  if (rc != AVR_OK) return rc;
-
-  // Rays are independent, so the pass is chunked and software-pipelined over three
-  // slots: while chunk c computes, chunk c+1 uploads and chunk c-1 downloads (PCIe is
-  // full duplex).  Chunks are multiples of 96 rays so every chunk start stays aligned
-  // for the span kernels whatever K is.
-  constexpr int kSlots = 3;
-  if (chunk_rays <= 0) {
-    int64_t target = (int64_t)(48ll << 20) / ((int64_t)K * 16);  // ~48 MiB of rgbs per chunk
-    chunk_rays = target < 96 ? 96 : target;
+static int alloc_workspace(avr_host_workspace* ws) {
+  const size_t nk = (size_t)ws->chunk_rays * ws->K;
+  const size_t nr = (size_t)ws->chunk_rays;
+  for (auto& sl : ws->slots) {
+    AVR_RT(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    AVR_RT(cudaMalloc(&sl.rgbs, nk * 16));
+    AVR_RT(cudaMalloc(&sl.z, nk * 4));
+    AVR_RT(cudaMalloc(&sl.g_rgb, nr * 12));
+    AVR_RT(cudaMalloc(&sl.g_depth, nr * 4));
+    AVR_RT(cudaMalloc(&sl.rgb, nr * 12));
+    AVR_RT(cudaMalloc(&sl.depth, nr * 4));
+    AVR_RT(cudaMalloc(&sl.d_rgbs, nk * 16));
   }
-  chunk_rays = (chunk_rays + 95) / 96 * 96;
-  if (chunk_rays > R) chunk_rays = R;
-  const int64_t n_chunks = (R + chunk_rays - 1) / chunk_rays;
+  return AVR_OK;
+}
 
-  struct Slot {
-    float *rgbs, *z, *g_rgb, *g_depth, *rgb, *depth, *d_rgbs;
-    cudaStream_t stream;
-  } slots[kSlots];
-  memset(slots, 0, sizeof(slots));
-  const size_t nk = (size_t)chunk_rays * K;
-  for (int s = 0; s < kSlots && s < n_chunks; ++s) {
-    AVR_RT(cudaStreamCreateWithFlags(&slots[s].stream, cudaStreamNonBlocking));
-    AVR_RT(cudaMalloc(&slots[s].rgbs, nk * 16));
-    AVR_RT(cudaMalloc(&slots[s].z, nk * 4));
-    AVR_RT(cudaMalloc(&slots[s].g_rgb, (size_t)chunk_rays * 12));
-    AVR_RT(cudaMalloc(&slots[s].g_depth, (size_t)chunk_rays * 4));
-    AVR_RT(cudaMalloc(&slots[s].rgb, (size_t)chunk_rays * 12));
-    AVR_RT(cudaMalloc(&slots[s].depth, (size_t)chunk_rays * 4));
-    AVR_RT(cudaMalloc(&slots[s].d_rgbs, nk * 16));
-  }
+static int run_host_pass(avr_host_workspace* ws, const float* rgbs, const float* z, const float* g_rgb,
+                         const float* g_depth, int64_t R, int white_back, float infinity, float* rgb,
+                         float* depth, float* d_rgbs) {
+  const int K = ws->K;
+  const int64_t chunk = ws->chunk_rays;
+  const int64_t n_chunks = (R + chunk - 1) / chunk;
+  int rc = AVR_OK;
   for (int64_t c = 0; c < n_chunks; ++c) {
-    Slot& sl = slots[c % kSlots];
-    const int64_t r0 = c * chunk_rays;
-    const int64_t rn = (R - r0 < chunk_rays) ? R - r0 : chunk_rays;
+    auto& sl = ws->slots[c % avr_host_workspace::kSlots];
+    const int64_t r0 = c * chunk;
+    const int64_t rn = (R - r0 < chunk) ? R - r0 : chunk;
     const size_t n = (size_t)rn * K;
-    // stream order inside a slot serialises reuse of its buffers
     AVR_RT(cudaMemcpyAsync(sl.rgbs, rgbs + r0 * K * 4, n * 16, cudaMemcpyHostToDevice, sl.stream));
     AVR_RT(cudaMemcpyAsync(sl.z, z + r0 * K, n * 4, cudaMemcpyHostToDevice, sl.stream));
     if (g_rgb) AVR_RT(cudaMemcpyAsync(sl.g_rgb, g_rgb + r0 * 3, (size_t)rn * 12, cudaMemcpyHostToDevice, sl.stream));
     if (g_depth) AVR_RT(cudaMemcpyAsync(sl.g_depth, g_depth + r0, (size_t)rn * 4, cudaMemcpyHostToDevice, sl.stream));
     rc = avr_composite_fwd(sl.rgbs, sl.z, rn, K, white_back, infinity, nullptr, sl.rgb, sl.depth, sl.stream);
-    if (rc != AVR_OK) goto cleanup;
-    rc = avr_composite_bwd(sl.rgbs, sl.z, g_rgb ? sl.g_rgb : nullptr, g_depth ? sl.g_depth : nullptr, nullptr, rn,
-                           K, white_back, infinity, sl.d_rgbs, nullptr, sl.stream);
-    if (rc != AVR_OK) goto cleanup;
+    if (rc != AVR_OK) return rc;
+    rc = avr_composite_bwd(sl.rgbs, sl.z, g_rgb ? sl.g_rgb : nullptr, g_depth ? sl.g_depth : nullptr, nullptr, rn, K,
+                           white_back, infinity, sl.d_rgbs, nullptr, sl.stream);
+    if (rc != AVR_OK) return rc;
     AVR_RT(cudaMemcpyAsync(rgb + r0 * 3, sl.rgb, (size_t)rn * 12, cudaMemcpyDeviceToHost, sl.stream));
     AVR_RT(cudaMemcpyAsync(depth + r0, sl.depth, (size_t)rn * 4, cudaMemcpyDeviceToHost, sl.stream));
     AVR_RT(cudaMemcpyAsync(d_rgbs + r0 * K * 4, sl.d_rgbs, n * 16, cudaMemcpyDeviceToHost, sl.stream));
   }
-  for (int s = 0; s < kSlots; ++s)
-    if (slots[s].stream) AVR_RT(cudaStreamSynchronize(slots[s].stream));
-cleanup:
-  for (int s = 0; s < kSlots; ++s) {
-    if (slots[s].stream) {
-      if (rc != AVR_OK) cudaStreamSynchronize(slots[s].stream);
-      cudaStreamDestroy(slots[s].stream);
-    }
-    cudaFree(slots[s].rgbs);
-    cudaFree(slots[s].z);
-    cudaFree(slots[s].g_rgb);
-    cudaFree(slots[s].g_depth);
-    cudaFree(slots[s].rgb);
-    cudaFree(slots[s].depth);
-    cudaFree(slots[s].d_rgbs);
+  for (auto& sl : ws->slots) AVR_RT(cudaStreamSynchronize(sl.stream));
+  return AVR_OK;
+}
+
+extern "C" {
+
+int avr_host_workspace_create(int K, int64_t chunk_rays, avr_host_workspace** out) {
+  if (!out || K < 1) return AVR_ERR_BAD_ARG;
+  *out = nullptr;
+  int rc = avr_device_check();
+  if (rc != AVR_OK) return rc;
+  if (chunk_rays <= 0) {
+    int64_t target = (int64_t)(48ll << 20) / ((int64_t)K * 16);
+    chunk_rays = target < 96 ? 96 : target;
   }
-  return rc;
+  auto* ws = new avr_host_workspace();
+  ws->K = K;
+  ws->chunk_rays = chunk_rays;
+  cudaGetDevice(&ws->device);
+  rc = alloc_workspace(ws);
+  if (rc != AVR_OK) {
+    free_workspace(ws);
+    return rc;
+  }
+  *out = ws;
+  return AVR_OK;
+}
+
+int avr_host_workspace_destroy(avr_host_workspace* ws) {
+  if (!ws) return AVR_OK;
+  free_workspace(ws);
+  return AVR_OK;
+}
+
+int avr_composite_fwd_bwd_host(avr_host_workspace* ws, const float* rgbs, const float* z, const float* g_rgb,
+                               const float* g_depth, int64_t R, int K, int white_back, float infinity,
+                               float* rgb, float* depth, float* d_rgbs) {
+  if (!ws || R < 0 || K < 1 || K != ws->K) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!rgbs || !z || !rgb || !depth || !d_rgbs) return AVR_ERR_BAD_ARG;
+  return run_host_pass(ws, rgbs, z, g_rgb, g_depth, R, white_back, infinity, rgb, depth, d_rgbs);
 }
 
 }  // extern "C"

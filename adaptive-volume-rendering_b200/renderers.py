@@ -73,17 +73,22 @@ def sample_depth(depth, num_samples: int, depth_std, *, normals: Optional[torch.
     return normals * depth_std
 
 
+def _same_layout(a: torch.Tensor, b: torch.Tensor) -> bool:
+    if a.shape != b.shape or a.data_ptr() != b.data_ptr():
+        return False
+    return all(sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()) if n != 1)
+
+
 def _as_rgbs(sigmas: torch.Tensor, radiances: torch.Tensor) -> torch.Tensor:
     """The reference passes sigma (...,K,1) and radiance (...,K,3) as two slices of one
     (…,K,4) buffer (renderers.py:177-178).  If that is what we were given, use the buffer
     itself (no copy, one gradient); otherwise interleave."""
-    base_s, base_r = sigmas._base, radiances._base
-    if base_s is not None and base_s is base_r and base_s.is_contiguous() and base_s.shape[-1] == 4 \
-            and base_s.numel() == sigmas.numel() * 4 and sigmas.stride(-1) == 1 and radiances.stride(-1) == 1 \
-            and sigmas.storage_offset() == base_s.storage_offset() + 3 \
-            and radiances.storage_offset() == base_s.storage_offset() \
-            and sigmas.stride()[:-1] == radiances.stride()[:-1] and sigmas.stride(-2) == 4:
-        return base_s.view(*sigmas.shape[:-1], 4)
+    base = sigmas._base
+    if base is not None and base is radiances._base and base.is_contiguous() \
+            and base.numel() == sigmas.numel() * 4 and base.shape[-1] == 4:
+        cand = base.view(*sigmas.shape[:-1], 4)
+        if _same_layout(sigmas, cand[..., 3:4]) and _same_layout(radiances, cand[..., :3]):
+            return cand
     return torch.cat([radiances, sigmas], dim=-1)
 
 

@@ -68,6 +68,11 @@ AVR_API int avr_device_check(void);
 /* Which composite kernel family a call will use (for tests/bench): 0 = generic
  * thread-per-ray, 1 = TMA-staged blocked scan ("span" kernels). */
 AVR_API int avr_composite_plan(int64_t R, int K, const void* rgbs, const void* z);
+/* Details of that choice (each out pointer may be NULL): samples per lane, whole rays per
+ * warp tile, and how many leading rays the span kernel covers (the remaining R - main_rays
+ * tail rays take the generic kernel in a second launch).  Returns 1 / 0 like the above. */
+AVR_API int avr_composite_plan_info(int64_t R, int K, const void* rgbs, const void* z,
+                                    int* samples_per_lane, int* rays_per_tile, int64_t* main_rays);
 /* Force the generic kernels (1) or restore automatic choice (0); process-wide, for tests. */
 AVR_API void avr_set_force_generic(int on);
 
@@ -162,16 +167,23 @@ AVR_API int avr_importance_sample_packed(const float* weights, const float* z_co
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
 /* One forward+backward compositing pass over HOST buffers (pinned for full speed):
- * chunks the rays, overlaps H2D copies, the two kernels and D2H copies on internal
+ * chunks the rays, overlaps H2D copies, the two kernels and D2H copies on the workspace's
  * streams, and returns when every output is on the host.  This is the call `bench.py`
  * times for the end-to-end figure.  Outputs rgb [R,3], depth [R], d_rgbs [R,K,4];
  * w is not returned (the fine pass discards it, renderers.py:270).
- * `chunk_rays` <= 0 picks a default. */
-AVR_API int avr_composite_fwd_bwd_host(const float* rgbs, const float* z,
-                               const float* g_rgb, const float* g_depth,
-                               int64_t R, int K, int white_back, float infinity,
-                               float* rgb, float* depth, float* d_rgbs,
-                               int64_t chunk_rays);
+ *
+ * The workspace owns the device staging buffers and streams (3 slots of `chunk_rays` rays
+ * x K samples); it is created once and reused across calls, is not thread-safe, and must
+ * be destroyed by the caller.  K of a call must equal the workspace's K.
+ * `chunk_rays` <= 0 picks a default (~48 MiB of rgbs per chunk). */
+typedef struct avr_host_workspace avr_host_workspace;
+AVR_API int avr_host_workspace_create(int K, int64_t chunk_rays, avr_host_workspace** out);
+AVR_API int avr_host_workspace_destroy(avr_host_workspace* ws);
+AVR_API int avr_composite_fwd_bwd_host(avr_host_workspace* ws,
+                                       const float* rgbs, const float* z,
+                                       const float* g_rgb, const float* g_depth,
+                                       int64_t R, int K, int white_back, float infinity,
+                                       float* rgb, float* depth, float* d_rgbs);
 
 #ifdef __cplusplus
 }

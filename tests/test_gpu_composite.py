@@ -1,0 +1,169 @@
+"""Parity of the compositing kernels (through the C ABI) with the reference:
+golden fixtures produced by the reference itself, the CPU oracle on seeded inputs, and
+size-independent properties at BASELINE.json's full size (2^20 rays x 96 samples)."""
+import pytest
+import torch
+
+import avr_oracle as O
+from conftest import ATOL, RTOL, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["k96", "k64", "k192", "k20", "k20_noback", "k1", "k7", "dense_pos"]
+
+
+@pytest.fixture(params=["auto", "generic"])
+def family(request):
+    """Run every case through the kernel the planner picks AND through the generic kernels."""
+    import avr_b200
+    lib = avr_b200.load_library()
+    lib.avr_set_force_generic(1 if request.param == "generic" else 0)
+    yield request.param
+    lib.avr_set_force_generic(0)
+
+
+def _sigma_grad_close(got, want, z_last_mask, what):
+    """d_sigma: the last sample of a ray carries the 1e10 interval (renderers.py:78-81); the
+    reference's own fp32 is far outside 1e-5/1e-6 there, so that element is
+    compared after dividing by 1e10.  All other elements use the plain parity bar."""
+    assert_close(got[..., :-1], want[..., :-1], what=what + " d_sigma[:-1]")
+    assert_close(got[..., -1] / 1e10, want[..., -1] / 1e10, what=what + " d_sigma[-1]/1e10")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_forward_backward(name, family, dev):
+    import avr_b200
+    g = load_golden("composite")
+    wb = bool(g[f"{name}_white_back"])
+    z = g[f"{name}_z"].to(dev)
+    x = g[f"{name}_rgbs"].to(dev).requires_grad_(True)
+    # reference signature: sigma and radiance as slices of the field's output
+    rgb, depth, w = avr_b200.volume_integral(z, x[..., 3:4], x[..., :3], white_back=wb)
+    assert rgb.shape == g[f"{name}_ref_rgb"].shape and depth.shape == g[f"{name}_ref_depth"].shape
+    assert w.shape == g[f"{name}_ref_w"].shape
+    assert_close(rgb, g[f"{name}_ref_rgb"], what="rgb")
+    assert_close(depth, g[f"{name}_ref_depth"], what="depth")
+    assert_close(w, g[f"{name}_ref_w"], what="weights")
+    torch.autograd.backward([rgb, depth], [g[f"{name}_g_rgb"].to(dev), g[f"{name}_g_depth"].to(dev)])
+    dx, ref = x.grad.cpu(), g[f"{name}_ref_d_rgbs"]
+    assert_close(dx[..., :3], ref[..., :3], what="d_rgb")
+    _sigma_grad_close(dx[..., 3], ref[..., 3], None, name)
+
+
+@pytest.mark.parametrize("name", ["k96", "k20", "k7", "k1"])
+def test_golden_grad_weights_and_z(name, dev):
+    """g_w and d_z (AdaptiveVolumeRenderer path; generic kernel)."""
+    from avr_b200 import ops
+    g = load_golden("composite")
+    wb = bool(g[f"{name}_white_back"])
+    z = g[f"{name}_z"].to(dev).requires_grad_(True)
+    x = g[f"{name}_rgbs"].to(dev).requires_grad_(True)
+    rgb, depth, w = ops.composite(x, z, wb, 1.8, want_w=True)
+    torch.autograd.backward([rgb, depth, w], [g[f"{name}_g_rgb"].to(dev), g[f"{name}_g_depth"].to(dev)[..., 0],
+                                              g[f"{name}_g_w"].to(dev)[..., 0]])
+    dx, ref = x.grad.cpu(), g[f"{name}_ref_d_rgbs_gw"]
+    assert_close(dx[..., :3], ref[..., :3], what="d_rgb")
+    _sigma_grad_close(dx[..., 3], ref[..., 3], None, name)
+    # d_z is a difference of large terms: the reference's fp32 is itself 2.5-12x outside the bar
+    # against fp64, so the bound is scaled by the ray's largest |d_z| and the
+    # yardstick is the reference run in fp64.
+    ref64 = g[f"{name}_ref64_d_z_gw"]
+    scale = ref64.abs().amax(-1, keepdim=True).clamp_min(1.0)
+    assert_close(z.grad.cpu() / scale, (ref64 / scale).float(), rtol=1e-5, atol=2e-5, what="d_z (scaled, vs fp64)")
+
+
+def test_known_answers(dev, family):
+    from avr_b200 import ops
+    g = load_golden("composite")
+    rgb, depth, w = ops.composite(g["kat_rgbs"].to(dev), g["kat_z"].to(dev), True, 1.8)
+    assert_close(rgb, g["kat_ref_rgb"], what="rgb")
+    assert_close(w, g["kat_ref_w"][..., 0], what="w")
+    rgb, depth, w = rgb.cpu(), depth.cpu(), w.cpu()
+    assert torch.equal(rgb[0, 0], torch.ones(3)) and depth[0, 0] == 0 and w[0, 0].abs().sum() == 0
+    assert w[0, 1, 0] == 1.0 and 0 < w[0, 1, 3] < 1e-29       # denormals are not flushed
+    assert w[0, 2, 5] == 1.0 and w[0, 2].sum() == 1.0
+
+
+def _synth(r, k, seed, dev, dup=0, sparse=True):
+    g = torch.Generator().manual_seed(seed)
+    z = 0.8 + torch.rand(1, r, k, generator=g)
+    if dup:
+        z[..., :dup] = 0.8
+    z = torch.sort(z, -1).values
+    rgb = torch.sigmoid(torch.randn(1, r, k, 3, generator=g))
+    sig = torch.relu(torch.randn(1, r, k, 1, generator=g)) * 30 if sparse else torch.rand(1, r, k, 1, generator=g) * 5
+    x = torch.cat([rgb, sig], -1)
+    return z, x, torch.randn(1, r, 3, generator=g), torch.randn(1, r, generator=g)
+
+
+@pytest.mark.parametrize("r,k,wb", [(4099, 96, True), (3000, 64, True), (1025, 192, False), (777, 33, True),
+                                     (512, 200, True), (300, 500, True), (5000, 20, True), (2048, 8, True),
+                                     (1500, 3, False), (2, 96, True), (1, 1, True)])
+def test_seeded_vs_oracle(r, k, wb, dev):
+    """Shapes chosen to hit: full tiles + tail rays, every lane-run length, rays shorter than
+    a lane's run (K < L), K beyond any tile (generic), tiny R."""
+    from avr_b200 import ops
+    z, x, g_rgb, g_d = _synth(r, k, seed=r * 1000 + k, dev=dev, dup=min(16, k // 4))
+    want = O.composite_rgbs(z, x, wb)
+    want_dx, _ = O.composite_grads(z, x, g_rgb, g_d.unsqueeze(-1), None, wb)
+    xd = x.to(dev).requires_grad_(True)
+    rgb, depth, w = ops.composite(xd, z.to(dev), wb, 1.8)
+    assert_close(rgb, want[0], what="rgb")
+    assert_close(depth, want[1][..., 0], what="depth")
+    assert_close(w, want[2][..., 0], what="w")
+    torch.autograd.backward([rgb, depth], [g_rgb.to(dev), g_d.to(dev)])
+    dx = xd.grad.cpu()
+    assert_close(dx[..., :3], want_dx[..., :3], what="d_rgb")
+    _sigma_grad_close(dx[..., 3], want_dx[..., 3], None, f"R={r} K={k}")
+    # fine-pass variant: weights not requested
+    rgb2, depth2, w2 = ops.composite(x.to(dev), z.to(dev), wb, 1.8, want_w=False)
+    assert w2 is None and torch.equal(rgb2, rgb) and torch.equal(depth2, depth)
+
+
+def test_planner_picks_span_for_headline_shapes(dev):
+    import avr_b200
+    lib = avr_b200.load_library()
+    a = torch.empty(16, device=dev)
+    for k in (96, 64, 192, 20, 128):
+        assert lib.avr_composite_plan(1 << 20, k, a.data_ptr(), a.data_ptr()) == 1, k
+    assert lib.avr_composite_plan(1 << 20, 500, a.data_ptr(), a.data_ptr()) == 0
+    assert lib.avr_composite_plan(1 << 20, 96, a.data_ptr() + 4, a.data_ptr()) == 0   # misaligned view
+
+
+def test_full_size_properties(dev):
+    """BASELINE.json config 2 at full size: 2^20 rays x 96 samples, forward + backward."""
+    from avr_b200 import ops
+    r, k = 1 << 20, 96
+    g = torch.Generator(device=dev).manual_seed(0)
+    z = torch.sort(0.8 + torch.rand(r, k, device=dev, generator=g), -1).values
+    z[:, :16] = 0.8                                        # the depth-sample quirk
+    x = torch.cat([torch.sigmoid(torch.randn(r, k, 3, device=dev, generator=g)),
+                   torch.relu(torch.randn(r, k, 1, device=dev, generator=g)) * 30], -1).requires_grad_(True)
+    g1 = torch.randn(r, 3, device=dev, generator=g)
+    g2 = torch.randn(r, device=dev, generator=g)
+    rgb, depth, w = ops.composite(x, z, True, 1.8)
+    assert (w >= 0).all() and w.sum(-1).max() <= 1 + 3 * 2 ** -24 + 1e-6
+    assert (w[:, :15] == 0).all()                          # zero-length intervals carry no weight
+    last_pos = x[:, -1, 3] > 0
+    assert ((w.sum(-1) - 1).abs()[last_pos] <= 5e-7).all() and (w[:, -1][~last_pos] == 0).all()
+    # a random subsample of rays against the oracle
+    pick = torch.randperm(r, generator=torch.Generator().manual_seed(1))[:4096]
+    want = O.composite_rgbs(z[pick].cpu().unsqueeze(0), x.detach()[pick].cpu().unsqueeze(0), True)
+    assert_close(rgb[pick], want[0][0], what="rgb subsample")
+    assert_close(depth[pick], want[1][0, :, 0], what="depth subsample")
+    assert_close(w[pick], want[2][0, :, :, 0], what="w subsample")
+    # backward is linear in the upstream gradients
+    (da,) = torch.autograd.grad([rgb, depth], [x], [g1, g2], retain_graph=True)
+    (db,) = torch.autograd.grad([rgb], [x], [g1], retain_graph=True)
+    (dc,) = torch.autograd.grad([depth], [x], [g2])
+    lin = (da[..., :3] - (db[..., :3] + dc[..., :3])).abs().max().item()
+    assert lin <= 1e-5, lin
+    want_dx, _ = O.composite_grads(z[pick].cpu().unsqueeze(0), x.detach()[pick].cpu().unsqueeze(0),
+                                   g1[pick].cpu().unsqueeze(0), g2[pick].cpu().reshape(1, -1, 1), None, True)
+    assert_close(da[pick][..., :3], want_dx[0][..., :3], what="d_rgb subsample")
+    _sigma_grad_close(da[pick][..., 3].cpu(), want_dx[0][..., 3], None, "full size")
+    # empty space stays empty
+    x0 = x.detach().clone()
+    x0[..., 3] = 0
+    rgb0, depth0, w0 = ops.composite(x0[:4096], z[:4096], True, 1.8)
+    assert (rgb0 == 1).all() and (depth0 == 0).all() and (w0 == 0).all()

@@ -1,0 +1,131 @@
+"""Packed (ragged) ray layout: per-ray sample counts with an offsets[R+1] array
+(BASELINE.json config 4).  The oracle buckets rays by count and runs the dense restatement
+of the reference per bucket (per-ray results do not depend on batch composition)."""
+import pytest
+import torch
+
+import avr_oracle as O
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _ragged(r, lo, hi, seed, zero_some=True):
+    g = torch.Generator().manual_seed(seed)
+    counts = torch.randint(lo, hi + 1, (r,), generator=g)
+    if zero_some:
+        counts[::97] = 0
+        counts[1::89] = 1
+    offsets = torch.zeros(r + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts, 0)
+    return counts, offsets, g
+
+
+def _packed_inputs(counts, offsets, g):
+    s = int(offsets[-1])
+    d = 0.9 + 0.8 * torch.rand(counts.numel(), generator=g)
+    near, far = d - 0.15, d + 0.15
+    u = torch.rand(s, generator=g)
+    x = torch.cat([torch.sigmoid(torch.randn(s, 3, generator=g)), torch.relu(torch.randn(s, 1, generator=g)) * 30], -1)
+    return near, far, u, x
+
+
+def test_packed_pipeline_vs_oracle(dev):
+    from avr_b200 import ops
+    r = 3000
+    counts, offsets, g = _ragged(r, 8, 256, seed=0)
+    near, far, u, x = _packed_inputs(counts, offsets, g)
+    od = offsets.to(dev)
+    # coarse sampling: each ray stratified over its own count -> bit-exact per bucket
+    z = ops.coarse_sample_packed(near.to(dev), far.to(dev), u.to(dev), od).cpu()
+    for k, rays, idx in O.bucketed(offsets):
+        if k == 0:
+            continue
+        want = O.coarse_z(near[rays].unsqueeze(0), far[rays].unsqueeze(0), k, u[idx].unsqueeze(0))[0]
+        assert torch.equal(z[idx], want), k
+    # compositing forward
+    xd = x.to(dev).requires_grad_(True)
+    zd = z.to(dev).requires_grad_(True)
+    rgb, depth, w = ops.composite_packed(xd, zd, od, True, 1.8)
+    want_rgb, want_depth, want_w = O.composite_packed(z, x, offsets, True, 1.8)
+    assert_close(rgb, want_rgb, what="rgb")
+    assert_close(depth, want_depth, what="depth")
+    assert_close(w, want_w, what="w")
+    empty = counts == 0
+    assert (rgb.cpu()[empty] == 1).all() and (depth.cpu()[empty] == 0).all()
+    # backward (incl. gradients into weights and z)
+    g_rgb, g_d, g_w = torch.randn(r, 3, generator=g), torch.randn(r, generator=g), torch.randn(int(offsets[-1]), generator=g)
+    torch.autograd.backward([rgb, depth, w], [g_rgb.to(dev), g_d.to(dev), g_w.to(dev)])
+    dx, dz = xd.grad.cpu(), zd.grad.cpu()
+    for k, rays, idx in O.bucketed(offsets):
+        if k == 0:
+            continue
+        zz, xx = z[idx].unsqueeze(0), x[idx].unsqueeze(0)
+        wdx, _ = O.composite_grads(zz, xx, g_rgb[rays].unsqueeze(0), g_d[rays].reshape(1, -1, 1), g_w[idx].reshape(1, -1, k, 1), True)
+        assert_close(dx[idx][..., :3], wdx[0][..., :3], what=f"d_rgb k={k}")
+        assert_close(dx[idx][..., 3][:, :-1], wdx[0][..., 3][:, :-1], what=f"d_sigma k={k}")
+        assert_close(dx[idx][..., 3][:, -1] / 1e10, wdx[0][..., 3][:, -1] / 1e10, what=f"d_sigma last k={k}")
+        _, wdz = O.composite_grads(zz.double(), xx.double(), g_rgb[rays].unsqueeze(0).double(), g_d[rays].reshape(1, -1, 1).double(),
+                                   g_w[idx].reshape(1, -1, k, 1).double(), True, want_dz=True)
+        scale = wdz.abs().amax(-1, keepdim=True).clamp_min(1.0)
+        assert_close(dz[idx] / scale[0], (wdz[0] / scale[0]).float(), rtol=1e-5, atol=2e-5, what=f"d_z k={k}")
+
+
+def test_packed_importance_and_merge(dev):
+    from avr_b200 import ops
+    r = 2000
+    counts, offsets, g = _ragged(r, 8, 128, seed=1, zero_some=False)
+    fine_counts = counts // 2
+    fine_offsets = torch.zeros(r + 1, dtype=torch.int64)
+    fine_offsets[1:] = torch.cumsum(fine_counts, 0)
+    near, far, u, _ = _packed_inputs(counts, offsets, g)
+    zc = ops.coarse_sample_packed(near.to(dev), far.to(dev), u.to(dev), offsets.to(dev)).cpu()
+    w = torch.rand(int(offsets[-1]), generator=g) ** 6
+    sf = int(fine_offsets[-1])
+    uf, uf2 = torch.rand(sf, generator=g), torch.rand(sf, generator=g)
+    zf, zs = ops.importance_sample_packed(w.to(dev), zc.to(dev), near.to(dev), far.to(dev), uf.to(dev), uf2.to(dev),
+                                          offsets.to(dev), fine_offsets.to(dev), 128, 64)
+    zf, zs = zf.cpu(), zs.cpu()
+    out_offsets = offsets + fine_offsets
+    mismatched = 0
+    for k, rays, idx in O.bucketed(offsets):
+        n = k // 2
+        fidx = fine_offsets[rays].unsqueeze(-1) + torch.arange(n)
+        oidx = out_offsets[rays].unsqueeze(-1) + torch.arange(k + n)
+        want, cdf, bins = O.fine_z(near[rays].unsqueeze(0), far[rays].unsqueeze(0), w[idx].unsqueeze(0),
+                                   uf[fidx].unsqueeze(0), uf2[fidx].unsqueeze(0), return_aux=True)
+        same = zf[fidx] == want[0]
+        mismatched += int((~same).sum())
+        # the merge is the exact sort of the kernel's own samples
+        assert torch.equal(zs[oidx], torch.sort(torch.cat([zc[idx], zf[fidx]], -1), -1).values), k
+    assert mismatched <= max(2, int(2e-5 * sf))          # rare one-bin flips from the CDF's summation order
+
+
+def test_packed_full_size_smoke(dev):
+    """2^22 rays with 8..256 samples would need ~11 GB of rgbs; this runs 2^18 rays end to end
+    (coarse -> composite -> importance -> merge -> composite) and checks invariants."""
+    from avr_b200 import ops
+    r = 1 << 18
+    g = torch.Generator(device=dev).manual_seed(0)
+    counts = torch.randint(8, 257, (r,), device=dev, generator=g)
+    offsets = torch.zeros(r + 1, dtype=torch.int64, device=dev)
+    offsets[1:] = torch.cumsum(counts, 0)
+    s = int(offsets[-1])
+    d = 0.9 + 0.8 * torch.rand(r, device=dev, generator=g)
+    near, far = d - 0.15, d + 0.15
+    z = ops.coarse_sample_packed(near, far, torch.rand(s, device=dev, generator=g), offsets)
+    x = torch.cat([torch.sigmoid(torch.randn(s, 3, device=dev, generator=g)),
+                   torch.relu(torch.randn(s, 1, device=dev, generator=g)) * 30], -1)
+    rgb, depth, w = ops.composite_packed(x, z, offsets, True, 1.8)
+    seg = torch.repeat_interleave(torch.arange(r, device=dev), counts)
+    acc = torch.zeros(r, device=dev).index_add_(0, seg, w)
+    assert (w >= 0).all() and acc.max() <= 1 + 1e-6
+    fine_offsets = torch.zeros(r + 1, dtype=torch.int64, device=dev)
+    fine_offsets[1:] = torch.cumsum(counts // 2, 0)
+    sf = int(fine_offsets[-1])
+    zf, zs = ops.importance_sample_packed(w, z, near, far, torch.rand(sf, device=dev, generator=g),
+                                          torch.rand(sf, device=dev, generator=g), offsets, fine_offsets, 256, 128)
+    seg2 = torch.repeat_interleave(torch.arange(r, device=dev), counts + counts // 2)
+    same_ray = seg2[1:] == seg2[:-1]
+    assert (zs[1:][same_ray] >= zs[:-1][same_ray]).all()
+    assert abs(zs.double().sum().item() - (z.double().sum() + zf.double().sum()).item()) < 1e-3

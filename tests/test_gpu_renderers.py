@@ -1,0 +1,87 @@
+"""The drop-in renderers against fixtures produced by the reference's own classes."""
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+from fields import TinyFeatureField, TinyField
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["default", "small"])
+def test_volume_renderer_golden(name, dev):
+    import avr_b200
+    g = load_golden(f"volume_renderer_{name}")
+    kc, nf, nd, wb = [int(v) for v in g["cfg"]]
+    field = TinyField(seed=2).to(dev)
+    ren = avr_b200.VolumeRenderer(0.8, 1.8, kc, nf, nd, 0.01, white_back=bool(wb))
+    assert list(ren.state_dict().keys()) == []
+    draws = tuple(g[k].to(dev) for k in ("u_coarse", "u_cdf", "u_bin", "normals"))
+    rc, rf, d0, d1 = ren(g["cam2world"].to(dev), g["intrinsics"].to(dev), g["x_pix"].to(dev), field, draws=draws)
+    assert d0 is d1 and d0.shape == g["ref_depth"].shape
+    assert_close(rc, g["ref_rgb_coarse"], rtol=1e-5, atol=2e-6, what="rgb_coarse")
+    # the fine pass sits behind a discontinuous resampling step (a CDF bin can flip on a 1-ulp
+    # difference of the field's output between CPU and GPU), so allow isolated outliers
+    for got, ref, what in ((rf, g["ref_rgb_fine"], "rgb_fine"), (d0, g["ref_depth"], "depth")):
+        err = (got.cpu() - ref).abs()
+        assert (err <= 2e-5 + 1e-4 * ref.abs()).float().mean() >= 0.97, what
+        assert err.max() < 2e-2, what
+    loss = ((rc - 0.3) ** 2).mean() + ((rf - 0.3) ** 2).mean() + 0.1 * d0.mean()
+    assert abs(loss.item() - g["ref_loss"].item()) < 1e-4
+    loss.backward()
+    for i, p in enumerate(field.parameters()):
+        ref = g[f"{name}_ref_grad_{i}"]
+        scale = ref.abs().max().item()
+        assert_close(p.grad.cpu() / scale, ref / scale, rtol=1e-3, atol=2e-3, what=f"field grad {i}")
+
+
+def test_volume_renderer_seeded_draws_and_from_conf(dev):
+    import avr_b200
+    from ref_shim import Conf
+    g = load_golden("volume_renderer_default")
+    ren = avr_b200.VolumeRenderer.from_conf(Conf(near=0.8, far=1.8, n_coarse=64, n_fine=32, n_fine_depth=16,
+                                                 depth_std=0.01, white_back=True))
+    assert (ren.n_coarse, ren.n_fine, ren.n_fine_depth) == (64, 32, 16)
+    dflt = avr_b200.VolumeRenderer.from_conf(Conf())
+    assert (dflt.n_coarse, dflt.n_fine, dflt.n_fine_depth, dflt.depth_std) == (32, 16, 8, 0.01)
+    field = TinyField(seed=2).to(dev)
+    args = (g["cam2world"].to(dev), g["intrinsics"].to(dev), g["x_pix"].to(dev), field)
+    with torch.no_grad():
+        torch.manual_seed(3)
+        a = ren(*args)
+        torch.manual_seed(3)
+        draws = (torch.rand(2, 64, 64, device=dev), torch.rand(2, 64, 16, device=dev),
+                 torch.rand(2, 64, 16, device=dev), torch.randn(2, 64, 16, device=dev))
+        b = ren(*args, draws=draws)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    with pytest.raises(avr_b200.AvrError):
+        ren(g["cam2world"], g["intrinsics"], g["x_pix"], TinyField(seed=2))
+
+
+def test_adaptive_renderer_golden(dev):
+    import avr_b200
+    g = load_golden("adaptive_renderer")
+    phi = TinyFeatureField(32, seed=4).to(dev)
+    ren = avr_b200.AdaptiveVolumeRenderer(32, raymarch_steps=3, epsilon=0.15, n_coarse=20, white_back=True)
+    state = {k[len("state_"):].replace("__", "."): v for k, v in g.items() if k.startswith("state_")}
+    assert sorted(state) == sorted(ren.state_dict().keys())      # checkpoints load unchanged
+    ren.load_state_dict(state)
+    ren = ren.to(dev)
+    rc, rgb, dc, depth = ren(g["cam2world"].to(dev), g["intrinsics"].to(dev), g["x_pix"].to(dev), phi,
+                             draws=(g["init_distance"].to(dev), g["u_coarse"].to(dev)))
+    assert rc.shape == (1, 48, 3) and dc.shape == (1, 48, 1) and depth.shape == (1, 48)
+    assert_close(rc, g["ref_rgb_coarse"], rtol=1e-4, atol=1e-5, what="rgb_coarse")
+    assert_close(dc, g["ref_depth_coarse"], rtol=1e-4, atol=1e-5, what="depth_coarse")
+    assert_close(rgb, g["ref_rgb"], rtol=1e-4, atol=2e-5, what="rgb")
+    assert_close(depth, g["ref_depth"], rtol=1e-4, atol=2e-5, what="depth")
+    loss = ((rgb - 0.3) ** 2).mean() + 0.1 * depth.mean() + ((rc - 0.2) ** 2).mean()
+    loss.backward()
+    for k, p in ren.named_parameters():
+        ref = g["ref_grad_" + k.replace(".", "__")]
+        scale = max(ref.abs().max().item(), 1e-6)
+        assert_close(p.grad.cpu() / scale, ref / scale, rtol=1e-3, atol=5e-3, what=f"grad {k}")
+    for i, p in enumerate(phi.parameters()):
+        ref = g[f"ref_phi_grad_{i}"]
+        scale = max(ref.abs().max().item(), 1e-6)
+        assert_close(p.grad.cpu() / scale, ref / scale, rtol=1e-3, atol=5e-3, what=f"phi grad {i}")
