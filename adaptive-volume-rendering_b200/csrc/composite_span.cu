@@ -15,31 +15,33 @@
 //     the same stage (w over z, d_rgbs over rgbs) and leave by bulk store.
 //   * Inside a tile each LANE owns L consecutive samples (a "run"; L is odd so the
 //     float4 and scalar shared-memory accesses of the 32 lanes hit distinct banks)
-//     and walks them sequentially in registers — ~30 instructions per sample and no
-//     shuffles.  Runs are stitched together with ONE segmented warp scan per tile
-//     over the per-lane aggregates (transmittance product + partial sums), which is
-//     the blocked form of the per-ray exclusive cumprod (renderers.py:90-93).
+//     and walks them sequentially in registers — no shuffles per sample.  Runs are
+//     stitched together with ONE segmented warp scan per tile over the per-lane
+//     aggregates (transmittance product + partial sums): the blocked form of the
+//     per-ray exclusive cumprod (renderers.py:90-93).
+//   * With K > L (every shipped configuration) a run holds at most one ray boundary,
+//     at a position that is fixed per lane for the whole launch.  The "simple" tile
+//     bodies below exploit that: straight-line code, two accumulator sets selected by
+//     a per-lane predicate, no per-sample branches.  K <= L takes the general bodies.
 //
 // Backward recomputes the transmittance (walk 1, also yields the reverse-scan
 // aggregates) and then walks each run back to front (walk 2) carrying
 //     Q_k = sum_{i>k} g_i alpha_i prod_{k<j<i} t_j ,   dL/dalpha_k = T_k (g_k - Q_k),
 // see composite_generic.cu for the derivation against torch's cumprod backward.
+#include <cstdlib>
+
 #include "avr_common.cuh"
 #include "kernels.h"
 
 namespace avr {
 
-constexpr int kSpanWarps = 4;  // warps per CTA
-
 template <int L>
 struct SpanCfg {
-  static constexpr int kStages = (L <= 9) ? 4 : 3;
   static constexpr int kTileSamples = 32 * L;
   static constexpr int kRgbsBytes = kTileSamples * 16;
   static constexpr int kZBytes = kTileSamples * 4;
-  static constexpr int kStageBytes = kRgbsBytes + kZBytes;  // multiple of 128
-  static constexpr int kWarpBytes = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kSpanWarps * kWarpBytes + kSpanWarps * kStages * 8;
+  // +16: the lane that owns the last sample reads one z past the tile (value unused)
+  static constexpr int kStageBytes = kRgbsBytes + kZBytes + 16;
 };
 
 struct SpanArgs {
@@ -54,17 +56,19 @@ struct SpanArgs {
   int64_t n_tiles;
   int K;
   int rays_per_tile;
+  int tail_rays;          // rays in the last tile (== rays_per_tile when it is full)
   int white_back;
   float infinity;
 };
 
-// Static description of a lane's run (identical for every tile of a dense launch).
+// A lane's run inside a tile (identical for every full tile of a launch).
 struct Run {
   int s0;         // first sample (tile-relative)
-  int nvalid;     // samples in the run (0..L)
+  int nvalid;     // samples of the run that exist (0..L)
   int k0;         // position of the first sample inside its ray
   int ray0;       // tile-relative ray of the first sample
   int carry_len;  // leading samples that belong to a ray started in an earlier lane
+  int end_pos;    // simple bodies: run index of the sample that ends a ray, or -1
 };
 
 template <int L>
@@ -77,6 +81,8 @@ __device__ __forceinline__ Run make_run(int lane, int K, int n_s) {
   r.ray0 = r.s0 / K;
   int to_head = (r.k0 == 0) ? 0 : K - r.k0;
   r.carry_len = to_head < r.nvalid ? to_head : r.nvalid;
+  int e = K - 1 - r.k0;
+  r.end_pos = e < r.nvalid ? e : -1;
   return r;
 }
 
@@ -152,13 +158,358 @@ __device__ __forceinline__ float scan_rev_exclusive(int lane, float A, float B) 
   return lane == 31 ? 0.f : q;
 }
 
-// ---- the per-warp tile pipeline ---------------------------------------------------
+__device__ __forceinline__ void store_ray(const SpanArgs& a, int64_t ray, const Sums& t) {
+  const float bg = a.white_back ? 1.0f - t.a : 0.f;
+  float* o3 = a.rgb + ray * 3;
+  o3[0] = t.r + bg;
+  o3[1] = t.g + bg;
+  o3[2] = t.b + bg;
+  a.depth[ray] = t.d;
+}
+
+struct RayGrad {
+  float r, g, b, d, bg;  // g_rgb, g_depth, and the white-background term sum(g_rgb)
+};
+__device__ __forceinline__ RayGrad load_ray_grad(const SpanArgs& a, int64_t ray) {
+  RayGrad g{0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.g_rgb) {
+    g.r = a.g_rgb[ray * 3 + 0];
+    g.g = a.g_rgb[ray * 3 + 1];
+    g.b = a.g_rgb[ray * 3 + 2];
+  }
+  if (a.g_depth) g.d = a.g_depth[ray];
+  g.bg = a.white_back ? (g.r + g.g + g.b) : 0.f;
+  return g;
+}
+
+// =====================================================================================
+// Tile bodies.  rg / zs point at the lane's OWN first sample inside the stage.
+// =====================================================================================
+
+// ---- forward, K > L: at most one ray end per run, at run index p -----------------------
+// Samples [0..p] (segment A) close the ray that contains the run's first sample; samples
+// after p (segment B) open the next ray.  Without an end the whole run is segment B.
+// Samples past the tile's end (idle lanes / partial tail tile) come after a ray end, so
+// whatever stale shared memory they read only reaches aggregates nobody consumes.
+template <int L, bool kWriteW>
+__device__ __forceinline__ void fwd_tile_simple(const SpanArgs& a, const Run& run, const float4* rg, float* zs,
+                                                int64_t ray_base, int lane) {
+  const int p = run.end_pos;
+  float wl[L];
+  float Tl = 1.0f;
+  Sums A = zero_sums(), B = zero_sums();
+  float zk = zs[0];
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    const bool last = (j == p);
+    const bool in_a = (j <= p);
+    const float4 c = rg[j];
+    const float z_after = zs[j + 1];
+    const float zn = last ? a.infinity : z_after;
+    const float delta = last ? kLastDelta : zn - zk;
+    const Opacity o = opacity(c.w, delta);
+    const float w = o.alpha * Tl;
+    wl[j] = w;
+    if (in_a) {
+      A.r += w * c.x;
+      A.g += w * c.y;
+      A.b += w * c.z;
+      A.d += w * zn;
+      A.a += w;
+    } else {
+      B.r += w * c.x;
+      B.g += w * c.y;
+      B.b += w * c.z;
+      B.d += w * zn;
+      B.a += w;
+    }
+    Tl = last ? 1.0f : Tl * o.t;
+    zk = z_after;
+  }
+  const bool head0 = (run.k0 == 0);
+  float T_in = Tl;
+  Sums s_in = B;
+  scan_fwd_exclusive(lane, head0 || p >= 0 || run.nvalid == 0, T_in, s_in);
+  if (head0) {
+    T_in = 1.0f;
+    s_in = zero_sums();
+  }
+  if (p >= 0) {
+    Sums t;
+    t.r = s_in.r + T_in * A.r;
+    t.g = s_in.g + T_in * A.g;
+    t.b = s_in.b + T_in * A.b;
+    t.d = s_in.d + T_in * A.d;
+    t.a = s_in.a + T_in * A.a;
+    store_ray(a, ray_base + run.ray0, t);
+  }
+  if (kWriteW) {
+    __syncwarp();  // every lane has finished reading z from this stage
+#pragma unroll
+    for (int j = 0; j < L; ++j) zs[j] = (p < 0 || j <= p) ? wl[j] * T_in : wl[j];
+  }
+}
+
+// ---- forward, any K (several boundaries per run possible) ----------------------------
+template <int L, bool kWriteW>
+__device__ __forceinline__ void fwd_tile_general(const SpanArgs& a, const Run& run, const float4* rg, float* zs,
+                                                 int64_t ray_base, int lane) {
+  const int K = a.K;
+  float wl[L];
+  float Tl = 1.0f;
+  Sums s = zero_sums();
+  Sums first_seg = zero_sums();  // continuing ray's part, if that ray ends inside this run
+  int first_seg_ray = -1;
+  bool seen_head = false, closed = false;
+  int k = run.k0, ray = run.ray0;
+  float zk = zs[0];
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    if (j < run.nvalid) {
+      if (k == 0) seen_head = true;
+      const bool last = (k == K - 1);
+      const float4 c = rg[j];
+      const float z_after = zs[j + 1];
+      const float zn = last ? a.infinity : z_after;
+      const float delta = last ? kLastDelta : zn - zk;
+      const Opacity o = opacity(c.w, delta);
+      const float w = o.alpha * Tl;
+      wl[j] = w;
+      s.r += w * c.x;
+      s.g += w * c.y;
+      s.b += w * c.z;
+      s.d += w * zn;
+      s.a += w;
+      Tl *= o.t;
+      zk = z_after;
+      if (last) {
+        if (seen_head) {  // ray lies entirely inside this run: finished here
+          store_ray(a, ray_base + ray, s);
+        } else {
+          first_seg = s;
+          first_seg_ray = ray;
+        }
+        closed = true;
+        Tl = 1.0f;
+        s = zero_sums();
+        k = 0;
+        ++ray;
+      } else {
+        ++k;
+      }
+    } else {
+      wl[j] = 0.f;
+    }
+  }
+  float T_in = Tl;
+  Sums s_in = s;
+  scan_fwd_exclusive(lane, seen_head || closed || run.nvalid == 0, T_in, s_in);
+  if (first_seg_ray >= 0) {
+    Sums t;
+    t.r = s_in.r + T_in * first_seg.r;
+    t.g = s_in.g + T_in * first_seg.g;
+    t.b = s_in.b + T_in * first_seg.b;
+    t.d = s_in.d + T_in * first_seg.d;
+    t.a = s_in.a + T_in * first_seg.a;
+    store_ray(a, ray_base + first_seg_ray, t);
+  }
+  if (kWriteW) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      if (j < run.nvalid) zs[j] = (j < run.carry_len) ? wl[j] * T_in : wl[j];
+    }
+  }
+}
+
+// ---- backward, K > L -------------------------------------------------------------------
 template <int L>
+__device__ __forceinline__ void bwd_tile_simple(const SpanArgs& a, const Run& run, float4* rg, const float* zs,
+                                                const RayGrad& gA, const RayGrad& gB, int lane) {
+  const int p = run.end_pos;
+  // walk 1, front to back: cache e_j and the local transmittance before sample j; sum the
+  // first segment's weighted terms (they give the reverse-scan aggregate A)
+  float ej[L], Tj[L];
+  float Tl = 1.0f;
+  Sums s = zero_sums();
+  {
+    float zk = zs[0];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const bool last = (j == p);
+      const bool first_seg = (p < 0 || j <= p);
+      const float4 c = rg[j];
+      const float z_after = zs[j + 1];
+      const float zn = last ? a.infinity : z_after;
+      const float delta = last ? kLastDelta : zn - zk;
+      const Opacity o = opacity(c.w, delta);
+      ej[j] = o.e;
+      Tj[j] = Tl;
+      if (first_seg) {
+        const float w = o.alpha * Tl;
+        s.r += w * c.x;
+        s.g += w * c.y;
+        s.b += w * c.z;
+        s.d += w * zn;
+        s.a += w;
+      }
+      Tl = last ? 1.0f : Tl * o.t;
+      zk = z_after;
+    }
+  }
+  const bool head0 = (run.k0 == 0);
+  const bool idle = (run.nvalid == 0);
+  // reverse-scan element of this run: Q_left = A + B * Q_right
+  float A = gA.r * s.r + gA.g * s.g + gA.b * s.b + gA.d * s.d - gA.bg * s.a;
+  float Bm = Tl;
+  if (p >= 0 || idle) Bm = 0.f;
+  if (idle) A = 0.f;
+  float T_in = scan_fwd_exclusive_T(lane, head0 || p >= 0 || idle, Tl);
+  if (head0) T_in = 1.0f;
+  float Q = scan_rev_exclusive(lane, A, Bm);
+
+  // walk 2, back to front: final gradients, written over the rgbs stage in place
+  float zn = zs[L];
+#pragma unroll
+  for (int j = L - 1; j >= 0; --j) {
+    const bool last = (j == p);
+    const bool first_seg = (p < 0 || j <= p);
+    const float4 c = rg[j];
+    const float zk = zs[j];
+    if (last) {
+      Q = 0.f;
+      zn = a.infinity;
+    }
+    const float delta = last ? kLastDelta : zn - zk;
+    const float e = ej[j];
+    const float alpha = 1.0f - e;
+    const float t = (1.0f - alpha) + kTransEps;
+    const float T = first_seg ? Tj[j] * T_in : Tj[j];
+    const float gr = first_seg ? gA.r : gB.r;
+    const float gg = first_seg ? gA.g : gB.g;
+    const float gb = first_seg ? gA.b : gB.b;
+    const float gd = first_seg ? gA.d : gB.d;
+    const float gbg = first_seg ? gA.bg : gB.bg;
+    const float g = gr * c.x + gg * c.y + gb * c.z + gd * zn - gbg;
+    const float dalpha = T * (g - Q);
+    Q = g * alpha + t * Q;
+    const float dsd = dalpha * e;
+    const float w = alpha * T;
+    rg[j] = make_float4(w * gr, w * gg, w * gb, dsd * delta);
+    zn = zk;
+  }
+}
+
+// ---- backward, any K ----------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void bwd_tile_general(const SpanArgs& a, const Run& run, float4* rg, const float* zs,
+                                                 const RayGrad& gA, const RayGrad& gB, int64_t ray_base,
+                                                 int lane) {
+  const int K = a.K;
+  const int last_idx = run.nvalid - 1;  // run-relative
+  const int k_end = run.nvalid > 0 ? (run.s0 + last_idx) % K : 0;
+  const int ray_end = run.nvalid > 0 ? (run.s0 + last_idx) / K : 0;
+  float ej[L], Tj[L];
+  float Tl = 1.0f;
+  Sums s = zero_sums();
+  bool seen_head = false, closed = false;
+  float A = 0.f, Bm = 1.0f;
+  {
+    int k = run.k0;
+    float zk = zs[0];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      if (j < run.nvalid) {
+        if (k == 0) seen_head = true;
+        const bool last = (k == K - 1);
+        const float4 c = rg[j];
+        const float z_after = zs[j + 1];
+        const float zn = last ? a.infinity : z_after;
+        const float delta = last ? kLastDelta : zn - zk;
+        const Opacity o = opacity(c.w, delta);
+        ej[j] = o.e;
+        Tj[j] = Tl;
+        if (!closed) {
+          const float w = o.alpha * Tl;
+          s.r += w * c.x;
+          s.g += w * c.y;
+          s.b += w * c.z;
+          s.d += w * zn;
+          s.a += w;
+        }
+        Tl *= o.t;
+        zk = z_after;
+        if (last) {
+          if (!closed) {
+            Bm = 0.f;  // a ray ends inside the run: nothing from the right reaches the left
+            closed = true;
+          }
+          Tl = 1.0f;
+          k = 0;
+        } else {
+          ++k;
+        }
+      } else {
+        ej[j] = 1.0f;
+        Tj[j] = 1.0f;
+      }
+    }
+  }
+  if (run.nvalid == 0) {
+    Bm = 0.f;
+  } else {
+    A = gA.r * s.r + gA.g * s.g + gA.b * s.b + gA.d * s.d - gA.bg * s.a;
+    if (!closed) Bm = Tl;  // whole run is one segment: Tl is its transmittance product
+  }
+  const float T_in = scan_fwd_exclusive_T(lane, seen_head || closed || run.nvalid == 0, Tl);
+  const float Q_in = scan_rev_exclusive(lane, A, Bm);
+  {
+    int k = k_end, ray = ray_end;
+    RayGrad g = gB;
+    float Q = Q_in;
+    float zn = run.nvalid > 0 ? zs[last_idx + 1] : 0.f;
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) {
+      if (j < run.nvalid) {
+        const bool last = (k == K - 1);
+        if (last) {
+          Q = 0.f;
+          zn = a.infinity;
+        }
+        const float4 c = rg[j];
+        const float zk = zs[j];
+        const float delta = last ? kLastDelta : zn - zk;
+        const float e = ej[j];
+        const float alpha = 1.0f - e;
+        const float t = (1.0f - alpha) + kTransEps;
+        const float T = (j < run.carry_len) ? Tj[j] * T_in : Tj[j];
+        const float gs = g.r * c.x + g.g * c.y + g.b * c.z + g.d * zn - g.bg;
+        const float dalpha = T * (gs - Q);
+        Q = gs * alpha + t * Q;
+        const float dsd = dalpha * e;
+        const float w = alpha * T;
+        rg[j] = make_float4(w * g.r, w * g.g, w * g.b, dsd * delta);
+        zn = zk;
+        if (k == 0) {
+          k = K - 1;
+          --ray;
+          if (j > 0) g = (ray == run.ray0) ? gA : load_ray_grad(a, ray_base + ray);
+        } else {
+          --k;
+        }
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// Kernels: per-warp tile pipeline around the bodies.
+// =====================================================================================
+template <int L, int NS>
 struct WarpPipe {
   using Cfg = SpanCfg<L>;
   unsigned char* base;  // this warp's stages
   uint64_t* bars;       // this warp's mbarriers
-  int lane;
 
   __device__ __forceinline__ float4* rgbs_stage(int st) const {
     return reinterpret_cast<float4*>(base + st * Cfg::kStageBytes);
@@ -166,48 +517,50 @@ struct WarpPipe {
   __device__ __forceinline__ float* z_stage(int st) const {
     return reinterpret_cast<float*>(base + st * Cfg::kStageBytes + Cfg::kRgbsBytes);
   }
-  __device__ __forceinline__ void init(unsigned char* smem, int warp, int lane_) {
-    lane = lane_;
-    base = smem + warp * Cfg::kWarpBytes;
-    bars = reinterpret_cast<uint64_t*>(smem + kSpanWarps * Cfg::kWarpBytes) + warp * Cfg::kStages;
+  __device__ __forceinline__ void init(unsigned char* smem, int warps, int warp, int lane) {
+    base = smem + warp * (NS * Cfg::kStageBytes);
+    bars = reinterpret_cast<uint64_t*>(smem + warps * (NS * Cfg::kStageBytes)) + warp * NS;
     if (lane == 0) {
 #pragma unroll
-      for (int s = 0; s < Cfg::kStages; ++s) mbar_init(&bars[s], 1);
+      for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
       fence_mbar_init();
     }
     __syncwarp();
   }
   // lane 0 only
-  __device__ __forceinline__ void load(int st, const float* rgbs, const float* z, int64_t tile, int n_s) {
+  __device__ __forceinline__ void load(int st, const SpanArgs& a, int64_t tile, int n_s_full, int n_s) {
     const uint32_t rb = (uint32_t)n_s * 16u, zb = (uint32_t)n_s * 4u;
     mbar_expect_tx(&bars[st], rb + zb);
-    bulk_g2s(rgbs_stage(st), rgbs + tile * (int64_t)n_s * 4, rb, &bars[st]);
-    bulk_g2s(z_stage(st), z + tile * (int64_t)n_s, zb, &bars[st]);
+    bulk_g2s(rgbs_stage(st), a.rgbs + tile * (int64_t)n_s_full * 4, rb, &bars[st]);
+    bulk_g2s(z_stage(st), a.z + tile * (int64_t)n_s_full, zb, &bars[st]);
   }
 };
 
-template <int L, bool kWriteW>
-__global__ void __launch_bounds__(kSpanWarps * 32)
+template <int L, int NS, bool kSimple, bool kWriteW>
+__global__ void __launch_bounds__(256)
 composite_fwd_span_kernel(const SpanArgs a) {
-  using Cfg = SpanCfg<L>;
-  constexpr int NS = Cfg::kStages;
   extern __shared__ __align__(128) unsigned char smem[];
+  const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpPipe<L> pipe;
-  pipe.init(smem, warp, lane);
+  WarpPipe<L, NS> pipe;
+  pipe.init(smem, warps, warp, lane);
 
   const int K = a.K;
   const int n_s = a.rays_per_tile * K;
-  const Run run = make_run<L>(lane, K, n_s);
+  const int n_s_tail = a.tail_rays * K;
+  const Run run_full = make_run<L>(lane, K, n_s);
 
-  const int64_t first = (int64_t)blockIdx.x * kSpanWarps + warp;
-  const int64_t stride = (int64_t)gridDim.x * kSpanWarps;
+  const int64_t first = (int64_t)blockIdx.x * warps + warp;
+  const int64_t stride = (int64_t)gridDim.x * warps;
   const int64_t n_my = first < a.n_tiles ? (a.n_tiles - first + stride - 1) / stride : 0;
+  auto samples_of = [&](int64_t tile) { return tile == a.n_tiles - 1 ? n_s_tail : n_s; };
 
   if (lane == 0) {
-    for (int p = 0; p < NS - 2 && p < n_my; ++p) pipe.load(p, a.rgbs, a.z, first + p * stride, n_s);
+    for (int p = 0; p < NS - 2 && p < n_my; ++p) {
+      const int64_t t = first + p * stride;
+      pipe.load(p, a, t, n_s, samples_of(t));
+    }
   }
-
   for (int64_t i = 0; i < n_my; ++i) {
     const int st = (int)(i % NS);
     const int64_t tile = first + i * stride;
@@ -215,99 +568,28 @@ composite_fwd_span_kernel(const SpanArgs a) {
       const int64_t pf = i + NS - 2;
       if (lane == 0 && pf < n_my) {
         if (kWriteW) bulk_wait_read<1>();  // the store that last read stage pf%NS (tile i-2) is done
-        pipe.load((int)(pf % NS), a.rgbs, a.z, first + pf * stride, n_s);
+        const int64_t t = first + pf * stride;
+        pipe.load((int)(pf % NS), a, t, n_s, samples_of(t));
       }
     }
+    const int n_cur = samples_of(tile);
+    Run run = run_full;
+    if (n_cur != n_s) run = make_run<L>(lane, K, n_cur);  // partial last tile (warp-uniform branch)
     mbar_wait(&pipe.bars[st], (uint32_t)((i / NS) & 1));
 
-    const float4* rg = pipe.rgbs_stage(st);
-    float* zs = pipe.z_stage(st);
+    const float4* rg = pipe.rgbs_stage(st) + run.s0;
+    float* zs = pipe.z_stage(st) + run.s0;
     const int64_t ray_base = tile * a.rays_per_tile;
-
-    // ---- walk the run front to back with a local transmittance starting at 1
-    float wl[L];
-    float Tl = 1.0f;
-    Sums s = zero_sums();
-    Sums first_seg = zero_sums();  // continuing ray's part, if that ray ends inside this run
-    int first_seg_ray = -1;
-    bool seen_head = false, closed = false;
-    int k = run.k0, ray = run.ray0;
-    float zk = run.nvalid > 0 ? zs[run.s0] : 0.f;
-#pragma unroll
-    for (int j = 0; j < L; ++j) {
-      if (j < run.nvalid) {
-        const int si = run.s0 + j;
-        if (k == 0) seen_head = true;
-        const bool last = (k == K - 1);
-        const float4 c = rg[si];
-        const float z_after = (si + 1 < n_s) ? zs[si + 1] : 0.f;
-        const float zn = last ? a.infinity : z_after;
-        const float delta = last ? kLastDelta : zn - zk;
-        const Opacity o = opacity(c.w, delta);
-        const float w = o.alpha * Tl;
-        wl[j] = w;
-        s.r += w * c.x;
-        s.g += w * c.y;
-        s.b += w * c.z;
-        s.d += w * zn;
-        s.a += w;
-        Tl *= o.t;
-        zk = z_after;
-        if (last) {
-          if (seen_head) {  // ray lies entirely inside this run: finished here
-            const float bg = a.white_back ? 1.0f - s.a : 0.f;
-            float* o3 = a.rgb + (ray_base + ray) * 3;
-            o3[0] = s.r + bg;
-            o3[1] = s.g + bg;
-            o3[2] = s.b + bg;
-            a.depth[ray_base + ray] = s.d;
-          } else {
-            first_seg = s;
-            first_seg_ray = ray;
-          }
-          closed = true;
-          Tl = 1.0f;
-          s = zero_sums();
-          k = 0;
-          ++ray;
-        } else {
-          ++k;
-        }
-      } else {
-        wl[j] = 0.f;
-      }
+    if (kSimple) {
+      fwd_tile_simple<L, kWriteW>(a, run, rg, zs, ray_base, lane);
+    } else {
+      fwd_tile_general<L, kWriteW>(a, run, rg, zs, ray_base, lane);
     }
-
-    // ---- stitch the runs: carry = aggregate of the open ray over the lanes before this one
-    float T_in = Tl;
-    Sums s_in = s;
-    scan_fwd_exclusive(lane, seen_head || closed || run.nvalid == 0, T_in, s_in);
-
-    if (first_seg_ray >= 0) {
-      Sums t;
-      t.r = s_in.r + T_in * first_seg.r;
-      t.g = s_in.g + T_in * first_seg.g;
-      t.b = s_in.b + T_in * first_seg.b;
-      t.d = s_in.d + T_in * first_seg.d;
-      t.a = s_in.a + T_in * first_seg.a;
-      const float bg = a.white_back ? 1.0f - t.a : 0.f;
-      float* o3 = a.rgb + (ray_base + first_seg_ray) * 3;
-      o3[0] = t.r + bg;
-      o3[1] = t.g + bg;
-      o3[2] = t.b + bg;
-      a.depth[ray_base + first_seg_ray] = t.d;
-    }
-
     if (kWriteW) {
-      __syncwarp();  // every lane has finished reading z from this stage
-#pragma unroll
-      for (int j = 0; j < L; ++j) {
-        if (j < run.nvalid) zs[run.s0 + j] = (j < run.carry_len) ? wl[j] * T_in : wl[j];
-      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        bulk_s2g(a.w + tile * (int64_t)n_s, zs, (uint32_t)n_s * 4u);
+        bulk_s2g(a.w + tile * (int64_t)n_s, pipe.z_stage(st), (uint32_t)n_cur * 4u);
         bulk_commit();
       }
     } else {
@@ -317,31 +599,31 @@ composite_fwd_span_kernel(const SpanArgs a) {
   if (kWriteW && lane == 0) bulk_wait_all<0>();
 }
 
-template <int L>
-__global__ void __launch_bounds__(kSpanWarps * 32)
+template <int L, int NS, bool kSimple>
+__global__ void __launch_bounds__(256)
 composite_bwd_span_kernel(const SpanArgs a) {
-  using Cfg = SpanCfg<L>;
-  constexpr int NS = Cfg::kStages;
   extern __shared__ __align__(128) unsigned char smem[];
+  const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpPipe<L> pipe;
-  pipe.init(smem, warp, lane);
+  WarpPipe<L, NS> pipe;
+  pipe.init(smem, warps, warp, lane);
 
   const int K = a.K;
   const int n_s = a.rays_per_tile * K;
-  const Run run = make_run<L>(lane, K, n_s);
-  const int last_idx = run.s0 + run.nvalid - 1;  // tile-relative, valid only if nvalid > 0
-  const int k_end = run.nvalid > 0 ? last_idx % K : 0;
-  const int ray_end = run.nvalid > 0 ? last_idx / K : 0;
+  const int n_s_tail = a.tail_rays * K;
+  const Run run_full = make_run<L>(lane, K, n_s);
 
-  const int64_t first = (int64_t)blockIdx.x * kSpanWarps + warp;
-  const int64_t stride = (int64_t)gridDim.x * kSpanWarps;
+  const int64_t first = (int64_t)blockIdx.x * warps + warp;
+  const int64_t stride = (int64_t)gridDim.x * warps;
   const int64_t n_my = first < a.n_tiles ? (a.n_tiles - first + stride - 1) / stride : 0;
+  auto samples_of = [&](int64_t tile) { return tile == a.n_tiles - 1 ? n_s_tail : n_s; };
 
   if (lane == 0) {
-    for (int p = 0; p < NS - 2 && p < n_my; ++p) pipe.load(p, a.rgbs, a.z, first + p * stride, n_s);
+    for (int p = 0; p < NS - 2 && p < n_my; ++p) {
+      const int64_t t = first + p * stride;
+      pipe.load(p, a, t, n_s, samples_of(t));
+    }
   }
-
   for (int64_t i = 0; i < n_my; ++i) {
     const int st = (int)(i % NS);
     const int64_t tile = first + i * stride;
@@ -349,154 +631,35 @@ composite_bwd_span_kernel(const SpanArgs a) {
       const int64_t pf = i + NS - 2;
       if (lane == 0 && pf < n_my) {
         bulk_wait_read<1>();
-        pipe.load((int)(pf % NS), a.rgbs, a.z, first + pf * stride, n_s);
+        const int64_t t = first + pf * stride;
+        pipe.load((int)(pf % NS), a, t, n_s, samples_of(t));
       }
     }
+    const int n_cur = samples_of(tile);
+    Run run = run_full;
+    if (n_cur != n_s) run = make_run<L>(lane, K, n_cur);
     const int64_t ray_base = tile * a.rays_per_tile;
 
     // upstream gradients of the first and last ray this run touches (issued before the
-    // wait so their latency hides behind the tile load / walk 1)
-    float gA[4] = {0.f, 0.f, 0.f, 0.f}, gB[4] = {0.f, 0.f, 0.f, 0.f};
+    // wait so their latency hides behind the tile load)
+    RayGrad gA{0.f, 0.f, 0.f, 0.f, 0.f}, gB{0.f, 0.f, 0.f, 0.f, 0.f};
     if (run.nvalid > 0) {
-      const int64_t ra = ray_base + run.ray0, rb = ray_base + ray_end;
-      if (a.g_rgb) {
-        gA[0] = a.g_rgb[ra * 3 + 0];
-        gA[1] = a.g_rgb[ra * 3 + 1];
-        gA[2] = a.g_rgb[ra * 3 + 2];
-        gB[0] = a.g_rgb[rb * 3 + 0];
-        gB[1] = a.g_rgb[rb * 3 + 1];
-        gB[2] = a.g_rgb[rb * 3 + 2];
-      }
-      if (a.g_depth) {
-        gA[3] = a.g_depth[ra];
-        gB[3] = a.g_depth[rb];
-      }
+      gA = load_ray_grad(a, ray_base + run.ray0);
+      const int ray_end = (run.s0 + run.nvalid - 1) / K;
+      gB = (ray_end != run.ray0) ? load_ray_grad(a, ray_base + ray_end) : gA;
     }
-
     mbar_wait(&pipe.bars[st], (uint32_t)((i / NS) & 1));
-    float4* rg = pipe.rgbs_stage(st);
-    const float* zs = pipe.z_stage(st);
-
-    // ---- walk 1, front to back: cache e_j and the local transmittance before sample j;
-    // accumulate the first segment's weighted sums (the part of the run that belongs to
-    // the ray entering from the left) — they give the reverse-scan aggregate A.
-    float ej[L], Tj[L];
-    float Tl = 1.0f;
-    Sums s = zero_sums();
-    bool seen_head = false, closed = false;
-    float A = 0.f, B = 1.0f;
-    {
-      int k = run.k0;
-      float zk = run.nvalid > 0 ? zs[run.s0] : 0.f;
-#pragma unroll
-      for (int j = 0; j < L; ++j) {
-        if (j < run.nvalid) {
-          const int si = run.s0 + j;
-          if (k == 0) seen_head = true;
-          const bool last = (k == K - 1);
-          const float4 c = rg[si];
-          const float z_after = (si + 1 < n_s) ? zs[si + 1] : 0.f;
-          const float zn = last ? a.infinity : z_after;
-          const float delta = last ? kLastDelta : zn - zk;
-          const Opacity o = opacity(c.w, delta);
-          ej[j] = o.e;
-          Tj[j] = Tl;
-          if (!closed) {
-            const float w = o.alpha * Tl;
-            s.r += w * c.x;
-            s.g += w * c.y;
-            s.b += w * c.z;
-            s.d += w * zn;
-            s.a += w;
-          }
-          Tl *= o.t;
-          zk = z_after;
-          if (last) {
-            if (!closed) {
-              B = 0.f;  // a ray ends inside the run: nothing from the right reaches the left
-              closed = true;
-            }
-            Tl = 1.0f;
-            k = 0;
-          } else {
-            ++k;
-          }
-        } else {
-          ej[j] = 1.0f;
-          Tj[j] = 1.0f;
-        }
-      }
-    }
-    if (run.nvalid == 0) {
-      B = 0.f;
+    float4* rg = pipe.rgbs_stage(st) + run.s0;
+    const float* zs = pipe.z_stage(st) + run.s0;
+    if (kSimple) {
+      bwd_tile_simple<L>(a, run, rg, zs, gA, gB, lane);
     } else {
-      // A = sum over the first segment of g_j * (alpha_j * Tlocal_j), g_j linear in the ray's grads
-      const float gbg = a.white_back ? (gA[0] + gA[1] + gA[2]) : 0.f;
-      A = gA[0] * s.r + gA[1] * s.g + gA[2] * s.b + gA[3] * s.d - gbg * s.a;
-      if (!closed) B = Tl;  // whole run is one segment: Tl is its transmittance product
-    }
-    const float T_in = scan_fwd_exclusive_T(lane, seen_head || closed || run.nvalid == 0, Tl);
-    const float Q_in = scan_rev_exclusive(lane, A, B);
-
-    // ---- walk 2, back to front: final gradients, written over the rgbs stage in place
-    {
-      int k = k_end, ray = ray_end;
-      float gr = gB[0], gg = gB[1], gb = gB[2], gd = gB[3];
-      float gbg = a.white_back ? (gr + gg + gb) : 0.f;
-      float Q = Q_in;
-      float zn = 0.f;
-      if (run.nvalid > 0 && last_idx + 1 < n_s) zn = zs[last_idx + 1];
-#pragma unroll
-      for (int j = L - 1; j >= 0; --j) {
-        if (j < run.nvalid) {
-          const int si = run.s0 + j;
-          const bool last = (k == K - 1);
-          if (last) {
-            Q = 0.f;
-            zn = a.infinity;
-          }
-          const float4 c = rg[si];
-          const float zk = zs[si];
-          const float delta = last ? kLastDelta : zn - zk;
-          const float e = ej[j];
-          const float alpha = 1.0f - e;
-          const float t = (1.0f - alpha) + kTransEps;
-          const float T = (j < run.carry_len) ? Tj[j] * T_in : Tj[j];
-          const float g = gr * c.x + gg * c.y + gb * c.z + gd * zn - gbg;
-          const float dalpha = T * (g - Q);
-          Q = g * alpha + t * Q;
-          const float dsd = dalpha * e;
-          const float w = alpha * T;
-          rg[si] = make_float4(w * gr, w * gg, w * gb, dsd * delta);
-          zn = zk;
-          if (k == 0) {
-            k = K - 1;
-            --ray;
-            if (j > 0) {  // the next (earlier) sample belongs to the previous ray
-              if (ray == run.ray0) {
-                gr = gA[0];
-                gg = gA[1];
-                gb = gA[2];
-                gd = gA[3];
-              } else {
-                const int64_t rr = ray_base + ray;
-                gr = a.g_rgb ? a.g_rgb[rr * 3 + 0] : 0.f;
-                gg = a.g_rgb ? a.g_rgb[rr * 3 + 1] : 0.f;
-                gb = a.g_rgb ? a.g_rgb[rr * 3 + 2] : 0.f;
-                gd = a.g_depth ? a.g_depth[rr] : 0.f;
-              }
-              gbg = a.white_back ? (gr + gg + gb) : 0.f;
-            }
-          } else {
-            --k;
-          }
-        }
-      }
+      bwd_tile_general<L>(a, run, rg, zs, gA, gB, ray_base, lane);
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      bulk_s2g(a.d_rgbs + tile * (int64_t)n_s * 4, rg, (uint32_t)n_s * 16u);
+      bulk_s2g(a.d_rgbs + tile * (int64_t)n_s * 4, pipe.rgbs_stage(st), (uint32_t)n_cur * 16u);
       bulk_commit();
     }
   }
@@ -506,19 +669,38 @@ composite_bwd_span_kernel(const SpanArgs a) {
 // ---- host side ----------------------------------------------------------------------
 static const int kLs[] = {5, 7, 9, 11, 13};
 
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// Tuning knobs (experiments only): AVR_SPAN_L forces the samples-per-lane, AVR_SPAN_STAGES
+// (3|4) the ring depth, AVR_SPAN_WARPS (1..8) the warps per CTA.
+static int stages_for(int L) {
+  int s = env_int("AVR_SPAN_STAGES", 0);
+  if (s == 3 || s == 4) return s;
+  return L <= 9 ? 4 : 3;
+}
+static int warps_per_cta() {
+  int w = env_int("AVR_SPAN_WARPS", 4);
+  return w < 1 ? 1 : (w > 8 ? 8 : w);
+}
+
 bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan) {
   if (K < 1 || R < 1) return false;
   if (!aligned16(rgbs) || !aligned16(z)) return false;
+  const int forced = env_int("AVR_SPAN_L", 0);
   int best_L = 0, best_nr = 0;
   double best_util = 0.0;
   for (int L : kLs) {
+    if (forced && L != forced) continue;
+    if (K <= L && L != 5) continue;  // the general (multi-boundary) bodies are built for L = 5 only
     int cap = 32 * L;
     int nr = cap / K;
     // tile byte counts must be multiples of 16 for the bulk copies: (nr*K) % 4 == 0
     while (nr > 0 && ((int64_t)nr * K) % 4 != 0) --nr;
     if (nr <= 0) continue;
     double util = (double)nr * K / cap;
-    // prefer fuller tiles; on ties prefer the middle of the range (L = 9)
     if (util > best_util + 1e-9) {
       best_util = util;
       best_L = L;
@@ -531,100 +713,113 @@ bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan
   plan->L = best_L;
   plan->rays_per_tile = best_nr;
   plan->main_rays = tiles * best_nr;
+  // a partial last tile joins the span launch when its byte counts stay 16-byte multiples
+  const int64_t rem = R - plan->main_rays;
+  if (rem > 0 && (rem * K) % 4 == 0) plan->main_rays = R;
   return true;
 }
 
 template <typename KernelT>
-static int span_grid(KernelT kernel, int smem_bytes, int64_t n_tiles, int* grid) {
+static int span_launch(KernelT kernel, int stage_bytes, int stages, const SpanArgs& a, cudaStream_t stream) {
+  const int warps = warps_per_cta();
+  const int smem_bytes = warps * stages * stage_bytes + warps * stages * 8;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) {
     set_last_cuda_error(e);
+    (void)cudaGetLastError();
     return AVR_ERR_LAUNCH;
   }
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSpanWarps * 32, smem_bytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, warps * 32, smem_bytes);
   if (e != cudaSuccess || occ < 1) {
     set_last_cuda_error(e);
+    (void)cudaGetLastError();
     return AVR_ERR_LAUNCH;
   }
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int64_t want = (n_tiles + kSpanWarps - 1) / kSpanWarps;
-  int64_t cap = (int64_t)sms * occ;
-  *grid = (int)(want < cap ? want : cap);
-  return AVR_OK;
-}
-
-template <int L>
-static int fwd_span_L(const SpanArgs& a, bool write_w, cudaStream_t stream) {
-  using Cfg = SpanCfg<L>;
-  int grid = 0, rc;
-  if (write_w) {
-    if ((rc = span_grid(composite_fwd_span_kernel<L, true>, Cfg::kSmemBytes, a.n_tiles, &grid))) return rc;
-    composite_fwd_span_kernel<L, true><<<grid, kSpanWarps * 32, Cfg::kSmemBytes, stream>>>(a);
-  } else {
-    if ((rc = span_grid(composite_fwd_span_kernel<L, false>, Cfg::kSmemBytes, a.n_tiles, &grid))) return rc;
-    composite_fwd_span_kernel<L, false><<<grid, kSpanWarps * 32, Cfg::kSmemBytes, stream>>>(a);
-  }
+  const int64_t want = (a.n_tiles + warps - 1) / warps;
+  const int64_t cap = (int64_t)sms * occ;
+  const int grid = (int)(want < cap ? want : cap);
+  kernel<<<grid, warps * 32, smem_bytes, stream>>>(a);
   return check_launch();
 }
 
-template <int L>
-static int bwd_span_L(const SpanArgs& a, cudaStream_t stream) {
-  using Cfg = SpanCfg<L>;
-  int grid = 0, rc;
-  if ((rc = span_grid(composite_bwd_span_kernel<L>, Cfg::kSmemBytes, a.n_tiles, &grid))) return rc;
-  composite_bwd_span_kernel<L><<<grid, kSpanWarps * 32, Cfg::kSmemBytes, stream>>>(a);
-  return check_launch();
+template <int L, int NS>
+static int fwd_span_LN(const SpanArgs& a, bool simple, bool write_w, cudaStream_t stream) {
+  constexpr int sb = SpanCfg<L>::kStageBytes;
+  if (simple) {
+    return write_w ? span_launch(composite_fwd_span_kernel<L, NS, true, true>, sb, NS, a, stream)
+                   : span_launch(composite_fwd_span_kernel<L, NS, true, false>, sb, NS, a, stream);
+  }
+  if constexpr (L == 5) {
+    return write_w ? span_launch(composite_fwd_span_kernel<L, NS, false, true>, sb, NS, a, stream)
+                   : span_launch(composite_fwd_span_kernel<L, NS, false, false>, sb, NS, a, stream);
+  }
+  return AVR_ERR_UNSUPPORTED;
 }
 
-#define AVR_DISPATCH_L(L_, CALL)          \
-  switch (L_) {                           \
-    case 5: return CALL(5);               \
-    case 7: return CALL(7);               \
-    case 9: return CALL(9);               \
-    case 11: return CALL(11);             \
-    case 13: return CALL(13);             \
-    default: return AVR_ERR_UNSUPPORTED;  \
+template <int L, int NS>
+static int bwd_span_LN(const SpanArgs& a, bool simple, cudaStream_t stream) {
+  constexpr int sb = SpanCfg<L>::kStageBytes;
+  if (simple) return span_launch(composite_bwd_span_kernel<L, NS, true>, sb, NS, a, stream);
+  if constexpr (L == 5) return span_launch(composite_bwd_span_kernel<L, NS, false>, sb, NS, a, stream);
+  return AVR_ERR_UNSUPPORTED;
+}
+
+#define AVR_DISPATCH_LN(L_, NS_, CALL)                             \
+  switch (L_) {                                                    \
+    case 5: return NS_ == 3 ? CALL(5, 3) : CALL(5, 4);             \
+    case 7: return NS_ == 3 ? CALL(7, 3) : CALL(7, 4);             \
+    case 9: return NS_ == 3 ? CALL(9, 3) : CALL(9, 4);             \
+    case 11: return NS_ == 3 ? CALL(11, 3) : CALL(11, 4);          \
+    case 13: return NS_ == 3 ? CALL(13, 3) : CALL(13, 4);          \
+    default: return AVR_ERR_UNSUPPORTED;                           \
   }
+
+static SpanArgs make_args(const SpanPlan& plan, int K, int white_back, float infinity) {
+  SpanArgs a{};
+  a.n_tiles = (plan.main_rays + plan.rays_per_tile - 1) / plan.rays_per_tile;
+  a.K = K;
+  a.rays_per_tile = plan.rays_per_tile;
+  const int rem = (int)(plan.main_rays % plan.rays_per_tile);
+  a.tail_rays = rem ? rem : plan.rays_per_tile;
+  a.white_back = white_back;
+  a.infinity = infinity;
+  return a;
+}
 
 int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
                               cudaStream_t stream) {
-  SpanArgs a{};
+  SpanArgs a = make_args(plan, K, white_back, infinity);
   a.rgbs = rgbs;
   a.z = z;
   a.w = w;
   a.rgb = rgb;
   a.depth = depth;
-  a.n_tiles = plan.main_rays / plan.rays_per_tile;
-  a.K = K;
-  a.rays_per_tile = plan.rays_per_tile;
-  a.white_back = white_back;
-  a.infinity = infinity;
   const bool write_w = (w != nullptr);
-#define CALL(LL) fwd_span_L<LL>(a, write_w, stream)
-  AVR_DISPATCH_L(plan.L, CALL)
+  const bool simple = K > plan.L;
+  const int ns = stages_for(plan.L);
+#define CALL(LL, NN) fwd_span_LN<LL, NN>(a, simple, write_w, stream)
+  AVR_DISPATCH_LN(plan.L, ns, CALL)
 #undef CALL
 }
 
 int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
                               cudaStream_t stream) {
-  SpanArgs a{};
+  SpanArgs a = make_args(plan, K, white_back, infinity);
   a.rgbs = rgbs;
   a.z = z;
   a.g_rgb = g_rgb;
   a.g_depth = g_depth;
   a.d_rgbs = d_rgbs;
-  a.n_tiles = plan.main_rays / plan.rays_per_tile;
-  a.K = K;
-  a.rays_per_tile = plan.rays_per_tile;
-  a.white_back = white_back;
-  a.infinity = infinity;
-#define CALL(LL) bwd_span_L<LL>(a, stream)
-  AVR_DISPATCH_L(plan.L, CALL)
+  const bool simple = K > plan.L;
+  const int ns = stages_for(plan.L);
+#define CALL(LL, NN) bwd_span_LN<LL, NN>(a, simple, stream)
+  AVR_DISPATCH_LN(plan.L, ns, CALL)
 #undef CALL
 }
 
