@@ -37,6 +37,14 @@ def test_fwd_bwd_host_matches_device_path(dev):
         xd = x.to(dev).requires_grad_(True)
         a, b, _ = ops.composite(xd, z.to(dev), True, 1.8, want_w=False)
         torch.autograd.backward([a, b], [g_rgb.to(dev), g_d.to(dev)])
-        assert torch.equal(rgb, a.cpu()) and torch.equal(depth, b.cpu()) and torch.equal(dx, xd.grad.cpu())
+        if chunk == 0:      # one chunk: the very same launches as the device path
+            assert torch.equal(rgb, a.cpu()) and torch.equal(depth, b.cpu()) and torch.equal(dx, xd.grad.cpu())
+        # chunking moves rays to other lanes of a warp tile, which regroups the scan: equal to
+        # rounding, not to the bit
+        assert_close(rgb, a, rtol=2e-6, atol=2e-7, what="rgb")
+        assert_close(depth, b, rtol=2e-6, atol=2e-7, what="depth")
+        assert_close(dx[..., :3], xd.grad[..., :3], rtol=2e-6, atol=2e-7, what="d_rgb")
+        assert_close(dx[..., -1, 3] / 1e10, xd.grad[..., -1, 3] / 1e10, rtol=1e-5, atol=1e-6, what="d_sigma[-1]/1e10")
+        assert_close(dx[..., :-1, 3], xd.grad[..., :-1, 3], rtol=1e-5, atol=1e-6, what="d_sigma[:-1]")
     want = O.composite_rgbs(z[:512].unsqueeze(0), x[:512].unsqueeze(0), True)
     assert_close(rgb[:512], want[0][0], what="rgb vs oracle")

@@ -56,7 +56,7 @@ def test_coarse_backward_matches_autograd(dev):
     assert_close(dd.grad, gz.sum(-1), rtol=1e-5, atol=5e-6, what="d_distance")
 
 
-def _check_importance(w, near, far, u, u2, dev, ref_z=None):
+def _check_importance(w, near, far, u, u2, dev, ref_z=None, min_same=0.9995):
     from avr_b200 import ops
     kc = w.shape[-2] if w.dim() == 4 else w.shape[-1]
     out = ops.importance_sample(w.to(dev), near.to(dev), far.to(dev), u.to(dev), u2.to(dev),
@@ -78,7 +78,7 @@ def _check_importance(w, near, far, u, u2, dev, ref_z=None):
         # end to end against the reference: identical wherever its own CDF gave the same bin
         ridx = O.cdf_search(ocdf, u)
         same = ridx == idx
-        assert same.float().mean() > 0.999
+        assert same.float().mean() > min_same
         assert torch.equal(zf[same], ref_z[same])
     return out
 
@@ -89,7 +89,9 @@ def test_importance_golden(dev):
     near = torch.tensor([0.8]).expand(1, r).contiguous()
     far = torch.tensor([1.8]).expand(1, r).contiguous()
     _check_importance(g["w"], near, far, g["u"], g["u2"], dev, g["ref_z"])
-    out = _check_importance(g["w"], near, far, g["u_adv"], g["u2_adv"], dev, g["ref_z_adv"])
+    # adversarial draws sit exactly on CDF edges (u = 1 - 2^-24 vs a cdf[-1] that rounds to
+    # 1 -/+ 1 ulp), where the summation order of the CDF decides the bin: flips are expected there
+    out = _check_importance(g["w"], near, far, g["u_adv"], g["u2_adv"], dev, g["ref_z_adv"], min_same=0.99)
     idx = out["idx"].cpu()
     assert (idx[..., 0] == 0).all() and (idx[..., 2] >= 63).all()
     d = g["pr_d"]
