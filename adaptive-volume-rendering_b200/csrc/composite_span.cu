@@ -674,15 +674,18 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
+// Defaults from the B200 sweep in profiles/r01_span_sweep.md: a 3-deep ring (one tile in
+// flight behind the one being computed) with as many resident warps as shared memory
+// allows (12/SM at L <= 9, 8/SM above) beat deeper rings with fewer warps.
 // Tuning knobs (experiments only): AVR_SPAN_L forces the samples-per-lane, AVR_SPAN_STAGES
 // (3|4) the ring depth, AVR_SPAN_WARPS (1..8) the warps per CTA.
 static int stages_for(int L) {
+  (void)L;
   int s = env_int("AVR_SPAN_STAGES", 0);
-  if (s == 3 || s == 4) return s;
-  return L <= 9 ? 4 : 3;
+  return (s == 3 || s == 4) ? s : 3;
 }
-static int warps_per_cta() {
-  int w = env_int("AVR_SPAN_WARPS", 4);
+static int warps_per_cta(int L) {
+  int w = env_int("AVR_SPAN_WARPS", L >= 11 ? 2 : 4);
   return w < 1 ? 1 : (w > 8 ? 8 : w);
 }
 
@@ -720,8 +723,8 @@ bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan
 }
 
 template <typename KernelT>
-static int span_launch(KernelT kernel, int stage_bytes, int stages, const SpanArgs& a, cudaStream_t stream) {
-  const int warps = warps_per_cta();
+static int span_launch(KernelT kernel, int L, int stage_bytes, int stages, const SpanArgs& a, cudaStream_t stream) {
+  const int warps = warps_per_cta(L);
   const int smem_bytes = warps * stages * stage_bytes + warps * stages * 8;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) {
@@ -750,12 +753,12 @@ template <int L, int NS>
 static int fwd_span_LN(const SpanArgs& a, bool simple, bool write_w, cudaStream_t stream) {
   constexpr int sb = SpanCfg<L>::kStageBytes;
   if (simple) {
-    return write_w ? span_launch(composite_fwd_span_kernel<L, NS, true, true>, sb, NS, a, stream)
-                   : span_launch(composite_fwd_span_kernel<L, NS, true, false>, sb, NS, a, stream);
+    return write_w ? span_launch(composite_fwd_span_kernel<L, NS, true, true>, L, sb, NS, a, stream)
+                   : span_launch(composite_fwd_span_kernel<L, NS, true, false>, L, sb, NS, a, stream);
   }
   if constexpr (L == 5) {
-    return write_w ? span_launch(composite_fwd_span_kernel<L, NS, false, true>, sb, NS, a, stream)
-                   : span_launch(composite_fwd_span_kernel<L, NS, false, false>, sb, NS, a, stream);
+    return write_w ? span_launch(composite_fwd_span_kernel<L, NS, false, true>, L, sb, NS, a, stream)
+                   : span_launch(composite_fwd_span_kernel<L, NS, false, false>, L, sb, NS, a, stream);
   }
   return AVR_ERR_UNSUPPORTED;
 }
@@ -763,8 +766,8 @@ static int fwd_span_LN(const SpanArgs& a, bool simple, bool write_w, cudaStream_
 template <int L, int NS>
 static int bwd_span_LN(const SpanArgs& a, bool simple, cudaStream_t stream) {
   constexpr int sb = SpanCfg<L>::kStageBytes;
-  if (simple) return span_launch(composite_bwd_span_kernel<L, NS, true>, sb, NS, a, stream);
-  if constexpr (L == 5) return span_launch(composite_bwd_span_kernel<L, NS, false>, sb, NS, a, stream);
+  if (simple) return span_launch(composite_bwd_span_kernel<L, NS, true>, L, sb, NS, a, stream);
+  if constexpr (L == 5) return span_launch(composite_bwd_span_kernel<L, NS, false>, L, sb, NS, a, stream);
   return AVR_ERR_UNSUPPORTED;
 }
 

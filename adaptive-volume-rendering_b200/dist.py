@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: rays are independent, so they shard across ranks with no data-path
+collective; the only exchange on this path is the all-gather of the per-ray outputs
+(rgb + depth, 16 B/ray), packed as one (R, 4) buffer so it is a single NCCL call.
+
+One process per GPU (torch.distributed, NCCL over NVLink on the GPU box; the same code
+runs over gloo on CPU tensors, which is how the host logic is tested).  The reference is
+single-process/single-GPU (train.py:238-240); this layer has no counterpart there.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rays: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous ray range [start, stop) of `rank`; the first n_rays % world ranks get one extra."""
+    base, extra = divmod(n_rays, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_bounds_packed(offsets: torch.Tensor, world: int, rank: int) -> Tuple[int, int]:
+    """Ray range of `rank` for a packed layout, balanced by SAMPLES (not rays): boundaries
+    are the rays whose start offset is nearest below rank/world of the sample stream."""
+    total = int(offsets[-1])
+    n_rays = offsets.numel() - 1
+    targets = torch.tensor([total * rank // world, total * (rank + 1) // world], dtype=offsets.dtype,
+                           device=offsets.device)
+    cuts = torch.searchsorted(offsets[:-1].contiguous(), targets, right=False)
+    start = 0 if rank == 0 else int(cuts[0])
+    stop = n_rays if rank == world - 1 else int(cuts[1])
+    return start, stop
+
+
+def all_gather_outputs(rgb: torch.Tensor, depth: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                       shard_sizes: Optional[list] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gather every rank's (R_local, 3) rgb and (R_local,) depth into (R, 3) / (R,), ordered by
+    rank.  Equal shards take one all_gather_into_tensor; unequal shards are padded to the
+    largest (pass `shard_sizes`, the per-rank ray counts)."""
+    world = dist.get_world_size(group)
+    packed = torch.cat([rgb.reshape(-1, 3), depth.reshape(-1, 1)], dim=-1).contiguous()
+    n_local = packed.shape[0]
+    if shard_sizes is None:
+        shard_sizes = [n_local] * world
+    n_max = max(shard_sizes)
+    if n_local < n_max:
+        packed = torch.cat([packed, packed.new_zeros(n_max - n_local, 4)], dim=0)
+    out = packed.new_empty(world * n_max, 4)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    if any(s != n_max for s in shard_sizes):
+        out = torch.cat([out[r * n_max: r * n_max + s] for r, s in enumerate(shard_sizes)], dim=0)
+    return out[:, :3], out[:, 3]
+
+
+def composite_sharded(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = True, infinity: float = 1.8,
+                      group: Optional[dist.ProcessGroup] = None, composite_fn=None):
+    """Each rank composites ITS rays (rgbs (R_local,K,4), z (R_local,K)) and receives the full
+    image: returns (rgb_local, depth_local, rgb_all, depth_all).  Gradients flow through the
+    local outputs only (each rank owns its rays' gradients; no backward collective)."""
+    if composite_fn is None:
+        from . import ops
+
+        composite_fn = ops.composite
+    rgb, depth, _ = composite_fn(rgbs, z, white_back, infinity, False)
+    with torch.no_grad():
+        world = dist.get_world_size(group)
+        sizes = [None] * world
+        n = torch.tensor([rgb.shape[0]], device=rgb.device)
+        all_n = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(all_n, n, group=group)
+        sizes = [int(t.item()) for t in all_n]
+        rgb_all, depth_all = all_gather_outputs(rgb.detach(), depth.detach(), group, sizes)
+    return rgb, depth, rgb_all, depth_all

@@ -221,7 +221,7 @@ def main():
     if dist is not None:
         dist.barrier()
     import avr_b200
-    from avr_b200 import ops
+    from avr_b200 import dist as avr_dist
 
     lib = avr_b200.load_library()
     assert lib.avr_device_check() == 0, lib.avr_last_cuda_error()
@@ -237,7 +237,6 @@ def main():
     rgb = torch.empty(rays, 3, device=dev)
     depth = torch.empty(rays, device=dev)
     dx = torch.empty_like(x)
-    gathered = torch.empty(world * rays, 4, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
@@ -259,8 +258,7 @@ def main():
     def step():
         fwd()
         if dist is not None:  # the path's only exchange: per-ray outputs, 16 B/ray
-            packed = torch.cat([rgb, depth.unsqueeze(-1)], -1)
-            dist.all_gather_into_tensor(gathered, packed)
+            avr_dist.all_gather_outputs(rgb, depth)
         bwd()
 
     for _ in range(args.warmup):
@@ -289,8 +287,7 @@ def main():
             fwd()
             ev[i][1].record(stream)
             if dist is not None:
-                packed = torch.cat([rgb, depth.unsqueeze(-1)], -1)
-                dist.all_gather_into_tensor(gathered, packed)
+                avr_dist.all_gather_outputs(rgb, depth)
                 ev[i][1] = torch.cuda.Event(enable_timing=True)
                 ev[i][1].record(stream)
             bwd()
