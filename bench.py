@@ -40,6 +40,9 @@ import torch  # noqa: E402
 METRIC = "composite_fwd_bwd_rays_per_sec"
 UNIT = "rays/s"
 
+# (rays, K) -> DRAM bytes per launch of composite_bwd_span_kernel (ncu, round 1)
+NCU_TRAFFIC_BWD = {(1 << 20, 96): 2.031371e9 + 1.570049e9}
+
 WORKLOADS = {
     # name: (rays per GPU, samples per ray, description)
     "c2": (1 << 20, 96, "BASELINE.json configs[1]: composite fwd+bwd, 2^20 rays x 96 samples fp32 per GPU"),
@@ -312,7 +315,10 @@ def main():
     roofline = {
         "kernel": f"composite_bwd_span_kernel<L={L.value}>" if span else "composite_bwd_ray_kernel",
         "bound": "hbm", "achieved": bb * rays / (bwd_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+        # capture of this kernel at this size (profiles/r01_ncu_span_kernels.md); null for other shapes
+        "traffic": NCU_TRAFFIC_BWD.get((rays, k)) if span else None,
         "algorithmic_bytes_per_launch": bb * rays, "avg_launch_ms": bwd_avg, "min_launch_ms": bwd_ms[0],
     }
     roofline["frac"] = roofline["achieved"] / peak

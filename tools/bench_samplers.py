@@ -1,0 +1,108 @@
+"""Microbenchmarks of the sampling kernels and the packed pipeline (BASELINE.json configs 3, 4).
+
+    python tools/bench_samplers.py [--rays N] [--iters 20] [--what coarse importance packed]
+
+Prints one JSON line per kernel: ms, rays/s and the fraction of the HBM roofline
+(algorithmic bytes of SURVEY.md section 8d / time / MEASURED_PEAKS.json copy bandwidth).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from avr_b200 import ops  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, ms, rays, bytes_per_ray, **kw):
+    gbs = bytes_per_ray * rays / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "rays_per_s": rays / (ms * 1e-3), "GBps": round(gbs, 1),
+                      "hbm_frac": round(gbs / peak(), 4), "bytes_per_ray": bytes_per_ray, **kw}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=1 << 20)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--what", nargs="+", default=["coarse", "importance", "packed"])
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(0)
+    r = a.rays
+    near = torch.tensor([0.8], device=dev)
+    far = torch.tensor([1.8], device=dev)
+    if "coarse" in a.what:
+        for k in (64, 96):
+            u = torch.rand(1, r, k, device=dev, generator=g)
+            ms = timeit(lambda: ops.coarse_sample_raw(near, far, 0, u), a.iters)
+            report(f"coarse_sample K={k}", ms, r, 8 * k + 8)
+    if "importance" in a.what:
+        for kc, n, nd in ((64, 128, 0), (64, 16, 16)):
+            w = torch.rand(1, r, kc, device=dev, generator=g) ** 6
+            u = torch.rand(1, r, n, device=dev, generator=g)
+            u2 = torch.rand(1, r, n, device=dev, generator=g)
+            nrm = torch.randn(1, r, nd, device=dev, generator=g) if nd else None
+            zc = ops.coarse_sample_raw(near, far, 0, torch.rand(1, r, kc, device=dev, generator=g))
+            ms = timeit(lambda: ops.importance_sample(w, near, far, u, u2, z_coarse=zc, normals=nrm, depth_std=0.01,
+                                                      want_fine=False, want_sorted=True), a.iters)
+            report(f"importance_sample+merge {kc}->{n}+{nd}", ms, r, 12 * kc + 12 * n + 8 * nd + 8)
+            ms = timeit(lambda: ops.importance_sample(w, near, far, u, u2, want_fine=True), a.iters)
+            report(f"importance_sample only {kc}->{n}", ms, r, 4 * kc + 12 * n + 8)
+    if "packed" in a.what:
+        rp = min(r, 1 << 20)
+        counts = torch.randint(8, 257, (rp,), device=dev, generator=g)
+        offsets = torch.zeros(rp + 1, dtype=torch.int64, device=dev)
+        offsets[1:] = torch.cumsum(counts, 0)
+        s = int(offsets[-1])
+        d = 0.9 + 0.8 * torch.rand(rp, device=dev, generator=g)
+        nr, fr = d - 0.15, d + 0.15
+        u = torch.rand(s, device=dev, generator=g)
+        ms = timeit(lambda: ops.coarse_sample_packed(nr, fr, u, offsets), a.iters)
+        report("coarse_sample_packed 8..256", ms, rp, 8 * s / rp + 16, samples=s)
+        z = ops.coarse_sample_packed(nr, fr, u, offsets)
+        x = torch.cat([torch.sigmoid(torch.randn(s, 3, device=dev, generator=g)),
+                       torch.relu(torch.randn(s, 1, device=dev, generator=g)) * 30], -1)
+        ms = timeit(lambda: ops.composite_packed_fwd_raw(x, z, offsets, True, 1.8, True), a.iters)
+        report("composite_fwd_packed 8..256", ms, rp, 24 * s / rp + 24, samples=s)
+        xg = x.clone().requires_grad_(True)
+        rgb, depth, w = ops.composite_packed(xg, z, offsets, True, 1.8, True)
+        g1, g2 = torch.randn_like(rgb), torch.randn_like(depth)
+
+        def bwd():
+            torch.autograd.grad([rgb, depth], [xg], [g1, g2], retain_graph=True)
+
+        ms = timeit(bwd, a.iters)
+        report("composite_bwd_packed 8..256 (incl. autograd + zeros_like)", ms, rp, 36 * s / rp + 24, samples=s)
+        fo = torch.zeros(rp + 1, dtype=torch.int64, device=dev)
+        fo[1:] = torch.cumsum(counts // 2, 0)
+        sf = int(fo[-1])
+        uf, uf2 = torch.rand(sf, device=dev, generator=g), torch.rand(sf, device=dev, generator=g)
+        ms = timeit(lambda: ops.importance_sample_packed(w.detach(), z, nr, fr, uf, uf2, offsets, fo, 256, 128), a.iters)
+        report("importance_sample_packed Kc 8..256 -> Kc/2", ms, rp, (12 * s + 12 * sf) / rp + 24, samples=s, fine=sf)
+
+
+if __name__ == "__main__":
+    main()
