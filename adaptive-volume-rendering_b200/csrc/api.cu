@@ -122,7 +122,7 @@ int avr_importance_sample(const float* weights, const float* z_coarse, const flo
   if (z_sorted && n_depth > 0 && !normals) return AVR_ERR_BAD_ARG;
   if (!z_sorted) n_depth = 0;
   return launch_importance(weights, z_coarse, u, u2, normals, near, far, bound_stride, nullptr, nullptr, R, Kc,
-                           n_imp, n_depth, depth_std, z_fine, z_sorted, cdf, idx, as_stream(stream));
+                           n_imp, n_depth, depth_std, z_fine, z_sorted, cdf, idx, !g_force_generic.load(), as_stream(stream));
 }
 
 int avr_importance_sample_packed(const float* weights, const float* z_coarse, const float* u, const float* u2,
@@ -135,7 +135,7 @@ int avr_importance_sample_packed(const float* weights, const float* z_coarse, co
   if (!weights || !near || !far || !offsets || !fine_offsets || !u || !u2) return AVR_ERR_BAD_ARG;
   if (z_sorted && !z_coarse) return AVR_ERR_BAD_ARG;
   return launch_importance(weights, z_coarse, u, u2, nullptr, near, far, bound_stride, offsets, fine_offsets, R,
-                           max_coarse, max_fine, 0, 0.f, z_fine, z_sorted, nullptr, nullptr, as_stream(stream));
+                           max_coarse, max_fine, 0, 0.f, z_fine, z_sorted, nullptr, nullptr, false, as_stream(stream));
 }
 
 int avr_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, avr_stream_t stream) {

@@ -1,0 +1,335 @@
+// Register-resident importance sampler + merge for the dense layout (the fast path of
+// avr_importance_sample; csrc/samplers.cu keeps the general shared-memory kernel).
+//
+// One warp per ray, no block-level synchronisation:
+//   1. pdf/cdf: sum and inclusive scan of (w + 1e-5)/S by warp shuffles (renderers.py:36-39);
+//      the table goes to shared memory padded with +inf to a power of two so the search is
+//      a fixed number of branch-free steps.
+//   2. each lane owns EPF *consecutive* new samples (importance samples, then the clamped
+//      "depth" samples, then +inf padding): inverse-CDF search (renderers.py:41-43), jitter
+//      and placement (:45-46) with the reference's rounding.
+//   3. the 32*EPF new samples are sorted IN REGISTERS by a bitonic network (lane-local
+//      compare-exchanges for small strides, one shuffle + one min/max per element for the
+//      rest).
+//   4. coarse depths are already ascending (stratified sampling), so
+//      [coarse ascending | +inf | new samples descending] is a bitonic sequence of
+//      P = 32*EPT elements: ONE bitonic merge (log2 P steps) in a lane-striped register
+//      layout finishes the sort (renderers.py:257-258), and the striped layout stores
+//      straight to global memory fully coalesced.  If a ray's coarse depths are not
+//      ascending (arbitrary caller input), that ray takes a full shared-memory sort instead.
+#include <math_constants.h>
+
+#include "avr_common.cuh"
+#include "kernels.h"
+
+namespace avr {
+
+constexpr int kRegWarps = 8;  // warps per CTA
+
+struct ImportanceRegArgs {
+  const float* weights;
+  const float* z_coarse;
+  const float* u;
+  const float* u2;
+  const float* normals;
+  const float* near;
+  const float* far;
+  int bound_stride;
+  int64_t R;
+  int Kc, n_imp, n_depth;
+  float depth_std;
+  int vec4;  // u/u2 rows are 16-byte aligned (n % 4 == 0 and aligned bases)
+  float* z_fine;
+  float* z_sorted;
+  float* cdf;
+  int32_t* idx;
+};
+
+__device__ __forceinline__ void cmp_swap(float& a, float& b, bool ascending) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = ascending ? lo : hi;
+  b = ascending ? hi : lo;
+}
+
+// Full bitonic sort of 32*EPF keys, blocked layout: key index e = lane*EPF + r.
+template <int EPF>
+__device__ __forceinline__ void sort_blocked(float (&v)[EPF], int lane) {
+  constexpr int M = 32 * EPF;
+#pragma unroll
+  for (int size = 2; size <= M; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride < EPF) {
+#pragma unroll
+        for (int r = 0; r < EPF; ++r) {
+          if ((r & stride) == 0) {
+            const bool asc = (((lane * EPF + r) & size) == 0);
+            cmp_swap(v[r], v[r | stride], asc);
+          }
+        }
+      } else {
+        const int lstride = stride / EPF;
+        const bool lower = ((lane & lstride) == 0);
+        const bool asc = (((lane * EPF) & size) == 0);
+        const bool keep_min = (lower == asc);
+#pragma unroll
+        for (int r = 0; r < EPF; ++r) {
+          const float o = __shfl_xor_sync(0xffffffffu, v[r], lstride);
+          v[r] = keep_min ? fminf(v[r], o) : fmaxf(v[r], o);
+        }
+      }
+    }
+  }
+}
+
+// Ascending bitonic merge of 32*EPT keys, striped layout: key index q = i*32 + lane.
+template <int EPT>
+__device__ __forceinline__ void merge_striped(float (&x)[EPT], int lane) {
+#pragma unroll
+  for (int stride = 16 * EPT; stride > 0; stride >>= 1) {
+    if (stride >= 32) {
+      const int istride = stride / 32;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        if ((i & istride) == 0) cmp_swap(x[i], x[i | istride], true);
+      }
+    } else {
+      const bool keep_min = ((lane & stride) == 0);
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        const float o = __shfl_xor_sync(0xffffffffu, x[i], stride);
+        x[i] = keep_min ? fminf(x[i], o) : fmaxf(x[i], o);
+      }
+    }
+  }
+}
+
+// smem bitonic sort (any content), P power of two; used for the rare unsorted-coarse ray
+__device__ __forceinline__ void sort_smem(float* key, int P, int lane) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < (P >> 1); t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool ascending = ((lo & size) == 0);
+        const float a = key[lo], b = key[hi];
+        if ((a > b) == ascending && a != b) {
+          key[lo] = b;
+          key[hi] = a;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int EPF, int EPT>
+__global__ void __launch_bounds__(kRegWarps * 32)
+importance_reg_kernel(const ImportanceRegArgs a) {
+  constexpr int M = 32 * EPF;  // new samples incl. padding
+  constexpr int P = 32 * EPT;  // merged length incl. padding; also the padded cdf table length
+  static_assert(EPT > EPF, "room for the coarse samples");
+  __shared__ float s_cdf[kRegWarps][P];
+  __shared__ float s_buf[kRegWarps][P];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* cdf = s_cdf[warp];
+  float* buf = s_buf[warp];
+  const int kc = a.Kc, n = a.n_imp, nd = a.n_depth;
+  const int total = kc + n + nd;
+  const bool do_sort = (a.z_sorted != nullptr);
+  const int64_t warps = (int64_t)gridDim.x * kRegWarps;
+
+  for (int64_t r = blockIdx.x * (int64_t)kRegWarps + warp; r < a.R; r += warps) {
+    const int64_t bi = a.bound_stride ? r : 0;
+    const float near = a.near[bi], far = a.far[bi];
+    const float span = __fsub_rn(far, near);
+    const float* wrow = a.weights + r * (int64_t)kc;
+
+    // ---- 1. cdf table -----------------------------------------------------------------
+    float part = 0.f;
+    for (int j = lane; j < kc; j += 32) part += __fadd_rn(wrow[j], kPdfEps);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    const float S = part;
+    __syncwarp();  // previous ray's readers of cdf/buf are done
+    if (lane == 0) cdf[0] = 0.f;
+    float carry = 0.f, hi = 0.f;
+    for (int j0 = 0; j0 < kc; j0 += 32) {
+      const int j = j0 + lane;
+      float v = (j < kc) ? __fdiv_rn(__fadd_rn(wrow[j], kPdfEps), S) : 0.f;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float p = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += p;
+      }
+      v += carry;
+      float m = fmaxf(v, hi);  // running max: the table must be non-decreasing
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float p = __shfl_up_sync(0xffffffffu, m, d);
+        if (lane >= d) m = fmaxf(m, p);
+      }
+      if (j < kc) cdf[j + 1] = m;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+      hi = __shfl_sync(0xffffffffu, m, 31);
+    }
+    for (int j = kc + 1 + lane; j < P; j += 32) cdf[j] = CUDART_INF_F;
+    __syncwarp();
+    if (a.cdf) {
+      float* out = a.cdf + r * (int64_t)(kc + 1);
+      for (int j = lane; j <= kc; j += 32) out[j] = cdf[j];
+    }
+
+    // ---- 2. the lane's EPF consecutive new samples --------------------------------------
+    float v[EPF];
+    const int e0 = lane * EPF;
+    const float* urow = a.u + r * (int64_t)n;
+    const float* u2row = a.u2 + r * (int64_t)n;
+    float uu[EPF], uj[EPF];
+    if (EPF >= 4 && a.vec4 && e0 + EPF <= n) {  // 16-byte loads of the lane's consecutive draws
+#pragma unroll
+      for (int q = 0; q < EPF; q += 4) {
+        const float4 p4 = *reinterpret_cast<const float4*>(urow + e0 + q);
+        const float4 j4 = *reinterpret_cast<const float4*>(u2row + e0 + q);
+        uu[q] = p4.x; uu[(q + 1) % EPF] = p4.y; uu[(q + 2) % EPF] = p4.z; uu[(q + 3) % EPF] = p4.w;
+        uj[q] = j4.x; uj[(q + 1) % EPF] = j4.y; uj[(q + 2) % EPF] = j4.z; uj[(q + 3) % EPF] = j4.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < EPF; ++q) {
+        const bool in = (e0 + q < n);
+        uu[q] = in ? urow[e0 + q] : 0.f;
+        uj[q] = in ? u2row[e0 + q] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < EPF; ++q) {
+      const int e = e0 + q;
+      float val = CUDART_INF_F;
+      if (e < n) {
+        // cnt = #{j : cdf[j] <= u} over the +inf-padded table (branch-free upper bound);
+        // bin = max(cnt - 1, 0)  ==  clamp_min(searchsorted(cdf, u, right=True) - 1, 0)
+        int cnt = 0;
+#pragma unroll
+        for (int step = P >> 1; step > 0; step >>= 1) {
+          if (cdf[cnt + step - 1] <= uu[q]) cnt += step;
+        }
+        const int bin = cnt > 0 ? cnt - 1 : 0;
+        const float t = __fdiv_rn(__fadd_rn((float)bin, uj[q]), (float)kc);
+        val = __fadd_rn(near, __fmul_rn(span, t));
+        if (a.idx) a.idx[r * (int64_t)n + e] = bin;
+        if (a.z_fine) a.z_fine[r * (int64_t)n + e] = val;
+      } else if (e < n + nd && do_sort) {
+        const float g = __fmul_rn(a.normals[r * (int64_t)nd + (e - n)], a.depth_std);
+        val = fminf(fmaxf(g, near), far);  // sample_depth's randn*std, clamped (renderers.py:62-66, :255)
+      }
+      v[q] = val;
+    }
+    if (!do_sort) continue;
+
+    // ---- 3. sort the new samples in registers -------------------------------------------
+    sort_blocked<EPF>(v, lane);
+
+    // ---- 4. lay out [coarse | +inf | new descending] striped over the lanes ---------------
+#pragma unroll
+    for (int q = 0; q < EPF; ++q) buf[P - 1 - (e0 + q)] = v[q];
+    __syncwarp();
+    float x[EPT];
+    const float* zrow = a.z_coarse + r * (int64_t)kc;
+    bool unsorted = false;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int q = i * 32 + lane;
+      float val = CUDART_INF_F;
+      if (q < kc) val = zrow[q];
+      else if (q >= P - M) val = buf[q];
+      x[i] = val;
+    }
+    // coarse depths must be ascending for the merge; check (q, q+1) pairs inside [0, kc)
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      float nxt = __shfl_down_sync(0xffffffffu, x[i], 1);
+      const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < EPT) ? i + 1 : i], 0);
+      if (lane == 31) nxt = first_next;
+      const int q = i * 32 + lane;
+      if (q + 1 < kc && x[i] > nxt) unsorted = true;
+    }
+    if (__any_sync(0xffffffffu, unsorted)) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) buf[i * 32 + lane] = x[i];
+      sort_smem(buf, P, lane);
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) x[i] = buf[i * 32 + lane];
+    } else {
+      merge_striped<EPT>(x, lane);
+    }
+
+    // ---- 5. coalesced store of the first `total` keys --------------------------------------
+    float* out = a.z_sorted + r * (int64_t)total;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int q = i * 32 + lane;
+      if (q < total) out[q] = x[i];
+    }
+  }
+}
+
+template <int EPF, int EPT>
+static int launch_reg(const ImportanceRegArgs& a, cudaStream_t stream) {
+  int64_t blocks = (a.R + kRegWarps - 1) / kRegWarps;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  importance_reg_kernel<EPF, EPT><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
+  return check_launch();
+}
+
+// Returns AVR_ERR_UNSUPPORTED when the shape does not fit a register variant (caller falls
+// back to the shared-memory kernel).
+int launch_importance_reg(const float* weights, const float* z_coarse, const float* u, const float* u2,
+                          const float* normals, const float* near, const float* far, int bound_stride,
+                          int64_t R, int Kc, int n_imp, int n_depth, float depth_std, float* z_fine,
+                          float* z_sorted, float* cdf, int32_t* idx, cudaStream_t stream) {
+  const int m = n_imp + (z_sorted ? n_depth : 0);
+  int epf = 1;
+  while (32 * epf < m) epf <<= 1;
+  int ept = 2 * epf;
+  while (32 * ept < Kc + 32 * epf || 32 * ept < Kc + 2) ept <<= 1;
+  if (epf > 8 || ept > 16 || m < 1) return AVR_ERR_UNSUPPORTED;
+  ImportanceRegArgs a;
+  a.weights = weights;
+  a.z_coarse = z_coarse;
+  a.u = u;
+  a.u2 = u2;
+  a.normals = normals;
+  a.near = near;
+  a.far = far;
+  a.bound_stride = bound_stride;
+  a.R = R;
+  a.Kc = Kc;
+  a.n_imp = n_imp;
+  a.n_depth = z_sorted ? n_depth : 0;
+  a.depth_std = depth_std;
+  a.vec4 = ((n_imp & 3) == 0) && aligned16(u) && aligned16(u2);
+  a.z_fine = z_fine;
+  a.z_sorted = z_sorted;
+  a.cdf = cdf;
+  a.idx = idx;
+#define AVR_REG_CASE(F, T) \
+  if (epf == F && ept == T) return launch_reg<F, T>(a, stream);
+  AVR_REG_CASE(1, 2)
+  AVR_REG_CASE(1, 4)
+  AVR_REG_CASE(1, 8)
+  AVR_REG_CASE(1, 16)
+  AVR_REG_CASE(2, 4)
+  AVR_REG_CASE(2, 8)
+  AVR_REG_CASE(2, 16)
+  AVR_REG_CASE(4, 8)
+  AVR_REG_CASE(4, 16)
+  AVR_REG_CASE(8, 16)
+#undef AVR_REG_CASE
+  return AVR_ERR_UNSUPPORTED;
+}
+
+}  // namespace avr

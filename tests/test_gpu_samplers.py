@@ -9,6 +9,16 @@ from conftest import assert_close, load_golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "generic"])
+def family(request):
+    """Run through the register-resident kernel the library picks AND the general shared-memory kernel."""
+    import avr_b200
+    lib = avr_b200.load_library()
+    lib.avr_set_force_generic(1 if request.param == "generic" else 0)
+    yield request.param
+    lib.avr_set_force_generic(0)
+
+
 def test_coarse_golden_bit_exact(dev):
     import avr_b200
     g = load_golden("coarse")
@@ -83,7 +93,7 @@ def _check_importance(w, near, far, u, u2, dev, ref_z=None, min_same=0.9995):
     return out
 
 
-def test_importance_golden(dev):
+def test_importance_golden(dev, family):
     g = load_golden("fine")
     r = g["w"].shape[1]
     near = torch.tensor([0.8]).expand(1, r).contiguous()
@@ -113,8 +123,9 @@ def test_sample_fine_signature_and_seed(dev):
     assert z.shape == (1, r, 128)
 
 
-@pytest.mark.parametrize("kc,n,nd", [(64, 16, 16), (64, 128, 0), (32, 8, 8), (20, 5, 3), (200, 300, 12), (1, 1, 1)])
-def test_merge_is_exact_sort(kc, n, nd, dev):
+@pytest.mark.parametrize("kc,n,nd", [(64, 16, 16), (64, 128, 0), (32, 8, 8), (20, 5, 3), (200, 300, 12), (1, 1, 1),
+                                     (128, 64, 0), (96, 250, 6), (300, 100, 20), (33, 31, 0)])
+def test_merge_is_exact_sort(kc, n, nd, dev, family):
     from avr_b200 import ops
     g = torch.Generator().manual_seed(kc * 7 + n)
     r = 257
@@ -124,6 +135,11 @@ def test_merge_is_exact_sort(kc, n, nd, dev):
     u, u2 = torch.rand(1, r, n, generator=g), torch.rand(1, r, n, generator=g)
     normals = torch.randn(1, r, nd, generator=g) if nd else None
     zc = O.coarse_z(near, far, kc, torch.rand(1, r, kc, generator=g))
+    if kc >= 20:
+        # arbitrary caller input: a few rays whose coarse depths are NOT ascending
+        zc[0, 5] = zc[0, 5].flip(-1)
+        zc[0, 77, [3, 11]] = zc[0, 77, [11, 3]]
+        zc[0, 200] = zc[0, 200][torch.randperm(kc, generator=g)]
     std = 50.0 if kc == 32 else 0.01        # std=50 puts the clamped depth samples all over [near, far]
     out = ops.importance_sample(w.to(dev), near.to(dev), far.to(dev), u.to(dev), u2.to(dev), z_coarse=zc.to(dev),
                                 normals=None if normals is None else normals.to(dev), depth_std=std,
