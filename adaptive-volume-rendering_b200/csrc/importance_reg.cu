@@ -124,11 +124,74 @@ __device__ __forceinline__ void sort_smem(float* key, int P, int lane) {
   __syncwarp();
 }
 
+// One ray's inputs, held in registers so the NEXT ray's loads are in flight while the
+// current ray is being processed (the kernel is otherwise bound by global-load latency:
+// weights -> sum -> cdf -> search is one dependent chain per ray).
+template <int EPF, int EPC>
+struct RayIn {
+  float w[EPC];    // coarse weights, striped: j = i*32 + lane
+  float zc[EPC];   // coarse depths, striped
+  float a[EPF];    // lane's consecutive new samples: u (e < n) or N(0,1) draw (n <= e < n+nd)
+  float b[EPF];    // in-bin jitter u2 (e < n)
+  float near, far;
+};
+
+template <int EPF, int EPC>
+__device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRegArgs& a, int64_t r, int lane,
+                                         bool do_sort) {
+  const int kc = a.Kc, n = a.n_imp, nd = a.n_depth;
+  const int64_t bi = a.bound_stride ? r : 0;
+  in.near = a.near[bi];
+  in.far = a.far[bi];
+  const float* wrow = a.weights + r * (int64_t)kc;
+#pragma unroll
+  for (int i = 0; i < EPC; ++i) {
+    const int j = i * 32 + lane;
+    in.w[i] = (j < kc) ? wrow[j] : 0.f;
+  }
+  if (do_sort) {
+    const float* zrow = a.z_coarse + r * (int64_t)kc;
+#pragma unroll
+    for (int i = 0; i < EPC; ++i) {
+      const int j = i * 32 + lane;
+      in.zc[i] = (j < kc) ? zrow[j] : CUDART_INF_F;
+    }
+  }
+  const int e0 = lane * EPF;
+  const float* urow = a.u + r * (int64_t)n;
+  const float* u2row = a.u2 + r * (int64_t)n;
+  if (EPF >= 4 && a.vec4 && e0 + EPF <= n) {  // 16-byte loads of the lane's consecutive draws
+#pragma unroll
+    for (int q = 0; q < EPF; q += 4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(urow + e0 + q);
+      const float4 j4 = *reinterpret_cast<const float4*>(u2row + e0 + q);
+      in.a[q] = p4.x; in.a[(q + 1) % EPF] = p4.y; in.a[(q + 2) % EPF] = p4.z; in.a[(q + 3) % EPF] = p4.w;
+      in.b[q] = j4.x; in.b[(q + 1) % EPF] = j4.y; in.b[(q + 2) % EPF] = j4.z; in.b[(q + 3) % EPF] = j4.w;
+    }
+  } else {
+    const float* nrow = a.normals ? a.normals + r * (int64_t)nd : nullptr;
+#pragma unroll
+    for (int q = 0; q < EPF; ++q) {
+      const int e = e0 + q;
+      float va = 0.f, vb = 0.f;
+      if (e < n) {
+        va = urow[e];
+        vb = u2row[e];
+      } else if (e < n + nd && do_sort) {
+        va = nrow[e - n];
+      }
+      in.a[q] = va;
+      in.b[q] = vb;
+    }
+  }
+}
+
 template <int EPF, int EPT>
 __global__ void __launch_bounds__(kRegWarps * 32)
 importance_reg_kernel(const ImportanceRegArgs a) {
-  constexpr int M = 32 * EPF;  // new samples incl. padding
-  constexpr int P = 32 * EPT;  // merged length incl. padding; also the padded cdf table length
+  constexpr int M = 32 * EPF;    // new samples incl. padding
+  constexpr int P = 32 * EPT;    // merged length incl. padding; also the padded cdf table length
+  constexpr int EPC = EPT - EPF; // coarse samples per lane (striped), Kc <= 32*EPC
   static_assert(EPT > EPF, "room for the coarse samples");
   __shared__ float s_cdf[kRegWarps][P];
   __shared__ float s_buf[kRegWarps][P];
@@ -138,43 +201,62 @@ importance_reg_kernel(const ImportanceRegArgs a) {
   const int kc = a.Kc, n = a.n_imp, nd = a.n_depth;
   const int total = kc + n + nd;
   const bool do_sort = (a.z_sorted != nullptr);
+  const float kcf = (float)kc;
+  const bool kc_pow2 = (kc & (kc - 1)) == 0;
+  const float inv_kc = 1.0f / kcf;  // exact when kc is a power of two: x*inv_kc == x/kc bit for bit
   const int64_t warps = (int64_t)gridDim.x * kRegWarps;
+  const int e0 = lane * EPF;
 
-  for (int64_t r = blockIdx.x * (int64_t)kRegWarps + warp; r < a.R; r += warps) {
-    const int64_t bi = a.bound_stride ? r : 0;
-    const float near = a.near[bi], far = a.far[bi];
+  // the +inf tail of the table never changes
+  for (int j = kc + 1 + lane; j < P; j += 32) cdf[j] = CUDART_INF_F;
+  if (lane == 0) cdf[0] = 0.f;
+
+  int64_t r = blockIdx.x * (int64_t)kRegWarps + warp;
+  RayIn<EPF, EPC> cur;
+  if (r < a.R) load_ray<EPF, EPC>(cur, a, r, lane, do_sort);
+  for (; r < a.R; r += warps) {
+    RayIn<EPF, EPC> nxt;
+    const bool more = (r + warps < a.R);
+    if (more) load_ray<EPF, EPC>(nxt, a, r + warps, lane, do_sort);
+
+    const float near = cur.near, far = cur.far;
     const float span = __fsub_rn(far, near);
-    const float* wrow = a.weights + r * (int64_t)kc;
 
     // ---- 1. cdf table -----------------------------------------------------------------
+    float wp[EPC];
     float part = 0.f;
-    for (int j = lane; j < kc; j += 32) part += __fadd_rn(wrow[j], kPdfEps);
+#pragma unroll
+    for (int i = 0; i < EPC; ++i) {
+      wp[i] = __fadd_rn(cur.w[i], kPdfEps);
+      if (i * 32 + lane < kc) part += wp[i];
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     const float S = part;
     __syncwarp();  // previous ray's readers of cdf/buf are done
-    if (lane == 0) cdf[0] = 0.f;
     float carry = 0.f, hi = 0.f;
-    for (int j0 = 0; j0 < kc; j0 += 32) {
-      const int j = j0 + lane;
-      float v = (j < kc) ? __fdiv_rn(__fadd_rn(wrow[j], kPdfEps), S) : 0.f;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float p = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += p;
-      }
-      v += carry;
-      float m = fmaxf(v, hi);  // running max: the table must be non-decreasing
+    for (int i = 0; i < EPC; ++i) {
+      if (i * 32 < kc) {  // warp-uniform
+        const int j = i * 32 + lane;
+        float v = (j < kc) ? __fdiv_rn(wp[i], S) : 0.f;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float p = __shfl_up_sync(0xffffffffu, m, d);
-        if (lane >= d) m = fmaxf(m, p);
+        for (int d = 1; d < 32; d <<= 1) {
+          const float p = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= d) v += p;
+        }
+        v += carry;
+        float m = fmaxf(v, hi);  // running max: the table must be non-decreasing
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float p = __shfl_up_sync(0xffffffffu, m, d);
+          if (lane >= d) m = fmaxf(m, p);
+        }
+        if (j < kc) cdf[j + 1] = m;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+        hi = __shfl_sync(0xffffffffu, m, 31);
       }
-      if (j < kc) cdf[j + 1] = m;
-      carry = __shfl_sync(0xffffffffu, v, 31);
-      hi = __shfl_sync(0xffffffffu, m, 31);
     }
-    for (int j = kc + 1 + lane; j < P; j += 32) cdf[j] = CUDART_INF_F;
     __syncwarp();
     if (a.cdf) {
       float* out = a.cdf + r * (int64_t)(kc + 1);
@@ -183,96 +265,77 @@ importance_reg_kernel(const ImportanceRegArgs a) {
 
     // ---- 2. the lane's EPF consecutive new samples --------------------------------------
     float v[EPF];
-    const int e0 = lane * EPF;
-    const float* urow = a.u + r * (int64_t)n;
-    const float* u2row = a.u2 + r * (int64_t)n;
-    float uu[EPF], uj[EPF];
-    if (EPF >= 4 && a.vec4 && e0 + EPF <= n) {  // 16-byte loads of the lane's consecutive draws
-#pragma unroll
-      for (int q = 0; q < EPF; q += 4) {
-        const float4 p4 = *reinterpret_cast<const float4*>(urow + e0 + q);
-        const float4 j4 = *reinterpret_cast<const float4*>(u2row + e0 + q);
-        uu[q] = p4.x; uu[(q + 1) % EPF] = p4.y; uu[(q + 2) % EPF] = p4.z; uu[(q + 3) % EPF] = p4.w;
-        uj[q] = j4.x; uj[(q + 1) % EPF] = j4.y; uj[(q + 2) % EPF] = j4.z; uj[(q + 3) % EPF] = j4.w;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < EPF; ++q) {
-        const bool in = (e0 + q < n);
-        uu[q] = in ? urow[e0 + q] : 0.f;
-        uj[q] = in ? u2row[e0 + q] : 0.f;
-      }
-    }
+    int32_t* irow = a.idx ? a.idx + r * (int64_t)n : nullptr;
+    float* frow = a.z_fine ? a.z_fine + r * (int64_t)n : nullptr;
 #pragma unroll
     for (int q = 0; q < EPF; ++q) {
       const int e = e0 + q;
-      float val = CUDART_INF_F;
-      if (e < n) {
-        // cnt = #{j : cdf[j] <= u} over the +inf-padded table (branch-free upper bound);
-        // bin = max(cnt - 1, 0)  ==  clamp_min(searchsorted(cdf, u, right=True) - 1, 0)
-        int cnt = 0;
+      // cnt = #{j : cdf[j] <= u} over the +inf-padded table (branch-free upper bound);
+      // bin = max(cnt - 1, 0)  ==  clamp_min(searchsorted(cdf, u, right=True) - 1, 0)
+      const float uu = cur.a[q];
+      int cnt = 0;
 #pragma unroll
-        for (int step = P >> 1; step > 0; step >>= 1) {
-          if (cdf[cnt + step - 1] <= uu[q]) cnt += step;
-        }
-        const int bin = cnt > 0 ? cnt - 1 : 0;
-        const float t = __fdiv_rn(__fadd_rn((float)bin, uj[q]), (float)kc);
-        val = __fadd_rn(near, __fmul_rn(span, t));
-        if (a.idx) a.idx[r * (int64_t)n + e] = bin;
-        if (a.z_fine) a.z_fine[r * (int64_t)n + e] = val;
-      } else if (e < n + nd && do_sort) {
-        const float g = __fmul_rn(a.normals[r * (int64_t)nd + (e - n)], a.depth_std);
-        val = fminf(fmaxf(g, near), far);  // sample_depth's randn*std, clamped (renderers.py:62-66, :255)
+      for (int step = P >> 1; step > 0; step >>= 1) {
+        if (cdf[cnt + step - 1] <= uu) cnt += step;
+      }
+      const int bin = cnt > 0 ? cnt - 1 : 0;
+      const float num = __fadd_rn((float)bin, cur.b[q]);
+      const float t = kc_pow2 ? __fmul_rn(num, inv_kc) : __fdiv_rn(num, kcf);
+      float val = __fadd_rn(near, __fmul_rn(span, t));
+      if (e < n) {
+        if (irow) irow[e] = bin;
+        if (frow) frow[e] = val;
+      } else if (e < n + nd) {
+        // sample_depth's randn*std (depth NOT added), clamped (renderers.py:62-66, :255)
+        val = fminf(fmaxf(__fmul_rn(cur.a[q], a.depth_std), near), far);
+      } else {
+        val = CUDART_INF_F;
       }
       v[q] = val;
     }
-    if (!do_sort) continue;
+    if (do_sort) {
+      // ---- 3. sort the new samples in registers -----------------------------------------
+      sort_blocked<EPF>(v, lane);
 
-    // ---- 3. sort the new samples in registers -------------------------------------------
-    sort_blocked<EPF>(v, lane);
-
-    // ---- 4. lay out [coarse | +inf | new descending] striped over the lanes ---------------
+      // ---- 4. lay out [coarse | +inf | new descending] striped over the lanes -------------
 #pragma unroll
-    for (int q = 0; q < EPF; ++q) buf[P - 1 - (e0 + q)] = v[q];
-    __syncwarp();
-    float x[EPT];
-    const float* zrow = a.z_coarse + r * (int64_t)kc;
-    bool unsorted = false;
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-      const int q = i * 32 + lane;
-      float val = CUDART_INF_F;
-      if (q < kc) val = zrow[q];
-      else if (q >= P - M) val = buf[q];
-      x[i] = val;
-    }
-    // coarse depths must be ascending for the merge; check (q, q+1) pairs inside [0, kc)
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-      float nxt = __shfl_down_sync(0xffffffffu, x[i], 1);
-      const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < EPT) ? i + 1 : i], 0);
-      if (lane == 31) nxt = first_next;
-      const int q = i * 32 + lane;
-      if (q + 1 < kc && x[i] > nxt) unsorted = true;
-    }
-    if (__any_sync(0xffffffffu, unsorted)) {
+      for (int q = 0; q < EPF; ++q) buf[P - 1 - (e0 + q)] = v[q];
       __syncwarp();
+      float x[EPT];
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) buf[i * 32 + lane] = x[i];
-      sort_smem(buf, P, lane);
+      for (int i = 0; i < EPT; ++i) {
+        if (i < EPC) x[i] = cur.zc[i];               // +inf beyond kc
+        else x[i] = buf[i * 32 + lane];              // positions >= P - M
+      }
+      // coarse depths must be ascending for the merge; check the (q, q+1) pairs inside [0, kc)
+      bool unsorted = false;
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) x[i] = buf[i * 32 + lane];
-    } else {
-      merge_striped<EPT>(x, lane);
-    }
+      for (int i = 0; i < EPC; ++i) {
+        float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
+        const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < EPC) ? i + 1 : i], 0);
+        if (lane == 31) nx = (i + 1 < EPC) ? first_next : CUDART_INF_F;
+        if (i * 32 + lane + 1 < kc && x[i] > nx) unsorted = true;
+      }
+      if (__any_sync(0xffffffffu, unsorted)) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) buf[i * 32 + lane] = x[i];
+        sort_smem(buf, P, lane);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) x[i] = buf[i * 32 + lane];
+      } else {
+        merge_striped<EPT>(x, lane);
+      }
 
-    // ---- 5. coalesced store of the first `total` keys --------------------------------------
-    float* out = a.z_sorted + r * (int64_t)total;
+      // ---- 5. coalesced store of the first `total` keys ------------------------------------
+      float* out = a.z_sorted + r * (int64_t)total;
 #pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-      const int q = i * 32 + lane;
-      if (q < total) out[q] = x[i];
+      for (int i = 0; i < EPT; ++i) {
+        const int q = i * 32 + lane;
+        if (q < total) out[q] = x[i];
+      }
     }
+    if (more) cur = nxt;
   }
 }
 
