@@ -129,7 +129,7 @@ __device__ __forceinline__ void sort_smem(float* key, int P, int lane) {
 // weights -> sum -> cdf -> search is one dependent chain per ray).
 template <int EPF, int EPC>
 struct RayIn {
-  float w[EPC];    // coarse weights, striped: j = i*32 + lane
+  float w[EPC];    // coarse weights, blocked: j = lane*ceil(Kc/32) + i
   float zc[EPC];   // coarse depths, striped
   float a[EPF];    // lane's consecutive new samples: u (e < n) or N(0,1) draw (n <= e < n+nd)
   float b[EPF];    // in-bin jitter u2 (e < n)
@@ -144,10 +144,11 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
   in.near = a.near[bi];
   in.far = a.far[bi];
   const float* wrow = a.weights + r * (int64_t)kc;
+  const int c = (kc + 31) >> 5;  // weights per lane, blocked: j = lane*c + i
 #pragma unroll
   for (int i = 0; i < EPC; ++i) {
-    const int j = i * 32 + lane;
-    in.w[i] = (j < kc) ? wrow[j] : 0.f;
+    const int j = lane * c + i;
+    in.w[i] = (i < c && j < kc) ? wrow[j] : 0.f;
   }
   if (do_sort) {
     const float* zrow = a.z_coarse + r * (int64_t)kc;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
 }
 
 template <int EPF, int EPT>
-__global__ void __launch_bounds__(kRegWarps * 32)
+__global__ void __launch_bounds__(kRegWarps * 32, 3)
 importance_reg_kernel(const ImportanceRegArgs a) {
   constexpr int M = 32 * EPF;    // new samples incl. padding
   constexpr int P = 32 * EPT;    // merged length incl. padding; also the padded cdf table length
@@ -223,39 +224,48 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     const float span = __fsub_rn(far, near);
 
     // ---- 1. cdf table -----------------------------------------------------------------
+    // blocked scan: each lane owns c consecutive bins; local running sums, one exclusive
+    // warp scan of the lane totals, then a running max (a parallel prefix sum is not
+    // monotone in floating point; the search needs a non-decreasing table)
+    const int c = (kc + 31) >> 5;
     float wp[EPC];
     float part = 0.f;
 #pragma unroll
     for (int i = 0; i < EPC; ++i) {
       wp[i] = __fadd_rn(cur.w[i], kPdfEps);
-      if (i * 32 + lane < kc) part += wp[i];
+      if (i < c && lane * c + i < kc) part += wp[i];
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     const float S = part;
-    __syncwarp();  // previous ray's readers of cdf/buf are done
-    float carry = 0.f, hi = 0.f;
+    float ps[EPC];
+    float run = 0.f;
 #pragma unroll
     for (int i = 0; i < EPC; ++i) {
-      if (i * 32 < kc) {  // warp-uniform
-        const int j = i * 32 + lane;
-        float v = (j < kc) ? __fdiv_rn(wp[i], S) : 0.f;
+      if (i < c && lane * c + i < kc) run += __fdiv_rn(wp[i], S);
+      ps[i] = run;
+    }
+    float incl = run;  // inclusive scan of the lane totals
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const float p = __shfl_up_sync(0xffffffffu, v, d);
-          if (lane >= d) v += p;
-        }
-        v += carry;
-        float m = fmaxf(v, hi);  // running max: the table must be non-decreasing
+    for (int d = 1; d < 32; d <<= 1) {
+      const float p = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += p;
+    }
+    float off = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) off = 0.f;
+    float mx = off + run;  // this lane's last (largest) entry
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const float p = __shfl_up_sync(0xffffffffu, m, d);
-          if (lane >= d) m = fmaxf(m, p);
-        }
-        if (j < kc) cdf[j + 1] = m;
-        carry = __shfl_sync(0xffffffffu, v, 31);
-        hi = __shfl_sync(0xffffffffu, m, 31);
-      }
+    for (int d = 1; d < 32; d <<= 1) {
+      const float p = __shfl_up_sync(0xffffffffu, mx, d);
+      if (lane >= d) mx = fmaxf(mx, p);
+    }
+    float floor_prev = __shfl_up_sync(0xffffffffu, mx, 1);
+    if (lane == 0) floor_prev = 0.f;
+    __syncwarp();  // previous ray's readers of cdf/buf are done
+#pragma unroll
+    for (int i = 0; i < EPC; ++i) {
+      const int j = lane * c + i;
+      if (i < c && j < kc) cdf[j + 1] = fmaxf(off + ps[i], floor_prev);
     }
     __syncwarp();
     if (a.cdf) {
