@@ -45,33 +45,48 @@ struct ImportanceRegArgs {
   int32_t* idx;
 };
 
-__device__ __forceinline__ void cmp_swap(float& a, float& b, bool ascending) {
+__device__ __forceinline__ void cmp_swap_asc(float& a, float& b) {
   const float lo = fminf(a, b), hi = fmaxf(a, b);
-  a = ascending ? lo : hi;
-  b = ascending ? hi : lo;
+  a = lo;
+  b = hi;
 }
 
 // Full bitonic sort of 32*EPF keys, blocked layout: key index e = lane*EPF + r.
+// All comparators point the same way (the lower index keeps the minimum): each merge phase
+// opens with a "mirror" step (e <-> e ^ (size-1)) instead of alternating directions, so the
+// lane-local compare-exchanges need no direction selects.
 template <int EPF>
 __device__ __forceinline__ void sort_blocked(float (&v)[EPF], int lane) {
   constexpr int M = 32 * EPF;
 #pragma unroll
   for (int size = 2; size <= M; size <<= 1) {
+    // mirror step
+    if (size <= EPF) {
 #pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int r = 0; r < EPF; ++r) {
+        const int pr = r ^ (size - 1);
+        if (r < pr) cmp_swap_asc(v[r], v[pr]);
+      }
+    } else {
+      const int lmask = size / EPF - 1;                       // partner lane = lane ^ lmask
+      const bool keep_min = ((lane & (size / EPF / 2)) == 0);  // lower index of the pair
+      float o[EPF];
+#pragma unroll
+      for (int r = 0; r < EPF; ++r) o[r] = __shfl_xor_sync(0xffffffffu, v[EPF - 1 - r], lmask);
+#pragma unroll
+      for (int r = 0; r < EPF; ++r) v[r] = keep_min ? fminf(v[r], o[r]) : fmaxf(v[r], o[r]);
+    }
+    // half-cleaner steps
+#pragma unroll
+    for (int stride = size >> 2; stride > 0; stride >>= 1) {
       if (stride < EPF) {
 #pragma unroll
         for (int r = 0; r < EPF; ++r) {
-          if ((r & stride) == 0) {
-            const bool asc = (((lane * EPF + r) & size) == 0);
-            cmp_swap(v[r], v[r | stride], asc);
-          }
+          if ((r & stride) == 0) cmp_swap_asc(v[r], v[r | stride]);
         }
       } else {
         const int lstride = stride / EPF;
-        const bool lower = ((lane & lstride) == 0);
-        const bool asc = (((lane * EPF) & size) == 0);
-        const bool keep_min = (lower == asc);
+        const bool keep_min = ((lane & lstride) == 0);
 #pragma unroll
         for (int r = 0; r < EPF; ++r) {
           const float o = __shfl_xor_sync(0xffffffffu, v[r], lstride);
@@ -91,7 +106,7 @@ __device__ __forceinline__ void merge_striped(float (&x)[EPT], int lane) {
       const int istride = stride / 32;
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
-        if ((i & istride) == 0) cmp_swap(x[i], x[i | istride], true);
+        if ((i & istride) == 0) cmp_swap_asc(x[i], x[i | istride]);
       }
     } else {
       const bool keep_min = ((lane & stride) == 0);
