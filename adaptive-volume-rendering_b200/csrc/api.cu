@@ -161,8 +161,9 @@ int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int w
     done = plan.main_rays;
   }
   if (done < R) {
-    return launch_composite_fwd_generic(rgbs + done * K * 4, z + done * K, nullptr, R - done, K, white_back,
-                                        infinity, w ? w + done * K : nullptr, rgb + done * 3, depth + done, st);
+    auto rest = g_force_generic.load() ? launch_composite_fwd_generic : launch_composite_fwd_wray;
+    return rest(rgbs + done * K * 4, z + done * K, nullptr, R - done, K, white_back, infinity,
+                w ? w + done * K : nullptr, rgb + done * 3, depth + done, st);
   }
   return AVR_OK;
 }
@@ -184,10 +185,10 @@ int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, con
     done = plan.main_rays;
   }
   if (done < R) {
-    return launch_composite_bwd_generic(rgbs + done * K * 4, z + done * K, nullptr,
-                                        g_rgb ? g_rgb + done * 3 : nullptr, g_depth ? g_depth + done : nullptr,
-                                        g_w ? g_w + done * K : nullptr, R - done, K, white_back, infinity,
-                                        d_rgbs + done * K * 4, d_z ? d_z + done * K : nullptr, st);
+    auto rest = g_force_generic.load() ? launch_composite_bwd_generic : launch_composite_bwd_wray;
+    return rest(rgbs + done * K * 4, z + done * K, nullptr, g_rgb ? g_rgb + done * 3 : nullptr,
+                g_depth ? g_depth + done : nullptr, g_w ? g_w + done * K : nullptr, R - done, K, white_back,
+                infinity, d_rgbs + done * K * 4, d_z ? d_z + done * K : nullptr, st);
   }
   return AVR_OK;
 }
@@ -199,8 +200,8 @@ int avr_composite_fwd_packed(const float* rgbs, const float* z, const int64_t* o
   if (R == 0) return AVR_OK;
   if (!offsets || !rgb || !depth) return AVR_ERR_BAD_ARG;
   if (S > 0 && (!rgbs || !z || !aligned16(rgbs))) return AVR_ERR_BAD_ARG;
-  return launch_composite_fwd_generic(rgbs, z, offsets, R, 0, white_back, infinity, w, rgb, depth,
-                                      as_stream(stream));
+  auto fn = g_force_generic.load() ? launch_composite_fwd_generic : launch_composite_fwd_wray;
+  return fn(rgbs, z, offsets, R, 0, white_back, infinity, w, rgb, depth, as_stream(stream));
 }
 
 int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* offsets, const float* g_rgb,
@@ -209,8 +210,8 @@ int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* o
   if (R < 0 || S < 0) return AVR_ERR_BAD_ARG;
   if (R == 0 || S == 0) return AVR_OK;
   if (!offsets || !rgbs || !z || !d_rgbs || !aligned16(rgbs) || !aligned16(d_rgbs)) return AVR_ERR_BAD_ARG;
-  return launch_composite_bwd_generic(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs,
-                                      d_z, as_stream(stream));
+  auto fn = g_force_generic.load() ? launch_composite_bwd_generic : launch_composite_bwd_wray;
+  return fn(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs, d_z, as_stream(stream));
 }
 
 /* ------------------------------------------------ host-buffer (end to end) -- */

@@ -14,6 +14,14 @@ int launch_composite_bwd_generic(const float* rgbs, const float* z, const int64_
                                  int K, int white_back, float infinity, float* d_rgbs, float* d_z,
                                  cudaStream_t stream);
 
+// composite_wray.cu — warp per ray, coalesced; any shape, dense (offsets == nullptr) or packed
+int launch_composite_fwd_wray(const float* rgbs, const float* z, const int64_t* offsets, int64_t R, int K,
+                              int white_back, float infinity, float* w, float* rgb, float* depth,
+                              cudaStream_t stream);
+int launch_composite_bwd_wray(const float* rgbs, const float* z, const int64_t* offsets, const float* g_rgb,
+                              const float* g_depth, const float* g_w, int64_t R, int K, int white_back,
+                              float infinity, float* d_rgbs, float* d_z, cudaStream_t stream);
+
 // composite_span.cu — dense, TMA-staged blocked scan.  `span_plan` says whether a
 // shape is eligible and how many leading rays the span kernel covers (the caller
 // runs the generic kernel on the remaining tail rays).

@@ -23,15 +23,51 @@ __device__ __forceinline__ float coarse_depth(float near, float far, int j, int 
   return __fadd_rn(z, __fdiv_rn(__fmul_rn(u, span), (float)K));
 }
 
+// Dense layout, one thread per 4 consecutive samples (16-byte loads/stores; K % 4 == 0 keeps
+// the four in one ray).  The per-bin term (far-near)*(j/K) only needs j/K, which is
+// tabulated once per block in shared memory; dividing by a power-of-two K is done as an
+// exact multiply (bit-identical).
+template <bool kVec4>
 __global__ void __launch_bounds__(256)
 coarse_fwd_dense_kernel(const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
                         const float* __restrict__ u, int64_t total, int K, float* __restrict__ z) {
+  extern __shared__ float s_bins[];  // j / K
+  for (int j = threadIdx.x; j < K; j += blockDim.x) s_bins[j] = __fdiv_rn((float)j, (float)K);
+  __syncthreads();
+  const float kf = (float)K;
+  const bool pow2 = (K & (K - 1)) == 0;
+  const float inv_k = 1.0f / kf;
+  constexpr int V = kVec4 ? 4 : 1;
+  const int64_t n_vec = total / V;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+  float n0 = near[0], f0 = far[0];
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_vec; v += stride) {
+    const int64_t i = v * V;
     const int64_t r = i / K;
     const int j = (int)(i - r * K);
-    const int64_t b = bound_stride ? r : 0;
-    z[i] = coarse_depth(near[b], far[b], j, K, u[i]);
+    if (bound_stride) {
+      n0 = near[r];
+      f0 = far[r];
+    }
+    const float span = __fsub_rn(f0, n0);
+    float uu[V], out[V];
+    if (kVec4) {
+      const float4 q = ldg_stream(reinterpret_cast<const float4*>(u + i));
+      uu[0] = q.x; uu[V > 1 ? 1 : 0] = q.y; uu[V > 2 ? 2 : 0] = q.z; uu[V > 3 ? 3 : 0] = q.w;
+    } else {
+      uu[0] = u[i];
+    }
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const float base = __fadd_rn(n0, __fmul_rn(span, s_bins[j + q]));
+      const float jit = __fmul_rn(uu[q], span);
+      out[q] = __fadd_rn(base, pow2 ? __fmul_rn(jit, inv_k) : __fdiv_rn(jit, kf));
+    }
+    if (kVec4) {
+      stg_stream(reinterpret_cast<float4*>(z + i), make_float4(out[0], out[V > 1 ? 1 : 0], out[V > 2 ? 2 : 0], out[V > 3 ? 3 : 0]));
+    } else {
+      z[i] = out[0];
+    }
   }
 }
 
@@ -279,8 +315,15 @@ int launch_coarse_fwd(const float* near, const float* far, int bound_stride, con
   } else {
     const int64_t total = R * (int64_t)K;
     if (total == 0) return AVR_OK;
-    coarse_fwd_dense_kernel<<<grid_for(total, 256, kNumSMs * 8), 256, 0, stream>>>(near, far, bound_stride, u,
-                                                                                 total, K, z);
+    const bool vec4 = (K % 4 == 0) && aligned16(u) && aligned16(z);
+    const int smem = K * (int)sizeof(float);
+    if (smem > 48 * 1024) return AVR_ERR_UNSUPPORTED;
+    const int blocks = grid_for(total / (vec4 ? 4 : 1), 256, kNumSMs * 8);
+    if (vec4) {
+      coarse_fwd_dense_kernel<true><<<blocks, 256, smem, stream>>>(near, far, bound_stride, u, total, K, z);
+    } else {
+      coarse_fwd_dense_kernel<false><<<blocks, 256, smem, stream>>>(near, far, bound_stride, u, total, K, z);
+    }
   }
   (void)S;
   return check_launch();

@@ -34,11 +34,29 @@ def shard_bounds_packed(offsets: torch.Tensor, world: int, rank: int) -> Tuple[i
     return start, stop
 
 
+class GatherHandle:
+    """Result of an asynchronous output gather: `wait()` returns (rgb_all (R,3), depth_all (R,))."""
+
+    def __init__(self, work, out, shard_sizes, n_max):
+        self._work, self._out, self._sizes, self._n_max = work, out, shard_sizes, n_max
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()       # makes the current stream wait for the collective
+            self._work = None
+        out, n_max = self._out, self._n_max
+        if any(s != n_max for s in self._sizes):
+            out = torch.cat([out[r * n_max: r * n_max + s] for r, s in enumerate(self._sizes)], dim=0)
+        return out[:, :3], out[:, 3]
+
+
 def all_gather_outputs(rgb: torch.Tensor, depth: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
-                       shard_sizes: Optional[list] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       shard_sizes: Optional[list] = None, async_op: bool = False):
     """Gather every rank's (R_local, 3) rgb and (R_local,) depth into (R, 3) / (R,), ordered by
     rank.  Equal shards take one all_gather_into_tensor; unequal shards are padded to the
-    largest (pass `shard_sizes`, the per-rank ray counts)."""
+    largest (pass `shard_sizes`, the per-rank ray counts).  With `async_op` the collective is
+    only enqueued (it overlaps whatever the caller launches next, e.g. the backward kernel)
+    and a GatherHandle is returned."""
     world = dist.get_world_size(group)
     packed = torch.cat([rgb.reshape(-1, 3), depth.reshape(-1, 1)], dim=-1).contiguous()
     n_local = packed.shape[0]
@@ -48,10 +66,9 @@ def all_gather_outputs(rgb: torch.Tensor, depth: torch.Tensor, group: Optional[d
     if n_local < n_max:
         packed = torch.cat([packed, packed.new_zeros(n_max - n_local, 4)], dim=0)
     out = packed.new_empty(world * n_max, 4)
-    dist.all_gather_into_tensor(out, packed, group=group)
-    if any(s != n_max for s in shard_sizes):
-        out = torch.cat([out[r * n_max: r * n_max + s] for r, s in enumerate(shard_sizes)], dim=0)
-    return out[:, :3], out[:, 3]
+    work = dist.all_gather_into_tensor(out, packed, group=group, async_op=async_op)
+    handle = GatherHandle(work if async_op else None, out, shard_sizes, n_max)
+    return handle if async_op else handle.wait()
 
 
 def composite_sharded(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = True, infinity: float = 1.8,

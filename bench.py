@@ -260,9 +260,12 @@ def main():
 
     def step():
         fwd()
-        if dist is not None:  # the path's only exchange: per-ray outputs, 16 B/ray
-            avr_dist.all_gather_outputs(rgb, depth)
+        pending = None
+        if dist is not None:  # the path's only exchange: per-ray outputs, 16 B/ray; overlaps backward
+            pending = avr_dist.all_gather_outputs(rgb, depth, async_op=True)
         bwd()
+        if pending is not None:
+            pending.wait()
 
     for _ in range(args.warmup):
         step()
@@ -289,12 +292,15 @@ def main():
             ev[i][0].record(stream)
             fwd()
             ev[i][1].record(stream)
+            pending = None
             if dist is not None:
-                avr_dist.all_gather_outputs(rgb, depth)
+                pending = avr_dist.all_gather_outputs(rgb, depth, async_op=True)
                 ev[i][1] = torch.cuda.Event(enable_timing=True)
                 ev[i][1].record(stream)
             bwd()
             ev[i][2].record(stream)
+            if pending is not None:
+                pending.wait()
         t_end.record(stream)
         torch.cuda.synchronize(dev)
     if dist is not None:
@@ -387,7 +393,7 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({(20 * k * rays) >> 20} MiB read per pass vs 126 MiB L2)",
                        "kernel_family": "span (TMA bulk-staged blocked scan)" if span else "generic",
                        "samples_per_lane": L.value, "rays_per_tile": rpt.value,
-                       "collective": "all_gather rgb+depth (16 B/ray) per step" if world > 1 else "none"},
+                       "collective": "NCCL all_gather of rgb+depth (16 B/ray) per step, overlapped with the backward kernel" if world > 1 else "none"},
             "samples_per_sec": value * k,
             "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

@@ -51,7 +51,7 @@ def test_golden_forward_backward(name, family, dev):
 
 
 @pytest.mark.parametrize("name", ["k96", "k20", "k7", "k1"])
-def test_golden_grad_weights_and_z(name, dev):
+def test_golden_grad_weights_and_z(name, dev, family):
     """g_w and d_z (AdaptiveVolumeRenderer path; generic kernel)."""
     from avr_b200 import ops
     g = load_golden("composite")
