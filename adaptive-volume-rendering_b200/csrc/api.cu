@@ -135,7 +135,7 @@ int avr_importance_sample_packed(const float* weights, const float* z_coarse, co
   if (!weights || !near || !far || !offsets || !fine_offsets || !u || !u2) return AVR_ERR_BAD_ARG;
   if (z_sorted && !z_coarse) return AVR_ERR_BAD_ARG;
   return launch_importance(weights, z_coarse, u, u2, nullptr, near, far, bound_stride, offsets, fine_offsets, R,
-                           max_coarse, max_fine, 0, 0.f, z_fine, z_sorted, nullptr, nullptr, false, as_stream(stream));
+                           max_coarse, max_fine, 0, 0.f, z_fine, z_sorted, nullptr, nullptr, !g_force_generic.load(), as_stream(stream));
 }
 
 int avr_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, avr_stream_t stream) {

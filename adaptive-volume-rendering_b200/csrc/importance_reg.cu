@@ -35,8 +35,10 @@ struct ImportanceRegArgs {
   const float* near;
   const float* far;
   int bound_stride;
+  const int64_t* offsets;       // packed coarse layout or null
+  const int64_t* fine_offsets;  // packed fine layout or null
   int64_t R;
-  int Kc, n_imp, n_depth;
+  int Kc, n_imp, n_depth;       // dense: exact; packed: Kc/n_imp unused (per-ray counts come from the offsets)
   float depth_std;
   int vec4;  // u/u2 rows are 16-byte aligned (n % 4 == 0 and aligned bases)
   float* z_fine;
@@ -149,16 +151,30 @@ struct RayIn {
   float a[EPF];    // lane's consecutive new samples: u (e < n) or N(0,1) draw (n <= e < n+nd)
   float b[EPF];    // in-bin jitter u2 (e < n)
   float near, far;
+  int kc, n;            // this ray's coarse / importance sample counts
+  int64_t cbase, fbase; // first coarse / importance sample of the ray in the streams
 };
 
 template <int EPF, int EPC>
 __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRegArgs& a, int64_t r, int lane,
                                          bool do_sort) {
-  const int kc = a.Kc, n = a.n_imp, nd = a.n_depth;
+  const int nd = a.n_depth;
+  if (a.offsets) {
+    in.cbase = a.offsets[r];
+    in.kc = (int)(a.offsets[r + 1] - in.cbase);
+    in.fbase = a.fine_offsets[r];
+    in.n = (int)(a.fine_offsets[r + 1] - in.fbase);
+  } else {
+    in.kc = a.Kc;
+    in.n = a.n_imp;
+    in.cbase = r * (int64_t)a.Kc;
+    in.fbase = r * (int64_t)a.n_imp;
+  }
+  const int kc = in.kc, n = in.n;
   const int64_t bi = a.bound_stride ? r : 0;
   in.near = a.near[bi];
   in.far = a.far[bi];
-  const float* wrow = a.weights + r * (int64_t)kc;
+  const float* wrow = a.weights + in.cbase;
   const int c = (kc + 31) >> 5;  // weights per lane, blocked: j = lane*c + i
 #pragma unroll
   for (int i = 0; i < EPC; ++i) {
@@ -166,7 +182,7 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
     in.w[i] = (i < c && j < kc) ? wrow[j] : 0.f;
   }
   if (do_sort) {
-    const float* zrow = a.z_coarse + r * (int64_t)kc;
+    const float* zrow = a.z_coarse + in.cbase;
 #pragma unroll
     for (int i = 0; i < EPC; ++i) {
       const int j = i * 32 + lane;
@@ -174,8 +190,8 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
     }
   }
   const int e0 = lane * EPF;
-  const float* urow = a.u + r * (int64_t)n;
-  const float* u2row = a.u2 + r * (int64_t)n;
+  const float* urow = a.u + in.fbase;
+  const float* u2row = a.u2 + in.fbase;
   if (EPF >= 4 && a.vec4 && e0 + EPF <= n) {  // 16-byte loads of the lane's consecutive draws
 #pragma unroll
     for (int q = 0; q < EPF; q += 4) {
@@ -214,20 +230,14 @@ importance_reg_kernel(const ImportanceRegArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* cdf = s_cdf[warp];
   float* buf = s_buf[warp];
-  const int kc = a.Kc, n = a.n_imp, nd = a.n_depth;
-  const int total = kc + n + nd;
+  const int nd = a.n_depth;
   const bool do_sort = (a.z_sorted != nullptr);
-  const float kcf = (float)kc;
-  const bool kc_pow2 = (kc & (kc - 1)) == 0;
-  const float inv_kc = 1.0f / kcf;  // exact when kc is a power of two: x*inv_kc == x/kc bit for bit
   const int64_t warps = (int64_t)gridDim.x * kRegWarps;
   const int e0 = lane * EPF;
-
-  // the +inf tail of the table never changes
-  for (int j = kc + 1 + lane; j < P; j += 32) cdf[j] = CUDART_INF_F;
   if (lane == 0) cdf[0] = 0.f;
 
   int64_t r = blockIdx.x * (int64_t)kRegWarps + warp;
+  bool first_ray = true;
   RayIn<EPF, EPC> cur;
   if (r < a.R) load_ray<EPF, EPC>(cur, a, r, lane, do_sort);
   for (; r < a.R; r += warps) {
@@ -237,6 +247,11 @@ importance_reg_kernel(const ImportanceRegArgs a) {
 
     const float near = cur.near, far = cur.far;
     const float span = __fsub_rn(far, near);
+    const int kc = cur.kc, n = cur.n;
+    const int total = kc + n + nd;
+    const float kcf = (float)kc;
+    const bool kc_pow2 = (kc & (kc - 1)) == 0;
+    const float inv_kc = 1.0f / kcf;  // exact when kc is a power of two: x*inv_kc == x/kc bit for bit
 
     // ---- 1. cdf table -----------------------------------------------------------------
     // blocked scan: each lane owns c consecutive bins; local running sums, one exclusive
@@ -282,16 +297,20 @@ importance_reg_kernel(const ImportanceRegArgs a) {
       const int j = lane * c + i;
       if (i < c && j < kc) cdf[j + 1] = fmaxf(off + ps[i], floor_prev);
     }
+    if (a.offsets || first_ray) {  // the +inf tail only moves when the count changes (packed)
+      for (int j = kc + 1 + lane; j < P; j += 32) cdf[j] = CUDART_INF_F;
+      first_ray = false;
+    }
     __syncwarp();
     if (a.cdf) {
-      float* out = a.cdf + r * (int64_t)(kc + 1);
+      float* out = a.cdf + (cur.cbase + r);
       for (int j = lane; j <= kc; j += 32) out[j] = cdf[j];
     }
 
     // ---- 2. the lane's EPF consecutive new samples --------------------------------------
     float v[EPF];
-    int32_t* irow = a.idx ? a.idx + r * (int64_t)n : nullptr;
-    float* frow = a.z_fine ? a.z_fine + r * (int64_t)n : nullptr;
+    int32_t* irow = a.idx ? a.idx + cur.fbase : nullptr;
+    float* frow = a.z_fine ? a.z_fine + cur.fbase : nullptr;
 #pragma unroll
     for (int q = 0; q < EPF; ++q) {
       const int e = e0 + q;
@@ -353,7 +372,7 @@ importance_reg_kernel(const ImportanceRegArgs a) {
       }
 
       // ---- 5. coalesced store of the first `total` keys ------------------------------------
-      float* out = a.z_sorted + r * (int64_t)total;
+      float* out = a.z_sorted + (cur.cbase + cur.fbase + r * (int64_t)nd);
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
         const int q = i * 32 + lane;
@@ -377,8 +396,10 @@ static int launch_reg(const ImportanceRegArgs& a, cudaStream_t stream) {
 // back to the shared-memory kernel).
 int launch_importance_reg(const float* weights, const float* z_coarse, const float* u, const float* u2,
                           const float* normals, const float* near, const float* far, int bound_stride,
-                          int64_t R, int Kc, int n_imp, int n_depth, float depth_std, float* z_fine,
-                          float* z_sorted, float* cdf, int32_t* idx, cudaStream_t stream) {
+                          const int64_t* offsets, const int64_t* fine_offsets, int64_t R, int Kc, int n_imp,
+                          int n_depth, float depth_std, float* z_fine, float* z_sorted, float* cdf, int32_t* idx,
+                          cudaStream_t stream) {
+  // packed layout: Kc / n_imp are the caller's per-ray maxima and size the register variant
   const int m = n_imp + (z_sorted ? n_depth : 0);
   int epf = 1;
   while (32 * epf < m) epf <<= 1;
@@ -394,12 +415,14 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   a.near = near;
   a.far = far;
   a.bound_stride = bound_stride;
+  a.offsets = offsets;
+  a.fine_offsets = fine_offsets;
   a.R = R;
   a.Kc = Kc;
   a.n_imp = n_imp;
   a.n_depth = z_sorted ? n_depth : 0;
   a.depth_std = depth_std;
-  a.vec4 = ((n_imp & 3) == 0) && aligned16(u) && aligned16(u2);
+  a.vec4 = !offsets && ((n_imp & 3) == 0) && aligned16(u) && aligned16(u2);
   a.z_fine = z_fine;
   a.z_sorted = z_sorted;
   a.cdf = cdf;

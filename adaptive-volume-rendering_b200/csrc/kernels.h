@@ -52,8 +52,9 @@ int launch_importance(const float* weights, const float* z_coarse, const float* 
 // shape does not fit (more than 256 new samples or more than 512 merged samples per ray)
 int launch_importance_reg(const float* weights, const float* z_coarse, const float* u, const float* u2,
                           const float* normals, const float* near, const float* far, int bound_stride,
-                          int64_t R, int Kc, int n_imp, int n_depth, float depth_std, float* z_fine,
-                          float* z_sorted, float* cdf, int32_t* idx, cudaStream_t stream);
+                          const int64_t* offsets, const int64_t* fine_offsets, int64_t R, int Kc, int n_imp,
+                          int n_depth, float depth_std, float* z_fine, float* z_sorted, float* cdf, int32_t* idx,
+                          cudaStream_t stream);
 int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, cudaStream_t stream);
 
 }  // namespace avr

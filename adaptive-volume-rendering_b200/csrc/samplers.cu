@@ -343,9 +343,10 @@ int launch_importance(const float* weights, const float* z_coarse, const float* 
                       int n_depth, float depth_std, float* z_fine, float* z_sorted, float* cdf,
                       int32_t* idx, bool allow_fast, cudaStream_t stream) {
   if (R == 0) return AVR_OK;
-  if (allow_fast && !offsets && n_imp > 0) {
-    const int rc = launch_importance_reg(weights, z_coarse, u, u2, normals, near, far, bound_stride, R, Kc, n_imp,
-                                         n_depth, depth_std, z_fine, z_sorted, cdf, idx, stream);
+  if (allow_fast && n_imp > 0) {
+    const int rc = launch_importance_reg(weights, z_coarse, u, u2, normals, near, far, bound_stride, offsets,
+                                         fine_offsets, R, Kc, n_imp, n_depth, depth_std, z_fine, z_sorted, cdf, idx,
+                                         stream);
     if (rc != AVR_ERR_UNSUPPORTED) return rc;
   }
   // dense: Kc/n_imp are exact; packed: they are the caller's per-ray maxima

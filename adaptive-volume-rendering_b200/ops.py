@@ -270,8 +270,9 @@ class CompositePacked(torch.autograd.Function):
         g_depth = None if g_depth is None else _f32c(g_depth)
         g_w = None if g_w is None else _f32c(g_w)
         want_dz = ctx.needs_input_grad[1]
-        d_rgbs = torch.zeros_like(rgbs_c)
-        d_z = torch.zeros_like(z_c) if want_dz else None
+        # every sample belongs to a ray with count > 0, so the kernel writes every element
+        d_rgbs = torch.empty_like(rgbs_c)
+        d_z = torch.empty_like(z_c) if want_dz else None
         r = offsets.numel() - 1
         with torch.cuda.device(z.device):
             check(_lib.load().avr_composite_bwd_packed(ptr(rgbs_c), ptr(z_c), ptr(offsets), ptr(g_rgb), ptr(g_depth),

@@ -87,20 +87,25 @@ def main():
                        torch.relu(torch.randn(s, 1, device=dev, generator=g)) * 30], -1)
         ms = timeit(lambda: ops.composite_packed_fwd_raw(x, z, offsets, True, 1.8, True), a.iters)
         report("composite_fwd_packed 8..256", ms, rp, 24 * s / rp + 24, samples=s)
-        xg = x.clone().requires_grad_(True)
-        rgb, depth, w = ops.composite_packed(xg, z, offsets, True, 1.8, True)
+        import avr_b200
+        lib = avr_b200.load_library()
+        rgb, depth, w = ops.composite_packed_fwd_raw(x, z, offsets, True, 1.8, True)
         g1, g2 = torch.randn_like(rgb), torch.randn_like(depth)
+        dx = torch.empty_like(x)
+        sp = torch.cuda.current_stream().cuda_stream
 
         def bwd():
-            torch.autograd.grad([rgb, depth], [xg], [g1, g2], retain_graph=True)
+            rc = lib.avr_composite_bwd_packed(x.data_ptr(), z.data_ptr(), offsets.data_ptr(), g1.data_ptr(), g2.data_ptr(),
+                                              None, rp, s, 1, 1.8, dx.data_ptr(), None, sp)
+            assert rc == 0
 
         ms = timeit(bwd, a.iters)
-        report("composite_bwd_packed 8..256 (incl. autograd + zeros_like)", ms, rp, 36 * s / rp + 24, samples=s)
+        report("composite_bwd_packed 8..256", ms, rp, 36 * s / rp + 24, samples=s)
         fo = torch.zeros(rp + 1, dtype=torch.int64, device=dev)
         fo[1:] = torch.cumsum(counts // 2, 0)
         sf = int(fo[-1])
         uf, uf2 = torch.rand(sf, device=dev, generator=g), torch.rand(sf, device=dev, generator=g)
-        ms = timeit(lambda: ops.importance_sample_packed(w.detach(), z, nr, fr, uf, uf2, offsets, fo, 256, 128), a.iters)
+        ms = timeit(lambda: ops.importance_sample_packed(w, z, nr, fr, uf, uf2, offsets, fo, 256, 128), a.iters)
         report("importance_sample_packed Kc 8..256 -> Kc/2", ms, rp, (12 * s + 12 * sf) / rp + 24, samples=s, fine=sf)
 
 
