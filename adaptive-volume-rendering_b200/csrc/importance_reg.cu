@@ -234,8 +234,6 @@ importance_reg_kernel(const ImportanceRegArgs a) {
   const bool do_sort = (a.z_sorted != nullptr);
   const int64_t warps = (int64_t)gridDim.x * kRegWarps;
   const int e0 = lane * EPF;
-  if (lane == 0) cdf[0] = 0.f;
-
   int64_t r = blockIdx.x * (int64_t)kRegWarps + warp;
   bool first_ray = true;
   RayIn<EPF, EPC> cur;
@@ -291,38 +289,53 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     }
     float floor_prev = __shfl_up_sync(0xffffffffu, mx, 1);
     if (lane == 0) floor_prev = 0.f;
+    // The table is stored as an implicit binary search tree in breadth-first order (heap
+    // index 1 = root): the nodes one search step can touch are contiguous, so the 32 lanes'
+    // probes fall into distinct banks (a sorted table probed at power-of-two strides is a
+    // worst case for bank conflicts).  Sorted position q in [1, Pc) holds cdf[q], +inf
+    // beyond Kc; cdf[0] = 0 is implicit.
+    int m = 1;  // tree depth: Pc = 2^m > kc
+    while ((1 << m) <= kc) ++m;
+    const int Pc = 1 << m;
+    auto heap_index = [m](int q) {
+      const int tz = __ffs(q) - 1;
+      return (1 << (m - 1 - tz)) + (q >> (tz + 1));
+    };
     __syncwarp();  // previous ray's readers of cdf/buf are done
+    float* cdf_out = a.cdf ? a.cdf + (cur.cbase + r) : nullptr;
 #pragma unroll
     for (int i = 0; i < EPC; ++i) {
       const int j = lane * c + i;
-      if (i < c && j < kc) cdf[j + 1] = fmaxf(off + ps[i], floor_prev);
+      if (i < c && j < kc) {
+        const float val = fmaxf(off + ps[i], floor_prev);
+        cdf[heap_index(j + 1)] = val;
+        if (cdf_out) cdf_out[j + 1] = val;
+      }
     }
+    if (cdf_out && lane == 0) cdf_out[0] = 0.f;
     if (a.offsets || first_ray) {  // the +inf tail only moves when the count changes (packed)
-      for (int j = kc + 1 + lane; j < P; j += 32) cdf[j] = CUDART_INF_F;
+      for (int q = kc + 1 + lane; q < Pc; q += 32) cdf[heap_index(q)] = CUDART_INF_F;
       first_ray = false;
     }
     __syncwarp();
-    if (a.cdf) {
-      float* out = a.cdf + (cur.cbase + r);
-      for (int j = lane; j <= kc; j += 32) out[j] = cdf[j];
-    }
 
     // ---- 2. the lane's EPF consecutive new samples --------------------------------------
     float v[EPF];
     int32_t* irow = a.idx ? a.idx + cur.fbase : nullptr;
     float* frow = a.z_fine ? a.z_fine + cur.fbase : nullptr;
+    // descend the tree: node <- 2*node + (tree[node] <= u); after m steps node - Pc is the
+    // number of entries cdf[q >= 1] <= u, i.e. clamp_min(searchsorted(cdf, u, right=True) - 1, 0)
+    int node[EPF];
+#pragma unroll
+    for (int q = 0; q < EPF; ++q) node[q] = 1;
+    for (int step = 0; step < m; ++step) {
+#pragma unroll
+      for (int q = 0; q < EPF; ++q) node[q] = 2 * node[q] + (cdf[node[q]] <= cur.a[q] ? 1 : 0);
+    }
 #pragma unroll
     for (int q = 0; q < EPF; ++q) {
       const int e = e0 + q;
-      // cnt = #{j : cdf[j] <= u} over the +inf-padded table (branch-free upper bound);
-      // bin = max(cnt - 1, 0)  ==  clamp_min(searchsorted(cdf, u, right=True) - 1, 0)
-      const float uu = cur.a[q];
-      int cnt = 0;
-#pragma unroll
-      for (int step = P >> 1; step > 0; step >>= 1) {
-        if (cdf[cnt + step - 1] <= uu) cnt += step;
-      }
-      const int bin = cnt > 0 ? cnt - 1 : 0;
+      const int bin = node[q] - Pc;
       const float num = __fadd_rn((float)bin, cur.b[q]);
       const float t = kc_pow2 ? __fmul_rn(num, inv_kc) : __fdiv_rn(num, kcf);
       float val = __fadd_rn(near, __fmul_rn(span, t));
