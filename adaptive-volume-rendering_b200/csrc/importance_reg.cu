@@ -328,9 +328,13 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     int node[EPF];
 #pragma unroll
     for (int q = 0; q < EPF; ++q) node[q] = 1;
-    for (int step = 0; step < m; ++step) {
+    constexpr int kMaxDepth = (EPT == 2) ? 6 : (EPT == 4) ? 7 : (EPT == 8) ? 8 : 9;  // log2(P)
 #pragma unroll
-      for (int q = 0; q < EPF; ++q) node[q] = 2 * node[q] + (cdf[node[q]] <= cur.a[q] ? 1 : 0);
+    for (int step = 0; step < kMaxDepth; ++step) {
+      if (step < m) {  // warp-uniform
+#pragma unroll
+        for (int q = 0; q < EPF; ++q) node[q] = 2 * node[q] + (cdf[node[q]] <= cur.a[q] ? 1 : 0);
+      }
     }
 #pragma unroll
     for (int q = 0; q < EPF; ++q) {
