@@ -66,34 +66,6 @@ __device__ __forceinline__ ChunkIn load_chunk(const float4* __restrict__ rgbs, c
   return in;
 }
 
-// The raw inputs of one chunk (6 registers), so that all of a ray's loads can be issued
-// before any of them is consumed: memory-level parallelism comes from the whole ray being
-// in flight per warp, not from one 32-sample chunk at a time.
-struct ChunkRaw {
-  float4 c;
-  float zk, z_after;
-};
-__device__ __forceinline__ ChunkRaw load_raw(const float4* __restrict__ rgbs, const float* __restrict__ z,
-                                             int64_t begin, int64_t count, int64_t k) {
-  ChunkRaw raw;
-  const bool valid = k < count;
-  raw.c = valid ? rgbs[begin + k] : make_float4(0.f, 0.f, 0.f, 0.f);
-  raw.zk = valid ? z[begin + k] : 0.f;
-  raw.z_after = (k + 1 < count) ? z[begin + k + 1] : 0.f;
-  return raw;
-}
-__device__ __forceinline__ ChunkIn make_chunk(const ChunkRaw& raw, int64_t count, int64_t k, float infinity) {
-  ChunkIn in;
-  in.valid = k < count;
-  in.last = (k == count - 1);
-  in.c = raw.c;
-  in.zk = raw.zk;
-  in.zn = in.last ? infinity : raw.z_after;
-  in.delta = in.last ? kLastDelta : in.zn - in.zk;
-  if (!in.valid) in.delta = 0.f;
-  return in;
-}
-
 __global__ void __launch_bounds__(kWrayWarps * 32)
 composite_fwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restrict__ z,
                           const int64_t* __restrict__ offsets, int64_t R, int K, int white_back,
@@ -105,7 +77,9 @@ composite_fwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
     const WraySpan s = wray_span(offsets, r, K);
     float carry = 1.0f;
     float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, acc = 0.f;
-    auto consume = [&](const ChunkIn& in, int64_t k) {
+    for (int64_t c0 = 0; c0 < s.count; c0 += 32) {
+      const int64_t k = c0 + lane;
+      const ChunkIn in = load_chunk(rgbs, z, s.begin, s.count, k, infinity);
       const Opacity o = opacity(in.c.w, in.delta);   // invalid lanes: alpha = 0, t = 1
       const float incl = warp_scan_mul(o.t, lane);
       float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -118,26 +92,6 @@ composite_fwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
       ad += w * in.zn;
       acc += w;
       carry *= __shfl_sync(0xffffffffu, incl, 31);
-    };
-    const int n_chunks = (int)((s.count + 31) >> 5);
-    if (n_chunks <= kWrayMaxChunks) {
-      ChunkRaw raw[kWrayMaxChunks];
-#pragma unroll
-      for (int i = 0; i < kWrayMaxChunks; ++i) {
-        if (i < n_chunks) raw[i] = load_raw(rgbs, z, s.begin, s.count, (int64_t)i * 32 + lane);
-      }
-#pragma unroll
-      for (int i = 0; i < kWrayMaxChunks; ++i) {
-        if (i < n_chunks) {
-          const int64_t k = (int64_t)i * 32 + lane;
-          consume(make_chunk(raw[i], s.count, k, infinity), k);
-        }
-      }
-    } else {
-      for (int64_t c0 = 0; c0 < s.count; c0 += 32) {
-        const int64_t k = c0 + lane;
-        consume(load_chunk(rgbs, z, s.begin, s.count, k, infinity), k);
-      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -221,19 +175,14 @@ composite_bwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
 
     // sweep 1, front to back: transmittance before every sample
     float e_c[kWrayMaxChunks], T_c[kWrayMaxChunks];
-    ChunkRaw raw[kWrayMaxChunks];
     if (in_regs) {
-#pragma unroll
-      for (int i = 0; i < kWrayMaxChunks; ++i) {
-        if (i < n_chunks) raw[i] = load_raw(rgbs, z, s.begin, s.count, (int64_t)i * 32 + lane);
-      }
       float carry = 1.0f;
 #pragma unroll
       for (int i = 0; i < kWrayMaxChunks; ++i) {
         e_c[i] = 1.0f;
         T_c[i] = 0.f;
         if (i < n_chunks) {
-          const ChunkIn in = make_chunk(raw[i], s.count, (int64_t)i * 32 + lane, infinity);
+          const ChunkIn in = load_chunk(rgbs, z, s.begin, s.count, (int64_t)i * 32 + lane, infinity);
           const Opacity o = opacity(in.c.w, in.delta);
           const float incl = warp_scan_mul(o.t, lane);
           float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -262,8 +211,9 @@ composite_bwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
     float Q_carry = 0.f;
     float pend_ddelta0 = 0.f;  // dL/d delta of the first sample of the chunk to the right
     bool have_pend = false;
-    auto do_chunk = [&](int i, float e, float T, const ChunkIn& in) {
+    auto do_chunk = [&](int i, float e, float T) {
       const int64_t k = (int64_t)i * 32 + lane;
+      const ChunkIn in = load_chunk(rgbs, z, s.begin, s.count, k, infinity);
       const float gw = (g_w && in.valid) ? g_w[s.begin + k] : 0.f;
       float4 d_out;
       float ddelta, a_next;
@@ -286,7 +236,7 @@ composite_bwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
     if (in_regs) {
 #pragma unroll
       for (int i = kWrayMaxChunks - 1; i >= 0; --i) {
-        if (i < n_chunks) do_chunk(i, e_c[i], T_c[i], make_chunk(raw[i], s.count, (int64_t)i * 32 + lane, infinity));
+        if (i < n_chunks) do_chunk(i, e_c[i], T_c[i]);
       }
     } else {
       for (int i = n_chunks - 1; i >= 0; --i) {
@@ -297,7 +247,7 @@ composite_bwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
         const ChunkIn in = load_chunk(rgbs, z, s.begin, s.count, k, infinity);
         const float e = opacity(in.c.w, in.delta).e;
         __syncwarp();
-        do_chunk(i, e, T, in);
+        do_chunk(i, e, T);
       }
     }
     if (d_z && lane == 0) d_z[s.begin] = -pend_ddelta0;
