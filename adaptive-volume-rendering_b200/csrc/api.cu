@@ -168,6 +168,22 @@ int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int w
   return AVR_OK;
 }
 
+int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t R, int K, int white_back, float infinity,
+                             float* w, float* rgb, float* depth, void* const* peer_gathered, int n_peers,
+                             int64_t row0, avr_stream_t stream) {
+  if (R < 0 || K < 1 || n_peers < 1 || row0 < 0 || !peer_gathered) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!rgbs || !z || !rgb || !depth || !aligned16(rgbs)) return AVR_ERR_BAD_ARG;
+  for (int p = 0; p < n_peers; ++p)
+    if (!peer_gathered[p] || !aligned16(peer_gathered[p])) return AVR_ERR_BAD_ARG;
+  SpanPlan plan;
+  // the fused epilogue lives in the span kernel: the whole batch must be tileable
+  if (g_force_generic.load() || !span_plan(R, K, rgbs, z, &plan) || plan.main_rays != R || (w && !aligned16(w)))
+    return AVR_ERR_UNSUPPORTED;
+  return launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, as_stream(stream),
+                                   peer_gathered, n_peers, row0);
+}
+
 int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, const float* g_depth,
                       const float* g_w, int64_t R, int K, int white_back, float infinity, float* d_rgbs,
                       float* d_z, avr_stream_t stream) {

@@ -35,6 +35,8 @@
 
 namespace avr {
 
+constexpr int kMaxPeers = 16;
+
 template <int L>
 struct SpanCfg {
   static constexpr int kTileSamples = 32 * L;
@@ -59,6 +61,12 @@ struct SpanArgs {
   int tail_rays;          // rays in the last tile (== rays_per_tile when it is full)
   int white_back;
   float infinity;
+  // fused all-gather (forward only): every finished ray is also written, packed as
+  // (r,g,b,depth), into row peer_row0 + ray of each peer's gathered [world*R,4] buffer —
+  // plain 16-byte stores to peer memory mapped over NVLink
+  float4* peers[kMaxPeers];
+  int n_peers;
+  int64_t peer_row0;
 };
 
 // A lane's run inside a tile (identical for every full tile of a launch).
@@ -165,6 +173,10 @@ __device__ __forceinline__ void store_ray(const SpanArgs& a, int64_t ray, const 
   o3[1] = t.g + bg;
   o3[2] = t.b + bg;
   a.depth[ray] = t.d;
+  if (a.n_peers > 0) {
+    const float4 packed = make_float4(t.r + bg, t.g + bg, t.b + bg, t.d);
+    for (int p = 0; p < a.n_peers; ++p) a.peers[p][a.peer_row0 + ray] = packed;
+  }
 }
 
 struct RayGrad {
@@ -795,8 +807,12 @@ static SpanArgs make_args(const SpanPlan& plan, int K, int white_back, float inf
 
 int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, void* const* peers, int n_peers, int64_t peer_row0) {
   SpanArgs a = make_args(plan, K, white_back, infinity);
+  if (n_peers > kMaxPeers) return AVR_ERR_UNSUPPORTED;
+  a.n_peers = n_peers;
+  a.peer_row0 = peer_row0;
+  for (int p = 0; p < n_peers; ++p) a.peers[p] = reinterpret_cast<float4*>(peers[p]);
   a.rgbs = rgbs;
   a.z = z;
   a.w = w;

@@ -90,3 +90,68 @@ def composite_sharded(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = Tr
         sizes = [int(t.item()) for t in all_n]
         rgb_all, depth_all = all_gather_outputs(rgb.detach(), depth.detach(), group, sizes)
     return rgb, depth, rgb_all, depth_all
+
+
+class FusedGather:
+    """All-gather of the per-ray outputs fused into the forward compositing kernel.
+
+    Every rank owns a symmetric-memory buffer ``gathered`` of shape (world*R_local, 4) =
+    (r,g,b,depth) per ray; the span kernel's epilogue stores each finished ray straight into
+    row ``rank*R_local + ray`` of EVERY rank's buffer (16-byte stores to peer memory over
+    NVLink / NVSwitch), so the exchange rides along with the kernel instead of following it.
+    ``finish()`` is the cross-rank barrier after which ``gathered`` is complete everywhere.
+    Falls back (``available == False``) when symmetric memory cannot be set up; callers then
+    use ``all_gather_outputs`` (NCCL).
+    """
+
+    def __init__(self, rays_local: int, device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        self.rays_local = rays_local
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.available = False
+        self.error = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.gathered = symm_mem.empty((self.world * rays_local, 4), dtype=torch.float32, device=device)
+            self.handle = symm_mem.rendezvous(self.gathered, self.group)
+            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            self._ptr_array = (ctypes.c_void_p * self.world)(*ptrs)
+            self.handle.barrier()
+            self.available = True
+        except Exception as exc:  # pragma: no cover - depends on the box
+            self.error = f"{type(exc).__name__}: {exc}"
+
+    def composite_fwd(self, rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = True, infinity: float = 1.8,
+                      want_w: bool = True):
+        """Forward compositing of this rank's rays + fused gather.  Returns (rgb, depth, w) or
+        None if the shape is not eligible for the fused kernel (caller falls back)."""
+        from . import _lib
+        from .ops import _f32c, _stream
+
+        rgbs, z = _f32c(rgbs), _f32c(z)
+        k = z.shape[-1]
+        r = z.numel() // k
+        if r != self.rays_local:
+            raise _lib.AvrError(f"FusedGather was sized for {self.rays_local} rays per rank, got {r}")
+        dev = z.device
+        w = torch.empty(r, k, dtype=torch.float32, device=dev) if want_w else None
+        rgb = torch.empty(r, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(r, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().avr_composite_fwd_gather(
+                rgbs.data_ptr(), z.data_ptr(), r, k, int(bool(white_back)), float(infinity),
+                None if w is None else w.data_ptr(), rgb.data_ptr(), depth.data_ptr(),
+                self._ptr_array, self.world, self.rank * self.rays_local, _stream(z))
+        if rc == -4:   # AVR_ERR_UNSUPPORTED
+            return None
+        _lib.check(rc, "avr_composite_fwd_gather")
+        return rgb, depth, w
+
+    def finish(self):
+        """Cross-rank barrier (stream-ordered): afterwards every rank's ``gathered`` holds all rays."""
+        self.handle.barrier()
+        return self.gathered[:, :3], self.gathered[:, 3]

@@ -195,6 +195,9 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="override rays per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: all-gather of rgb+depth fused into the forward kernel (peer stores into "
+                         "symmetric memory; falls back to nccl if unavailable) or a NCCL all_gather overlapped with backward")
     args = ap.parse_args()
     rays, k, desc = WORKLOADS[args.workload]
     if args.rays:
@@ -248,7 +251,26 @@ def main():
                                        ctypes.byref(main_rays))
     launches_per_step = 2 * (1 + (1 if (span and main_rays.value < rays) else 0)) if span else 2
 
+    fused = None
+    if dist is not None and args.gather == "fused":
+        fused = avr_dist.FusedGather(rays, dev)
+        ok = torch.tensor([1 if fused.available else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            if rank == 0:
+                print(f"[bench] fused gather unavailable ({fused.error}); using NCCL", file=sys.stderr)
+            fused = None
+    gather_mode = "none" if dist is None else ("fused epilogue (peer stores over NVLink into symmetric memory) + barrier"
+                                               if fused is not None else "NCCL all_gather overlapped with the backward kernel")
+
+    def fwd_fused():
+        rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
+                                          depth.data_ptr(), fused._ptr_array, fused.world, fused.rank * rays, sp)
+        assert rc == 0, (rc, lib.avr_last_cuda_error())
+
     def fwd():
+        if fused is not None:
+            return fwd_fused()
         rc = lib.avr_composite_fwd(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
                                    depth.data_ptr(), sp)
         assert rc == 0, lib.avr_last_cuda_error()
@@ -261,11 +283,13 @@ def main():
     def step():
         fwd()
         pending = None
-        if dist is not None:  # the path's only exchange: per-ray outputs, 16 B/ray; overlaps backward
-            pending = avr_dist.all_gather_outputs(rgb, depth, async_op=True)
+        if dist is not None and fused is None:  # the path's only exchange: per-ray outputs, 16 B/ray
+            pending = avr_dist.all_gather_outputs(rgb, depth, async_op=True)   # overlaps backward
         bwd()
         if pending is not None:
             pending.wait()
+        if fused is not None:
+            fused.finish()
 
     for _ in range(args.warmup):
         step()
@@ -293,7 +317,7 @@ def main():
             fwd()
             ev[i][1].record(stream)
             pending = None
-            if dist is not None:
+            if dist is not None and fused is None:
                 pending = avr_dist.all_gather_outputs(rgb, depth, async_op=True)
                 ev[i][1] = torch.cuda.Event(enable_timing=True)
                 ev[i][1].record(stream)
@@ -301,6 +325,8 @@ def main():
             ev[i][2].record(stream)
             if pending is not None:
                 pending.wait()
+            if fused is not None:
+                fused.finish()
         t_end.record(stream)
         torch.cuda.synchronize(dev)
     if dist is not None:
@@ -393,7 +419,7 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({(20 * k * rays) >> 20} MiB read per pass vs 126 MiB L2)",
                        "kernel_family": "span (TMA bulk-staged blocked scan)" if span else "generic",
                        "samples_per_lane": L.value, "rays_per_tile": rpt.value,
-                       "collective": "NCCL all_gather of rgb+depth (16 B/ray) per step, overlapped with the backward kernel" if world > 1 else "none"},
+                       "collective": f"all-gather of rgb+depth (16 B/ray) per step: {gather_mode}"},
             "samples_per_sec": value * k,
             "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

@@ -129,6 +129,20 @@ AVR_API int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int 
                       int white_back, float infinity,
                       float* w, float* rgb, float* depth, avr_stream_t stream);
 
+/* Forward compositing with the output all-gather fused into the kernel's epilogue (multi-GPU):
+ * besides rgb/depth, every ray's (r,g,b,depth) is stored as one float4 into row `row0 + ray` of
+ * each of the `n_peers` buffers in `peer_gathered` (HOST array of DEVICE pointers, each a
+ * [world*R, 4] fp32 buffer; peers' buffers are peer-mapped over NVLink, e.g. the `buffer_ptrs`
+ * of a torch symmetric-memory allocation; include the local buffer to fill the local copy).
+ * The caller orders the ranks afterwards (a barrier) before reading the gathered buffers.
+ * Returns AVR_ERR_UNSUPPORTED when the batch is not eligible for the span kernels (the
+ * caller then composites normally and all-gathers with NCCL). */
+AVR_API int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t R, int K,
+                                     int white_back, float infinity,
+                                     float* w, float* rgb, float* depth,
+                                     void* const* peer_gathered, int n_peers, int64_t row0,
+                                     avr_stream_t stream);
+
 /* Gradient of the above; transmittance is recomputed, nothing is saved by forward.
  *   g_rgb [R,3] (may be NULL = zeros), g_depth [R] (may be NULL), g_w [R,K] (may be NULL)
  *   d_rgbs [R,K,4] (required), d_z [R,K] (may be NULL: VolumeRenderer's z carries no grad) */
