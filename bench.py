@@ -160,7 +160,7 @@ def time_cpu(rays, k, steps, warmup):
     return times, cores
 
 
-def run_reference_arm(args, k, desc):
+def run_reference_arm(args, k, desc, emit):
     """--impl reference: the reference's own CPU implementation of the path (its torch op
     sequence, restated in oracle/ because a Python reference cannot travel to the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -181,11 +181,20 @@ def run_reference_arm(args, k, desc):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm
 def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL prints its version banner to
+    # stdout) are pointed at stderr until the line is written
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -203,7 +212,7 @@ def main():
     if args.rays:
         rays = args.rays
     if args.impl == "reference":
-        run_reference_arm(args, k, desc)
+        run_reference_arm(args, k, desc, emit)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -261,7 +270,7 @@ def main():
                 print(f"[bench] fused gather unavailable ({fused.error}); using NCCL", file=sys.stderr)
             fused = None
     gather_mode = "none" if dist is None else ("fused epilogue (peer stores over NVLink into symmetric memory) + barrier"
-                                               if fused is not None else "NCCL all_gather overlapped with the backward kernel")
+                                               if fused is not None else "NCCL all_gather_into_tensor between forward and backward")
 
     def fwd_fused():
         rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
@@ -282,12 +291,11 @@ def main():
 
     def step():
         fwd()
-        pending = None
         if dist is not None and fused is None:  # the path's only exchange: per-ray outputs, 16 B/ray
-            pending = avr_dist.all_gather_outputs(rgb, depth, async_op=True)   # overlaps backward
+            # in-stream: an async all-gather cannot co-schedule with the persistent backward
+            # kernel (it holds every SM) and measured 2.6x slower than this
+            avr_dist.all_gather_outputs(rgb, depth)
         bwd()
-        if pending is not None:
-            pending.wait()
         if fused is not None:
             fused.finish()
 
@@ -316,15 +324,12 @@ def main():
             ev[i][0].record(stream)
             fwd()
             ev[i][1].record(stream)
-            pending = None
             if dist is not None and fused is None:
-                pending = avr_dist.all_gather_outputs(rgb, depth, async_op=True)
+                avr_dist.all_gather_outputs(rgb, depth)
                 ev[i][1] = torch.cuda.Event(enable_timing=True)
                 ev[i][1].record(stream)
             bwd()
             ev[i][2].record(stream)
-            if pending is not None:
-                pending.wait()
             if fused is not None:
                 fused.finish()
         t_end.record(stream)
@@ -426,7 +431,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
         }
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
