@@ -216,6 +216,9 @@ int avr_composite_fwd_packed(const float* rgbs, const float* z, const int64_t* o
   if (R == 0) return AVR_OK;
   if (!offsets || !rgb || !depth) return AVR_ERR_BAD_ARG;
   if (S > 0 && (!rgbs || !z || !aligned16(rgbs))) return AVR_ERR_BAD_ARG;
+  if (!g_force_generic.load() && S > 0 && span_packed_eligible(rgbs, z, w, nullptr))
+    return launch_composite_fwd_span_packed(rgbs, z, offsets, R, S, white_back, infinity, w, rgb, depth,
+                                            as_stream(stream));
   auto fn = g_force_generic.load() ? launch_composite_fwd_generic : launch_composite_fwd_wray;
   return fn(rgbs, z, offsets, R, 0, white_back, infinity, w, rgb, depth, as_stream(stream));
 }
@@ -226,6 +229,9 @@ int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* o
   if (R < 0 || S < 0) return AVR_ERR_BAD_ARG;
   if (R == 0 || S == 0) return AVR_OK;
   if (!offsets || !rgbs || !z || !d_rgbs || !aligned16(rgbs) || !aligned16(d_rgbs)) return AVR_ERR_BAD_ARG;
+  if (!g_force_generic.load() && !g_w && !d_z && span_packed_eligible(rgbs, z, nullptr, d_rgbs))
+    return launch_composite_bwd_span_packed(rgbs, z, offsets, g_rgb, g_depth, R, S, white_back, infinity, d_rgbs,
+                                            as_stream(stream));
   auto fn = g_force_generic.load() ? launch_composite_bwd_generic : launch_composite_bwd_wray;
   return fn(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs, d_z, as_stream(stream));
 }

@@ -1,0 +1,427 @@
+// Span compositing kernels for the PACKED (ragged) layout: per-ray sample counts given by
+// offsets[R+1] (BASELINE.json config 4, "adaptive" rays of 8..256 samples).
+//
+// Same machinery as the dense span kernels (composite_span.cu): whole-ray tiles staged in
+// shared memory by 1-D bulk async copies, per-warp private ring + mbarriers, each lane walks
+// L consecutive samples, one segmented warp scan per tile — but the tiling is dynamic:
+//
+//   * each warp owns a contiguous range of rays holding ~1/n-th of the SAMPLES (ranges are
+//     cut by a warp-wide 32-ary search of `offsets`, so short and long rays balance out);
+//   * walking its range, the warp packs consecutive rays greedily into tiles of at most
+//     C = 32*L samples (at most 32 rays): the next 32 ray ends are read with one coalesced
+//     load one iteration ahead, a ballot finds how many fit;
+//   * a tile only takes rays with more than L samples, so a lane's run holds at most one
+//     ray boundary and the branch-free "simple" tile bodies apply unchanged; the per-lane
+//     run description (ray, boundary position) is found per tile by a 6-step search of the
+//     tile's ray-end table in shared memory;
+//   * rays a tile cannot take — count <= L (incl. empty rays) or count > C — are composited
+//     by the same warp with the warp-per-ray routine straight from global memory;
+//   * z and w slices start at arbitrary sample offsets: the stage keeps the global 16-byte
+//     phase (bulk copies cover the aligned interior, up to 3 elements at either end go
+//     through ordinary loads/stores).
+#include <climits>
+#include <cstdlib>
+
+#include "avr_common.cuh"
+#include "kernels.h"
+#include "span_bodies.cuh"
+#include "wray_device.cuh"
+
+namespace avr {
+
+constexpr int kPkL = 13;
+constexpr int kPkC = 32 * kPkL;  // samples per tile
+constexpr int kPkStages = 3;
+constexpr int kPkWarps = 2;
+constexpr int kPkRgbsBytes = kPkC * 16;
+constexpr int kPkZFloats = kPkC + 8;  // + phase shift (<= 3) + one z past the tile + slack
+constexpr int kPkStageBytes = kPkRgbsBytes + kPkZFloats * 4 + 32 * 4;  // rgbs | z | ray ends
+constexpr int kPkSmemBytes = kPkWarps * kPkStages * kPkStageBytes + kPkWarps * kPkStages * 8;
+
+struct PackedArgs {
+  SpanArgs sp;  // rgbs, z, outputs, gradients, white_back, infinity (tile fields unused)
+  const int64_t* offsets;
+  int64_t R, S;
+};
+
+enum { kItemNone = 0, kItemTile = 1, kItemRay = 2 };
+struct Item {
+  int64_t r0;  // first ray
+  int64_t sb;  // first sample
+  int64_t n_s; // samples
+  int nr;      // rays
+  int kind;
+};
+
+// smallest r in [0, R] with offsets[r] >= target (offsets[R] = S >= target); all lanes cooperate
+__device__ __forceinline__ int64_t warp_lower_bound(const int64_t* __restrict__ offsets, int64_t R,
+                                                    int64_t target, int lane) {
+  if (target <= 0) return 0;
+  int64_t lo = 0, hi = R;  // offsets[lo] < target <= offsets[hi]
+  while (hi - lo > 1) {
+    const int64_t chunk = (hi - lo + 31) >> 5;
+    int64_t q = lo + (int64_t)(lane + 1) * chunk;
+    if (q > hi) q = hi;
+    const bool ge = offsets[q] >= target;
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    const int f = __ffs(m) - 1;  // m != 0: the last probe is hi
+    const int64_t q_f = __shfl_sync(0xffffffffu, q, f);
+    const int64_t q_prev = __shfl_sync(0xffffffffu, q, f > 0 ? f - 1 : 0);
+    hi = q_f;
+    if (f > 0) lo = q_prev;
+  }
+  return hi;
+}
+
+struct Window {
+  int64_t ostart;  // offsets[r]
+  int64_t oend;    // offsets[r + 1 + lane] (INT64_MAX past the warp's range)
+};
+__device__ __forceinline__ Window load_window(const int64_t* __restrict__ offsets, int64_t r, int64_t rb, int lane) {
+  Window w;
+  w.ostart = (r < rb) ? offsets[r] : 0;
+  w.oend = (r + lane < rb) ? offsets[r + 1 + lane] : INT64_MAX;
+  return w;
+}
+
+// Decide what the next work item starting at ray r is.  `rel_end` returns the lane's ray end
+// relative to the item start (INT_MAX for lanes past it); meaningful for tiles.
+__device__ __forceinline__ Item next_item(const Window& w, int64_t r, int64_t rb, int lane, int& rel_end) {
+  Item it;
+  it.r0 = r;
+  it.sb = w.ostart;
+  it.kind = kItemNone;
+  it.nr = 0;
+  it.n_s = 0;
+  rel_end = INT_MAX;
+  if (r >= rb) return it;
+  const bool valid = (r + lane < rb);
+  const int64_t rel64 = valid ? (w.oend - w.ostart) : (int64_t)INT_MAX;
+  const int rel = rel64 > (int64_t)INT_MAX ? INT_MAX : (int)rel64;
+  int prev = __shfl_up_sync(0xffffffffu, rel, 1);
+  if (lane == 0) prev = 0;
+  const int cnt = rel - prev;
+  const bool ok = valid && rel <= kPkC && cnt > kPkL;
+  const unsigned mask = __ballot_sync(0xffffffffu, ok);
+  const int nr = (mask == 0xffffffffu) ? 32 : (__ffs(~mask) - 1);  // leading rays that fit
+  if (nr == 0) {  // first ray is too short or too long for a tile: composite it on its own
+    it.kind = kItemRay;
+    it.nr = 1;
+    it.n_s = __shfl_sync(0xffffffffu, rel64, 0);
+    return it;
+  }
+  it.kind = kItemTile;
+  it.nr = nr;
+  it.n_s = __shfl_sync(0xffffffffu, rel, nr - 1);
+  rel_end = (lane < nr) ? rel : INT_MAX;
+  return it;
+}
+
+struct PkPipe {
+  unsigned char* base;
+  uint64_t* bars;
+  __device__ __forceinline__ float4* rgbs_stage(int st) const {
+    return reinterpret_cast<float4*>(base + st * kPkStageBytes);
+  }
+  __device__ __forceinline__ float* z_stage(int st) const {
+    return reinterpret_cast<float*>(base + st * kPkStageBytes + kPkRgbsBytes);
+  }
+  __device__ __forceinline__ int* ends_stage(int st) const {
+    return reinterpret_cast<int*>(base + st * kPkStageBytes + kPkRgbsBytes + kPkZFloats * 4);
+  }
+  __device__ __forceinline__ void init(unsigned char* smem, int warp, int lane) {
+    base = smem + warp * (kPkStages * kPkStageBytes);
+    bars = reinterpret_cast<uint64_t*>(smem + kPkWarps * (kPkStages * kPkStageBytes)) + warp * kPkStages;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < kPkStages; ++s) mbar_init(&bars[s], 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+  }
+};
+
+// z elements [zb, zb + bulk) go by bulk copy (zb = sb rounded down to 4; everything inside the
+// buffer's last full 16 bytes); the rest of the tile's z (<= 3 elements at the very end of the
+// buffer) is patched by plain loads after the wait
+__device__ __forceinline__ int z_bulk_elems(int64_t sb, int n_s, int64_t S) {
+  const int shift = (int)(sb & 3);
+  const int64_t zb = sb - shift;
+  int64_t end = zb + ((shift + n_s + 3) & ~3);
+  const int64_t cap = S & ~(int64_t)3;
+  if (end > cap) end = cap;
+  return end > zb ? (int)(end - zb) : 0;
+}
+
+// all lanes: publish the tile's ray ends, lane 0: issue the bulk loads
+__device__ __forceinline__ void issue_tile(const PkPipe& pipe, int st, const PackedArgs& a, const Item& it,
+                                           int rel_end, int lane) {
+  pipe.ends_stage(st)[lane] = rel_end;
+  __syncwarp();
+  if (lane == 0) {
+    const int n_s = (int)it.n_s;
+    const int shift = (int)(it.sb & 3);
+    const int zel = z_bulk_elems(it.sb, n_s, a.S);
+    const uint32_t rb = (uint32_t)n_s * 16u, zbytes = (uint32_t)zel * 4u;
+    mbar_expect_tx(&pipe.bars[st], rb + zbytes);
+    bulk_g2s(pipe.rgbs_stage(st), a.sp.rgbs + it.sb * 4, rb, &pipe.bars[st]);
+    if (zel > 0) bulk_g2s(pipe.z_stage(st), a.sp.z + (it.sb - shift), zbytes, &pipe.bars[st]);
+  }
+}
+
+// after the mbarrier wait: fetch the (<= 3) tile samples of z the bulk copy could not cover
+__device__ __forceinline__ void patch_z_tail(const PkPipe& pipe, int st, const PackedArgs& a, const Item& it, int lane) {
+  const int n_s = (int)it.n_s;
+  const int shift = (int)(it.sb & 3);
+  const int64_t zb = it.sb - shift;
+  const int64_t covered = zb + z_bulk_elems(it.sb, n_s, a.S);
+  const int64_t gi = covered + lane;
+  if (gi < it.sb + n_s) pipe.z_stage(st)[gi - zb] = a.sp.z[gi];  // at most 3 lanes (warp-uniform loop-free)
+  __syncwarp();
+}
+
+// The lane's run inside a ragged tile: which ray its first sample belongs to and where (if
+// anywhere) that ray ends inside the run.  ends[i] = end of the tile's i-th ray, INT_MAX padded.
+__device__ __forceinline__ Run ragged_run(const int* ends, int n_s, int lane) {
+  Run run;
+  run.s0 = lane * kPkL;
+  const int rem = n_s - run.s0;
+  run.nvalid = rem < 0 ? 0 : (rem > kPkL ? kPkL : rem);
+  int cnt = 0;  // rays ending at or before s0
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    if (ends[cnt + step - 1] <= run.s0) cnt += step;
+  }
+  if (ends[cnt] <= run.s0) ++cnt;   // cnt in [0, 32]
+  if (cnt > 31) cnt = 31;           // idle lanes only
+  const int start = cnt > 0 ? ends[cnt - 1] : 0;
+  const int end = ends[cnt];
+  run.ray0 = cnt;
+  run.k0 = run.s0 - start;
+  const int to_head = (run.k0 == 0) ? 0 : (end == INT_MAX ? kPkL : end - run.s0);
+  run.carry_len = to_head < run.nvalid ? to_head : run.nvalid;
+  const int e = (end == INT_MAX) ? INT_MAX : end - 1 - run.s0;
+  run.end_pos = e < run.nvalid ? e : -1;
+  return run;
+}
+
+template <bool kWriteW>
+__global__ void __launch_bounds__(kPkWarps * 32)
+composite_fwd_span_packed_kernel(const PackedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PkPipe pipe;
+  pipe.init(smem, warp, lane);
+
+  const int64_t gw = (int64_t)blockIdx.x * kPkWarps + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * kPkWarps;
+  const int64_t ra = warp_lower_bound(a.offsets, a.R, (a.S / n_warps) * gw + min(gw, a.S % n_warps), lane);
+  const int64_t rb = (gw + 1 == n_warps)
+                         ? a.R
+                         : warp_lower_bound(a.offsets, a.R, (a.S / n_warps) * (gw + 1) + min(gw + 1, a.S % n_warps), lane);
+  const float4* rgbs4 = reinterpret_cast<const float4*>(a.sp.rgbs);
+
+  int64_t tiles = 0;  // tiles issued so far (tile t lives in stage t % NS, parity (t / NS) & 1)
+  int rel_end;
+  Window win = load_window(a.offsets, ra, rb, lane);
+  Item cur = next_item(win, ra, rb, lane, rel_end);
+  int64_t cur_tile = -1;
+  if (cur.kind == kItemTile) {
+    cur_tile = tiles++;
+    issue_tile(pipe, (int)(cur_tile % kPkStages), a, cur, rel_end, lane);
+  }
+  int64_t r_next = ra + cur.nr;
+  win = load_window(a.offsets, r_next, rb, lane);
+
+  while (cur.kind != kItemNone) {
+    // ---- prepare the next item (its window was loaded one iteration ago) and start its loads
+    Item nxt = next_item(win, r_next, rb, lane, rel_end);
+    int64_t nxt_tile = -1;
+    if (nxt.kind == kItemTile) {
+      nxt_tile = tiles++;
+      if (kWriteW && lane == 0) bulk_wait_read<1>();  // the store that last read this stage is done
+      issue_tile(pipe, (int)(nxt_tile % kPkStages), a, nxt, rel_end, lane);
+    }
+    r_next += nxt.nr;
+    if (nxt.kind != kItemNone) win = load_window(a.offsets, r_next, rb, lane);
+
+    // ---- process the current item
+    if (cur.kind == kItemTile) {
+      const int st = (int)(cur_tile % kPkStages);
+      const int n_s = (int)cur.n_s;
+      const int shift = (int)(cur.sb & 3);
+      mbar_wait(&pipe.bars[st], (uint32_t)((cur_tile / kPkStages) & 1));
+      patch_z_tail(pipe, st, a, cur, lane);
+      const Run run = ragged_run(pipe.ends_stage(st), n_s, lane);
+      const float4* rg = pipe.rgbs_stage(st) + run.s0;
+      float* zs = pipe.z_stage(st) + shift + run.s0;
+      fwd_tile_simple<kPkL, kWriteW>(a.sp, run, rg, zs, cur.r0, lane);
+      if (kWriteW) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        // aligned interior by bulk store, up to 3 samples at either end by ordinary stores
+        int a0 = (4 - shift) & 3;
+        if (a0 > n_s) a0 = n_s;
+        const int len = (n_s - a0) & ~3;
+        const float* zt = pipe.z_stage(st) + shift;  // tile sample s at zt[s]
+        float* wg = a.sp.w + cur.sb;
+        if (lane == 0 && len > 0) bulk_s2g(wg + a0, zt + a0, (uint32_t)len * 4u);
+        if (lane == 0) bulk_commit();
+        if (lane < a0) wg[lane] = zt[lane];
+        const int t0 = a0 + len;
+        if (t0 + lane < n_s) wg[t0 + lane] = zt[t0 + lane];
+      } else {
+        __syncwarp();
+      }
+    } else {
+      wray_fwd_ray(rgbs4, a.sp.z, cur.sb, cur.n_s, cur.r0, a.sp.white_back, a.sp.infinity, a.sp.w, a.sp.rgb,
+                   a.sp.depth, lane);
+    }
+    cur = nxt;
+    cur_tile = nxt_tile;
+  }
+  if (kWriteW && lane == 0) bulk_wait_all<0>();
+}
+
+__global__ void __launch_bounds__(kPkWarps * 32)
+composite_bwd_span_packed_kernel(const PackedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PkPipe pipe;
+  pipe.init(smem, warp, lane);
+
+  const int64_t gw = (int64_t)blockIdx.x * kPkWarps + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * kPkWarps;
+  const int64_t ra = warp_lower_bound(a.offsets, a.R, (a.S / n_warps) * gw + min(gw, a.S % n_warps), lane);
+  const int64_t rb = (gw + 1 == n_warps)
+                         ? a.R
+                         : warp_lower_bound(a.offsets, a.R, (a.S / n_warps) * (gw + 1) + min(gw + 1, a.S % n_warps), lane);
+  const float4* rgbs4 = reinterpret_cast<const float4*>(a.sp.rgbs);
+  float4* d4 = reinterpret_cast<float4*>(a.sp.d_rgbs);
+
+  int64_t tiles = 0;
+  int rel_end;
+  Window win = load_window(a.offsets, ra, rb, lane);
+  Item cur = next_item(win, ra, rb, lane, rel_end);
+  int64_t cur_tile = -1;
+  if (cur.kind == kItemTile) {
+    cur_tile = tiles++;
+    issue_tile(pipe, (int)(cur_tile % kPkStages), a, cur, rel_end, lane);
+  }
+  int64_t r_next = ra + cur.nr;
+  win = load_window(a.offsets, r_next, rb, lane);
+
+  while (cur.kind != kItemNone) {
+    Item nxt = next_item(win, r_next, rb, lane, rel_end);
+    int64_t nxt_tile = -1;
+    if (nxt.kind == kItemTile) {
+      nxt_tile = tiles++;
+      if (lane == 0) bulk_wait_read<1>();
+      issue_tile(pipe, (int)(nxt_tile % kPkStages), a, nxt, rel_end, lane);
+    }
+    r_next += nxt.nr;
+    if (nxt.kind != kItemNone) win = load_window(a.offsets, r_next, rb, lane);
+
+    if (cur.kind == kItemTile) {
+      const int st = (int)(cur_tile % kPkStages);
+      const int n_s = (int)cur.n_s;
+      const int shift = (int)(cur.sb & 3);
+      mbar_wait(&pipe.bars[st], (uint32_t)((cur_tile / kPkStages) & 1));
+      patch_z_tail(pipe, st, a, cur, lane);
+      const Run run = ragged_run(pipe.ends_stage(st), n_s, lane);
+      RayGrad gA{0.f, 0.f, 0.f, 0.f, 0.f}, gB{0.f, 0.f, 0.f, 0.f, 0.f};
+      if (run.nvalid > 0) {
+        gA = load_ray_grad(a.sp, cur.r0 + run.ray0);
+        gB = (run.end_pos >= 0 && run.end_pos + 1 < run.nvalid) ? load_ray_grad(a.sp, cur.r0 + run.ray0 + 1) : gA;
+      }
+      float4* rg = pipe.rgbs_stage(st) + run.s0;
+      const float* zs = pipe.z_stage(st) + shift + run.s0;
+      bwd_tile_simple<kPkL>(a.sp, run, rg, zs, gA, gB, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(a.sp.d_rgbs + cur.sb * 4, pipe.rgbs_stage(st), (uint32_t)n_s * 16u);
+        bulk_commit();
+      }
+    } else if (cur.n_s > 0) {
+      wray_bwd_ray<false>(rgbs4, a.sp.z, cur.sb, cur.n_s, cur.r0, a.sp.g_rgb, a.sp.g_depth, nullptr,
+                          a.sp.white_back, a.sp.infinity, d4, nullptr, lane);
+    }
+    cur = nxt;
+    cur_tile = nxt_tile;
+  }
+  if (lane == 0) bulk_wait_all<0>();
+}
+
+// ---- host side -----------------------------------------------------------------------
+bool span_packed_eligible(const void* rgbs, const void* z, const void* w_or_null, const void* d_rgbs_or_null) {
+  const char* off = std::getenv("AVR_PACKED_SPAN");
+  if (off && off[0] == '0') return false;
+  return aligned16(rgbs) && aligned16(z) && aligned16(w_or_null) && aligned16(d_rgbs_or_null);
+}
+
+template <typename KernelT>
+static int packed_launch(KernelT kernel, const PackedArgs& a, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmemBytes);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e);
+    (void)cudaGetLastError();
+    return AVR_ERR_LAUNCH;
+  }
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kPkWarps * 32, kPkSmemBytes);
+  if (e != cudaSuccess || occ < 1) {
+    set_last_cuda_error(e);
+    (void)cudaGetLastError();
+    return AVR_ERR_LAUNCH;
+  }
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // enough samples per warp to amortise the range search; never more warps than tiles
+  int64_t want = (a.S / kPkC + kPkWarps) / kPkWarps;
+  if (want < 1) want = 1;
+  const int64_t cap = (int64_t)sms * occ;
+  const int grid = (int)(want < cap ? want : cap);
+  kernel<<<grid, kPkWarps * 32, kPkSmemBytes, stream>>>(a);
+  return check_launch();
+}
+
+int launch_composite_fwd_span_packed(const float* rgbs, const float* z, const int64_t* offsets, int64_t R,
+                                     int64_t S, int white_back, float infinity, float* w, float* rgb,
+                                     float* depth, cudaStream_t stream) {
+  if (R == 0) return AVR_OK;
+  PackedArgs a{};
+  a.sp.rgbs = rgbs;
+  a.sp.z = z;
+  a.sp.w = w;
+  a.sp.rgb = rgb;
+  a.sp.depth = depth;
+  a.sp.white_back = white_back;
+  a.sp.infinity = infinity;
+  a.offsets = offsets;
+  a.R = R;
+  a.S = S;
+  return w ? packed_launch(composite_fwd_span_packed_kernel<true>, a, stream)
+           : packed_launch(composite_fwd_span_packed_kernel<false>, a, stream);
+}
+
+int launch_composite_bwd_span_packed(const float* rgbs, const float* z, const int64_t* offsets,
+                                     const float* g_rgb, const float* g_depth, int64_t R, int64_t S,
+                                     int white_back, float infinity, float* d_rgbs, cudaStream_t stream) {
+  if (R == 0 || S == 0) return AVR_OK;
+  PackedArgs a{};
+  a.sp.rgbs = rgbs;
+  a.sp.z = z;
+  a.sp.g_rgb = g_rgb;
+  a.sp.g_depth = g_depth;
+  a.sp.d_rgbs = d_rgbs;
+  a.sp.white_back = white_back;
+  a.sp.infinity = infinity;
+  a.offsets = offsets;
+  a.R = R;
+  a.S = S;
+  return packed_launch(composite_bwd_span_packed_kernel, a, stream);
+}
+
+}  // namespace avr

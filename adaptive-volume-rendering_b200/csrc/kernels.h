@@ -39,6 +39,15 @@ int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const flo
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
                               cudaStream_t stream);
 
+// composite_span_packed.cu — packed layout, TMA-staged whole-ray tiles packed on the fly
+bool span_packed_eligible(const void* rgbs, const void* z, const void* w_or_null, const void* d_rgbs_or_null);
+int launch_composite_fwd_span_packed(const float* rgbs, const float* z, const int64_t* offsets, int64_t R,
+                                     int64_t S, int white_back, float infinity, float* w, float* rgb,
+                                     float* depth, cudaStream_t stream);
+int launch_composite_bwd_span_packed(const float* rgbs, const float* z, const int64_t* offsets,
+                                     const float* g_rgb, const float* g_depth, int64_t R, int64_t S,
+                                     int white_back, float infinity, float* d_rgbs, cudaStream_t stream);
+
 // samplers.cu
 int launch_coarse_fwd(const float* near, const float* far, int bound_stride, const float* u,
                       const int64_t* offsets, int64_t R, int K, int64_t S, float* z, cudaStream_t stream);

@@ -1,0 +1,315 @@
+// Tile bodies and warp scans shared by the dense (composite_span.cu) and packed
+// (composite_span_packed.cu) span kernels.  See composite_span.cu for the design.
+#pragma once
+
+#include "avr_common.cuh"
+
+namespace avr {
+
+constexpr int kMaxPeers = 16;
+
+template <int L>
+struct SpanCfg {
+  static constexpr int kTileSamples = 32 * L;
+  static constexpr int kRgbsBytes = kTileSamples * 16;
+  static constexpr int kZBytes = kTileSamples * 4;
+  // +16: the lane that owns the last sample reads one z past the tile (value unused)
+  static constexpr int kStageBytes = kRgbsBytes + kZBytes + 16;
+};
+
+struct SpanArgs {
+  const float* rgbs;
+  const float* z;
+  float* w;               // fwd (nullable)
+  float* rgb;             // fwd
+  float* depth;           // fwd
+  const float* g_rgb;     // bwd (nullable)
+  const float* g_depth;   // bwd (nullable)
+  float* d_rgbs;          // bwd
+  int64_t n_tiles;
+  int K;
+  int rays_per_tile;
+  int tail_rays;          // rays in the last tile (== rays_per_tile when it is full)
+  int white_back;
+  float infinity;
+  // fused all-gather (forward only): every finished ray is also written, packed as
+  // (r,g,b,depth), into row peer_row0 + ray of each peer's gathered [world*R,4] buffer —
+  // plain 16-byte stores to peer memory mapped over NVLink
+  float4* peers[kMaxPeers];
+  int n_peers;
+  int64_t peer_row0;
+};
+
+// A lane's run inside a tile (identical for every full tile of a launch).
+struct Run {
+  int s0;         // first sample (tile-relative)
+  int nvalid;     // samples of the run that exist (0..L)
+  int k0;         // position of the first sample inside its ray
+  int ray0;       // tile-relative ray of the first sample
+  int carry_len;  // leading samples that belong to a ray started in an earlier lane
+  int end_pos;    // simple bodies: run index of the sample that ends a ray, or -1
+};
+
+template <int L>
+__device__ __forceinline__ Run make_run(int lane, int K, int n_s) {
+  Run r;
+  r.s0 = lane * L;
+  int rem = n_s - r.s0;
+  r.nvalid = rem < 0 ? 0 : (rem > L ? L : rem);
+  r.k0 = r.s0 % K;
+  r.ray0 = r.s0 / K;
+  int to_head = (r.k0 == 0) ? 0 : K - r.k0;
+  r.carry_len = to_head < r.nvalid ? to_head : r.nvalid;
+  int e = K - 1 - r.k0;
+  r.end_pos = e < r.nvalid ? e : -1;
+  return r;
+}
+
+struct Sums {
+  float r, g, b, d, a;
+};
+__device__ __forceinline__ Sums zero_sums() { return Sums{0.f, 0.f, 0.f, 0.f, 0.f}; }
+
+// ---- warp scans over per-lane aggregates ------------------------------------------
+// Forward, segmented: element = (flag, T, sums); combine(A earlier, B later) =
+// (A.T*B.T, A.s + A.T*B.s) unless B.flag.  Returns the EXCLUSIVE result (carry into the lane).
+__device__ __forceinline__ void scan_fwd_exclusive(int lane, bool flag, float& T, Sums& s) {
+  unsigned f = flag ? 1u : 0u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float Tp = __shfl_up_sync(0xffffffffu, T, d);
+    float pr = __shfl_up_sync(0xffffffffu, s.r, d);
+    float pg = __shfl_up_sync(0xffffffffu, s.g, d);
+    float pb = __shfl_up_sync(0xffffffffu, s.b, d);
+    float pd = __shfl_up_sync(0xffffffffu, s.d, d);
+    float pa = __shfl_up_sync(0xffffffffu, s.a, d);
+    unsigned fp = __shfl_up_sync(0xffffffffu, f, d);
+    if (lane >= d && !f) {
+      s.r = pr + Tp * s.r;
+      s.g = pg + Tp * s.g;
+      s.b = pb + Tp * s.b;
+      s.d = pd + Tp * s.d;
+      s.a = pa + Tp * s.a;
+      T = Tp * T;
+      f = fp;
+    }
+  }
+  T = __shfl_up_sync(0xffffffffu, T, 1);
+  s.r = __shfl_up_sync(0xffffffffu, s.r, 1);
+  s.g = __shfl_up_sync(0xffffffffu, s.g, 1);
+  s.b = __shfl_up_sync(0xffffffffu, s.b, 1);
+  s.d = __shfl_up_sync(0xffffffffu, s.d, 1);
+  s.a = __shfl_up_sync(0xffffffffu, s.a, 1);
+  if (lane == 0) {
+    T = 1.0f;
+    s = zero_sums();
+  }
+}
+
+__device__ __forceinline__ float scan_fwd_exclusive_T(int lane, bool flag, float T) {
+  unsigned f = flag ? 1u : 0u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float Tp = __shfl_up_sync(0xffffffffu, T, d);
+    unsigned fp = __shfl_up_sync(0xffffffffu, f, d);
+    if (lane >= d && !f) {
+      T = Tp * T;
+      f = fp;
+    }
+  }
+  T = __shfl_up_sync(0xffffffffu, T, 1);
+  return lane == 0 ? 1.0f : T;
+}
+
+// Reverse: element = affine map Q_left = A + B*Q_right (B == 0 where a ray ends inside
+// the run, which is what stops the carry).  Returns Q entering the lane from the right.
+__device__ __forceinline__ float scan_rev_exclusive(int lane, float A, float B) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float Ap = __shfl_down_sync(0xffffffffu, A, d);
+    float Bp = __shfl_down_sync(0xffffffffu, B, d);
+    if (lane + d < 32) {
+      A = A + B * Ap;
+      B = B * Bp;
+    }
+  }
+  float q = __shfl_down_sync(0xffffffffu, A, 1);
+  return lane == 31 ? 0.f : q;
+}
+
+__device__ __forceinline__ void store_ray(const SpanArgs& a, int64_t ray, const Sums& t) {
+  const float bg = a.white_back ? 1.0f - t.a : 0.f;
+  float* o3 = a.rgb + ray * 3;
+  o3[0] = t.r + bg;
+  o3[1] = t.g + bg;
+  o3[2] = t.b + bg;
+  a.depth[ray] = t.d;
+  if (a.n_peers > 0) {
+    const float4 packed = make_float4(t.r + bg, t.g + bg, t.b + bg, t.d);
+    for (int p = 0; p < a.n_peers; ++p) a.peers[p][a.peer_row0 + ray] = packed;
+  }
+}
+
+struct RayGrad {
+  float r, g, b, d, bg;  // g_rgb, g_depth, and the white-background term sum(g_rgb)
+};
+__device__ __forceinline__ RayGrad load_ray_grad(const SpanArgs& a, int64_t ray) {
+  RayGrad g{0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.g_rgb) {
+    g.r = a.g_rgb[ray * 3 + 0];
+    g.g = a.g_rgb[ray * 3 + 1];
+    g.b = a.g_rgb[ray * 3 + 2];
+  }
+  if (a.g_depth) g.d = a.g_depth[ray];
+  g.bg = a.white_back ? (g.r + g.g + g.b) : 0.f;
+  return g;
+}
+
+// =====================================================================================
+// Tile bodies.  rg / zs point at the lane's OWN first sample inside the stage.
+// =====================================================================================
+
+// ---- forward, K > L: at most one ray end per run, at run index p -----------------------
+// Samples [0..p] (segment A) close the ray that contains the run's first sample; samples
+// after p (segment B) open the next ray.  Without an end the whole run is segment B.
+// Samples past the tile's end (idle lanes / partial tail tile) come after a ray end, so
+// whatever stale shared memory they read only reaches aggregates nobody consumes.
+template <int L, bool kWriteW>
+__device__ __forceinline__ void fwd_tile_simple(const SpanArgs& a, const Run& run, const float4* rg, float* zs,
+                                                int64_t ray_base, int lane) {
+  const int p = run.end_pos;
+  float wl[L];
+  float Tl = 1.0f;
+  Sums A = zero_sums(), B = zero_sums();
+  float zk = zs[0];
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    const bool last = (j == p);
+    const bool in_a = (j <= p);
+    const float4 c = rg[j];
+    const float z_after = zs[j + 1];
+    const float zn = last ? a.infinity : z_after;
+    const float delta = last ? kLastDelta : zn - zk;
+    const Opacity o = opacity(c.w, delta);
+    const float w = o.alpha * Tl;
+    wl[j] = w;
+    if (in_a) {
+      A.r += w * c.x;
+      A.g += w * c.y;
+      A.b += w * c.z;
+      A.d += w * zn;
+      A.a += w;
+    } else {
+      B.r += w * c.x;
+      B.g += w * c.y;
+      B.b += w * c.z;
+      B.d += w * zn;
+      B.a += w;
+    }
+    Tl = last ? 1.0f : Tl * o.t;
+    zk = z_after;
+  }
+  const bool head0 = (run.k0 == 0);
+  float T_in = Tl;
+  Sums s_in = B;
+  scan_fwd_exclusive(lane, head0 || p >= 0 || run.nvalid == 0, T_in, s_in);
+  if (head0) {
+    T_in = 1.0f;
+    s_in = zero_sums();
+  }
+  if (p >= 0) {
+    Sums t;
+    t.r = s_in.r + T_in * A.r;
+    t.g = s_in.g + T_in * A.g;
+    t.b = s_in.b + T_in * A.b;
+    t.d = s_in.d + T_in * A.d;
+    t.a = s_in.a + T_in * A.a;
+    store_ray(a, ray_base + run.ray0, t);
+  }
+  if (kWriteW) {
+    __syncwarp();  // every lane has finished reading z from this stage
+#pragma unroll
+    for (int j = 0; j < L; ++j) zs[j] = (p < 0 || j <= p) ? wl[j] * T_in : wl[j];
+  }
+}
+
+// ---- backward, K > L -------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void bwd_tile_simple(const SpanArgs& a, const Run& run, float4* rg, const float* zs,
+                                                const RayGrad& gA, const RayGrad& gB, int lane) {
+  const int p = run.end_pos;
+  // walk 1, front to back: cache e_j and the local transmittance before sample j; sum the
+  // first segment's weighted terms (they give the reverse-scan aggregate A)
+  float ej[L], Tj[L];
+  float Tl = 1.0f;
+  Sums s = zero_sums();
+  {
+    float zk = zs[0];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const bool last = (j == p);
+      const bool first_seg = (p < 0 || j <= p);
+      const float4 c = rg[j];
+      const float z_after = zs[j + 1];
+      const float zn = last ? a.infinity : z_after;
+      const float delta = last ? kLastDelta : zn - zk;
+      const Opacity o = opacity(c.w, delta);
+      ej[j] = o.e;
+      Tj[j] = Tl;
+      if (first_seg) {
+        const float w = o.alpha * Tl;
+        s.r += w * c.x;
+        s.g += w * c.y;
+        s.b += w * c.z;
+        s.d += w * zn;
+        s.a += w;
+      }
+      Tl = last ? 1.0f : Tl * o.t;
+      zk = z_after;
+    }
+  }
+  const bool head0 = (run.k0 == 0);
+  const bool idle = (run.nvalid == 0);
+  // reverse-scan element of this run: Q_left = A + B * Q_right
+  float A = gA.r * s.r + gA.g * s.g + gA.b * s.b + gA.d * s.d - gA.bg * s.a;
+  float Bm = Tl;
+  if (p >= 0 || idle) Bm = 0.f;
+  if (idle) A = 0.f;
+  float T_in = scan_fwd_exclusive_T(lane, head0 || p >= 0 || idle, Tl);
+  if (head0) T_in = 1.0f;
+  float Q = scan_rev_exclusive(lane, A, Bm);
+
+  // walk 2, back to front: final gradients, written over the rgbs stage in place
+  float zn = zs[L];
+#pragma unroll
+  for (int j = L - 1; j >= 0; --j) {
+    const bool last = (j == p);
+    const bool first_seg = (p < 0 || j <= p);
+    const float4 c = rg[j];
+    const float zk = zs[j];
+    if (last) {
+      Q = 0.f;
+      zn = a.infinity;
+    }
+    const float delta = last ? kLastDelta : zn - zk;
+    const float e = ej[j];
+    const float alpha = 1.0f - e;
+    const float t = (1.0f - alpha) + kTransEps;
+    const float T = first_seg ? Tj[j] * T_in : Tj[j];
+    const float gr = first_seg ? gA.r : gB.r;
+    const float gg = first_seg ? gA.g : gB.g;
+    const float gb = first_seg ? gA.b : gB.b;
+    const float gd = first_seg ? gA.d : gB.d;
+    const float gbg = first_seg ? gA.bg : gB.bg;
+    const float g = gr * c.x + gg * c.y + gb * c.z + gd * zn - gbg;
+    const float dalpha = T * (g - Q);
+    Q = g * alpha + t * Q;
+    const float dsd = dalpha * e;
+    const float w = alpha * T;
+    rg[j] = make_float4(w * gr, w * gg, w * gb, dsd * delta);
+    zn = zk;
+  }
+}
+
+
+}  // namespace avr

@@ -142,3 +142,58 @@ def test_packed_full_size_smoke(dev):
     same_ray = seg2[1:] == seg2[:-1]
     assert (zs[1:][same_ray] >= zs[:-1][same_ray]).all()
     assert abs(zs.double().sum().item() - (z.double().sum() + zf.double().sum()).item()) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["medium", "short_only", "capacity_edges", "single_ray", "few_rays", "with_empty_tail",
+                                  "misaligned_end"])
+def test_packed_span_tiling_matches_generic(name, dev):
+    """The dynamically tiled span kernels against the thread-per-ray generic kernels on count
+    distributions that hit every tiling decision (tile / too short / too long / partial quads)."""
+    import avr_b200
+    from avr_b200 import ops
+    lib = avr_b200.load_library()
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    counts = {
+        "medium": torch.randint(14, 300, (4000,), generator=g),
+        "short_only": torch.randint(0, 14, (3000,), generator=g),
+        "capacity_edges": torch.tensor([416, 417, 415, 14, 13, 402, 14, 208, 208, 1, 416] * 50),
+        "single_ray": torch.tensor([97]),
+        "few_rays": torch.tensor([20, 3, 150, 416, 33]),
+        "with_empty_tail": torch.cat([torch.randint(14, 200, (500,), generator=g), torch.zeros(40, dtype=torch.int64)]),
+        "misaligned_end": torch.tensor([15, 17, 19, 21, 23, 30, 14, 15]),   # S % 4 != 0, tiles end inside the last quad
+    }[name]
+    r = counts.numel()
+    offsets = torch.zeros(r + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts, 0)
+    s = int(offsets[-1])
+    z = torch.zeros(s)
+    for k, rays, idx in O.bucketed(offsets):
+        if k:
+            z[idx] = torch.sort(0.8 + torch.rand(rays.numel(), k, generator=g), -1).values
+    x = torch.cat([torch.sigmoid(torch.randn(s, 3, generator=g)), torch.relu(torch.randn(s, 1, generator=g)) * 30], -1)
+    g_rgb, g_d = torch.randn(r, 3, generator=g), torch.randn(r, generator=g)
+    res = {}
+    for fam in (0, 1):
+        lib.avr_set_force_generic(fam)
+        try:
+            xd = x.to(dev).requires_grad_(True)
+            rgb, depth, w = ops.composite_packed(xd, z.to(dev), offsets.to(dev), True, 1.8)
+            rgb2, depth2, none = ops.composite_packed(x.to(dev), z.to(dev), offsets.to(dev), False, 1.8, want_w=False)
+            torch.autograd.backward([rgb, depth], [g_rgb.to(dev), g_d.to(dev)])
+            res[fam] = (rgb.detach().cpu(), depth.detach().cpu(), w.detach().cpu(), xd.grad.cpu(), rgb2.cpu(), depth2.cpu())
+        finally:
+            lib.avr_set_force_generic(0)
+    a, b = res[0], res[1]
+    for i, what in enumerate(["rgb", "depth", "w"]):
+        assert_close(a[i], b[i], rtol=3e-6, atol=3e-7, what=what)
+    assert_close(a[3][:, :3], b[3][:, :3], rtol=3e-6, atol=3e-7, what="d_rgb")
+    last = offsets[1:][counts > 0] - 1
+    mask = torch.ones(s, dtype=torch.bool)
+    mask[last] = False
+    assert_close(a[3][mask, 3], b[3][mask, 3], rtol=1e-5, atol=1e-6, what="d_sigma")
+    assert_close(a[3][last, 3] / 1e10, b[3][last, 3] / 1e10, rtol=1e-5, atol=1e-6, what="d_sigma last / 1e10")
+    assert_close(a[4], b[4], rtol=3e-6, atol=3e-7, what="rgb (no white background, no weights)")
+    assert_close(a[5], b[5], rtol=3e-6, atol=3e-7, what="depth (no weights)")
+    want = O.composite_packed(z, x, offsets, True, 1.8)
+    assert_close(a[0], want[0], what="rgb vs oracle")
+    assert_close(a[2], want[2], what="w vs oracle")
