@@ -1,0 +1,343 @@
+// Importance sampler + merge for the hot dense shapes, G = 8 lanes per ray (four rays per warp).
+//
+// Same algorithm as importance_reg.cu (cdf scan -> inverse-CDF search -> jitter -> register
+// bitonic sort of the new samples -> one bitonic merge with the ascending coarse depths;
+// renderers.py:27-66, 255-258), re-mapped so that more of it is lane-local:
+//   * a lane owns KC/8 coarse bins and (NI+ND)/8 new samples, so 22 of the 28 compare-exchange
+//     stages of a 128-key sort (and 5 of the 8 merge stages) are register-to-register; only
+//     the stages over the 3 lane bits inside a group need a shuffle;
+//   * the per-ray fixed work (sum, scan, running max, bounds, addressing) is issued once per
+//     FOUR rays;
+//   * the cdf is searched as a perfect binary tree over cdf[1..KC-1] (log2 KC probes, stored
+//     breadth-first so a probe step's nodes are contiguous) plus one compare against the last
+//     entry, which stays in a register.
+// The kernel is issue-bound, not memory-bound; see DESIGN.md section 3.3 for the instruction
+// budget.  Shapes are template constants; anything else takes importance_reg.cu.
+#include <math_constants.h>
+
+#include <cstdlib>
+
+#include "avr_common.cuh"
+#include "importance_args.cuh"
+#include "kernels.h"
+#include "sort_net.cuh"
+
+namespace avr {
+
+constexpr int kGrpWarps = 8;
+
+__host__ __device__ constexpr int pow2ceil_c(int v) { return v <= 1 ? 1 : 2 * pow2ceil_c((v + 1) / 2); }
+
+template <int G, int KC, int NI, int ND>
+struct GrpCfg {
+  static constexpr int RPW = 32 / G;                 // rays per warp
+  static constexpr int NIL = NI / G, NDL = ND / G;   // importance / depth samples per lane
+  static constexpr int EPF = pow2ceil_c(NIL + NDL);  // new samples per lane incl. +inf padding
+  static constexpr int M = G * EPF;
+  static constexpr int CW = KC / G;                  // coarse bins per lane
+  static constexpr int EPT = pow2ceil_c(CW + EPF);   // merged samples per lane incl. padding
+  static constexpr int EPC = EPT - EPF;
+  static constexpr int P = G * EPT;
+  static constexpr int TOTAL = KC + NI + ND;
+  static constexpr int DEPTH = ilog2_c(KC);          // perfect tree over cdf[1..KC-1]
+  static constexpr int TREE_STRIDE = KC + 8;         // +8 floats: the rays of a warp start in different banks
+  static constexpr int PAD = EPF >= 8 ? 4 : 0;       // floats after each lane's chunk of the exchange buffer
+  static constexpr int BUF_FLOATS = (P > M + G * PAD ? P : M + G * PAD);
+  static constexpr int BUF_STRIDE = BUF_FLOATS + 8;
+  static constexpr unsigned kInf0 = ((EPC >= 32 ? 0xffffffffu : ((1u << EPC) - 1u)) & ~((1u << CW) - 1u));
+  static_assert(G == 8 || G == 16 || G == 32, "group width");
+  static_assert((KC & (KC - 1)) == 0 && KC % G == 0 && NI % G == 0 && ND % G == 0, "shape must split evenly over the group");
+  static_assert(EPT <= 32 && BUF_STRIDE % 4 == 0 && TREE_STRIDE % 4 == 0, "layout");
+};
+
+// shared-memory bitonic sort of P keys by the G lanes of a group (all groups of the warp in
+// lock step); used only when a ray's coarse depths arrive unsorted
+__device__ __noinline__ void sort_smem_grp(float* key, int P, int g, int G) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = g; t < (P >> 1); t += G) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool ascending = ((lo & size) == 0);
+        const float a = key[lo], b = key[hi];
+        if ((a > b) == ascending && a != b) {
+          key[lo] = b;
+          key[hi] = a;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int N>
+__device__ __forceinline__ void load_consecutive(float (&dst)[N], const float* src, bool vec_ok) {
+  if (N % 4 == 0 && vec_ok) {
+#pragma unroll
+    for (int q = 0; q < N; q += 4) {
+      const float4 p = *reinterpret_cast<const float4*>(src + q);
+      dst[q] = p.x; dst[(q + 1) % N] = p.y; dst[(q + 2) % N] = p.z; dst[(q + 3) % N] = p.w;
+    }
+  } else if (N % 2 == 0 && vec_ok) {
+#pragma unroll
+    for (int q = 0; q < N; q += 2) {
+      const float2 p = *reinterpret_cast<const float2*>(src + q);
+      dst[q] = p.x; dst[(q + 1) % N] = p.y;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) dst[q] = src[q];
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void store_consecutive(float* dst, const float (&src)[N], bool vec_ok) {
+  if (N % 4 == 0 && vec_ok) {
+#pragma unroll
+    for (int q = 0; q < N; q += 4)
+      *reinterpret_cast<float4*>(dst + q) = make_float4(src[q], src[(q + 1) % N], src[(q + 2) % N], src[(q + 3) % N]);
+  } else if (N % 2 == 0 && vec_ok) {
+#pragma unroll
+    for (int q = 0; q < N; q += 2) *reinterpret_cast<float2*>(dst + q) = make_float2(src[q], src[(q + 1) % N]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) dst[q] = src[q];
+  }
+}
+
+template <int G, int KC, int NI, int ND>
+__global__ void __launch_bounds__(kGrpWarps * 32, (G >= 16 ? 4 : 2))
+importance_grp_kernel(const ImportanceRegArgs a) {
+  using C = GrpCfg<G, KC, NI, ND>;
+  constexpr int RPW = C::RPW, NIL = C::NIL, NDL = C::NDL, EPF = C::EPF, CW = C::CW, EPT = C::EPT, EPC = C::EPC;
+  constexpr int DEPTH = C::DEPTH, PAD = C::PAD;
+  __shared__ __align__(16) float s_tree[kGrpWarps][RPW][C::TREE_STRIDE];
+  __shared__ __align__(16) float s_buf[kGrpWarps][RPW][C::BUF_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane & (G - 1), sub = lane / G;
+  float* tree = s_tree[warp][sub];
+  float* buf = s_buf[warp][sub];
+  const bool do_sort = (a.z_sorted != nullptr);
+  const LaneSigns sg = lane_signs(lane);
+  const float inv_kc = 1.0f / (float)KC;  // KC is a power of two: x * inv_kc == x / KC bit for bit
+
+  // tree slots of this lane's cdf entries q = g*CW + i + 1 (breadth-first order, root = 1);
+  // the last entry q == KC is not part of the tree: it is dumped into the unused slot 0
+  int hidx[CW];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) {
+    const int q = g * CW + i + 1;
+    const int tz = __ffs(q) - 1;
+    hidx[i] = (q < KC) ? (1 << (DEPTH - 1 - tz)) + (q >> (tz + 1)) : 0;
+  }
+
+  const int64_t n_wg = (a.R + RPW - 1) / RPW;
+  for (int64_t wg = blockIdx.x * (int64_t)kGrpWarps + warp; wg < n_wg; wg += (int64_t)gridDim.x * kGrpWarps) {
+    const int64_t r_raw = wg * RPW + sub;
+    const bool live = r_raw < a.R;               // a dead group (last warp only) recomputes ray R-1 and stores nothing
+    const int64_t r = live ? r_raw : a.R - 1;
+    const int64_t bi = a.bound_stride ? r : 0;
+    const float near = a.near[bi], far = a.far[bi];
+    const float span = __fsub_rn(far, near);
+
+    // ---- loads: everything this lane needs of its ray --------------------------------------
+    float w[CW], uu[NIL > 0 ? NIL : 1], jj[NIL > 0 ? NIL : 1], nn[NDL > 0 ? NDL : 1];
+    float x[EPT];
+    load_consecutive<CW>(w, a.weights + r * KC + g * CW, a.vecw != 0);
+    if (NIL > 0) {
+      load_consecutive<(NIL > 0 ? NIL : 1)>(uu, a.u + r * NI + g * NIL, a.vec4 != 0);
+      load_consecutive<(NIL > 0 ? NIL : 1)>(jj, a.u2 + r * NI + g * NIL, a.vec4 != 0);
+    }
+    if (do_sort) {
+      if (NDL > 0) load_consecutive<(NDL > 0 ? NDL : 1)>(nn, a.normals + r * ND + g * NDL, a.vecz != 0);
+      const float* zrow = a.z_coarse + r * KC;
+#pragma unroll
+      for (int i = 0; i < CW; ++i) x[i] = zrow[i * G + g];  // striped: merged position q = i*G + g
+    }
+
+    // ---- 1. cdf (renderers.py:36-39): blocked scan + running max (the search needs a
+    //         non-decreasing table; a parallel prefix sum is not monotone in floating point)
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      w[i] = __fadd_rn(w[i], kPdfEps);
+      part += w[i];
+    }
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    const float S = part;
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      run += __fdiv_rn(w[i], S);
+      w[i] = run;  // local inclusive prefix
+    }
+    float incl = run;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const float p = __shfl_up_sync(0xffffffffu, incl, d);
+      if (g >= d) incl += p;
+    }
+    float off = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (g == 0) off = 0.f;
+    float mx = off + run;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const float p = __shfl_up_sync(0xffffffffu, mx, d);
+      if (g >= d) mx = fmaxf(mx, p);
+    }
+    float floor_prev = __shfl_up_sync(0xffffffffu, mx, 1);
+    if (g == 0) floor_prev = 0.f;
+    __syncwarp();  // the previous iteration's readers of tree/buf are done
+    float* cdf_out = (a.cdf && live) ? a.cdf + r * (KC + 1) : nullptr;
+    float last = 0.f;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      const float val = fmaxf(off + w[i], floor_prev);
+      tree[hidx[i]] = val;
+      if (cdf_out) cdf_out[g * CW + i + 1] = val;
+      last = val;
+    }
+    if (cdf_out && g == 0) cdf_out[0] = 0.f;
+    last = __shfl_sync(0xffffffffu, last, lane | (G - 1));  // cdf[KC]
+    __syncwarp();
+
+    // ---- 2. this lane's new samples -----------------------------------------------------------
+    float v[EPF];
+    if (NIL > 0) {
+      int32_t* irow = (a.idx && live) ? a.idx + r * NI + g * NIL : nullptr;
+      float* frow = (a.z_fine && live) ? a.z_fine + r * NI + g * NIL : nullptr;
+      // node <- 2*node + (tree[node] <= u): after DEPTH probes node - KC counts the entries
+      // cdf[1..KC-1] <= u; adding (cdf[KC] <= u) gives clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
+      // (c <= u) is the complement of the sign bit of u - c (exact in sign: nothing is flushed).
+      unsigned node[NIL > 0 ? NIL : 1];
+      int bins[NIL > 0 ? NIL : 1];
+#pragma unroll
+      for (int q = 0; q < NIL; ++q) node[q] = 1;
+#pragma unroll
+      for (int step = 0; step < DEPTH; ++step) {
+#pragma unroll
+        for (int q = 0; q < NIL; ++q) {
+          const float d = __fsub_rn(uu[q], tree[node[q]]);
+          node[q] = 2 * node[q] + 1 - (__float_as_uint(d) >> 31);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NIL; ++q) {
+        const float dl = __fsub_rn(uu[q], last);
+        const int bin = (int)(node[q] - KC) + 1 - (int)(__float_as_uint(dl) >> 31);
+        const float num = __fadd_rn((float)bin, jj[q]);                    // renderers.py:45
+        const float val = __fadd_rn(near, __fmul_rn(span, __fmul_rn(num, inv_kc)));  // :46
+        bins[q] = bin;
+        v[q] = val;
+      }
+      if (irow) store_consecutive<(NIL > 0 ? NIL : 1)>(reinterpret_cast<float*>(irow), reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(bins), a.vec4 != 0);
+      if (frow) store_consecutive<(NIL > 0 ? NIL : 1)>(frow, reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(v), a.vec4 != 0);
+    }
+    if (!do_sort) continue;
+#pragma unroll
+    for (int q = 0; q < NDL; ++q) {
+      // sample_depth's randn*std (the depth is NOT added), clamped (renderers.py:62-66, :255)
+      v[NIL + q] = fminf(fmaxf(__fmul_rn(nn[q], a.depth_std), near), far);
+    }
+#pragma unroll
+    for (int q = NIL + NDL; q < EPF; ++q) v[q] = CUDART_INF_F;
+
+    // ---- 3. sort the group's G*EPF new samples in registers -------------------------------------
+    sort_blocked<EPF, G>(v, sg);
+
+    // ---- 4. [coarse ascending | +inf | new descending], striped over the group --------------------
+    {
+      float* chunk = buf + (G - 1 - g) * (EPF + PAD);  // descending: this lane's keys go to the mirrored chunk
+      if (EPF % 4 == 0) {
+#pragma unroll
+        for (int o = 0; o < EPF; o += 4)
+          *reinterpret_cast<float4*>(chunk + o) =
+              make_float4(v[EPF - 1 - o], v[(EPF - 2 - o + EPF) % EPF], v[(EPF - 3 - o + EPF) % EPF], v[(EPF - 4 - o + EPF) % EPF]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < EPF; ++o) chunk[o] = v[EPF - 1 - o];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = CW; i < EPT; ++i) {
+      if (i < EPC) {
+        x[i] = CUDART_INF_F;
+      } else {
+        const int idx = (i - EPC) * G + g;          // position in the descending new-sample sequence
+        x[i] = buf[idx + (idx / EPF) * PAD];
+      }
+    }
+    // coarse depths must be ascending for the merge (they are when they come from sample_coarse)
+    bool unsorted = false;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
+      const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], lane & ~(G - 1));
+      if (g == G - 1) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
+      if (x[i] > nx) unsorted = true;
+    }
+    if (__any_sync(0xffffffffu, unsorted)) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) buf[i * G + g] = x[i];
+      sort_smem_grp(buf, C::P, g, G);
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) x[i] = buf[i * G + g];
+    } else {
+      merge_striped<EPT, C::kInf0, G>(x, sg);
+    }
+
+    // ---- 5. store the first TOTAL keys: each group writes 32-byte segments of its row -------------
+    if (live) {
+      float* out = a.z_sorted + r * C::TOTAL;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        const int q = i * G + g;
+        if (q < C::TOTAL) out[q] = x[i];
+      }
+    }
+  }
+}
+
+template <int G, int KC, int NI, int ND>
+static int launch_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
+  constexpr int RPW = 32 / G;
+  const int64_t n_wg = (a.R + RPW - 1) / RPW;
+  int64_t blocks = (n_wg + kGrpWarps - 1) / kGrpWarps;
+  const int64_t cap = (int64_t)kNumSMs * (G >= 16 ? 4 : 2) * 4;  // 2 resident CTAs per SM, a few waves for balance
+  if (blocks > cap) blocks = cap;
+  importance_grp_kernel<G, KC, NI, ND><<<(unsigned)blocks, kGrpWarps * 32, 0, stream>>>(a);
+  return check_launch();
+}
+
+// Hot dense shapes, compiled with the shape as constants: BASELINE.json config 3 (64 -> 128),
+// conf/default.conf's renderer (64 coarse, 16 importance + 16 depth, renderers.py:252-258) and
+// VolumeRenderer.from_conf's defaults (32 coarse, 8 + 8, renderers.py:279-289).
+int launch_importance_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
+  if (a.offsets) return AVR_ERR_UNSUPPORTED;
+  // lanes per ray: 16 for the 128-sample shape (64 registers -> 32 resident warps/SM beats the
+  // fewer shuffle stages of 8 lanes at 118 registers: 0.77 vs 0.83 ms for 2^20 rays on B200);
+  // 8 for the small shapes.  AVR_GRP_G=8|16 overrides (experiments).
+  const char* gsw = std::getenv("AVR_GRP_G");
+  const int force_g = (gsw && *gsw) ? std::atoi(gsw) : 0;
+#define AVR_GRP_CASE(G_, KC_, NI_, ND_)                                        \
+  if (a.Kc == KC_ && a.n_imp == NI_ && a.n_depth == ND_) {                     \
+    if (force_g == 8) return launch_grp<8, KC_, NI_, ND_>(a, stream);          \
+    if (force_g == 16) return launch_grp<16, KC_, NI_, ND_>(a, stream);        \
+    return launch_grp<G_, KC_, NI_, ND_>(a, stream);                           \
+  }
+  AVR_GRP_CASE(16, 64, 128, 0)
+  AVR_GRP_CASE(8, 64, 16, 16)
+  AVR_GRP_CASE(8, 64, 16, 0)
+  AVR_GRP_CASE(8, 64, 64, 0)
+  // VolumeRenderer.from_conf's defaults (renderers.py:279-289): 8 + 8 new samples only split over 8 lanes
+  if (a.Kc == 32 && a.n_imp == 8 && a.n_depth == 8) return launch_grp<8, 32, 8, 8>(a, stream);
+  if (a.Kc == 32 && a.n_imp == 8 && a.n_depth == 0) return launch_grp<8, 32, 8, 0>(a, stream);
+#undef AVR_GRP_CASE
+  return AVR_ERR_UNSUPPORTED;
+}
+
+}  // namespace avr

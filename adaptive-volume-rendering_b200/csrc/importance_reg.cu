@@ -1,128 +1,47 @@
-// Register-resident importance sampler + merge for the dense layout (the fast path of
-// avr_importance_sample; csrc/samplers.cu keeps the general shared-memory kernel).
+// Register-resident importance sampler + merge (the fast path of avr_importance_sample;
+// csrc/samplers.cu keeps the general shared-memory kernel).
 //
 // One warp per ray, no block-level synchronisation:
 //   1. pdf/cdf: sum and inclusive scan of (w + 1e-5)/S by warp shuffles (renderers.py:36-39);
-//      the table goes to shared memory padded with +inf to a power of two so the search is
-//      a fixed number of branch-free steps.
+//      the table goes to shared memory as an implicit binary search tree padded with +inf to
+//      a power of two, so the search is a fixed number of branch-free steps.
 //   2. each lane owns EPF *consecutive* new samples (importance samples, then the clamped
 //      "depth" samples, then +inf padding): inverse-CDF search (renderers.py:41-43), jitter
 //      and placement (:45-46) with the reference's rounding.
 //   3. the 32*EPF new samples are sorted IN REGISTERS by a bitonic network (lane-local
-//      compare-exchanges for small strides, one shuffle + one min/max per element for the
-//      rest).
+//      compare-exchanges for small strides, one shuffle + one min per element for the rest).
 //   4. coarse depths are already ascending (stratified sampling), so
 //      [coarse ascending | +inf | new samples descending] is a bitonic sequence of
 //      P = 32*EPT elements: ONE bitonic merge (log2 P steps) in a lane-striped register
 //      layout finishes the sort (renderers.py:257-258), and the striped layout stores
 //      straight to global memory fully coalesced.  If a ray's coarse depths are not
 //      ascending (arbitrary caller input), that ray takes a full shared-memory sort instead.
+//
+// The kernel is bound by the SM's ALU pipe (min/max, compares, integer logic issue at half
+// the FP32 rate on sm_100), so the hot shapes are compiled with the shape as template
+// constants (no per-ray bounds logic), and work is moved to the FMA pipe where possible:
+//   * cross-lane compare-exchanges run in a "signed domain": a lane that must keep the
+//     maximum holds its keys negated, so BOTH partners execute the same min(w, -other)
+//     (one FMNMX instead of a min/max pair); the sign pattern changes between stages by
+//     one multiply by +-1 (FMA pipe, exact);
+//   * the search step's compare is the sign bit of u - cdf[node] (an FADD);
+//   * merge comparators whose inputs are known +inf padding are dropped at compile time.
 #include <math_constants.h>
+
+#include <cstdlib>
 
 #include "avr_common.cuh"
 #include "kernels.h"
+#include "importance_args.cuh"
+#include "sort_net.cuh"
 
 namespace avr {
 
 constexpr int kRegWarps = 8;  // warps per CTA
 
-struct ImportanceRegArgs {
-  const float* weights;
-  const float* z_coarse;
-  const float* u;
-  const float* u2;
-  const float* normals;
-  const float* near;
-  const float* far;
-  int bound_stride;
-  const int64_t* offsets;       // packed coarse layout or null
-  const int64_t* fine_offsets;  // packed fine layout or null
-  int64_t R;
-  int Kc, n_imp, n_depth;       // dense: exact; packed: Kc/n_imp unused (per-ray counts come from the offsets)
-  float depth_std;
-  int vec4;  // u/u2 rows are 16-byte aligned (n % 4 == 0 and aligned bases)
-  float* z_fine;
-  float* z_sorted;
-  float* cdf;
-  int32_t* idx;
-};
-
-__device__ __forceinline__ void cmp_swap_asc(float& a, float& b) {
-  const float lo = fminf(a, b), hi = fmaxf(a, b);
-  a = lo;
-  b = hi;
-}
-
-// Full bitonic sort of 32*EPF keys, blocked layout: key index e = lane*EPF + r.
-// All comparators point the same way (the lower index keeps the minimum): each merge phase
-// opens with a "mirror" step (e <-> e ^ (size-1)) instead of alternating directions, so the
-// lane-local compare-exchanges need no direction selects.
-template <int EPF>
-__device__ __forceinline__ void sort_blocked(float (&v)[EPF], int lane) {
-  constexpr int M = 32 * EPF;
-#pragma unroll
-  for (int size = 2; size <= M; size <<= 1) {
-    // mirror step
-    if (size <= EPF) {
-#pragma unroll
-      for (int r = 0; r < EPF; ++r) {
-        const int pr = r ^ (size - 1);
-        if (r < pr) cmp_swap_asc(v[r], v[pr]);
-      }
-    } else {
-      const int lmask = size / EPF - 1;                       // partner lane = lane ^ lmask
-      const bool keep_min = ((lane & (size / EPF / 2)) == 0);  // lower index of the pair
-      float o[EPF];
-#pragma unroll
-      for (int r = 0; r < EPF; ++r) o[r] = __shfl_xor_sync(0xffffffffu, v[EPF - 1 - r], lmask);
-#pragma unroll
-      for (int r = 0; r < EPF; ++r) v[r] = keep_min ? fminf(v[r], o[r]) : fmaxf(v[r], o[r]);
-    }
-    // half-cleaner steps
-#pragma unroll
-    for (int stride = size >> 2; stride > 0; stride >>= 1) {
-      if (stride < EPF) {
-#pragma unroll
-        for (int r = 0; r < EPF; ++r) {
-          if ((r & stride) == 0) cmp_swap_asc(v[r], v[r | stride]);
-        }
-      } else {
-        const int lstride = stride / EPF;
-        const bool keep_min = ((lane & lstride) == 0);
-#pragma unroll
-        for (int r = 0; r < EPF; ++r) {
-          const float o = __shfl_xor_sync(0xffffffffu, v[r], lstride);
-          v[r] = keep_min ? fminf(v[r], o) : fmaxf(v[r], o);
-        }
-      }
-    }
-  }
-}
-
-// Ascending bitonic merge of 32*EPT keys, striped layout: key index q = i*32 + lane.
-template <int EPT>
-__device__ __forceinline__ void merge_striped(float (&x)[EPT], int lane) {
-#pragma unroll
-  for (int stride = 16 * EPT; stride > 0; stride >>= 1) {
-    if (stride >= 32) {
-      const int istride = stride / 32;
-#pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        if ((i & istride) == 0) cmp_swap_asc(x[i], x[i | istride]);
-      }
-    } else {
-      const bool keep_min = ((lane & stride) == 0);
-#pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        const float o = __shfl_xor_sync(0xffffffffu, x[i], stride);
-        x[i] = keep_min ? fminf(x[i], o) : fmaxf(x[i], o);
-      }
-    }
-  }
-}
 
 // smem bitonic sort (any content), P power of two; used for the rare unsorted-coarse ray
-__device__ __forceinline__ void sort_smem(float* key, int P, int lane) {
+__device__ __noinline__ void sort_smem(float* key, int P, int lane) {
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncwarp();
@@ -155,11 +74,19 @@ struct RayIn {
   int64_t cbase, fbase; // first coarse / importance sample of the ray in the streams
 };
 
-template <int EPF, int EPC>
+// KC > 0: the dense shape (KC coarse, NI importance, ND depth samples) is a compile-time constant
+// with KC % 32 == 0; KC == 0: shapes are read at run time (packed layout, unusual dense shapes).
+template <int EPF, int EPC, int KC, int NI, int ND>
 __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRegArgs& a, int64_t r, int lane,
                                          bool do_sort) {
-  const int nd = a.n_depth;
-  if (a.offsets) {
+  constexpr bool kStatic = KC > 0;
+  const int nd = kStatic ? ND : a.n_depth;
+  if (kStatic) {
+    in.kc = KC;
+    in.n = NI;
+    in.cbase = r * (int64_t)KC;
+    in.fbase = r * (int64_t)NI;
+  } else if (a.offsets) {
     in.cbase = a.offsets[r];
     in.kc = (int)(a.offsets[r + 1] - in.cbase);
     in.fbase = a.fine_offsets[r];
@@ -175,24 +102,45 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
   in.near = a.near[bi];
   in.far = a.far[bi];
   const float* wrow = a.weights + in.cbase;
-  const int c = (kc + 31) >> 5;  // weights per lane, blocked: j = lane*c + i
+  if (kStatic) {
+    constexpr int CW = KC / 32;
+    if (CW == 2 && a.vecw) {
+      const float2 p = *reinterpret_cast<const float2*>(wrow + 2 * lane);
+      in.w[0] = p.x;
+      in.w[CW > 1 ? 1 : 0] = p.y;
+    } else if (CW == 4 && a.vecw) {
+      const float4 p = *reinterpret_cast<const float4*>(wrow + 4 * lane);
+      in.w[0] = p.x; in.w[CW > 1 ? 1 : 0] = p.y; in.w[CW > 2 ? 2 : 0] = p.z; in.w[CW > 3 ? 3 : 0] = p.w;
+    } else {
 #pragma unroll
-  for (int i = 0; i < EPC; ++i) {
-    const int j = lane * c + i;
-    in.w[i] = (i < c && j < kc) ? wrow[j] : 0.f;
-  }
-  if (do_sort) {
-    const float* zrow = a.z_coarse + in.cbase;
+      for (int i = 0; i < CW; ++i) in.w[i] = wrow[lane * CW + i];
+    }
+    if (do_sort) {
+      const float* zrow = a.z_coarse + in.cbase;
+#pragma unroll
+      for (int i = 0; i < CW; ++i) in.zc[i] = zrow[i * 32 + lane];
+    }
+  } else {
+    const int c = (kc + 31) >> 5;  // weights per lane, blocked: j = lane*c + i
 #pragma unroll
     for (int i = 0; i < EPC; ++i) {
-      const int j = i * 32 + lane;
-      in.zc[i] = (j < kc) ? zrow[j] : CUDART_INF_F;
+      const int j = lane * c + i;
+      in.w[i] = (i < c && j < kc) ? wrow[j] : 0.f;
+    }
+    if (do_sort) {
+      const float* zrow = a.z_coarse + in.cbase;
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) {
+        const int j = i * 32 + lane;
+        in.zc[i] = (j < kc) ? zrow[j] : CUDART_INF_F;
+      }
     }
   }
   const int e0 = lane * EPF;
   const float* urow = a.u + in.fbase;
   const float* u2row = a.u2 + in.fbase;
-  if (EPF >= 4 && a.vec4 && e0 + EPF <= n) {  // 16-byte loads of the lane's consecutive draws
+  const bool all_imp = kStatic ? (NI == 32 * EPF) : (e0 + EPF <= n);
+  if (EPF >= 4 && a.vec4 && all_imp) {  // 16-byte loads of the lane's consecutive draws
 #pragma unroll
     for (int q = 0; q < EPF; q += 4) {
       const float4 p4 = *reinterpret_cast<const float4*>(urow + e0 + q);
@@ -218,34 +166,40 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
   }
 }
 
-template <int EPF, int EPT>
+template <int EPF, int EPT, int KC, int NI, int ND>
 __global__ void __launch_bounds__(kRegWarps * 32, 3)
 importance_reg_kernel(const ImportanceRegArgs a) {
+  constexpr bool kStatic = KC > 0;
   constexpr int M = 32 * EPF;    // new samples incl. padding
   constexpr int P = 32 * EPT;    // merged length incl. padding; also the padded cdf table length
   constexpr int EPC = EPT - EPF; // coarse samples per lane (striped), Kc <= 32*EPC
+  constexpr int CW = kStatic ? KC / 32 : EPC;  // registers that can hold real coarse samples
+  // merge registers known to be +inf padding: coarse registers beyond KC (static shapes only)
+  constexpr unsigned kInf0 = kStatic ? (((1u << EPC) - 1u) & ~((1u << CW) - 1u)) : 0u;
   static_assert(EPT > EPF, "room for the coarse samples");
+  static_assert(!kStatic || (KC % 32 == 0 && KC <= 32 * EPC && NI + ND <= M), "static shape must fit");
   __shared__ float s_cdf[kRegWarps][P];
   __shared__ float s_buf[kRegWarps][P];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* cdf = s_cdf[warp];
   float* buf = s_buf[warp];
-  const int nd = a.n_depth;
+  const int nd = kStatic ? ND : a.n_depth;
   const bool do_sort = (a.z_sorted != nullptr);
   const int64_t warps = (int64_t)gridDim.x * kRegWarps;
   const int e0 = lane * EPF;
+  const LaneSigns sg = lane_signs(lane);
   int64_t r = blockIdx.x * (int64_t)kRegWarps + warp;
   bool first_ray = true;
   RayIn<EPF, EPC> cur;
-  if (r < a.R) load_ray<EPF, EPC>(cur, a, r, lane, do_sort);
+  if (r < a.R) load_ray<EPF, EPC, KC, NI, ND>(cur, a, r, lane, do_sort);
   for (; r < a.R; r += warps) {
     RayIn<EPF, EPC> nxt;
     const bool more = (r + warps < a.R);
-    if (more) load_ray<EPF, EPC>(nxt, a, r + warps, lane, do_sort);
+    if (more) load_ray<EPF, EPC, KC, NI, ND>(nxt, a, r + warps, lane, do_sort);
 
     const float near = cur.near, far = cur.far;
     const float span = __fsub_rn(far, near);
-    const int kc = cur.kc, n = cur.n;
+    const int kc = kStatic ? KC : cur.kc, n = kStatic ? NI : cur.n;
     const int total = kc + n + nd;
     const float kcf = (float)kc;
     const bool kc_pow2 = (kc & (kc - 1)) == 0;
@@ -255,22 +209,22 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     // blocked scan: each lane owns c consecutive bins; local running sums, one exclusive
     // warp scan of the lane totals, then a running max (a parallel prefix sum is not
     // monotone in floating point; the search needs a non-decreasing table)
-    const int c = (kc + 31) >> 5;
-    float wp[EPC];
+    const int c = kStatic ? CW : ((kc + 31) >> 5);
+    float wp[CW];
     float part = 0.f;
 #pragma unroll
-    for (int i = 0; i < EPC; ++i) {
+    for (int i = 0; i < CW; ++i) {
       wp[i] = __fadd_rn(cur.w[i], kPdfEps);
-      if (i < c && lane * c + i < kc) part += wp[i];
+      if (kStatic || (i < c && lane * c + i < kc)) part += wp[i];
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     const float S = part;
-    float ps[EPC];
+    float ps[CW];
     float run = 0.f;
 #pragma unroll
-    for (int i = 0; i < EPC; ++i) {
-      if (i < c && lane * c + i < kc) run += __fdiv_rn(wp[i], S);
+    for (int i = 0; i < CW; ++i) {
+      if (kStatic || (i < c && lane * c + i < kc)) run += __fdiv_rn(wp[i], S);
       ps[i] = run;
     }
     float incl = run;  // inclusive scan of the lane totals
@@ -294,8 +248,10 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     // probes fall into distinct banks (a sorted table probed at power-of-two strides is a
     // worst case for bank conflicts).  Sorted position q in [1, Pc) holds cdf[q], +inf
     // beyond Kc; cdf[0] = 0 is implicit.
-    int m = 1;  // tree depth: Pc = 2^m > kc
-    while ((1 << m) <= kc) ++m;
+    int m = kStatic ? ilog2_c(KC) + 1 : 1;  // tree depth: Pc = 2^m > kc
+    if (!kStatic) {
+      while ((1 << m) <= kc) ++m;
+    }
     const int Pc = 1 << m;
     auto heap_index = [m](int q) {
       const int tz = __ffs(q) - 1;
@@ -304,9 +260,9 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     __syncwarp();  // previous ray's readers of cdf/buf are done
     float* cdf_out = a.cdf ? a.cdf + (cur.cbase + r) : nullptr;
 #pragma unroll
-    for (int i = 0; i < EPC; ++i) {
+    for (int i = 0; i < CW; ++i) {
       const int j = lane * c + i;
-      if (i < c && j < kc) {
+      if (kStatic || (i < c && j < kc)) {
         const float val = fmaxf(off + ps[i], floor_prev);
         cdf[heap_index(j + 1)] = val;
         if (cdf_out) cdf_out[j + 1] = val;
@@ -324,22 +280,27 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     int32_t* irow = a.idx ? a.idx + cur.fbase : nullptr;
     float* frow = a.z_fine ? a.z_fine + cur.fbase : nullptr;
     // descend the tree: node <- 2*node + (tree[node] <= u); after m steps node - Pc is the
-    // number of entries cdf[q >= 1] <= u, i.e. clamp_min(searchsorted(cdf, u, right=True) - 1, 0)
-    int node[EPF];
+    // number of entries cdf[q >= 1] <= u, i.e. clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
+    // (tree[node] <= u) is the complement of the sign bit of u - tree[node]: the subtraction
+    // is exact in sign (no flush to zero), +inf padding gives -inf.
+    unsigned node[EPF];
 #pragma unroll
     for (int q = 0; q < EPF; ++q) node[q] = 1;
-    constexpr int kMaxDepth = (EPT == 2) ? 6 : (EPT == 4) ? 7 : (EPT == 8) ? 8 : 9;  // log2(P)
+    constexpr int kMaxDepth = kStatic ? ilog2_c(KC) + 1 : ((EPT == 2) ? 6 : (EPT == 4) ? 7 : (EPT == 8) ? 8 : 9);
 #pragma unroll
     for (int step = 0; step < kMaxDepth; ++step) {
-      if (step < m) {  // warp-uniform
+      if (kStatic || step < m) {  // warp-uniform
 #pragma unroll
-        for (int q = 0; q < EPF; ++q) node[q] = 2 * node[q] + (cdf[node[q]] <= cur.a[q] ? 1 : 0);
+        for (int q = 0; q < EPF; ++q) {
+          const float d = __fsub_rn(cur.a[q], cdf[node[q]]);
+          node[q] = 2 * node[q] + 1 - (__float_as_uint(d) >> 31);
+        }
       }
     }
 #pragma unroll
     for (int q = 0; q < EPF; ++q) {
       const int e = e0 + q;
-      const int bin = node[q] - Pc;
+      const int bin = (int)node[q] - Pc;
       const float num = __fadd_rn((float)bin, cur.b[q]);
       const float t = kc_pow2 ? __fmul_rn(num, inv_kc) : __fdiv_rn(num, kcf);
       float val = __fadd_rn(near, __fmul_rn(span, t));
@@ -356,7 +317,7 @@ importance_reg_kernel(const ImportanceRegArgs a) {
     }
     if (do_sort) {
       // ---- 3. sort the new samples in registers -----------------------------------------
-      sort_blocked<EPF>(v, lane);
+      sort_blocked<EPF>(v, sg);
 
       // ---- 4. lay out [coarse | +inf | new descending] striped over the lanes -------------
 #pragma unroll
@@ -365,17 +326,18 @@ importance_reg_kernel(const ImportanceRegArgs a) {
       float x[EPT];
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
-        if (i < EPC) x[i] = cur.zc[i];               // +inf beyond kc
-        else x[i] = buf[i * 32 + lane];              // positions >= P - M
+        if (i < CW) x[i] = cur.zc[i];                 // runtime shapes: +inf beyond kc
+        else if (i < EPC) x[i] = CUDART_INF_F;        // static shapes: pure padding
+        else x[i] = buf[i * 32 + lane];               // positions >= P - M
       }
       // coarse depths must be ascending for the merge; check the (q, q+1) pairs inside [0, kc)
       bool unsorted = false;
 #pragma unroll
-      for (int i = 0; i < EPC; ++i) {
+      for (int i = 0; i < CW; ++i) {
         float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
-        const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < EPC) ? i + 1 : i], 0);
-        if (lane == 31) nx = (i + 1 < EPC) ? first_next : CUDART_INF_F;
-        if (i * 32 + lane + 1 < kc && x[i] > nx) unsorted = true;
+        const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], 0);
+        if (lane == 31) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
+        if ((kStatic || i * 32 + lane + 1 < kc) && x[i] > nx) unsorted = true;
       }
       if (__any_sync(0xffffffffu, unsorted)) {
         __syncwarp();
@@ -385,7 +347,7 @@ importance_reg_kernel(const ImportanceRegArgs a) {
 #pragma unroll
         for (int i = 0; i < EPT; ++i) x[i] = buf[i * 32 + lane];
       } else {
-        merge_striped<EPT>(x, lane);
+        merge_striped<EPT, kInf0>(x, sg);
       }
 
       // ---- 5. coalesced store of the first `total` keys ------------------------------------
@@ -400,12 +362,12 @@ importance_reg_kernel(const ImportanceRegArgs a) {
   }
 }
 
-template <int EPF, int EPT>
+template <int EPF, int EPT, int KC = 0, int NI = 0, int ND = 0>
 static int launch_reg(const ImportanceRegArgs& a, cudaStream_t stream) {
   int64_t blocks = (a.R + kRegWarps - 1) / kRegWarps;
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (blocks > cap) blocks = cap;
-  importance_reg_kernel<EPF, EPT><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
+  importance_reg_kernel<EPF, EPT, KC, NI, ND><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
   return check_launch();
 }
 
@@ -417,7 +379,8 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
                           int n_depth, float depth_std, float* z_fine, float* z_sorted, float* cdf, int32_t* idx,
                           cudaStream_t stream) {
   // packed layout: Kc / n_imp are the caller's per-ray maxima and size the register variant
-  const int m = n_imp + (z_sorted ? n_depth : 0);
+  const int nd_eff = z_sorted ? n_depth : 0;
+  const int m = n_imp + nd_eff;
   int epf = 1;
   while (32 * epf < m) epf <<= 1;
   int ept = 2 * epf;
@@ -437,13 +400,30 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   a.R = R;
   a.Kc = Kc;
   a.n_imp = n_imp;
-  a.n_depth = z_sorted ? n_depth : 0;
+  a.n_depth = nd_eff;
   a.depth_std = depth_std;
   a.vec4 = !offsets && ((n_imp & 3) == 0) && aligned16(u) && aligned16(u2);
+  a.vecw = !offsets && ((Kc & 3) == 0) && aligned16(weights);
+  a.vecz = !offsets && ((Kc & 3) == 0) && ((nd_eff & 3) == 0) && ((n_imp & 3) == 0) && aligned16(z_coarse) &&
+           aligned16(normals) && aligned16(z_sorted);
   a.z_fine = z_fine;
   a.z_sorted = z_sorted;
   a.cdf = cdf;
   a.idx = idx;
+  // hot dense shapes: eight lanes per ray, shape as template constants (importance_grp.cu);
+  // AVR_IMPORTANCE_GRP=0 keeps them on the warp-per-ray kernel (A/B experiments)
+  if (!offsets) {
+    const char* sw = std::getenv("AVR_IMPORTANCE_GRP");
+    if (!(sw && sw[0] == '0')) {
+      const int rc = launch_importance_grp(a, stream);
+      if (rc != AVR_ERR_UNSUPPORTED) return rc;
+    }
+#define AVR_REG_STATIC(F, T, KC_, NI_, ND_) \
+  if (Kc == KC_ && n_imp == NI_ && nd_eff == ND_) return launch_reg<F, T, KC_, NI_, ND_>(a, stream);
+    AVR_REG_STATIC(4, 8, 64, 128, 0)
+    AVR_REG_STATIC(1, 4, 64, 16, 16)
+#undef AVR_REG_STATIC
+  }
 #define AVR_REG_CASE(F, T) \
   if (epf == F && ept == T) return launch_reg<F, T>(a, stream);
   AVR_REG_CASE(1, 2)

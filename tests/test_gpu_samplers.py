@@ -9,13 +9,19 @@ from conftest import assert_close, load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "generic"])
+@pytest.fixture(params=["auto", "warp", "generic"])
 def family(request):
-    """Run through the register-resident kernel the library picks AND the general shared-memory kernel."""
+    """Run through the kernel the library picks (8/16 lanes per ray for the hot shapes), the
+    warp-per-ray register kernel, AND the general shared-memory kernel."""
+    import os
+
     import avr_b200
     lib = avr_b200.load_library()
     lib.avr_set_force_generic(1 if request.param == "generic" else 0)
+    if request.param == "warp":
+        os.environ["AVR_IMPORTANCE_GRP"] = "0"
     yield request.param
+    os.environ.pop("AVR_IMPORTANCE_GRP", None)
     lib.avr_set_force_generic(0)
 
 

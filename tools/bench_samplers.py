@@ -24,8 +24,11 @@ def peak():
         return 6650.0
 
 
+WARMUP = 3
+
+
 def timeit(fn, iters):
-    for _ in range(3):
+    for _ in range(WARMUP):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -48,7 +51,10 @@ def main():
     ap.add_argument("--rays", type=int, default=1 << 20)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--what", nargs="+", default=["coarse", "importance", "packed"])
+    ap.add_argument("--warmup", type=int, default=3, help="untimed launches per kernel (1 for ncu captures)")
     a = ap.parse_args()
+    global WARMUP
+    WARMUP = a.warmup
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
     r = a.rays
