@@ -166,198 +166,244 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
   }
 }
 
+// Everything that happens to one ray once its inputs are in registers (one warp, all lanes).
 template <int EPF, int EPT, int KC, int NI, int ND>
-__global__ void __launch_bounds__(kRegWarps * 32, 3)
-importance_reg_kernel(const ImportanceRegArgs a) {
+__device__ __forceinline__ void process_ray(const ImportanceRegArgs& a, const RayIn<EPF, EPT - EPF>& cur, int64_t r,
+                                            float* cdf, float* buf, int lane, const LaneSigns& sg, bool& first_ray) {
   constexpr bool kStatic = KC > 0;
-  constexpr int M = 32 * EPF;    // new samples incl. padding
   constexpr int P = 32 * EPT;    // merged length incl. padding; also the padded cdf table length
   constexpr int EPC = EPT - EPF; // coarse samples per lane (striped), Kc <= 32*EPC
   constexpr int CW = kStatic ? KC / 32 : EPC;  // registers that can hold real coarse samples
   // merge registers known to be +inf padding: coarse registers beyond KC (static shapes only)
   constexpr unsigned kInf0 = kStatic ? (((1u << EPC) - 1u) & ~((1u << CW) - 1u)) : 0u;
+  const int nd = kStatic ? ND : a.n_depth;
+  const bool do_sort = (a.z_sorted != nullptr);
+  const int e0 = lane * EPF;
+  const float near = cur.near, far = cur.far;
+  const float span = __fsub_rn(far, near);
+  const int kc = kStatic ? KC : cur.kc, n = kStatic ? NI : cur.n;
+  const int total = kc + n + nd;
+  const float kcf = (float)kc;
+  const bool kc_pow2 = (kc & (kc - 1)) == 0;
+  const float inv_kc = 1.0f / kcf;  // exact when kc is a power of two: x*inv_kc == x/kc bit for bit
+
+  // ---- 1. cdf table -----------------------------------------------------------------
+  // blocked scan: each lane owns c consecutive bins; local running sums, one exclusive
+  // warp scan of the lane totals, then a running max (a parallel prefix sum is not
+  // monotone in floating point; the search needs a non-decreasing table)
+  const int c = kStatic ? CW : ((kc + 31) >> 5);
+  float wp[CW];
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < CW; ++i) {
+    wp[i] = __fadd_rn(cur.w[i], kPdfEps);
+    if (kStatic || (i < c && lane * c + i < kc)) part += wp[i];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  const float S = part;
+  float ps[CW];
+  float run = 0.f;
+#pragma unroll
+  for (int i = 0; i < CW; ++i) {
+    if (kStatic || (i < c && lane * c + i < kc)) run += __fdiv_rn(wp[i], S);
+    ps[i] = run;
+  }
+  float incl = run;  // inclusive scan of the lane totals
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float p = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += p;
+  }
+  float off = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) off = 0.f;
+  float mx = off + run;  // this lane's last (largest) entry
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float p = __shfl_up_sync(0xffffffffu, mx, d);
+    if (lane >= d) mx = fmaxf(mx, p);
+  }
+  float floor_prev = __shfl_up_sync(0xffffffffu, mx, 1);
+  if (lane == 0) floor_prev = 0.f;
+  // The table is stored as an implicit binary search tree in breadth-first order (heap
+  // index 1 = root): the nodes one search step can touch are contiguous, so the 32 lanes'
+  // probes fall into distinct banks (a sorted table probed at power-of-two strides is a
+  // worst case for bank conflicts).  Sorted position q in [1, Pc) holds cdf[q], +inf
+  // beyond Kc; cdf[0] = 0 is implicit.
+  int m = kStatic ? ilog2_c(KC) + 1 : 1;  // tree depth: Pc = 2^m > kc
+  if (!kStatic) {
+    while ((1 << m) <= kc) ++m;
+  }
+  const int Pc = 1 << m;
+  auto heap_index = [m](int q) {
+    const int tz = __ffs(q) - 1;
+    return (1 << (m - 1 - tz)) + (q >> (tz + 1));
+  };
+  __syncwarp();  // previous ray's readers of cdf/buf are done
+  float* cdf_out = a.cdf ? a.cdf + (cur.cbase + r) : nullptr;
+#pragma unroll
+  for (int i = 0; i < CW; ++i) {
+    const int j = lane * c + i;
+    if (kStatic || (i < c && j < kc)) {
+      const float val = fmaxf(off + ps[i], floor_prev);
+      cdf[heap_index(j + 1)] = val;
+      if (cdf_out) cdf_out[j + 1] = val;
+    }
+  }
+  if (cdf_out && lane == 0) cdf_out[0] = 0.f;
+  if (a.offsets || first_ray) {  // the +inf tail only moves when the count changes (packed)
+    for (int q = kc + 1 + lane; q < Pc; q += 32) cdf[heap_index(q)] = CUDART_INF_F;
+    first_ray = false;
+  }
+  __syncwarp();
+
+  // ---- 2. the lane's EPF consecutive new samples --------------------------------------
+  float v[EPF];
+  int32_t* irow = a.idx ? a.idx + cur.fbase : nullptr;
+  float* frow = a.z_fine ? a.z_fine + cur.fbase : nullptr;
+  // descend the tree: node <- 2*node + (tree[node] <= u); after m steps node - Pc is the
+  // number of entries cdf[q >= 1] <= u, i.e. clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
+  // (tree[node] <= u) is the complement of the sign bit of u - tree[node]: the subtraction
+  // is exact in sign (no flush to zero), +inf padding gives -inf.
+  unsigned node[EPF];
+#pragma unroll
+  for (int q = 0; q < EPF; ++q) node[q] = 1;
+  constexpr int kMaxDepth = kStatic ? ilog2_c(KC) + 1 : ((EPT == 2) ? 6 : (EPT == 4) ? 7 : (EPT == 8) ? 8 : 9);
+#pragma unroll
+  for (int step = 0; step < kMaxDepth; ++step) {
+    if (kStatic || step < m) {  // warp-uniform
+#pragma unroll
+      for (int q = 0; q < EPF; ++q) {
+        const float d = __fsub_rn(cur.a[q], cdf[node[q]]);
+        node[q] = 2 * node[q] + 1 - (__float_as_uint(d) >> 31);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < EPF; ++q) {
+    const int e = e0 + q;
+    const int bin = (int)node[q] - Pc;
+    const float num = __fadd_rn((float)bin, cur.b[q]);
+    const float t = kc_pow2 ? __fmul_rn(num, inv_kc) : __fdiv_rn(num, kcf);
+    float val = __fadd_rn(near, __fmul_rn(span, t));
+    if (e < n) {
+      if (irow) irow[e] = bin;
+      if (frow) frow[e] = val;
+    } else if (e < n + nd) {
+      // sample_depth's randn*std (depth NOT added), clamped (renderers.py:62-66, :255)
+      val = fminf(fmaxf(__fmul_rn(cur.a[q], a.depth_std), near), far);
+    } else {
+      val = CUDART_INF_F;
+    }
+    v[q] = val;
+  }
+  if (do_sort) {
+    // ---- 3. sort the new samples in registers -----------------------------------------
+    sort_blocked<EPF>(v, sg);
+
+    // ---- 4. lay out [coarse | +inf | new descending] striped over the lanes -------------
+#pragma unroll
+    for (int q = 0; q < EPF; ++q) buf[P - 1 - (e0 + q)] = v[q];
+    __syncwarp();
+    float x[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      if (i < CW) x[i] = cur.zc[i];                 // runtime shapes: +inf beyond kc
+      else if (i < EPC) x[i] = CUDART_INF_F;        // static shapes: pure padding
+      else x[i] = buf[i * 32 + lane];               // positions >= P - M
+    }
+    // coarse depths must be ascending for the merge; check the (q, q+1) pairs inside [0, kc)
+    bool unsorted = false;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
+      const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], 0);
+      if (lane == 31) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
+      if ((kStatic || i * 32 + lane + 1 < kc) && x[i] > nx) unsorted = true;
+    }
+    if (__any_sync(0xffffffffu, unsorted)) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) buf[i * 32 + lane] = x[i];
+      sort_smem(buf, P, lane);
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) x[i] = buf[i * 32 + lane];
+    } else {
+      merge_striped<EPT, kInf0>(x, sg);
+    }
+
+    // ---- 5. coalesced store of the first `total` keys ------------------------------------
+    float* out = a.z_sorted + (cur.cbase + cur.fbase + r * (int64_t)nd);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int q = i * 32 + lane;
+      if (q < total) out[q] = x[i];
+    }
+  }
+}
+
+// The (EPF, EPT) variant a ray of kc coarse and m new samples needs: the smallest register
+// footprint that holds it (same rule as the host-side choice for dense shapes).
+__host__ __device__ inline void ray_class(int kc, int m, int& epf, int& ept) {
+  epf = 1;
+  while (32 * epf < m) epf <<= 1;
+  ept = 2 * epf;
+  while (32 * ept < kc + 32 * epf || 32 * ept < kc + 2) ept <<= 1;
+}
+
+// kFilter == false: every ray (dense layout, or packed rays all treated at the maximum shape).
+// kFilter == true (packed layout): the launch handles only the rays whose class is exactly
+// (EPF, EPT); the host launches one such kernel per class, so a short ray never pays for the
+// longest one and each class gets its own register budget.
+template <int EPF, int EPT, int KC, int NI, int ND, bool kFilter>
+__global__ void __launch_bounds__(kRegWarps * 32, (EPT >= 16 ? 2 : 3))
+importance_reg_kernel(const ImportanceRegArgs a) {
+  constexpr int P = 32 * EPT;
+  constexpr int EPC = EPT - EPF;
   static_assert(EPT > EPF, "room for the coarse samples");
-  static_assert(!kStatic || (KC % 32 == 0 && KC <= 32 * EPC && NI + ND <= M), "static shape must fit");
+  static_assert(KC == 0 || (KC % 32 == 0 && KC <= 32 * EPC && NI + ND <= 32 * EPF), "static shape must fit");
   __shared__ float s_cdf[kRegWarps][P];
   __shared__ float s_buf[kRegWarps][P];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* cdf = s_cdf[warp];
   float* buf = s_buf[warp];
-  const int nd = kStatic ? ND : a.n_depth;
   const bool do_sort = (a.z_sorted != nullptr);
   const int64_t warps = (int64_t)gridDim.x * kRegWarps;
-  const int e0 = lane * EPF;
   const LaneSigns sg = lane_signs(lane);
-  int64_t r = blockIdx.x * (int64_t)kRegWarps + warp;
   bool first_ray = true;
+  if (kFilter) {
+    // 32 consecutive rays per step: each lane classifies one, the warp walks the matches
+    // (prefetching the next match's inputs was tried: the extra registers cost more than the
+    // exposed load latency, 3.2 vs 2.95 ms on BASELINE.json config 4's distribution)
+    for (int64_t base = (blockIdx.x * (int64_t)kRegWarps + warp) * 32; base < a.R; base += warps * 32) {
+      const int64_t rr = base + lane;
+      bool mine = false;
+      if (rr < a.R) {
+        const int kc = (int)(a.offsets[rr + 1] - a.offsets[rr]);
+        const int n = (int)(a.fine_offsets[rr + 1] - a.fine_offsets[rr]);
+        int epf, ept;
+        ray_class(kc, n + a.n_depth, epf, ept);
+        mine = (epf == EPF && ept == EPT);
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, mine);
+      while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        RayIn<EPF, EPC> cur;
+        load_ray<EPF, EPC, KC, NI, ND>(cur, a, base + b, lane, do_sort);
+        process_ray<EPF, EPT, KC, NI, ND>(a, cur, base + b, cdf, buf, lane, sg, first_ray);
+      }
+    }
+    return;
+  }
+  int64_t r = blockIdx.x * (int64_t)kRegWarps + warp;
   RayIn<EPF, EPC> cur;
   if (r < a.R) load_ray<EPF, EPC, KC, NI, ND>(cur, a, r, lane, do_sort);
   for (; r < a.R; r += warps) {
     RayIn<EPF, EPC> nxt;
     const bool more = (r + warps < a.R);
     if (more) load_ray<EPF, EPC, KC, NI, ND>(nxt, a, r + warps, lane, do_sort);
-
-    const float near = cur.near, far = cur.far;
-    const float span = __fsub_rn(far, near);
-    const int kc = kStatic ? KC : cur.kc, n = kStatic ? NI : cur.n;
-    const int total = kc + n + nd;
-    const float kcf = (float)kc;
-    const bool kc_pow2 = (kc & (kc - 1)) == 0;
-    const float inv_kc = 1.0f / kcf;  // exact when kc is a power of two: x*inv_kc == x/kc bit for bit
-
-    // ---- 1. cdf table -----------------------------------------------------------------
-    // blocked scan: each lane owns c consecutive bins; local running sums, one exclusive
-    // warp scan of the lane totals, then a running max (a parallel prefix sum is not
-    // monotone in floating point; the search needs a non-decreasing table)
-    const int c = kStatic ? CW : ((kc + 31) >> 5);
-    float wp[CW];
-    float part = 0.f;
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      wp[i] = __fadd_rn(cur.w[i], kPdfEps);
-      if (kStatic || (i < c && lane * c + i < kc)) part += wp[i];
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    const float S = part;
-    float ps[CW];
-    float run = 0.f;
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      if (kStatic || (i < c && lane * c + i < kc)) run += __fdiv_rn(wp[i], S);
-      ps[i] = run;
-    }
-    float incl = run;  // inclusive scan of the lane totals
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const float p = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += p;
-    }
-    float off = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) off = 0.f;
-    float mx = off + run;  // this lane's last (largest) entry
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const float p = __shfl_up_sync(0xffffffffu, mx, d);
-      if (lane >= d) mx = fmaxf(mx, p);
-    }
-    float floor_prev = __shfl_up_sync(0xffffffffu, mx, 1);
-    if (lane == 0) floor_prev = 0.f;
-    // The table is stored as an implicit binary search tree in breadth-first order (heap
-    // index 1 = root): the nodes one search step can touch are contiguous, so the 32 lanes'
-    // probes fall into distinct banks (a sorted table probed at power-of-two strides is a
-    // worst case for bank conflicts).  Sorted position q in [1, Pc) holds cdf[q], +inf
-    // beyond Kc; cdf[0] = 0 is implicit.
-    int m = kStatic ? ilog2_c(KC) + 1 : 1;  // tree depth: Pc = 2^m > kc
-    if (!kStatic) {
-      while ((1 << m) <= kc) ++m;
-    }
-    const int Pc = 1 << m;
-    auto heap_index = [m](int q) {
-      const int tz = __ffs(q) - 1;
-      return (1 << (m - 1 - tz)) + (q >> (tz + 1));
-    };
-    __syncwarp();  // previous ray's readers of cdf/buf are done
-    float* cdf_out = a.cdf ? a.cdf + (cur.cbase + r) : nullptr;
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      const int j = lane * c + i;
-      if (kStatic || (i < c && j < kc)) {
-        const float val = fmaxf(off + ps[i], floor_prev);
-        cdf[heap_index(j + 1)] = val;
-        if (cdf_out) cdf_out[j + 1] = val;
-      }
-    }
-    if (cdf_out && lane == 0) cdf_out[0] = 0.f;
-    if (a.offsets || first_ray) {  // the +inf tail only moves when the count changes (packed)
-      for (int q = kc + 1 + lane; q < Pc; q += 32) cdf[heap_index(q)] = CUDART_INF_F;
-      first_ray = false;
-    }
-    __syncwarp();
-
-    // ---- 2. the lane's EPF consecutive new samples --------------------------------------
-    float v[EPF];
-    int32_t* irow = a.idx ? a.idx + cur.fbase : nullptr;
-    float* frow = a.z_fine ? a.z_fine + cur.fbase : nullptr;
-    // descend the tree: node <- 2*node + (tree[node] <= u); after m steps node - Pc is the
-    // number of entries cdf[q >= 1] <= u, i.e. clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
-    // (tree[node] <= u) is the complement of the sign bit of u - tree[node]: the subtraction
-    // is exact in sign (no flush to zero), +inf padding gives -inf.
-    unsigned node[EPF];
-#pragma unroll
-    for (int q = 0; q < EPF; ++q) node[q] = 1;
-    constexpr int kMaxDepth = kStatic ? ilog2_c(KC) + 1 : ((EPT == 2) ? 6 : (EPT == 4) ? 7 : (EPT == 8) ? 8 : 9);
-#pragma unroll
-    for (int step = 0; step < kMaxDepth; ++step) {
-      if (kStatic || step < m) {  // warp-uniform
-#pragma unroll
-        for (int q = 0; q < EPF; ++q) {
-          const float d = __fsub_rn(cur.a[q], cdf[node[q]]);
-          node[q] = 2 * node[q] + 1 - (__float_as_uint(d) >> 31);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < EPF; ++q) {
-      const int e = e0 + q;
-      const int bin = (int)node[q] - Pc;
-      const float num = __fadd_rn((float)bin, cur.b[q]);
-      const float t = kc_pow2 ? __fmul_rn(num, inv_kc) : __fdiv_rn(num, kcf);
-      float val = __fadd_rn(near, __fmul_rn(span, t));
-      if (e < n) {
-        if (irow) irow[e] = bin;
-        if (frow) frow[e] = val;
-      } else if (e < n + nd) {
-        // sample_depth's randn*std (depth NOT added), clamped (renderers.py:62-66, :255)
-        val = fminf(fmaxf(__fmul_rn(cur.a[q], a.depth_std), near), far);
-      } else {
-        val = CUDART_INF_F;
-      }
-      v[q] = val;
-    }
-    if (do_sort) {
-      // ---- 3. sort the new samples in registers -----------------------------------------
-      sort_blocked<EPF>(v, sg);
-
-      // ---- 4. lay out [coarse | +inf | new descending] striped over the lanes -------------
-#pragma unroll
-      for (int q = 0; q < EPF; ++q) buf[P - 1 - (e0 + q)] = v[q];
-      __syncwarp();
-      float x[EPT];
-#pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        if (i < CW) x[i] = cur.zc[i];                 // runtime shapes: +inf beyond kc
-        else if (i < EPC) x[i] = CUDART_INF_F;        // static shapes: pure padding
-        else x[i] = buf[i * 32 + lane];               // positions >= P - M
-      }
-      // coarse depths must be ascending for the merge; check the (q, q+1) pairs inside [0, kc)
-      bool unsorted = false;
-#pragma unroll
-      for (int i = 0; i < CW; ++i) {
-        float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
-        const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], 0);
-        if (lane == 31) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
-        if ((kStatic || i * 32 + lane + 1 < kc) && x[i] > nx) unsorted = true;
-      }
-      if (__any_sync(0xffffffffu, unsorted)) {
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) buf[i * 32 + lane] = x[i];
-        sort_smem(buf, P, lane);
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) x[i] = buf[i * 32 + lane];
-      } else {
-        merge_striped<EPT, kInf0>(x, sg);
-      }
-
-      // ---- 5. coalesced store of the first `total` keys ------------------------------------
-      float* out = a.z_sorted + (cur.cbase + cur.fbase + r * (int64_t)nd);
-#pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        const int q = i * 32 + lane;
-        if (q < total) out[q] = x[i];
-      }
-    }
+    process_ray<EPF, EPT, KC, NI, ND>(a, cur, r, cdf, buf, lane, sg, first_ray);
     if (more) cur = nxt;
   }
 }
@@ -367,7 +413,17 @@ static int launch_reg(const ImportanceRegArgs& a, cudaStream_t stream) {
   int64_t blocks = (a.R + kRegWarps - 1) / kRegWarps;
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (blocks > cap) blocks = cap;
-  importance_reg_kernel<EPF, EPT, KC, NI, ND><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
+  importance_reg_kernel<EPF, EPT, KC, NI, ND, false><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
+  return check_launch();
+}
+
+// packed layout: only the rays of class (EPF, EPT)
+template <int EPF, int EPT>
+static int launch_reg_class(const ImportanceRegArgs& a, cudaStream_t stream) {
+  int64_t blocks = (a.R + kRegWarps * 32 - 1) / (kRegWarps * 32);
+  const int64_t cap = (int64_t)kNumSMs * (EPT >= 16 ? 2 : 3);
+  if (blocks > cap) blocks = cap;
+  importance_reg_kernel<EPF, EPT, 0, 0, 0, true><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
   return check_launch();
 }
 
@@ -423,6 +479,30 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
     AVR_REG_STATIC(4, 8, 64, 128, 0)
     AVR_REG_STATIC(1, 4, 64, 16, 16)
 #undef AVR_REG_STATIC
+  }
+  // packed layout with enough rays to amortise the launches: one launch per ray class up to
+  // the caller's maxima (AVR_PACKED_CLASSES=0: one launch, every ray at the maximum shape)
+  if (offsets && R >= 4096) {
+    const char* sw = std::getenv("AVR_PACKED_CLASSES");
+    if (!(sw && sw[0] == '0')) {
+#define AVR_REG_CLASS(F, T)                              \
+  if (F <= epf && T <= ept) {                            \
+    const int rc = launch_reg_class<F, T>(a, stream);    \
+    if (rc != AVR_OK) return rc;                         \
+  }
+      AVR_REG_CLASS(1, 2)
+      AVR_REG_CLASS(1, 4)
+      AVR_REG_CLASS(1, 8)
+      AVR_REG_CLASS(1, 16)
+      AVR_REG_CLASS(2, 4)
+      AVR_REG_CLASS(2, 8)
+      AVR_REG_CLASS(2, 16)
+      AVR_REG_CLASS(4, 8)
+      AVR_REG_CLASS(4, 16)
+      AVR_REG_CLASS(8, 16)
+#undef AVR_REG_CLASS
+      return AVR_OK;
+    }
   }
 #define AVR_REG_CASE(F, T) \
   if (epf == F && ept == T) return launch_reg<F, T>(a, stream);
