@@ -120,48 +120,83 @@ __device__ __forceinline__ void load_ray(RayIn<EPF, EPC>& in, const ImportanceRe
 #pragma unroll
       for (int i = 0; i < CW; ++i) in.zc[i] = zrow[i * 32 + lane];
     }
-  } else {
-    const int c = (kc + 31) >> 5;  // weights per lane, blocked: j = lane*c + i
+  } else if (kc > 0) {
+    // run-time shapes use a FIXED layout per kernel variant (EPC bins per lane, whatever the
+    // ray's count): clamped unconditional loads + selects instead of guarded loads, and every
+    // index that depends only on the lane is hoisted out of the ray loop
+    const int last = kc - 1;
 #pragma unroll
     for (int i = 0; i < EPC; ++i) {
-      const int j = lane * c + i;
-      in.w[i] = (i < c && j < kc) ? wrow[j] : 0.f;
+      const int j = lane * EPC + i;
+      in.w[i] = wrow[j < last ? j : last];  // entries with j >= kc are masked where they are used
     }
     if (do_sort) {
       const float* zrow = a.z_coarse + in.cbase;
 #pragma unroll
       for (int i = 0; i < EPC; ++i) {
         const int j = i * 32 + lane;
-        in.zc[i] = (j < kc) ? zrow[j] : CUDART_INF_F;
+        const float zv = zrow[j < last ? j : last];
+        in.zc[i] = (j < kc) ? zv : CUDART_INF_F;
       }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPC; ++i) {
+      in.w[i] = 0.f;
+      in.zc[i] = CUDART_INF_F;
     }
   }
   const int e0 = lane * EPF;
   const float* urow = a.u + in.fbase;
   const float* u2row = a.u2 + in.fbase;
-  const bool all_imp = kStatic ? (NI == 32 * EPF) : (e0 + EPF <= n);
-  if (EPF >= 4 && a.vec4 && all_imp) {  // 16-byte loads of the lane's consecutive draws
+  if (kStatic) {
+    if (EPF >= 4 && a.vec4 && NI == 32 * EPF) {  // 16-byte loads of the lane's consecutive draws
 #pragma unroll
-    for (int q = 0; q < EPF; q += 4) {
-      const float4 p4 = *reinterpret_cast<const float4*>(urow + e0 + q);
-      const float4 j4 = *reinterpret_cast<const float4*>(u2row + e0 + q);
-      in.a[q] = p4.x; in.a[(q + 1) % EPF] = p4.y; in.a[(q + 2) % EPF] = p4.z; in.a[(q + 3) % EPF] = p4.w;
-      in.b[q] = j4.x; in.b[(q + 1) % EPF] = j4.y; in.b[(q + 2) % EPF] = j4.z; in.b[(q + 3) % EPF] = j4.w;
+      for (int q = 0; q < EPF; q += 4) {
+        const float4 p4 = *reinterpret_cast<const float4*>(urow + e0 + q);
+        const float4 j4 = *reinterpret_cast<const float4*>(u2row + e0 + q);
+        in.a[q] = p4.x; in.a[(q + 1) % EPF] = p4.y; in.a[(q + 2) % EPF] = p4.z; in.a[(q + 3) % EPF] = p4.w;
+        in.b[q] = j4.x; in.b[(q + 1) % EPF] = j4.y; in.b[(q + 2) % EPF] = j4.z; in.b[(q + 3) % EPF] = j4.w;
+      }
+    } else {
+      const float* nrow = a.normals ? a.normals + r * (int64_t)nd : nullptr;
+#pragma unroll
+      for (int q = 0; q < EPF; ++q) {
+        const int e = e0 + q;
+        float va = 0.f, vb = 0.f;
+        if (e < n) {
+          va = urow[e];
+          vb = u2row[e];
+        } else if (e < n + nd && do_sort) {
+          va = nrow[e - n];
+        }
+        in.a[q] = va;
+        in.b[q] = vb;
+      }
     }
   } else {
-    const float* nrow = a.normals ? a.normals + r * (int64_t)nd : nullptr;
 #pragma unroll
     for (int q = 0; q < EPF; ++q) {
-      const int e = e0 + q;
-      float va = 0.f, vb = 0.f;
-      if (e < n) {
-        va = urow[e];
-        vb = u2row[e];
-      } else if (e < n + nd && do_sort) {
-        va = nrow[e - n];
+      in.a[q] = 0.f;
+      in.b[q] = 0.f;
+    }
+    if (n > 0) {
+#pragma unroll
+      for (int q = 0; q < EPF; ++q) {
+        const int e = e0 + q;
+        const int ec = e < n - 1 ? e : n - 1;
+        in.a[q] = urow[ec];
+        in.b[q] = u2row[ec];
       }
-      in.a[q] = va;
-      in.b[q] = vb;
+    }
+    if (nd > 0 && do_sort) {  // dense only: the packed entry point has no depth samples
+      const float* nrow = a.normals + r * (int64_t)nd;
+#pragma unroll
+      for (int q = 0; q < EPF; ++q) {
+        const int e = e0 + q - n;
+        const float nv = nrow[e < 0 ? 0 : (e < nd - 1 ? e : nd - 1)];
+        if (e >= 0) in.a[q] = nv;  // only read where n <= e0 + q < n + nd
+      }
     }
   }
 }
@@ -191,22 +226,27 @@ __device__ __forceinline__ void process_ray(const ImportanceRegArgs& a, const Ra
   // blocked scan: each lane owns c consecutive bins; local running sums, one exclusive
   // warp scan of the lane totals, then a running max (a parallel prefix sum is not
   // monotone in floating point; the search needs a non-decreasing table)
-  const int c = kStatic ? CW : ((kc + 31) >> 5);
+  constexpr int c = CW;  // bins per lane: KC/32 (static shapes) or the variant's EPC (run-time shapes)
+  auto valid = [&](int i) { return kStatic || (lane * c + i < kc); };
   float wp[CW];
   float part = 0.f;
 #pragma unroll
   for (int i = 0; i < CW; ++i) {
-    wp[i] = __fadd_rn(cur.w[i], kPdfEps);
-    if (kStatic || (i < c && lane * c + i < kc)) part += wp[i];
+    wp[i] = valid(i) ? __fadd_rn(cur.w[i], kPdfEps) : 0.f;
+    part += wp[i];
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
   const float S = part;
+  // static shapes divide like the reference (renderers.py:37); run-time shapes (a lane may own
+  // up to 12 bins) multiply by 1/S: <= 1 ulp per pdf entry, far inside the cdf's tolerance, and
+  // the search stays bit-exact with respect to the cdf the kernel exports
+  const float rS = kStatic ? 0.f : __fdiv_rn(1.0f, S);
   float ps[CW];
   float run = 0.f;
 #pragma unroll
   for (int i = 0; i < CW; ++i) {
-    if (kStatic || (i < c && lane * c + i < kc)) run += __fdiv_rn(wp[i], S);
+    run += kStatic ? __fdiv_rn(wp[i], S) : __fmul_rn(wp[i], rS);
     ps[i] = run;
   }
   float incl = run;  // inclusive scan of the lane totals
@@ -229,13 +269,10 @@ __device__ __forceinline__ void process_ray(const ImportanceRegArgs& a, const Ra
   // index 1 = root): the nodes one search step can touch are contiguous, so the 32 lanes'
   // probes fall into distinct banks (a sorted table probed at power-of-two strides is a
   // worst case for bank conflicts).  Sorted position q in [1, Pc) holds cdf[q], +inf
-  // beyond Kc; cdf[0] = 0 is implicit.
-  int m = kStatic ? ilog2_c(KC) + 1 : 1;  // tree depth: Pc = 2^m > kc
-  if (!kStatic) {
-    while ((1 << m) <= kc) ++m;
-  }
-  const int Pc = 1 << m;
-  auto heap_index = [m](int q) {
+  // beyond Kc; cdf[0] = 0 is implicit.  The depth is a constant of the variant.
+  constexpr int m = kStatic ? ilog2_c(KC) + 1 : ilog2_c(P);
+  constexpr int Pc = 1 << m;
+  auto heap_index = [](int q) {
     const int tz = __ffs(q) - 1;
     return (1 << (m - 1 - tz)) + (q >> (tz + 1));
   };
@@ -244,15 +281,13 @@ __device__ __forceinline__ void process_ray(const ImportanceRegArgs& a, const Ra
 #pragma unroll
   for (int i = 0; i < CW; ++i) {
     const int j = lane * c + i;
-    if (kStatic || (i < c && j < kc)) {
-      const float val = fmaxf(off + ps[i], floor_prev);
-      cdf[heap_index(j + 1)] = val;
-      if (cdf_out) cdf_out[j + 1] = val;
-    }
+    const float val = fmaxf(off + ps[i], floor_prev);
+    cdf[heap_index(j + 1)] = valid(i) ? val : CUDART_INF_F;
+    if (cdf_out && valid(i)) cdf_out[j + 1] = val;
   }
   if (cdf_out && lane == 0) cdf_out[0] = 0.f;
-  if (a.offsets || first_ray) {  // the +inf tail only moves when the count changes (packed)
-    for (int q = kc + 1 + lane; q < Pc; q += 32) cdf[heap_index(q)] = CUDART_INF_F;
+  if (first_ray) {  // slots no lane owns: +inf once
+    for (int q = 32 * c + 1 + lane; q < Pc; q += 32) cdf[heap_index(q)] = CUDART_INF_F;
     first_ray = false;
   }
   __syncwarp();
@@ -268,15 +303,12 @@ __device__ __forceinline__ void process_ray(const ImportanceRegArgs& a, const Ra
   unsigned node[EPF];
 #pragma unroll
   for (int q = 0; q < EPF; ++q) node[q] = 1;
-  constexpr int kMaxDepth = kStatic ? ilog2_c(KC) + 1 : ((EPT == 2) ? 6 : (EPT == 4) ? 7 : (EPT == 8) ? 8 : 9);
 #pragma unroll
-  for (int step = 0; step < kMaxDepth; ++step) {
-    if (kStatic || step < m) {  // warp-uniform
+  for (int step = 0; step < m; ++step) {
 #pragma unroll
-      for (int q = 0; q < EPF; ++q) {
-        const float d = __fsub_rn(cur.a[q], cdf[node[q]]);
-        node[q] = 2 * node[q] + 1 - (__float_as_uint(d) >> 31);
-      }
+    for (int q = 0; q < EPF; ++q) {
+      const float d = __fsub_rn(cur.a[q], cdf[node[q]]);
+      node[q] = 2 * node[q] + 1 - (__float_as_uint(d) >> 31);
     }
   }
 #pragma unroll
