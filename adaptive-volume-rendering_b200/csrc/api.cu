@@ -236,6 +236,48 @@ int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* o
   return fn(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs, d_z, as_stream(stream));
 }
 
+/* ------------------------------------------ ray setup / sample points / depth -- */
+
+int avr_ray_points_fwd(const float* ros, const float* rds, const float* z, int64_t R, int K, float* pts,
+                       float* viewdirs, avr_stream_t stream) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!ros || !rds || !z || !pts) return AVR_ERR_BAD_ARG;
+  return launch_ray_points(ros, rds, z, nullptr, nullptr, 0, false, R, K, nullptr, pts, viewdirs, as_stream(stream));
+}
+
+int avr_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K, float* d_z, avr_stream_t stream) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!rds || !g_pts || !d_z) return AVR_ERR_BAD_ARG;
+  return launch_ray_points_bwd(rds, g_pts, R, K, d_z, as_stream(stream));
+}
+
+int avr_coarse_sample_points_fwd(const float* near, const float* far, int bound_stride, const float* u,
+                                 const float* ros, const float* rds, int64_t R, int K, float* z, float* pts,
+                                 float* viewdirs, avr_stream_t stream) {
+  if (R < 0 || K < 1 || (bound_stride != 0 && bound_stride != 1)) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!near || !far || !u || !ros || !rds || !z || !pts) return AVR_ERR_BAD_ARG;
+  return launch_ray_points(ros, rds, u, near, far, bound_stride, true, R, K, z, pts, viewdirs, as_stream(stream));
+}
+
+int avr_world_rays(const float* x_pix, const float* kinv, const float* cam2world, int64_t R, int64_t rays_per_cam,
+                   float* ros, float* rds, avr_stream_t stream) {
+  if (R < 0 || rays_per_cam < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!x_pix || !kinv || !cam2world || !ros || !rds || !aligned16(cam2world)) return AVR_ERR_BAD_ARG;
+  return launch_world_rays(x_pix, kinv, cam2world, R, rays_per_cam, ros, rds, as_stream(stream));
+}
+
+int avr_depth_from_world(const float* ros, const float* rds, const float* dist, const float* cam2world, int64_t R,
+                         float* depth, float* grad_row, avr_stream_t stream) {
+  if (R < 0) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!ros || !cam2world || !depth || (dist && !rds) || !aligned16(cam2world)) return AVR_ERR_BAD_ARG;
+  return launch_depth_from_world(ros, rds, dist, cam2world, R, depth, grad_row, as_stream(stream));
+}
+
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
 }  // extern "C"

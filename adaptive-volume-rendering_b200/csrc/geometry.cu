@@ -1,0 +1,246 @@
+// The seams either side of the sampling/compositing path:
+//
+//   * sample points for the radiance-field callback: pts = o + d*z and the K-fold view-direction
+//     broadcast the reference materialises with expand().reshape()  (renderers.py:171-175,
+//     260-265, 496-500), optionally fused with the stratified coarse sampler so z, pts and
+//     viewdirs leave in one pass over the uniforms;
+//   * ray setup, utils.get_world_rays (utils.py:246-267, 309-336): unproject the pixel through
+//     K^-1, flip to the camera's -z convention, normalise, rotate into the world;
+//   * depth re-projection, utils.depth_from_world (utils.py:358-361): -z of the composited
+//     point in camera coordinates.  The reference inverts the (SB,R,4,4) pose tensor per ray;
+//     here each thread forms only the third row of its pose's inverse (cofactors).
+//
+// All of it is elementwise, HBM-bound streaming: 16-byte accesses, one thread per 4 samples.
+#include "avr_common.cuh"
+#include "kernels.h"
+
+namespace avr {
+
+struct Ray3 {
+  float ox, oy, oz, dx, dy, dz;
+};
+__device__ __forceinline__ Ray3 load_ray3(const float* __restrict__ ros, const float* __restrict__ rds, int64_t r) {
+  Ray3 q;
+  q.ox = ros[r * 3 + 0]; q.oy = ros[r * 3 + 1]; q.oz = ros[r * 3 + 2];
+  q.dx = rds[r * 3 + 0]; q.dy = rds[r * 3 + 1]; q.dz = rds[r * 3 + 2];
+  return q;
+}
+
+// pts = ros + rds * z with the reference's two roundings (mul, then add: renderers.py:171)
+__device__ __forceinline__ float3 point_on_ray(const Ray3& q, float z) {
+  return make_float3(__fadd_rn(q.ox, __fmul_rn(q.dx, z)), __fadd_rn(q.oy, __fmul_rn(q.dy, z)),
+                     __fadd_rn(q.oz, __fmul_rn(q.dz, z)));
+}
+
+// z = near + (far-near)*(j/K) + (u*(far-near))/K       renderers.py:12-14
+__device__ __forceinline__ float coarse_z(float near, float span, int j, float kf, float inv_k, bool pow2, float u) {
+  const float base = __fadd_rn(near, __fmul_rn(span, __fdiv_rn((float)j, kf)));
+  const float jit = __fmul_rn(u, span);
+  return __fadd_rn(base, pow2 ? __fmul_rn(jit, inv_k) : __fdiv_rn(jit, kf));
+}
+
+// One thread per 4 consecutive samples (K % 4 == 0 keeps them in one ray): 16 B of z (or u) in,
+// 48 B of points and 48 B of view directions out as three 16-byte stores each.
+// kFromU: `zu` holds the uniforms; z is computed here (and stored) — the fused coarse sampler.
+template <bool kFromU>
+__global__ void __launch_bounds__(256)
+ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ rds, const float* __restrict__ zu,
+                       const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
+                       int64_t n_vec, int K, float* __restrict__ z_out, float* __restrict__ pts,
+                       float* __restrict__ viewdirs) {
+  const float kf = (float)K;
+  const bool pow2 = (K & (K - 1)) == 0;
+  const float inv_k = 1.0f / kf;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_vec; v += stride) {
+    const int64_t i = v * 4;
+    const int64_t r = i / K;
+    const int j = (int)(i - r * K);
+    const Ray3 q = load_ray3(ros, rds, r);
+    float4 z4 = ldg_stream(reinterpret_cast<const float4*>(zu + i));
+    if (kFromU) {
+      const int64_t b = bound_stride ? r : 0;
+      const float n0 = near[b];
+      const float span = __fsub_rn(far[b], n0);
+      z4.x = coarse_z(n0, span, j + 0, kf, inv_k, pow2, z4.x);
+      z4.y = coarse_z(n0, span, j + 1, kf, inv_k, pow2, z4.y);
+      z4.z = coarse_z(n0, span, j + 2, kf, inv_k, pow2, z4.z);
+      z4.w = coarse_z(n0, span, j + 3, kf, inv_k, pow2, z4.w);
+      stg_stream(reinterpret_cast<float4*>(z_out + i), z4);
+    }
+    const float3 p0 = point_on_ray(q, z4.x), p1 = point_on_ray(q, z4.y), p2 = point_on_ray(q, z4.z),
+                 p3 = point_on_ray(q, z4.w);
+    float4* po = reinterpret_cast<float4*>(pts + i * 3);
+    stg_stream(po + 0, make_float4(p0.x, p0.y, p0.z, p1.x));
+    stg_stream(po + 1, make_float4(p1.y, p1.z, p2.x, p2.y));
+    stg_stream(po + 2, make_float4(p2.z, p3.x, p3.y, p3.z));
+    if (viewdirs) {
+      float4* vo = reinterpret_cast<float4*>(viewdirs + i * 3);
+      stg_stream(vo + 0, make_float4(q.dx, q.dy, q.dz, q.dx));
+      stg_stream(vo + 1, make_float4(q.dy, q.dz, q.dx, q.dy));
+      stg_stream(vo + 2, make_float4(q.dz, q.dx, q.dy, q.dz));
+    }
+  }
+}
+
+// any K / alignment: one thread per sample
+template <bool kFromU>
+__global__ void __launch_bounds__(256)
+ray_points_scalar_kernel(const float* __restrict__ ros, const float* __restrict__ rds, const float* __restrict__ zu,
+                         const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
+                         int64_t total, int K, float* __restrict__ z_out, float* __restrict__ pts,
+                         float* __restrict__ viewdirs) {
+  const float kf = (float)K;
+  const bool pow2 = (K & (K - 1)) == 0;
+  const float inv_k = 1.0f / kf;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / K;
+    const Ray3 q = load_ray3(ros, rds, r);
+    float z = zu[i];
+    if (kFromU) {
+      const int64_t b = bound_stride ? r : 0;
+      const float n0 = near[b];
+      z = coarse_z(n0, __fsub_rn(far[b], n0), (int)(i - r * K), kf, inv_k, pow2, z);
+      z_out[i] = z;
+    }
+    const float3 p = point_on_ray(q, z);
+    pts[i * 3 + 0] = p.x; pts[i * 3 + 1] = p.y; pts[i * 3 + 2] = p.z;
+    if (viewdirs) {
+      viewdirs[i * 3 + 0] = q.dx; viewdirs[i * 3 + 1] = q.dy; viewdirs[i * 3 + 2] = q.dz;
+    }
+  }
+}
+
+// d_z[r,k] = g_pts[r,k,:] . rds[r,:]   (AdaptiveVolumeRenderer: the sample depths carry grad)
+__global__ void __launch_bounds__(256)
+ray_points_bwd_kernel(const float* __restrict__ rds, const float* __restrict__ g_pts, int64_t total, int K,
+                      float* __restrict__ d_z) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / K;
+    const float gx = g_pts[i * 3 + 0], gy = g_pts[i * 3 + 1], gz = g_pts[i * 3 + 2];
+    d_z[i] = gx * rds[r * 3 + 0] + gy * rds[r * 3 + 1] + gz * rds[r * 3 + 2];
+  }
+}
+
+// utils.get_world_rays: origin = pose[:3,3]; dir = R_pose * normalize(flip(K^-1 [x,y,1]))
+// kinv: [n_cams,3,3] (the inverse intrinsics, one per object: ray r uses camera r / rays_per_cam)
+__global__ void __launch_bounds__(256)
+world_rays_kernel(const float* __restrict__ x_pix, const float* __restrict__ kinv, const float* __restrict__ c2w,
+                  int64_t R, int64_t rays_per_cam, float* __restrict__ ros, float* __restrict__ rds) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += stride) {
+    const float* ki = kinv + (r / rays_per_cam) * 9;
+    const float x = x_pix[r * 2 + 0], y = x_pix[r * 2 + 1];
+    // einsum('ij,kj->ki', K^-1, [x,y,1])  (utils.py:263)
+    float cx = ki[0] * x + ki[1] * y + ki[2];
+    float cy = ki[3] * x + ki[4] * y + ki[5];
+    float cz = ki[6] * x + ki[7] * y + ki[8];
+    // unproject negates x, then scales by z = -1 (utils.py:264-266, :312)
+    cx = -cx;
+    cx *= -1.0f; cy *= -1.0f; cz *= -1.0f;
+    const float nrm = sqrtf(cx * cx + cy * cy + cz * cz);   // torch.norm (utils.py:313)
+    cx = cx / nrm; cy = cy / nrm; cz = cz / nrm;
+    const float4* m = reinterpret_cast<const float4*>(c2w + r * 16);
+    const float4 r0 = m[0], r1 = m[1], r2 = m[2];
+    ros[r * 3 + 0] = r0.w; ros[r * 3 + 1] = r1.w; ros[r * 3 + 2] = r2.w;      // pose[:3, -1]
+    rds[r * 3 + 0] = r0.x * cx + r0.y * cy + r0.z * cz;                          // pose @ [dir, 0]
+    rds[r * 3 + 1] = r1.x * cx + r1.y * cy + r1.z * cz;
+    rds[r * 3 + 2] = r2.x * cx + r2.y * cy + r2.z * cz;
+  }
+}
+
+// utils.depth_from_world on the composited point p = o + d*dist (renderers.py:274-275, 508-509),
+// or on given points (dist == nullptr: `ros` holds the points; renderers.py:486):
+// depth = -(pose^-1 [p,1])_z.  Only row 2 of the inverse is needed: cofactors of the 4x4.
+__global__ void __launch_bounds__(256)
+depth_from_world_kernel(const float* __restrict__ ros, const float* __restrict__ rds, const float* __restrict__ dist,
+                        const float* __restrict__ c2w, int64_t R, float* __restrict__ depth,
+                        float* __restrict__ grad_row) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += stride) {
+    float px = ros[r * 3 + 0], py = ros[r * 3 + 1], pz = ros[r * 3 + 2];
+    if (dist) {
+      const float t = dist[r];
+      px = __fadd_rn(px, __fmul_rn(rds[r * 3 + 0], t));
+      py = __fadd_rn(py, __fmul_rn(rds[r * 3 + 1], t));
+      pz = __fadd_rn(pz, __fmul_rn(rds[r * 3 + 2], t));
+    }
+    const float4* mp = reinterpret_cast<const float4*>(c2w + r * 16);
+    const float4 a = mp[0], b = mp[1], c = mp[2], d = mp[3];
+    // inverse(M)[2][j] = cofactor(M)[j][2] / det(M); the cofactors C_j2 delete column 2 of M
+    // 3x3 minors over columns (0,1,3):
+    auto det3 = [](float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) {
+      return a0 * (b1 * c2 - b2 * c1) - a1 * (b0 * c2 - b2 * c0) + a2 * (b0 * c1 - b1 * c0);
+    };
+    const float c02 = det3(b.x, b.y, b.w, c.x, c.y, c.w, d.x, d.y, d.w);    // delete row 0, col 2, sign +
+    const float c12 = -det3(a.x, a.y, a.w, c.x, c.y, c.w, d.x, d.y, d.w);   // row 1, sign -
+    const float c22 = det3(a.x, a.y, a.w, b.x, b.y, b.w, d.x, d.y, d.w);    // row 2, sign +
+    const float c32 = -det3(a.x, a.y, a.w, b.x, b.y, b.w, c.x, c.y, c.w);   // row 3, sign -
+    // det(M) by expansion along column 2
+    const float det = a.z * c02 + b.z * c12 + c.z * c22 + d.z * c32;
+    const float zc = (c02 * px + c12 * py + c22 * pz + c32) / det;
+    depth[r] = -zc;
+    if (grad_row) {  // d depth / d p: what the backward pass multiplies by (depth is affine in p)
+      grad_row[r * 3 + 0] = -(c02 / det);
+      grad_row[r * 3 + 1] = -(c12 / det);
+      grad_row[r * 3 + 2] = -(c22 / det);
+    }
+  }
+}
+
+static int grid_1d(int64_t work, int max_blocks) {
+  int64_t b = (work + 255) / 256;
+  if (b < 1) b = 1;
+  return (int)(b < max_blocks ? b : max_blocks);
+}
+
+int launch_ray_points(const float* ros, const float* rds, const float* z_or_u, const float* near, const float* far,
+                      int bound_stride, bool from_u, int64_t R, int K, float* z_out, float* pts, float* viewdirs,
+                      cudaStream_t stream) {
+  const int64_t total = R * (int64_t)K;
+  if (total == 0) return AVR_OK;
+  const bool vec = (K % 4 == 0) && aligned16(z_or_u) && aligned16(pts) && aligned16(viewdirs) && aligned16(z_out);
+  const int max_blocks = kNumSMs * 16;
+  if (vec) {
+    const int64_t n_vec = total / 4;
+    if (from_u) {
+      ray_points_vec4_kernel<true><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
+                                                                                  bound_stride, n_vec, K, z_out, pts, viewdirs);
+    } else {
+      ray_points_vec4_kernel<false><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
+                                                                                   bound_stride, n_vec, K, z_out, pts, viewdirs);
+    }
+  } else if (from_u) {
+    ray_points_scalar_kernel<true><<<grid_1d(total, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
+                                                                                  bound_stride, total, K, z_out, pts, viewdirs);
+  } else {
+    ray_points_scalar_kernel<false><<<grid_1d(total, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
+                                                                                   bound_stride, total, K, z_out, pts, viewdirs);
+  }
+  return check_launch();
+}
+
+int launch_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K, float* d_z, cudaStream_t stream) {
+  const int64_t total = R * (int64_t)K;
+  if (total == 0) return AVR_OK;
+  ray_points_bwd_kernel<<<grid_1d(total, kNumSMs * 16), 256, 0, stream>>>(rds, g_pts, total, K, d_z);
+  return check_launch();
+}
+
+int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, int64_t R, int64_t rays_per_cam,
+                      float* ros, float* rds, cudaStream_t stream) {
+  if (R == 0) return AVR_OK;
+  world_rays_kernel<<<grid_1d(R, kNumSMs * 16), 256, 0, stream>>>(x_pix, kinv, c2w, R, rays_per_cam, ros, rds);
+  return check_launch();
+}
+
+int launch_depth_from_world(const float* ros, const float* rds, const float* dist, const float* c2w, int64_t R,
+                            float* depth, float* grad_row, cudaStream_t stream) {
+  if (R == 0) return AVR_OK;
+  depth_from_world_kernel<<<grid_1d(R, kNumSMs * 16), 256, 0, stream>>>(ros, rds, dist, c2w, R, depth, grad_row);
+  return check_launch();
+}
+
+}  // namespace avr

@@ -65,6 +65,15 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
                           const int64_t* offsets, const int64_t* fine_offsets, int64_t R, int Kc, int n_imp,
                           int n_depth, float depth_std, float* z_fine, float* z_sorted, float* cdf, int32_t* idx,
                           cudaStream_t stream);
+// geometry.cu — ray setup, sample points for the radiance-field callback, depth re-projection
+int launch_ray_points(const float* ros, const float* rds, const float* z_or_u, const float* near, const float* far,
+                      int bound_stride, bool from_u, int64_t R, int K, float* z_out, float* pts, float* viewdirs,
+                      cudaStream_t stream);
+int launch_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K, float* d_z, cudaStream_t stream);
+int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, int64_t R, int64_t rays_per_cam,
+                      float* ros, float* rds, cudaStream_t stream);
+int launch_depth_from_world(const float* ros, const float* rds, const float* dist, const float* c2w, int64_t R,
+                            float* depth, float* grad_row, cudaStream_t stream);
 int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, cudaStream_t stream);
 
 }  // namespace avr

@@ -316,3 +316,144 @@ def importance_sample_packed(weights, z_coarse, near, far, u, u2, offsets, fine_
             ptr(offsets.contiguous()), ptr(fine_offsets.contiguous()), r, int(max_coarse), int(max_fine),
             ptr(z_fine), ptr(z_sorted), _stream(u)), "avr_importance_sample_packed")
     return z_fine, z_sorted
+
+
+# ------------------------------------------- ray setup / sample points / depth
+def _rays3(t: torch.Tensor) -> torch.Tensor:
+    return _f32c(t.reshape(-1, 3))
+
+
+class RayPoints(torch.autograd.Function):
+    """pts = ros + rds * z and the K-fold view-direction copy the radiance field is called with
+    (renderers.py:171-175, 260-265, 496-500).  Returns pts (..., K, 3), viewdirs (..., K, 3).
+    Backward: d_z in CUDA (the adaptive renderer's depths carry grad); gradients w.r.t. the ray
+    origins/directions are per-ray reductions nobody on the reference's path asks for — they are
+    formed with torch ops if requested."""
+
+    @staticmethod
+    def forward(ctx, ros, rds, z):
+        require_cuda(ros, rds, z)
+        zc = _f32c(z)
+        k = zc.shape[-1]
+        r = zc.numel() // k
+        o, d = _rays3(ros), _rays3(rds)
+        if o.shape[0] != r or d.shape[0] != r:
+            raise _lib.AvrError(f"ros/rds hold {o.shape[0]}/{d.shape[0]} rays, z holds {r}")
+        pts = torch.empty(*zc.shape, 3, dtype=torch.float32, device=zc.device)
+        vd = torch.empty_like(pts)
+        with torch.cuda.device(zc.device):
+            check(_lib.load().avr_ray_points_fwd(ptr(o), ptr(d), ptr(zc), r, k, ptr(pts), ptr(vd), _stream(zc)),
+                  "avr_ray_points_fwd")
+        ctx.save_for_backward(d, zc)
+        ctx.shapes = (ros.shape, rds.shape)
+        return pts, vd
+
+    @staticmethod
+    def backward(ctx, g_pts, g_vd):
+        d, zc = ctx.saved_tensors
+        k = zc.shape[-1]
+        r = zc.numel() // k
+        d_z = d_o = d_d = None
+        if g_pts is not None and ctx.needs_input_grad[2]:
+            g = _f32c(g_pts)
+            d_z = torch.empty_like(zc)
+            with torch.cuda.device(zc.device):
+                check(_lib.load().avr_ray_points_bwd(ptr(d), ptr(g), r, k, ptr(d_z), _stream(zc)), "avr_ray_points_bwd")
+        if ctx.needs_input_grad[0] and g_pts is not None:
+            d_o = g_pts.reshape(r, k, 3).sum(1).reshape(ctx.shapes[0])
+        if ctx.needs_input_grad[1]:
+            acc = torch.zeros(r, 3, dtype=torch.float32, device=zc.device)
+            if g_pts is not None:
+                acc = acc + (g_pts.reshape(r, k, 3) * zc.reshape(r, k, 1)).sum(1)
+            if g_vd is not None:
+                acc = acc + g_vd.reshape(r, k, 3).sum(1)
+            d_d = acc.reshape(ctx.shapes[1])
+        return d_o, d_d, d_z
+
+
+def ray_points(ros: torch.Tensor, rds: torch.Tensor, z: torch.Tensor):
+    """(pts, viewdirs), each (..., K, 3), for rays (..., 3) and depths (..., K)."""
+    return RayPoints.apply(ros, rds, z)
+
+
+def coarse_sample_points(near, far, bound_stride: int, u: torch.Tensor, ros: torch.Tensor, rds: torch.Tensor):
+    """sample_coarse + point generation in one pass over the uniforms (renderers.py:169-175).
+    Returns z (..., K), pts (..., K, 3), viewdirs (..., K, 3); non-differentiable (VolumeRenderer's
+    bounds are constants)."""
+    require_cuda(near, far, u, ros, rds)
+    u = _f32c(u)
+    k = u.shape[-1]
+    r = u.numel() // k
+    o, d = _rays3(ros.detach()), _rays3(rds.detach())
+    z = torch.empty_like(u)
+    pts = torch.empty(*u.shape, 3, dtype=torch.float32, device=u.device)
+    vd = torch.empty_like(pts)
+    with torch.cuda.device(u.device):
+        check(_lib.load().avr_coarse_sample_points_fwd(ptr(near), ptr(far), bound_stride, ptr(u), ptr(o), ptr(d), r, k,
+                                                       ptr(z), ptr(pts), ptr(vd), _stream(u)),
+              "avr_coarse_sample_points_fwd")
+    return z, pts, vd
+
+
+def world_rays(xy_pix: torch.Tensor, intrinsics: torch.Tensor, cam2world: torch.Tensor):
+    """utils.get_world_rays (utils.py:309-336): xy_pix (SB,R,2), intrinsics (SB,3,3), cam2world
+    (SB,R,4,4) -> origins, unit directions (SB,R,3).  The SB 3x3 inverses are taken with
+    torch.inverse exactly as the reference does (utils.py:263); everything per ray is the kernel.
+    Non-differentiable (the reference's poses and intrinsics are data)."""
+    require_cuda(xy_pix, intrinsics, cam2world)
+    sb, n = xy_pix.shape[0], xy_pix.shape[1]
+    x = _f32c(xy_pix.detach())
+    c2w = _f32c(cam2world.detach())
+    kinv = _f32c(intrinsics.detach().inverse())
+    if kinv.shape[0] != sb:
+        kinv = _f32c(kinv.expand(sb, 3, 3))
+    ros = torch.empty(sb, n, 3, dtype=torch.float32, device=x.device)
+    rds = torch.empty_like(ros)
+    with torch.cuda.device(x.device):
+        check(_lib.load().avr_world_rays(ptr(x), ptr(kinv), ptr(c2w), sb * n, n, ptr(ros), ptr(rds), _stream(x)),
+              "avr_world_rays")
+    return ros, rds
+
+
+class DepthFromWorld(torch.autograd.Function):
+    """depth = -(cam2world^-1 [p,1])_z with p = ros + rds*dist (dist given) or p = ros (dist None):
+    utils.depth_from_world (utils.py:358-361) at renderers.py:274-275, 486, 508-509.  depth is
+    affine in p, so backward is the saved per-ray row d depth/d p times the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, ros, rds, dist, cam2world):
+        require_cuda(ros, cam2world)
+        o = _rays3(ros)
+        r = o.shape[0]
+        d = _rays3(rds) if dist is not None else None
+        t = _f32c(dist.reshape(-1)) if dist is not None else None
+        c2w = _f32c(cam2world.detach().reshape(-1, 4, 4))
+        if c2w.shape[0] != r:
+            raise _lib.AvrError(f"cam2world holds {c2w.shape[0]} poses for {r} points")
+        need_grad = any(ctx.needs_input_grad[:3])
+        depth = torch.empty(ros.shape[:-1], dtype=torch.float32, device=o.device)
+        row = torch.empty(r, 3, dtype=torch.float32, device=o.device) if need_grad else None
+        with torch.cuda.device(o.device):
+            check(_lib.load().avr_depth_from_world(ptr(o), ptr(d), ptr(t), ptr(c2w), r, ptr(depth), ptr(row), _stream(o)),
+                  "avr_depth_from_world")
+        ctx.save_for_backward(row, d, t)
+        ctx.shapes = (ros.shape, None if rds is None else rds.shape, None if dist is None else dist.shape)
+        return depth
+
+    @staticmethod
+    def backward(ctx, g):
+        row, d, t = ctx.saved_tensors
+        gp = g.reshape(-1, 1) * row                      # dL/dp, (R,3)
+        d_o = gp.reshape(ctx.shapes[0]) if ctx.needs_input_grad[0] else None
+        d_d = d_t = None
+        if t is not None:
+            if ctx.needs_input_grad[1]:
+                d_d = (gp * t.reshape(-1, 1)).reshape(ctx.shapes[1])
+            if ctx.needs_input_grad[2]:
+                d_t = (gp * d).sum(-1).reshape(ctx.shapes[2])
+        return d_o, d_d, d_t, None
+
+
+def depth_from_world(ros, rds, dist, cam2world):
+    """Depth (SB,R) of ros + rds*dist (or of the points `ros` when dist is None) seen from cam2world."""
+    return DepthFromWorld.apply(ros, rds, dist, cam2world)

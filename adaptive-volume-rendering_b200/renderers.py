@@ -143,12 +143,9 @@ class VolumeRenderer(nn.Module):
 
         ros, rds = get_world_rays(x_pix, intrinsics, cam2world)                       # :166
 
-        # coarse pass
-        z_c = ops.coarse_sample_raw(near, far, 0, u_c)                                # :169
-        pts = ros.unsqueeze(-2) + rds.unsqueeze(-2) * z_c.unsqueeze(-1)               # :171
-        out = radiance_field(pts.reshape(sb, -1, 3),
-                             viewdirs=rds.unsqueeze(-2).expand(sb, num_rays, kc, -1).reshape(sb, -1, 3),
-                             coarse=True)                                             # :173
+        # coarse pass: depths, sample points and the view-direction copy in one kernel  # :169-175
+        z_c, pts, vd = ops.coarse_sample_points(near, far, 0, u_c, ros, rds)
+        out = radiance_field(pts.view(sb, -1, 3), viewdirs=vd.view(sb, -1, 3), coarse=True)   # :173
         rgb_c, _dist_c, w_c = ops.composite(out.view(sb, num_rays, kc, 4), z_c, white_back, 1.8, want_w=True)  # :180
 
         # importance + "depth" resampling, merged and sorted in one kernel             # :252-258
@@ -156,13 +153,11 @@ class VolumeRenderer(nn.Module):
                                     normals=normals if kd > 0 else None, depth_std=self.depth_std,
                                     want_fine=False, want_sorted=True)["z_sorted"]
         k = kc + self.n_fine
-        pts = ros.unsqueeze(-2) + rds.unsqueeze(-2) * z_s.unsqueeze(-1)               # :260
-        out = radiance_field(pts.reshape(sb, -1, 3),
-                             viewdirs=rds.unsqueeze(-2).expand(sb, num_rays, k, -1).reshape(sb, -1, 3),
-                             coarse=False)                                            # :263
+        pts, vd = ops.ray_points(ros, rds, z_s)                                       # :260-265
+        out = radiance_field(pts.view(sb, -1, 3), viewdirs=vd.view(sb, -1, 3), coarse=False)  # :263
         rgb_f, dist_f, _ = ops.composite(out.view(sb, num_rays, k, 4), z_s, white_back, 1.8, want_w=False)  # :270
 
-        depth = depth_from_world(ros + rds * dist_f.unsqueeze(-1), cam2world)         # :274-275
+        depth = depth_from_world(ros, cam2world, rds=rds, dist=dist_f)                # :274-275
         return rgb_c, rgb_f, depth, depth
 
     @classmethod
@@ -254,13 +249,11 @@ class AdaptiveVolumeRenderer(nn.Module):
         z = sample_coarse(final_distance - self.epsilon, final_distance + self.epsilon,
                           self.n_coarse, device=dev, u=u)                               # :492
         z_sorted, _ = ops.SortRays.apply(z)                                             # :494
-        pts = ros.unsqueeze(-2) + rds.unsqueeze(-2) * z_sorted.unsqueeze(-1)            # :496
-        out = phi(pts.reshape(sb, -1, 3), coarse=False,
-                  viewdirs=rds.unsqueeze(-2).expand(sb, num_rays, self.n_coarse, -1).reshape(sb, -1, 3),
-                  return_features=False)                                                # :499
+        pts, vd = ops.ray_points(ros, rds, z_sorted)                                    # :496-498 (d_z flows back)
+        out = phi(pts.view(sb, -1, 3), coarse=False, viewdirs=vd.view(sb, -1, 3), return_features=False)  # :499
         rgb, dist, _ = ops.composite(out.reshape(sb, num_rays, self.n_coarse, 4), z_sorted,
                                      bool(self.white_back), 1.8, want_w=False)          # :505
-        depth = depth_from_world(ros + rds * dist.unsqueeze(-1), cam2world)             # :508-509
+        depth = depth_from_world(ros, cam2world, rds=rds, dist=dist)                    # :508-509
         if debug:
             print("now AVR")
             print(f" pixel location is {xy_pix[0][64]}")

@@ -178,6 +178,39 @@ AVR_API int avr_importance_sample_packed(const float* weights, const float* z_co
                                  int64_t R, int max_coarse, int max_fine,
                                  float* z_fine, float* z_sorted, avr_stream_t stream);
 
+/* ------------------------------------------ ray setup / sample points / depth -- */
+
+/* Sample points handed to the radiance-field callback (renderers.py:171-175, 260-265, 496-500):
+ *   pts[r,k,:] = ros[r,:] + rds[r,:] * z[r,k]      (separate mul and add, like the reference)
+ *   viewdirs[r,k,:] = rds[r,:]                      (the expand().reshape() copy; may be NULL)
+ * ros, rds [R,3]; z [R,K]; pts, viewdirs [R,K,3] — i.e. the callback's (SB, R*K, 3) buffers. */
+AVR_API int avr_ray_points_fwd(const float* ros, const float* rds, const float* z, int64_t R, int K,
+                               float* pts, float* viewdirs, avr_stream_t stream);
+/* Gradient of the above w.r.t. z (AdaptiveVolumeRenderer, where the depths carry grad):
+ *   d_z[r,k] = g_pts[r,k,:] . rds[r,:] */
+AVR_API int avr_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K, float* d_z,
+                               avr_stream_t stream);
+/* sample_coarse fused with the point generation (renderers.py:169-175 in one pass over the
+ * uniforms): writes z [R,K] (bit-identical to avr_coarse_sample_fwd), pts and viewdirs. */
+AVR_API int avr_coarse_sample_points_fwd(const float* near, const float* far, int bound_stride, const float* u,
+                                         const float* ros, const float* rds, int64_t R, int K,
+                                         float* z, float* pts, float* viewdirs, avr_stream_t stream);
+
+/* utils.get_world_rays (utils.py:309-336): ray origins and unit directions in world coordinates.
+ *   x_pix [R,2]; kinv [n_cams,3,3] = inverse intrinsics, ray r uses camera r / rays_per_cam;
+ *   cam2world [R,4,4] (one pose per ray, as the reference's callers expand it, train.py:83);
+ *   ros, rds [R,3]. */
+AVR_API int avr_world_rays(const float* x_pix, const float* kinv, const float* cam2world, int64_t R,
+                           int64_t rays_per_cam, float* ros, float* rds, avr_stream_t stream);
+/* utils.depth_from_world (utils.py:358-361) of the composited point ros + rds * dist
+ * (renderers.py:274-275, 508-509); dist == NULL: `ros` holds the world points themselves and
+ * rds is ignored (renderers.py:486).  depth [R] = -(cam2world^-1 [p,1])_z.
+ * grad_row [R,3] (may be NULL) receives d depth / d p, the per-ray constant the backward pass
+ * needs (depth is affine in the point; the loss's depth penalty, utils.py:374-376, sends
+ * gradient through it). */
+AVR_API int avr_depth_from_world(const float* ros, const float* rds, const float* dist, const float* cam2world,
+                                 int64_t R, float* depth, float* grad_row, avr_stream_t stream);
+
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
 /* One forward+backward compositing pass over HOST buffers (pinned for full speed):

@@ -235,6 +235,29 @@ def case_adaptive_renderer(ref):
          **{f"ref_phi_grad_{i}": p.grad.clone() for i, p in enumerate(phi.parameters())})
 
 
+def case_geometry(ref):
+    """utils.get_world_rays / depth_from_world and the point generation of renderers.py:171-175,
+    run by the reference's own utils module (star-imported into renderers, renderers.py:1)."""
+    g = torch.Generator().manual_seed(31)
+    sb, r, k = 2, 75, 12
+    cam2world, intrinsics, x_pix = camera_setup(sb, r, seed=5)
+    # per-ray poses that differ (a general rigid pose per ray, as the API allows)
+    jitter = torch.zeros(sb, r, 4, 4)
+    jitter[..., :3, 3] = 0.05 * torch.randn(sb, r, 3, generator=g)
+    cam2world = cam2world + jitter
+    ros, rds = ref.get_world_rays(x_pix, intrinsics, cam2world)
+    z = torch.sort(0.8 + torch.rand(sb, r, k, generator=g), -1).values
+    pts = ros.unsqueeze(-2) + rds.unsqueeze(-2) * z.unsqueeze(-1)                # renderers.py:171
+    viewdirs = rds.unsqueeze(-2).expand(sb, r, k, -1).reshape(sb, -1, 3)          # :174
+    dist = 0.8 + torch.rand(sb, r, generator=g)
+    world = (ros + rds * dist.unsqueeze(-1)).requires_grad_(True)
+    depth = ref.depth_from_world(world, cam2world)                                # :274-275
+    gd = torch.randn(sb, r, generator=g)
+    depth.backward(gd)
+    save("geometry", cam2world=cam2world, intrinsics=intrinsics, x_pix=x_pix, z=z, dist=dist, g_depth=gd,
+         ref_ros=ros, ref_rds=rds, ref_pts=pts, ref_viewdirs=viewdirs, ref_depth=depth, ref_d_world=world.grad)
+
+
 def main():
     ref = ref_shim.load()
     torch.set_num_threads(1)   # one thread: reductions are order-stable across machines
@@ -243,6 +266,7 @@ def main():
     case_fine(ref)
     case_volume_renderer(ref)
     case_adaptive_renderer(ref)
+    case_geometry(ref)
 
 
 if __name__ == "__main__":

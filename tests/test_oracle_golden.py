@@ -91,3 +91,18 @@ def test_volume_renderer_golden(name):
     assert_close(rc, g["ref_rgb_coarse"], what="rgb_coarse", rtol=1e-5, atol=1e-6)
     assert_close(rf, g["ref_rgb_fine"], what="rgb_fine", rtol=1e-4, atol=1e-5)
     assert_close(d, g["ref_depth"], what="depth", rtol=1e-4, atol=1e-5)
+
+
+def test_geometry_golden():
+    """utils.get_world_rays / depth_from_world and the sample-point generation."""
+    g = load_golden("geometry")
+    ros, rds = O.world_rays(g["x_pix"], g["intrinsics"], g["cam2world"])
+    assert_close(ros, g["ref_ros"], what="ros", **TIGHT)
+    assert_close(rds, g["ref_rds"], what="rds", **TIGHT)
+    pts = g["ref_ros"].unsqueeze(-2) + g["ref_rds"].unsqueeze(-2) * g["z"].unsqueeze(-1)
+    assert torch.equal(pts, g["ref_pts"])
+    world = (g["ref_ros"] + g["ref_rds"] * g["dist"].unsqueeze(-1)).requires_grad_(True)
+    depth = O.camera_depth(world, g["cam2world"])
+    assert_close(depth, g["ref_depth"], what="depth", **TIGHT)
+    depth.backward(g["g_depth"])
+    assert_close(world.grad, g["ref_d_world"], what="d_world", **TIGHT)
