@@ -184,6 +184,27 @@ int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t R, int K
                                    peer_gathered, n_peers, row0);
 }
 
+int avr_gather_push_rows(void* const* peer_gathered, int n_peers, int self, int64_t row0, int64_t rows,
+                         avr_stream_t stream) {
+  if (!peer_gathered || n_peers < 1 || self < 0 || self >= n_peers || row0 < 0 || rows < 0) return AVR_ERR_BAD_ARG;
+  if (rows == 0) return AVR_OK;
+  for (int p = 0; p < n_peers; ++p)
+    if (!peer_gathered[p]) return AVR_ERR_BAD_ARG;
+  const size_t off = (size_t)row0 * 16, bytes = (size_t)rows * 16;
+  const char* src = static_cast<const char*>(peer_gathered[self]) + off;
+  for (int d = 1; d < n_peers; ++d) {
+    const int p = (self + d) % n_peers;  // staggered: at any moment every rank targets a different peer
+    cudaError_t e = cudaMemcpyAsync(static_cast<char*>(peer_gathered[p]) + off, src, bytes, cudaMemcpyDefault,
+                                    as_stream(stream));
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e);
+      (void)cudaGetLastError();
+      return AVR_ERR_RUNTIME;
+    }
+  }
+  return AVR_OK;
+}
+
 int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, const float* g_depth,
                       const float* g_w, int64_t R, int K, int white_back, float infinity, float* d_rgbs,
                       float* d_z, avr_stream_t stream) {

@@ -204,9 +204,11 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="override rays per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
-                    help="N>1: all-gather of rgb+depth fused into the forward kernel (peer stores into "
-                         "symmetric memory; falls back to nccl if unavailable) or a NCCL all_gather overlapped with backward")
+    ap.add_argument("--gather", default="ce", choices=["ce", "fused", "nccl"],
+                    help="N>1, the all-gather of rgb+depth: 'ce' = the forward kernel packs the local rows into a "
+                         "symmetric-memory buffer and the copy engines push them to the peers over NVLink while the "
+                         "backward kernel runs; 'fused' = 16-byte peer stores from the forward kernel's epilogue; "
+                         "'nccl' = all_gather_into_tensor between forward and backward (both fall back to nccl)")
     args = ap.parse_args()
     rays, k, desc = WORKLOADS[args.workload]
     if args.rays:
@@ -261,7 +263,7 @@ def main():
     launches_per_step = 2 * (1 + (1 if (span and main_rays.value < rays) else 0)) if span else 2
 
     fused = None
-    if dist is not None and args.gather == "fused":
+    if dist is not None and args.gather in ("fused", "ce"):
         fused = avr_dist.FusedGather(rays, dev)
         ok = torch.tensor([1 if fused.available else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -269,13 +271,22 @@ def main():
             if rank == 0:
                 print(f"[bench] fused gather unavailable ({fused.error}); using NCCL", file=sys.stderr)
             fused = None
-    gather_mode = "none" if dist is None else ("fused epilogue (peer stores over NVLink into symmetric memory) + barrier"
-                                               if fused is not None else "NCCL all_gather_into_tensor between forward and backward")
+    ce = fused is not None and args.gather == "ce"
+    gather_mode = "none" if dist is None else (
+        "NCCL all_gather_into_tensor between forward and backward" if fused is None else
+        "forward kernel packs local rows; copy-engine pushes over NVLink + barrier on a side stream, overlapped with backward"
+        if ce else "fused epilogue (peer stores over NVLink into symmetric memory) + barrier")
 
     def fwd_fused():
-        rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
-                                          depth.data_ptr(), fused._ptr_array, fused.world, fused.rank * rays, sp)
+        if ce:
+            rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
+                                              depth.data_ptr(), fused.local_ptr_array, 1, fused.rank * rays, sp)
+        else:
+            rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
+                                              depth.data_ptr(), fused._ptr_array, fused.world, fused.rank * rays, sp)
         assert rc == 0, (rc, lib.avr_last_cuda_error())
+        if ce:
+            fused.push_async()
 
     def fwd():
         if fused is not None:
@@ -297,7 +308,7 @@ def main():
             avr_dist.all_gather_outputs(rgb, depth)
         bwd()
         if fused is not None:
-            fused.finish()
+            fused.wait() if ce else fused.finish()
 
     for _ in range(args.warmup):
         step()
@@ -331,7 +342,7 @@ def main():
             bwd()
             ev[i][2].record(stream)
             if fused is not None:
-                fused.finish()
+                fused.wait() if ce else fused.finish()
         t_end.record(stream)
         torch.cuda.synchronize(dev)
     if dist is not None:

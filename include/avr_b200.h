@@ -143,6 +143,17 @@ AVR_API int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t 
                                      void* const* peer_gathered, int n_peers, int64_t row0,
                                      avr_stream_t stream);
 
+/* All-gather by the copy engines (multi-GPU): copy rows [row0, row0 + rows) of this rank's
+ * gathered buffer `peer_gathered[self]` into the same rows of every other rank's buffer
+ * (one cudaMemcpyAsync per peer over NVLink: no SM is involved, so the transfer overlaps a
+ * persistent kernel — the backward pass — running on another stream).  `peer_gathered` is a
+ * HOST array of `n_peers` DEVICE pointers to [world*R, 4] fp32 buffers, peer-mapped (e.g. the
+ * buffer_ptrs of a torch symmetric-memory allocation).  Typical use: avr_composite_fwd_gather
+ * with only the local buffer as target, then this call on a side stream, then a cross-rank
+ * barrier. */
+AVR_API int avr_gather_push_rows(void* const* peer_gathered, int n_peers, int self, int64_t row0, int64_t rows,
+                                 avr_stream_t stream);
+
 /* Gradient of the above; transmittance is recomputed, nothing is saved by forward.
  *   g_rgb [R,3] (may be NULL = zeros), g_depth [R] (may be NULL), g_w [R,K] (may be NULL)
  *   d_rgbs [R,K,4] (required), d_z [R,K] (may be NULL: VolumeRenderer's z carries no grad) */

@@ -54,6 +54,17 @@ def _worker(rank, world, port, q):
             torch.cuda.synchronize()
             ok_fused = bool(torch.equal(rgb_f, rgb) and torch.equal(depth_f, depth)
                             and torch.equal(g_rgb, rgb_all) and torch.equal(g_depth, depth_all))
+            # (3) copy-engine all-gather: local pack in the kernel, NVLink DMA pushes on a side stream
+            fg.gathered.zero_()
+            fg.handle.barrier()
+            out = fg.composite_fwd(xs, zs, True, 1.8, want_w=False, local_only=True)
+            assert out is not None
+            fg.push_async()
+            busy = ops.composite(x.to(dev), z.to(dev), True, 1.8, want_w=False)   # work the pushes overlap with
+            c_rgb, c_depth = fg.wait()
+            torch.cuda.synchronize()
+            ok_fused = ok_fused and bool(torch.equal(out[0], rgb) and torch.equal(c_rgb, rgb_all)
+                                         and torch.equal(c_depth, depth_all) and torch.equal(busy[0], full_rgb))
         q.put((rank, ok_nccl, ok_fused, note))
     finally:
         dist.destroy_process_group()
