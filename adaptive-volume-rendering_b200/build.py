@@ -55,12 +55,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB_PATH
     nvcc = find_nvcc()
+    extra = os.environ.get("AVR_NVCC_EXTRA", "").split()   # tuning experiments: -DAVR_PK_L=9 ...
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

@@ -29,10 +29,20 @@
 
 namespace avr {
 
-constexpr int kPkL = 13;
+// tuning knobs (compile-time; -DAVR_PK_L=.. -DAVR_PK_WARPS=.. -DAVR_PK_STAGES=.. for experiments)
+#ifndef AVR_PK_L
+#define AVR_PK_L 13
+#endif
+#ifndef AVR_PK_WARPS
+#define AVR_PK_WARPS 2
+#endif
+#ifndef AVR_PK_STAGES
+#define AVR_PK_STAGES 3
+#endif
+constexpr int kPkL = AVR_PK_L;   // samples per lane (odd: conflict-free shared-memory runs)
 constexpr int kPkC = 32 * kPkL;  // samples per tile
-constexpr int kPkStages = 3;
-constexpr int kPkWarps = 2;
+constexpr int kPkStages = AVR_PK_STAGES;
+constexpr int kPkWarps = AVR_PK_WARPS;
 constexpr int kPkRgbsBytes = kPkC * 16;
 constexpr int kPkZFloats = kPkC + 8;  // + phase shift (<= 3) + one z past the tile + slack
 constexpr int kPkStageBytes = kPkRgbsBytes + kPkZFloats * 4 + 32 * 4;  // rgbs | z | ray ends

@@ -126,11 +126,9 @@ class FusedGather:
             self.error = f"{type(exc).__name__}: {exc}"
 
     def composite_fwd(self, rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = True, infinity: float = 1.8,
-                      want_w: bool = True, local_only: bool = False):
+                      want_w: bool = True):
         """Forward compositing of this rank's rays + fused gather.  Returns (rgb, depth, w) or
-        None if the shape is not eligible for the fused kernel (caller falls back).
-        ``local_only``: the kernel packs its rows into the LOCAL gathered buffer only; follow
-        with ``push_async()`` / ``wait()`` (copy-engine all-gather overlapped with backward)."""
+        None if the shape is not eligible for the fused kernel (caller falls back)."""
         from . import _lib
         from .ops import _f32c, _stream
 
@@ -147,8 +145,7 @@ class FusedGather:
             rc = _lib.load().avr_composite_fwd_gather(
                 rgbs.data_ptr(), z.data_ptr(), r, k, int(bool(white_back)), float(infinity),
                 None if w is None else w.data_ptr(), rgb.data_ptr(), depth.data_ptr(),
-                self.local_ptr_array if local_only else self._ptr_array, 1 if local_only else self.world,
-                self.rank * self.rays_local, _stream(z))
+                self._ptr_array, self.world, self.rank * self.rays_local, _stream(z))
         if rc == -4:   # AVR_ERR_UNSUPPORTED
             return None
         _lib.check(rc, "avr_composite_fwd_gather")
@@ -159,40 +156,91 @@ class FusedGather:
         self.handle.barrier()
         return self.gathered[:, :3], self.gathered[:, 3]
 
-    # ---- copy-engine variant: the kernel fills only the LOCAL rows; the rows then travel to the
-    # peers by cudaMemcpyAsync on a side stream (NVLink DMA, no SMs), overlapping whatever the
-    # caller launches next on its own stream — the backward kernel.  Measured on 2 B200s
-    # (2^20 rays x 96): 16-byte peer stores from the kernel epilogue 1.23 ms/step, NCCL
-    # all-gather between forward and backward 1.01 ms/step; see profiles/ for this variant.
-    @property
-    def local_ptr_array(self):
+
+class PipelinedGather:
+    """Copy-engine all-gather of the per-ray outputs, double-buffered so it never sits on the
+    critical path.
+
+    Step i: the forward kernel packs this rank's (r,g,b,depth) rows into slot ``i % slots`` of a
+    symmetric-memory buffer (local 16-byte stores); a side stream then pushes those rows to
+    every peer with ``cudaMemcpyAsync`` over NVLink (copy engines, no SMs) and runs the
+    cross-rank barrier, while the caller's stream goes on with backward and with the NEXT step.
+    ``wait(slot)`` orders the caller's stream after that slot's pushes + barrier.
+
+    Why: on 8 B200s the pushes take 0.25 ms alone but ~1 ms while the persistent backward
+    kernel saturates HBM, and a barrier inside every step pays the slowest rank's jitter; with
+    one step of slack both disappear behind compute (tools/diag_gather.py, profiles/).
+
+    Contract for consumers: read slot s (after ``wait(s)``) BEFORE launching the forward of
+    the following step on the same stream — a peer's next push into that slot is ordered after
+    this rank's following push, hence after the read.
+    """
+
+    def __init__(self, rays_local: int, device, group: Optional[dist.ProcessGroup] = None, slots: int = 2):
         import ctypes
 
-        if not hasattr(self, "_local_ptr"):
-            self._local_ptr = (ctypes.c_void_p * 1)(int(self.handle.buffer_ptrs[self.rank]))
-        return self._local_ptr
+        self.rays_local, self.slots = rays_local, slots
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.available, self.error = False, None
+        self.slot = 0
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
 
-    def push_async(self):
-        """After the forward kernel (launched with ``local_ptr_array`` as its only target) has been
-        enqueued on the current stream: enqueue the row pushes and the cross-rank barrier on the
-        side stream.  Returns immediately; call ``wait()`` before reading ``gathered`` or
-        launching the next forward."""
+            rows = self.world * rays_local
+            self.buffer = symm_mem.empty((slots * rows, 4), dtype=torch.float32, device=device)
+            self.handle = symm_mem.rendezvous(self.buffer, self.group)
+            base = [int(p) for p in self.handle.buffer_ptrs]
+            self._peer_arrays = [(ctypes.c_void_p * self.world)(*[b + s * rows * 16 for b in base]) for s in range(slots)]
+            self._local_arrays = [(ctypes.c_void_p * 1)(base[self.rank] + s * rows * 16) for s in range(slots)]
+            self._side = torch.cuda.Stream(device=device)
+            self._fwd_done = torch.cuda.Event()
+            self._slot_done = [torch.cuda.Event() for _ in range(slots)]
+            self._pending = [False] * slots
+            self.handle.barrier()
+            self.available = True
+        except Exception as exc:  # pragma: no cover - depends on the box
+            self.error = f"{type(exc).__name__}: {exc}"
+
+    def gathered(self, slot: int):
+        rows = self.world * self.rays_local
+        g = self.buffer[slot * rows:(slot + 1) * rows]
+        return g[:, :3], g[:, 3]
+
+    def forward_target(self):
+        """(ctypes pointer array, n_peers, row0) for avr_composite_fwd_gather into the current slot;
+        orders the caller's stream after the slot's previous pushes."""
+        self.wait(self.slot)
+        return self._local_arrays[self.slot], 1, self.rank * self.rays_local
+
+    def push_async(self) -> int:
+        """Call right after the forward kernel has been enqueued on the current stream.  Returns
+        the slot that is now travelling."""
         from . import _lib
 
-        cur = torch.cuda.current_stream(self.gathered.device)
-        if not hasattr(self, "_side"):
-            self._side = torch.cuda.Stream(device=self.gathered.device)
-            self._ev = torch.cuda.Event()
-        self._ev.record(cur)
-        self._side.wait_event(self._ev)
-        with torch.cuda.device(self.gathered.device):
-            _lib.check(_lib.load().avr_gather_push_rows(self._ptr_array, self.world, self.rank,
+        s = self.slot
+        dev = self.buffer.device
+        self._fwd_done.record(torch.cuda.current_stream(dev))
+        self._side.wait_event(self._fwd_done)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().avr_gather_push_rows(self._peer_arrays[s], self.world, self.rank,
                                                         self.rank * self.rays_local, self.rays_local,
                                                         self._side.cuda_stream), "avr_gather_push_rows")
         with torch.cuda.stream(self._side):
             self.handle.barrier()
+        self._slot_done[s].record(self._side)
+        self._pending[s] = True
+        self.slot = (s + 1) % self.slots
+        return s
 
-    def wait(self):
-        """Make the current stream wait for the pushes and the barrier; returns the gathered views."""
-        torch.cuda.current_stream(self.gathered.device).wait_stream(self._side)
-        return self.gathered[:, :3], self.gathered[:, 3]
+    def wait(self, slot: int):
+        """Order the current stream after the pushes + barrier last issued for `slot`."""
+        if self._pending[slot]:
+            torch.cuda.current_stream(self.buffer.device).wait_event(self._slot_done[slot])
+            self._pending[slot] = False
+        return self.gathered(slot)
+
+    def wait_all(self):
+        for s in range(self.slots):
+            self.wait(s)

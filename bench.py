@@ -204,11 +204,12 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="override rays per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="ce", choices=["ce", "fused", "nccl"],
+    ap.add_argument("--gather", default="ce", choices=["ce", "fused", "nccl", "none"],
                     help="N>1, the all-gather of rgb+depth: 'ce' = the forward kernel packs the local rows into a "
                          "symmetric-memory buffer and the copy engines push them to the peers over NVLink while the "
                          "backward kernel runs; 'fused' = 16-byte peer stores from the forward kernel's epilogue; "
-                         "'nccl' = all_gather_into_tensor between forward and backward (both fall back to nccl)")
+                         "'nccl' = all_gather_into_tensor between forward and backward (both fall back to nccl); 'none' = no exchange "
+                         "(diagnostic: the compute-only step under the same launch)")
     args = ap.parse_args()
     rays, k, desc = WORKLOADS[args.workload]
     if args.rays:
@@ -264,7 +265,7 @@ def main():
 
     fused = None
     if dist is not None and args.gather in ("fused", "ce"):
-        fused = avr_dist.FusedGather(rays, dev)
+        fused = avr_dist.PipelinedGather(rays, dev) if args.gather == "ce" else avr_dist.FusedGather(rays, dev)
         ok = torch.tensor([1 if fused.available else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if not int(ok.item()):
@@ -272,15 +273,17 @@ def main():
                 print(f"[bench] fused gather unavailable ({fused.error}); using NCCL", file=sys.stderr)
             fused = None
     ce = fused is not None and args.gather == "ce"
-    gather_mode = "none" if dist is None else (
+    gather_mode = "none" if (dist is None or args.gather == "none") else (
         "NCCL all_gather_into_tensor between forward and backward" if fused is None else
-        "forward kernel packs local rows; copy-engine pushes over NVLink + barrier on a side stream, overlapped with backward"
+        "forward kernel packs local rows into a double-buffered symmetric-memory slot; copy-engine pushes over NVLink + "
+        "cross-rank barrier on a side stream, overlapped with backward and the next step (all waited inside the timed region)"
         if ce else "fused epilogue (peer stores over NVLink into symmetric memory) + barrier")
 
     def fwd_fused():
         if ce:
+            target, n_t, row0 = fused.forward_target()
             rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
-                                              depth.data_ptr(), fused.local_ptr_array, 1, fused.rank * rays, sp)
+                                              depth.data_ptr(), target, n_t, row0, sp)
         else:
             rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
                                               depth.data_ptr(), fused._ptr_array, fused.world, fused.rank * rays, sp)
@@ -302,16 +305,18 @@ def main():
 
     def step():
         fwd()
-        if dist is not None and fused is None:  # the path's only exchange: per-ray outputs, 16 B/ray
+        if dist is not None and fused is None and args.gather != "none":  # the path's only exchange: per-ray outputs, 16 B/ray
             # in-stream: an async all-gather cannot co-schedule with the persistent backward
             # kernel (it holds every SM) and measured 2.6x slower than this
             avr_dist.all_gather_outputs(rgb, depth)
         bwd()
-        if fused is not None:
-            fused.wait() if ce else fused.finish()
+        if fused is not None and not ce:
+            fused.finish()
 
     for _ in range(args.warmup):
         step()
+    if ce:
+        fused.wait_all()
     torch.cuda.synchronize(dev)
 
     # correctness spot-check against the oracle on a few rays (outside the timed region)
@@ -335,14 +340,16 @@ def main():
             ev[i][0].record(stream)
             fwd()
             ev[i][1].record(stream)
-            if dist is not None and fused is None:
+            if dist is not None and fused is None and args.gather != "none":
                 avr_dist.all_gather_outputs(rgb, depth)
                 ev[i][1] = torch.cuda.Event(enable_timing=True)
                 ev[i][1].record(stream)
             bwd()
             ev[i][2].record(stream)
-            if fused is not None:
-                fused.wait() if ce else fused.finish()
+            if fused is not None and not ce:
+                fused.finish()
+        if ce:
+            fused.wait_all()     # every slot's pushes + barrier have completed before the clock stops
         t_end.record(stream)
         torch.cuda.synchronize(dev)
     if dist is not None:

@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "oracle")]
     import torch.distributed as dist
-    from avr_b200 import dist as avr_dist, ops
+    from avr_b200 import _lib, dist as avr_dist, ops
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -54,17 +54,33 @@ def _worker(rank, world, port, q):
             torch.cuda.synchronize()
             ok_fused = bool(torch.equal(rgb_f, rgb) and torch.equal(depth_f, depth)
                             and torch.equal(g_rgb, rgb_all) and torch.equal(g_depth, depth_all))
-            # (3) copy-engine all-gather: local pack in the kernel, NVLink DMA pushes on a side stream
-            fg.gathered.zero_()
-            fg.handle.barrier()
-            out = fg.composite_fwd(xs, zs, True, 1.8, want_w=False, local_only=True)
-            assert out is not None
-            fg.push_async()
-            busy = ops.composite(x.to(dev), z.to(dev), True, 1.8, want_w=False)   # work the pushes overlap with
-            c_rgb, c_depth = fg.wait()
-            torch.cuda.synchronize()
-            ok_fused = ok_fused and bool(torch.equal(out[0], rgb) and torch.equal(c_rgb, rgb_all)
-                                         and torch.equal(c_depth, depth_all) and torch.equal(busy[0], full_rgb))
+            # (3) copy-engine all-gather, double-buffered: three steps through two slots
+            pg = avr_dist.PipelinedGather(hi - lo, dev)
+            assert pg.available, pg.error
+            lib = _lib.load()
+            r_loc = hi - lo
+            for step in range(3):
+                scale = float(step + 1)
+                xs2 = xs.clone()
+                xs2[..., :3] *= 1.0 / scale                      # a different image every step
+                target, n_t, row0 = pg.forward_target()
+                o_rgb = torch.empty(r_loc, 3, device=dev)
+                o_depth = torch.empty(r_loc, device=dev)
+                rc = lib.avr_composite_fwd_gather(xs2.data_ptr(), zs.data_ptr(), r_loc, k, 1, 1.8, None, o_rgb.data_ptr(),
+                                                  o_depth.data_ptr(), target, n_t, row0,
+                                                  torch.cuda.current_stream(dev).cuda_stream)
+                assert rc == 0
+                slot = pg.push_async()
+                busy = ops.composite(x.to(dev), z.to(dev), True, 1.8, want_w=False)   # work the pushes overlap with
+                c_rgb, c_depth = pg.wait(slot)
+                x2 = x.clone()
+                x2[..., :3] *= 1.0 / scale
+                want_rgb, want_depth, _ = ops.composite(x2.to(dev), z.to(dev), True, 1.8, want_w=False)
+                torch.cuda.synchronize()
+                ok_fused = ok_fused and bool(torch.allclose(c_rgb, want_rgb, rtol=2e-6, atol=2e-7)
+                                             and torch.allclose(c_depth, want_depth, rtol=2e-6, atol=2e-7)
+                                             and torch.equal(c_rgb[lo:hi], o_rgb) and torch.equal(busy[0], full_rgb))
+                dist.barrier()                                   # consumers are done before the slot is reused
         q.put((rank, ok_nccl, ok_fused, note))
     finally:
         dist.destroy_process_group()
