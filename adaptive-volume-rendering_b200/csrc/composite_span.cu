@@ -258,9 +258,17 @@ composite_fwd_span_kernel(const SpanArgs a) {
   const int n_s_tail = a.tail_rays * K;
   const Run run_full = make_run<L>(lane, K, n_s);
 
-  const int64_t first = (int64_t)blockIdx.x * warps + warp;
-  const int64_t stride = (int64_t)gridDim.x * warps;
-  const int64_t n_my = first < a.n_tiles ? (a.n_tiles - first + stride - 1) / stride : 0;
+  // tiles are dealt round-robin over all warps (neighbouring warps stream neighbouring
+  // addresses); with the fused all-gather each warp takes a contiguous block of tiles instead,
+  // so that the rays it finishes are consecutive and leave for the peers in 512-byte stores
+  const bool gather = a.n_peers > 0;
+  const int64_t gw = (int64_t)blockIdx.x * warps + warp, n_warps = (int64_t)gridDim.x * warps;
+  const int64_t per_warp = (a.n_tiles + n_warps - 1) / n_warps;
+  const int64_t first = gather ? gw * per_warp : gw;
+  const int64_t stride = gather ? 1 : n_warps;
+  const int64_t n_my = gather ? (first < a.n_tiles ? (a.n_tiles - first < per_warp ? a.n_tiles - first : per_warp) : 0)
+                              : (first < a.n_tiles ? (a.n_tiles - first + stride - 1) / stride : 0);
+  int64_t flushed = first * a.rays_per_tile;  // gather: rays below this are already at the peers
   auto samples_of = [&](int64_t tile) { return tile == a.n_tiles - 1 ? n_s_tail : n_s; };
 
   if (lane == 0) {
@@ -302,6 +310,14 @@ composite_fwd_span_kernel(const SpanArgs a) {
       }
     } else {
       __syncwarp();  // stage may be refilled two iterations from now
+    }
+    if (gather) {
+      const int64_t done = ray_base + n_cur / K;
+      const int64_t upto = (i + 1 == n_my) ? done : flushed + ((done - flushed) & ~(int64_t)31);  // whole 512-byte rows
+      if (upto > flushed) {
+        flush_rays_to_peers(a, flushed, upto, lane);
+        flushed = upto;
+      }
     }
   }
   if (kWriteW && lane == 0) bulk_wait_all<0>();

@@ -204,10 +204,11 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="override rays per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="ce", choices=["ce", "fused", "nccl", "none"],
-                    help="N>1, the all-gather of rgb+depth: 'ce' = the forward kernel packs the local rows into a "
-                         "symmetric-memory buffer and the copy engines push them to the peers over NVLink while the "
-                         "backward kernel runs; 'fused' = 16-byte peer stores from the forward kernel's epilogue; "
+    ap.add_argument("--gather", default="fused", choices=["ce", "fused", "nccl", "none"],
+                    help="N>1, the all-gather of rgb+depth: 'fused' = the forward kernel forwards every 32 finished rays "
+                         "to each peer's symmetric-memory buffer as one coalesced 512-byte store over NVLink, then a "
+                         "cross-rank barrier; 'ce' = the kernel packs local rows and the copy engines push them on a side "
+                         "stream (double-buffered; starved by the HBM-saturating kernels, kept for comparison); "
                          "'nccl' = all_gather_into_tensor between forward and backward (both fall back to nccl); 'none' = no exchange "
                          "(diagnostic: the compute-only step under the same launch)")
     args = ap.parse_args()
@@ -277,7 +278,7 @@ def main():
         "NCCL all_gather_into_tensor between forward and backward" if fused is None else
         "forward kernel packs local rows into a double-buffered symmetric-memory slot; copy-engine pushes over NVLink + "
         "cross-rank barrier on a side stream, overlapped with backward and the next step (all waited inside the timed region)"
-        if ce else "fused epilogue (peer stores over NVLink into symmetric memory) + barrier")
+        if ce else "fused into the forward kernel (coalesced 512-byte peer stores over NVLink into symmetric memory) + barrier")
 
     def fwd_fused():
         if ce:
