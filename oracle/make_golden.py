@@ -258,6 +258,71 @@ def case_geometry(ref):
          ref_ros=ros, ref_rds=rds, ref_pts=pts, ref_viewdirs=viewdirs, ref_depth=depth, ref_d_world=world.grad)
 
 
+class _Recorder(torch.nn.Module):
+    """Wraps the reference radiance field: records what the renderer asks and what it gets."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net, self.calls = net, []
+
+    def forward(self, xyz, viewdirs=None, coarse=True, **kw):
+        out = self.net(xyz, coarse=coarse, viewdirs=viewdirs, **kw)
+        out.retain_grad()
+        self.calls.append((xyz.detach().clone(), viewdirs.detach().clone(), out))
+        return out
+
+
+def case_pixelnerf_replay(ref):
+    """BASELINE.json config 1: the reference VolumeRenderer around the reference's own
+    NewPixelNeRFNet (conf/default.conf model{} values, random init because there is no network
+    for the ImageNet weights), single source view, 128x128 pixel grid subsampled to 512 rays,
+    64 coarse + 32 fine (16 importance + 16 depth) samples.  The radiance field cannot travel to
+    the GPU box (26 M parameters, reference code), so the fixture records every exchange at the
+    renderer <-> field boundary: the points/viewdirs the renderer sent, the (SB, R*K, 4) buffers
+    the field returned, and the gradient that came back into them.  tests/test_gpu_renderers.py
+    replays the field side."""
+    import models
+    from ref_shim import Conf
+
+    torch.manual_seed(0)
+    conf = Conf(use_encoder=True, use_global_encoder=False, use_xyz=True, canon_xyz=False, use_code=True,
+                code=dict(num_freqs=6, freq_factor=1.5, include_input=True), use_viewdirs=True,
+                use_code_viewdirs=False, mlp_coarse=dict(type="resnet", n_blocks=3, d_hidden=512),
+                mlp_fine=dict(type="resnet", n_blocks=3, d_hidden=512),
+                encoder=dict(backbone="resnet34", pretrained=False, num_layers=4))
+    net = models.make_new_model(conf)
+    sl = 128
+    cam2world, intrinsics, _ = camera_setup(1, 1, seed=0)
+    x_all = ref.get_opencv_pixel_coordinates(sl, sl).reshape(1, sl * sl, 2)          # utils.py:339-356
+    pick = torch.arange(0, sl * sl, 32) + (torch.arange(0, sl * sl, 32) // sl) % 32   # 512 rays over the frame
+    x_pix = x_all[:, pick].contiguous()
+    r = x_pix.shape[1]
+    c2w = cam2world[:, :1].expand(1, r, 4, 4).contiguous()                            # train.py:150
+    src = torch.rand(1, 1, 3, sl, sl) * 2 - 1
+    focal = torch.tensor(131.25)
+    with torch.no_grad():
+        net.encode(src, cam2world[:, :1], focal)                                      # train.py:68
+    ren = ref.VolumeRenderer.from_conf(Conf(near=0.8, far=1.8, n_coarse=64, n_fine=32, n_fine_depth=16,
+                                            depth_std=0.01, white_back=True))
+    rec = _Recorder(net)
+    torch.manual_seed(77)
+    rc, rf, depth, _ = ren(c2w, intrinsics, x_pix, rec)
+    torch.manual_seed(77)   # replay the draws the reference consumed (renderers.py:14, :41, :45, :63)
+    u_c = torch.rand_like(torch.empty(1, r, 64))
+    u_cdf = torch.rand(1, r, 16)
+    u_bin = torch.rand_like(u_cdf)
+    normals = torch.randn_like(torch.empty(1, r, 16))
+    gen = torch.Generator().manual_seed(5)
+    g_rc, g_rf, g_d = torch.randn(1, r, 3, generator=gen), torch.randn(1, r, 3, generator=gen), torch.randn(1, r, generator=gen)
+    torch.autograd.backward([rc, rf, depth], [g_rc, g_rf, g_d])
+    (xyz_c, vd_c, out_c), (xyz_f, vd_f, out_f) = rec.calls
+    save("pixelnerf_replay", cam2world=c2w, intrinsics=intrinsics, x_pix=x_pix,
+         u_coarse=u_c, u_cdf=u_cdf, u_bin=u_bin, normals=normals, g_rgb_coarse=g_rc, g_rgb_fine=g_rf, g_depth=g_d,
+         ref_xyz_coarse=xyz_c, ref_viewdirs_coarse=vd_c, field_out_coarse=out_c, ref_grad_out_coarse=out_c.grad,
+         ref_xyz_fine=xyz_f, field_out_fine=out_f, ref_grad_out_fine=out_f.grad,
+         ref_rgb_coarse=rc, ref_rgb_fine=rf, ref_depth=depth)
+
+
 def main():
     ref = ref_shim.load()
     torch.set_num_threads(1)   # one thread: reductions are order-stable across machines
@@ -267,6 +332,7 @@ def main():
     case_volume_renderer(ref)
     case_adaptive_renderer(ref)
     case_geometry(ref)
+    case_pixelnerf_replay(ref)
 
 
 if __name__ == "__main__":

@@ -85,3 +85,54 @@ def test_adaptive_renderer_golden(dev):
         ref = g[f"ref_phi_grad_{i}"]
         scale = max(ref.abs().max().item(), 1e-6)
         assert_close(p.grad.cpu() / scale, ref / scale, rtol=1e-3, atol=5e-3, what=f"phi grad {i}")
+
+
+class _ReplayField(torch.nn.Module):
+    """The radiance-field side of tests/golden/pixelnerf_replay.npz: hands back what the
+    reference's NewPixelNeRFNet returned to the reference renderer, and keeps what it was asked."""
+
+    def __init__(self, g, dev):
+        super().__init__()
+        self.g, self.dev, self.asked, self.outs = g, dev, {}, {}
+
+    def forward(self, xyz, viewdirs=None, coarse=True):
+        key = "coarse" if coarse else "fine"
+        self.asked[key] = (xyz.detach().cpu(), viewdirs.detach().cpu())
+        out = self.g[f"field_out_{key}"].to(self.dev).clone().requires_grad_(True)
+        self.outs[key] = out
+        assert xyz.is_contiguous() and viewdirs.is_contiguous() and xyz.shape == viewdirs.shape == out.shape[:-1] + (3,)
+        return out
+
+
+def test_volume_renderer_pixelnerf_replay(dev):
+    """BASELINE.json config 1 (conf/default.conf renderer around the reference's PixelNeRF, 64 + 32
+    samples): every tensor that crossed the renderer <-> field boundary in the reference run."""
+    import avr_b200
+    g = load_golden("pixelnerf_replay")
+    field = _ReplayField(g, dev)
+    ren = avr_b200.VolumeRenderer(0.8, 1.8, 64, 32, 16, 0.01, white_back=True)
+    draws = tuple(g[k].to(dev) for k in ("u_coarse", "u_cdf", "u_bin", "normals"))
+    rc, rf, d0, d1 = ren(g["cam2world"].to(dev), g["intrinsics"].to(dev), g["x_pix"].to(dev), field, draws=draws)
+    r = g["x_pix"].shape[1]
+    # what the renderer asked the field: the coarse sample points and view directions
+    xyz_c, vd_c = field.asked["coarse"]
+    assert_close(xyz_c, g["ref_xyz_coarse"], rtol=1e-5, atol=2e-6, what="coarse sample points")
+    assert_close(vd_c, g["ref_viewdirs_coarse"], rtol=1e-5, atol=1e-6, what="coarse view directions")
+    assert_close(rc, g["ref_rgb_coarse"], rtol=1e-5, atol=2e-6, what="rgb_coarse")
+    # the fine points sit behind the resampling step: a CDF bin may flip on the last ulp of a weight
+    xyz_f = field.asked["fine"][0].reshape(r, 96, 3)
+    ref_f = g["ref_xyz_fine"].reshape(r, 96, 3)
+    same_ray = ((xyz_f - ref_f).abs() <= 3e-6 + 1e-5 * ref_f.abs()).all(-1).all(-1)
+    assert same_ray.float().mean() >= 0.97, f"only {int(same_ray.sum())}/{r} rays asked the field the reference's fine points"
+    assert d0 is d1 and d0.shape == g["ref_depth"].shape
+    assert_close(rf[0][same_ray], g["ref_rgb_fine"][0][same_ray], rtol=1e-5, atol=2e-6, what="rgb_fine")
+    assert_close(d0[0][same_ray], g["ref_depth"][0][same_ray], rtol=1e-5, atol=2e-6, what="depth")
+    # gradients that come back INTO the field's outputs
+    torch.autograd.backward([rc, rf, d0], [g["g_rgb_coarse"].to(dev), g["g_rgb_fine"].to(dev), g["g_depth"].to(dev)])
+    for key, k, rows in (("coarse", 64, slice(None)), ("fine", 96, same_ray)):
+        got = field.outs[key].grad.cpu().reshape(r, k, 4)[rows]
+        ref = g[f"ref_grad_out_{key}"].reshape(r, k, 4)[rows]
+        assert_close(got[..., :3], ref[..., :3], rtol=1e-5, atol=2e-6, what=f"{key} d_rgb")
+        assert_close(got[..., :-1, 3], ref[..., :-1, 3], rtol=1e-5, atol=2e-6, what=f"{key} d_sigma[:-1]")
+        # last sample: 1e10 interval (renderers.py:78-81), compared after dividing it out (SURVEY 8d)
+        assert_close(got[..., -1, 3] / 1e10, ref[..., -1, 3] / 1e10, rtol=1e-5, atol=2e-6, what=f"{key} d_sigma[-1]/1e10")

@@ -106,3 +106,24 @@ def test_geometry_golden():
     assert_close(depth, g["ref_depth"], what="depth", **TIGHT)
     depth.backward(g["g_depth"])
     assert_close(world.grad, g["ref_d_world"], what="d_world", **TIGHT)
+
+
+def test_pixelnerf_replay_golden():
+    """BASELINE.json config 1: the oracle's renderer against the reference VolumeRenderer run
+    around the reference's own PixelNeRF (the field side is replayed from the fixture)."""
+    g = load_golden("pixelnerf_replay")
+    asked = {}
+
+    def field(xyz, viewdirs=None, coarse=True):
+        key = "coarse" if coarse else "fine"
+        asked[key] = xyz
+        return g[f"field_out_{key}"]
+
+    draws = tuple(g[k] for k in ("u_coarse", "u_cdf", "u_bin", "normals"))
+    rc, rf, depth, _ = O.render_volume(g["cam2world"], g["intrinsics"], g["x_pix"], field, 0.8, 1.8, 64, 32, 16, 0.01,
+                                       True, draws)
+    assert_close(asked["coarse"], g["ref_xyz_coarse"], what="coarse points", **TIGHT)
+    assert_close(asked["fine"], g["ref_xyz_fine"], what="fine points", **TIGHT)
+    assert_close(rc, g["ref_rgb_coarse"], what="rgb_coarse", **TIGHT)
+    assert_close(rf, g["ref_rgb_fine"], what="rgb_fine", **TIGHT)
+    assert_close(depth, g["ref_depth"], what="depth", rtol=2e-6, atol=5e-7)
