@@ -50,7 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=1 << 20)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--what", nargs="+", default=["coarse", "importance", "packed"])
+    ap.add_argument("--what", nargs="+", default=["coarse", "importance", "packed", "geometry"])
     ap.add_argument("--warmup", type=int, default=3, help="untimed launches per kernel (1 for ncu captures)")
     a = ap.parse_args()
     global WARMUP
@@ -77,6 +77,52 @@ def main():
             report(f"importance_sample+merge {kc}->{n}+{nd}", ms, r, 12 * kc + 12 * n + 8 * nd + 8)
             ms = timeit(lambda: ops.importance_sample(w, near, far, u, u2, want_fine=True), a.iters)
             report(f"importance_sample only {kc}->{n}", ms, r, 4 * kc + 12 * n + 8)
+    if "geometry" in a.what:
+        import avr_b200
+        lib = avr_b200.load_library()
+        sp = torch.cuda.current_stream().cuda_stream
+        ros = torch.randn(1, r, 3, device=dev, generator=g)
+        rds = torch.nn.functional.normalize(torch.randn(1, r, 3, device=dev, generator=g), dim=-1)
+        for k in (64, 96):
+            u = torch.rand(1, r, k, device=dev, generator=g)
+            z = ops.coarse_sample_raw(near, far, 0, u)
+            pts = torch.empty(1, r, k, 3, device=dev)
+            vd = torch.empty_like(pts)
+
+            def points():
+                rc = lib.avr_ray_points_fwd(ros.data_ptr(), rds.data_ptr(), z.data_ptr(), r, k, pts.data_ptr(), vd.data_ptr(), sp)
+                assert rc == 0
+
+            def fused():
+                rc = lib.avr_coarse_sample_points_fwd(near.data_ptr(), far.data_ptr(), 0, u.data_ptr(), ros.data_ptr(),
+                                                      rds.data_ptr(), r, k, z.data_ptr(), pts.data_ptr(), vd.data_ptr(), sp)
+                assert rc == 0
+
+            report(f"ray_points (pts + viewdirs) K={k}", timeit(points, a.iters), r, 28 * k + 24)
+            report(f"coarse_sample + points fused K={k}", timeit(fused, a.iters), r, 32 * k + 32)
+            ms = timeit(lambda: (ros.unsqueeze(-2) + rds.unsqueeze(-2) * z.unsqueeze(-1),
+                                 rds.unsqueeze(-2).expand(1, r, k, 3).reshape(1, -1, 3)), a.iters)
+            report(f"torch eager equivalent (renderers.py:171-174) K={k}", ms, r, 28 * k + 24)
+            gp = torch.randn(1, r, k, 3, device=dev, generator=g)
+            dz = torch.empty(1, r, k, device=dev)
+
+            def bwd():
+                rc = lib.avr_ray_points_bwd(rds.data_ptr(), gp.data_ptr(), r, k, dz.data_ptr(), sp)
+                assert rc == 0
+
+            report(f"ray_points_bwd (d_z) K={k}", timeit(bwd, a.iters), r, 16 * k + 12)
+            del pts, vd, gp, dz
+        x_pix = torch.rand(1, r, 2, device=dev, generator=g)
+        c2w = torch.eye(4, device=dev).repeat(1, r, 1, 1) + 0.01 * torch.randn(1, r, 4, 4, device=dev, generator=g)
+        kin = torch.tensor([[[1.025, 0.0, 0.5], [0.0, 1.025, 0.5], [0.0, 0.0, 1.0]]], device=dev)
+        report("world_rays (get_world_rays)", timeit(lambda: ops.world_rays(x_pix, kin, c2w), a.iters), r, 8 + 64 + 24)
+        dist_t = torch.rand(1, r, device=dev, generator=g)
+        report("depth_from_world", timeit(lambda: ops.depth_from_world(ros, rds, dist_t, c2w), a.iters), r, 24 + 4 + 64 + 4)
+        from avr_b200 import geometry as _g  # noqa: F401
+        pts1 = ros + rds * dist_t.unsqueeze(-1)
+        h = torch.cat((pts1, torch.ones_like(pts1[..., :1])), -1)
+        ms = timeit(lambda: -torch.einsum("...ij,...j->...i", torch.inverse(c2w), h)[..., 2], a.iters)
+        report("torch eager depth_from_world (utils.py:358-361)", ms, r, 24 + 4 + 64 + 4)
     if "packed" in a.what:
         rp = min(r, 1 << 20)
         counts = torch.randint(8, 257, (rp,), device=dev, generator=g)
