@@ -40,7 +40,10 @@ __device__ __forceinline__ float coarse_z(float near, float span, int j, float k
 }
 
 // One thread per 4 consecutive samples (K % 4 == 0 keeps them in one ray): 16 B of z (or u) in,
-// 48 B of points and 48 B of view directions out as three 16-byte stores each.
+// 48 B of points and 48 B of view directions out.  A thread's 48 bytes are contiguous but the
+// warp's stores would interleave at a 48-byte stride (half-filled sectors), so each warp
+// transposes its 1536 bytes through shared memory and writes three fully coalesced 512-byte rows
+// (the 48-byte stride is conflict-free for 16-byte shared-memory accesses).
 // kFromU: `zu` holds the uniforms; z is computed here (and stored) — the fused coarse sampler.
 template <bool kFromU>
 __global__ void __launch_bounds__(256)
@@ -48,12 +51,18 @@ ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ 
                        const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
                        int64_t n_vec, int K, float* __restrict__ z_out, float* __restrict__ pts,
                        float* __restrict__ viewdirs) {
+  __shared__ float4 s_stage[8][96];
+  const int lane = threadIdx.x & 31;
+  float4* sw = s_stage[threadIdx.x >> 5];
   const float kf = (float)K;
   const bool pow2 = (K & (K - 1)) == 0;
   const float inv_k = 1.0f / kf;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_vec; v += stride) {
-    const int64_t i = v * 4;
+  // warp-uniform loop: v0 is the warp's first vector, every lane stays until the warp is done
+  for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x - lane); v0 < n_vec; v0 += stride) {
+    const int64_t v = v0 + lane;
+    const bool valid = v < n_vec;
+    const int64_t i = (valid ? v : n_vec - 1) * 4;
     const int64_t r = i / K;
     const int j = (int)(i - r * K);
     const Ray3 q = load_ray3(ros, rds, r);
@@ -66,19 +75,31 @@ ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ 
       z4.y = coarse_z(n0, span, j + 1, kf, inv_k, pow2, z4.y);
       z4.z = coarse_z(n0, span, j + 2, kf, inv_k, pow2, z4.z);
       z4.w = coarse_z(n0, span, j + 3, kf, inv_k, pow2, z4.w);
-      stg_stream(reinterpret_cast<float4*>(z_out + i), z4);
+      if (valid) stg_stream(reinterpret_cast<float4*>(z_out + i), z4);
     }
     const float3 p0 = point_on_ray(q, z4.x), p1 = point_on_ray(q, z4.y), p2 = point_on_ray(q, z4.z),
                  p3 = point_on_ray(q, z4.w);
-    float4* po = reinterpret_cast<float4*>(pts + i * 3);
-    stg_stream(po + 0, make_float4(p0.x, p0.y, p0.z, p1.x));
-    stg_stream(po + 1, make_float4(p1.y, p1.z, p2.x, p2.y));
-    stg_stream(po + 2, make_float4(p2.z, p3.x, p3.y, p3.z));
+    const int64_t n_left = n_vec - v0;
+    const int n_f4 = (int)(n_left < 32 ? n_left : 32) * 3;  // float4s this warp writes per output
+    sw[lane * 3 + 0] = make_float4(p0.x, p0.y, p0.z, p1.x);
+    sw[lane * 3 + 1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+    sw[lane * 3 + 2] = make_float4(p2.z, p3.x, p3.y, p3.z);
+    __syncwarp();
+    float4* po = reinterpret_cast<float4*>(pts + v0 * 12);
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      if (t * 32 + lane < n_f4) stg_stream(po + t * 32 + lane, sw[t * 32 + lane]);
+    __syncwarp();
     if (viewdirs) {
-      float4* vo = reinterpret_cast<float4*>(viewdirs + i * 3);
-      stg_stream(vo + 0, make_float4(q.dx, q.dy, q.dz, q.dx));
-      stg_stream(vo + 1, make_float4(q.dy, q.dz, q.dx, q.dy));
-      stg_stream(vo + 2, make_float4(q.dz, q.dx, q.dy, q.dz));
+      sw[lane * 3 + 0] = make_float4(q.dx, q.dy, q.dz, q.dx);
+      sw[lane * 3 + 1] = make_float4(q.dy, q.dz, q.dx, q.dy);
+      sw[lane * 3 + 2] = make_float4(q.dz, q.dx, q.dy, q.dz);
+      __syncwarp();
+      float4* vo = reinterpret_cast<float4*>(viewdirs + v0 * 12);
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+        if (t * 32 + lane < n_f4) stg_stream(vo + t * 32 + lane, sw[t * 32 + lane]);
+      __syncwarp();
     }
   }
 }
@@ -125,13 +146,21 @@ ray_points_bwd_kernel(const float* __restrict__ rds, const float* __restrict__ g
 }
 
 // utils.get_world_rays: origin = pose[:3,3]; dir = R_pose * normalize(flip(K^-1 [x,y,1]))
-// kinv: [n_cams,3,3] (the inverse intrinsics, one per object: ray r uses camera r / rays_per_cam)
+// intr: [n_cams,3,3] intrinsics, one per object (ray r uses camera r / rays_per_cam); the 3x3
+// inverse (utils.py:263) is formed per thread from the cofactors — 9 cached loads and ~30 flops.
 __global__ void __launch_bounds__(256)
-world_rays_kernel(const float* __restrict__ x_pix, const float* __restrict__ kinv, const float* __restrict__ c2w,
+world_rays_kernel(const float* __restrict__ x_pix, const float* __restrict__ intr, const float* __restrict__ c2w,
                   int64_t R, int64_t rays_per_cam, float* __restrict__ ros, float* __restrict__ rds) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += stride) {
-    const float* ki = kinv + (r / rays_per_cam) * 9;
+    const float* km = intr + (r / rays_per_cam) * 9;
+    const float a00 = km[0], a01 = km[1], a02 = km[2], a10 = km[3], a11 = km[4], a12 = km[5], a20 = km[6],
+                a21 = km[7], a22 = km[8];
+    const float c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    const float idet = 1.0f / (a00 * c00 + a01 * c01 + a02 * c02);
+    const float ki[9] = {c00 * idet, (a02 * a21 - a01 * a22) * idet, (a01 * a12 - a02 * a11) * idet,
+                         c01 * idet, (a00 * a22 - a02 * a20) * idet, (a02 * a10 - a00 * a12) * idet,
+                         c02 * idet, (a01 * a20 - a00 * a21) * idet, (a00 * a11 - a01 * a10) * idet};
     const float x = x_pix[r * 2 + 0], y = x_pix[r * 2 + 1];
     // einsum('ij,kj->ki', K^-1, [x,y,1])  (utils.py:263)
     float cx = ki[0] * x + ki[1] * y + ki[2];

@@ -2,8 +2,7 @@
 
 ``utils.get_world_rays`` (utils.py:315-336, via ``unproject`` :246-267) and
 ``utils.depth_from_world`` (utils.py:358-361) as CUDA kernels (csrc/geometry.cu) behind
-``ops.world_rays`` / ``ops.depth_from_world``: SURVEY.md section 8(f) row 2.  The only torch
-arithmetic left is the SB 3x3 ``intrinsics.inverse()`` the reference also calls.
+``ops.world_rays`` / ``ops.depth_from_world``: SURVEY.md section 8(f) row 2.
 """
 from __future__ import annotations
 

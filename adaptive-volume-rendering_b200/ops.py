@@ -397,14 +397,13 @@ def coarse_sample_points(near, far, bound_stride: int, u: torch.Tensor, ros: tor
 
 def world_rays(xy_pix: torch.Tensor, intrinsics: torch.Tensor, cam2world: torch.Tensor):
     """utils.get_world_rays (utils.py:309-336): xy_pix (SB,R,2), intrinsics (SB,3,3), cam2world
-    (SB,R,4,4) -> origins, unit directions (SB,R,3).  The SB 3x3 inverses are taken with
-    torch.inverse exactly as the reference does (utils.py:263); everything per ray is the kernel.
-    Non-differentiable (the reference's poses and intrinsics are data)."""
+    (SB,R,4,4) -> origins, unit directions (SB,R,3), all of it (including the 3x3 inverse of
+    utils.py:263) in one kernel.  Non-differentiable (the reference's poses and intrinsics are data)."""
     require_cuda(xy_pix, intrinsics, cam2world)
     sb, n = xy_pix.shape[0], xy_pix.shape[1]
     x = _f32c(xy_pix.detach())
     c2w = _f32c(cam2world.detach())
-    kinv = _f32c(intrinsics.detach().inverse())
+    kinv = _f32c(intrinsics.detach().reshape(-1, 3, 3))
     if kinv.shape[0] != sb:
         kinv = _f32c(kinv.expand(sb, 3, 3))
     ros = torch.empty(sb, n, 3, dtype=torch.float32, device=x.device)

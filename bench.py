@@ -184,6 +184,63 @@ def run_reference_arm(args, k, desc, emit):
     emit(line)
 
 
+# ------------------------------------------------------------------ other configs (short)
+def measure_other_configs(dev, peak):
+    """BASELINE.json configs 3-5 on one GPU, a few iterations each (CUDA events; inputs larger than
+    L2).  ms per launch, rays/s and fraction of the measured HBM roofline from the algorithmic
+    bytes of SURVEY.md section 8(d)."""
+    from avr_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(1)
+
+    def timeit(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    def entry(ms, rays, bytes_per_ray):
+        gbs = bytes_per_ray * rays / (ms * 1e-3) / 1e9
+        return {"ms": round(ms, 4), "rays_per_s": rays / (ms * 1e-3), "GBps": round(gbs, 1), "hbm_frac": round(gbs / peak, 4)}
+
+    out = {}
+    r = 1 << 20
+    near, far = torch.tensor([0.8], device=dev), torch.tensor([1.8], device=dev)
+    # config 3: importance sampling 64 coarse weights -> 128 fine samples (+ merge with the coarse depths)
+    w = torch.rand(1, r, 64, device=dev, generator=g) ** 6
+    u, u2 = torch.rand(1, r, 128, device=dev, generator=g), torch.rand(1, r, 128, device=dev, generator=g)
+    zc = ops.coarse_sample_raw(near, far, 0, torch.rand(1, r, 64, device=dev, generator=g))
+    out["c3_importance_64_to_128_with_merge"] = entry(
+        timeit(lambda: ops.importance_sample(w, near, far, u, u2, z_coarse=zc, want_fine=False, want_sorted=True)), r, 2312)
+    out["c3_importance_64_to_128_sampling_only"] = entry(
+        timeit(lambda: ops.importance_sample(w, near, far, u, u2, want_fine=True)), r, 1800)
+    del w, u, u2, zc
+    # config 4: ragged rays, counts 8..256 (2^20-ray slice of the 2^22-ray config): composite fwd + bwd, packed
+    counts = torch.randint(8, 257, (r,), device=dev, generator=g)
+    offsets = torch.zeros(r + 1, dtype=torch.int64, device=dev)
+    offsets[1:] = torch.cumsum(counts, 0)
+    s = int(offsets[-1])
+    zp = torch.sort(0.8 + torch.rand(s, device=dev, generator=g)).values   # ascending everywhere => ascending per ray
+    xp = torch.cat([torch.sigmoid(torch.randn(s, 3, device=dev, generator=g)),
+                    torch.relu(torch.randn(s, 1, device=dev, generator=g)) * 30], -1)
+    xp.requires_grad_(True)
+
+    def packed_step():
+        xp.grad = None
+        rgb, depth, _ = ops.composite_packed(xp, zp, offsets, True, 1.8, want_w=False)
+        torch.autograd.backward([rgb, depth], [rgb, depth])
+
+    out["c4_packed_composite_fwd_bwd_8_to_256"] = dict(entry(timeit(packed_step, iters=5), r, (56 * s) // r + 48), samples=s)
+    del xp, zp, offsets, counts
+    return out
+
+
 # ------------------------------------------------------------------ GPU arm
 def main():
     # stdout carries exactly ONE JSON line: libraries (NCCL prints its version banner to
@@ -204,6 +261,7 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="override rays per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of the other BASELINE.json configs")
     ap.add_argument("--gather", default="fused", choices=["ce", "fused", "nccl", "none"],
                     help="N>1, the all-gather of rgb+depth: 'fused' = the forward kernel forwards every 32 finished rays "
                          "to each peer's symmetric-memory buffer as one coalesced 512-byte store over NVLink, then a "
@@ -425,6 +483,14 @@ def main():
                "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                "api": "avr_composite_fwd_bwd_host (C ABI, pinned host buffers, 3-slot H2D/compute/D2H pipeline)"}
 
+    # ---- the other BASELINE.json configs, briefly (N=1 only; reported beside the headline, never instead of it)
+    others = None
+    if world == 1 and not args.no_extras:
+        try:
+            others = measure_other_configs(dev, peak)
+        except Exception as exc:  # the headline line must survive a failure here
+            others = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -449,6 +515,8 @@ def main():
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }
+        if others is not None:
+            line["other_configs"] = others
         line.update(extra)
         emit(line)
     if dist is not None:

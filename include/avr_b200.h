@@ -208,10 +208,11 @@ AVR_API int avr_coarse_sample_points_fwd(const float* near, const float* far, in
                                          float* z, float* pts, float* viewdirs, avr_stream_t stream);
 
 /* utils.get_world_rays (utils.py:309-336): ray origins and unit directions in world coordinates.
- *   x_pix [R,2]; kinv [n_cams,3,3] = inverse intrinsics, ray r uses camera r / rays_per_cam;
+ *   x_pix [R,2]; intrinsics [n_cams,3,3], ray r uses camera r / rays_per_cam (the 3x3 inverse of
+ *   utils.py:263 is formed inside the kernel);
  *   cam2world [R,4,4] (one pose per ray, as the reference's callers expand it, train.py:83);
  *   ros, rds [R,3]. */
-AVR_API int avr_world_rays(const float* x_pix, const float* kinv, const float* cam2world, int64_t R,
+AVR_API int avr_world_rays(const float* x_pix, const float* intrinsics, const float* cam2world, int64_t R,
                            int64_t rays_per_cam, float* ros, float* rds, avr_stream_t stream);
 /* utils.depth_from_world (utils.py:358-361) of the composited point ros + rds * dist
  * (renderers.py:274-275, 508-509); dist == NULL: `ros` holds the world points themselves and
