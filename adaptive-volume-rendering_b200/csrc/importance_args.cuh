@@ -24,6 +24,7 @@ struct ImportanceRegArgs {
   int vec4;  // u/u2 rows are 16-byte aligned (n % 4 == 0 and aligned bases)
   int vecw;  // weight rows are 16-byte aligned
   int vecz;  // z_coarse rows, normals rows and the z_sorted rows are 16-byte aligned
+  int skip_grp_classes;  // packed, importance_reg.cu's class kernels: leave rays that importance_grp.cu's ragged classes cover
   float* z_fine;
   float* z_sorted;
   float* cdf;
@@ -32,5 +33,8 @@ struct ImportanceRegArgs {
 
 // importance_grp.cu: static dense shapes, G lanes per ray; AVR_ERR_UNSUPPORTED for other shapes
 int launch_importance_grp(const ImportanceRegArgs& a, cudaStream_t stream);
+// packed layout: per-class ragged kernels for rays of at most 256 coarse / 128 new samples
+int launch_importance_grp_ragged(const ImportanceRegArgs& a, int max_coarse, int max_fine, bool* covers_all,
+                                 cudaStream_t stream);
 
 }  // namespace avr

@@ -24,7 +24,7 @@
 
 namespace avr {
 
-constexpr int kGrpWarps = 8;
+
 
 __host__ __device__ constexpr int pow2ceil_c(int v) { return v <= 1 ? 1 : 2 * pow2ceil_c((v + 1) / 2); }
 
@@ -45,6 +45,11 @@ struct GrpCfg {
   static constexpr int BUF_FLOATS = (P > M + G * PAD ? P : M + G * PAD);
   static constexpr int BUF_STRIDE = BUF_FLOATS + 8;
   static constexpr unsigned kInf0 = ((EPC >= 32 ? 0xffffffffu : ((1u << EPC) - 1u)) & ~((1u << CW) - 1u));
+  // warps per CTA: as many as the static shared-memory limit (48 KiB) allows, at most 8
+  static constexpr int SMEM_PER_WARP = RPW * (TREE_STRIDE + BUF_STRIDE) * 4;
+  static constexpr int WARPS = (8 * SMEM_PER_WARP <= 48 * 1024) ? 8 : 4;
+  // register budget: 64/thread where the per-lane arrays are small, 128 otherwise
+  static constexpr int MIN_BLOCKS = (EPT <= 16 && G >= 16) ? (32 / WARPS) : (16 / WARPS);
   static_assert(G == 8 || G == 16 || G == 32, "group width");
   static_assert((KC & (KC - 1)) == 0 && KC % G == 0 && NI % G == 0 && ND % G == 0, "shape must split evenly over the group");
   static_assert(EPT <= 32 && BUF_STRIDE % 4 == 0 && TREE_STRIDE % 4 == 0, "layout");
@@ -106,12 +111,28 @@ __device__ __forceinline__ void store_consecutive(float* dst, const float (&src)
   }
 }
 
-template <int G, int KC, int NI, int ND>
-__global__ void __launch_bounds__(kGrpWarps * 32, (G >= 16 ? 4 : 2))
+// The class of a packed ray for the ragged kernels below: the smallest (KC, NI) box that holds
+// its kc coarse and n new samples, or -1 (empty ray, or larger than the largest box: those
+// rays take importance_reg.cu's per-class kernels).
+__host__ __device__ inline int grp_ragged_class(int kc, int n) {
+  if (kc < 1 || kc > 256 || n > 128) return -1;
+  if (kc <= 32 && n <= 16) return 0;
+  if (kc <= 64 && n <= 32) return 1;
+  if (kc <= 128 && n <= 64) return 2;
+  return 3;
+}
+
+// kRagged == false: dense rays of exactly (KC, NI, ND) samples.
+// kRagged == true (packed layout): rays of class kClass, i.e. at most KC coarse and NI new
+// samples, padded to the box with masked lanes / +inf keys; the launch handles only its class
+// (warp-level filter over 32 consecutive rays), so a short ray never pays for the longest.
+template <int G, int KC, int NI, int ND, bool kRagged, int kClass>
+__global__ void __launch_bounds__(GrpCfg<G, KC, NI, ND>::WARPS * 32, GrpCfg<G, KC, NI, ND>::MIN_BLOCKS)
 importance_grp_kernel(const ImportanceRegArgs a) {
   using C = GrpCfg<G, KC, NI, ND>;
   constexpr int RPW = C::RPW, NIL = C::NIL, NDL = C::NDL, EPF = C::EPF, CW = C::CW, EPT = C::EPT, EPC = C::EPC;
-  constexpr int DEPTH = C::DEPTH, PAD = C::PAD;
+  constexpr int DEPTH = C::DEPTH, PAD = C::PAD, kGrpWarps = C::WARPS;
+  static_assert(!kRagged || ND == 0, "the packed entry point has no depth samples");
   __shared__ __align__(16) float s_tree[kGrpWarps][RPW][C::TREE_STRIDE];
   __shared__ __align__(16) float s_buf[kGrpWarps][RPW][C::BUF_STRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,28 +153,61 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     hidx[i] = (q < KC) ? (1 << (DEPTH - 1 - tz)) + (q >> (tz + 1)) : 0;
   }
 
-  const int64_t n_wg = (a.R + RPW - 1) / RPW;
-  for (int64_t wg = blockIdx.x * (int64_t)kGrpWarps + warp; wg < n_wg; wg += (int64_t)gridDim.x * kGrpWarps) {
-    const int64_t r_raw = wg * RPW + sub;
-    const bool live = r_raw < a.R;               // a dead group (last warp only) recomputes ray R-1 and stores nothing
-    const int64_t r = live ? r_raw : a.R - 1;
+  // one ray per group: `live` == false marks a group without work of its own (it recomputes a
+  // valid ray alongside the others and stores nothing)
+  auto process = [&](const int64_t r, const bool live) {
     const int64_t bi = a.bound_stride ? r : 0;
     const float near = a.near[bi], far = a.far[bi];
     const float span = __fsub_rn(far, near);
+    // ragged: this ray's counts and its slices of the packed streams
+    int kc = KC, n = NI;
+    int64_t cbase = r * KC, fbase = r * NI;
+    if (kRagged) {
+      cbase = a.offsets[r];
+      kc = (int)(a.offsets[r + 1] - cbase);
+      fbase = a.fine_offsets[r];
+      n = (int)(a.fine_offsets[r + 1] - fbase);
+    }
 
     // ---- loads: everything this lane needs of its ray --------------------------------------
     float w[CW], uu[NIL > 0 ? NIL : 1], jj[NIL > 0 ? NIL : 1], nn[NDL > 0 ? NDL : 1];
     float x[EPT];
-    load_consecutive<CW>(w, a.weights + r * KC + g * CW, a.vecw != 0);
-    if (NIL > 0) {
-      load_consecutive<(NIL > 0 ? NIL : 1)>(uu, a.u + r * NI + g * NIL, a.vec4 != 0);
-      load_consecutive<(NIL > 0 ? NIL : 1)>(jj, a.u2 + r * NI + g * NIL, a.vec4 != 0);
-    }
-    if (do_sort) {
-      if (NDL > 0) load_consecutive<(NDL > 0 ? NDL : 1)>(nn, a.normals + r * ND + g * NDL, a.vecz != 0);
-      const float* zrow = a.z_coarse + r * KC;
+    if (kRagged) {
+      // clamped unconditional loads; entries past the ray's counts are masked where they are used
+      const float* wrow = a.weights + cbase;
 #pragma unroll
-      for (int i = 0; i < CW; ++i) x[i] = zrow[i * G + g];  // striped: merged position q = i*G + g
+      for (int i = 0; i < CW; ++i) {
+        const int j = g * CW + i;
+        w[i] = wrow[j < kc ? j : kc - 1];
+      }
+#pragma unroll
+      for (int q = 0; q < NIL; ++q) {
+        const int e = g * NIL + q;
+        const int ec = n > 0 ? (e < n ? e : n - 1) : 0;
+        uu[q] = n > 0 ? a.u[fbase + ec] : 0.f;
+        jj[q] = n > 0 ? a.u2[fbase + ec] : 0.f;
+      }
+      if (do_sort) {
+        const float* zrow = a.z_coarse + cbase;
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          const int j = i * G + g;
+          const float zv = zrow[j < kc ? j : kc - 1];
+          x[i] = j < kc ? zv : CUDART_INF_F;
+        }
+      }
+    } else {
+      load_consecutive<CW>(w, a.weights + r * KC + g * CW, a.vecw != 0);
+      if (NIL > 0) {
+        load_consecutive<(NIL > 0 ? NIL : 1)>(uu, a.u + r * NI + g * NIL, a.vec4 != 0);
+        load_consecutive<(NIL > 0 ? NIL : 1)>(jj, a.u2 + r * NI + g * NIL, a.vec4 != 0);
+      }
+      if (do_sort) {
+        if (NDL > 0) load_consecutive<(NDL > 0 ? NDL : 1)>(nn, a.normals + r * ND + g * NDL, a.vecz != 0);
+        const float* zrow = a.z_coarse + r * KC;
+#pragma unroll
+        for (int i = 0; i < CW; ++i) x[i] = zrow[i * G + g];  // striped: merged position q = i*G + g
+      }
     }
 
     // ---- 1. cdf (renderers.py:36-39): blocked scan + running max (the search needs a
@@ -161,16 +215,19 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     float part = 0.f;
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
-      w[i] = __fadd_rn(w[i], kPdfEps);
+      w[i] = (!kRagged || g * CW + i < kc) ? __fadd_rn(w[i], kPdfEps) : 0.f;
       part += w[i];
     }
 #pragma unroll
     for (int d = G / 2; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     const float S = part;
+    // dense shapes divide like the reference (renderers.py:37); ragged rays multiply by 1/S (a lane
+    // owns up to 16 bins; <= 1 ulp per pdf entry, same rule as importance_reg.cu's run-time shapes)
+    const float rS = kRagged ? __fdiv_rn(1.0f, S) : 0.f;
     float run = 0.f;
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
-      run += __fdiv_rn(w[i], S);
+      run += kRagged ? __fmul_rn(w[i], rS) : __fdiv_rn(w[i], S);
       w[i] = run;  // local inclusive prefix
     }
     float incl = run;
@@ -190,11 +247,12 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     float floor_prev = __shfl_up_sync(0xffffffffu, mx, 1);
     if (g == 0) floor_prev = 0.f;
     __syncwarp();  // the previous iteration's readers of tree/buf are done
-    float* cdf_out = (a.cdf && live) ? a.cdf + r * (KC + 1) : nullptr;
+    float* cdf_out = (!kRagged && a.cdf && live) ? a.cdf + r * (KC + 1) : nullptr;
     float last = 0.f;
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
-      const float val = fmaxf(off + w[i], floor_prev);
+      float val = fmaxf(off + w[i], floor_prev);
+      if (kRagged && g * CW + i >= kc) val = CUDART_INF_F;  // past the ray's last bin
       tree[hidx[i]] = val;
       if (cdf_out) cdf_out[g * CW + i + 1] = val;
       last = val;
@@ -206,8 +264,9 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     // ---- 2. this lane's new samples -----------------------------------------------------------
     float v[EPF];
     if (NIL > 0) {
-      int32_t* irow = (a.idx && live) ? a.idx + r * NI + g * NIL : nullptr;
-      float* frow = (a.z_fine && live) ? a.z_fine + r * NI + g * NIL : nullptr;
+      int32_t* irow = (!kRagged && a.idx && live) ? a.idx + r * NI + g * NIL : nullptr;
+      float* frow = (a.z_fine && live) ? a.z_fine + fbase + g * NIL : nullptr;
+      const float kcf = (float)kc;
       // node <- 2*node + (tree[node] <= u): after DEPTH probes node - KC counts the entries
       // cdf[1..KC-1] <= u; adding (cdf[KC] <= u) gives clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
       // (c <= u) is the complement of the sign bit of u - c (exact in sign: nothing is flushed).
@@ -228,14 +287,24 @@ importance_grp_kernel(const ImportanceRegArgs a) {
         const float dl = __fsub_rn(uu[q], last);
         const int bin = (int)(node[q] - KC) + 1 - (int)(__float_as_uint(dl) >> 31);
         const float num = __fadd_rn((float)bin, jj[q]);                    // renderers.py:45
-        const float val = __fadd_rn(near, __fmul_rn(span, __fmul_rn(num, inv_kc)));  // :46
+        const float t = kRagged ? __fdiv_rn(num, kcf) : __fmul_rn(num, inv_kc);
+        const float val = __fadd_rn(near, __fmul_rn(span, t));              // :46
         bins[q] = bin;
         v[q] = val;
       }
-      if (irow) store_consecutive<(NIL > 0 ? NIL : 1)>(reinterpret_cast<float*>(irow), reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(bins), a.vec4 != 0);
-      if (frow) store_consecutive<(NIL > 0 ? NIL : 1)>(frow, reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(v), a.vec4 != 0);
+      if (kRagged) {
+#pragma unroll
+        for (int q = 0; q < NIL; ++q) {
+          const bool has = g * NIL + q < n;
+          if (frow && has) frow[q] = v[q];
+          if (!has) v[q] = CUDART_INF_F;  // padding of the class box
+        }
+      } else {
+        if (irow) store_consecutive<(NIL > 0 ? NIL : 1)>(reinterpret_cast<float*>(irow), reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(bins), a.vec4 != 0);
+        if (frow) store_consecutive<(NIL > 0 ? NIL : 1)>(frow, reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(v), a.vec4 != 0);
+      }
     }
-    if (!do_sort) continue;
+    if (!do_sort) return;
 #pragma unroll
     for (int q = 0; q < NDL; ++q) {
       // sample_depth's randn*std (the depth is NOT added), clamped (renderers.py:62-66, :255)
@@ -277,7 +346,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
       const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], lane & ~(G - 1));
       if (g == G - 1) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
-      if (x[i] > nx) unsorted = true;
+      if ((!kRagged || i * G + g + 1 < kc) && x[i] > nx) unsorted = true;
     }
     if (__any_sync(0xffffffffu, unsorted)) {
       __syncwarp();
@@ -292,25 +361,79 @@ importance_grp_kernel(const ImportanceRegArgs a) {
 
     // ---- 5. store the first TOTAL keys: each group writes 32-byte segments of its row -------------
     if (live) {
-      float* out = a.z_sorted + r * C::TOTAL;
+      float* out = a.z_sorted + (kRagged ? cbase + fbase : r * C::TOTAL);
+      const int total = kRagged ? kc + n : C::TOTAL;
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
         const int q = i * G + g;
-        if (q < C::TOTAL) out[q] = x[i];
+        if (q < total) out[q] = x[i];
       }
+    }
+  };
+
+  if (kRagged) {
+    // 32 consecutive rays per step: each lane classifies one; the groups take RPW matches at a time
+    const int64_t step = (int64_t)gridDim.x * kGrpWarps * 32;
+    for (int64_t base = (blockIdx.x * (int64_t)kGrpWarps + warp) * 32; base < a.R; base += step) {
+      const int64_t rr = base + lane;
+      bool mine = false;
+      if (rr < a.R) {
+        const int kc = (int)(a.offsets[rr + 1] - a.offsets[rr]);
+        const int n = (int)(a.fine_offsets[rr + 1] - a.fine_offsets[rr]);
+        mine = grp_ragged_class(kc, n) == kClass;
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, mine);
+      while (todo) {
+        const unsigned pick = __fns(todo, 0, sub + 1);        // the (sub+1)-th match, if there is one
+        const bool live = pick != 0xffffffffu;
+        const int64_t r = base + (live ? (int)pick : __ffs(todo) - 1);
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) todo &= todo - 1;       // (x & (x-1)) of 0 stays 0
+        process(r, live);
+      }
+    }
+  } else {
+    const int64_t n_wg = (a.R + RPW - 1) / RPW;
+    for (int64_t wg = blockIdx.x * (int64_t)kGrpWarps + warp; wg < n_wg; wg += (int64_t)gridDim.x * kGrpWarps) {
+      const int64_t r_raw = wg * RPW + sub;
+      process(r_raw < a.R ? r_raw : a.R - 1, r_raw < a.R);   // a dead group (last warp only) recomputes ray R-1
     }
   }
 }
 
 template <int G, int KC, int NI, int ND>
 static int launch_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
+  using C = GrpCfg<G, KC, NI, ND>;
   constexpr int RPW = 32 / G;
   const int64_t n_wg = (a.R + RPW - 1) / RPW;
-  int64_t blocks = (n_wg + kGrpWarps - 1) / kGrpWarps;
-  const int64_t cap = (int64_t)kNumSMs * (G >= 16 ? 4 : 2) * 4;  // 2 resident CTAs per SM, a few waves for balance
+  int64_t blocks = (n_wg + C::WARPS - 1) / C::WARPS;
+  const int64_t cap = (int64_t)kNumSMs * C::MIN_BLOCKS * 4;  // a few waves for balance
   if (blocks > cap) blocks = cap;
-  importance_grp_kernel<G, KC, NI, ND><<<(unsigned)blocks, kGrpWarps * 32, 0, stream>>>(a);
+  importance_grp_kernel<G, KC, NI, ND, false, 0><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
   return check_launch();
+}
+
+template <int G, int KC, int NI, int kClass>
+static int launch_grp_ragged(const ImportanceRegArgs& a, cudaStream_t stream) {
+  using C = GrpCfg<G, KC, NI, 0>;
+  int64_t blocks = (a.R + C::WARPS * 32 - 1) / (C::WARPS * 32);
+  const int64_t cap = (int64_t)kNumSMs * C::MIN_BLOCKS * 2;
+  if (blocks > cap) blocks = cap;
+  importance_grp_kernel<G, KC, NI, 0, true, kClass><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
+  return check_launch();
+}
+
+// Packed layout: one launch per ray class that the caller's maxima allow.  Returns AVR_OK after
+// launching; rays outside every class (kc > 256 or n > 128) are left to the caller
+// (importance_reg.cu), which is told by `*covers_all`.
+int launch_importance_grp_ragged(const ImportanceRegArgs& a, int max_coarse, int max_fine, bool* covers_all,
+                                 cudaStream_t stream) {
+  *covers_all = (max_coarse <= 256 && max_fine <= 128);
+  int rc = launch_grp_ragged<8, 32, 16, 0>(a, stream);
+  if (rc == AVR_OK && (max_coarse > 32 || max_fine > 16)) rc = launch_grp_ragged<8, 64, 32, 1>(a, stream);
+  if (rc == AVR_OK && (max_coarse > 64 || max_fine > 32)) rc = launch_grp_ragged<16, 128, 64, 2>(a, stream);
+  if (rc == AVR_OK && (max_coarse > 128 || max_fine > 64)) rc = launch_grp_ragged<16, 256, 128, 3>(a, stream);
+  return rc;
 }
 
 // Hot dense shapes, compiled with the shape as constants: BASELINE.json config 3 (64 -> 128),

@@ -415,7 +415,7 @@ importance_reg_kernel(const ImportanceRegArgs a) {
         const int n = (int)(a.fine_offsets[rr + 1] - a.fine_offsets[rr]);
         int epf, ept;
         ray_class(kc, n + a.n_depth, epf, ept);
-        mine = (epf == EPF && ept == EPT);
+        mine = (epf == EPF && ept == EPT) && kc > 0 && !(a.skip_grp_classes && kc <= 256 && n <= 128);
       }
       unsigned todo = __ballot_sync(0xffffffffu, mine);
       while (todo) {
@@ -494,6 +494,7 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   a.vecw = !offsets && ((Kc & 3) == 0) && aligned16(weights);
   a.vecz = !offsets && ((Kc & 3) == 0) && ((nd_eff & 3) == 0) && ((n_imp & 3) == 0) && aligned16(z_coarse) &&
            aligned16(normals) && aligned16(z_sorted);
+  a.skip_grp_classes = 0;
   a.z_fine = z_fine;
   a.z_sorted = z_sorted;
   a.cdf = cdf;
@@ -516,7 +517,15 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   // the caller's maxima (AVR_PACKED_CLASSES=0: one launch, every ray at the maximum shape)
   if (offsets && R >= 4096) {
     const char* sw = std::getenv("AVR_PACKED_CLASSES");
+    const char* gs = std::getenv("AVR_IMPORTANCE_GRP");
     if (!(sw && sw[0] == '0')) {
+      if (!(gs && gs[0] == '0') && a.n_depth == 0 && !cdf && !idx) {
+        // rays of at most 256 coarse / 128 new samples: 8 or 16 lanes per ray (importance_grp.cu)
+        bool covers_all = false;
+        const int rc = launch_importance_grp_ragged(a, Kc, n_imp, &covers_all, stream);
+        if (rc != AVR_OK || covers_all) return rc;
+        a.skip_grp_classes = 1;
+      }
 #define AVR_REG_CLASS(F, T)                              \
   if (F <= epf && T <= ept) {                            \
     const int rc = launch_reg_class<F, T>(a, stream);    \

@@ -84,10 +84,12 @@ def test_packed_pipeline_vs_oracle(dev, family):
         assert_close(dz[idx] / scale[0], (wdz[0] / scale[0]).float(), rtol=1e-5, atol=2e-5, what=f"d_z k={k}")
 
 
-def test_packed_importance_and_merge(dev):
+@pytest.mark.parametrize("r,lo,hi", [(2000, 8, 128),     # few rays: one launch at the maximum shape
+                                     (6000, 1, 256),     # per-class ragged kernels (8/16 lanes per ray), n = 0 for k = 1
+                                     (5000, 8, 300)])    # rays beyond the largest class box take the warp-per-ray classes
+def test_packed_importance_and_merge(r, lo, hi, dev):
     from avr_b200 import ops
-    r = 2000
-    counts, offsets, g = _ragged(r, 8, 128, seed=1, zero_some=False)
+    counts, offsets, g = _ragged(r, lo, hi, seed=1, zero_some=False)
     fine_counts = counts // 2
     fine_offsets = torch.zeros(r + 1, dtype=torch.int64)
     fine_offsets[1:] = torch.cumsum(fine_counts, 0)
@@ -97,7 +99,7 @@ def test_packed_importance_and_merge(dev):
     sf = int(fine_offsets[-1])
     uf, uf2 = torch.rand(sf, generator=g), torch.rand(sf, generator=g)
     zf, zs = ops.importance_sample_packed(w.to(dev), zc.to(dev), near.to(dev), far.to(dev), uf.to(dev), uf2.to(dev),
-                                          offsets.to(dev), fine_offsets.to(dev), 128, 64)
+                                          offsets.to(dev), fine_offsets.to(dev), hi, hi // 2)
     zf, zs = zf.cpu(), zs.cpu()
     out_offsets = offsets + fine_offsets
     mismatched = 0
