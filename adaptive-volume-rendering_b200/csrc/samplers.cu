@@ -113,6 +113,40 @@ coarse_bwd_kernel(const float* __restrict__ g_z, const float* __restrict__ u, in
   }
 }
 
+// Short rays (the adaptive renderer's K = 20): one THREAD per ray, 16-byte loads of its own row
+// (a warp's 32 rows are one contiguous block, so every sector is used), no shuffles, no idle lanes.
+template <int V>
+__global__ void __launch_bounds__(256)
+coarse_bwd_thread_kernel(const float* __restrict__ g_z, const float* __restrict__ u, int64_t R, int K,
+                         float* __restrict__ d_near, float* __restrict__ d_far) {
+  const float inv_k = 1.0f / (float)K;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += stride) {
+    const float* gr = g_z + r * K;
+    const float* ur = u + r * K;
+    float dn = 0.f, df = 0.f;
+    for (int j = 0; j < K; j += V) {
+      float gv[V], uv[V];
+      if (V == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(gr + j), b = *reinterpret_cast<const float4*>(ur + j);
+        gv[0] = a.x; gv[V > 1 ? 1 : 0] = a.y; gv[V > 2 ? 2 : 0] = a.z; gv[V > 3 ? 3 : 0] = a.w;
+        uv[0] = b.x; uv[V > 1 ? 1 : 0] = b.y; uv[V > 2 ? 2 : 0] = b.z; uv[V > 3 ? 3 : 0] = b.w;
+      } else {
+        gv[0] = gr[j];
+        uv[0] = ur[j];
+      }
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float f = (float)(j + q) * inv_k + uv[q] * inv_k;
+        df += gv[q] * f;
+        dn += gv[q] * (1.0f - f);
+      }
+    }
+    d_near[r] = dn;
+    d_far[r] = df;
+  }
+}
+
 // ---- warp-synchronous bitonic sort of P (power of two) keys in shared memory --------
 // With `idx` non-null the (key, index) pairs are ordered lexicographically, which makes
 // the result the stable sort of the keys.
@@ -299,6 +333,58 @@ sort_rays_kernel(const float* __restrict__ z_in, int64_t R, int K, int P, float*
   }
 }
 
+// Short rays that are (almost always) ALREADY ascending — the adaptive renderer sorts stratified
+// depths (renderers.py:492-494), so the sort is the identity and only routes gradients.  One
+// thread per ray checks its row with 16-byte loads; an ascending ray is copied and gets the
+// identity permutation; the rare unsorted ray is then sorted by its whole warp with the
+// shared-memory network above (stable, like torch.sort(stable=True)).
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+sort_rays_presorted_kernel(const float* __restrict__ z_in, int64_t R, int K, int P, float* __restrict__ z_out,
+                           int32_t* __restrict__ perm) {
+  extern __shared__ __align__(16) float fsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* key = fsmem + warp * 2 * P;
+  int* idx = reinterpret_cast<int*>(key + P);
+  const int64_t warps = (int64_t)gridDim.x * kSamplerWarps;
+  for (int64_t r0 = (blockIdx.x * (int64_t)kSamplerWarps + warp) * 32; r0 < R; r0 += warps * 32) {
+    const int64_t r = r0 + lane;
+    bool sorted = true;
+    if (r < R) {
+      const float4* row = reinterpret_cast<const float4*>(z_in + r * K);
+      float4* orow = reinterpret_cast<float4*>(z_out + r * K);
+      float prev = -CUDART_INF_F;
+      for (int j = 0; j < K / 4; ++j) {
+        const float4 q = row[j];
+        // strictly "not descending": ties keep their order under a stable sort, so they are fine
+        sorted = sorted && (prev <= q.x) && (q.x <= q.y) && (q.y <= q.z) && (q.z <= q.w);
+        prev = q.w;
+        orow[j] = q;                       // overwritten below if the ray turns out unsorted
+      }
+      if (perm && sorted) {
+        int4* prow = reinterpret_cast<int4*>(perm + r * K);
+        for (int j = 0; j < K / 4; ++j) prow[j] = make_int4(4 * j, 4 * j + 1, 4 * j + 2, 4 * j + 3);
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, !sorted);
+    while (todo) {                          // NaNs land here too (comparisons fail) and take the network
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t rr = r0 + b;
+      __syncwarp();
+      for (int i = lane; i < P; i += 32) {
+        key[i] = (i < K) ? z_in[rr * K + i] : CUDART_INF_F;
+        idx[i] = i;
+      }
+      warp_bitonic_sort(key, idx, P, lane);
+      for (int i = lane; i < K; i += 32) {
+        z_out[rr * K + i] = key[i];
+        if (perm) perm[rr * K + i] = idx[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---- launchers ------------------------------------------------------------------------
 static int grid_for(int64_t work_items, int per_block, int max_blocks) {
   int64_t b = (work_items + per_block - 1) / per_block;
@@ -332,6 +418,14 @@ int launch_coarse_fwd(const float* near, const float* far, int bound_stride, con
 int launch_coarse_bwd(const float* g_z, const float* u, int64_t R, int K, float* d_near, float* d_far,
                       cudaStream_t stream) {
   if (R == 0) return AVR_OK;
+  if (K <= 64) {  // short rays: one thread per ray
+    if (K % 4 == 0 && aligned16(g_z) && aligned16(u)) {
+      coarse_bwd_thread_kernel<4><<<grid_for(R, 256, kNumSMs * 8), 256, 0, stream>>>(g_z, u, R, K, d_near, d_far);
+    } else {
+      coarse_bwd_thread_kernel<1><<<grid_for(R, 256, kNumSMs * 8), 256, 0, stream>>>(g_z, u, R, K, d_near, d_far);
+    }
+    return check_launch();
+  }
   coarse_bwd_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 16), kSamplerWarps * 32, 0, stream>>>(g_z, u, R, K,
                                                                                                 d_near, d_far);
   return check_launch();
@@ -391,6 +485,11 @@ int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t*
   if (K > AVR_MAX_SORT) return AVR_ERR_UNSUPPORTED;
   const int P = next_pow2(K);
   const int smem = kSamplerWarps * 2 * P * (int)sizeof(float);
+  if (K % 4 == 0 && K <= 128 && aligned16(z_in) && aligned16(z_out) && aligned16(perm)) {
+    sort_rays_presorted_kernel<<<grid_for(R, kSamplerWarps * 32, kNumSMs * 8), kSamplerWarps * 32, smem, stream>>>(
+        z_in, R, K, P, z_out, perm);
+    return check_launch();
+  }
   sort_rays_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 8), kSamplerWarps * 32, smem, stream>>>(z_in, R, K, P,
                                                                                                 z_out, perm);
   return check_launch();

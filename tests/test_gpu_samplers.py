@@ -161,6 +161,10 @@ def test_sort_rays_and_grad(dev):
     for k in (1, 20, 33, 96, 1024):
         z = torch.rand(3, 40, k, generator=g)
         z[0, 0, : k // 2] = 0.5                                  # ties: stable order expected
+        z[1] = torch.sort(z[1], -1).values                       # already ascending rays (the adaptive renderer's case)
+        z[2, ::3] = torch.sort(z[2, ::3], -1).values             # sorted and unsorted rays mixed inside a warp
+        if k >= 8:
+            z[1, 7, 3:6] = z[1, 7, 3]                            # ascending with ties
         zd = z.to(dev).requires_grad_(True)
         out, perm = ops.SortRays.apply(zd)
         want = torch.sort(z, dim=-1, stable=True)

@@ -50,7 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=1 << 20)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--what", nargs="+", default=["coarse", "importance", "packed", "geometry"])
+    ap.add_argument("--what", nargs="+", default=["coarse", "importance", "packed", "geometry", "adaptive"])
     ap.add_argument("--warmup", type=int, default=3, help="untimed launches per kernel (1 for ncu captures)")
     a = ap.parse_args()
     global WARMUP
@@ -123,6 +123,39 @@ def main():
         h = torch.cat((pts1, torch.ones_like(pts1[..., :1])), -1)
         ms = timeit(lambda: -torch.einsum("...ij,...j->...i", torch.inverse(c2w), h)[..., 2], a.iters)
         report("torch eager depth_from_world (utils.py:358-361)", ms, r, 24 + 4 + 64 + 4)
+    if "adaptive" in a.what:
+        # AdaptiveVolumeRenderer's tail (renderers.py:489-509): K = 20 samples in [d-eps, d+eps], depths carry grad
+        import avr_b200
+        lib = avr_b200.load_library()
+        sp = torch.cuda.current_stream().cuda_stream
+        k = 20
+        d = 0.9 + 0.8 * torch.rand(1, r, device=dev, generator=g)
+        nr, fr = (d - 0.15).reshape(-1).contiguous(), (d + 0.15).reshape(-1).contiguous()
+        u = torch.rand(1, r, k, device=dev, generator=g)
+        report(f"coarse_sample per-ray bounds K={k}", timeit(lambda: ops.coarse_sample_raw(nr, fr, 1, u), a.iters), r, 8 * k + 8)
+        z = ops.coarse_sample_raw(nr, fr, 1, u)
+        gz = torch.randn(1, r, k, device=dev, generator=g)
+        dn, df = torch.empty(r, device=dev), torch.empty(r, device=dev)
+
+        def cbwd():
+            assert lib.avr_coarse_sample_bwd(gz.data_ptr(), u.data_ptr(), r, k, dn.data_ptr(), df.data_ptr(), sp) == 0
+
+        report(f"coarse_sample_bwd (d_near, d_far) K={k}", timeit(cbwd, a.iters), r, 8 * k + 8)
+        zs, perm = torch.empty_like(z), torch.empty(1, r, k, dtype=torch.int32, device=dev)
+
+        def srt():
+            assert lib.avr_sort_rays(z.data_ptr(), r, k, zs.data_ptr(), perm.data_ptr(), sp) == 0
+
+        report(f"sort_rays (+perm) K={k}", timeit(srt, a.iters), r, 12 * k)
+        x = torch.cat([torch.sigmoid(torch.randn(1, r, k, 3, device=dev, generator=g)),
+                       torch.relu(torch.randn(1, r, k, 1, device=dev, generator=g)) * 30], -1).contiguous()
+        report(f"composite_fwd K={k} (no weights)", timeit(lambda: ops.composite_fwd_raw(x, z, True, 1.8, False), a.iters), r, 20 * k + 16)
+        g1, g2 = torch.randn(1, r, 3, device=dev, generator=g), torch.randn(1, r, device=dev, generator=g)
+        report(f"composite_bwd K={k} with d_z", timeit(lambda: ops.composite_bwd_raw(x, z, g1, g2, None, True, 1.8, True), a.iters),
+               r, 40 * k + 16)
+        report(f"composite_bwd K={k} without d_z", timeit(lambda: ops.composite_bwd_raw(x, z, g1, g2, None, True, 1.8, False), a.iters),
+               r, 36 * k + 16)
+        del x, z, zs, perm, gz
     if "packed" in a.what:
         rp = min(r, 1 << 20)
         counts = torch.randint(8, 257, (rp,), device=dev, generator=g)
