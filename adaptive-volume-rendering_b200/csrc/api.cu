@@ -214,10 +214,12 @@ int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, con
   cudaStream_t st = as_stream(stream);
   SpanPlan plan;
   int64_t done = 0;
-  // the span kernel covers the training configuration (no grad into weights or z);
-  // g_w / d_z requests take the generic kernel
-  if (!g_force_generic.load() && !g_w && !d_z && span_plan(R, K, rgbs, z, &plan)) {
-    int rc = launch_composite_bwd_span(plan, rgbs, z, g_rgb, g_depth, K, white_back, infinity, d_rgbs, st);
+  // the span kernel covers the training configurations: no grad into the weights; grad into z
+  // (adaptive renderer) when a lane's run holds at most one ray end (K > L) and d_z is 16-byte
+  // aligned.  g_w requests and the remaining shapes take the warp-per-ray kernel.
+  if (!g_force_generic.load() && !g_w && span_plan(R, K, rgbs, z, &plan) &&
+      (!d_z || (K > plan.L && aligned16(d_z)))) {
+    int rc = launch_composite_bwd_span(plan, rgbs, z, g_rgb, g_depth, K, white_back, infinity, d_rgbs, d_z, st);
     if (rc != AVR_OK) return rc;
     done = plan.main_rays;
   }

@@ -323,7 +323,7 @@ composite_fwd_span_kernel(const SpanArgs a) {
   if (kWriteW && lane == 0) bulk_wait_all<0>();
 }
 
-template <int L, int NS, bool kSimple>
+template <int L, int NS, bool kSimple, bool kDz>
 __global__ void __launch_bounds__(256)
 composite_bwd_span_kernel(const SpanArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -374,9 +374,9 @@ composite_bwd_span_kernel(const SpanArgs a) {
     }
     mbar_wait(&pipe.bars[st], (uint32_t)((i / NS) & 1));
     float4* rg = pipe.rgbs_stage(st) + run.s0;
-    const float* zs = pipe.z_stage(st) + run.s0;
+    float* zs = pipe.z_stage(st) + run.s0;
     if (kSimple) {
-      bwd_tile_simple<L>(a, run, rg, zs, gA, gB, lane);
+      bwd_tile_simple<L, kDz>(a, run, rg, zs, gA, gB, lane);
     } else {
       bwd_tile_general<L>(a, run, rg, zs, gA, gB, ray_base, lane);
     }
@@ -384,6 +384,7 @@ composite_bwd_span_kernel(const SpanArgs a) {
     __syncwarp();
     if (lane == 0) {
       bulk_s2g(a.d_rgbs + tile * (int64_t)n_s * 4, pipe.rgbs_stage(st), (uint32_t)n_cur * 16u);
+      if (kDz) bulk_s2g(a.d_z + tile * (int64_t)n_s, pipe.z_stage(st), (uint32_t)n_cur * 4u);
       bulk_commit();
     }
   }
@@ -490,8 +491,12 @@ static int fwd_span_LN(const SpanArgs& a, bool simple, bool write_w, cudaStream_
 template <int L, int NS>
 static int bwd_span_LN(const SpanArgs& a, bool simple, cudaStream_t stream) {
   constexpr int sb = SpanCfg<L>::kStageBytes;
-  if (simple) return span_launch(composite_bwd_span_kernel<L, NS, true>, L, sb, NS, a, stream);
-  if constexpr (L == 5) return span_launch(composite_bwd_span_kernel<L, NS, false>, L, sb, NS, a, stream);
+  if (simple) {
+    return a.d_z ? span_launch(composite_bwd_span_kernel<L, NS, true, true>, L, sb, NS, a, stream)
+                 : span_launch(composite_bwd_span_kernel<L, NS, true, false>, L, sb, NS, a, stream);
+  }
+  if (a.d_z) return AVR_ERR_UNSUPPORTED;  // callers check span_supports_dz() first
+  if constexpr (L == 5) return span_launch(composite_bwd_span_kernel<L, NS, false, false>, L, sb, NS, a, stream);
   return AVR_ERR_UNSUPPORTED;
 }
 
@@ -540,8 +545,9 @@ int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const flo
 
 int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
-                              cudaStream_t stream) {
+                              float* d_z, cudaStream_t stream) {
   SpanArgs a = make_args(plan, K, white_back, infinity);
+  a.d_z = d_z;
   a.rgbs = rgbs;
   a.z = z;
   a.g_rgb = g_rgb;

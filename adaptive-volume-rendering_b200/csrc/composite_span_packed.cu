@@ -345,8 +345,8 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
         gB = (run.end_pos >= 0 && run.end_pos + 1 < run.nvalid) ? load_ray_grad(a.sp, cur.r0 + run.ray0 + 1) : gA;
       }
       float4* rg = pipe.rgbs_stage(st) + run.s0;
-      const float* zs = pipe.z_stage(st) + shift + run.s0;
-      bwd_tile_simple<kPkL>(a.sp, run, rg, zs, gA, gB, lane);
+      float* zs = pipe.z_stage(st) + shift + run.s0;
+      bwd_tile_simple<kPkL, false>(a.sp, run, rg, zs, gA, gB, lane);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {

@@ -37,7 +37,7 @@ int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const flo
                               int64_t peer_row0 = 0);
 int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
-                              cudaStream_t stream);
+                              float* d_z /* nullable; needs K > plan.L */, cudaStream_t stream);
 
 // composite_span_packed.cu — packed layout, TMA-staged whole-ray tiles packed on the fly
 bool span_packed_eligible(const void* rgbs, const void* z, const void* w_or_null, const void* d_rgbs_or_null);

@@ -26,6 +26,7 @@ struct SpanArgs {
   const float* g_rgb;     // bwd (nullable)
   const float* g_depth;   // bwd (nullable)
   float* d_rgbs;          // bwd
+  float* d_z;             // bwd (nullable): gradient w.r.t. the depths (adaptive renderer)
   int64_t n_tiles;
   int K;
   int rays_per_tile;
@@ -244,8 +245,12 @@ __device__ __forceinline__ void fwd_tile_simple(const SpanArgs& a, const Run& ru
 }
 
 // ---- backward, K > L -------------------------------------------------------------------
-template <int L>
-__device__ __forceinline__ void bwd_tile_simple(const SpanArgs& a, const Run& run, float4* rg, const float* zs,
+// kDz: also form d_z (the adaptive renderer's depths carry grad, renderers.py:490-509):
+//   d_z[k] = [k > 0] (dL/ddelta_{k-1} + g_depth * w_{k-1}) - [k < K-1] dL/ddelta_k,
+//   dL/ddelta_k = dL/d(sigma*delta)_k * sigma_k.
+// The values are written over the tile's z (once every lane has read it) and leave by bulk store.
+template <int L, bool kDz>
+__device__ __forceinline__ void bwd_tile_simple(const SpanArgs& a, const Run& run, float4* rg, float* zs,
                                                 const RayGrad& gA, const RayGrad& gB, int lane) {
   const int p = run.end_pos;
   // walk 1, front to back: cache e_j and the local transmittance before sample j; sum the
@@ -290,6 +295,9 @@ __device__ __forceinline__ void bwd_tile_simple(const SpanArgs& a, const Run& ru
   float Q = scan_rev_exclusive(lane, A, Bm);
 
   // walk 2, back to front: final gradients, written over the rgbs stage in place
+  float dzl[kDz ? L : 1];   // d_z of the run, completed below
+  float dd_next = 0.f;      // dL/ddelta of sample j+1 (kDz)
+  float a_last = 0.f;       // what the run's last sample sends to the NEXT lane's first sample (kDz)
   float zn = zs[L];
 #pragma unroll
   for (int j = L - 1; j >= 0; --j) {
@@ -317,7 +325,22 @@ __device__ __forceinline__ void bwd_tile_simple(const SpanArgs& a, const Run& ru
     const float dsd = dalpha * e;
     const float w = alpha * T;
     rg[j] = make_float4(w * gr, w * gg, w * gb, dsd * delta);
+    if (kDz) {
+      const float dd = last ? 0.f : dsd * c.w;           // dL/ddelta_j
+      const float to_next = last ? 0.f : dd + gd * w;     // lands on z_{j+1}
+      if (j == L - 1) a_last = to_next;
+      else dzl[kDz ? j + 1 : 0] = to_next - dd_next;
+      dd_next = dd;
+    }
     zn = zk;
+  }
+  if (kDz) {
+    float from_prev = __shfl_up_sync(0xffffffffu, a_last, 1);   // the previous lane's last sample (0 if it ended a ray)
+    if (lane == 0) from_prev = 0.f;                              // tiles start at a ray head
+    dzl[0] = from_prev - dd_next;
+    __syncwarp();  // every lane has finished reading z from this stage
+#pragma unroll
+    for (int j = 0; j < L; ++j) zs[j] = dzl[kDz ? j : 0];
   }
 }
 

@@ -167,3 +167,35 @@ def test_full_size_properties(dev):
     x0[..., 3] = 0
     rgb0, depth0, w0 = ops.composite(x0[:4096], z[:4096], True, 1.8)
     assert (rgb0 == 1).all() and (depth0 == 0).all() and (w0 == 0).all()
+
+
+@pytest.mark.parametrize("r,k", [(4099, 20), (1000, 96), (777, 64), (515, 192), (300, 12), (64, 7)])
+def test_dz_from_the_span_kernel(r, k, dev):
+    """d_z without g_w (the adaptive renderer's backward) takes the span kernel where a lane's run
+    holds at most one ray end; it must agree with the warp-per-ray / generic kernels and, scaled
+    by the ray's largest |d_z| (d_z is a difference of large terms), with the
+    fp64 oracle."""
+    import avr_b200
+    from avr_b200 import ops
+    lib = avr_b200.load_library()
+    g = torch.Generator().manual_seed(r + k)
+    z = torch.sort(0.8 + torch.rand(1, r, k, generator=g), -1).values
+    z[0, 3, : k // 2] = 0.8                                            # zero-length intervals
+    x = torch.cat([torch.sigmoid(torch.randn(1, r, k, 3, generator=g)), torch.rand(1, r, k, 1, generator=g) * 5], -1)
+    g_rgb, g_d = torch.randn(1, r, 3, generator=g), torch.randn(1, r, generator=g)
+    outs = {}
+    for fam in ("auto", "generic"):
+        lib.avr_set_force_generic(1 if fam == "generic" else 0)
+        try:
+            outs[fam] = ops.composite_bwd_raw(x.to(dev), z.to(dev), g_rgb.to(dev), g_d.to(dev), None, True, 1.8, True)
+        finally:
+            lib.avr_set_force_generic(0)
+    wdx, wdz = O.composite_grads(z.double(), x.double(), g_rgb.double(), g_d.double().unsqueeze(-1), None, True, want_dz=True)
+    for fam, (dx, dz) in outs.items():
+        scale = wdz.abs().amax(-1, keepdim=True).clamp_min(1e-3)
+        assert_close(dz.cpu() / scale, (wdz / scale).float(), rtol=1e-5, atol=2e-5, what=f"{fam} d_z k={k}")
+        assert_close(dx.cpu()[..., :3], wdx[..., :3].float(), what=f"{fam} d_rgb k={k}")
+        assert_close(dx.cpu()[..., :-1, 3], wdx[..., :-1, 3].float(), rtol=1e-5, atol=2e-6, what=f"{fam} d_sigma k={k}")
+    dz_scale = wdz.abs().amax(-1, keepdim=True).clamp_min(1e-3).float()
+    assert_close(outs["auto"][1].cpu() / dz_scale, outs["generic"][1].cpu() / dz_scale, rtol=1e-5, atol=2e-5,
+                 what="span vs generic d_z")
