@@ -32,6 +32,7 @@ PROTOTYPES = {
     "avr_importance_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int,
                                       c_float, _P, _P, _P, _P, _P]),
     "avr_sort_rays": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
+    "avr_sort_rays_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P]),
     "avr_composite_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P]),
     "avr_composite_fwd_gather": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,
                                          ctypes.POINTER(c_void_p), c_int, c_int64, _P]),

@@ -145,6 +145,13 @@ int avr_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* pe
   return launch_sort_rays(z_in, R, K, z_out, perm, as_stream(stream));
 }
 
+int avr_sort_rays_bwd(const float* g_out, const int32_t* perm, int64_t R, int K, float* d_in, avr_stream_t stream) {
+  if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!g_out || !perm || !d_in) return AVR_ERR_BAD_ARG;
+  return launch_sort_rays_bwd(g_out, perm, R, K, d_in, as_stream(stream));
+}
+
 /* ------------------------------------------------------------- compositing -- */
 
 int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int white_back, float infinity,

@@ -74,6 +74,7 @@ int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, i
                       float* ros, float* rds, cudaStream_t stream);
 int launch_depth_from_world(const float* ros, const float* rds, const float* dist, const float* c2w, int64_t R,
                             float* depth, float* grad_row, cudaStream_t stream);
+int launch_sort_rays_bwd(const float* g_out, const int32_t* perm, int64_t R, int K, float* d_in, cudaStream_t stream);
 int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, cudaStream_t stream);
 
 }  // namespace avr

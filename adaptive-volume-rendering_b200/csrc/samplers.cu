@@ -385,6 +385,17 @@ sort_rays_presorted_kernel(const float* __restrict__ z_in, int64_t R, int K, int
   }
 }
 
+// gradient routing of the sort: d_in[r, perm[r,k]] = g_out[r,k]   (torch.sort's backward, renderers.py:494)
+__global__ void __launch_bounds__(256)
+sort_rays_bwd_kernel(const float* __restrict__ g_out, const int32_t* __restrict__ perm, int64_t total, int K,
+                     float* __restrict__ d_in) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / K;
+    d_in[r * K + perm[i]] = g_out[i];
+  }
+}
+
 // ---- launchers ------------------------------------------------------------------------
 static int grid_for(int64_t work_items, int per_block, int max_blocks) {
   int64_t b = (work_items + per_block - 1) / per_block;
@@ -477,6 +488,13 @@ int launch_importance(const float* weights, const float* z_coarse, const float* 
     }
   }
   importance_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 8), kSamplerWarps * 32, smem, stream>>>(a);
+  return check_launch();
+}
+
+int launch_sort_rays_bwd(const float* g_out, const int32_t* perm, int64_t R, int K, float* d_in, cudaStream_t stream) {
+  const int64_t total = R * (int64_t)K;
+  if (total == 0) return AVR_OK;
+  sort_rays_bwd_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, stream>>>(g_out, perm, total, K, d_in);
   return check_launch();
 }
 

@@ -153,8 +153,12 @@ class SortRays(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, _g_perm):
         (perm,) = ctx.saved_tensors
+        g_out = _f32c(g_out)
+        k = g_out.shape[-1]
         g_in = torch.empty_like(g_out)
-        g_in.scatter_(-1, perm.long(), g_out)
+        with torch.cuda.device(g_out.device):
+            check(_lib.load().avr_sort_rays_bwd(ptr(g_out), ptr(perm), g_out.numel() // k, k, ptr(g_in), _stream(g_out)),
+                  "avr_sort_rays_bwd")
         return g_in
 
 

@@ -118,6 +118,11 @@ AVR_API int avr_importance_sample(const float* weights, const float* z_coarse,
 AVR_API int avr_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm,
                   avr_stream_t stream);
 
+/* Gradient of the sort: d_in[r, perm[r,k]] = g_out[r,k] (every element of d_in is written: perm is
+ * a permutation of each row). */
+AVR_API int avr_sort_rays_bwd(const float* g_out, const int32_t* perm, int64_t R, int K, float* d_in,
+                              avr_stream_t stream);
+
 /* ------------------------------------------------------------- compositing -- */
 
 /* Replaces volume_integral, renderers.py:69-119 (fused: deltas, alpha, exclusive
