@@ -49,7 +49,7 @@ struct GrpCfg {
   static constexpr int SMEM_PER_WARP = RPW * (TREE_STRIDE + BUF_STRIDE) * 4;
   static constexpr int WARPS = (8 * SMEM_PER_WARP <= 48 * 1024) ? 8 : 4;
   // register budget: 64/thread where the per-lane arrays are small, 128 otherwise
-  static constexpr int MIN_BLOCKS = (EPT <= 16 && G >= 16) ? (32 / WARPS) : (16 / WARPS);
+  static constexpr int MIN_BLOCKS = (EPT <= 16 && (G >= 16 || EPF <= 4)) ? (32 / WARPS) : (16 / WARPS);
   static_assert(G == 8 || G == 16 || G == 32, "group width");
   static_assert((KC & (KC - 1)) == 0 && KC % G == 0 && NI % G == 0 && ND % G == 0, "shape must split evenly over the group");
   static_assert(EPT <= 32 && BUF_STRIDE % 4 == 0 && TREE_STRIDE % 4 == 0, "layout");
