@@ -37,11 +37,17 @@ namespace avr {
 #define AVR_PK_WARPS 2
 #endif
 #ifndef AVR_PK_STAGES
-#define AVR_PK_STAGES 3
+#define AVR_PK_STAGES 2
 #endif
 constexpr int kPkL = AVR_PK_L;   // samples per lane (odd: conflict-free shared-memory runs)
 constexpr int kPkC = 32 * kPkL;  // samples per tile
 constexpr int kPkStages = AVR_PK_STAGES;
+// Results leave the stage by bulk store when the ring has a third slot to cover the store's read of
+// shared memory; with a 2-slot ring they leave by ordinary coalesced stores inside the iteration, which
+// frees the slot at once.  The packed kernels are bound by per-warp instruction latency (a tile's walk is
+// one dependent chain; 0.25 IPC per warp), so what pays is resident warps: 2 x 8.6 KB per warp = 12
+// warps/SM instead of 8 (profiles/r01_span_sweep.md).
+constexpr bool kOutByTma = kPkStages >= 3;
 constexpr int kPkWarps = AVR_PK_WARPS;
 constexpr int kPkRgbsBytes = kPkC * 16;
 constexpr int kPkZFloats = kPkC + 8;  // + phase shift (<= 3) + one z past the tile + slack
@@ -169,6 +175,7 @@ __device__ __forceinline__ void issue_tile(const PkPipe& pipe, int st, const Pac
   pipe.ends_stage(st)[lane] = rel_end;
   __syncwarp();
   if (lane == 0) {
+    if (!kOutByTma) fence_proxy_async_smem();  // generic reads/writes of this slot precede the async refill
     const int n_s = (int)it.n_s;
     const int shift = (int)(it.sb & 3);
     const int zel = z_bulk_elems(it.sb, n_s, a.S);
@@ -249,7 +256,7 @@ composite_fwd_span_packed_kernel(const PackedArgs a) {
     int64_t nxt_tile = -1;
     if (nxt.kind == kItemTile) {
       nxt_tile = tiles++;
-      if (kWriteW && lane == 0) bulk_wait_read<1>();  // the store that last read this stage is done
+      if (kOutByTma && kWriteW && lane == 0) bulk_wait_read<1>();  // the store that last read this stage is done
       issue_tile(pipe, (int)(nxt_tile % kPkStages), a, nxt, rel_end, lane);
     }
     r_next += nxt.nr;
@@ -275,11 +282,18 @@ composite_fwd_span_packed_kernel(const PackedArgs a) {
         const int len = (n_s - a0) & ~3;
         const float* zt = pipe.z_stage(st) + shift;  // tile sample s at zt[s]
         float* wg = a.sp.w + cur.sb;
-        if (lane == 0 && len > 0) bulk_s2g(wg + a0, zt + a0, (uint32_t)len * 4u);
-        if (lane == 0) bulk_commit();
+        if (kOutByTma) {
+          if (lane == 0 && len > 0) bulk_s2g(wg + a0, zt + a0, (uint32_t)len * 4u);
+          if (lane == 0) bulk_commit();
+        } else {  // coalesced 16-byte stores: the stage is free again when this iteration ends
+          const float4* src4 = reinterpret_cast<const float4*>(zt + a0);
+          float4* dst4 = reinterpret_cast<float4*>(wg + a0);
+          for (int v = lane; v < (len >> 2); v += 32) dst4[v] = src4[v];
+        }
         if (lane < a0) wg[lane] = zt[lane];
         const int t0 = a0 + len;
         if (t0 + lane < n_s) wg[t0 + lane] = zt[t0 + lane];
+        if (!kOutByTma) __syncwarp();
       } else {
         __syncwarp();
       }
@@ -290,7 +304,7 @@ composite_fwd_span_packed_kernel(const PackedArgs a) {
     cur = nxt;
     cur_tile = nxt_tile;
   }
-  if (kWriteW && lane == 0) bulk_wait_all<0>();
+  if (kOutByTma && kWriteW && lane == 0) bulk_wait_all<0>();
 }
 
 __global__ void __launch_bounds__(kPkWarps * 32)
@@ -326,7 +340,7 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
     int64_t nxt_tile = -1;
     if (nxt.kind == kItemTile) {
       nxt_tile = tiles++;
-      if (lane == 0) bulk_wait_read<1>();
+      if (kOutByTma && lane == 0) bulk_wait_read<1>();
       issue_tile(pipe, (int)(nxt_tile % kPkStages), a, nxt, rel_end, lane);
     }
     r_next += nxt.nr;
@@ -347,11 +361,19 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
       float4* rg = pipe.rgbs_stage(st) + run.s0;
       float* zs = pipe.z_stage(st) + shift + run.s0;
       bwd_tile_simple<kPkL, false>(a.sp, run, rg, zs, gA, gB, lane);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        bulk_s2g(a.sp.d_rgbs + cur.sb * 4, pipe.rgbs_stage(st), (uint32_t)n_s * 16u);
-        bulk_commit();
+      if (kOutByTma) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(a.sp.d_rgbs + cur.sb * 4, pipe.rgbs_stage(st), (uint32_t)n_s * 16u);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        const float4* src4 = pipe.rgbs_stage(st);
+        float4* dst4 = d4 + cur.sb;
+        for (int v = lane; v < n_s; v += 32) dst4[v] = src4[v];  // 512-byte coalesced rows
+        __syncwarp();
       }
     } else if (cur.n_s > 0) {
       wray_bwd_ray<false>(rgbs4, a.sp.z, cur.sb, cur.n_s, cur.r0, a.sp.g_rgb, a.sp.g_depth, nullptr,
@@ -360,7 +382,7 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
     cur = nxt;
     cur_tile = nxt_tile;
   }
-  if (lane == 0) bulk_wait_all<0>();
+  if (kOutByTma && lane == 0) bulk_wait_all<0>();
 }
 
 // ---- host side -----------------------------------------------------------------------
