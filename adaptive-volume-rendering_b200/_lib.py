@@ -36,6 +36,7 @@ PROTOTYPES = {
     "avr_composite_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P]),
     "avr_composite_fwd_gather": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,
                                          ctypes.POINTER(c_void_p), c_int, c_int64, _P]),
+    "avr_composite_fwd_gather_multicast": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
     "avr_gather_push_rows": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int64, c_int64, _P]),
     "avr_composite_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
     "avr_composite_fwd_packed": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_float, _P, _P, _P, _P]),

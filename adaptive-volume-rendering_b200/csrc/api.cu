@@ -191,6 +191,20 @@ int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t R, int K
                                    peer_gathered, n_peers, row0);
 }
 
+int avr_composite_fwd_gather_multicast(const float* rgbs, const float* z, int64_t R, int K, int white_back,
+                                       float infinity, float* w, float* rgb, float* depth, void* multicast_gathered,
+                                       int64_t row0, avr_stream_t stream) {
+  if (R < 0 || K < 1 || row0 < 0 || !multicast_gathered || !aligned16(multicast_gathered)) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!rgbs || !z || !rgb || !depth || !aligned16(rgbs)) return AVR_ERR_BAD_ARG;
+  SpanPlan plan;
+  if (g_force_generic.load() || !span_plan(R, K, rgbs, z, &plan) || plan.main_rays != R || (w && !aligned16(w)))
+    return AVR_ERR_UNSUPPORTED;
+  void* one[1] = {multicast_gathered};
+  return launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, as_stream(stream), one, 1,
+                                   row0, true);
+}
+
 int avr_gather_push_rows(void* const* peer_gathered, int n_peers, int self, int64_t row0, int64_t rows,
                          avr_stream_t stream) {
   if (!peer_gathered || n_peers < 1 || self < 0 || self >= n_peers || row0 < 0 || rows < 0) return AVR_ERR_BAD_ARG;

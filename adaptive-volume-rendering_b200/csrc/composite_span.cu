@@ -524,10 +524,12 @@ static SpanArgs make_args(const SpanPlan& plan, int K, int white_back, float inf
 
 int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
-                              cudaStream_t stream, void* const* peers, int n_peers, int64_t peer_row0) {
+                              cudaStream_t stream, void* const* peers, int n_peers, int64_t peer_row0,
+                              bool multicast) {
   SpanArgs a = make_args(plan, K, white_back, infinity);
   if (n_peers > kMaxPeers) return AVR_ERR_UNSUPPORTED;
   a.n_peers = n_peers;
+  a.peers_multicast = multicast ? 1 : 0;
   a.peer_row0 = peer_row0;
   for (int p = 0; p < n_peers; ++p) a.peers[p] = reinterpret_cast<float4*>(peers[p]);
   a.rgbs = rgbs;

@@ -34,7 +34,7 @@ bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan
 int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
                               cudaStream_t stream, void* const* peers = nullptr, int n_peers = 0,
-                              int64_t peer_row0 = 0);
+                              int64_t peer_row0 = 0, bool multicast = false);
 int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
                               float* d_z /* nullable; needs K > plan.L */, cudaStream_t stream);

@@ -40,6 +40,7 @@ struct SpanArgs {
   // NVLink-packet-rate bound: 1.23 vs 0.93 ms per step measured on 2 GPUs).
   float4* peers[kMaxPeers];
   int n_peers;
+  int peers_multicast;    // peers[0] is an NVSwitch multicast address: one multimem.st reaches every rank
   int64_t peer_row0;
 };
 
@@ -157,7 +158,15 @@ __device__ __forceinline__ void flush_rays_to_peers(const SpanArgs& a, int64_t l
   for (int64_t ray = lo + lane; ray < hi; ray += 32) {
     const float4 v = make_float4(__ldcg(a.rgb + ray * 3), __ldcg(a.rgb + ray * 3 + 1), __ldcg(a.rgb + ray * 3 + 2),
                                  __ldcg(a.depth + ray));
-    for (int p = 0; p < a.n_peers; ++p) a.peers[p][a.peer_row0 + ray] = v;
+    if (a.peers_multicast) {
+      // the switch replicates the store into every rank's buffer (this rank's included): 16 B per ray
+      // leave the GPU instead of 16 B per ray and peer
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a.peers[0] + a.peer_row0 + ray),
+                   "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    } else {
+      for (int p = 0; p < a.n_peers; ++p) a.peers[p][a.peer_row0 + ray] = v;
+    }
   }
 }
 

@@ -120,6 +120,12 @@ class FusedGather:
             self.handle = symm_mem.rendezvous(self.gathered, self.group)
             ptrs = [int(p) for p in self.handle.buffer_ptrs]
             self._ptr_array = (ctypes.c_void_p * self.world)(*ptrs)
+            # NVSwitch multicast mapping of the same buffers (0 when the box has no NVLS support)
+            import os
+
+            self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+            if os.environ.get("AVR_GATHER_MULTICAST", "1") == "0":
+                self.multicast_ptr = 0
             self.handle.barrier()
             self.available = True
         except Exception as exc:  # pragma: no cover - depends on the box
@@ -142,14 +148,20 @@ class FusedGather:
         rgb = torch.empty(r, 3, dtype=torch.float32, device=dev)
         depth = torch.empty(r, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            rc = _lib.load().avr_composite_fwd_gather(
-                rgbs.data_ptr(), z.data_ptr(), r, k, int(bool(white_back)), float(infinity),
-                None if w is None else w.data_ptr(), rgb.data_ptr(), depth.data_ptr(),
-                self._ptr_array, self.world, self.rank * self.rays_local, _stream(z))
+            rc = self.launch(_lib.load(), rgbs.data_ptr(), z.data_ptr(), r, k, int(bool(white_back)), float(infinity),
+                             None if w is None else w.data_ptr(), rgb.data_ptr(), depth.data_ptr(), _stream(z))
         if rc == -4:   # AVR_ERR_UNSUPPORTED
             return None
         _lib.check(rc, "avr_composite_fwd_gather")
         return rgb, depth, w
+
+    def launch(self, lib, rgbs_ptr, z_ptr, r, k, white_back, infinity, w_ptr, rgb_ptr, depth_ptr, stream):
+        """The raw C-ABI call: multicast stores when the box supports them, per-peer stores otherwise."""
+        if self.multicast_ptr:
+            return lib.avr_composite_fwd_gather_multicast(rgbs_ptr, z_ptr, r, k, white_back, infinity, w_ptr, rgb_ptr,
+                                                          depth_ptr, self.multicast_ptr, self.rank * self.rays_local, stream)
+        return lib.avr_composite_fwd_gather(rgbs_ptr, z_ptr, r, k, white_back, infinity, w_ptr, rgb_ptr, depth_ptr,
+                                            self._ptr_array, self.world, self.rank * self.rays_local, stream)
 
     def finish(self):
         """Cross-rank barrier (stream-ordered): afterwards every rank's ``gathered`` holds all rays."""

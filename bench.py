@@ -336,7 +336,9 @@ def main():
         "NCCL all_gather_into_tensor between forward and backward" if fused is None else
         "forward kernel packs local rows into a double-buffered symmetric-memory slot; copy-engine pushes over NVLink + "
         "cross-rank barrier on a side stream, overlapped with backward and the next step (all waited inside the timed region)"
-        if ce else "fused into the forward kernel (coalesced 512-byte peer stores over NVLink into symmetric memory) + barrier")
+        if ce else ("fused into the forward kernel (512-byte multimem.st through the NVSwitch multicast mapping of the "
+                    "symmetric-memory buffers) + barrier" if getattr(fused, "multicast_ptr", 0) else
+                    "fused into the forward kernel (coalesced 512-byte peer stores over NVLink into symmetric memory) + barrier"))
 
     def fwd_fused():
         if ce:
@@ -344,8 +346,8 @@ def main():
             rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
                                               depth.data_ptr(), target, n_t, row0, sp)
         else:
-            rc = lib.avr_composite_fwd_gather(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
-                                              depth.data_ptr(), fused._ptr_array, fused.world, fused.rank * rays, sp)
+            rc = fused.launch(lib, x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(),
+                              depth.data_ptr(), sp)
         assert rc == 0, (rc, lib.avr_last_cuda_error())
         if ce:
             fused.push_async()

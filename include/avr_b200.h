@@ -148,6 +148,15 @@ AVR_API int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t 
                                      void* const* peer_gathered, int n_peers, int64_t row0,
                                      avr_stream_t stream);
 
+/* Same, through an NVSwitch MULTICAST mapping of the gathered buffers (e.g. the multicast_ptr of a
+ * torch symmetric-memory allocation on an NVLS-capable box): every 32 finished rays leave as one
+ * 512-byte multimem.st that the switch replicates into every rank's buffer, this rank's included —
+ * 16 bytes per ray cross the GPU's links instead of 16 bytes per ray and peer. */
+AVR_API int avr_composite_fwd_gather_multicast(const float* rgbs, const float* z, int64_t R, int K,
+                                               int white_back, float infinity,
+                                               float* w, float* rgb, float* depth,
+                                               void* multicast_gathered, int64_t row0, avr_stream_t stream);
+
 /* All-gather by the copy engines (multi-GPU): copy rows [row0, row0 + rows) of this rank's
  * gathered buffer `peer_gathered[self]` into the same rows of every other rank's buffer
  * (one cudaMemcpyAsync per peer over NVLink: no SM is involved, so the transfer overlaps a
