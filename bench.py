@@ -371,9 +371,10 @@ def main():
             # kernel (it holds every SM) and measured 2.6x slower than this
             avr_dist.all_gather_outputs(rgb, depth)
         bwd()
-        if fused is not None and not ce:
+        if fused is not None and not ce and not no_barrier:
             fused.finish()
 
+    no_barrier = os.environ.get("AVR_GATHER_NO_BARRIER", "0") == "1"   # diagnostic: kernel-only cost of the fused gather
     for _ in range(args.warmup):
         step()
     if ce:
@@ -407,7 +408,7 @@ def main():
                 ev[i][1].record(stream)
             bwd()
             ev[i][2].record(stream)
-            if fused is not None and not ce:
+            if fused is not None and not ce and not no_barrier:
                 fused.finish()
         if ce:
             fused.wait_all()     # every slot's pushes + barrier have completed before the clock stops
@@ -421,7 +422,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     bwd_ms = sorted(ev[i][1].elapsed_time(ev[i][2]) for i in range(args.steps))
-    fwd_ms = sorted(ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)) if dist is None else None
+    fwd_ms = sorted(ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)) if (dist is None or fused is not None or args.gather == "none") else None
     bwd_avg = sum(bwd_ms) / len(bwd_ms)
 
     ms_per_step = total_ms / args.steps
@@ -445,7 +446,8 @@ def main():
                                  "bound": "hbm", "achieved": fb * rays / (fwd_avg * 1e-3) / 1e9, "peak": peak,
                                  "unit": "GB/s", "frac": fb * rays / (fwd_avg * 1e-3) / 1e9 / peak,
                                  "avg_launch_ms": fwd_avg, "min_launch_ms": fwd_ms[0]}
-        extra["step_hbm_frac"] = (fb + bb) * rays / (ms_per_step * 1e-3) / 1e9 / peak
+        if dist is None:
+            extra["step_hbm_frac"] = (fb + bb) * rays / (ms_per_step * 1e-3) / 1e9 / peak
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory both ways)
     e2e = None
