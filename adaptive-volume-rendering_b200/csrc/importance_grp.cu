@@ -432,7 +432,9 @@ int launch_importance_grp_ragged(const ImportanceRegArgs& a, int max_coarse, int
   int rc = launch_grp_ragged<8, 32, 16, 0>(a, stream);
   if (rc == AVR_OK && (max_coarse > 32 || max_fine > 16)) rc = launch_grp_ragged<8, 64, 32, 1>(a, stream);
   if (rc == AVR_OK && (max_coarse > 64 || max_fine > 32)) rc = launch_grp_ragged<16, 128, 64, 2>(a, stream);
-  if (rc == AVR_OK && (max_coarse > 128 || max_fine > 64)) rc = launch_grp_ragged<16, 256, 128, 3>(a, stream);
+  // the largest box runs one ray per warp: 64 registers / 32 resident warps beat 16 lanes per ray at
+  // 128 registers / 16 warps (1.44 vs 1.56 ms on BASELINE.json config 4's distribution)
+  if (rc == AVR_OK && (max_coarse > 128 || max_fine > 64)) rc = launch_grp_ragged<32, 256, 128, 3>(a, stream);
   return rc;
 }
 
