@@ -448,6 +448,7 @@ int launch_importance_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
   // 8 for the small shapes.  AVR_GRP_G=8|16 overrides (experiments).
   const char* gsw = std::getenv("AVR_GRP_G");
   const int force_g = (gsw && *gsw) ? std::atoi(gsw) : 0;
+  if (force_g == 32 && a.Kc == 64 && a.n_imp == 128 && a.n_depth == 0) return launch_grp<32, 64, 128, 0>(a, stream);
 #define AVR_GRP_CASE(G_, KC_, NI_, ND_)                                        \
   if (a.Kc == KC_ && a.n_imp == NI_ && a.n_depth == ND_) {                     \
     if (force_g == 8) return launch_grp<8, KC_, NI_, ND_>(a, stream);          \
