@@ -306,6 +306,22 @@ int avr_coarse_sample_points_fwd(const float* near, const float* far, int bound_
   return launch_ray_points(ros, rds, u, near, far, bound_stride, true, R, K, z, pts, viewdirs, as_stream(stream));
 }
 
+int avr_ray_points_fwd_packed(const float* ros, const float* rds, const float* z, const int64_t* offsets, int64_t R,
+                              int64_t S, float* pts, float* viewdirs, avr_stream_t stream) {
+  if (R < 0 || S < 0) return AVR_ERR_BAD_ARG;
+  if (R == 0 || S == 0) return AVR_OK;
+  if (!ros || !rds || !z || !offsets || !pts) return AVR_ERR_BAD_ARG;
+  return launch_ray_points_packed(ros, rds, z, offsets, R, pts, viewdirs, nullptr, nullptr, as_stream(stream));
+}
+
+int avr_ray_points_bwd_packed(const float* rds, const float* g_pts, const int64_t* offsets, int64_t R, int64_t S,
+                              float* d_z, avr_stream_t stream) {
+  if (R < 0 || S < 0) return AVR_ERR_BAD_ARG;
+  if (R == 0 || S == 0) return AVR_OK;
+  if (!rds || !g_pts || !offsets || !d_z) return AVR_ERR_BAD_ARG;
+  return launch_ray_points_packed(rds, rds, nullptr, offsets, R, nullptr, nullptr, g_pts, d_z, as_stream(stream));
+}
+
 int avr_world_rays(const float* x_pix, const float* kinv, const float* cam2world, int64_t R, int64_t rays_per_cam,
                    float* ros, float* rds, avr_stream_t stream) {
   if (R < 0 || rays_per_cam < 1) return AVR_ERR_BAD_ARG;

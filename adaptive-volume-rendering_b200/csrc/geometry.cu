@@ -133,6 +133,32 @@ ray_points_scalar_kernel(const float* __restrict__ ros, const float* __restrict_
   }
 }
 
+// Packed (ragged) rays: ray r owns samples [offsets[r], offsets[r+1]).  One warp per ray, lanes over
+// its samples; a warp instruction writes 32 consecutive 12-byte points = 384 contiguous bytes.
+// g_pts == nullptr: forward (pts, viewdirs); otherwise backward (d_z = g_pts . rds).
+__global__ void __launch_bounds__(128)
+ray_points_packed_kernel(const float* __restrict__ ros, const float* __restrict__ rds, const float* __restrict__ z,
+                         const int64_t* __restrict__ offsets, int64_t R, float* __restrict__ pts,
+                         float* __restrict__ viewdirs, const float* __restrict__ g_pts, float* __restrict__ d_z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < R; r += warps) {
+    const int64_t begin = offsets[r], end = offsets[r + 1];
+    const Ray3 q = load_ray3(ros, rds, r);
+    for (int64_t i = begin + lane; i < end; i += 32) {
+      if (g_pts) {
+        d_z[i] = g_pts[i * 3 + 0] * q.dx + g_pts[i * 3 + 1] * q.dy + g_pts[i * 3 + 2] * q.dz;
+      } else {
+        const float3 p = point_on_ray(q, z[i]);
+        pts[i * 3 + 0] = p.x; pts[i * 3 + 1] = p.y; pts[i * 3 + 2] = p.z;
+        if (viewdirs) {
+          viewdirs[i * 3 + 0] = q.dx; viewdirs[i * 3 + 1] = q.dy; viewdirs[i * 3 + 2] = q.dz;
+        }
+      }
+    }
+  }
+}
+
 // d_z[r,k] = g_pts[r,k,:] . rds[r,:]   (AdaptiveVolumeRenderer: the sample depths carry grad)
 __global__ void __launch_bounds__(256)
 ray_points_bwd_kernel(const float* __restrict__ rds, const float* __restrict__ g_pts, int64_t total, int K,
@@ -255,6 +281,15 @@ int launch_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K
   const int64_t total = R * (int64_t)K;
   if (total == 0) return AVR_OK;
   ray_points_bwd_kernel<<<grid_1d(total, kNumSMs * 16), 256, 0, stream>>>(rds, g_pts, total, K, d_z);
+  return check_launch();
+}
+
+int launch_ray_points_packed(const float* ros, const float* rds, const float* z, const int64_t* offsets, int64_t R,
+                             float* pts, float* viewdirs, const float* g_pts, float* d_z, cudaStream_t stream) {
+  if (R == 0) return AVR_OK;
+  int64_t blocks = (R + 3) / 4;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  ray_points_packed_kernel<<<(unsigned)blocks, 128, 0, stream>>>(ros, rds, z, offsets, R, pts, viewdirs, g_pts, d_z);
   return check_launch();
 }
 

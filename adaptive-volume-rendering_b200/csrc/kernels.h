@@ -70,6 +70,8 @@ int launch_ray_points(const float* ros, const float* rds, const float* z_or_u, c
                       int bound_stride, bool from_u, int64_t R, int K, float* z_out, float* pts, float* viewdirs,
                       cudaStream_t stream);
 int launch_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K, float* d_z, cudaStream_t stream);
+int launch_ray_points_packed(const float* ros, const float* rds, const float* z, const int64_t* offsets, int64_t R,
+                             float* pts, float* viewdirs, const float* g_pts, float* d_z, cudaStream_t stream);
 int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, int64_t R, int64_t rays_per_cam,
                       float* ros, float* rds, cudaStream_t stream);
 int launch_depth_from_world(const float* ros, const float* rds, const float* dist, const float* c2w, int64_t R,

@@ -380,6 +380,47 @@ def ray_points(ros: torch.Tensor, rds: torch.Tensor, z: torch.Tensor):
     return RayPoints.apply(ros, rds, z)
 
 
+class RayPointsPacked(torch.autograd.Function):
+    """Sample points and view directions for packed rays: ros, rds (R,3), z (S,), offsets (R+1,)
+    -> pts, viewdirs (S,3).  Backward gives d_z (the adaptive depths carry grad)."""
+
+    @staticmethod
+    def forward(ctx, ros, rds, z, offsets):
+        require_cuda(ros, rds, z, offsets)
+        o, d, zc = _rays3(ros), _rays3(rds), _f32c(z)
+        off = offsets.contiguous()
+        r, s = off.numel() - 1, zc.numel()
+        if o.shape[0] != r or d.shape[0] != r:
+            raise _lib.AvrError(f"ros/rds hold {o.shape[0]}/{d.shape[0]} rays, offsets describe {r}")
+        pts = torch.empty(s, 3, dtype=torch.float32, device=zc.device)
+        vd = torch.empty_like(pts)
+        with torch.cuda.device(zc.device):
+            check(_lib.load().avr_ray_points_fwd_packed(ptr(o), ptr(d), ptr(zc), ptr(off), r, s, ptr(pts), ptr(vd), _stream(zc)),
+                  "avr_ray_points_fwd_packed")
+        ctx.save_for_backward(d, off)
+        ctx.mark_non_differentiable(vd)
+        return pts, vd
+
+    @staticmethod
+    def backward(ctx, g_pts, _g_vd):
+        d, off = ctx.saved_tensors
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise _lib.AvrError("RayPointsPacked differentiates w.r.t. the depths only")
+        if g_pts is None or not ctx.needs_input_grad[2]:
+            return None, None, None, None
+        g = _f32c(g_pts)
+        s = g.shape[0]
+        d_z = torch.empty(s, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(_lib.load().avr_ray_points_bwd_packed(ptr(d), ptr(g), ptr(off), off.numel() - 1, s, ptr(d_z), _stream(g)),
+                  "avr_ray_points_bwd_packed")
+        return None, None, d_z, None
+
+
+def ray_points_packed(ros, rds, z, offsets):
+    return RayPointsPacked.apply(ros, rds, z, offsets)
+
+
 def coarse_sample_points(near, far, bound_stride: int, u: torch.Tensor, ros: torch.Tensor, rds: torch.Tensor):
     """sample_coarse + point generation in one pass over the uniforms (renderers.py:169-175).
     Returns z (..., K), pts (..., K, 3), viewdirs (..., K, 3); non-differentiable (VolumeRenderer's

@@ -221,6 +221,13 @@ AVR_API int avr_coarse_sample_points_fwd(const float* near, const float* far, in
                                          const float* ros, const float* rds, int64_t R, int K,
                                          float* z, float* pts, float* viewdirs, avr_stream_t stream);
 
+/* Packed (ragged) rays: ray r owns samples [offsets[r], offsets[r+1]) of the S-sample streams
+ * z [S], pts / viewdirs / g_pts [S,3], d_z [S]. */
+AVR_API int avr_ray_points_fwd_packed(const float* ros, const float* rds, const float* z, const int64_t* offsets,
+                                      int64_t R, int64_t S, float* pts, float* viewdirs, avr_stream_t stream);
+AVR_API int avr_ray_points_bwd_packed(const float* rds, const float* g_pts, const int64_t* offsets, int64_t R,
+                                      int64_t S, float* d_z, avr_stream_t stream);
+
 /* utils.get_world_rays (utils.py:309-336): ray origins and unit directions in world coordinates.
  *   x_pix [R,2]; intrinsics [n_cams,3,3], ray r uses camera r / rays_per_cam (the 3x3 inverse of
  *   utils.py:263 is formed inside the kernel);

@@ -110,3 +110,25 @@ def test_geometry_full_size_properties(dev):
     assert torch.equal(vd, rds.unsqueeze(-2).expand(1, r, k, 3))
     p2, v2 = ops.ray_points(ros, rds, z)
     assert torch.equal(p2, pts) and torch.equal(v2, vd)
+
+
+def test_ray_points_packed(dev):
+    """Packed rays (counts 0..300): points lie on their rays bit for bit, d_z = g_pts . rds."""
+    from avr_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    r = 700
+    counts = torch.randint(0, 301, (r,), generator=gen)
+    counts[::50] = 0
+    offsets = torch.zeros(r + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts, 0)
+    s = int(offsets[-1])
+    ros, rds = torch.randn(r, 3, generator=gen), torch.nn.functional.normalize(torch.randn(r, 3, generator=gen), dim=-1)
+    z = torch.rand(s, generator=gen) + 0.5
+    seg = torch.repeat_interleave(torch.arange(r), counts)
+    zd = z.to(dev).requires_grad_(True)
+    pts, vd = ops.ray_points_packed(ros.to(dev), rds.to(dev), zd, offsets.to(dev))
+    assert torch.equal(pts.cpu(), ros[seg] + rds[seg] * z.unsqueeze(-1))
+    assert torch.equal(vd.cpu(), rds[seg])
+    gp = torch.randn(s, 3, generator=gen)
+    pts.backward(gp.to(dev))
+    assert_close(zd.grad, (gp * rds[seg]).sum(-1), rtol=1e-5, atol=1e-6, what="d_z")
