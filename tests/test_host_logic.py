@@ -1,0 +1,69 @@
+"""Host-side logic that needs no GPU: how the reference's tensors are mapped onto the kernels'
+layouts (zero-copy recovery of the radiance field's buffer, scalar vs per-ray bounds), ray sharding,
+the ray classes of the packed importance sampler, and the refusal to run on CPU."""
+import pytest
+import torch
+
+
+def test_as_rgbs_recovers_the_field_buffer_without_a_copy():
+    from avr_b200.renderers import _as_rgbs
+    out = torch.rand(2, 5 * 7, 4)                       # the field's (SB, R*K, 4) output
+    x = out.view(2, 5, 7, 4)
+    sigma, rad = x[..., 3:4], x[..., :3]                # how the reference slices it (renderers.py:177-178)
+    rgbs = _as_rgbs(sigma, rad)
+    assert rgbs.data_ptr() == out.data_ptr() and rgbs.shape == (2, 5, 7, 4)
+    # anything else is interleaved into a fresh buffer with the same values
+    rgbs2 = _as_rgbs(sigma.clone(), rad.clone())
+    assert rgbs2.data_ptr() != out.data_ptr() and torch.equal(rgbs2, x)
+    # slices of two different buffers must not be mistaken for one
+    other = torch.rand(2, 5, 7, 4)
+    assert torch.equal(_as_rgbs(other[..., 3:4], rad), torch.cat([rad, other[..., 3:4]], -1))
+
+
+def test_bounds_scalar_and_per_ray():
+    from avr_b200 import ops
+    near = torch.tensor([0.8]).expand(3, 11)            # VolumeRenderer: stride-0 expand of one element (renderers.py:169)
+    far = torch.tensor([1.8]).expand(3, 11)
+    n, f, stride = ops._bounds(near, far, 33)
+    assert stride == 0 and n.numel() == 1 and f.numel() == 1 and float(n) == pytest.approx(0.8)
+    d = torch.rand(3, 11)
+    n, f, stride = ops._bounds(d - 0.15, d + 0.15, 33)  # AdaptiveVolumeRenderer: per-ray bounds
+    assert stride == 1 and n.shape == (33,) and n.is_contiguous()
+    n, f, stride = ops._bounds(near, d + 0.15, 33)       # mixed: the scalar side is broadcast
+    assert stride == 1 and torch.equal(n, torch.full((33,), 0.8))
+    with pytest.raises(Exception):
+        ops._bounds(d[:, :5], d, 33)
+
+
+def test_cpu_tensors_are_refused():
+    import avr_b200
+    from avr_b200 import ops
+    with pytest.raises(avr_b200.AvrError):
+        ops.composite(torch.rand(4, 8, 4), torch.rand(4, 8))
+    with pytest.raises(avr_b200.AvrError):
+        avr_b200.sample_coarse(torch.rand(1, 4), torch.rand(1, 4) + 1, 8, u=torch.rand(1, 4, 8))
+    with pytest.raises(avr_b200.AvrError):
+        ops.ray_points(torch.rand(1, 4, 3), torch.rand(1, 4, 3), torch.rand(1, 4, 8))
+    ren = avr_b200.VolumeRenderer(0.8, 1.8, 8, 4, 2, 0.01)
+    assert list(ren.state_dict()) == []
+    with pytest.raises(avr_b200.AvrError):
+        ren(torch.eye(4).expand(1, 4, 4, 4), torch.eye(3)[None], torch.rand(1, 4, 2), lambda *a, **k: None)
+
+
+def test_fp64_is_refused():
+    from avr_b200 import ops, AvrError
+    with pytest.raises(AvrError):
+        ops._f32c(torch.rand(3, dtype=torch.float64))
+
+
+def test_shard_bounds_packed_balances_samples():
+    from avr_b200.dist import shard_bounds, shard_bounds_packed
+    counts = torch.tensor([1] * 50 + [100] * 50)
+    offsets = torch.zeros(101, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts, 0)
+    cuts = [shard_bounds_packed(offsets, 4, r) for r in range(4)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == 100
+    assert all(cuts[i][1] == cuts[i + 1][0] for i in range(3))
+    per_rank = [int(offsets[b] - offsets[a]) for a, b in cuts]
+    assert max(per_rank) - min(per_rank) <= 200           # within two long rays of each other
+    assert [shard_bounds(10, 3, r) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
