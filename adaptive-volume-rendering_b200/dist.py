@@ -123,8 +123,10 @@ class FusedGather:
             # NVSwitch multicast mapping of the same buffers (0 when the box has no NVLS support)
             import os
 
+            # opt-in (AVR_GATHER_MULTICAST=1): measured identical to the per-peer stores at 2 and 4 GPUs
+            # (profiles/r01_multi_gpu.md) and not yet run at 8, so the per-peer path stays the default
             self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
-            if os.environ.get("AVR_GATHER_MULTICAST", "1") == "0":
+            if os.environ.get("AVR_GATHER_MULTICAST", "0") != "1":
                 self.multicast_ptr = 0
             self.handle.barrier()
             self.available = True
