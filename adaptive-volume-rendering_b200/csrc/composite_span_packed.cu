@@ -18,7 +18,10 @@
 //     by the same warp with the warp-per-ray routine straight from global memory;
 //   * z and w slices start at arbitrary sample offsets: the stage keeps the global 16-byte
 //     phase (bulk copies cover the aligned interior, up to 3 elements at either end go
-//     through ordinary loads/stores).
+//     through ordinary loads/stores);
+//   * the ring has two slots and results (w, d_rgbs) leave by ordinary coalesced 16-byte stores
+//     inside the iteration instead of bulk stores: these kernels are bound by per-warp
+//     instruction latency, so 12 resident warps/SM (2 x 8.6 KB each) beat 8 with a third slot.
 #include <climits>
 #include <cstdlib>
 
