@@ -435,6 +435,21 @@ bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan
       best_nr = nr;
     }
   }
+  // L = 5 fills best for short rays (K = 20, 32, 40 ...) but its 160-sample tiles are mostly per-tile
+  // overhead: a larger run that fills within 5 % is faster (K = 20: fwd 0.083 -> 0.069 ms, 81 -> 98 %
+  // of the roofline with L = 9)
+  if (best_L == 5 && !forced && K > 9) {
+    for (int L : {9, 7}) {
+      int nr = (32 * L) / K;
+      while (nr > 0 && ((int64_t)nr * K) % 4 != 0) --nr;
+      if (nr > 0 && (double)nr * K / (32 * L) >= best_util - 0.05) {
+        best_util = (double)nr * K / (32 * L);
+        best_L = L;
+        best_nr = nr;
+        break;
+      }
+    }
+  }
   if (best_L == 0 || best_util < 0.5) return false;
   int64_t tiles = R / best_nr;
   if (tiles < 1) return false;
