@@ -146,7 +146,7 @@ class VolumeRenderer(nn.Module):
         # coarse pass: depths, sample points and the view-direction copy in one kernel  # :169-175
         z_c, pts, vd = ops.coarse_sample_points(near, far, 0, u_c, ros, rds)
         out = radiance_field(pts.view(sb, -1, 3), viewdirs=vd.view(sb, -1, 3), coarse=True)   # :173
-        rgb_c, _dist_c, w_c = ops.composite(out.view(sb, num_rays, kc, 4), z_c, white_back, 1.8, want_w=True)  # :180
+        rgb_c, _dist_c, w_c = ops.composite(out.reshape(sb, num_rays, kc, 4), z_c, white_back, 1.8, want_w=True)  # :180
 
         # importance + "depth" resampling, merged and sorted in one kernel             # :252-258
         z_s = ops.importance_sample(w_c, near, far, u_cdf, u_bin, z_coarse=z_c,
@@ -155,7 +155,7 @@ class VolumeRenderer(nn.Module):
         k = kc + self.n_fine
         pts, vd = ops.ray_points(ros, rds, z_s)                                       # :260-265
         out = radiance_field(pts.view(sb, -1, 3), viewdirs=vd.view(sb, -1, 3), coarse=False)  # :263
-        rgb_f, dist_f, _ = ops.composite(out.view(sb, num_rays, k, 4), z_s, white_back, 1.8, want_w=False)  # :270
+        rgb_f, dist_f, _ = ops.composite(out.reshape(sb, num_rays, k, 4), z_s, white_back, 1.8, want_w=False)  # :270
 
         depth = depth_from_world(ros, cam2world, rds=rds, dist=dist_f)                # :274-275
         return rgb_c, rgb_f, depth, depth
