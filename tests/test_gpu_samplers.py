@@ -130,7 +130,7 @@ def test_sample_fine_signature_and_seed(dev):
 
 
 @pytest.mark.parametrize("kc,n,nd", [(64, 16, 16), (64, 128, 0), (32, 8, 8), (20, 5, 3), (200, 300, 12), (1, 1, 1),
-                                     (128, 64, 0), (96, 250, 6), (300, 100, 20), (33, 31, 0)])
+                                     (128, 64, 0), (96, 250, 6), (300, 100, 20), (33, 31, 0), (64, 0, 16), (32, 8, 8)])
 def test_merge_is_exact_sort(kc, n, nd, dev, family):
     from avr_b200 import ops
     g = torch.Generator().manual_seed(kc * 7 + n)
