@@ -37,7 +37,7 @@ namespace avr {
 #define AVR_PK_L 13
 #endif
 #ifndef AVR_PK_WARPS
-#define AVR_PK_WARPS 2
+#define AVR_PK_WARPS 1
 #endif
 #ifndef AVR_PK_STAGES
 #define AVR_PK_STAGES 2
@@ -48,8 +48,8 @@ constexpr int kPkStages = AVR_PK_STAGES;
 // Results leave the stage by bulk store when the ring has a third slot to cover the store's read of
 // shared memory; with a 2-slot ring they leave by ordinary coalesced stores inside the iteration, which
 // frees the slot at once.  The packed kernels are bound by per-warp instruction latency (a tile's walk is
-// one dependent chain; 0.25 IPC per warp), so what pays is resident warps: 2 x 8.6 KB per warp = 12
-// warps/SM instead of 8 (profiles/r01_span_sweep.md).
+// one dependent chain; 0.25 IPC per warp), so what pays is resident warps: 2 x 8.6 KB per warp = 13
+// warps/SM with one-warp CTAs instead of 8 (profiles/r01_span_sweep.md).
 constexpr bool kOutByTma = kPkStages >= 3;
 constexpr int kPkWarps = AVR_PK_WARPS;
 constexpr int kPkRgbsBytes = kPkC * 16;
