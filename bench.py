@@ -41,7 +41,7 @@ METRIC = "composite_fwd_bwd_rays_per_sec"
 UNIT = "rays/s"
 
 # (rays, K) -> DRAM bytes per launch of composite_bwd_span_kernel (ncu, round 1)
-NCU_TRAFFIC_BWD = {(1 << 20, 96): 2.031371e9 + 1.570049e9}
+NCU_TRAFFIC_BWD = {(1 << 20, 96): 2.030087e9 + 1.566062e9}
 
 WORKLOADS = {
     # name: (rays per GPU, samples per ray, description)
