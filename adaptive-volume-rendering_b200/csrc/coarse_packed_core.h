@@ -1,0 +1,229 @@
+// Packed (ragged) stratified coarse sampler: the per-lane work of
+// coarse_fwd_packed_flat_kernel (samplers.cu), written so that the SAME code also compiles as
+// plain host C++.  tests/test_host_kernel_cores.py builds it with g++ and walks a whole launch
+// lane by lane against the reference formula (renderers.py:12-14) — the kernel's index
+// arithmetic and its division shortcut are checked in the CPU suite, the GPU tests then only
+// have to confirm the launch itself.
+//
+// Layout of the work.  A warp owns a SEGMENT = 32 consecutive rays, i.e. one contiguous slice
+// [offsets[r0], offsets[r0+32]) of the packed u / z streams.  The 33 offsets (relative to the
+// segment start) and the rays' parameters go to shared memory once; after that the segment is
+// processed as a flat stream, four consecutive samples (one 16-byte access) per lane and step,
+// each lane finding its ray by a 5-probe search of the 33 offsets.  Rays of any length,
+// including empty ones, cost nothing beyond their samples: no lane idles on a short ray and
+// there is one dependent global-load chain per 32 rays instead of one per ray.
+//
+// Division.  z = near + span*(j/K) + (u*span)/K has two IEEE divisions per sample
+// (renderers.py:12, :14).  K is constant along a ray, so y = RN(1/K) is formed once per ray and
+// every a/K is  q0 = RN(a*y); r = fma(-K, q0, a); q = fma(r, y, q0)  — Markstein's sequence,
+// which returns the correctly rounded quotient whenever y is the correctly rounded reciprocal,
+// K's significand is not all ones and nothing leaves the normal range on the way.  Rays and
+// numerators outside those conditions take the IEEE division.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AVR_HD __device__ __forceinline__
+#else
+#include <math.h>
+#define AVR_HD inline
+#endif
+
+namespace avr {
+
+#if defined(__CUDACC__)
+AVR_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
+AVR_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
+AVR_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
+AVR_HD float f_div(float a, float b) { return __fdiv_rn(a, b); }
+AVR_HD float f_rcp(float a) { return __frcp_rn(a); }
+AVR_HD float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+// host build: -ffp-contract=off keeps these as single IEEE operations
+AVR_HD float f_mul(float a, float b) { return a * b; }
+AVR_HD float f_add(float a, float b) { return a + b; }
+AVR_HD float f_sub(float a, float b) { return a - b; }
+AVR_HD float f_div(float a, float b) { return a / b; }
+AVR_HD float f_rcp(float a) { return 1.0f / a; }
+AVR_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+constexpr int kSegRays = 32;                       // rays per segment (= lanes per warp)
+constexpr int kMarksteinMaxCount = (1 << 24) - 2;  // above: float(K) may have an all-ones significand
+
+// Per-ray constants of a segment (one 16-byte shared-memory load per ray change).
+struct CoarseRay {
+  float near, span, kf, rcp;  // rcp == 0 marks a ray that divides the IEEE way
+};
+
+struct CoarseSegment {
+  int rel[kSegRays + 1];  // offsets relative to the segment start; rel[32] = segment length
+  int pad[3];
+  CoarseRay ray[kSegRays];
+};
+
+// a / K given y = RN(1/K): Markstein's correction, the correctly rounded quotient under the
+// conditions checked by the caller (see the header comment)
+AVR_HD float div_markstein(float a, float kf, float y) {
+  const float q0 = f_mul(a, y);
+  const float r = f_fma(-kf, q0, a);
+  return f_fma(r, y, q0);
+}
+
+// renderers.py:12-14 for sample j of a ray.  The numerators are j (an integer below 2^24) and
+// u*span; the latter takes the shortcut only for magnitudes in [2^-90, 2^100) or zero, where no
+// intermediate of the sequence can leave the normal range (inf / nan / denormals divide the IEEE way).
+AVR_HD float coarse_depth_ray(const CoarseRay& p, int j, float u) {
+  const float jf = (float)j;
+  const float jit = f_mul(u, p.span);
+  const float aj = jit < 0.f ? -jit : jit;
+  const bool fast = p.rcp != 0.f && ((aj >= 0x1p-90f && aj < 0x1p100f) || aj == 0.f);
+  float bin, t;
+  if (fast) {
+    bin = div_markstein(jf, p.kf, p.rcp);
+    t = div_markstein(jit, p.kf, p.rcp);
+  } else {
+    bin = f_div(jf, p.kf);
+    t = f_div(jit, p.kf);
+  }
+  return f_add(f_add(p.near, f_mul(p.span, bin)), t);
+}
+
+// Phase 1, lane `lane` of the warp that owns rays [r0, r0+32): fill this lane's table entries.
+// Returns false when the segment cannot use 32-bit relative offsets (its caller then takes the
+// per-ray loop for the whole segment; warp-uniform after a vote).
+AVR_HD bool coarse_segment_build(int lane, int64_t r0, int64_t R, const int64_t* offsets, const float* near,
+                                 const float* far, int bound_stride, CoarseSegment* seg) {
+  const int64_t seg_begin = offsets[r0];
+  const int64_t r = r0 + lane < R ? r0 + lane : R;  // rays past the end are empty
+  const int64_t begin = offsets[r];
+  const int64_t end = offsets[r < R ? r + 1 : R];
+  const int64_t rel = begin - seg_begin;
+  const int64_t cnt = end - begin;
+  const bool ok = rel >= 0 && cnt >= 0 && (end - seg_begin) < (int64_t)0x7fffffff;
+  seg->rel[lane] = (int)rel;
+  if (lane == kSegRays - 1) seg->rel[kSegRays] = (int)(end - seg_begin);
+  CoarseRay p;
+  const int64_t b = bound_stride ? (r < R ? r : R - 1) : 0;
+  p.near = near[b];
+  p.span = f_sub(far[b], p.near);
+  p.kf = (float)cnt;
+  p.rcp = (cnt > 0 && cnt <= kMarksteinMaxCount) ? f_rcp(p.kf) : 0.f;
+  seg->ray[lane] = p;
+  return ok;
+}
+
+// largest k in [0, 31] with rel[k] <= i  (0 <= i < rel[32]); with empty rays (equal entries)
+// this is the ray that actually holds sample i
+AVR_HD int coarse_segment_find(const CoarseSegment* seg, int i) {
+  int k = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int step = kSegRays / 2; step > 0; step >>= 1)
+    if (seg->rel[k + step] <= i) k += step;
+  return k;
+}
+
+// Phase 2, lane `lane`: samples of the segment, four consecutive ones (one aligned 16-byte
+// access of the packed streams) per group.  A group is described by the relative index i0 of
+// its first slot; slots outside [0, seg_len) belong to the neighbouring segments and are
+// neither read nor written.
+struct CoarseGroup {
+  int i0, lo, hi;  // slots [lo, hi) of [i0, i0+4) are this segment's
+  bool full;       // all four, and the streams are 16-byte aligned: one vector access
+  float u[4];
+};
+
+AVR_HD CoarseGroup coarse_group_load(int g, int head, int seg_len, const float* ua, bool vec_ok) {
+  CoarseGroup c;
+  c.i0 = 4 * g - head;
+  c.lo = c.i0 < 0 ? 0 : c.i0;
+  c.hi = c.i0 + 4 < seg_len ? c.i0 + 4 : seg_len;
+  c.full = vec_ok && (c.hi - c.lo == 4);
+  c.u[0] = c.u[1] = c.u[2] = c.u[3] = 0.f;
+  if (c.full) {
+#if defined(__CUDACC__)
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(ua + 4 * g));
+    c.u[0] = q.x; c.u[1] = q.y; c.u[2] = q.z; c.u[3] = q.w;
+#else
+    for (int q = 0; q < 4; ++q) c.u[q] = ua[4 * g + q];
+#endif
+  } else {
+    for (int q = 0; q < 4; ++q)
+      if (c.i0 + q >= c.lo && c.i0 + q < c.hi) c.u[q] = ua[4 * g + q];
+  }
+  return c;
+}
+
+AVR_HD void coarse_group_finish(const CoarseGroup& c, int g, const CoarseSegment* seg, float* za) {
+  if (c.hi <= c.lo) return;
+  int k = coarse_segment_find(seg, c.lo);
+  CoarseRay p = seg->ray[k];
+  int rb = seg->rel[k], re = seg->rel[k + 1];
+  float out[4];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) {
+    const int i = c.i0 + q;
+    out[q] = 0.f;
+    if (i < c.lo || i >= c.hi) continue;
+    if (i >= re) {  // on to the next non-empty ray (i < seg_len bounds the walk)
+      do {
+        ++k;
+        re = seg->rel[k + 1];
+      } while (i >= re);
+      rb = seg->rel[k];
+      p = seg->ray[k];
+    }
+    out[q] = coarse_depth_ray(p, i - rb, c.u[q]);
+  }
+  if (c.full) {
+#if defined(__CUDACC__)
+    __stcs(reinterpret_cast<float4*>(za + 4 * g), make_float4(out[0], out[1], out[2], out[3]));
+#else
+    for (int q = 0; q < 4; ++q) za[4 * g + q] = out[q];
+#endif
+  } else {
+    for (int q = 0; q < 4; ++q)
+      if (c.i0 + q >= c.lo && c.i0 + q < c.hi) za[4 * g + q] = out[q];
+  }
+}
+
+// `vec_ok`: u and z are 16-byte aligned.  Two groups per lane are in flight per step (both
+// loads are issued before either is consumed).
+AVR_HD void coarse_segment_run(int lane, const CoarseSegment* seg, int64_t seg_begin, const float* u, float* z,
+                               bool vec_ok) {
+  const int seg_len = seg->rel[kSegRays];
+  const int head = (int)(seg_begin & 3);  // samples between the 16-byte boundary below and the segment
+  const int n_groups = (head + seg_len + 3) >> 2;
+  const float* ua = u + (seg_begin - head);
+  float* za = z + (seg_begin - head);
+  for (int g = lane; g < n_groups; g += 64) {
+    const bool two = g + 32 < n_groups;
+    const CoarseGroup c0 = coarse_group_load(g, head, seg_len, ua, vec_ok);
+    CoarseGroup c1 = c0;
+    if (two) c1 = coarse_group_load(g + 32, head, seg_len, ua, vec_ok);
+    coarse_group_finish(c0, g, seg, za);
+    if (two) coarse_group_finish(c1, g + 32, seg, za);
+  }
+}
+
+// Per-ray loop for a segment the flat walk cannot take (>= 2^31 samples in 32 rays).
+AVR_HD void coarse_segment_slow(int lane, int64_t r0, int64_t R, const int64_t* offsets, const float* near,
+                                const float* far, int bound_stride, const float* u, float* z) {
+  for (int64_t r = r0; r < r0 + kSegRays && r < R; ++r) {
+    const int64_t begin = offsets[r];
+    const int64_t cnt = offsets[r + 1] - begin;
+    const int64_t b = bound_stride ? r : 0;
+    const float nr = near[b], span = f_sub(far[b], nr), kf = (float)cnt;
+    for (int64_t j = lane; j < cnt; j += 32) {
+      const float zz = f_add(nr, f_mul(span, f_div((float)j, kf)));
+      z[begin + j] = f_add(zz, f_div(f_mul(u[begin + j], span), kf));
+    }
+  }
+}
+
+}  // namespace avr

@@ -8,7 +8,10 @@
 // torch-CPU.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "avr_common.cuh"
+#include "coarse_packed_core.h"
 #include "kernels.h"
 
 namespace avr {
@@ -71,7 +74,33 @@ coarse_fwd_dense_kernel(const float* __restrict__ near, const float* __restrict_
   }
 }
 
-// packed: one warp per ray, each ray stratified over its own count
+// packed, flat: a warp owns 32 consecutive rays = one contiguous slice of the packed streams and
+// walks it four samples per lane at a time (coarse_packed_core.h has the per-lane code and the
+// reasoning; the same code runs on the host in the CPU test suite)
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+coarse_fwd_packed_flat_kernel(const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
+                              const float* __restrict__ u, const int64_t* __restrict__ offsets, int64_t R,
+                              float* __restrict__ z, int vec_ok) {
+  __shared__ __align__(16) CoarseSegment s_seg[kSamplerWarps];
+  const int lane = threadIdx.x & 31;
+  CoarseSegment* seg = &s_seg[threadIdx.x >> 5];
+  const int64_t n_seg = (R + kSegRays - 1) / kSegRays;
+  const int64_t warps = (int64_t)gridDim.x * kSamplerWarps;
+  for (int64_t sidx = blockIdx.x * (int64_t)kSamplerWarps + (threadIdx.x >> 5); sidx < n_seg; sidx += warps) {
+    const int64_t r0 = sidx * kSegRays;
+    const bool ok = coarse_segment_build(lane, r0, R, offsets, near, far, bound_stride, seg);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();  // table writes before the reads
+    if (all_ok) {
+      coarse_segment_run(lane, seg, offsets[r0], u, z, vec_ok != 0);
+    } else {
+      coarse_segment_slow(lane, r0, R, offsets, near, far, bound_stride, u, z);
+    }
+    __syncwarp();  // the next segment's build overwrites the tables
+  }
+}
+
+// packed: one warp per ray, each ray stratified over its own count (AVR_COARSE_PACKED=ray)
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 coarse_fwd_packed_kernel(const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
                          const float* __restrict__ u, const int64_t* __restrict__ offsets, int64_t R,
@@ -407,8 +436,16 @@ int launch_coarse_fwd(const float* near, const float* far, int bound_stride, con
                       const int64_t* offsets, int64_t R, int K, int64_t S, float* z, cudaStream_t stream) {
   if (R == 0) return AVR_OK;
   if (offsets) {
-    coarse_fwd_packed_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 16), kSamplerWarps * 32, 0, stream>>>(
-        near, far, bound_stride, u, offsets, R, z);
+    // AVR_COARSE_PACKED=ray selects the one-warp-per-ray kernel (kept for A/B measurements)
+    const char* sw = std::getenv("AVR_COARSE_PACKED");
+    if (sw && sw[0] == 'r') {
+      coarse_fwd_packed_kernel<<<grid_for(R, kSamplerWarps, kNumSMs * 16), kSamplerWarps * 32, 0, stream>>>(
+          near, far, bound_stride, u, offsets, R, z);
+    } else {
+      const int64_t n_seg = (R + kSegRays - 1) / kSegRays;
+      coarse_fwd_packed_flat_kernel<<<grid_for(n_seg, kSamplerWarps, kNumSMs * 16), kSamplerWarps * 32, 0, stream>>>(
+          near, far, bound_stride, u, offsets, R, z, (aligned16(u) && aligned16(z)) ? 1 : 0);
+    }
   } else {
     const int64_t total = R * (int64_t)K;
     if (total == 0) return AVR_OK;

@@ -199,3 +199,48 @@ def test_packed_span_tiling_matches_generic(name, dev):
     want = O.composite_packed(z, x, offsets, True, 1.8)
     assert_close(a[0], want[0], what="rgb vs oracle")
     assert_close(a[2], want[2], what="w vs oracle")
+
+
+@pytest.mark.parametrize("variant", ["flat", "ray"])
+@pytest.mark.parametrize("case", ["c4_like", "empty_and_single", "empty_segments", "long", "scalar_bounds", "unaligned"])
+def test_packed_coarse_sampler_bit_exact(case, variant, dev, monkeypatch):
+    """Packed coarse sampler (segment-of-32-rays flat kernel and the one-warp-per-ray kernel) against
+    the oracle per bucket, bit for bit: ragged counts, empty rays, whole empty segments, rays longer
+    than a warp step, scalar bounds, and u/z views off the 16-byte grid (the CPU suite walks the
+    same per-lane code on the host: tests/test_host_kernel_cores.py)."""
+    from avr_b200 import ops
+    monkeypatch.setenv("AVR_COARSE_PACKED", variant)
+    g = torch.Generator().manual_seed(3)
+    counts = {
+        "c4_like": lambda: torch.randint(8, 257, (4099,), generator=g),
+        "empty_and_single": lambda: torch.tensor([0, 0, 1, 2, 3, 5, 31, 32, 33, 64, 200])[torch.randint(0, 11, (1500,), generator=g)],
+        "empty_segments": lambda: torch.cat([torch.zeros(70, dtype=torch.int64), torch.tensor([5]), torch.zeros(40, dtype=torch.int64), torch.tensor([1, 0, 0, 9])]),
+        "long": lambda: torch.tensor([1030, 0, 4097, 7, 700, 257]),
+        "scalar_bounds": lambda: torch.randint(0, 300, (777,), generator=g),
+        "unaligned": lambda: torch.randint(1, 12, (333,), generator=g) * 2 + 1,
+    }[case]().to(torch.int64)
+    r = counts.numel()
+    offsets = torch.zeros(r + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts, 0)
+    s = int(offsets[-1])
+    if case == "scalar_bounds":
+        near, far = torch.tensor([0.8]), torch.tensor([1.8])
+    else:
+        d = 0.9 + 0.8 * torch.rand(r, generator=g)
+        near, far = d - 0.15, d + 0.15
+    u = torch.rand(s, generator=g)
+    u[::13] = torch.tensor([0.0, 2.0 ** -24, 1 - 2.0 ** -24, 1e-30, 1e-38, 1e-44])[torch.arange(u[::13].numel()) % 6]
+    ud = u.to(dev)
+    if case == "unaligned":
+        buf = torch.zeros(s + 1, device=dev)
+        buf[1:] = ud
+        ud = buf[1:]                                     # 4 bytes off the 16-byte grid
+        assert ud.data_ptr() % 16 == 4
+    z = ops.coarse_sample_packed(near.to(dev), far.to(dev), ud, offsets.to(dev)).cpu()
+    for k, rays, idx in O.bucketed(offsets):
+        if k == 0:
+            continue
+        n = near[rays] if near.numel() > 1 else near.expand(len(rays))
+        f = far[rays] if far.numel() > 1 else far.expand(len(rays))
+        want = O.coarse_z(n.unsqueeze(0), f.unsqueeze(0), k, u[idx].unsqueeze(0))[0]
+        assert torch.equal(z[idx], want), (case, variant, k)
