@@ -16,9 +16,11 @@ from .renderers import (  # noqa: F401
     volume_integral,
     volume_integral_rgbs,
 )
-from . import ops, geometry  # noqa: F401
+from . import ops, geometry, field  # noqa: F401
+from .field import FieldConfig, field_inputs, fuse_field_inputs  # noqa: F401
 
 __all__ = [
     "AdaptiveVolumeRenderer", "VolumeRenderer", "sample_coarse", "sample_depth", "sample_fine",
-    "volume_integral", "volume_integral_rgbs", "ops", "geometry", "AvrError", "load_library", "LIB_PATH",
+    "volume_integral", "volume_integral_rgbs", "ops", "geometry", "field", "FieldConfig", "field_inputs",
+    "fuse_field_inputs", "AvrError", "load_library", "LIB_PATH",
 ]

@@ -338,6 +338,39 @@ int avr_depth_from_world(const float* ros, const float* rds, const float* dist, 
   return launch_depth_from_world(ros, rds, dist, cam2world, R, depth, grad_row, as_stream(stream));
 }
 
+/* ------------------------------------------ radiance-field front end -- */
+
+static int check_field_desc(const avr_field_inputs* d, bool backward) {
+  if (!d || d->B < 0 || d->NV < 0 || d->NS < 1 || d->NV % d->NS != 0) return AVR_ERR_BAD_ARG;
+  if (d->C < 4 || d->C % 4 != 0 || d->H < 1 || d->W < 1) return AVR_ERR_BAD_ARG;
+  if (d->n_sin < 0 || d->n_sin > AVR_FIELD_MAX_SIN) return AVR_ERR_BAD_ARG;
+  if (d->NV * d->B == 0) return AVR_OK;
+  const int width = d->features_only ? 0 : (d->include_input ? 3 : 0) + 3 * d->n_sin + (d->use_viewdirs ? 3 : 0);
+  if ((d->C + width) % 2 != 0) return AVR_ERR_UNSUPPORTED;  // rows are written in 8-byte pieces
+  if (!d->xyz || !d->poses || !d->focal || !d->c || !d->latent) return AVR_ERR_BAD_ARG;
+  if (d->use_viewdirs && !d->features_only && !d->viewdirs) return AVR_ERR_BAD_ARG;
+  if (!aligned16(d->latent)) return AVR_ERR_BAD_ARG;
+  if (backward) {
+    if (!d->g_out || (reinterpret_cast<uintptr_t>(d->g_out) & 7u)) return AVR_ERR_BAD_ARG;
+    if (d->d_latent && !aligned16(d->d_latent)) return AVR_ERR_BAD_ARG;
+  } else {
+    if (!d->out || (reinterpret_cast<uintptr_t>(d->out) & 7u)) return AVR_ERR_BAD_ARG;
+  }
+  return 1;  // work to do
+}
+
+int avr_field_inputs_fwd(const avr_field_inputs* desc, avr_stream_t stream) {
+  const int rc = check_field_desc(desc, false);
+  if (rc <= 0) return rc;
+  return launch_field_inputs_fwd(*desc, as_stream(stream));
+}
+
+int avr_field_inputs_bwd(const avr_field_inputs* desc, avr_stream_t stream) {
+  const int rc = check_field_desc(desc, true);
+  if (rc < 0) return rc;
+  return launch_field_inputs_bwd(*desc, desc->NV / desc->NS, as_stream(stream));
+}
+
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
 }  // extern "C"

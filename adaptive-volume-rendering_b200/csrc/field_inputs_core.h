@@ -1,0 +1,506 @@
+// Radiance-field front end: what NewPixelNeRFNet.forward does
+// between receiving the renderer's sample points and calling its MLP (models.py:754-820) —
+//   world -> source-view transform        xyz_rot = R p,  xyz = xyz_rot + t            :757-761
+//   positional encoding                   [x, sin(phase_k + x f_k)] of xyz_rot or xyz  :764-781, :45-71
+//   view direction into the view frame    R d                                            :783-794
+//   projection + pixel-aligned features   uv = -xy/z * focal + c; grid_sample(latent)    :803-815, :256-279
+//   concatenation                         mlp_input = [latent | code | viewdir]          :826
+// as per-lane code that compiles for the device (nvcc) and for the host (g++; the CPU suite walks
+// it lane by lane against the oracle: tests/test_host_kernel_cores.py).
+//
+// One warp per (source view, point).  Every lane redoes the ~60 flops of coordinate work (no
+// shuffles), then owns channels {4*lane + 128*i} of the feature vector and code entries
+// {lane, lane+32}.  The feature map is channels-last (N, H, W, C): one bilinear tap is one
+// contiguous C*4-byte row.
+//
+// The operation order reproduces torch-CPU's kernels so that everything except the sine is
+// bit-identical to the reference on the same inputs (probed against the reference, see
+// oracle/make_golden.py case_field_inputs): the 3x3 product accumulates left to right without
+// contraction (bmm's small-matrix loop), the encoding argument is ONE fused multiply-add
+// (addcmul), pixel coordinates follow grid_sampler's unnormalize / clip / floor with
+// align_corners=True and border padding, and the four taps accumulate nw, ne, sw, se through
+// fused multiply-adds.
+#pragma once
+
+#include <stdint.h>
+
+#include "avr_b200.h"
+
+#if defined(__CUDACC__)
+#define AVR_FI __device__ __forceinline__
+#else
+#include <math.h>
+#define AVR_FI inline
+#endif
+
+namespace avr {
+
+#if defined(__CUDACC__)
+AVR_FI float fi_mul(float a, float b) { return __fmul_rn(a, b); }
+AVR_FI float fi_add(float a, float b) { return __fadd_rn(a, b); }
+AVR_FI float fi_sub(float a, float b) { return __fsub_rn(a, b); }
+AVR_FI float fi_div(float a, float b) { return __fdiv_rn(a, b); }
+AVR_FI float fi_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+AVR_FI float fi_mul(float a, float b) { return a * b; }
+AVR_FI float fi_add(float a, float b) { return a + b; }
+AVR_FI float fi_sub(float a, float b) { return a - b; }
+AVR_FI float fi_div(float a, float b) { return a / b; }
+AVR_FI float fi_fma(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+// Launch-constant description of the front end (the public descriptor of include/avr_b200.h,
+// passed by value to the kernels).
+using FieldInputsArgs = ::avr_field_inputs;
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int field_code_width(const FieldInputsArgs& a) {
+  return (a.include_input ? 3 : 0) + 3 * a.n_sin + (a.use_viewdirs ? 3 : 0);
+}
+
+// Coordinates of one (view, point): everything that does not depend on the lane.
+struct FieldPoint {
+  float enc[3];   // what the positional code encodes (R p, or R p + t)
+  float vrot[3];  // R d
+  float cam[3];   // R p + t
+  float ix, iy;   // clipped pixel coordinates in the feature map
+  int x0, y0;     // floor
+  float nw, ne, sw, se;
+  bool clip_x, clip_y;  // coordinate was clamped (its gradient is zero)
+};
+
+AVR_FI void rotate3(const float* R, float x, float y, float z, float* o) {
+  // (R[i][0]*x + R[i][1]*y) + R[i][2]*z, products and sums rounded one by one; rows are 4 floats apart
+  for (int i = 0; i < 3; ++i)
+    o[i] = fi_add(fi_add(fi_mul(R[4 * i], x), fi_mul(R[4 * i + 1], y)), fi_mul(R[4 * i + 2], z));
+}
+
+AVR_FI FieldPoint field_point(const FieldInputsArgs& a, int64_t v, int64_t b) {
+  FieldPoint p;
+  const int64_t obj = v / a.NS;
+  const float* R = a.poses + v * 12;
+  const float* w = a.xyz + (obj * a.B + b) * 3;
+  float rot[3];
+  rotate3(R, w[0], w[1], w[2], rot);
+  for (int i = 0; i < 3; ++i) {
+    p.cam[i] = fi_add(rot[i], R[4 * i + 3]);
+    p.enc[i] = a.normalize_z ? rot[i] : p.cam[i];
+  }
+  p.vrot[0] = p.vrot[1] = p.vrot[2] = 0.f;
+  if (a.use_viewdirs && !a.features_only) {
+    const float* d = a.viewdirs + (obj * a.B + b) * 3;
+    rotate3(R, d[0], d[1], d[2], p.vrot);
+  }
+  // uv = -xy / z; uv *= focal; uv += c; uv = uv * scale - 1          models.py:803-811, :268-270
+  const float* f = a.focal + (a.focal_per_obj ? obj * 2 : 0);
+  const float* c = a.c + (a.c_per_obj ? obj * 2 : 0);
+  const float u = fi_sub(fi_mul(fi_add(fi_mul(fi_div(-p.cam[0], p.cam[2]), f[0]), c[0]), a.scale_x), 1.0f);
+  const float t = fi_sub(fi_mul(fi_add(fi_mul(fi_div(-p.cam[1], p.cam[2]), f[1]), c[1]), a.scale_y), 1.0f);
+  // grid_sample, align_corners=True, padding_mode="border": x = (u + 1) * ((W-1)/2), clamped
+  const float mx = (float)(a.W - 1), my = (float)(a.H - 1);
+  const float ux = fi_mul(fi_add(u, 1.0f), mx / 2), uy = fi_mul(fi_add(t, 1.0f), my / 2);
+  p.clip_x = !(ux > 0.f && ux < mx);  // grid_sampler's clip has zero gradient on and beyond the border
+  p.clip_y = !(uy > 0.f && uy < my);
+  p.ix = fminf(mx, fmaxf(ux, 0.f));
+  p.iy = fminf(my, fmaxf(uy, 0.f));
+  const float fx = floorf(p.ix), fy = floorf(p.iy);
+  p.x0 = (int)fx;
+  p.y0 = (int)fy;
+  const float wx = fi_sub(p.ix, fx), ex = fi_sub(1.0f, wx);
+  const float wy = fi_sub(p.iy, fy), sy = fi_sub(1.0f, wy);
+  p.nw = fi_mul(sy, ex);
+  p.ne = fi_mul(sy, wx);
+  p.sw = fi_mul(wy, ex);
+  p.se = fi_mul(wy, wx);
+  return p;
+}
+
+// v[d] by selects (a run-time index would put the array into local memory)
+AVR_FI float pick3(const float* v, int d) { return d == 0 ? v[0] : (d == 1 ? v[1] : v[2]); }
+
+// Entry e of the code part of a row: [enc (3) | sin rows (3 per row) | view direction (3)]
+AVR_FI float field_code_entry(const FieldInputsArgs& a, const FieldPoint& p, int e) {
+  if (a.include_input) {
+    if (e < 3) return p.enc[e];
+    e -= 3;
+  }
+  if (e < 3 * a.n_sin) {
+    const int k = e / 3, d = e - 3 * k;
+    return sinf(fi_fma(pick3(p.enc, d), a.freqs[k], a.phases[k]));  // addcmul(phases, x, freqs) then sin, :66-67
+  }
+  return pick3(p.vrot, e - 3 * a.n_sin);
+}
+
+// One bilinear tap row: address of channel 0 of texel (x, y) of view v, or null outside the map
+// (grid_sample reads such a tap as zero; with border padding its weight is zero as well).
+AVR_FI const float* field_tap(const FieldInputsArgs& a, int64_t v, int x, int y) {
+  if (x < 0 || y < 0 || x >= a.W || y >= a.H) return nullptr;
+  return a.latent + ((v * a.H + y) * (int64_t)a.W + x) * a.C;
+}
+
+// nw, ne, sw, se accumulated by fused multiply-adds, in that order
+AVR_FI float field_blend(const FieldPoint& p, float t_nw, float t_ne, float t_sw, float t_se) {
+  float acc = fi_mul(t_nw, p.nw);
+  acc = fi_fma(t_ne, p.ne, acc);
+  acc = fi_fma(t_sw, p.sw, acc);
+  return fi_fma(t_se, p.se, acc);
+}
+
+// ---- forward: one lane's share of one output row ---------------------------------------------
+// CPL = float4 groups per lane and tap (C == 128 * CPL).  The four taps stay in registers from
+// one point to the next: consecutive samples of a ray usually fall into the same texel cell, so
+// the feature rows are re-read only when the cell (or the view) changes.
+template <int CPL>
+struct FieldTapCache {
+  float t[4][CPL][4];  // [nw, ne, sw, se][group][component]
+  int x0, y0;
+  int64_t v;
+};
+
+template <int CPL>
+AVR_FI void field_cache_reset(FieldTapCache<CPL>* c) {
+  c->x0 = c->y0 = -1;
+  c->v = -1;
+}
+
+AVR_FI void field_load4(const float* src, float* dst) {
+#if defined(__CUDACC__)
+  const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+  dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+#else
+  for (int i = 0; i < 4; ++i) dst[i] = src[i];
+#endif
+}
+
+AVR_FI void field_store2(float* dst, float x, float y) {
+#if defined(__CUDACC__)
+  __stcs(reinterpret_cast<float2*>(dst), make_float2(x, y));
+#else
+  dst[0] = x;
+  dst[1] = y;
+#endif
+}
+
+template <int CPL>
+AVR_FI void field_cache_fill(const FieldInputsArgs& a, const FieldPoint& p, int64_t v, int lane, FieldTapCache<CPL>* c) {
+  if (c->x0 == p.x0 && c->y0 == p.y0 && c->v == v) return;  // warp-uniform
+  c->x0 = p.x0;
+  c->y0 = p.y0;
+  c->v = v;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    const float* row = field_tap(a, v, p.x0 + (k & 1), p.y0 + (k >> 1));
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int i = 0; i < CPL; ++i) {
+      if (row) {
+        field_load4(row + 4 * lane + 128 * i, c->t[k][i]);
+      } else {
+        c->t[k][i][0] = c->t[k][i][1] = c->t[k][i][2] = c->t[k][i][3] = 0.f;
+      }
+    }
+  }
+}
+
+// Row `row` = v*B + b of the output.  The row stride is even (C and the code width are checked by
+// the launcher), so 8-byte stores are always aligned; 16-byte ones would not be (554 floats).
+template <int CPL>
+AVR_FI void field_row_lane(const FieldInputsArgs& a, int64_t row, int lane, int row_stride, FieldTapCache<CPL>* c) {
+  const int64_t v = row / a.B, b = row - v * a.B;
+  const FieldPoint p = field_point(a, v, b);
+  field_cache_fill<CPL>(a, p, v, lane, c);
+  float* out = a.out + row * row_stride;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < CPL; ++i) {
+    float o[4];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) o[q] = field_blend(p, c->t[0][i][q], c->t[1][i][q], c->t[2][i][q], c->t[3][i][q]);
+    field_store2(out + 4 * lane + 128 * i, o[0], o[1]);
+    field_store2(out + 4 * lane + 128 * i + 2, o[2], o[3]);
+  }
+  if (!a.features_only) {
+    const int width = field_code_width(a);
+    for (int e = lane; e < width; e += 32) out[a.C + e] = field_code_entry(a, p, e);
+  }
+}
+
+// Any C % 4 == 0 (no tap cache): lanes stride over the float4 groups of the row.
+AVR_FI void field_row_lane_generic(const FieldInputsArgs& a, int64_t row, int lane, int row_stride) {
+  const int64_t v = row / a.B, b = row - v * a.B;
+  const FieldPoint p = field_point(a, v, b);
+  float* out = a.out + row * row_stride;
+  const float* rows[4];
+  for (int k = 0; k < 4; ++k) rows[k] = field_tap(a, v, p.x0 + (k & 1), p.y0 + (k >> 1));
+  for (int g = lane; g < a.C / 4; g += 32) {
+    float t[4][4];
+    for (int k = 0; k < 4; ++k) {
+      if (rows[k]) {
+        field_load4(rows[k] + 4 * g, t[k]);
+      } else {
+        t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0.f;
+      }
+    }
+    float o[4];
+    for (int q = 0; q < 4; ++q) o[q] = field_blend(p, t[0][q], t[1][q], t[2][q], t[3][q]);
+    field_store2(out + 4 * g, o[0], o[1]);
+    field_store2(out + 4 * g + 2, o[2], o[3]);
+  }
+  if (!a.features_only) {
+    const int width = field_code_width(a);
+    for (int e = lane; e < width; e += 32) out[a.C + e] = field_code_entry(a, p, e);
+  }
+}
+
+// ---- backward --------------------------------------------------------------------------------
+// Same walk as the forward pass (a warp visits chunks of consecutive rows).  For row (v, b) with
+// upstream gradient g (row of g_out):
+//   d_latent[tap_k] += g_c * weight_k                     (grid_sample's backward w.r.t. its input)
+//   d ix = sum_c g_c [(t_ne - t_nw) sy + (t_se - t_sw) wy],  d iy likewise   (w.r.t. its grid)
+//   d enc = g_code (raw entries) + sum_k g_k cos(arg_k) f_k;  d vrot = g_view
+//   d p = R^T (d cam + d enc),  d viewdir = R^T d vrot;  accumulated over the NS views of an
+//   object by atomic adds (d_xyz / d_viewdirs are zeroed by the launcher).
+// The d_latent contributions are summed in registers for as long as consecutive rows stay in one
+// texel cell and flushed with vector atomics when the cell changes: samples along a ray would
+// otherwise queue on the same four addresses in L2.
+template <int CPL>
+struct FieldGradCache {
+  float acc[4][CPL][4];
+  int x0, y0;
+  int64_t v;
+};
+
+template <int CPL>
+AVR_FI void field_grad_reset(FieldGradCache<CPL>* c) {
+  c->x0 = c->y0 = -1;
+  c->v = -1;
+}
+
+AVR_FI void field_atomic_add4(float* dst, const float* v) {
+#if defined(__CUDACC__)
+  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+#else
+  for (int i = 0; i < 4; ++i) dst[i] += v[i];
+#endif
+}
+
+AVR_FI void field_atomic_add(float* dst, float v) {
+#if defined(__CUDACC__)
+  atomicAdd(dst, v);
+#else
+  *dst += v;
+#endif
+}
+
+AVR_FI void field_load2(const float* src, float* dst) {
+#if defined(__CUDACC__)
+  const float2 q = __ldcs(reinterpret_cast<const float2*>(src));
+  dst[0] = q.x; dst[1] = q.y;
+#else
+  dst[0] = src[0];
+  dst[1] = src[1];
+#endif
+}
+
+// address of texel (x, y) of view v in d_latent (same layout as latent), or null outside the map
+AVR_FI float* field_grad_tap(const FieldInputsArgs& a, int64_t v, int x, int y) {
+  if (x < 0 || y < 0 || x >= a.W || y >= a.H) return nullptr;
+  return a.d_latent + ((v * a.H + y) * (int64_t)a.W + x) * a.C;
+}
+
+template <int CPL>
+AVR_FI void field_grad_flush(const FieldInputsArgs& a, int lane, FieldGradCache<CPL>* c) {
+  if (c->v < 0) return;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    float* row = field_grad_tap(a, c->v, c->x0 + (k & 1), c->y0 + (k >> 1));
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int i = 0; i < CPL; ++i)
+      if (row) field_atomic_add4(row + 4 * lane + 128 * i, c->acc[k][i]);
+  }
+  c->v = -1;
+}
+
+// Per-lane partial sums of one row that the warp has to add up.
+struct FieldRowPartial {
+  float gix, giy;   // d / d(ix, iy) over this lane's channels
+  float enc[3];     // d / d enc over this lane's code entries
+  float vrot[3];    // d / d vrot
+};
+
+AVR_FI void field_partial_zero(FieldRowPartial* s) {
+  s->gix = s->giy = 0.f;
+  s->enc[0] = s->enc[1] = s->enc[2] = 0.f;
+  s->vrot[0] = s->vrot[1] = s->vrot[2] = 0.f;
+}
+
+// code entries of this lane: the mirror of field_code_entry
+AVR_FI void field_code_grad_lane(const FieldInputsArgs& a, const FieldPoint& p, const float* g_code, int lane,
+                                 FieldRowPartial* s) {
+  const int width = field_code_width(a);
+  for (int e0 = lane; e0 < width; e0 += 32) {
+    const float g = g_code[e0];
+    int e = e0;
+    if (a.include_input) {
+      if (e < 3) {
+        s->enc[0] += e == 0 ? g : 0.f;
+        s->enc[1] += e == 1 ? g : 0.f;
+        s->enc[2] += e == 2 ? g : 0.f;
+        continue;
+      }
+      e -= 3;
+    }
+    if (e < 3 * a.n_sin) {
+      const int k = e / 3, d = e - 3 * k;
+      const float t = g * cosf(fi_fma(pick3(p.enc, d), a.freqs[k], a.phases[k])) * a.freqs[k];
+      s->enc[0] += d == 0 ? t : 0.f;
+      s->enc[1] += d == 1 ? t : 0.f;
+      s->enc[2] += d == 2 ? t : 0.f;
+    } else {
+      const int d = e - 3 * a.n_sin;
+      s->vrot[0] += d == 0 ? g : 0.f;
+      s->vrot[1] += d == 1 ? g : 0.f;
+      s->vrot[2] += d == 2 ? g : 0.f;
+    }
+  }
+}
+
+// Lane `lane` of row `row`: accumulates into the d_latent cache (kLatent) and returns its partial
+// sums of the point gradient (kPoint; zero otherwise).  `taps` is the forward tap cache (read only
+// when kPoint).
+template <int CPL, bool kLatent, bool kPoint>
+AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, int64_t row, int lane, int row_stride,
+                                          const FieldPoint& p, FieldTapCache<CPL>* taps, FieldGradCache<CPL>* grads) {
+  const int64_t v = row / a.B;
+  FieldRowPartial s;
+  field_partial_zero(&s);
+  const float* g_row = a.g_out + row * row_stride;
+  if (kPoint) field_cache_fill<CPL>(a, p, v, lane, taps);
+  if (kLatent && !(grads->x0 == p.x0 && grads->y0 == p.y0 && grads->v == v)) {  // warp-uniform
+    field_grad_flush<CPL>(a, lane, grads);
+    grads->x0 = p.x0;
+    grads->y0 = p.y0;
+    grads->v = v;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k)
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int i = 0; i < CPL; ++i) grads->acc[k][i][0] = grads->acc[k][i][1] = grads->acc[k][i][2] = grads->acc[k][i][3] = 0.f;
+  }
+  // bilinear weights again, split into their factors for the coordinate gradient
+  const float wx = fi_sub(p.ix, (float)p.x0), ex = fi_sub(1.0f, wx);
+  const float wy = fi_sub(p.iy, (float)p.y0), sy = fi_sub(1.0f, wy);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < CPL; ++i) {
+    float g[4];
+    field_load2(g_row + 4 * lane + 128 * i, g);
+    field_load2(g_row + 4 * lane + 128 * i + 2, g + 2);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) {
+      if (kLatent) {
+        grads->acc[0][i][q] = fi_fma(g[q], p.nw, grads->acc[0][i][q]);
+        grads->acc[1][i][q] = fi_fma(g[q], p.ne, grads->acc[1][i][q]);
+        grads->acc[2][i][q] = fi_fma(g[q], p.sw, grads->acc[2][i][q]);
+        grads->acc[3][i][q] = fi_fma(g[q], p.se, grads->acc[3][i][q]);
+      }
+      if (kPoint) {
+        const float t_nw = taps->t[0][i][q], t_ne = taps->t[1][i][q], t_sw = taps->t[2][i][q], t_se = taps->t[3][i][q];
+        s.gix += g[q] * ((t_ne - t_nw) * sy + (t_se - t_sw) * wy);
+        s.giy += g[q] * ((t_sw - t_nw) * ex + (t_se - t_ne) * wx);
+      }
+    }
+  }
+  if (kPoint && !a.features_only) field_code_grad_lane(a, p, g_row + a.C, lane, &s);
+  return s;
+}
+
+// Once per row, with the partials summed over the warp: chain rule through the projection and
+// the rigid transform, then atomic accumulation over the object's views.
+AVR_FI void field_bwd_row_finish(const FieldInputsArgs& a, int64_t row, const FieldPoint& p, const FieldRowPartial& s) {
+  const int64_t v = row / a.B, b = row - v * a.B;
+  const int64_t obj = v / a.NS;
+  const float* R = a.poses + v * 12;
+  const float* f = a.focal + (a.focal_per_obj ? obj * 2 : 0);
+  // ix = clip((u + 1) (W-1)/2): zero gradient where clamped; u = (-x/z * fx + cx) * scale_x - 1
+  const float gu = p.clip_x ? 0.f : s.gix * ((float)(a.W - 1) / 2) * a.scale_x * f[0];
+  const float gt = p.clip_y ? 0.f : s.giy * ((float)(a.H - 1) / 2) * a.scale_y * f[1];
+  const float iz = 1.0f / p.cam[2];
+  float d_cam[3];
+  d_cam[0] = -gu * iz;
+  d_cam[1] = -gt * iz;
+  d_cam[2] = (gu * p.cam[0] + gt * p.cam[1]) * iz * iz;
+  for (int i = 0; i < 3; ++i) d_cam[i] += s.enc[i];  // enc is R p (+ t): same Jacobian as cam
+  if (a.d_xyz) {
+    float* dst = a.d_xyz + (obj * a.B + b) * 3;
+    for (int j = 0; j < 3; ++j) field_atomic_add(dst + j, R[j] * d_cam[0] + R[4 + j] * d_cam[1] + R[8 + j] * d_cam[2]);
+  }
+  if (a.d_viewdirs && a.use_viewdirs && !a.features_only) {
+    float* dst = a.d_viewdirs + (obj * a.B + b) * 3;
+    for (int j = 0; j < 3; ++j) field_atomic_add(dst + j, R[j] * s.vrot[0] + R[4 + j] * s.vrot[1] + R[8 + j] * s.vrot[2]);
+  }
+}
+
+// Any C % 4 == 0: no caches, every row adds straight into d_latent.
+template <bool kLatent, bool kPoint>
+AVR_FI FieldRowPartial field_bwd_row_lane_generic(const FieldInputsArgs& a, int64_t row, int lane, int row_stride,
+                                                  const FieldPoint& p) {
+  const int64_t v = row / a.B;
+  FieldRowPartial s;
+  field_partial_zero(&s);
+  const float* g_row = a.g_out + row * row_stride;
+  const float wx = fi_sub(p.ix, (float)p.x0), ex = fi_sub(1.0f, wx);
+  const float wy = fi_sub(p.iy, (float)p.y0), sy = fi_sub(1.0f, wy);
+  const float wk[4] = {p.nw, p.ne, p.sw, p.se};
+  for (int grp = lane; grp < a.C / 4; grp += 32) {
+    float g[4], t[4][4];
+    field_load2(g_row + 4 * grp, g);
+    field_load2(g_row + 4 * grp + 2, g + 2);
+    for (int k = 0; k < 4; ++k) {
+      const int x = p.x0 + (k & 1), y = p.y0 + (k >> 1);
+      if (kLatent) {
+        float* dst = field_grad_tap(a, v, x, y);
+        if (dst) {
+          const float c[4] = {g[0] * wk[k], g[1] * wk[k], g[2] * wk[k], g[3] * wk[k]};
+          field_atomic_add4(dst + 4 * grp, c);
+        }
+      }
+      if (kPoint) {
+        const float* src = field_tap(a, v, x, y);
+        if (src) {
+          field_load4(src + 4 * grp, t[k]);
+        } else {
+          t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0.f;
+        }
+      }
+    }
+    if (kPoint) {
+      for (int q = 0; q < 4; ++q) {
+        s.gix += g[q] * ((t[1][q] - t[0][q]) * sy + (t[3][q] - t[2][q]) * wy);
+        s.giy += g[q] * ((t[2][q] - t[0][q]) * ex + (t[3][q] - t[1][q]) * wx);
+      }
+    }
+  }
+  if (kPoint && !a.features_only) field_code_grad_lane(a, p, g_row + a.C, lane, &s);
+  return s;
+}
+
+}  // namespace avr

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "avr_b200.h"
+
 namespace avr {
 
 // composite_generic.cu — any shape, dense (offsets == nullptr) or packed
@@ -76,6 +78,10 @@ int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, i
                       float* ros, float* rds, cudaStream_t stream);
 int launch_depth_from_world(const float* ros, const float* rds, const float* dist, const float* c2w, int64_t R,
                             float* depth, float* grad_row, cudaStream_t stream);
+// field_inputs.cu — radiance-field front end (models.py:754-826), SURVEY 8(f) row 3
+using FieldInputsArgs = ::avr_field_inputs;
+int launch_field_inputs_fwd(const FieldInputsArgs& a, cudaStream_t stream);
+int launch_field_inputs_bwd(const FieldInputsArgs& a, int64_t SB, cudaStream_t stream);
 int launch_sort_rays_bwd(const float* g_out, const int32_t* perm, int64_t R, int K, float* d_in, cudaStream_t stream);
 int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, cudaStream_t stream);
 

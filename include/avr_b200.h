@@ -244,6 +244,59 @@ AVR_API int avr_world_rays(const float* x_pix, const float* intrinsics, const fl
 AVR_API int avr_depth_from_world(const float* ros, const float* rds, const float* dist, const float* cam2world,
                                  int64_t R, float* depth, float* grad_row, avr_stream_t stream);
 
+/* ------------------------------------------ radiance-field front end -- */
+
+/* what NewPixelNeRFNet.forward computes between receiving the
+ * renderer's sample points and calling its MLP (models.py:754-826) — world->view transform,
+ * positional encoding (models.py:62-71), view direction into the view frame, projection and
+ * the bilinear fetch of pixel-aligned encoder features (ConvEncoder.index, models.py:256-279:
+ * F.grid_sample, align_corners=True, border padding), concatenated into the MLP's input
+ *     out[v*B + b] = [ features (C) | xyz code (3 + 6*num_freqs) | view direction (3) ]
+ * for source view v = obj*NS + s and point b of object obj.  The encoder and the MLP stay the
+ * reference's torch modules; this replaces the ~25 ATen calls (and ~5x the traffic) between them.
+ *
+ * The descriptor carries the module state the reference keeps on `self` (poses, focal, c,
+ * image_shape / latent_scaling folded into `scale_*`, PositionalEncoding._freqs / ._phases).
+ * The feature map is channels-last, (NV, H, W, C) — torch.channels_last strides of the
+ * reference's (NV, C, H, W) `encoder.latent`; C % 4 == 0 and C + code width must be even.
+ * Given identical inputs every value except the sines is bit-identical to torch-CPU. */
+#define AVR_FIELD_MAX_SIN 32
+typedef struct avr_field_inputs {
+  const float* xyz;       /* (SB, B, 3) world points                                          */
+  const float* viewdirs;  /* (SB, B, 3), may be NULL when use_viewdirs == 0                    */
+  const float* poses;     /* (NV, 3, 4) world -> view, NV = SB*NS           models.py:705-707 */
+  const float* focal;     /* (1 or SB, 2), y already negated                 models.py:721-722 */
+  const float* c;         /* (1 or SB, 2) principal point                    models.py:724-733 */
+  const float* latent;    /* (NV, H, W, C) channels-last feature map                           */
+  float* out;             /* (NV*B, C + code) — (NV*B, C) when features_only                   */
+  int64_t B;              /* points per object                                                 */
+  int64_t NV;             /* source views in total                                             */
+  int NS;                 /* views per object                                                  */
+  int focal_per_obj;      /* 0: focal[0] for every view; 1: focal[v / NS]    models.py:805-807 */
+  int c_per_obj;          /* same for c                                      models.py:808-810 */
+  float scale_x, scale_y; /* latent_scaling / image_shape                    models.py:268-270 */
+  int C, H, W;
+  int n_sin;              /* 2 * num_freqs rows of the encoding, <= AVR_FIELD_MAX_SIN          */
+  float freqs[AVR_FIELD_MAX_SIN];  /* PositionalEncoding._freqs   (f1 f1 f2 f2 ...)  :53-56    */
+  float phases[AVR_FIELD_MAX_SIN]; /* PositionalEncoding._phases  (0 pi/2 0 pi/2 ...) :58-60   */
+  int include_input;      /* raw coordinates precede the encoding            models.py:69-70   */
+  int normalize_z;        /* 1: encode R p, 0: encode R p + t                models.py:766-769 */
+  int use_viewdirs;       /* append R d                                      models.py:783-794 */
+  int features_only;      /* return_features=True: the features alone        models.py:828-829 */
+  /* backward only */
+  const float* g_out;     /* (NV*B, row) gradient w.r.t. `out`                                 */
+  float* d_latent;        /* (NV, H, W, C) or NULL; overwritten                                */
+  float* d_xyz;           /* (SB, B, 3) or NULL; overwritten (summed over the NS views)        */
+  float* d_viewdirs;      /* (SB, B, 3) or NULL; overwritten                                   */
+} avr_field_inputs;
+
+/* Forward: fills desc->out.  The descriptor is read during the call (host memory). */
+AVR_API int avr_field_inputs_fwd(const avr_field_inputs* desc, avr_stream_t stream);
+/* Backward of the above: the gradients whose pointers are non-NULL (feature map via vector
+ * atomics, summed in registers while consecutive samples stay in one texel cell; points and
+ * view directions through the projection, the encoding and the rigid transform). */
+AVR_API int avr_field_inputs_bwd(const avr_field_inputs* desc, avr_stream_t stream);
+
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
 /* One forward+backward compositing pass over HOST buffers (pinned for full speed):

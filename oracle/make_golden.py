@@ -323,9 +323,120 @@ def case_pixelnerf_replay(ref):
          ref_rgb_coarse=rc, ref_rgb_fine=rf, ref_depth=depth)
 
 
+class _CaptureMLP(torch.nn.Module):
+    """Stands in for NewPixelNeRFNet.mlp_coarse: keeps the (N, C + code) tensor the front end built."""
+
+    def __init__(self):
+        super().__init__()
+        self.seen = None
+
+    def forward(self, x, combine_inner_dims=(1,), **kw):
+        self.seen = x
+        return x.new_zeros(x.shape[0] // combine_inner_dims[0], 4) + 0 * x.sum()
+
+
+def _source_poses(n, seed):
+    """n camera-to-world poses at distance ~1.3 looking at the origin (dataset.py:85-86 flip)."""
+    from fields import camera_setup
+    return camera_setup(n, 1, seed=seed)[0][:, 0].contiguous()
+
+
+def _run_field_front_end(net, xyz, viewdirs, g_out, dtype):
+    """The reference's forward up to its MLP, and the gradients of <out, g_out>."""
+    cap = _CaptureMLP()
+    net.mlp_coarse = cap
+    xyz = xyz.detach().to(dtype).clone().requires_grad_(True)
+    viewdirs = viewdirs.detach().to(dtype).clone().requires_grad_(True)
+    lat = net.encoder.latent.detach().to(dtype).requires_grad_(True)
+    net.encoder.latent = lat
+    net(xyz, coarse=True, viewdirs=viewdirs)
+    out = cap.seen
+    feats = net(xyz, coarse=True, viewdirs=viewdirs, return_features=True).detach()
+    torch.autograd.backward([out], [g_out.to(dtype)])
+    return out.detach(), feats, lat.grad, xyz.grad, viewdirs.grad
+
+
+def case_field_inputs(ref):
+    """NewPixelNeRFNet.forward between the renderer's points and the
+    MLP (models.py:754-826), run by the reference itself with its MLP replaced by a recorder.
+
+    field_inputs_c512: conf/default.conf's model around its own resnet34 encoder (random init, a
+    24x24 source image -> 512 x 12 x 12 features), one object, two source views.
+    field_inputs_small: the same code with the module state set by hand — 64 channels on a 8 x 10
+    map, two objects x three views, per-object focal length and principal point, normalize_z off,
+    and a third of the points projecting outside the map (border clamp).
+    fp64 runs of the same reference code are stored as ref64_* (the yardstick for the gradients)."""
+    import models
+    from ref_shim import Conf
+
+    torch.manual_seed(0)
+    conf = Conf(use_encoder=True, use_global_encoder=False, use_xyz=True, canon_xyz=False, use_code=True,
+                code=dict(num_freqs=6, freq_factor=1.5, include_input=True), use_viewdirs=True,
+                use_code_viewdirs=False, mlp_coarse=dict(type="resnet", n_blocks=3, d_hidden=512),
+                mlp_fine=dict(type="resnet", n_blocks=3, d_hidden=512),
+                encoder=dict(backbone="resnet34", pretrained=False, num_layers=4))
+    net = models.make_new_model(conf)
+    g = torch.Generator().manual_seed(11)
+
+    # ---- c512: the real encoder ----------------------------------------------------------
+    sb, ns, b, sl = 1, 2, 80, 24
+    src = torch.rand(sb, ns, 3, sl, sl, generator=g) * 2 - 1
+    c2w = _source_poses(ns, seed=3).reshape(sb, ns, 4, 4)
+    with torch.no_grad():
+        net.encode(src, c2w, torch.tensor(131.25 / 128 * sl))                  # train.py:68
+    xyz = torch.randn(sb, b, 3, generator=g) * 0.25
+    vd = torch.nn.functional.normalize(torch.randn(sb, b, 3, generator=g), dim=-1)
+    g_out = torch.randn(sb * ns * b, 512 + 42, generator=g)
+    state = dict(poses=net.poses.clone(), focal=net.focal.clone(), c=net.c.clone(), image_shape=net.image_shape.clone(),
+                 latent=net.encoder.latent.detach().clone(), latent_scaling=net.encoder.latent_scaling.clone(),
+                 freqs=net.code._freqs.clone(), phases=net.code._phases.clone())
+    out, feats, d_lat, d_xyz, d_vd = _run_field_front_end(net, xyz, vd, g_out, torch.float32)
+    save("field_inputs_c512", xyz=xyz, viewdirs=vd, g_out=g_out, ns=ns, normalize_z=1, **state,
+         ref_out=out, ref_features=feats, ref_d_latent=d_lat, ref_d_xyz=d_xyz, ref_d_viewdirs=d_vd)
+
+    # ---- small: module state set by hand --------------------------------------------------
+    sb, ns, b, ch, h, w = 2, 3, 50, 64, 8, 10
+    nv = sb * ns
+    c2w = _source_poses(nv, seed=7)
+    rot = c2w[:, :3, :3].transpose(1, 2)
+    net.poses = torch.cat((rot, -torch.bmm(rot, c2w[:, :3, 3:])), dim=-1)      # models.py:705-707
+    net.num_views_per_obj = ns
+    net.image_shape = torch.tensor([40.0, 32.0])                               # [W, H]
+    net.focal = torch.tensor([[40.0, -40.0], [47.0, -44.0]])                   # per object, y negated (:721-722)
+    net.c = torch.tensor([[20.0, 16.0], [18.5, 17.25]])
+    net.encoder.latent = torch.randn(nv, ch, h, w, generator=g)
+    ls = torch.tensor([float(w), float(h)])
+    net.encoder.latent_scaling = ls / (ls - 1) * 2.0                           # :325-327
+    net.latent_size = ch
+    net.normalize_z = False
+    xyz = torch.randn(sb, b, 3, generator=g) * 0.25
+    xyz[:, ::3] *= 4.0                                                        # these leave the image
+    vd = torch.nn.functional.normalize(torch.randn(sb, b, 3, generator=g), dim=-1)
+    g_out = torch.randn(nv * b, ch + 42, generator=g)
+    state = dict(poses=net.poses.clone(), focal=net.focal.clone(), c=net.c.clone(), image_shape=net.image_shape.clone(),
+                 latent=net.encoder.latent.clone(), latent_scaling=net.encoder.latent_scaling.clone(),
+                 freqs=net.code._freqs.clone(), phases=net.code._phases.clone())
+    out, feats, d_lat, d_xyz, d_vd = _run_field_front_end(net, xyz, vd, g_out, torch.float32)
+    # the same reference code in fp64
+    net64 = net.double()
+    for name in ("poses", "focal", "c", "image_shape"):
+        setattr(net64, name, state[name].double())
+    net64.encoder.latent = state["latent"].double()
+    net64.encoder.latent_scaling = state["latent_scaling"].double()
+    out64, _, d_lat64, d_xyz64, d_vd64 = _run_field_front_end(net64, xyz, vd, g_out, torch.float64)
+    save("field_inputs_small", xyz=xyz, viewdirs=vd, g_out=g_out, ns=ns, normalize_z=0, **state,
+         ref_out=out, ref_features=feats, ref_d_latent=d_lat, ref_d_xyz=d_xyz, ref_d_viewdirs=d_vd,
+         ref64_out=out64, ref64_d_latent=d_lat64, ref64_d_xyz=d_xyz64, ref64_d_viewdirs=d_vd64)
+
+
 def main():
     ref = ref_shim.load()
     torch.set_num_threads(1)   # one thread: reductions are order-stable across machines
+    only = sys.argv[1:]        # optional: names of the cases to regenerate (e.g. field_inputs)
+    if only:
+        for name in only:
+            globals()["case_" + name](ref)
+        return
     case_coarse(ref)
     case_composite(ref)
     case_fine(ref)
@@ -333,6 +444,7 @@ def main():
     case_adaptive_renderer(ref)
     case_geometry(ref)
     case_pixelnerf_replay(ref)
+    case_field_inputs(ref)
 
 
 if __name__ == "__main__":

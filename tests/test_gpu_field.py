@@ -1,0 +1,141 @@
+"""Radiance-field front end on the GPU (csrc/field_inputs.cu through
+the C ABI): the fixtures the reference's own NewPixelNeRFNet.forward produced
+(oracle/make_golden.py case_field_inputs), ray-ordered points against the oracle (the register
+caches are reused there), and the drop-in `fuse_field_inputs` around a module with the
+reference's attribute names.  The same per-lane code is walked on the host in the CPU suite
+(tests/test_host_kernel_cores.py); these tests confirm the launches."""
+import math
+
+import pytest
+import torch
+
+import field_oracle as FO
+from conftest import assert_close
+from field_stub import StubNet, ray_ordered_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(d):
+    from avr_b200 import field
+    scale = (d["latent_scaling"] / d["image_shape"]).tolist()
+    return field.FieldConfig(ns=int(d["ns"]), scale=(scale[0], scale[1]), freqs=tuple(d["freqs"].reshape(-1).tolist()),
+                             phases=tuple(d["phases"].reshape(-1).tolist()), include_input=True,
+                             normalize_z=bool(int(d.get("normalize_z", 1))), use_viewdirs=True)
+
+
+def _xyz_bound(err, ref):
+    """d_xyz: magnitude-scaled bound (the reference's own fp32 is 34x outside 1e-5/1e-6 against its
+    fp64 evaluation, fixture ref64_d_xyz; see tests/test_host_kernel_cores.py)."""
+    return bool((err <= 1e-5 * ref.abs() + 2e-6 * ref.abs().max()).all())
+
+
+@pytest.mark.parametrize("name", ["field_inputs_c512", "field_inputs_small"])
+def test_field_inputs_golden(name, golden, dev):
+    from avr_b200 import field_inputs
+    d = golden(name)
+    cfg = _cfg(d)
+    xyz = d["xyz"].to(dev).requires_grad_(True)
+    vd = d["viewdirs"].to(dev).requires_grad_(True)
+    lat = d["latent"].to(dev).requires_grad_(True)
+    nhwc = lat.permute(0, 2, 3, 1).contiguous()
+    poses, focal, c = d["poses"].to(dev), d["focal"].to(dev), d["c"].to(dev)
+    out = field_inputs(xyz, vd, nhwc, poses, focal, c, cfg)
+    ch = lat.shape[1]
+    # same operation order as torch-CPU: the features, raw coordinates and view directions agree to
+    # the last bit on the host walk; here they are held to the north-star bar, the sines to 1 ulp
+    assert_close(out, d["ref_out"], what="mlp input")
+    assert float((out[:, :ch].cpu() - d["ref_out"][:, :ch]).abs().max()) <= 1e-6
+    feats = field_inputs(xyz, vd, nhwc, poses, focal, c, cfg, features_only=True)
+    assert_close(feats, d["ref_features"], what="features")
+    out.backward(d["g_out"].to(dev))
+    assert_close(lat.grad, d["ref_d_latent"], what="d_latent")
+    assert_close(vd.grad, d["ref_d_viewdirs"], what="d_viewdirs")
+    ref = d["ref_d_xyz"]
+    err = (xyz.grad.cpu() - ref).abs()
+    assert _xyz_bound(err, ref), float(err.max())
+    if "ref64_d_xyz" in d:
+        r64 = d["ref64_d_xyz"]
+        assert float((xyz.grad.cpu().double() - r64).abs().max()) <= 2 * float((ref.double() - r64).abs().max())
+
+
+@pytest.mark.parametrize("ch,needs", [(512, "all"), (256, "all"), (128, "latent"), (64, "all"), (512, "points")])
+def test_field_inputs_ray_ordered_vs_oracle(ch, needs, dev):
+    """Every channel-count variant of the kernels (register caches for 128/256/512, the generic
+    walk otherwise) and every gradient subset, on samples ordered along rays."""
+    from avr_b200 import field_inputs
+    d = ray_ordered_case(sb=2, ns=2, rays=40, k=64, ch=ch, h=16, w=12, seed=ch)
+    cfg = _cfg(d)
+    xyz_c, vd_c, lat_c = (d[k].clone().requires_grad_(True) for k in ("xyz", "viewdirs", "latent"))
+    want = FO.field_inputs(xyz_c, vd_c, d["poses"], d["focal"], d["c"], d["image_shape"], lat_c, d["latent_scaling"],
+                           d["freqs"], d["phases"], ns=d["ns"])
+    want.backward(d["g_out"])
+    xyz = d["xyz"].to(dev).requires_grad_(needs != "latent")
+    vd = d["viewdirs"].to(dev).requires_grad_(needs != "latent")
+    lat = d["latent"].to(dev).requires_grad_(needs != "points")
+    out = field_inputs(xyz, vd, lat.permute(0, 2, 3, 1).contiguous(), d["poses"].to(dev), d["focal"].to(dev), d["c"].to(dev), cfg)
+    assert_close(out, want, what="mlp input")
+    out.backward(d["g_out"].to(dev))
+    if needs != "points":
+        assert_close(lat.grad, lat_c.grad, rtol=2e-5, atol=2e-6 * float(lat_c.grad.abs().max()), what="d_latent")
+    else:
+        assert lat.grad is None
+    if needs != "latent":
+        assert_close(vd.grad, vd_c.grad, what="d_viewdirs")
+        err = (xyz.grad.cpu() - xyz_c.grad).abs()
+        assert _xyz_bound(err, xyz_c.grad), float(err.max())
+    else:
+        assert xyz.grad is None and vd.grad is None
+
+
+def test_fuse_field_inputs_drop_in(dev):
+    """`fuse_field_inputs` rebinds forward on the module itself: same signature, same outputs, and
+    the gradients reach the encoder's and the MLP's parameters as through the stock torch path."""
+    import copy
+    import avr_b200
+    from fields import camera_setup
+    torch.manual_seed(0)
+    cpu_net = StubNet()
+    gpu_net = avr_b200.fuse_field_inputs(copy.deepcopy(cpu_net).to(dev))
+    assert set(gpu_net.state_dict()) == set(cpu_net.state_dict())
+    sb, ns, b = 2, 2, 300
+    g = torch.Generator().manual_seed(1)
+    images = torch.rand(sb, ns, 3, 20, 24, generator=g) * 2 - 1
+    c2w = camera_setup(sb * ns, 1, seed=4)[0][:, 0].reshape(sb, ns, 4, 4)
+    xyz = torch.randn(sb, b, 3, generator=g) * 0.25
+    vd = torch.nn.functional.normalize(torch.randn(sb, b, 3, generator=g), dim=-1)
+    g_out = torch.randn(sb, b, 4, generator=g)
+    cpu_net.encode(images, c2w, 24.0)
+    gpu_net.encode(images.to(dev), c2w.to(dev), 24.0)
+    for coarse in (True, False):
+        want = cpu_net(xyz, coarse=coarse, viewdirs=vd)
+        got = gpu_net(xyz.to(dev), coarse=coarse, viewdirs=vd.to(dev))
+        assert_close(got, want, rtol=1e-5, atol=2e-6, what=f"field output coarse={coarse}")
+    assert_close(gpu_net(xyz.to(dev), viewdirs=vd.to(dev), return_features=True),
+                 cpu_net(xyz, viewdirs=vd, return_features=True), what="return_features")
+    cpu_net(xyz, coarse=True, viewdirs=vd).backward(g_out)
+    gpu_net(xyz.to(dev), coarse=True, viewdirs=vd.to(dev)).backward(g_out.to(dev))
+    for (name, p), (_, q) in zip(gpu_net.named_parameters(), cpu_net.named_parameters()):
+        if "mlp_fine" in name:
+            continue
+        assert_close(p.grad, q.grad, rtol=1e-4, atol=1e-5 * float(q.grad.abs().max()) + 1e-7, what=name)
+    # a second encode() is picked up (new feature map, new camera state)
+    gpu_net.encode(images.flip(0).to(dev), c2w.to(dev), 24.0)
+    cpu_net.encode(images.flip(0), c2w, 24.0)
+    assert_close(gpu_net(xyz.to(dev), viewdirs=vd.to(dev)), cpu_net(xyz, viewdirs=vd), rtol=1e-5, atol=2e-6, what="after re-encode")
+
+
+def test_field_inputs_refuses_cpu_and_bad_shapes(dev):
+    import avr_b200
+    from avr_b200 import field_inputs, FieldConfig
+    cfg = FieldConfig(ns=1, scale=(0.1, 0.1), freqs=(1.5,) * 12, phases=(0.0,) * 12)
+    x = torch.zeros(1, 5, 3)
+    with pytest.raises(avr_b200.AvrError):
+        field_inputs(x, x, torch.zeros(1, 4, 4, 8), torch.zeros(1, 3, 4), torch.ones(1, 2), torch.ones(1, 2), cfg)
+    xd = x.to(dev)
+    with pytest.raises(avr_b200.AvrError):      # two feature maps for one object x one view
+        field_inputs(xd, xd, torch.zeros(2, 4, 4, 8, device=dev), torch.zeros(2, 3, 4, device=dev),
+                     torch.ones(1, 2, device=dev), torch.ones(1, 2, device=dev), cfg)
+    with pytest.raises(avr_b200.AvrError):      # channels not a multiple of 4
+        field_inputs(xd, xd, torch.zeros(1, 4, 4, 6, device=dev), torch.zeros(1, 3, 4, device=dev),
+                     torch.ones(1, 2, device=dev), torch.ones(1, 2, device=dev), cfg)

@@ -74,3 +74,61 @@ def test_volume_renderer_bit_exact(ref):
         got = O.render_volume(cam2world, intrinsics, x_pix, field, 0.8, 1.8, 64, 32, 16, 0.01, True, draws)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+class _KeepInput(torch.nn.Module):
+    """Stands in for the reference net's MLP: records the tensor the front end built."""
+
+    def forward(self, x, combine_inner_dims=(1,), **kw):
+        self.seen = x
+        return x.new_zeros(x.shape[0] // combine_inner_dims[0], 4) + 0 * x.sum()
+
+
+def test_field_front_end_bit_exact_and_config(ref):
+    """oracle/field_oracle.py against NewPixelNeRFNet.forward itself (models.py:754-826) on fresh
+    inputs: the MLP's input, the return_features path and the autograd gradients, bit for bit;
+    and the host-side logic that reads the launch constants off the reference module."""
+    import models
+    import field_oracle as FO
+    from avr_b200 import field
+    from ref_shim import Conf
+
+    torch.manual_seed(4)
+    conf = Conf(use_encoder=True, use_global_encoder=False, use_xyz=True, canon_xyz=False, use_code=True,
+                code=dict(num_freqs=6, freq_factor=1.5, include_input=True), use_viewdirs=True, use_code_viewdirs=False,
+                mlp_coarse=dict(type="resnet", n_blocks=1, d_hidden=32), mlp_fine=dict(type="resnet", n_blocks=1, d_hidden=32),
+                encoder=dict(backbone="resnet34", pretrained=False, num_layers=4))
+    net = models.make_new_model(conf)
+    sb, ns, b, sl = 2, 2, 37, 16
+    g = torch.Generator().manual_seed(8)
+    c2w = camera_setup(sb * ns, 1, seed=2)[0][:, 0].reshape(sb, ns, 4, 4)
+    with torch.no_grad():
+        net.encode(torch.rand(sb, ns, 3, sl, sl, generator=g) * 2 - 1, c2w, torch.tensor(131.25 / 128 * sl))
+    field._check_supported(net)
+    cfg = field._config_of(net)
+    assert cfg.ns == ns and len(cfg.freqs) == 12 and cfg.include_input and cfg.normalize_z and cfg.use_viewdirs
+    assert cfg.scale == tuple((net.encoder.latent_scaling / net.image_shape).tolist())
+    assert cfg.code_width() == net.d_in == 42
+    net.mlp_coarse = _KeepInput()
+    xyz = (torch.randn(sb, b, 3, generator=g) * 0.3).requires_grad_(True)
+    vd = torch.nn.functional.normalize(torch.randn(sb, b, 3, generator=g), dim=-1).requires_grad_(True)
+    lat = net.encoder.latent.detach().clone().requires_grad_(True)
+    net.encoder.latent = lat
+    net(xyz, coarse=True, viewdirs=vd)
+    want = net.mlp_coarse.seen
+    g_out = torch.randn(want.shape, generator=g)
+    want.backward(g_out)
+    grads = [t.grad.clone() for t in (xyz, vd, lat)]
+    for t in (xyz, vd, lat):
+        t.grad = None
+    args = (xyz, vd, net.poses, net.focal, net.c, net.image_shape, lat, net.encoder.latent_scaling, net.code._freqs, net.code._phases)
+    got = FO.field_inputs(*args, ns=ns)
+    assert torch.equal(got, want)
+    got.backward(g_out)
+    assert all(torch.equal(t.grad, w) for t, w in zip((xyz, vd, lat), grads))
+    with torch.no_grad():
+        assert torch.equal(FO.field_inputs(*args, ns=ns, features_only=True), net(xyz, viewdirs=vd, return_features=True))
+    # configurations outside the kernels' family are refused up front
+    net.use_global_encoder = True
+    with pytest.raises(field.AvrError):
+        field.fuse_field_inputs(net)
