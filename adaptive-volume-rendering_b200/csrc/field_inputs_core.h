@@ -60,44 +60,94 @@ inline int field_code_width(const FieldInputsArgs& a) {
   return (a.include_input ? 3 : 0) + 3 * a.n_sin + (a.use_viewdirs ? 3 : 0);
 }
 
-// Coordinates of one (view, point): everything that does not depend on the lane.
-struct FieldPoint {
-  float enc[3];   // what the positional code encodes (R p, or R p + t)
-  float vrot[3];  // R d
-  float cam[3];   // R p + t
-  float ix, iy;   // clipped pixel coordinates in the feature map
-  int x0, y0;     // floor
-  float nw, ne, sw, se;
-  bool clip_x, clip_y;  // coordinate was clamped (its gradient is zero)
+// Where a walk stands: row = v*B + b of the output, v = obj*NS + s.  Rows are visited in runs of
+// consecutive rows, so the (64-bit) divisions happen once per run, not once per row.
+struct FieldCursor {
+  int64_t row, v, b, obj;
 };
 
-AVR_FI void rotate3(const float* R, float x, float y, float z, float* o) {
-  // (R[i][0]*x + R[i][1]*y) + R[i][2]*z, products and sums rounded one by one; rows are 4 floats apart
-  for (int i = 0; i < 3; ++i)
-    o[i] = fi_add(fi_add(fi_mul(R[4 * i], x), fi_mul(R[4 * i + 1], y)), fi_mul(R[4 * i + 2], z));
+AVR_FI FieldCursor field_cursor_at(const FieldInputsArgs& a, int64_t row) {
+  FieldCursor c;
+  c.row = row;
+  c.v = row / a.B;
+  c.b = row - c.v * a.B;
+  c.obj = c.v / a.NS;
+  return c;
 }
 
-AVR_FI FieldPoint field_point(const FieldInputsArgs& a, int64_t v, int64_t b) {
-  FieldPoint p;
-  const int64_t obj = v / a.NS;
-  const float* R = a.poses + v * 12;
-  const float* w = a.xyz + (obj * a.B + b) * 3;
-  float rot[3];
-  rotate3(R, w[0], w[1], w[2], rot);
-  for (int i = 0; i < 3; ++i) {
-    p.cam[i] = fi_add(rot[i], R[4 * i + 3]);
-    p.enc[i] = a.normalize_z ? rot[i] : p.cam[i];
+AVR_FI void field_cursor_next(const FieldInputsArgs& a, FieldCursor* c) {
+  ++c->row;
+  if (++c->b == a.B) {
+    c->b = 0;
+    ++c->v;
+    c->obj = c->v / a.NS;
   }
-  p.vrot[0] = p.vrot[1] = p.vrot[2] = 0.f;
+}
+
+// Per-view constants, kept in registers while consecutive rows belong to one source view.
+struct FieldView {
+  float R[12];          // world -> view, rows of 4 (rotation | translation)
+  float fx, fy, cx, cy;
+  int64_t v;
+};
+
+AVR_FI void field_view_reset(FieldView* w) { w->v = -1; }
+
+AVR_FI void field_view_fill(const FieldInputsArgs& a, const FieldCursor& cur, FieldView* w) {
+  if (w->v == cur.v) return;  // warp-uniform
+  w->v = cur.v;
+  const float* R = a.poses + cur.v * 12;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 12; ++i) w->R[i] = R[i];
+  const float* f = a.focal + (a.focal_per_obj ? cur.obj * 2 : 0);
+  const float* c = a.c + (a.c_per_obj ? cur.obj * 2 : 0);
+  w->fx = f[0];
+  w->fy = f[1];
+  w->cx = c[0];
+  w->cy = c[1];
+}
+
+// Coordinates of one (view, point): everything that does not depend on the lane.
+struct FieldPoint {
+  float enc0, enc1, enc2;     // what the positional code encodes (R p, or R p + t)
+  float vrot0, vrot1, vrot2;  // R d
+  float cam0, cam1, cam2;     // R p + t
+  float ix, iy;               // clipped pixel coordinates in the feature map
+  int x0, y0;                 // floor
+  float nw, ne, sw, se;
+  bool clip_x, clip_y;        // coordinate was clamped (its gradient is zero)
+};
+
+// row i of R times (x, y, z): (R[i][0]*x + R[i][1]*y) + R[i][2]*z, products and sums rounded one
+// by one (torch-CPU's small-matrix bmm loop)
+AVR_FI float rot_row(const float* R, int i, float x, float y, float z) {
+  return fi_add(fi_add(fi_mul(R[4 * i], x), fi_mul(R[4 * i + 1], y)), fi_mul(R[4 * i + 2], z));
+}
+
+AVR_FI FieldPoint field_point(const FieldInputsArgs& a, const FieldCursor& cur, const FieldView& w) {
+  FieldPoint p;
+  const float* q = a.xyz + (cur.obj * a.B + cur.b) * 3;
+  const float x = q[0], y = q[1], z = q[2];
+  const float r0 = rot_row(w.R, 0, x, y, z), r1 = rot_row(w.R, 1, x, y, z), r2 = rot_row(w.R, 2, x, y, z);
+  p.cam0 = fi_add(r0, w.R[3]);
+  p.cam1 = fi_add(r1, w.R[7]);
+  p.cam2 = fi_add(r2, w.R[11]);
+  p.enc0 = a.normalize_z ? r0 : p.cam0;
+  p.enc1 = a.normalize_z ? r1 : p.cam1;
+  p.enc2 = a.normalize_z ? r2 : p.cam2;
+  p.vrot0 = p.vrot1 = p.vrot2 = 0.f;
   if (a.use_viewdirs && !a.features_only) {
-    const float* d = a.viewdirs + (obj * a.B + b) * 3;
-    rotate3(R, d[0], d[1], d[2], p.vrot);
+    const float* d = a.viewdirs + (cur.obj * a.B + cur.b) * 3;
+    const float dx = d[0], dy = d[1], dz = d[2];
+    p.vrot0 = rot_row(w.R, 0, dx, dy, dz);
+    p.vrot1 = rot_row(w.R, 1, dx, dy, dz);
+    p.vrot2 = rot_row(w.R, 2, dx, dy, dz);
   }
   // uv = -xy / z; uv *= focal; uv += c; uv = uv * scale - 1          models.py:803-811, :268-270
-  const float* f = a.focal + (a.focal_per_obj ? obj * 2 : 0);
-  const float* c = a.c + (a.c_per_obj ? obj * 2 : 0);
-  const float u = fi_sub(fi_mul(fi_add(fi_mul(fi_div(-p.cam[0], p.cam[2]), f[0]), c[0]), a.scale_x), 1.0f);
-  const float t = fi_sub(fi_mul(fi_add(fi_mul(fi_div(-p.cam[1], p.cam[2]), f[1]), c[1]), a.scale_y), 1.0f);
+  const float u = fi_sub(fi_mul(fi_add(fi_mul(fi_div(-p.cam0, p.cam2), w.fx), w.cx), a.scale_x), 1.0f);
+  const float t = fi_sub(fi_mul(fi_add(fi_mul(fi_div(-p.cam1, p.cam2), w.fy), w.cy), a.scale_y), 1.0f);
   // grid_sample, align_corners=True, padding_mode="border": x = (u + 1) * ((W-1)/2), clamped
   const float mx = (float)(a.W - 1), my = (float)(a.H - 1);
   const float ux = fi_mul(fi_add(u, 1.0f), mx / 2), uy = fi_mul(fi_add(t, 1.0f), my / 2);
@@ -117,20 +167,53 @@ AVR_FI FieldPoint field_point(const FieldInputsArgs& a, int64_t v, int64_t b) {
   return p;
 }
 
-// v[d] by selects (a run-time index would put the array into local memory)
-AVR_FI float pick3(const float* v, int d) { return d == 0 ? v[0] : (d == 1 ? v[1] : v[2]); }
+AVR_FI float pick3(float v0, float v1, float v2, int d) { return d == 0 ? v0 : (d == 1 ? v1 : v2); }
 
-// Entry e of the code part of a row: [enc (3) | sin rows (3 per row) | view direction (3)]
-AVR_FI float field_code_entry(const FieldInputsArgs& a, const FieldPoint& p, int e) {
-  if (a.include_input) {
-    if (e < 3) return p.enc[e];
-    e -= 3;
+// The code part of a row is [enc (3) | sin rows (3 per row) | view direction (3)]; lane l owns
+// entries l and l + 32.  What those entries are does not change from row to row:
+struct FieldLaneCode {
+  int kind[2];   // 0: none, 1: enc[d], 2: sin(enc[d] * freq + phase), 3: vrot[d]
+  int d[2];
+  float freq[2], phase[2];
+};
+
+AVR_FI FieldLaneCode field_lane_code(const FieldInputsArgs& a, int lane) {
+  FieldLaneCode lc;
+  const int width = field_code_width(a);
+  for (int s = 0; s < 2; ++s) {
+    int e = lane + 32 * s;
+    lc.kind[s] = 0;
+    lc.d[s] = 0;
+    lc.freq[s] = lc.phase[s] = 0.f;
+    if (e >= width || a.features_only) continue;
+    if (a.include_input) {
+      if (e < 3) {
+        lc.kind[s] = 1;
+        lc.d[s] = e;
+        continue;
+      }
+      e -= 3;
+    }
+    if (e < 3 * a.n_sin) {
+      const int k = e / 3;
+      lc.kind[s] = 2;
+      lc.d[s] = e - 3 * k;
+      lc.freq[s] = a.freqs[k];
+      lc.phase[s] = a.phases[k];
+    } else {
+      lc.kind[s] = 3;
+      lc.d[s] = e - 3 * a.n_sin;
+    }
   }
-  if (e < 3 * a.n_sin) {
-    const int k = e / 3, d = e - 3 * k;
-    return sinf(fi_fma(pick3(p.enc, d), a.freqs[k], a.phases[k]));  // addcmul(phases, x, freqs) then sin, :66-67
-  }
-  return pick3(p.vrot, e - 3 * a.n_sin);
+  return lc;
+}
+
+// slot s of this lane's code entries; addcmul(phases, x, freqs) is one fused multiply-add, then sin (:66-67)
+AVR_FI float field_code_value(const FieldLaneCode& lc, int s, const FieldPoint& p) {
+  const float x = pick3(p.enc0, p.enc1, p.enc2, lc.d[s]);
+  if (lc.kind[s] == 2) return sinf(fi_fma(x, lc.freq[s], lc.phase[s]));
+  if (lc.kind[s] == 1) return x;
+  return pick3(p.vrot0, p.vrot1, p.vrot2, lc.d[s]);
 }
 
 // One bilinear tap row: address of channel 0 of texel (x, y) of view v, or null outside the map
@@ -207,14 +290,13 @@ AVR_FI void field_cache_fill(const FieldInputsArgs& a, const FieldPoint& p, int6
   }
 }
 
-// Row `row` = v*B + b of the output.  The row stride is even (C and the code width are checked by
-// the launcher), so 8-byte stores are always aligned; 16-byte ones would not be (554 floats).
+// One row of the output, lane `lane`.  The row stride is even (checked by the launcher), so
+// 8-byte stores are always aligned; 16-byte ones would not be (554 floats per row).
 template <int CPL>
-AVR_FI void field_row_lane(const FieldInputsArgs& a, int64_t row, int lane, int row_stride, FieldTapCache<CPL>* c) {
-  const int64_t v = row / a.B, b = row - v * a.B;
-  const FieldPoint p = field_point(a, v, b);
-  field_cache_fill<CPL>(a, p, v, lane, c);
-  float* out = a.out + row * row_stride;
+AVR_FI void field_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
+                           int row_stride, const FieldLaneCode& lc, FieldTapCache<CPL>* c) {
+  field_cache_fill<CPL>(a, p, cur.v, lane, c);
+  float* out = a.out + cur.row * row_stride;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -227,37 +309,34 @@ AVR_FI void field_row_lane(const FieldInputsArgs& a, int64_t row, int lane, int 
     field_store2(out + 4 * lane + 128 * i, o[0], o[1]);
     field_store2(out + 4 * lane + 128 * i + 2, o[2], o[3]);
   }
-  if (!a.features_only) {
-    const int width = field_code_width(a);
-    for (int e = lane; e < width; e += 32) out[a.C + e] = field_code_entry(a, p, e);
-  }
+  if (lc.kind[0]) out[a.C + lane] = field_code_value(lc, 0, p);
+  if (lc.kind[1]) out[a.C + lane + 32] = field_code_value(lc, 1, p);
 }
 
 // Any C % 4 == 0 (no tap cache): lanes stride over the float4 groups of the row.
-AVR_FI void field_row_lane_generic(const FieldInputsArgs& a, int64_t row, int lane, int row_stride) {
-  const int64_t v = row / a.B, b = row - v * a.B;
-  const FieldPoint p = field_point(a, v, b);
-  float* out = a.out + row * row_stride;
-  const float* rows[4];
-  for (int k = 0; k < 4; ++k) rows[k] = field_tap(a, v, p.x0 + (k & 1), p.y0 + (k >> 1));
+AVR_FI void field_row_lane_generic(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
+                                   int row_stride, const FieldLaneCode& lc) {
+  float* out = a.out + cur.row * row_stride;
+  const float* r0 = field_tap(a, cur.v, p.x0, p.y0);
+  const float* r1 = field_tap(a, cur.v, p.x0 + 1, p.y0);
+  const float* r2 = field_tap(a, cur.v, p.x0, p.y0 + 1);
+  const float* r3 = field_tap(a, cur.v, p.x0 + 1, p.y0 + 1);
   for (int g = lane; g < a.C / 4; g += 32) {
-    float t[4][4];
-    for (int k = 0; k < 4; ++k) {
-      if (rows[k]) {
-        field_load4(rows[k] + 4 * g, t[k]);
-      } else {
-        t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0.f;
-      }
-    }
+    float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f}, t3[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r0) field_load4(r0 + 4 * g, t0);
+    if (r1) field_load4(r1 + 4 * g, t1);
+    if (r2) field_load4(r2 + 4 * g, t2);
+    if (r3) field_load4(r3 + 4 * g, t3);
     float o[4];
-    for (int q = 0; q < 4; ++q) o[q] = field_blend(p, t[0][q], t[1][q], t[2][q], t[3][q]);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) o[q] = field_blend(p, t0[q], t1[q], t2[q], t3[q]);
     field_store2(out + 4 * g, o[0], o[1]);
     field_store2(out + 4 * g + 2, o[2], o[3]);
   }
-  if (!a.features_only) {
-    const int width = field_code_width(a);
-    for (int e = lane; e < width; e += 32) out[a.C + e] = field_code_entry(a, p, e);
-  }
+  if (lc.kind[0]) out[a.C + lane] = field_code_value(lc, 0, p);
+  if (lc.kind[1]) out[a.C + lane + 32] = field_code_value(lc, 1, p);
 }
 
 // ---- backward --------------------------------------------------------------------------------
@@ -335,58 +414,49 @@ AVR_FI void field_grad_flush(const FieldInputsArgs& a, int lane, FieldGradCache<
 
 // Per-lane partial sums of one row that the warp has to add up.
 struct FieldRowPartial {
-  float gix, giy;   // d / d(ix, iy) over this lane's channels
-  float enc[3];     // d / d enc over this lane's code entries
-  float vrot[3];    // d / d vrot
+  float gix, giy;           // d / d(ix, iy) over this lane's channels
+  float enc0, enc1, enc2;   // d / d enc over this lane's code entries
+  float vr0, vr1, vr2;      // d / d vrot
 };
 
 AVR_FI void field_partial_zero(FieldRowPartial* s) {
   s->gix = s->giy = 0.f;
-  s->enc[0] = s->enc[1] = s->enc[2] = 0.f;
-  s->vrot[0] = s->vrot[1] = s->vrot[2] = 0.f;
+  s->enc0 = s->enc1 = s->enc2 = 0.f;
+  s->vr0 = s->vr1 = s->vr2 = 0.f;
 }
 
-// code entries of this lane: the mirror of field_code_entry
-AVR_FI void field_code_grad_lane(const FieldInputsArgs& a, const FieldPoint& p, const float* g_code, int lane,
+// this lane's two code entries: the mirror of field_code_value
+AVR_FI void field_code_grad_lane(const FieldLaneCode& lc, const FieldPoint& p, const float* g_code, int lane,
                                  FieldRowPartial* s) {
-  const int width = field_code_width(a);
-  for (int e0 = lane; e0 < width; e0 += 32) {
-    const float g = g_code[e0];
-    int e = e0;
-    if (a.include_input) {
-      if (e < 3) {
-        s->enc[0] += e == 0 ? g : 0.f;
-        s->enc[1] += e == 1 ? g : 0.f;
-        s->enc[2] += e == 2 ? g : 0.f;
-        continue;
-      }
-      e -= 3;
+  for (int slot = 0; slot < 2; ++slot) {
+    const int kind = lc.kind[slot], d = lc.d[slot];
+    if (kind == 0) continue;
+    const float g = g_code[lane + 32 * slot];
+    if (kind == 3) {
+      s->vr0 += d == 0 ? g : 0.f;
+      s->vr1 += d == 1 ? g : 0.f;
+      s->vr2 += d == 2 ? g : 0.f;
+      continue;
     }
-    if (e < 3 * a.n_sin) {
-      const int k = e / 3, d = e - 3 * k;
-      const float t = g * cosf(fi_fma(pick3(p.enc, d), a.freqs[k], a.phases[k])) * a.freqs[k];
-      s->enc[0] += d == 0 ? t : 0.f;
-      s->enc[1] += d == 1 ? t : 0.f;
-      s->enc[2] += d == 2 ? t : 0.f;
-    } else {
-      const int d = e - 3 * a.n_sin;
-      s->vrot[0] += d == 0 ? g : 0.f;
-      s->vrot[1] += d == 1 ? g : 0.f;
-      s->vrot[2] += d == 2 ? g : 0.f;
-    }
+    float t = g;
+    if (kind == 2) t = g * cosf(fi_fma(pick3(p.enc0, p.enc1, p.enc2, d), lc.freq[slot], lc.phase[slot])) * lc.freq[slot];
+    s->enc0 += d == 0 ? t : 0.f;
+    s->enc1 += d == 1 ? t : 0.f;
+    s->enc2 += d == 2 ? t : 0.f;
   }
 }
 
-// Lane `lane` of row `row`: accumulates into the d_latent cache (kLatent) and returns its partial
+// Lane `lane` of one row: accumulates into the d_latent cache (kLatent) and returns its partial
 // sums of the point gradient (kPoint; zero otherwise).  `taps` is the forward tap cache (read only
 // when kPoint).
 template <int CPL, bool kLatent, bool kPoint>
-AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, int64_t row, int lane, int row_stride,
-                                          const FieldPoint& p, FieldTapCache<CPL>* taps, FieldGradCache<CPL>* grads) {
-  const int64_t v = row / a.B;
+AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
+                                          int row_stride, const FieldLaneCode& lc, FieldTapCache<CPL>* taps,
+                                          FieldGradCache<CPL>* grads) {
+  const int64_t v = cur.v;
   FieldRowPartial s;
   field_partial_zero(&s);
-  const float* g_row = a.g_out + row * row_stride;
+  const float* g_row = a.g_out + cur.row * row_stride;
   if (kPoint) field_cache_fill<CPL>(a, p, v, lane, taps);
   if (kLatent && !(grads->x0 == p.x0 && grads->y0 == p.y0 && grads->v == v)) {  // warp-uniform
     field_grad_flush<CPL>(a, lane, grads);
@@ -429,57 +499,56 @@ AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, int64_t row,
       }
     }
   }
-  if (kPoint && !a.features_only) field_code_grad_lane(a, p, g_row + a.C, lane, &s);
+  if (kPoint) field_code_grad_lane(lc, p, g_row + a.C, lane, &s);
   return s;
 }
 
 // Once per row, with the partials summed over the warp: chain rule through the projection and
 // the rigid transform, then atomic accumulation over the object's views.
-AVR_FI void field_bwd_row_finish(const FieldInputsArgs& a, int64_t row, const FieldPoint& p, const FieldRowPartial& s) {
-  const int64_t v = row / a.B, b = row - v * a.B;
-  const int64_t obj = v / a.NS;
-  const float* R = a.poses + v * 12;
-  const float* f = a.focal + (a.focal_per_obj ? obj * 2 : 0);
+AVR_FI void field_bwd_row_finish(const FieldInputsArgs& a, const FieldCursor& cur, const FieldView& w, const FieldPoint& p,
+                                 const FieldRowPartial& s) {
   // ix = clip((u + 1) (W-1)/2): zero gradient where clamped; u = (-x/z * fx + cx) * scale_x - 1
-  const float gu = p.clip_x ? 0.f : s.gix * ((float)(a.W - 1) / 2) * a.scale_x * f[0];
-  const float gt = p.clip_y ? 0.f : s.giy * ((float)(a.H - 1) / 2) * a.scale_y * f[1];
-  const float iz = 1.0f / p.cam[2];
-  float d_cam[3];
-  d_cam[0] = -gu * iz;
-  d_cam[1] = -gt * iz;
-  d_cam[2] = (gu * p.cam[0] + gt * p.cam[1]) * iz * iz;
-  for (int i = 0; i < 3; ++i) d_cam[i] += s.enc[i];  // enc is R p (+ t): same Jacobian as cam
+  const float gu = p.clip_x ? 0.f : s.gix * ((float)(a.W - 1) / 2) * a.scale_x * w.fx;
+  const float gt = p.clip_y ? 0.f : s.giy * ((float)(a.H - 1) / 2) * a.scale_y * w.fy;
+  const float iz = 1.0f / p.cam2;
+  // enc is R p (+ t): same Jacobian as cam
+  const float d0 = -gu * iz + s.enc0;
+  const float d1 = -gt * iz + s.enc1;
+  const float d2 = (gu * p.cam0 + gt * p.cam1) * iz * iz + s.enc2;
   if (a.d_xyz) {
-    float* dst = a.d_xyz + (obj * a.B + b) * 3;
-    for (int j = 0; j < 3; ++j) field_atomic_add(dst + j, R[j] * d_cam[0] + R[4 + j] * d_cam[1] + R[8 + j] * d_cam[2]);
+    float* dst = a.d_xyz + (cur.obj * a.B + cur.b) * 3;
+    for (int j = 0; j < 3; ++j) field_atomic_add(dst + j, w.R[j] * d0 + w.R[4 + j] * d1 + w.R[8 + j] * d2);
   }
   if (a.d_viewdirs && a.use_viewdirs && !a.features_only) {
-    float* dst = a.d_viewdirs + (obj * a.B + b) * 3;
-    for (int j = 0; j < 3; ++j) field_atomic_add(dst + j, R[j] * s.vrot[0] + R[4 + j] * s.vrot[1] + R[8 + j] * s.vrot[2]);
+    float* dst = a.d_viewdirs + (cur.obj * a.B + cur.b) * 3;
+    for (int j = 0; j < 3; ++j) field_atomic_add(dst + j, w.R[j] * s.vr0 + w.R[4 + j] * s.vr1 + w.R[8 + j] * s.vr2);
   }
 }
 
 // Any C % 4 == 0: no caches, every row adds straight into d_latent.
 template <bool kLatent, bool kPoint>
-AVR_FI FieldRowPartial field_bwd_row_lane_generic(const FieldInputsArgs& a, int64_t row, int lane, int row_stride,
-                                                  const FieldPoint& p) {
-  const int64_t v = row / a.B;
+AVR_FI FieldRowPartial field_bwd_row_lane_generic(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p,
+                                                  int lane, int row_stride, const FieldLaneCode& lc) {
+  const int64_t v = cur.v;
   FieldRowPartial s;
   field_partial_zero(&s);
-  const float* g_row = a.g_out + row * row_stride;
+  const float* g_row = a.g_out + cur.row * row_stride;
   const float wx = fi_sub(p.ix, (float)p.x0), ex = fi_sub(1.0f, wx);
   const float wy = fi_sub(p.iy, (float)p.y0), sy = fi_sub(1.0f, wy);
-  const float wk[4] = {p.nw, p.ne, p.sw, p.se};
   for (int grp = lane; grp < a.C / 4; grp += 32) {
     float g[4], t[4][4];
     field_load2(g_row + 4 * grp, g);
     field_load2(g_row + 4 * grp + 2, g + 2);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
     for (int k = 0; k < 4; ++k) {
       const int x = p.x0 + (k & 1), y = p.y0 + (k >> 1);
+      const float wk = k == 0 ? p.nw : (k == 1 ? p.ne : (k == 2 ? p.sw : p.se));
       if (kLatent) {
         float* dst = field_grad_tap(a, v, x, y);
         if (dst) {
-          const float c[4] = {g[0] * wk[k], g[1] * wk[k], g[2] * wk[k], g[3] * wk[k]};
+          const float c[4] = {g[0] * wk, g[1] * wk, g[2] * wk, g[3] * wk};
           field_atomic_add4(dst + 4 * grp, c);
         }
       }
@@ -493,13 +562,16 @@ AVR_FI FieldRowPartial field_bwd_row_lane_generic(const FieldInputsArgs& a, int6
       }
     }
     if (kPoint) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
       for (int q = 0; q < 4; ++q) {
         s.gix += g[q] * ((t[1][q] - t[0][q]) * sy + (t[3][q] - t[2][q]) * wy);
         s.giy += g[q] * ((t[2][q] - t[0][q]) * ex + (t[3][q] - t[1][q]) * wx);
       }
     }
   }
-  if (kPoint && !a.features_only) field_code_grad_lane(a, p, g_row + a.C, lane, &s);
+  if (kPoint) field_code_grad_lane(lc, p, g_row + a.C, lane, &s);
   return s;
 }
 

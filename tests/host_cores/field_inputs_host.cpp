@@ -10,22 +10,34 @@ namespace {
 
 template <int CPL>
 void walk_fwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_warps) {
+  constexpr int N = CPL > 0 ? CPL : 1;
   const int64_t rows = a.NV * a.B;
   const int64_t n_chunks = (rows + chunk - 1) / chunk;
   for (int warp = 0; warp < n_warps; ++warp) {
-    // the 32 lanes of a warp each carry their own cache (registers on the device)
-    avr::FieldTapCache<(CPL > 0 ? CPL : 1)> cache[32];
-    for (int l = 0; l < 32; ++l) avr::field_cache_reset(&cache[l]);
+    // per-lane state that lives in registers on the device
+    avr::FieldTapCache<N> cache[32];
+    avr::FieldView view[32];
+    avr::FieldLaneCode lc[32];
+    for (int l = 0; l < 32; ++l) {
+      avr::field_cache_reset(&cache[l]);
+      avr::field_view_reset(&view[l]);
+      lc[l] = avr::field_lane_code(a, l);
+    }
     for (int64_t ch = warp; ch < n_chunks; ch += n_warps) {
-      const int64_t first = ch * chunk, last = first + chunk < rows ? first + chunk : rows;
-      for (int64_t row = first; row < last; ++row)
-        for (int lane = 0; lane < 32; ++lane) {
+      const int64_t first = ch * chunk;
+      const int n = (int)(first + chunk < rows ? chunk : rows - first);
+      for (int lane = 0; lane < 32; ++lane) {
+        avr::FieldCursor cur = avr::field_cursor_at(a, first);
+        for (int r = 0; r < n; ++r, avr::field_cursor_next(a, &cur)) {
+          avr::field_view_fill(a, cur, &view[lane]);
+          const avr::FieldPoint p = avr::field_point(a, cur, view[lane]);
           if (CPL > 0) {
-            avr::field_row_lane<(CPL > 0 ? CPL : 1)>(a, row, lane, row_stride, &cache[lane]);
+            avr::field_row_lane<N>(a, cur, p, lane, row_stride, lc[lane], &cache[lane]);
           } else {
-            avr::field_row_lane_generic(a, row, lane, row_stride);
+            avr::field_row_lane_generic(a, cur, p, lane, row_stride, lc[lane]);
           }
         }
+      }
     }
   }
 }
@@ -38,32 +50,42 @@ void walk_bwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_wa
   for (int warp = 0; warp < n_warps; ++warp) {
     avr::FieldTapCache<N> taps[32];
     avr::FieldGradCache<N> grads[32];
+    avr::FieldView view[32];
+    avr::FieldLaneCode lc[32];
     for (int l = 0; l < 32; ++l) {
       avr::field_cache_reset(&taps[l]);
       avr::field_grad_reset(&grads[l]);
+      avr::field_view_reset(&view[l]);
+      lc[l] = avr::field_lane_code(a, l);
     }
     for (int64_t ch = warp; ch < n_chunks; ch += n_warps) {
-      const int64_t first = ch * chunk, last = first + chunk < rows ? first + chunk : rows;
-      for (int64_t row = first; row < last; ++row) {
-        const int64_t v = row / a.B;
-        const avr::FieldPoint p = avr::field_point(a, v, row - v * a.B);
+      const int64_t first = ch * chunk;
+      const int n = (int)(first + chunk < rows ? chunk : rows - first);
+      avr::FieldCursor cur = avr::field_cursor_at(a, first);
+      for (int r = 0; r < n; ++r, avr::field_cursor_next(a, &cur)) {
         avr::FieldRowPartial sum;
         avr::field_partial_zero(&sum);
+        avr::FieldPoint p0;
         for (int lane = 0; lane < 32; ++lane) {
+          avr::field_view_fill(a, cur, &view[lane]);
+          const avr::FieldPoint p = avr::field_point(a, cur, view[lane]);
+          if (lane == 0) p0 = p;
           avr::FieldRowPartial s;
           if (CPL > 0) {
-            s = avr::field_bwd_row_lane<N, kLatent, kPoint>(a, row, lane, row_stride, p, &taps[lane], &grads[lane]);
+            s = avr::field_bwd_row_lane<N, kLatent, kPoint>(a, cur, p, lane, row_stride, lc[lane], &taps[lane], &grads[lane]);
           } else {
-            s = avr::field_bwd_row_lane_generic<kLatent, kPoint>(a, row, lane, row_stride, p);
+            s = avr::field_bwd_row_lane_generic<kLatent, kPoint>(a, cur, p, lane, row_stride, lc[lane]);
           }
           sum.gix += s.gix;
           sum.giy += s.giy;
-          for (int i = 0; i < 3; ++i) {
-            sum.enc[i] += s.enc[i];
-            sum.vrot[i] += s.vrot[i];
-          }
+          sum.enc0 += s.enc0;
+          sum.enc1 += s.enc1;
+          sum.enc2 += s.enc2;
+          sum.vr0 += s.vr0;
+          sum.vr1 += s.vr1;
+          sum.vr2 += s.vr2;
         }
-        if (kPoint) avr::field_bwd_row_finish(a, row, p, sum);
+        if (kPoint) avr::field_bwd_row_finish(a, cur, view[0], p0, sum);  // lane 0 on the device
       }
     }
     if (kLatent && CPL > 0)

