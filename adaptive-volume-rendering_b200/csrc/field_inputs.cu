@@ -12,47 +12,133 @@
 
 namespace avr {
 
+constexpr bool kFieldStageDefault = false;  // measured: 0.127 ms staged vs 0.118 ms direct (L2 merges the half sectors)
 constexpr int kFieldWarps = 4;
-constexpr int kFieldChunk = 16;  // consecutive rows per warp visit: samples of one ray, same view
+// consecutive rows per warp visit (samples of one ray, same view): 32 when the lanes share out the
+// per-row coordinate work, 16 otherwise
+template <bool kShare>
+struct FieldChunk {
+  static constexpr int value = kShare ? 32 : 16;
+};
 
-template <int CPL>
+// kShare: the coordinate work of a row (field_point: two 3x3 products, the projection, two
+// divisions, the bilinear weights — ~100 instructions that do not depend on the lane) is done ONCE
+// per row instead of once per lane: lane l computes the point of row first + l of a 32-row chunk,
+// and the row loop fetches row r's values from lane r by shuffles.
+template <bool kFull>
+__device__ __forceinline__ FieldPoint point_from_lane(const FieldPoint& m, int src) {
+  FieldPoint p;
+#define AVR_BCAST(f) p.f = __shfl_sync(0xffffffffu, m.f, src)
+  AVR_BCAST(enc0); AVR_BCAST(enc1); AVR_BCAST(enc2);
+  AVR_BCAST(vrot0); AVR_BCAST(vrot1); AVR_BCAST(vrot2);
+  AVR_BCAST(x0); AVR_BCAST(y0);
+  AVR_BCAST(nw); AVR_BCAST(ne); AVR_BCAST(sw); AVR_BCAST(se);
+  if (kFull) {  // the backward pass also needs the camera-space point, the pixel coordinates and the clip flags
+    AVR_BCAST(cam0); AVR_BCAST(cam1); AVR_BCAST(cam2);
+    AVR_BCAST(ix); AVR_BCAST(iy);
+    const int clip = __shfl_sync(0xffffffffu, (m.clip_x ? 1 : 0) | (m.clip_y ? 2 : 0), src);
+    p.clip_x = (clip & 1) != 0;
+    p.clip_y = (clip & 2) != 0;
+  } else {
+    p.cam0 = p.cam1 = p.cam2 = p.ix = p.iy = 0.f;
+    p.clip_x = p.clip_y = false;
+  }
+#undef AVR_BCAST
+  return p;
+}
+
+// the point of row min(first + lane, rows - 1), with this lane's own view constants
+__device__ __forceinline__ FieldPoint point_of_my_row(const FieldInputsArgs& a, int64_t first, int lane, int64_t rows,
+                                                      FieldView* view) {
+  const int64_t mine = first + lane < rows ? first + lane : rows - 1;
+  const FieldCursor mc = field_cursor_at(a, mine);
+  field_view_fill(a, mc, view);
+  return field_point(a, mc, *view);
+}
+
+// kStage: rows leave through shared memory.  A lane's 16 channels of a row are 4 separate 16-byte
+// pieces, and rows are only 8-byte aligned, so direct stores are 8 bytes per lane at a 16-byte
+// stride: every 32-byte sector is written in two halves by two instructions (57 % of the roofline).
+// Staged, two consecutive rows (2 * row bytes: a multiple of 16, starting 16-byte aligned at even
+// rows) are assembled in a per-warp double buffer and leave as ONE bulk copy
+// (cp.async.bulk.global.shared::cta), full lines at a time.
+template <int CPL, bool kShare, bool kStage>
 __global__ void __launch_bounds__(kFieldWarps * 32, 4)
 field_inputs_fwd_kernel(const FieldInputsArgs a, int row_stride) {
+  extern __shared__ __align__(16) float s_stage[];  // [warp][2 slots][2 rows][row_stride]
   constexpr int N = CPL > 0 ? CPL : 1;
+  constexpr int kChunk = FieldChunk<kShare>::value;
   const int lane = threadIdx.x & 31;
   const int64_t rows = a.NV * a.B;
-  const int64_t n_chunks = (rows + kFieldChunk - 1) / kFieldChunk;
+  const int64_t n_chunks = (rows + kChunk - 1) / kChunk;
   const int64_t warps = (int64_t)gridDim.x * kFieldWarps;
   const FieldLaneCode lc = field_lane_code(a, lane);
+  float* stage = s_stage + (size_t)(threadIdx.x >> 5) * 4 * row_stride;
+  int slot = 0;
   FieldTapCache<N> cache;
   FieldView view;
   field_cache_reset(&cache);
   field_view_reset(&view);
   for (int64_t ch = blockIdx.x * (int64_t)kFieldWarps + (threadIdx.x >> 5); ch < n_chunks; ch += warps) {
-    const int64_t first = ch * kFieldChunk;
-    const int n = (int)(first + kFieldChunk < rows ? kFieldChunk : rows - first);
+    const int64_t first = ch * kChunk;  // even: pairs (r, r+1) of a chunk start at even rows
+    const int n = (int)(first + kChunk < rows ? kChunk : rows - first);
+    FieldPoint mine;
+    if (kShare) mine = point_of_my_row(a, first, lane, rows, &view);
     FieldCursor cur = field_cursor_at(a, first);
     for (int r = 0; r < n; ++r, field_cursor_next(a, &cur)) {
-      field_view_fill(a, cur, &view);
-      const FieldPoint p = field_point(a, cur, view);
-      if (CPL > 0) {
-        field_row_lane<N>(a, cur, p, lane, row_stride, lc, &cache);
+      FieldPoint p;
+      if (kShare) {
+        p = point_from_lane<false>(mine, r);
       } else {
-        field_row_lane_generic(a, cur, p, lane, row_stride, lc);
+        field_view_fill(a, cur, &view);
+        p = field_point(a, cur, view);
+      }
+      const bool paired = kStage && (r | 1) < n;  // both rows of the pair exist (only the very last row can be single)
+      float* out = a.out + cur.row * row_stride;
+      if (paired) {
+        if ((r & 1) == 0) {
+          if (lane == 0) bulk_wait_read<1>();  // the copy that last read this slot (two pairs ago) is done
+          __syncwarp();
+        }
+        out = stage + (size_t)(2 * slot + (r & 1)) * row_stride;
+      }
+      if (paired) {
+        if (CPL > 0) {
+          field_row_lane<N, false>(a, cur, p, lane, out, lc, &cache);
+        } else {
+          field_row_lane_generic<false>(a, cur, p, lane, out, lc);
+        }
+        if (r & 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            bulk_s2g(a.out + (cur.row - 1) * row_stride, stage + (size_t)2 * slot * row_stride, (uint32_t)row_stride * 8u);
+            bulk_commit();
+          }
+          slot ^= 1;
+        }
+      } else {
+        if (CPL > 0) {
+          field_row_lane<N, true>(a, cur, p, lane, out, lc, &cache);
+        } else {
+          field_row_lane_generic<true>(a, cur, p, lane, out, lc);
+        }
       }
     }
   }
+  if (kStage && lane == 0) bulk_wait_all<0>();
 }
 
 // one gradient kind per launch: capped at 170 registers (3 CTAs = 12 warps per SM; the uncapped 180 of
 // the feature-map variant left 8 and ran 0.219 instead of 0.194 ms)
-template <int CPL, bool kLatent, bool kPoint>
+template <int CPL, bool kLatent, bool kPoint, bool kShare>
 __global__ void __launch_bounds__(kFieldWarps * 32, (kLatent && kPoint) ? 1 : 3)
 field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
   constexpr int N = CPL > 0 ? CPL : 1;
+  constexpr int kChunk = FieldChunk<kShare>::value;
   const int lane = threadIdx.x & 31;
   const int64_t rows = a.NV * a.B;
-  const int64_t n_chunks = (rows + kFieldChunk - 1) / kFieldChunk;
+  const int64_t n_chunks = (rows + kChunk - 1) / kChunk;
   const int64_t warps = (int64_t)gridDim.x * kFieldWarps;
   const FieldLaneCode lc = field_lane_code(a, lane);
   FieldTapCache<N> taps;
@@ -62,12 +148,19 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
   field_grad_reset(&grads);
   field_view_reset(&view);
   for (int64_t ch = blockIdx.x * (int64_t)kFieldWarps + (threadIdx.x >> 5); ch < n_chunks; ch += warps) {
-    const int64_t first = ch * kFieldChunk;
-    const int n = (int)(first + kFieldChunk < rows ? kFieldChunk : rows - first);
+    const int64_t first = ch * kChunk;
+    const int n = (int)(first + kChunk < rows ? kChunk : rows - first);
+    FieldPoint mine;
+    if (kShare) mine = point_of_my_row(a, first, lane, rows, &view);
     FieldCursor cur = field_cursor_at(a, first);
     for (int r = 0; r < n; ++r, field_cursor_next(a, &cur)) {
-      field_view_fill(a, cur, &view);
-      const FieldPoint p = field_point(a, cur, view);
+      FieldPoint p;
+      if (kShare) {
+        p = point_from_lane<true>(mine, r);
+      } else {
+        field_view_fill(a, cur, &view);
+        p = field_point(a, cur, view);
+      }
       FieldRowPartial s;
       if (CPL > 0) {
         s = field_bwd_row_lane<N, kLatent, kPoint>(a, cur, p, lane, row_stride, lc, &taps, &grads);
@@ -86,7 +179,10 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
           s.vr1 += __shfl_xor_sync(0xffffffffu, s.vr1, d);
           s.vr2 += __shfl_xor_sync(0xffffffffu, s.vr2, d);
         }
-        if (lane == 0) field_bwd_row_finish(a, cur, view, p, s);
+        if (lane == 0) {
+          if (kShare) field_view_fill(a, cur, &view);  // lane 0's view is that of ITS row of the chunk
+          field_bwd_row_finish(a, cur, view, p, s);
+        }
       }
     }
   }
@@ -94,29 +190,48 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
 }
 
 // Experiment knobs (A/B measurements; defaults are what the measurements picked):
-//   AVR_FIELD_NOCACHE=1    every channel count takes the generic walk (no register caches)
-//   AVR_FIELD_BWD_SPLIT=0  feature-map and point gradients in ONE launch instead of two (234 registers,
-//                          8 resident warps/SM: 0.645 ms against 0.56 ms for the two launches)
+//   AVR_FIELD_NOCACHE=1      every channel count takes the generic walk (no register caches)
+//   AVR_FIELD_BWD_SPLIT=0    feature-map and point gradients in ONE launch instead of two (234 registers,
+//                            8 resident warps/SM: 0.645 ms against 0.56 ms for the two launches)
+//   AVR_FIELD_SHARE_POINT=x  per-row coordinate work shared out over the lanes (see point_from_lane)
+//   AVR_FIELD_STAGE=x        forward rows leave through shared memory and bulk copies (see kStage)
 static bool env_flag(const char* name, bool dflt) {
   const char* v = std::getenv(name);
   return (v && *v) ? (*v != '0') : dflt;
 }
 static bool field_no_cache() { return env_flag("AVR_FIELD_NOCACHE", false); }
 static bool field_bwd_split() { return env_flag("AVR_FIELD_BWD_SPLIT", true); }
+// unset: the measured defaults (forward and feature-map backward share, the point backward does not:
+// 0.346 vs 0.362 ms); 0 / 1 force every kernel one way
+static bool field_share_point(bool dflt) { return env_flag("AVR_FIELD_SHARE_POINT", dflt); }
+static bool field_stage_rows() { return env_flag("AVR_FIELD_STAGE", kFieldStageDefault); }
+
+static unsigned field_grid(int64_t rows, int chunk) {
+  const int64_t n_chunks = (rows + chunk - 1) / chunk;
+  int64_t blocks = (n_chunks + kFieldWarps - 1) / kFieldWarps;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (unsigned)(blocks > cap ? cap : blocks);
+}
+
+template <int CPL, bool kLatent, bool kPoint>
+static void launch_bwd_kernel(const FieldInputsArgs& a, int row_stride, bool share, cudaStream_t stream) {
+  const unsigned t = kFieldWarps * 32;
+  if (share) {
+    field_inputs_bwd_kernel<CPL, kLatent, kPoint, true><<<field_grid(a.NV * a.B, FieldChunk<true>::value), t, 0, stream>>>(a, row_stride);
+  } else {
+    field_inputs_bwd_kernel<CPL, kLatent, kPoint, false><<<field_grid(a.NV * a.B, FieldChunk<false>::value), t, 0, stream>>>(a, row_stride);
+  }
+}
 
 template <int CPL>
-static void launch_bwd_variant(const FieldInputsArgs& a, int row_stride, unsigned g, unsigned t, cudaStream_t stream) {
+static void launch_bwd_variant(const FieldInputsArgs& a, int row_stride, cudaStream_t stream) {
   const bool latent = a.d_latent != nullptr, point = a.d_xyz != nullptr || a.d_viewdirs != nullptr;
-  if (latent && point && field_bwd_split()) {
-    field_inputs_bwd_kernel<CPL, true, false><<<g, t, 0, stream>>>(a, row_stride);
-    field_inputs_bwd_kernel<CPL, false, true><<<g, t, 0, stream>>>(a, row_stride);
-  } else if (latent && point) {
-    field_inputs_bwd_kernel<CPL, true, true><<<g, t, 0, stream>>>(a, row_stride);
-  } else if (latent) {
-    field_inputs_bwd_kernel<CPL, true, false><<<g, t, 0, stream>>>(a, row_stride);
-  } else {
-    field_inputs_bwd_kernel<CPL, false, true><<<g, t, 0, stream>>>(a, row_stride);
+  if (latent && point && !field_bwd_split()) {
+    launch_bwd_kernel<CPL, true, true>(a, row_stride, field_share_point(false), stream);
+    return;
   }
+  if (latent) launch_bwd_kernel<CPL, true, false>(a, row_stride, field_share_point(true), stream);
+  if (point) launch_bwd_kernel<CPL, false, true>(a, row_stride, field_share_point(false), stream);
 }
 
 int launch_field_inputs_bwd(const FieldInputsArgs& a, int64_t SB, cudaStream_t stream) {
@@ -131,39 +246,52 @@ int launch_field_inputs_bwd(const FieldInputsArgs& a, int64_t SB, cudaStream_t s
     return AVR_ERR_LAUNCH;
   }
   if (rows == 0) return AVR_OK;
-  const int width = a.features_only ? 0 : field_code_width(a);
-  const int row_stride = a.C + width;
-  const int64_t n_chunks = (rows + kFieldChunk - 1) / kFieldChunk;
-  int64_t blocks = (n_chunks + kFieldWarps - 1) / kFieldWarps;
-  const int64_t cap = (int64_t)kNumSMs * 8;
-  if (blocks > cap) blocks = cap;
-  const unsigned g = (unsigned)blocks, t = kFieldWarps * 32;
+  const int row_stride = a.C + (a.features_only ? 0 : field_code_width(a));
   switch (field_no_cache() ? 0 : a.C) {
-    case 512: launch_bwd_variant<4>(a, row_stride, g, t, stream); break;
-    case 256: launch_bwd_variant<2>(a, row_stride, g, t, stream); break;
-    case 128: launch_bwd_variant<1>(a, row_stride, g, t, stream); break;
-    default: launch_bwd_variant<0>(a, row_stride, g, t, stream); break;
+    case 512: launch_bwd_variant<4>(a, row_stride, stream); break;
+    case 256: launch_bwd_variant<2>(a, row_stride, stream); break;
+    case 128: launch_bwd_variant<1>(a, row_stride, stream); break;
+    default: launch_bwd_variant<0>(a, row_stride, stream); break;
   }
   return check_launch();
+}
+
+template <int CPL, bool kShare>
+static int launch_fwd_variant(const FieldInputsArgs& a, int row_stride, cudaStream_t stream) {
+  const unsigned g = field_grid(a.NV * a.B, FieldChunk<kShare>::value), t = kFieldWarps * 32;
+  // staging buffer: 2 slots x 2 rows per warp; needs 16-byte aligned output and room in shared memory
+  const size_t smem = (size_t)kFieldWarps * 4 * row_stride * sizeof(float);
+  if (field_stage_rows() && aligned16(a.out) && smem <= 56 * 1024) {
+    auto kern = field_inputs_fwd_kernel<CPL, kShare, true>;
+    if (smem > 48 * 1024) {
+      const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) {
+        set_last_cuda_error(e);
+        return AVR_ERR_LAUNCH;
+      }
+    }
+    kern<<<g, t, smem, stream>>>(a, row_stride);
+  } else {
+    field_inputs_fwd_kernel<CPL, kShare, false><<<g, t, 0, stream>>>(a, row_stride);
+  }
+  return check_launch();
+}
+
+template <bool kShare>
+static int launch_fwd_share(const FieldInputsArgs& a, int row_stride, cudaStream_t stream) {
+  switch (field_no_cache() ? 0 : a.C) {
+    case 512: return launch_fwd_variant<4, kShare>(a, row_stride, stream);
+    case 256: return launch_fwd_variant<2, kShare>(a, row_stride, stream);
+    case 128: return launch_fwd_variant<1, kShare>(a, row_stride, stream);
+    default: return launch_fwd_variant<0, kShare>(a, row_stride, stream);
+  }
 }
 
 int launch_field_inputs_fwd(const FieldInputsArgs& a, cudaStream_t stream) {
   const int64_t rows = a.NV * a.B;
   if (rows == 0) return AVR_OK;
-  const int width = a.features_only ? 0 : field_code_width(a);
-  const int row_stride = a.C + width;
-  const int64_t n_chunks = (rows + kFieldChunk - 1) / kFieldChunk;
-  int64_t blocks = (n_chunks + kFieldWarps - 1) / kFieldWarps;
-  const int64_t cap = (int64_t)kNumSMs * 8;
-  if (blocks > cap) blocks = cap;
-  const unsigned g = (unsigned)blocks, t = kFieldWarps * 32;
-  switch (field_no_cache() ? 0 : a.C) {
-    case 512: field_inputs_fwd_kernel<4><<<g, t, 0, stream>>>(a, row_stride); break;
-    case 256: field_inputs_fwd_kernel<2><<<g, t, 0, stream>>>(a, row_stride); break;
-    case 128: field_inputs_fwd_kernel<1><<<g, t, 0, stream>>>(a, row_stride); break;
-    default: field_inputs_fwd_kernel<0><<<g, t, 0, stream>>>(a, row_stride); break;
-  }
-  return check_launch();
+  const int row_stride = a.C + (a.features_only ? 0 : field_code_width(a));
+  return field_share_point(true) ? launch_fwd_share<true>(a, row_stride, stream) : launch_fwd_share<false>(a, row_stride, stream);
 }
 
 }  // namespace avr

@@ -257,9 +257,15 @@ AVR_FI void field_load4(const float* src, float* dst) {
 #endif
 }
 
+// kStream: dst is global memory, written once (streaming hint); otherwise any address space
+template <bool kStream>
 AVR_FI void field_store2(float* dst, float x, float y) {
 #if defined(__CUDACC__)
-  __stcs(reinterpret_cast<float2*>(dst), make_float2(x, y));
+  if (kStream) {
+    __stcs(reinterpret_cast<float2*>(dst), make_float2(x, y));
+  } else {
+    *reinterpret_cast<float2*>(dst) = make_float2(x, y);
+  }
 #else
   dst[0] = x;
   dst[1] = y;
@@ -290,13 +296,13 @@ AVR_FI void field_cache_fill(const FieldInputsArgs& a, const FieldPoint& p, int6
   }
 }
 
-// One row of the output, lane `lane`.  The row stride is even (checked by the launcher), so
-// 8-byte stores are always aligned; 16-byte ones would not be (554 floats per row).
-template <int CPL>
-AVR_FI void field_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
-                           int row_stride, const FieldLaneCode& lc, FieldTapCache<CPL>* c) {
+// One row of the output, lane `lane`, written to `out` — the row's place in global memory
+// (kStream) or in a shared-memory staging buffer that a bulk copy takes to global memory.  Rows are
+// 8-byte aligned (the stride is even, checked by the launcher), not 16: 554 floats per row.
+template <int CPL, bool kStream>
+AVR_FI void field_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane, float* out,
+                           const FieldLaneCode& lc, FieldTapCache<CPL>* c) {
   field_cache_fill<CPL>(a, p, cur.v, lane, c);
-  float* out = a.out + cur.row * row_stride;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -306,17 +312,17 @@ AVR_FI void field_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, con
 #pragma unroll
 #endif
     for (int q = 0; q < 4; ++q) o[q] = field_blend(p, c->t[0][i][q], c->t[1][i][q], c->t[2][i][q], c->t[3][i][q]);
-    field_store2(out + 4 * lane + 128 * i, o[0], o[1]);
-    field_store2(out + 4 * lane + 128 * i + 2, o[2], o[3]);
+    field_store2<kStream>(out + 4 * lane + 128 * i, o[0], o[1]);
+    field_store2<kStream>(out + 4 * lane + 128 * i + 2, o[2], o[3]);
   }
   if (lc.kind[0]) out[a.C + lane] = field_code_value(lc, 0, p);
   if (lc.kind[1]) out[a.C + lane + 32] = field_code_value(lc, 1, p);
 }
 
 // Any C % 4 == 0 (no tap cache): lanes stride over the float4 groups of the row.
+template <bool kStream>
 AVR_FI void field_row_lane_generic(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
-                                   int row_stride, const FieldLaneCode& lc) {
-  float* out = a.out + cur.row * row_stride;
+                                   float* out, const FieldLaneCode& lc) {
   const float* r0 = field_tap(a, cur.v, p.x0, p.y0);
   const float* r1 = field_tap(a, cur.v, p.x0 + 1, p.y0);
   const float* r2 = field_tap(a, cur.v, p.x0, p.y0 + 1);
@@ -332,8 +338,8 @@ AVR_FI void field_row_lane_generic(const FieldInputsArgs& a, const FieldCursor& 
 #pragma unroll
 #endif
     for (int q = 0; q < 4; ++q) o[q] = field_blend(p, t0[q], t1[q], t2[q], t3[q]);
-    field_store2(out + 4 * g, o[0], o[1]);
-    field_store2(out + 4 * g + 2, o[2], o[3]);
+    field_store2<kStream>(out + 4 * g, o[0], o[1]);
+    field_store2<kStream>(out + 4 * g + 2, o[2], o[3]);
   }
   if (lc.kind[0]) out[a.C + lane] = field_code_value(lc, 0, p);
   if (lc.kind[1]) out[a.C + lane + 32] = field_code_value(lc, 1, p);

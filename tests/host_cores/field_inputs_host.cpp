@@ -31,10 +31,11 @@ void walk_fwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_wa
         for (int r = 0; r < n; ++r, avr::field_cursor_next(a, &cur)) {
           avr::field_view_fill(a, cur, &view[lane]);
           const avr::FieldPoint p = avr::field_point(a, cur, view[lane]);
+          float* out = a.out + cur.row * row_stride;
           if (CPL > 0) {
-            avr::field_row_lane<N>(a, cur, p, lane, row_stride, lc[lane], &cache[lane]);
+            avr::field_row_lane<N, true>(a, cur, p, lane, out, lc[lane], &cache[lane]);
           } else {
-            avr::field_row_lane_generic(a, cur, p, lane, row_stride, lc[lane]);
+            avr::field_row_lane_generic<true>(a, cur, p, lane, out, lc[lane]);
           }
         }
       }

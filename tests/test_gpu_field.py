@@ -16,6 +16,20 @@ from field_stub import StubNet, ray_ordered_case
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["default", "per_lane", "shared", "shared_staged"])
+def kernel_variant(request, monkeypatch):
+    """Every way the kernels are built (csrc/field_inputs.cu): a row's coordinate work done by each
+    lane for itself or once per row and fetched by shuffles (AVR_FIELD_SHARE_POINT), output rows
+    stored directly or staged in shared memory and sent by bulk copies (AVR_FIELD_STAGE)."""
+    if request.param == "default":          # what the library picks by itself
+        monkeypatch.delenv("AVR_FIELD_SHARE_POINT", raising=False)
+        monkeypatch.delenv("AVR_FIELD_STAGE", raising=False)
+    else:
+        monkeypatch.setenv("AVR_FIELD_SHARE_POINT", "0" if request.param == "per_lane" else "1")
+        monkeypatch.setenv("AVR_FIELD_STAGE", "1" if request.param == "shared_staged" else "0")
+    return request.param
+
+
 def _cfg(d):
     from avr_b200 import field
     scale = (d["latent_scaling"] / d["image_shape"]).tolist()
