@@ -12,6 +12,7 @@
 
 namespace avr {
 
+constexpr bool kFieldBwdPrefetchDefault = false;
 constexpr bool kFieldStageDefault = false;  // measured: 0.127 ms staged vs 0.118 ms direct (L2 merges the half sectors)
 constexpr int kFieldWarps = 4;
 // consecutive rows per warp visit (samples of one ray, same view): 32 when the lanes share out the
@@ -131,7 +132,9 @@ field_inputs_fwd_kernel(const FieldInputsArgs a, int row_stride) {
 
 // one gradient kind per launch: capped at 170 registers (3 CTAs = 12 warps per SM; the uncapped 180 of
 // the feature-map variant left 8 and ran 0.219 instead of 0.194 ms)
-template <int CPL, bool kLatent, bool kPoint, bool kShare>
+// kPre: the next row's upstream gradient is requested before the current row is processed (the
+// feature-map variant was waiting on those loads: 4.6 long-scoreboard stalls per issued instruction)
+template <int CPL, bool kLatent, bool kPoint, bool kShare, bool kPre>
 __global__ void __launch_bounds__(kFieldWarps * 32, (kLatent && kPoint) ? 1 : 3)
 field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
   constexpr int N = CPL > 0 ? CPL : 1;
@@ -150,20 +153,24 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
   for (int64_t ch = blockIdx.x * (int64_t)kFieldWarps + (threadIdx.x >> 5); ch < n_chunks; ch += warps) {
     const int64_t first = ch * kChunk;
     const int n = (int)(first + kChunk < rows ? kChunk : rows - first);
+    FieldRowGrad<N> rg, rg_next;
+    if (CPL > 0 && kPre) field_load_row_grad<N>(a, first, lane, row_stride, &rg);
     FieldPoint mine;
     if (kShare) mine = point_of_my_row(a, first, lane, rows, &view);
     FieldCursor cur = field_cursor_at(a, first);
     for (int r = 0; r < n; ++r, field_cursor_next(a, &cur)) {
+      if (CPL > 0 && kPre && r + 1 < n) field_load_row_grad<N>(a, cur.row + 1, lane, row_stride, &rg_next);
       FieldPoint p;
       if (kShare) {
-        p = point_from_lane<true>(mine, r);
+        p = point_from_lane<kPoint>(mine, r);  // the feature-map gradient only needs the cell and its weights
       } else {
         field_view_fill(a, cur, &view);
         p = field_point(a, cur, view);
       }
       FieldRowPartial s;
       if (CPL > 0) {
-        s = field_bwd_row_lane<N, kLatent, kPoint>(a, cur, p, lane, row_stride, lc, &taps, &grads);
+        s = field_bwd_row_lane<N, kLatent, kPoint, kPre>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads);
+        if (kPre) rg = rg_next;
       } else {
         s = field_bwd_row_lane_generic<kLatent, kPoint>(a, cur, p, lane, row_stride, lc);
       }
@@ -195,6 +202,7 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
 //                            8 resident warps/SM: 0.645 ms against 0.56 ms for the two launches)
 //   AVR_FIELD_SHARE_POINT=x  per-row coordinate work shared out over the lanes (see point_from_lane)
 //   AVR_FIELD_STAGE=x        forward rows leave through shared memory and bulk copies (see kStage)
+//   AVR_FIELD_BWD_PREFETCH=x backward kernels that share the point work also prefetch the next row of g_out
 static bool env_flag(const char* name, bool dflt) {
   const char* v = std::getenv(name);
   return (v && *v) ? (*v != '0') : dflt;
@@ -204,6 +212,7 @@ static bool field_bwd_split() { return env_flag("AVR_FIELD_BWD_SPLIT", true); }
 // unset: the measured defaults (forward and feature-map backward share, the point backward does not:
 // 0.346 vs 0.362 ms); 0 / 1 force every kernel one way
 static bool field_share_point(bool dflt) { return env_flag("AVR_FIELD_SHARE_POINT", dflt); }
+static bool field_bwd_prefetch() { return env_flag("AVR_FIELD_BWD_PREFETCH", kFieldBwdPrefetchDefault); }
 static bool field_stage_rows() { return env_flag("AVR_FIELD_STAGE", kFieldStageDefault); }
 
 static unsigned field_grid(int64_t rows, int chunk) {
@@ -216,10 +225,12 @@ static unsigned field_grid(int64_t rows, int chunk) {
 template <int CPL, bool kLatent, bool kPoint>
 static void launch_bwd_kernel(const FieldInputsArgs& a, int row_stride, bool share, cudaStream_t stream) {
   const unsigned t = kFieldWarps * 32;
-  if (share) {
-    field_inputs_bwd_kernel<CPL, kLatent, kPoint, true><<<field_grid(a.NV * a.B, FieldChunk<true>::value), t, 0, stream>>>(a, row_stride);
+  if (share && field_bwd_prefetch()) {
+    field_inputs_bwd_kernel<CPL, kLatent, kPoint, true, true><<<field_grid(a.NV * a.B, FieldChunk<true>::value), t, 0, stream>>>(a, row_stride);
+  } else if (share) {
+    field_inputs_bwd_kernel<CPL, kLatent, kPoint, true, false><<<field_grid(a.NV * a.B, FieldChunk<true>::value), t, 0, stream>>>(a, row_stride);
   } else {
-    field_inputs_bwd_kernel<CPL, kLatent, kPoint, false><<<field_grid(a.NV * a.B, FieldChunk<false>::value), t, 0, stream>>>(a, row_stride);
+    field_inputs_bwd_kernel<CPL, kLatent, kPoint, false, false><<<field_grid(a.NV * a.B, FieldChunk<false>::value), t, 0, stream>>>(a, row_stride);
   }
 }
 

@@ -452,13 +452,33 @@ AVR_FI void field_code_grad_lane(const FieldLaneCode& lc, const FieldPoint& p, c
   }
 }
 
+// This lane's share of a row of g_out (the latent part): loaded ahead of its use by the kernels
+// that prefetch the next row while the current one is processed.
+template <int CPL>
+struct FieldRowGrad {
+  float g[CPL][4];
+};
+
+template <int CPL>
+AVR_FI void field_load_row_grad(const FieldInputsArgs& a, int64_t row, int lane, int row_stride, FieldRowGrad<CPL>* rg) {
+  const float* g_row = a.g_out + row * row_stride;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < CPL; ++i) {
+    field_load2(g_row + 4 * lane + 128 * i, rg->g[i]);
+    field_load2(g_row + 4 * lane + 128 * i + 2, rg->g[i] + 2);
+  }
+}
+
 // Lane `lane` of one row: accumulates into the d_latent cache (kLatent) and returns its partial
 // sums of the point gradient (kPoint; zero otherwise).  `taps` is the forward tap cache (read only
-// when kPoint).
-template <int CPL, bool kLatent, bool kPoint>
+// when kPoint); with kPreloaded `rg` holds this lane's part of the row's upstream gradient,
+// otherwise it is read here, group by group.
+template <int CPL, bool kLatent, bool kPoint, bool kPreloaded>
 AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
-                                          int row_stride, const FieldLaneCode& lc, FieldTapCache<CPL>* taps,
-                                          FieldGradCache<CPL>* grads) {
+                                          int row_stride, const FieldLaneCode& lc, const FieldRowGrad<CPL>& rg,
+                                          FieldTapCache<CPL>* taps, FieldGradCache<CPL>* grads) {
   const int64_t v = cur.v;
   FieldRowPartial s;
   field_partial_zero(&s);
@@ -486,8 +506,12 @@ AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldC
 #endif
   for (int i = 0; i < CPL; ++i) {
     float g[4];
-    field_load2(g_row + 4 * lane + 128 * i, g);
-    field_load2(g_row + 4 * lane + 128 * i + 2, g + 2);
+    if (kPreloaded) {
+      g[0] = rg.g[i][0]; g[1] = rg.g[i][1]; g[2] = rg.g[i][2]; g[3] = rg.g[i][3];
+    } else {  // `rg` is not touched: one group of four in flight at a time
+      field_load2(g_row + 4 * lane + 128 * i, g);
+      field_load2(g_row + 4 * lane + 128 * i + 2, g + 2);
+    }
 #if defined(__CUDACC__)
 #pragma unroll
 #endif

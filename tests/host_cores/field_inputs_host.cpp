@@ -44,7 +44,7 @@ void walk_fwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_wa
 }
 
 template <int CPL, bool kLatent, bool kPoint>
-void walk_bwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_warps) {
+void walk_bwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_warps, bool preloaded) {
   constexpr int N = CPL > 0 ? CPL : 1;
   const int64_t rows = a.NV * a.B;
   const int64_t n_chunks = (rows + chunk - 1) / chunk;
@@ -73,7 +73,13 @@ void walk_bwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_wa
           if (lane == 0) p0 = p;
           avr::FieldRowPartial s;
           if (CPL > 0) {
-            s = avr::field_bwd_row_lane<N, kLatent, kPoint>(a, cur, p, lane, row_stride, lc[lane], &taps[lane], &grads[lane]);
+            avr::FieldRowGrad<N> rg;
+            if (preloaded) {
+              avr::field_load_row_grad<N>(a, cur.row, lane, row_stride, &rg);
+              s = avr::field_bwd_row_lane<N, kLatent, kPoint, true>(a, cur, p, lane, row_stride, lc[lane], rg, &taps[lane], &grads[lane]);
+            } else {
+              s = avr::field_bwd_row_lane<N, kLatent, kPoint, false>(a, cur, p, lane, row_stride, lc[lane], rg, &taps[lane], &grads[lane]);
+            }
           } else {
             s = avr::field_bwd_row_lane_generic<kLatent, kPoint>(a, cur, p, lane, row_stride, lc[lane]);
           }
@@ -95,14 +101,14 @@ void walk_bwd(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_wa
 }
 
 template <int CPL>
-void walk_bwd_variant(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_warps) {
+void walk_bwd_variant(const avr::FieldInputsArgs& a, int row_stride, int chunk, int n_warps, bool preloaded) {
   const bool latent = a.d_latent != nullptr, point = a.d_xyz != nullptr || a.d_viewdirs != nullptr;
   if (latent && point) {
-    walk_bwd<CPL, true, true>(a, row_stride, chunk, n_warps);
+    walk_bwd<CPL, true, true>(a, row_stride, chunk, n_warps, preloaded);
   } else if (latent) {
-    walk_bwd<CPL, true, false>(a, row_stride, chunk, n_warps);
+    walk_bwd<CPL, true, false>(a, row_stride, chunk, n_warps, preloaded);
   } else if (point) {
-    walk_bwd<CPL, false, true>(a, row_stride, chunk, n_warps);
+    walk_bwd<CPL, false, true>(a, row_stride, chunk, n_warps, preloaded);
   }
 }
 
@@ -111,16 +117,18 @@ void walk_bwd_variant(const avr::FieldInputsArgs& a, int row_stride, int chunk, 
 extern "C" {
 
 // Backward walk; the caller zeroes d_latent / d_xyz / d_viewdirs (the library's launcher does).
+// use_cache: 0 generic walk, 1 register caches, 3 register caches + the row's gradient loaded ahead
 int host_field_inputs_bwd(const avr::FieldInputsArgs* a, int use_cache, int chunk, int n_warps) {
+  const bool preloaded = (use_cache & 2) != 0;
   const int width = a->features_only ? 0 : avr::field_code_width(*a);
   const int row_stride = a->C + width;
   if (a->C % 4 != 0 || (row_stride & 1)) return -1;
   const int cpl = (use_cache && a->C % 128 == 0) ? a->C / 128 : 0;
   switch (cpl) {
-    case 4: walk_bwd_variant<4>(*a, row_stride, chunk, n_warps); break;
-    case 2: walk_bwd_variant<2>(*a, row_stride, chunk, n_warps); break;
-    case 1: walk_bwd_variant<1>(*a, row_stride, chunk, n_warps); break;
-    default: walk_bwd_variant<0>(*a, row_stride, chunk, n_warps); break;
+    case 4: walk_bwd_variant<4>(*a, row_stride, chunk, n_warps, preloaded); break;
+    case 2: walk_bwd_variant<2>(*a, row_stride, chunk, n_warps, preloaded); break;
+    case 1: walk_bwd_variant<1>(*a, row_stride, chunk, n_warps, preloaded); break;
+    default: walk_bwd_variant<0>(*a, row_stride, chunk, n_warps, preloaded); break;
   }
   return 0;
 }

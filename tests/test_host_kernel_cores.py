@@ -189,7 +189,7 @@ def test_field_inputs_core_forward(host_field, golden, name, use_cache, features
 
 
 @pytest.mark.parametrize("name", ["field_inputs_c512", "field_inputs_small"])
-@pytest.mark.parametrize("use_cache", [1, 0])
+@pytest.mark.parametrize("use_cache", [1, 0, 3])
 @pytest.mark.parametrize("which", ["all", "latent_only", "points_only"])
 def test_field_inputs_core_backward(host_field, golden, name, use_cache, which):
     """Gradients against the reference's autograd.  Feature-map and view-direction gradients meet
