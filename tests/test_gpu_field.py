@@ -164,3 +164,26 @@ def test_field_inputs_refuses_cpu_and_bad_shapes(dev):
     with pytest.raises(avr_b200.AvrError):      # channels not a multiple of 4
         field_inputs(xd, xd, torch.zeros(1, 4, 4, 6, device=dev), torch.zeros(1, 3, 4, device=dev),
                      torch.ones(1, 2, device=dev), torch.ones(1, 2, device=dev), cfg)
+
+
+def test_field_features_only_backward(dev):
+    """return_features=True (models.py:828-829): the rows hold the features alone; the adaptive
+    renderer's march differentiates them with respect to the points and the feature map."""
+    from avr_b200 import field_inputs
+    d = ray_ordered_case(sb=1, ns=2, rays=20, k=32, ch=512, h=9, w=13, seed=5)
+    cfg = _cfg(d)
+    xyz_c, lat_c = d["xyz"].clone().requires_grad_(True), d["latent"].clone().requires_grad_(True)
+    want = FO.field_inputs(xyz_c, d["viewdirs"], d["poses"], d["focal"], d["c"], d["image_shape"], lat_c, d["latent_scaling"],
+                           d["freqs"], d["phases"], ns=d["ns"], features_only=True)
+    g_out = d["g_out"][:, :512].contiguous()
+    want.backward(g_out)
+    xyz = d["xyz"].to(dev).requires_grad_(True)
+    lat = d["latent"].to(dev).requires_grad_(True)
+    out = field_inputs(xyz, None, lat.permute(0, 2, 3, 1).contiguous(), d["poses"].to(dev), d["focal"].to(dev), d["c"].to(dev),
+                       cfg, features_only=True)
+    assert out.shape == want.shape
+    assert_close(out, want, what="features")
+    out.backward(g_out.to(dev))
+    assert_close(lat.grad, lat_c.grad, rtol=2e-5, atol=2e-6 * float(lat_c.grad.abs().max()), what="d_latent")
+    err = (xyz.grad.cpu() - xyz_c.grad).abs()
+    assert _xyz_bound(err, xyz_c.grad), float(err.max())

@@ -337,9 +337,50 @@ def test_fused_forward_glue_on_the_host_walk(host_field, monkeypatch):
     for net in (stock, fused):
         net.encode(images.flip(0), c2w, 30.0)
     assert_close(fused(xyz, viewdirs=vd), stock(xyz, viewdirs=vd), what="after re-encode")
+    # the functional form with the features alone and no view directions (the march's call)
+    lat = stock.encoder.latent.detach().clone().requires_grad_(True)
+    x = xyz.clone().requires_grad_(True)
+    cfg = field._config_of(stock)
+    feats = avr_b200.field_inputs(x, None, lat.permute(0, 2, 3, 1).contiguous(), stock.poses, stock.focal, stock.c, cfg,
+                                  features_only=True)
+    assert feats.shape == (sb * ns * b, 128)
+    feats.square().sum().backward()
+    assert x.grad is not None and lat.grad is not None and bool(x.grad.abs().sum() > 0)
     # stop_encoder_grad: the feature map is detached (models.py:817-818)
     fused.stop_encoder_grad = True
     fused.encode(images, c2w, 24.0)
     fused.zero_grad()
     fused(xyz, viewdirs=vd).sum().backward()
     assert fused.encoder.conv.weight.grad is None and fused.mlp_coarse.lin.weight.grad is not None
+
+
+@pytest.mark.parametrize("use_cache", [1, 0])
+def test_field_inputs_core_backward_of_the_features_alone(host_field, use_cache):
+    """return_features=True (models.py:828-829; the adaptive renderer's ray march reads the features
+    and differentiates through the point): rows are C wide, there is no code part, and the point
+    gradient comes from the projection alone."""
+    import field_oracle as FO
+    from avr_b200 import field
+    from conftest import assert_close
+    from field_stub import ray_ordered_case
+    d = ray_ordered_case(sb=1, ns=2, rays=10, k=24, ch=128, h=7, w=11, seed=3)
+    scale = (d["latent_scaling"] / d["image_shape"]).tolist()
+    cfg = field.FieldConfig(ns=d["ns"], scale=(scale[0], scale[1]), freqs=tuple(d["freqs"].reshape(-1).tolist()),
+                            phases=tuple(d["phases"].reshape(-1).tolist()))
+    xyz, lat = d["xyz"].clone().requires_grad_(True), d["latent"].clone().requires_grad_(True)
+    want = FO.field_inputs(xyz, d["viewdirs"], d["poses"], d["focal"], d["c"], d["image_shape"], lat, d["latent_scaling"],
+                           d["freqs"], d["phases"], ns=d["ns"], features_only=True)
+    g_out = d["g_out"][:, :128].contiguous()
+    want.backward(g_out)
+    nhwc = d["latent"].permute(0, 2, 3, 1).contiguous()
+    desc = field._fill(cfg, d["xyz"], None, nhwc, d["poses"], d["focal"], d["c"], True)
+    out = torch.full(tuple(want.shape), float("nan"))
+    desc.out, desc.g_out = out.data_ptr(), g_out.data_ptr()
+    assert host_field.host_field_inputs_fwd(ctypes.byref(desc), use_cache, 16, 2) == 0
+    assert torch.equal(out, want.detach())
+    d_lat, d_xyz = torch.zeros_like(nhwc), torch.zeros_like(d["xyz"])
+    desc.d_latent, desc.d_xyz = d_lat.data_ptr(), d_xyz.data_ptr()
+    assert host_field.host_field_inputs_bwd(ctypes.byref(desc), use_cache, 16, 2) == 0
+    assert_close(d_lat.permute(0, 3, 1, 2), lat.grad, rtol=2e-5, atol=2e-6 * float(lat.grad.abs().max()), what="d_latent")
+    err = (d_xyz - xyz.grad).abs()
+    assert bool((err <= 1e-5 * xyz.grad.abs() + 2e-6 * xyz.grad.abs().max()).all()), float(err.max())
