@@ -494,6 +494,15 @@ def main():
             others = measure_other_configs(dev, peak)
         except Exception as exc:  # the headline line must survive a failure here
             others = {"error": f"{type(exc).__name__}: {exc}"}
+        # SURVEY 8(f) row 3, the radiance field's front end (tools/bench_field.py: raw C-ABI launches over
+        # rotating inputs larger than L2; 2048 rays x 96 samples, conf/default.conf's 512 + 42 wide rows)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_field
+            recs = list(bench_field.run(bench_field.parse_args(["--raw-only", "--iters", "5"]), dev))
+            others["field_front_end_2048x96"] = {r["kernel"]: {k: r[k] for k in ("ms", "rows_per_s", "GBps", "hbm_frac")} for r in recs}
+        except Exception as exc:
+            others["field_front_end_2048x96"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None

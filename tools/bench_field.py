@@ -48,7 +48,7 @@ def torch_front_end(xyz, vd, poses, focal, c, scale, latent, freqs, phases, ns):
     return torch.cat((s[:, :, :, 0].transpose(1, 2).reshape(-1, latent.shape[1]), zf), -1)
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=2048)
     ap.add_argument("--samples", type=int, default=96)
@@ -56,8 +56,12 @@ def main():
     ap.add_argument("--batches", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--raw-only", action="store_true", help="only the raw C-ABI kernel timings")
-    a = ap.parse_args()
-    dev = torch.device("cuda:0")
+    return ap.parse_args(argv)
+
+
+def run(a, dev=None):
+    """Yields one record (dict) per measurement; `a` as from parse_args()."""
+    dev = dev or torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
     ch, h, w, ns = 512, 64, 64, a.views
     b = a.rays * a.samples
@@ -98,7 +102,7 @@ def main():
     lib = avr_b200.load_library()
     from avr_b200 import field as F_
     import ctypes
-    sp = torch.cuda.current_stream().cuda_stream
+    sp = torch.cuda.current_stream(dev).cuda_stream
 
     # ---- raw C-ABI launches with prebuilt descriptors: kernel time without the Python wrapper ----
     out = torch.empty(rows, ch + 42, device=dev)
@@ -133,9 +137,9 @@ def main():
     for key, name in (("fwd", "field_inputs_fwd"), ("bwd_all", "field_inputs_bwd (latent + points)"),
                       ("bwd_latent", "field_inputs_bwd (latent only)"), ("bwd_points", "field_inputs_bwd (points only)")):
         ms = raw(key)
-        print(json.dumps({"kernel": name, "rows": rows, "ms": round(ms, 4), "rows_per_s": rows / (ms * 1e-3),
-                          "GBps": round(rows * row_bytes / ms / 1e6, 1), "hbm_frac": round(rows * row_bytes / ms / 1e6 / pk, 4),
-                          "knobs": tag}), flush=True)
+        yield {"kernel": name, "rows": rows, "ms": round(ms, 4), "rows_per_s": rows / (ms * 1e-3),
+               "GBps": round(rows * row_bytes / ms / 1e6, 1), "hbm_frac": round(rows * row_bytes / ms / 1e6 / pk, 4),
+               "knobs": tag}
     if a.raw_only:
         return
 
@@ -173,10 +177,15 @@ def main():
 
     t_f, t_fb = timed(fwd), timed(fwd_bwd)
     tt_f, tt_fb = timed(torch_fwd), timed(torch_fwd_bwd)
-    print(json.dumps({"autograd_api": {"fwd_ms": round(t_f, 4), "fwd_bwd_ms": round(t_fb, 4)},
-                      "torch_eager_same_device": {"fwd_ms": round(tt_f, 4), "fwd_bwd_ms": round(tt_fb, 4)},
-                      "speedup_fwd": round(tt_f / t_f, 2), "speedup_fwd_bwd": round(tt_fb / t_fb, 2),
-                      "max_abs_diff_vs_torch_cuda": float((outs["o"] - outs["t"]).detach().abs().max())}), flush=True)
+    yield {"autograd_api": {"fwd_ms": round(t_f, 4), "fwd_bwd_ms": round(t_fb, 4)},
+           "torch_eager_same_device": {"fwd_ms": round(tt_f, 4), "fwd_bwd_ms": round(tt_fb, 4)},
+           "speedup_fwd": round(tt_f / t_f, 2), "speedup_fwd_bwd": round(tt_fb / t_fb, 2),
+           "max_abs_diff_vs_torch_cuda": float((outs["o"] - outs["t"]).detach().abs().max())}
+
+
+def main():
+    for rec in run(parse_args()):
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":
