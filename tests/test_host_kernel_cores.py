@@ -384,3 +384,56 @@ def test_field_inputs_core_backward_of_the_features_alone(host_field, use_cache)
     assert_close(d_lat.permute(0, 3, 1, 2), lat.grad, rtol=2e-5, atol=2e-6 * float(lat.grad.abs().max()), what="d_latent")
     err = (d_xyz - xyz.grad).abs()
     assert bool((err <= 1e-5 * xyz.grad.abs() + 2e-6 * xyz.grad.abs().max()).all()), float(err.max())
+
+
+@pytest.mark.parametrize("include_input,use_viewdirs,normalize_z,ch,rays,k,ns", [
+    (False, True, True, 128, 7, 9, 1),      # 63 rows: odd, not a multiple of any chunk
+    (True, False, False, 64, 5, 13, 3),     # no view directions: 39-wide code, odd row width is refused below
+    (False, False, True, 256, 3, 11, 2),
+    (True, True, False, 132, 4, 8, 1),      # C not a multiple of 128: the generic walk even when caches are asked for
+])
+def test_field_inputs_core_flag_combinations(host_field, include_input, use_viewdirs, normalize_z, ch, rays, k, ns):
+    """The code layout switches of the reference module (PositionalEncoding.include_input,
+    use_viewdirs, normalize_z; models.py:69-70, 766-769, 783-794), channel counts on and off the cached
+    variants, row counts that leave a partial last chunk — forward bit for bit, backward within the
+    bounds, for several chunk sizes / warp counts (the walk order must not matter)."""
+    import field_oracle as FO
+    from avr_b200 import field
+    from conftest import assert_close
+    from field_stub import ray_ordered_case
+    d = ray_ordered_case(sb=2, ns=ns, rays=rays, k=k, ch=ch, h=6, w=7, seed=ch + k)
+    scale = (d["latent_scaling"] / d["image_shape"]).tolist()
+    cfg = field.FieldConfig(ns=ns, scale=(scale[0], scale[1]), freqs=tuple(d["freqs"].reshape(-1).tolist()),
+                            phases=tuple(d["phases"].reshape(-1).tolist()), include_input=include_input,
+                            normalize_z=normalize_z, use_viewdirs=use_viewdirs)
+    width = cfg.code_width()
+    nhwc = d["latent"].permute(0, 2, 3, 1).contiguous()
+    vd_in = d["viewdirs"] if use_viewdirs else None
+    desc = field._fill(cfg, d["xyz"], vd_in, nhwc, d["poses"], d["focal"], d["c"], False)
+    if (ch + width) % 2:
+        # rows are written in 8-byte pieces: an odd row width is refused by the library (AVR_ERR_UNSUPPORTED)
+        assert host_field.host_field_inputs_fwd(ctypes.byref(desc), 1, 16, 2) == -1
+        return
+    xyz, vd, lat = (d[key].clone().requires_grad_(True) for key in ("xyz", "viewdirs", "latent"))
+    want = FO.field_inputs(xyz, vd, d["poses"], d["focal"], d["c"], d["image_shape"], lat, d["latent_scaling"], d["freqs"],
+                           d["phases"], ns=ns, include_input=include_input, normalize_z=normalize_z, use_viewdirs=use_viewdirs)
+    g_out = d["g_out"][:, :ch + width].contiguous()
+    want.backward(g_out)
+    n_sin = 3 * len(cfg.freqs)
+    lo = ch + (3 if include_input else 0)
+    for chunk, n_warps in ((16, 3), (32, 1), (5, 7)):
+        out = torch.full(tuple(want.shape), float("nan"))
+        desc.out = out.data_ptr()
+        assert host_field.host_field_inputs_fwd(ctypes.byref(desc), 1, chunk, n_warps) == 0
+        assert torch.equal(out[:, :lo], want[:, :lo].detach()) and torch.equal(out[:, lo + n_sin:], want[:, lo + n_sin:].detach())
+        assert float((out - want.detach()).abs().max()) <= 1.2e-7
+        desc.g_out = g_out.data_ptr()
+        d_lat, d_xyz, d_vd = torch.zeros_like(nhwc), torch.zeros_like(d["xyz"]), torch.zeros_like(d["viewdirs"])
+        desc.d_latent, desc.d_xyz = d_lat.data_ptr(), d_xyz.data_ptr()
+        desc.d_viewdirs = d_vd.data_ptr() if use_viewdirs else None
+        assert host_field.host_field_inputs_bwd(ctypes.byref(desc), 1, chunk, n_warps) == 0
+        assert_close(d_lat.permute(0, 3, 1, 2), lat.grad, rtol=2e-5, atol=2e-6 * float(lat.grad.abs().max()), what="d_latent")
+        if use_viewdirs:
+            assert_close(d_vd, vd.grad, what="d_viewdirs")
+        err = (d_xyz - xyz.grad).abs()
+        assert bool((err <= 1e-5 * xyz.grad.abs() + 2e-6 * xyz.grad.abs().max()).all()), float(err.max())
