@@ -4,6 +4,8 @@
 // Bound by the HBM write of the MLP input: (C + code) * 4 bytes per (view, point), 2216 B for
 // conf/default.conf's 512 + 42; the feature rows it blends come from the L2-resident map (8 MB at
 // 64 x 64 x 512) and stay in registers while consecutive samples of a ray sit in one texel cell.
+// Measured (profiles/r01_field_inputs.md): forward 58 %, feature-map backward 46 %, point backward 20 % of
+// the HBM roofline; all three latency-bound at 10-14 resident warps/SM, DRAM traffic = algorithmic bytes.
 #include <cstdlib>
 
 #include "avr_common.cuh"
@@ -12,7 +14,7 @@
 
 namespace avr {
 
-constexpr bool kFieldBwdPrefetchDefault = false;
+constexpr bool kFieldBwdPrefetchDefault = false;  // measured: 0.200 vs 0.147 ms (spills under the 168-register cap)
 constexpr bool kFieldStageDefault = false;  // measured: 0.127 ms staged vs 0.118 ms direct (L2 merges the half sectors)
 constexpr int kFieldWarps = 4;
 // consecutive rows per warp visit (samples of one ray, same view): 32 when the lanes share out the

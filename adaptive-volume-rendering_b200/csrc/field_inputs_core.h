@@ -8,10 +8,12 @@
 // as per-lane code that compiles for the device (nvcc) and for the host (g++; the CPU suite walks
 // it lane by lane against the oracle: tests/test_host_kernel_cores.py).
 //
-// One warp per (source view, point).  Every lane redoes the ~60 flops of coordinate work (no
-// shuffles), then owns channels {4*lane + 128*i} of the feature vector and code entries
-// {lane, lane+32}.  The feature map is channels-last (N, H, W, C): one bilinear tap is one
-// contiguous C*4-byte row.
+// One warp per (source view, point) = one output row; rows are walked in runs of consecutive
+// rows (FieldCursor).  The lane-independent coordinate work of a row is field_point(); the kernels
+// either let every lane do it for itself or do it once per row and hand it round by shuffles
+// (field_inputs.cu) — the functions below take the finished FieldPoint either way.  A lane then
+// owns channels {4*lane + 128*i} of the feature vector and code entries {lane, lane+32}.  The
+// feature map is channels-last (N, H, W, C): one bilinear tap is one contiguous C*4-byte row.
 //
 // The operation order reproduces torch-CPU's kernels so that everything except the sine is
 // bit-identical to the reference on the same inputs (probed against the reference, see
