@@ -437,3 +437,73 @@ def test_field_inputs_core_flag_combinations(host_field, include_input, use_view
             assert_close(d_vd, vd.grad, what="d_viewdirs")
         err = (d_xyz - xyz.grad).abs()
         assert bool((err <= 1e-5 * xyz.grad.abs() + 2e-6 * xyz.grad.abs().max()).all()), float(err.max())
+
+
+def test_fused_forward_around_the_reference_module(host_field, monkeypatch):
+    """The real thing: the reference's own NewPixelNeRFNet (imported unmodified, conf/default_mv.conf's
+    flags, two source views, small MLPs), once stock and once through `fuse_field_inputs`, on CPU —
+    the two C-ABI calls replaced by the host walk of the kernel cores, in this test only.  Checks
+    what a stub cannot: the attribute names, the MLP call convention (combine_inner_dims) and the output
+    epilogue of models.py:831-866, and that the gradients reach the encoder and MLP parameters."""
+    import contextlib
+    import copy
+    import types
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference checkout not present")
+    ref_shim.load()
+    import models
+    import avr_b200
+    from avr_b200 import field
+    from fields import camera_setup
+    from conftest import assert_close
+    from ref_shim import Conf
+
+    class HostLib:
+        def avr_field_inputs_fwd(self, desc_ref, stream):
+            return host_field.host_field_inputs_fwd(desc_ref, 1, 32, 2)
+
+        def avr_field_inputs_bwd(self, desc_ref, stream):
+            d = desc_ref._obj
+            for p, n in ((d.d_latent, d.NV * d.H * d.W * d.C), (d.d_xyz, d.NV // d.NS * d.B * 3),
+                         (d.d_viewdirs, d.NV // d.NS * d.B * 3)):
+                if p:
+                    ctypes.memset(p, 0, 4 * n)
+            return host_field.host_field_inputs_bwd(desc_ref, 1, 32, 2)
+
+    monkeypatch.setattr(field._lib, "load", lambda: HostLib())
+    monkeypatch.setattr(field, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda *_a, **_k: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *_a, **_k: types.SimpleNamespace(cuda_stream=0))
+
+    torch.manual_seed(3)
+    mlp = dict(type="resnet", n_blocks=3, d_hidden=32, combine_layer=2, combine_type="average")
+    conf = Conf(use_encoder=True, use_global_encoder=False, use_xyz=True, canon_xyz=False, use_code=True,
+                code=dict(num_freqs=6, freq_factor=1.5, include_input=True), use_viewdirs=True, use_code_viewdirs=False,
+                mlp_coarse=mlp, mlp_fine=mlp, encoder=dict(backbone="resnet34", pretrained=False, num_layers=4))
+    stock = models.make_new_model(conf)
+    fused = avr_b200.fuse_field_inputs(copy.deepcopy(stock))
+    assert set(fused.state_dict()) == set(stock.state_dict())
+    sb, ns, b, sl = 2, 2, 40, 16
+    g = torch.Generator().manual_seed(5)
+    images = torch.rand(sb, ns, 3, sl, sl, generator=g) * 2 - 1
+    c2w = camera_setup(sb * ns, 1, seed=6)[0][:, 0].reshape(sb, ns, 4, 4)
+    focal = torch.tensor(131.25 / 128 * sl)
+    xyz = torch.randn(sb, b, 3, generator=g) * 0.25
+    vd = torch.nn.functional.normalize(torch.randn(sb, b, 3, generator=g), dim=-1)
+    g_out = torch.randn(sb, b, 4, generator=g)
+    for net in (stock, fused):
+        net.encode(images, c2w, focal)                      # train.py:68; the encoder runs with autograd
+    for coarse in (True, False):
+        want, got = stock(xyz, coarse=coarse, viewdirs=vd), fused(xyz, coarse=coarse, viewdirs=vd)
+        assert got.shape == want.shape == (sb, b, 4)
+        assert_close(got, want, what=f"coarse={coarse}")
+    assert_close(fused(xyz, viewdirs=vd, return_features=True), stock(xyz, viewdirs=vd, return_features=True), what="features")
+    grads = {}
+    for key, net in (("stock", stock), ("fused", fused)):
+        x = xyz.clone().requires_grad_(True)
+        net(x, coarse=True, viewdirs=vd).backward(g_out)
+        grads[key] = {"xyz": x.grad, **{n: p.grad for n, p in net.named_parameters() if p.grad is not None}}
+    assert set(grads["fused"]) == set(grads["stock"]) and any(k.startswith("encoder.") for k in grads["fused"])
+    for k, want in grads["stock"].items():
+        assert_close(grads["fused"][k], want, rtol=1e-4, atol=1e-5 * float(want.abs().max()) + 1e-9, what=k)
