@@ -101,7 +101,7 @@ AVR_HD bool coarse_segment_build(int lane, int64_t r0, int64_t R, const int64_t*
   const int64_t end = offsets[r < R ? r + 1 : R];
   const int64_t rel = begin - seg_begin;
   const int64_t cnt = end - begin;
-  const bool ok = rel >= 0 && cnt >= 0 && (end - seg_begin) < (int64_t)0x7fffffff;
+  const bool ok = rel >= 0 && cnt >= 0 && (end - seg_begin) < (int64_t)0x7ffffff0;  // head + len + 3 stays an int
   seg->rel[lane] = (int)rel;
   if (lane == kSegRays - 1) seg->rel[kSegRays] = (int)(end - seg_begin);
   CoarseRay p;
