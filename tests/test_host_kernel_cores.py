@@ -165,6 +165,34 @@ def host_field(host):
     return host
 
 
+@pytest.fixture
+def host_abi(host_field, monkeypatch):
+    """Routes the Python package's two front-end C-ABI calls to the host walk and lets its wrappers
+    accept CPU tensors — for the duration of one test.  The product never does this: without the CUDA
+    library (or on CPU tensors) `avr_b200` raises."""
+    import contextlib
+    import types
+    from avr_b200 import field
+
+    class HostLib:
+        def avr_field_inputs_fwd(self, desc_ref, stream):
+            return host_field.host_field_inputs_fwd(desc_ref, 1, 32, 2)
+
+        def avr_field_inputs_bwd(self, desc_ref, stream):
+            d = desc_ref._obj
+            for p, n in ((d.d_latent, d.NV * d.H * d.W * d.C), (d.d_xyz, d.NV // d.NS * d.B * 3),
+                         (d.d_viewdirs, d.NV // d.NS * d.B * 3)):
+                if p and n:
+                    ctypes.memset(p, 0, 4 * n)       # what launch_field_inputs_bwd does on the stream
+            return host_field.host_field_inputs_bwd(desc_ref, 1, 32, 2)
+
+    monkeypatch.setattr(field._lib, "load", lambda: HostLib())
+    monkeypatch.setattr(field, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda *_a, **_k: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *_a, **_k: types.SimpleNamespace(cuda_stream=0))
+    return field
+
+
 @pytest.mark.parametrize("name", ["field_inputs_c512", "field_inputs_small"])
 @pytest.mark.parametrize("use_cache", [1, 0])
 @pytest.mark.parametrize("features_only", [False, True])
@@ -279,7 +307,7 @@ def test_field_inputs_core_on_ray_ordered_points(host_field):
         assert bool((err <= 1e-5 * xyz.grad.abs() + 2e-6 * xyz.grad.abs().max()).all()), float(err.max())
 
 
-def test_fused_forward_glue_on_the_host_walk(host_field, monkeypatch):
+def test_fused_forward_glue_on_the_host_walk(host_abi):
     """The Python side of the drop-in (`fuse_field_inputs`: reading the launch constants off the
     module, the NHWC copy of the feature map, descriptor filling, the autograd Function, the
     MLP call and output epilogue) run on CPU tensors, with the two C-ABI entry points replaced —
@@ -294,22 +322,6 @@ def test_fused_forward_glue_on_the_host_walk(host_field, monkeypatch):
     from fields import camera_setup
     from conftest import assert_close
 
-    class HostLib:
-        def avr_field_inputs_fwd(self, desc_ref, stream):
-            return host_field.host_field_inputs_fwd(desc_ref, 1, 16, 3)
-
-        def avr_field_inputs_bwd(self, desc_ref, stream):
-            d = desc_ref._obj
-            for p, n in ((d.d_latent, d.NV * d.H * d.W * d.C), (d.d_xyz, d.NV // d.NS * d.B * 3),
-                         (d.d_viewdirs, d.NV // d.NS * d.B * 3)):
-                if p:
-                    ctypes.memset(p, 0, 4 * n)       # what launch_field_inputs_bwd does on the stream
-            return host_field.host_field_inputs_bwd(desc_ref, 1, 16, 3)
-
-    monkeypatch.setattr(field._lib, "load", lambda: HostLib())
-    monkeypatch.setattr(field, "require_cuda", lambda *a: None)
-    monkeypatch.setattr(torch.cuda, "device", lambda *_a, **_k: contextlib.nullcontext())
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *_a, **_k: types.SimpleNamespace(cuda_stream=0))
 
     torch.manual_seed(0)
     stock = StubNet()
@@ -439,7 +451,7 @@ def test_field_inputs_core_flag_combinations(host_field, include_input, use_view
         assert bool((err <= 1e-5 * xyz.grad.abs() + 2e-6 * xyz.grad.abs().max()).all()), float(err.max())
 
 
-def test_fused_forward_around_the_reference_module(host_field, monkeypatch):
+def test_fused_forward_around_the_reference_module(host_abi):
     """The real thing: the reference's own NewPixelNeRFNet (imported unmodified, conf/default_mv.conf's
     flags, two source views, small MLPs), once stock and once through `fuse_field_inputs`, on CPU —
     the two C-ABI calls replaced by the host walk of the kernel cores, in this test only.  Checks
@@ -459,22 +471,6 @@ def test_fused_forward_around_the_reference_module(host_field, monkeypatch):
     from conftest import assert_close
     from ref_shim import Conf
 
-    class HostLib:
-        def avr_field_inputs_fwd(self, desc_ref, stream):
-            return host_field.host_field_inputs_fwd(desc_ref, 1, 32, 2)
-
-        def avr_field_inputs_bwd(self, desc_ref, stream):
-            d = desc_ref._obj
-            for p, n in ((d.d_latent, d.NV * d.H * d.W * d.C), (d.d_xyz, d.NV // d.NS * d.B * 3),
-                         (d.d_viewdirs, d.NV // d.NS * d.B * 3)):
-                if p:
-                    ctypes.memset(p, 0, 4 * n)
-            return host_field.host_field_inputs_bwd(desc_ref, 1, 32, 2)
-
-    monkeypatch.setattr(field._lib, "load", lambda: HostLib())
-    monkeypatch.setattr(field, "require_cuda", lambda *a: None)
-    monkeypatch.setattr(torch.cuda, "device", lambda *_a, **_k: contextlib.nullcontext())
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *_a, **_k: types.SimpleNamespace(cuda_stream=0))
 
     torch.manual_seed(3)
     mlp = dict(type="resnet", n_blocks=3, d_hidden=32, combine_layer=2, combine_type="average")
@@ -507,3 +503,19 @@ def test_fused_forward_around_the_reference_module(host_field, monkeypatch):
     assert set(grads["fused"]) == set(grads["stock"]) and any(k.startswith("encoder.") for k in grads["fused"])
     for k, want in grads["stock"].items():
         assert_close(grads["fused"][k], want, rtol=1e-4, atol=1e-5 * float(want.abs().max()) + 1e-9, what=k)
+
+
+def test_field_inputs_empty_batch(host_abi):
+    """No points: the forward returns a (0, row) tensor and the feature-map gradient is zero."""
+    import avr_b200
+    from field_stub import ray_ordered_case
+    d = ray_ordered_case(sb=2, ns=1, rays=2, k=4, ch=128, h=5, w=6, seed=1)
+    scale = (d["latent_scaling"] / d["image_shape"]).tolist()
+    cfg = avr_b200.FieldConfig(ns=1, scale=(scale[0], scale[1]), freqs=tuple(d["freqs"].reshape(-1).tolist()),
+                               phases=tuple(d["phases"].reshape(-1).tolist()))
+    lat = d["latent"].permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    empty = torch.zeros(2, 0, 3)
+    out = avr_b200.field_inputs(empty, empty, lat, d["poses"], d["focal"], d["c"], cfg)
+    assert out.shape == (0, 128 + 42)
+    out.sum().backward()
+    assert lat.grad is not None and not lat.grad.any()
