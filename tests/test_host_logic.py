@@ -67,3 +67,45 @@ def test_shard_bounds_packed_balances_samples():
     per_rank = [int(offsets[b] - offsets[a]) for a, b in cuts]
     assert max(per_rank) - min(per_rank) <= 200           # within two long rays of each other
     assert [shard_bounds(10, 3, r) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+
+
+def test_accelerate_switches_a_reference_model():
+    """avr_b200.accelerate on the reference's own RadFieldAndRenderer (train.py:255-276): the renderers
+    are replaced by their avr_b200 equivalents with the same configuration, the adaptive renderer's
+    lstm / out_layer stay the same objects, the field's forward is rebound, the state_dict is unchanged."""
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference checkout not present")
+    ref = ref_shim.load()
+    import models
+    import avr_b200
+    from ref_shim import Conf
+    conf = Conf(use_encoder=True, use_global_encoder=False, use_xyz=True, canon_xyz=False, use_code=True,
+                code=dict(num_freqs=6, freq_factor=1.5, include_input=True), use_viewdirs=True, use_code_viewdirs=False,
+                mlp_coarse=dict(type="resnet", n_blocks=1, d_hidden=16), mlp_fine=dict(type="resnet", n_blocks=1, d_hidden=16),
+                encoder=dict(backbone="resnet34", pretrained=False, num_layers=4))
+    net = models.make_new_model(conf)
+    ren = ref.VolumeRenderer.from_conf(Conf(near=0.8, far=1.8, n_coarse=64, n_fine=32, n_fine_depth=16, depth_std=0.01))
+    model = models.RadFieldAndRenderer(net, ren)
+    keys = set(model.state_dict())
+    stock_forward = net.forward
+    out = avr_b200.accelerate(model)
+    assert out is model and isinstance(model.renderer, avr_b200.VolumeRenderer) and set(model.state_dict()) == keys
+    r = model.renderer
+    assert (r.n_coarse, r.n_fine, r.n_fine_depth, r.depth_std, r.white_back) == (64, 32, 16, 0.01, True)
+    assert torch.equal(r.near.cpu(), ren.near.cpu()) and torch.equal(r.far.cpu(), ren.far.cpu())
+    assert model.rf is net and net.forward != stock_forward and net.forward.__func__.__name__ == "_fused_forward"
+    # adaptive renderer: parameters are shared, not copied
+    aren = ref.AdaptiveVolumeRenderer(512, 10, 0.15, 20, True)
+    model2 = avr_b200.accelerate(models.RadFieldAndRenderer(models.make_new_model(conf), aren), fuse_field=False)
+    a = model2.renderer
+    assert isinstance(a, avr_b200.AdaptiveVolumeRenderer) and a.lstm is aren.lstm and a.out_layer is aren.out_layer
+    assert (a.steps, a.epsilon, a.n_coarse, a.white_back, a.n_feature_channels) == (10, 0.15, 20, True, 512)
+    assert model2.rf.forward.__func__.__name__ == "forward"             # untouched with fuse_field=False
+    # a field outside the kernels' family keeps its torch forward; the renderer is still switched
+    other = models.make_new_model(conf)
+    other.use_global_encoder = True
+    model3 = avr_b200.accelerate(models.RadFieldAndRenderer(other, ref.VolumeRenderer(0.8, 1.8, 8, 4, 4, 0.01)))
+    assert isinstance(model3.renderer, avr_b200.VolumeRenderer) and other.forward.__func__.__name__ == "forward"
+    with pytest.raises(avr_b200.AvrError):
+        avr_b200.convert_renderer(torch.nn.Linear(2, 2))
