@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libavr_b200.so")
 
 AVR_OK = 0
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _P = c_void_p  # every device pointer crosses as a plain address
 
@@ -27,6 +27,9 @@ PROTOTYPES = {
     "avr_composite_plan_info": (c_int, [c_int64, c_int, _P, _P, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                         ctypes.POINTER(c_int64)]),
     "avr_set_force_generic": (None, [c_int]),
+    "avr_set_option": (c_int, [c_char_p, c_int, c_int]),
+    "avr_dispatch_counters": (c_int, [ctypes.POINTER(c_int64), c_int]),
+    "avr_dispatch_reset": (None, []),
     "avr_coarse_sample_fwd": (c_int, [_P, _P, c_int, _P, c_int64, c_int, _P, _P]),
     "avr_coarse_sample_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
     "avr_importance_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int,
@@ -37,6 +40,10 @@ PROTOTYPES = {
     "avr_composite_fwd_gather": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,
                                          ctypes.POINTER(c_void_p), c_int, c_int64, _P]),
     "avr_composite_fwd_gather_multicast": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
+    "avr_composite_fwd_gather_signal": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P,
+                                                ctypes.POINTER(c_void_p), c_int, c_int, c_int64,
+                                                ctypes.POINTER(c_void_p), c_int, c_int, ctypes.c_uint32, _P, _P]),
+    "avr_gather_wait": (c_int, [_P, c_int, ctypes.c_uint32, _P, _P]),
     "avr_gather_push_rows": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int64, c_int64, _P]),
     "avr_composite_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
     "avr_composite_fwd_packed": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_float, _P, _P, _P, _P]),
@@ -55,7 +62,7 @@ PROTOTYPES = {
     "avr_field_inputs_bwd": (c_int, [_P, _P]),
     "avr_host_workspace_create": (c_int, [c_int, c_int64, ctypes.POINTER(c_void_p)]),
     "avr_host_workspace_destroy": (c_int, [_P]),
-    "avr_composite_fwd_bwd_host": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "avr_composite_fwd_bwd_host": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -92,6 +99,27 @@ def check(status: int, what: str) -> None:
         msg = lib.avr_status_string(status).decode()
         detail = lib.avr_last_cuda_error().decode()
         raise AvrError(f"{what}: {msg} ({status})" + (f" [{detail}]" if detail and status in (-2, -3, -5) else ""))
+
+
+DISPATCH_NAMES = ("fwd_span", "fwd_wray", "fwd_generic", "fwd_span_packed", "bwd_span", "bwd_wray", "bwd_generic",
+                  "bwd_span_packed", "importance_bins", "importance_grp", "importance_reg", "importance_smem")
+
+
+def dispatch_counters() -> dict:
+    """Calls served per kernel family since the last ``dispatch_reset`` (process-wide)."""
+    buf = (c_int64 * len(DISPATCH_NAMES))()
+    load().avr_dispatch_counters(buf, len(DISPATCH_NAMES))
+    return dict(zip(DISPATCH_NAMES, (int(v) for v in buf)))
+
+
+def dispatch_reset() -> None:
+    load().avr_dispatch_reset()
+
+
+def set_option(name: str, value: int | None) -> None:
+    """Override one of the library's A/B switches (None: back to the default)."""
+    check(load().avr_set_option(name.encode(), 0 if value is None else int(value), 1 if value is None else 0),
+          f"avr_set_option({name})")
 
 
 def ptr(t) -> int | None:

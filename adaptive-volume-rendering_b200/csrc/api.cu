@@ -165,9 +165,11 @@ int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int w
   if (!g_force_generic.load() && span_plan(R, K, rgbs, z, &plan) && (w == nullptr || aligned16(w))) {
     int rc = launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, st);
     if (rc != AVR_OK) return rc;
+    count_dispatch(AVR_DISPATCH_FWD_SPAN);
     done = plan.main_rays;
   }
   if (done < R) {
+    count_dispatch(g_force_generic.load() ? AVR_DISPATCH_FWD_GENERIC : AVR_DISPATCH_FWD_WRAY);
     auto rest = g_force_generic.load() ? launch_composite_fwd_generic : launch_composite_fwd_wray;
     return rest(rgbs + done * K * 4, z + done * K, nullptr, R - done, K, white_back, infinity,
                 w ? w + done * K : nullptr, rgb + done * 3, depth + done, st);
@@ -189,6 +191,28 @@ int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t R, int K
     return AVR_ERR_UNSUPPORTED;
   return launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, as_stream(stream),
                                    peer_gathered, n_peers, row0);
+}
+
+int avr_composite_fwd_gather_signal(const float* rgbs, const float* z, int64_t R, int K, int white_back,
+                                    float infinity, float* w, float* rgb, float* depth, void* const* peer_gathered,
+                                    int n_peers, int multicast, int64_t row0, uint32_t* const* peer_flags,
+                                    int n_flag_peers, int self_rank, uint32_t value, uint32_t* done_counter,
+                                    avr_stream_t stream) {
+  if (R < 1 || K < 1 || n_peers < 1 || row0 < 0 || !peer_gathered || !peer_flags || !done_counter) return AVR_ERR_BAD_ARG;
+  if (n_flag_peers < 1 || n_flag_peers > 16 || self_rank < 0 || self_rank >= 32) return AVR_ERR_BAD_ARG;
+  if (multicast && n_peers != 1) return AVR_ERR_BAD_ARG;
+  if (!rgbs || !z || !rgb || !depth || !aligned16(rgbs)) return AVR_ERR_BAD_ARG;
+  for (int p = 0; p < n_peers; ++p)
+    if (!peer_gathered[p] || !aligned16(peer_gathered[p])) return AVR_ERR_BAD_ARG;
+  for (int p = 0; p < n_flag_peers; ++p)
+    if (!peer_flags[p]) return AVR_ERR_BAD_ARG;
+  SpanPlan plan;
+  if (g_force_generic.load() || !span_plan(R, K, rgbs, z, &plan) || plan.main_rays != R || (w && !aligned16(w)))
+    return AVR_ERR_UNSUPPORTED;
+  GatherSignal sig{peer_flags, n_flag_peers, self_rank, value, done_counter};
+  count_dispatch(AVR_DISPATCH_FWD_SPAN);
+  return launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, as_stream(stream),
+                                   peer_gathered, n_peers, row0, multicast != 0, &sig);
 }
 
 int avr_composite_fwd_gather_multicast(const float* rgbs, const float* z, int64_t R, int K, int white_back,
@@ -242,9 +266,11 @@ int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, con
       (!d_z || (K > plan.L && aligned16(d_z)))) {
     int rc = launch_composite_bwd_span(plan, rgbs, z, g_rgb, g_depth, K, white_back, infinity, d_rgbs, d_z, st);
     if (rc != AVR_OK) return rc;
+    count_dispatch(AVR_DISPATCH_BWD_SPAN);
     done = plan.main_rays;
   }
   if (done < R) {
+    count_dispatch(g_force_generic.load() ? AVR_DISPATCH_BWD_GENERIC : AVR_DISPATCH_BWD_WRAY);
     auto rest = g_force_generic.load() ? launch_composite_bwd_generic : launch_composite_bwd_wray;
     return rest(rgbs + done * K * 4, z + done * K, nullptr, g_rgb ? g_rgb + done * 3 : nullptr,
                 g_depth ? g_depth + done : nullptr, g_w ? g_w + done * K : nullptr, R - done, K, white_back,
@@ -260,9 +286,12 @@ int avr_composite_fwd_packed(const float* rgbs, const float* z, const int64_t* o
   if (R == 0) return AVR_OK;
   if (!offsets || !rgb || !depth) return AVR_ERR_BAD_ARG;
   if (S > 0 && (!rgbs || !z || !aligned16(rgbs))) return AVR_ERR_BAD_ARG;
-  if (!g_force_generic.load() && S > 0 && span_packed_eligible(rgbs, z, w, nullptr))
+  if (!g_force_generic.load() && S > 0 && span_packed_eligible(rgbs, z, w, nullptr)) {
+    count_dispatch(AVR_DISPATCH_FWD_SPAN_PACKED);
     return launch_composite_fwd_span_packed(rgbs, z, offsets, R, S, white_back, infinity, w, rgb, depth,
                                             as_stream(stream));
+  }
+  count_dispatch(g_force_generic.load() ? AVR_DISPATCH_FWD_GENERIC : AVR_DISPATCH_FWD_WRAY);
   auto fn = g_force_generic.load() ? launch_composite_fwd_generic : launch_composite_fwd_wray;
   return fn(rgbs, z, offsets, R, 0, white_back, infinity, w, rgb, depth, as_stream(stream));
 }
@@ -273,9 +302,12 @@ int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* o
   if (R < 0 || S < 0) return AVR_ERR_BAD_ARG;
   if (R == 0 || S == 0) return AVR_OK;
   if (!offsets || !rgbs || !z || !d_rgbs || !aligned16(rgbs) || !aligned16(d_rgbs)) return AVR_ERR_BAD_ARG;
-  if (!g_force_generic.load() && !g_w && !d_z && span_packed_eligible(rgbs, z, nullptr, d_rgbs))
+  if (!g_force_generic.load() && !g_w && !d_z && span_packed_eligible(rgbs, z, nullptr, d_rgbs)) {
+    count_dispatch(AVR_DISPATCH_BWD_SPAN_PACKED);
     return launch_composite_bwd_span_packed(rgbs, z, offsets, g_rgb, g_depth, R, S, white_back, infinity, d_rgbs,
                                             as_stream(stream));
+  }
+  count_dispatch(g_force_generic.load() ? AVR_DISPATCH_BWD_GENERIC : AVR_DISPATCH_BWD_WRAY);
   auto fn = g_force_generic.load() ? launch_composite_bwd_generic : launch_composite_bwd_wray;
   return fn(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs, d_z, as_stream(stream));
 }
@@ -382,7 +414,7 @@ struct avr_host_workspace {
   static constexpr int kSlots = 3;
   struct Slot {
     float *rgbs = nullptr, *z = nullptr, *g_rgb = nullptr, *g_depth = nullptr;
-    float *rgb = nullptr, *depth = nullptr, *d_rgbs = nullptr;
+    float *rgb = nullptr, *depth = nullptr, *d_rgbs = nullptr, *w = nullptr;
     cudaStream_t stream = nullptr;
   } slots[kSlots];
   int K = 0;
@@ -403,6 +435,7 @@ static void free_workspace(avr_host_workspace* ws) {
     cudaFree(sl.rgb);
     cudaFree(sl.depth);
     cudaFree(sl.d_rgbs);
+    cudaFree(sl.w);
   }
   delete ws;
 }
@@ -429,13 +462,14 @@ static int alloc_workspace(avr_host_workspace* ws) {
     AVR_RT(cudaMalloc(&sl.rgb, nr * 12));
     AVR_RT(cudaMalloc(&sl.depth, nr * 4));
     AVR_RT(cudaMalloc(&sl.d_rgbs, nk * 16));
+    AVR_RT(cudaMalloc(&sl.w, nk * 4));
   }
   return AVR_OK;
 }
 
-static int run_host_pass(avr_host_workspace* ws, const float* rgbs, const float* z, const float* g_rgb,
-                         const float* g_depth, int64_t R, int white_back, float infinity, float* rgb,
-                         float* depth, float* d_rgbs) {
+static int enqueue_host_pass(avr_host_workspace* ws, const float* rgbs, const float* z, const float* g_rgb,
+                             const float* g_depth, int64_t R, int white_back, float infinity, float* rgb,
+                             float* depth, float* w, float* d_rgbs) {
   const int K = ws->K;
   const int64_t chunk = ws->chunk_rays;
   const int64_t n_chunks = (R + chunk - 1) / chunk;
@@ -449,17 +483,38 @@ static int run_host_pass(avr_host_workspace* ws, const float* rgbs, const float*
     AVR_RT(cudaMemcpyAsync(sl.z, z + r0 * K, n * 4, cudaMemcpyHostToDevice, sl.stream));
     if (g_rgb) AVR_RT(cudaMemcpyAsync(sl.g_rgb, g_rgb + r0 * 3, (size_t)rn * 12, cudaMemcpyHostToDevice, sl.stream));
     if (g_depth) AVR_RT(cudaMemcpyAsync(sl.g_depth, g_depth + r0, (size_t)rn * 4, cudaMemcpyHostToDevice, sl.stream));
-    rc = avr_composite_fwd(sl.rgbs, sl.z, rn, K, white_back, infinity, nullptr, sl.rgb, sl.depth, sl.stream);
+    rc = avr_composite_fwd(sl.rgbs, sl.z, rn, K, white_back, infinity, w ? sl.w : nullptr, sl.rgb, sl.depth, sl.stream);
     if (rc != AVR_OK) return rc;
     rc = avr_composite_bwd(sl.rgbs, sl.z, g_rgb ? sl.g_rgb : nullptr, g_depth ? sl.g_depth : nullptr, nullptr, rn, K,
                            white_back, infinity, sl.d_rgbs, nullptr, sl.stream);
     if (rc != AVR_OK) return rc;
     AVR_RT(cudaMemcpyAsync(rgb + r0 * 3, sl.rgb, (size_t)rn * 12, cudaMemcpyDeviceToHost, sl.stream));
     AVR_RT(cudaMemcpyAsync(depth + r0, sl.depth, (size_t)rn * 4, cudaMemcpyDeviceToHost, sl.stream));
+    if (w) AVR_RT(cudaMemcpyAsync(w + r0 * K, sl.w, n * 4, cudaMemcpyDeviceToHost, sl.stream));
     AVR_RT(cudaMemcpyAsync(d_rgbs + r0 * K * 4, sl.d_rgbs, n * 16, cudaMemcpyDeviceToHost, sl.stream));
   }
-  for (auto& sl : ws->slots) AVR_RT(cudaStreamSynchronize(sl.stream));
   return AVR_OK;
+}
+
+// Whatever was enqueued is drained before returning — also on the error path, so no copy into the
+// caller's host buffers is still in flight once the call has reported its status.
+static int run_host_pass(avr_host_workspace* ws, const float* rgbs, const float* z, const float* g_rgb,
+                         const float* g_depth, int64_t R, int white_back, float infinity, float* rgb,
+                         float* depth, float* w, float* d_rgbs) {
+  int prev = 0;
+  AVR_RT(cudaGetDevice(&prev));
+  if (prev != ws->device) AVR_RT(cudaSetDevice(ws->device));  // streams and buffers live on the workspace's device
+  int rc = enqueue_host_pass(ws, rgbs, z, g_rgb, g_depth, R, white_back, infinity, rgb, depth, w, d_rgbs);
+  for (auto& sl : ws->slots) {
+    cudaError_t e = cudaStreamSynchronize(sl.stream);
+    if (e != cudaSuccess && rc == AVR_OK) {
+      set_last_cuda_error(e);
+      (void)cudaGetLastError();
+      rc = AVR_ERR_RUNTIME;
+    }
+  }
+  if (prev != ws->device) (void)cudaSetDevice(prev);
+  return rc;
 }
 
 extern "C" {
@@ -494,11 +549,11 @@ int avr_host_workspace_destroy(avr_host_workspace* ws) {
 
 int avr_composite_fwd_bwd_host(avr_host_workspace* ws, const float* rgbs, const float* z, const float* g_rgb,
                                const float* g_depth, int64_t R, int K, int white_back, float infinity,
-                               float* rgb, float* depth, float* d_rgbs) {
+                               float* rgb, float* depth, float* w, float* d_rgbs) {
   if (!ws || R < 0 || K < 1 || K != ws->K) return AVR_ERR_BAD_ARG;
   if (R == 0) return AVR_OK;
   if (!rgbs || !z || !rgb || !depth || !d_rgbs) return AVR_ERR_BAD_ARG;
-  return run_host_pass(ws, rgbs, z, g_rgb, g_depth, R, white_back, infinity, rgb, depth, d_rgbs);
+  return run_host_pass(ws, rgbs, z, g_rgb, g_depth, R, white_back, infinity, rgb, depth, w, d_rgbs);
 }
 
 }  // extern "C"

@@ -321,6 +321,7 @@ composite_fwd_span_kernel(const SpanArgs a) {
     }
   }
   if (kWriteW && lane == 0) bulk_wait_all<0>();
+  if (gather && a.n_signal > 0) signal_gather_done(a);
 }
 
 template <int L, int NS, bool kSimple, bool kDz>
@@ -394,10 +395,6 @@ composite_bwd_span_kernel(const SpanArgs a) {
 // ---- host side ----------------------------------------------------------------------
 static const int kLs[] = {5, 7, 9, 11, 13};
 
-static int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return (v && *v) ? std::atoi(v) : dflt;
-}
 
 // Defaults from the B200 sweep in profiles/r01_span_sweep.md: a 3-deep ring (one tile in
 // flight behind the one being computed) with as many resident warps as shared memory
@@ -406,18 +403,18 @@ static int env_int(const char* name, int dflt) {
 // (3|4) the ring depth, AVR_SPAN_WARPS (1..8) the warps per CTA.
 static int stages_for(int L) {
   (void)L;
-  int s = env_int("AVR_SPAN_STAGES", 0);
+  int s = option(OPT_SPAN_STAGES, 0);
   return (s == 3 || s == 4) ? s : 3;
 }
 static int warps_per_cta(int L) {
-  int w = env_int("AVR_SPAN_WARPS", L >= 11 ? 2 : 4);
+  int w = option(OPT_SPAN_WARPS, L >= 11 ? 2 : 4);
   return w < 1 ? 1 : (w > 8 ? 8 : w);
 }
 
 bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan) {
   if (K < 1 || R < 1) return false;
   if (!aligned16(rgbs) || !aligned16(z)) return false;
-  const int forced = env_int("AVR_SPAN_L", 0);
+  const int forced = option(OPT_SPAN_L, 0);
   int best_L = 0, best_nr = 0;
   double best_util = 0.0;
   for (int L : kLs) {
@@ -479,9 +476,7 @@ static int span_launch(KernelT kernel, int L, int stage_bytes, int stages, const
     (void)cudaGetLastError();
     return AVR_ERR_LAUNCH;
   }
-  int dev = 0, sms = kNumSMs;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = num_sms();
   const int64_t want = (a.n_tiles + warps - 1) / warps;
   const int64_t cap = (int64_t)sms * occ;
   const int grid = (int)(want < cap ? want : cap);
@@ -540,9 +535,17 @@ static SpanArgs make_args(const SpanPlan& plan, int K, int white_back, float inf
 int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
                               cudaStream_t stream, void* const* peers, int n_peers, int64_t peer_row0,
-                              bool multicast) {
+                              bool multicast, const GatherSignal* signal) {
   SpanArgs a = make_args(plan, K, white_back, infinity);
   if (n_peers > kMaxPeers) return AVR_ERR_UNSUPPORTED;
+  if (signal && signal->n > 0) {
+    if (signal->n > kMaxPeers || n_peers < 1) return AVR_ERR_UNSUPPORTED;
+    a.n_signal = signal->n;
+    a.signal_slot = signal->slot;
+    a.signal_value = signal->value;
+    a.done_counter = signal->done_counter;
+    for (int p = 0; p < signal->n; ++p) a.signal_flags[p] = signal->flags[p];
+  }
   a.n_peers = n_peers;
   a.peers_multicast = multicast ? 1 : 0;
   a.peer_row0 = peer_row0;

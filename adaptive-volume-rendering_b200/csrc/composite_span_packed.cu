@@ -390,8 +390,7 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
 
 // ---- host side -----------------------------------------------------------------------
 bool span_packed_eligible(const void* rgbs, const void* z, const void* w_or_null, const void* d_rgbs_or_null) {
-  const char* off = std::getenv("AVR_PACKED_SPAN");
-  if (off && off[0] == '0') return false;
+  if (!option(OPT_PACKED_SPAN, 1)) return false;
   return aligned16(rgbs) && aligned16(z) && aligned16(w_or_null) && aligned16(d_rgbs_or_null);
 }
 
@@ -410,9 +409,7 @@ static int packed_launch(KernelT kernel, const PackedArgs& a, cudaStream_t strea
     (void)cudaGetLastError();
     return AVR_ERR_LAUNCH;
   }
-  int dev = 0, sms = kNumSMs;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = num_sms();
   // enough samples per warp to amortise the range search; never more warps than tiles
   int64_t want = (a.S / kPkC + kPkWarps) / kPkWarps;
   if (want < 1) want = 1;

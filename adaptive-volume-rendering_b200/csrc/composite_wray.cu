@@ -68,7 +68,7 @@ composite_bwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
 
 static unsigned wray_grid(int64_t R) {
   int64_t b = (R + kWrayWarps - 1) / kWrayWarps;
-  const int64_t cap = (int64_t)kNumSMs * 16;
+  const int64_t cap = (int64_t)num_sms() * 16;
   if (b > cap) b = cap;
   return (unsigned)(b < 1 ? 1 : b);
 }

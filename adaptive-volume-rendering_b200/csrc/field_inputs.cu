@@ -205,22 +205,18 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
 //   AVR_FIELD_SHARE_POINT=x  per-row coordinate work shared out over the lanes (see point_from_lane)
 //   AVR_FIELD_STAGE=x        forward rows leave through shared memory and bulk copies (see kStage)
 //   AVR_FIELD_BWD_PREFETCH=x backward kernels that share the point work also prefetch the next row of g_out
-static bool env_flag(const char* name, bool dflt) {
-  const char* v = std::getenv(name);
-  return (v && *v) ? (*v != '0') : dflt;
-}
-static bool field_no_cache() { return env_flag("AVR_FIELD_NOCACHE", false); }
-static bool field_bwd_split() { return env_flag("AVR_FIELD_BWD_SPLIT", true); }
+static bool field_no_cache() { return option(OPT_FIELD_NOCACHE, 0) != 0; }
+static bool field_bwd_split() { return option(OPT_FIELD_BWD_SPLIT, 1) != 0; }
 // unset: the measured defaults (forward and feature-map backward share, the point backward does not:
 // 0.346 vs 0.362 ms); 0 / 1 force every kernel one way
-static bool field_share_point(bool dflt) { return env_flag("AVR_FIELD_SHARE_POINT", dflt); }
-static bool field_bwd_prefetch() { return env_flag("AVR_FIELD_BWD_PREFETCH", kFieldBwdPrefetchDefault); }
-static bool field_stage_rows() { return env_flag("AVR_FIELD_STAGE", kFieldStageDefault); }
+static bool field_share_point(bool dflt) { return option(OPT_FIELD_SHARE_POINT, dflt ? 1 : 0) != 0; }
+static bool field_bwd_prefetch() { return option(OPT_FIELD_BWD_PREFETCH, kFieldBwdPrefetchDefault ? 1 : 0) != 0; }
+static bool field_stage_rows() { return option(OPT_FIELD_STAGE, kFieldStageDefault ? 1 : 0) != 0; }
 
 static unsigned field_grid(int64_t rows, int chunk) {
   const int64_t n_chunks = (rows + chunk - 1) / chunk;
   int64_t blocks = (n_chunks + kFieldWarps - 1) / kFieldWarps;
-  const int64_t cap = (int64_t)kNumSMs * 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
   return (unsigned)(blocks > cap ? cap : blocks);
 }
 

@@ -257,7 +257,7 @@ int launch_ray_points(const float* ros, const float* rds, const float* z_or_u, c
   const int64_t total = R * (int64_t)K;
   if (total == 0) return AVR_OK;
   const bool vec = (K % 4 == 0) && aligned16(z_or_u) && aligned16(pts) && aligned16(viewdirs) && aligned16(z_out);
-  const int max_blocks = kNumSMs * 16;
+  const int max_blocks = num_sms() * 16;
   if (vec) {
     const int64_t n_vec = total / 4;
     if (from_u) {
@@ -280,7 +280,7 @@ int launch_ray_points(const float* ros, const float* rds, const float* z_or_u, c
 int launch_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K, float* d_z, cudaStream_t stream) {
   const int64_t total = R * (int64_t)K;
   if (total == 0) return AVR_OK;
-  ray_points_bwd_kernel<<<grid_1d(total, kNumSMs * 16), 256, 0, stream>>>(rds, g_pts, total, K, d_z);
+  ray_points_bwd_kernel<<<grid_1d(total, num_sms() * 16), 256, 0, stream>>>(rds, g_pts, total, K, d_z);
   return check_launch();
 }
 
@@ -288,7 +288,7 @@ int launch_ray_points_packed(const float* ros, const float* rds, const float* z,
                              float* pts, float* viewdirs, const float* g_pts, float* d_z, cudaStream_t stream) {
   if (R == 0) return AVR_OK;
   int64_t blocks = (R + 3) / 4;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   ray_points_packed_kernel<<<(unsigned)blocks, 128, 0, stream>>>(ros, rds, z, offsets, R, pts, viewdirs, g_pts, d_z);
   return check_launch();
 }
@@ -296,14 +296,14 @@ int launch_ray_points_packed(const float* ros, const float* rds, const float* z,
 int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, int64_t R, int64_t rays_per_cam,
                       float* ros, float* rds, cudaStream_t stream) {
   if (R == 0) return AVR_OK;
-  world_rays_kernel<<<grid_1d(R, kNumSMs * 16), 256, 0, stream>>>(x_pix, kinv, c2w, R, rays_per_cam, ros, rds);
+  world_rays_kernel<<<grid_1d(R, num_sms() * 16), 256, 0, stream>>>(x_pix, kinv, c2w, R, rays_per_cam, ros, rds);
   return check_launch();
 }
 
 int launch_depth_from_world(const float* ros, const float* rds, const float* dist, const float* c2w, int64_t R,
                             float* depth, float* grad_row, cudaStream_t stream) {
   if (R == 0) return AVR_OK;
-  depth_from_world_kernel<<<grid_1d(R, kNumSMs * 16), 256, 0, stream>>>(ros, rds, dist, c2w, R, depth, grad_row);
+  depth_from_world_kernel<<<grid_1d(R, num_sms() * 16), 256, 0, stream>>>(ros, rds, dist, c2w, R, depth, grad_row);
   return check_launch();
 }
 

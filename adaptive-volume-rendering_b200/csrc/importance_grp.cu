@@ -407,7 +407,7 @@ static int launch_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
   constexpr int RPW = 32 / G;
   const int64_t n_wg = (a.R + RPW - 1) / RPW;
   int64_t blocks = (n_wg + C::WARPS - 1) / C::WARPS;
-  const int64_t cap = (int64_t)kNumSMs * C::MIN_BLOCKS * 4;  // a few waves for balance
+  const int64_t cap = (int64_t)num_sms() * C::MIN_BLOCKS * 4;  // a few waves for balance
   if (blocks > cap) blocks = cap;
   importance_grp_kernel<G, KC, NI, ND, false, 0><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
   return check_launch();
@@ -417,7 +417,7 @@ template <int G, int KC, int NI, int kClass>
 static int launch_grp_ragged(const ImportanceRegArgs& a, cudaStream_t stream) {
   using C = GrpCfg<G, KC, NI, 0>;
   int64_t blocks = (a.R + C::WARPS * 32 - 1) / (C::WARPS * 32);
-  const int64_t cap = (int64_t)kNumSMs * C::MIN_BLOCKS * 2;
+  const int64_t cap = (int64_t)num_sms() * C::MIN_BLOCKS * 2;
   if (blocks > cap) blocks = cap;
   importance_grp_kernel<G, KC, NI, 0, true, kClass><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
   return check_launch();
@@ -446,8 +446,7 @@ int launch_importance_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
   // lanes per ray: 16 for the 128-sample shape (64 registers -> 32 resident warps/SM beats the
   // fewer shuffle stages of 8 lanes at 118 registers: 0.77 vs 0.83 ms for 2^20 rays on B200);
   // 8 for the small shapes.  AVR_GRP_G=8|16 overrides (experiments).
-  const char* gsw = std::getenv("AVR_GRP_G");
-  const int force_g = (gsw && *gsw) ? std::atoi(gsw) : 0;
+  const int force_g = option(OPT_GRP_G, 0);
   if (force_g == 32 && a.Kc == 64 && a.n_imp == 128 && a.n_depth == 0) return launch_grp<32, 64, 128, 0>(a, stream);
 #define AVR_GRP_CASE(G_, KC_, NI_, ND_)                                        \
   if (a.Kc == KC_ && a.n_imp == NI_ && a.n_depth == ND_) {                     \

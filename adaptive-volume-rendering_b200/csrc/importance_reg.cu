@@ -443,7 +443,7 @@ importance_reg_kernel(const ImportanceRegArgs a) {
 template <int EPF, int EPT, int KC = 0, int NI = 0, int ND = 0>
 static int launch_reg(const ImportanceRegArgs& a, cudaStream_t stream) {
   int64_t blocks = (a.R + kRegWarps - 1) / kRegWarps;
-  const int64_t cap = (int64_t)kNumSMs * 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   importance_reg_kernel<EPF, EPT, KC, NI, ND, false><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
   return check_launch();
@@ -453,7 +453,7 @@ static int launch_reg(const ImportanceRegArgs& a, cudaStream_t stream) {
 template <int EPF, int EPT>
 static int launch_reg_class(const ImportanceRegArgs& a, cudaStream_t stream) {
   int64_t blocks = (a.R + kRegWarps * 32 - 1) / (kRegWarps * 32);
-  const int64_t cap = (int64_t)kNumSMs * (EPT >= 16 ? 2 : 3);
+  const int64_t cap = (int64_t)num_sms() * (EPT >= 16 ? 2 : 3);
   if (blocks > cap) blocks = cap;
   importance_reg_kernel<EPF, EPT, 0, 0, 0, true><<<(unsigned)blocks, kRegWarps * 32, 0, stream>>>(a);
   return check_launch();
@@ -502,8 +502,7 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   // hot dense shapes: eight lanes per ray, shape as template constants (importance_grp.cu);
   // AVR_IMPORTANCE_GRP=0 keeps them on the warp-per-ray kernel (A/B experiments)
   if (!offsets) {
-    const char* sw = std::getenv("AVR_IMPORTANCE_GRP");
-    if (!(sw && sw[0] == '0')) {
+    if (option(OPT_IMPORTANCE_GRP, 1)) {
       const int rc = launch_importance_grp(a, stream);
       if (rc != AVR_ERR_UNSUPPORTED) return rc;
     }
@@ -516,10 +515,8 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   // packed layout with enough rays to amortise the launches: one launch per ray class up to
   // the caller's maxima (AVR_PACKED_CLASSES=0: one launch, every ray at the maximum shape)
   if (offsets && R >= 4096) {
-    const char* sw = std::getenv("AVR_PACKED_CLASSES");
-    const char* gs = std::getenv("AVR_IMPORTANCE_GRP");
-    if (!(sw && sw[0] == '0')) {
-      if (!(gs && gs[0] == '0') && a.n_depth == 0 && !cdf && !idx) {
+    if (option(OPT_PACKED_CLASSES, 1)) {
+      if (option(OPT_IMPORTANCE_GRP, 1) && a.n_depth == 0 && !cdf && !idx) {
         // rays of at most 256 coarse / 128 new samples: 8 or 16 lanes per ray (importance_grp.cu)
         bool covers_all = false;
         const int rc = launch_importance_grp_ragged(a, Kc, n_imp, &covers_all, stream);

@@ -7,6 +7,18 @@
 
 namespace avr {
 
+// runtime.cu — switches (environment read once; avr_set_option overrides), SM count, counters
+enum Opt {
+  OPT_SPAN_L, OPT_SPAN_STAGES, OPT_SPAN_WARPS, OPT_COARSE_PACKED_RAY,
+  OPT_PACKED_SPAN, OPT_IMPORTANCE_GRP, OPT_PACKED_CLASSES, OPT_GRP_G,
+  OPT_FIELD_NOCACHE, OPT_FIELD_BWD_SPLIT, OPT_FIELD_SHARE_POINT, OPT_FIELD_BWD_PREFETCH,
+  OPT_FIELD_STAGE, OPT_IMPORTANCE_BINS, OPT_FIELD_BWD_RING,
+  OPT_COUNT
+};
+int option(Opt o, int dflt);
+int num_sms();                  // SMs of the current device (cached)
+void count_dispatch(int which); // AVR_DISPATCH_* of avr_b200.h
+
 // composite_generic.cu — any shape, dense (offsets == nullptr) or packed
 int launch_composite_fwd_generic(const float* rgbs, const float* z, const int64_t* offsets, int64_t R,
                                  int K, int white_back, float infinity, float* w, float* rgb,
@@ -33,10 +45,21 @@ struct SpanPlan {
   int64_t main_rays;  // rays covered by full tiles
 };
 bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan);
+// completion signal of a fused-gather launch (see SpanArgs::signal_flags)
+struct GatherSignal {
+  uint32_t* const* flags;   // per peer: that peer's flag array (device pointers, peer-mapped)
+  int n;                    // peers to signal
+  int slot;                 // word written in each array (this rank's index)
+  uint32_t value;
+  unsigned* done_counter;   // local device word, zero between launches
+};
 int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
                               cudaStream_t stream, void* const* peers = nullptr, int n_peers = 0,
-                              int64_t peer_row0 = 0, bool multicast = false);
+                              int64_t peer_row0 = 0, bool multicast = false,
+                              const GatherSignal* signal = nullptr);
+// runtime.cu: wait until flags[0..n) >= value (acquire, system scope); bounded spin
+int launch_gather_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* status, cudaStream_t stream);
 int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
                               float* d_z /* nullable; needs K > plan.L */, cudaStream_t stream);

@@ -42,6 +42,15 @@ struct SpanArgs {
   int n_peers;
   int peers_multicast;    // peers[0] is an NVSwitch multicast address: one multimem.st reaches every rank
   int64_t peer_row0;
+  // completion signal of the fused all-gather (nullable): when the LAST CTA of the launch has
+  // pushed its rows, it writes `signal_value` into word `signal_slot` of every peer's flag array
+  // (release, system scope).  A consumer waits for all sources' words (avr_gather_wait) instead
+  // of a cross-rank barrier, so no rank ever stalls on a peer that is merely behind.
+  uint32_t* signal_flags[kMaxPeers];
+  int n_signal;
+  int signal_slot;
+  uint32_t signal_value;
+  unsigned* done_counter;  // local device word, zero between launches
 };
 
 // A lane's run inside a tile (identical for every full tile of a launch).
@@ -166,6 +175,27 @@ __device__ __forceinline__ void flush_rays_to_peers(const SpanArgs& a, int64_t l
                    : "memory");
     } else {
       for (int p = 0; p < a.n_peers; ++p) a.peers[p][a.peer_row0 + ray] = v;
+    }
+  }
+}
+
+// End of a gather launch: every thread has issued its peer stores.  Count the CTA in; the last one
+// publishes the launch's signal value to every peer.  Ordering: each thread fences its own (weak)
+// peer stores at system scope, the CTA barrier carries them to thread 0, whose fence + atomic
+// releases them; the last CTA's thread 0 has observed every CTA's atomic, fences, then stores the
+// flags with release semantics — a consumer's ld.acquire.sys of the flag sees every row.
+__device__ __forceinline__ void signal_gather_done(const SpanArgs& a) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned prev = atomicAdd(a.done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done_counter = 0u;  // the next launch on this stream starts from zero
+      __threadfence_system();
+      for (int p = 0; p < a.n_signal; ++p)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.signal_flags[p] + a.signal_slot), "r"(a.signal_value)
+                     : "memory");
     }
   }
 }

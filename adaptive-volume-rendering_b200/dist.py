@@ -93,19 +93,36 @@ def composite_sharded(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = Tr
 
 
 class FusedGather:
-    """All-gather of the per-ray outputs fused into the forward compositing kernel.
+    """All-gather of the per-ray outputs fused into the forward compositing kernel, with no
+    cross-rank barrier on the step's critical path.
 
-    Every rank owns a symmetric-memory buffer ``gathered`` of shape (world*R_local, 4) =
-    (r,g,b,depth) per ray; the span kernel's epilogue stores each finished ray straight into
-    row ``rank*R_local + ray`` of EVERY rank's buffer (16-byte stores to peer memory over
-    NVLink / NVSwitch), so the exchange rides along with the kernel instead of following it.
-    ``finish()`` is the cross-rank barrier after which ``gathered`` is complete everywhere.
+    Every rank owns a symmetric-memory buffer holding TWO slots of ``gathered`` rows — shape
+    (R_total, 4) = (r,g,b,depth) per ray, ranks' shards back to back (shards may differ in
+    size) — plus a small signal area.  The span kernel's epilogue stores each finished group
+    of 32 rays straight into the current slot of EVERY rank's buffer (coalesced 512-byte
+    stores to peer memory over NVLink / NVSwitch, or one ``multimem.st`` through the NVSwitch
+    multicast mapping), and the last CTA of the launch then publishes the step number into
+    word ``rank`` of every rank's flag array (release, system scope).  ``finish()`` enqueues a
+    one-warp kernel that waits until all ``world`` words of the LOCAL flag array carry the
+    step number (acquire) — so a rank only ever waits for data it is about to read, typically
+    long after it arrived, instead of rendezvousing with every peer once per step.
+
+    Contract (same as PipelinedGather): call ``finish()`` once per ``launch()``, and read the
+    views it returns on the same stream BEFORE the next ``launch()``.  Steps alternate between
+    the two slots: a peer can be at most one step ahead (its step i+2 forward is ordered after
+    its own wait for step i+1, i.e. after this rank launched step i+1, i.e. after this rank's
+    reads of step i), so it never overwrites rows that are still being read.
+
     Falls back (``available == False``) when symmetric memory cannot be set up; callers then
     use ``all_gather_outputs`` (NCCL).
     """
 
+    SLOTS = 2
+    _SIGNAL_ROWS = 64          # 1 KiB: flags[slot][32] at +0 / +128, done counter at +512, status at +516
+
     def __init__(self, rays_local: int, device, group: Optional[dist.ProcessGroup] = None):
         import ctypes
+        import os
 
         self.rays_local = rays_local
         self.group = group if group is not None else dist.group.WORLD
@@ -113,25 +130,48 @@ class FusedGather:
         self.rank = dist.get_rank(self.group)
         self.available = False
         self.error = None
+        self.step = 0              # launches so far; step i uses slot i % 2 and signal value i + 1
+        self._waited = 0           # steps whose wait has been enqueued
         try:
+            if self.world > 16:
+                raise RuntimeError("the fused gather addresses at most 16 peers")
             import torch.distributed._symmetric_memory as symm_mem
 
-            self.gathered = symm_mem.empty((self.world * rays_local, 4), dtype=torch.float32, device=device)
-            self.handle = symm_mem.rendezvous(self.gathered, self.group)
-            ptrs = [int(p) for p in self.handle.buffer_ptrs]
-            self._ptr_array = (ctypes.c_void_p * self.world)(*ptrs)
-            # NVSwitch multicast mapping of the same buffers (0 when the box has no NVLS support)
-            import os
-
-            # opt-in (AVR_GATHER_MULTICAST=1): measured identical to the per-peer stores at 2 and 4 GPUs
-            # (profiles/r01_multi_gpu.md) and not yet run at 8, so the per-peer path stays the default
-            self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
-            if os.environ.get("AVR_GATHER_MULTICAST", "0") != "1":
-                self.multicast_ptr = 0
-            self.handle.barrier()
+            # shards may be uneven (shard_bounds): every rank needs every rank's row range
+            n = torch.tensor([rays_local], dtype=torch.int64, device=device)
+            sizes = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(sizes, n, group=self.group)
+            self.sizes = [int(t.item()) for t in sizes]
+            self.row0 = sum(self.sizes[:self.rank])
+            self.rows_total = sum(self.sizes)
+            rows = self.SLOTS * self.rows_total + self._SIGNAL_ROWS
+            self.buffer = symm_mem.empty((rows, 4), dtype=torch.float32, device=device)
+            self.buffer.zero_()
+            self.handle = symm_mem.rendezvous(self.buffer, self.group)
+            base = [int(p) for p in self.handle.buffer_ptrs]
+            slot_bytes = self.rows_total * 16
+            sig = self.SLOTS * slot_bytes
+            self._peer_rows = [(ctypes.c_void_p * self.world)(*[b + s * slot_bytes for b in base]) for s in range(self.SLOTS)]
+            self._peer_flags = [(ctypes.c_void_p * self.world)(*[b + sig + s * 128 for b in base]) for s in range(self.SLOTS)]
+            self._local_flags = [base[self.rank] + sig + s * 128 for s in range(self.SLOTS)]
+            self._done_counter = base[self.rank] + sig + 512
+            self._status_ptr = base[self.rank] + sig + 516
+            # NVSwitch multicast mapping of the same buffers (0 when the box has no NVLS support);
+            # opt-in (AVR_GATHER_MULTICAST=1): same step time as the per-peer stores at 2 and 4 GPUs
+            mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+            self.multicast_ptr = mc if os.environ.get("AVR_GATHER_MULTICAST", "0") == "1" else 0
+            self._mc_rows = [(ctypes.c_void_p * 1)(self.multicast_ptr + s * slot_bytes) for s in range(self.SLOTS)]
+            torch.cuda.synchronize(device)
+            self.handle.barrier()          # every rank's buffer is zeroed before anyone signals into it
+            torch.cuda.synchronize(device)
             self.available = True
         except Exception as exc:  # pragma: no cover - depends on the box
             self.error = f"{type(exc).__name__}: {exc}"
+
+    # the views of one slot
+    def gathered(self, slot: int):
+        g = self.buffer[slot * self.rows_total:(slot + 1) * self.rows_total]
+        return g[:, :3], g[:, 3]
 
     def composite_fwd(self, rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = True, infinity: float = 1.8,
                       want_w: bool = True):
@@ -154,21 +194,49 @@ class FusedGather:
                              None if w is None else w.data_ptr(), rgb.data_ptr(), depth.data_ptr(), _stream(z))
         if rc == -4:   # AVR_ERR_UNSUPPORTED
             return None
-        _lib.check(rc, "avr_composite_fwd_gather")
+        _lib.check(rc, "avr_composite_fwd_gather_signal")
         return rgb, depth, w
 
     def launch(self, lib, rgbs_ptr, z_ptr, r, k, white_back, infinity, w_ptr, rgb_ptr, depth_ptr, stream):
-        """The raw C-ABI call: multicast stores when the box supports them, per-peer stores otherwise."""
+        """The raw C-ABI call for the next step (multicast stores when enabled, per-peer stores
+        otherwise).  Returns the status; on success the step counter advances."""
+        if self._waited != self.step:
+            raise RuntimeError("FusedGather.launch: finish() of the previous step was not called")
+        slot = self.step % self.SLOTS
         if self.multicast_ptr:
-            return lib.avr_composite_fwd_gather_multicast(rgbs_ptr, z_ptr, r, k, white_back, infinity, w_ptr, rgb_ptr,
-                                                          depth_ptr, self.multicast_ptr, self.rank * self.rays_local, stream)
-        return lib.avr_composite_fwd_gather(rgbs_ptr, z_ptr, r, k, white_back, infinity, w_ptr, rgb_ptr, depth_ptr,
-                                            self._ptr_array, self.world, self.rank * self.rays_local, stream)
+            rows, n_rows, mc = self._mc_rows[slot], 1, 1
+        else:
+            rows, n_rows, mc = self._peer_rows[slot], self.world, 0
+        rc = lib.avr_composite_fwd_gather_signal(rgbs_ptr, z_ptr, r, k, white_back, infinity, w_ptr, rgb_ptr, depth_ptr,
+                                                 rows, n_rows, mc, self.row0, self._peer_flags[slot], self.world,
+                                                 self.rank, (self.step + 1) & 0xFFFFFFFF, self._done_counter, stream)
+        if rc == 0:
+            self.step += 1
+        return rc
 
-    def finish(self):
-        """Cross-rank barrier (stream-ordered): afterwards every rank's ``gathered`` holds all rays."""
-        self.handle.barrier()
-        return self.gathered[:, :3], self.gathered[:, 3]
+    def finish(self, stream: Optional[int] = None):
+        """Stream-ordered wait for the rows of the last launched step from EVERY rank; returns the
+        views (rgb_all (R,3), depth_all (R,)) of that step's slot.  No rendezvous: ranks that are
+        ahead are not held back."""
+        from . import _lib
+
+        if self.step == 0 or self._waited == self.step:
+            raise RuntimeError("FusedGather.finish: nothing launched since the last finish()")
+        step = self.step - 1
+        slot = step % self.SLOTS
+        dev = self.buffer.device
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().avr_gather_wait(self._local_flags[slot], self.world, (step + 1) & 0xFFFFFFFF,
+                                                   self._status_ptr, stream), "avr_gather_wait")
+        self._waited = self.step
+        return self.gathered(slot)
+
+    def timed_out(self) -> bool:
+        """True if a wait gave up (a peer never signalled).  Synchronises the device."""
+        sig = self.buffer[self.SLOTS * self.rows_total:].view(torch.int32).reshape(-1)
+        return bool(int(sig[129].item()))     # status word: byte 516 of the signal area
 
 
 class PipelinedGather:
@@ -202,6 +270,11 @@ class PipelinedGather:
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
+            n = torch.tensor([rays_local], dtype=torch.int64, device=device)
+            sizes = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(sizes, n, group=self.group)
+            if any(int(t.item()) != rays_local for t in sizes):
+                raise RuntimeError("PipelinedGather needs equal shards on every rank (FusedGather takes uneven ones)")
             rows = self.world * rays_local
             self.buffer = symm_mem.empty((slots * rows, 4), dtype=torch.float32, device=device)
             self.handle = symm_mem.rendezvous(self.buffer, self.group)

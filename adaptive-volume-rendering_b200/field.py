@@ -117,6 +117,7 @@ class _FieldInputs(torch.autograd.Function):
             check(_lib.load().avr_field_inputs_fwd(ctypes.byref(d), torch.cuda.current_stream(xyz.device).cuda_stream),
                   "avr_field_inputs_fwd")
         ctx.cfg, ctx.features_only = cfg, features_only
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(xyz, viewdirs, latent, poses, focal, c)
         return out
 
@@ -125,7 +126,7 @@ class _FieldInputs(torch.autograd.Function):
         xyz, viewdirs, latent, poses, focal, c = ctx.saved_tensors
         need_xyz, need_vd, need_lat = ctx.needs_input_grad[:3]
         need_vd = need_vd and viewdirs is not None
-        if not (need_xyz or need_vd or need_lat):
+        if g_out is None or not (need_xyz or need_vd or need_lat):
             return (None,) * 8
         g_out = _f32c(g_out, "g_out")
         d = _fill(ctx.cfg, xyz, viewdirs, latent, poses, focal, c, ctx.features_only)

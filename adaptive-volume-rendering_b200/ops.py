@@ -64,6 +64,7 @@ class CoarseSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, near, far, u):
         near_c, far_c, stride = _bounds(near, far, u.numel() // u.shape[-1])
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(u)
         ctx.bshape = (near.shape, far.shape)
         ctx.stride = stride
@@ -71,6 +72,8 @@ class CoarseSample(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_z):
+        if g_z is None:
+            return None, None, None
         (u,) = ctx.saved_tensors
         g_z = _f32c(g_z)
         u = _f32c(u)
@@ -146,12 +149,15 @@ class SortRays(torch.autograd.Function):
         perm = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
         with torch.cuda.device(zc.device):
             check(_lib.load().avr_sort_rays(ptr(zc), r, k, ptr(out), ptr(perm), _stream(zc)), "avr_sort_rays")
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(perm)
         ctx.mark_non_differentiable(perm)
         return out, perm
 
     @staticmethod
     def backward(ctx, g_out, _g_perm):
+        if g_out is None:
+            return None
         (perm,) = ctx.saved_tensors
         g_out = _f32c(g_out)
         k = g_out.shape[-1]
@@ -206,6 +212,10 @@ class Composite(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rgbs, z, white_back: bool, infinity: float, want_w: bool):
         rgb, depth, w = composite_fwd_raw(rgbs, z, white_back, infinity, want_w)
+        # an output nobody differentiates through must reach backward as None, not as a tensor of
+        # zeros: a materialised g_w would push every training step of VolumeRenderer's coarse pass
+        # (w_c only feeds the detached sampler, renderers.py:36) off the span kernel (api.cu)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(rgbs, z)
         ctx.cfg = (bool(white_back), float(infinity))
         if w is None:
@@ -219,6 +229,8 @@ class Composite(torch.autograd.Function):
         white_back, infinity = ctx.cfg
         if g_w is not None and g_w.numel() == 0:
             g_w = None
+        if g_rgb is None and g_depth is None and g_w is None:
+            return None, None, None, None, None
         want_dz = ctx.needs_input_grad[1]
         d_rgbs, d_z = composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back, infinity, want_dz)
         return (d_rgbs.view_as(rgbs) if ctx.needs_input_grad[0] else None), d_z, None, None, None
@@ -256,6 +268,7 @@ class CompositePacked(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rgbs, z, offsets, white_back, infinity, want_w):
         rgb, depth, w = composite_packed_fwd_raw(rgbs, z, offsets, white_back, infinity, want_w)
+        ctx.set_materialize_grads(False)   # see Composite.forward
         ctx.save_for_backward(rgbs, z, offsets)
         ctx.cfg = (bool(white_back), float(infinity))
         if w is None:
@@ -270,6 +283,8 @@ class CompositePacked(torch.autograd.Function):
         rgbs_c, z_c = _f32c(rgbs), _f32c(z)
         if g_w is not None and g_w.numel() == 0:
             g_w = None
+        if g_rgb is None and g_depth is None and g_w is None:
+            return None, None, None, None, None, None
         g_rgb = None if g_rgb is None else _f32c(g_rgb)
         g_depth = None if g_depth is None else _f32c(g_depth)
         g_w = None if g_w is None else _f32c(g_w)
@@ -348,6 +363,7 @@ class RayPoints(torch.autograd.Function):
         with torch.cuda.device(zc.device):
             check(_lib.load().avr_ray_points_fwd(ptr(o), ptr(d), ptr(zc), r, k, ptr(pts), ptr(vd), _stream(zc)),
                   "avr_ray_points_fwd")
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(d, zc)
         ctx.shapes = (ros.shape, rds.shape)
         return pts, vd
@@ -365,7 +381,7 @@ class RayPoints(torch.autograd.Function):
                 check(_lib.load().avr_ray_points_bwd(ptr(d), ptr(g), r, k, ptr(d_z), _stream(zc)), "avr_ray_points_bwd")
         if ctx.needs_input_grad[0] and g_pts is not None:
             d_o = g_pts.reshape(r, k, 3).sum(1).reshape(ctx.shapes[0])
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and (g_pts is not None or g_vd is not None):
             acc = torch.zeros(r, 3, dtype=torch.float32, device=zc.device)
             if g_pts is not None:
                 acc = acc + (g_pts.reshape(r, k, 3) * zc.reshape(r, k, 1)).sum(1)
@@ -397,6 +413,7 @@ class RayPointsPacked(torch.autograd.Function):
         with torch.cuda.device(zc.device):
             check(_lib.load().avr_ray_points_fwd_packed(ptr(o), ptr(d), ptr(zc), ptr(off), r, s, ptr(pts), ptr(vd), _stream(zc)),
                   "avr_ray_points_fwd_packed")
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(d, off)
         ctx.mark_non_differentiable(vd)
         return pts, vd
@@ -404,10 +421,10 @@ class RayPointsPacked(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pts, _g_vd):
         d, off = ctx.saved_tensors
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            raise _lib.AvrError("RayPointsPacked differentiates w.r.t. the depths only")
         if g_pts is None or not ctx.needs_input_grad[2]:
             return None, None, None, None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise _lib.AvrError("RayPointsPacked differentiates w.r.t. the depths only")
         g = _f32c(g_pts)
         s = g.shape[0]
         d_z = torch.empty(s, dtype=torch.float32, device=g.device)
@@ -480,12 +497,15 @@ class DepthFromWorld(torch.autograd.Function):
         with torch.cuda.device(o.device):
             check(_lib.load().avr_depth_from_world(ptr(o), ptr(d), ptr(t), ptr(c2w), r, ptr(depth), ptr(row), _stream(o)),
                   "avr_depth_from_world")
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(row, d, t)
         ctx.shapes = (ros.shape, None if rds is None else rds.shape, None if dist is None else dist.shape)
         return depth
 
     @staticmethod
     def backward(ctx, g):
+        if g is None:
+            return None, None, None, None
         row, d, t = ctx.saved_tensors
         gp = g.reshape(-1, 1) * row                      # dL/dp, (R,3)
         d_o = gp.reshape(ctx.shapes[0]) if ctx.needs_input_grad[0] else None

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define AVR_B200_ABI_VERSION 1
+#define AVR_B200_ABI_VERSION 2
 
 typedef void* avr_stream_t; /* cudaStream_t */
 
@@ -75,6 +75,24 @@ AVR_API int avr_composite_plan_info(int64_t R, int K, const void* rgbs, const vo
                                     int* samples_per_lane, int* rays_per_tile, int64_t* main_rays);
 /* Force the generic kernels (1) or restore automatic choice (0); process-wide, for tests. */
 AVR_API void avr_set_force_generic(int on);
+/* Tuning / A-B switches (process-wide).  Each is read from the environment variable of the same
+ * name ONCE, at first use (no getenv on any launch path); this call overrides it (unset != 0:
+ * back to the built-in default).  Names: AVR_SPAN_L, AVR_SPAN_STAGES, AVR_SPAN_WARPS,
+ * AVR_COARSE_PACKED (1 = one warp per ray), AVR_PACKED_SPAN, AVR_IMPORTANCE_GRP,
+ * AVR_PACKED_CLASSES, AVR_GRP_G, AVR_IMPORTANCE_BINS, AVR_FIELD_*.  AVR_ERR_BAD_ARG for an
+ * unknown name. */
+AVR_API int avr_set_option(const char* name, int value, int unset);
+/* Which kernel family served the composite calls so far (process-wide counters; tests and
+ * bench.py assert that training shapes stay on the span kernels).  Fills out[0..n) and returns
+ * AVR_DISPATCH_COUNT. */
+enum avr_dispatch {
+  AVR_DISPATCH_FWD_SPAN = 0, AVR_DISPATCH_FWD_WRAY, AVR_DISPATCH_FWD_GENERIC, AVR_DISPATCH_FWD_SPAN_PACKED,
+  AVR_DISPATCH_BWD_SPAN, AVR_DISPATCH_BWD_WRAY, AVR_DISPATCH_BWD_GENERIC, AVR_DISPATCH_BWD_SPAN_PACKED,
+  AVR_DISPATCH_IMPORTANCE_BINS, AVR_DISPATCH_IMPORTANCE_GRP, AVR_DISPATCH_IMPORTANCE_REG, AVR_DISPATCH_IMPORTANCE_SMEM,
+  AVR_DISPATCH_COUNT
+};
+AVR_API int avr_dispatch_counters(int64_t* out, int n);
+AVR_API void avr_dispatch_reset(void);
 
 /* ---------------------------------------------------------------- samplers -- */
 
@@ -147,6 +165,27 @@ AVR_API int avr_composite_fwd_gather(const float* rgbs, const float* z, int64_t 
                                      float* w, float* rgb, float* depth,
                                      void* const* peer_gathered, int n_peers, int64_t row0,
                                      avr_stream_t stream);
+
+/* The fused all-gather WITHOUT a cross-rank barrier.  Same stores as avr_composite_fwd_gather
+ * (multicast != 0: `peer_gathered[0]` is an NVSwitch multicast address, n_peers == 1), and when the
+ * last CTA of the launch has pushed its rows it writes `value` into word `self_rank` of each of the
+ * `n_flag_peers` flag arrays in `peer_flags` (HOST array of DEVICE pointers to uint32 arrays in peer-
+ * mapped memory, one array per rank, the local one included), release / system scope.  A consumer
+ * runs avr_gather_wait on ITS array before reading its gathered buffer.  `done_counter`: one zeroed
+ * device word owned by this rank (used to find the last CTA; left at zero).  `value` is a step
+ * number: later launches must pass larger values (serial-number arithmetic, wraps allowed).
+ * Double-buffer the gathered rows by step parity: a rank may run one step ahead of its peers. */
+AVR_API int avr_composite_fwd_gather_signal(const float* rgbs, const float* z, int64_t R, int K,
+                                            int white_back, float infinity,
+                                            float* w, float* rgb, float* depth,
+                                            void* const* peer_gathered, int n_peers, int multicast, int64_t row0,
+                                            uint32_t* const* peer_flags, int n_flag_peers, int self_rank,
+                                            uint32_t value, uint32_t* done_counter, avr_stream_t stream);
+/* Stream-ordered wait (one tiny kernel) until flags[0..n_sources) have all reached `value`
+ * (ld.acquire.sys).  The spin is bounded (~4 s): on expiry *status (device word, may be NULL) is set
+ * to 1 and the kernel returns, so a dead peer cannot hang this GPU. */
+AVR_API int avr_gather_wait(const uint32_t* flags, int n_sources, uint32_t value, uint32_t* status,
+                            avr_stream_t stream);
 
 /* Same, through an NVSwitch MULTICAST mapping of the gathered buffers (e.g. the multicast_ptr of a
  * torch symmetric-memory allocation on an NVLS-capable box): every 32 finished rays leave as one
@@ -302,8 +341,9 @@ AVR_API int avr_field_inputs_bwd(const avr_field_inputs* desc, avr_stream_t stre
 /* One forward+backward compositing pass over HOST buffers (pinned for full speed):
  * chunks the rays, overlaps H2D copies, the two kernels and D2H copies on the workspace's
  * streams, and returns when every output is on the host.  This is the call `bench.py`
- * times for the end-to-end figure.  Outputs rgb [R,3], depth [R], d_rgbs [R,K,4];
- * w is not returned (the fine pass discards it, renderers.py:270).
+ * times for the end-to-end figure.  Outputs rgb [R,3], depth [R], d_rgbs [R,K,4] and, when `w`
+ * is not NULL, the weights [R,K] (the coarse pass needs them, renderers.py:180/252; the fine
+ * pass discards them, :270).
  *
  * The workspace owns the device staging buffers and streams (3 slots of `chunk_rays` rays
  * x K samples); it is created once and reused across calls, is not thread-safe, and must
@@ -316,7 +356,7 @@ AVR_API int avr_composite_fwd_bwd_host(avr_host_workspace* ws,
                                        const float* rgbs, const float* z,
                                        const float* g_rgb, const float* g_depth,
                                        int64_t R, int K, int white_back, float infinity,
-                                       float* rgb, float* depth, float* d_rgbs);
+                                       float* rgb, float* depth, float* w, float* d_rgbs);
 
 #ifdef __cplusplus
 }

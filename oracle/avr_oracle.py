@@ -41,7 +41,8 @@ _PDF_EPS = 1e-5
 
 
 def _f32const(v: float, like: torch.Tensor) -> torch.Tensor:
-    return torch.tensor([v], dtype=torch.float32).to(like.dtype)
+    # created on the host and moved, like the reference's torch.Tensor([...]).to(device)
+    return torch.tensor([v], dtype=torch.float32).to(device=like.device, dtype=like.dtype)
 
 
 # --------------------------------------------------------------------------
@@ -52,7 +53,7 @@ def coarse_z(near: torch.Tensor, far: torch.Tensor, n: int, u: torch.Tensor) -> 
 
     near, far: (SB, R);  u: (SB, R, n) uniforms in [0,1).  Returns (SB, R, n).
     """
-    bins = torch.arange(n, dtype=torch.float32).to(u.dtype) / n          # :12
+    bins = torch.arange(n, dtype=torch.float32, device=u.device).to(u.dtype) / n   # :12
     span = far - near
     z = near.unsqueeze(-1) + torch.einsum("bs,j->bsj", span, bins)        # :13
     z = z + torch.einsum("bsi,bs->bsi", u, span) / n                      # :14
@@ -254,8 +255,9 @@ def render_volume(
     u_c, u_cdf, u_bin, normals = draws
     sb, r, _ = x_pix.shape
     ros, rds = world_rays(x_pix, intrinsics, cam2world)                    # :166
-    near_t = torch.tensor([near]).expand_as(ros[..., 0])
-    far_t = torch.tensor([far]).expand_as(ros[..., 0])
+    dev = x_pix.device                      # the reference keeps near/far on the device (to_gpu, :124-125)
+    near_t = torch.tensor([near]).to(dev).expand_as(ros[..., 0])
+    far_t = torch.tensor([far]).to(dev).expand_as(ros[..., 0])
     z_c = coarse_z(near_t, far_t, n_coarse, u_c)                           # :169
     pts = ros.unsqueeze(-2) + torch.einsum("bsi,bsj->bsji", rds, z_c)      # :171
     out = radiance_field(pts.reshape(sb, -1, 3),
@@ -264,7 +266,7 @@ def render_volume(
     out = out.view(sb, r, n_coarse, 4)
     rgb_c, dist_c, w_c = composite_rgbs(z_c, out, white_back)              # :180
     z_f = fine_z(near_t, far_t, w_c, u_cdf, u_bin)                         # :252
-    z_d = depth_z(normals, depth_std, torch.tensor([near]), torch.tensor([far]))  # :254-255
+    z_d = depth_z(normals, depth_std, torch.tensor([near]).to(dev), torch.tensor([far]).to(dev))  # :254-255
     z_s = merge_sorted(z_c, z_f, z_d)                                      # :257-258
     k = n_coarse + n_fine
     pts = ros.unsqueeze(-2) + torch.einsum("bsi,bsj->bsji", rds, z_s)      # :260

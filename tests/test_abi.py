@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_strings(lib):
-    assert lib.avr_abi_version() == 1
+    assert lib.avr_abi_version() == 2
     assert lib.avr_status_string(0) == b"ok" and lib.avr_status_string(-1) == b"bad argument"
 
 
@@ -56,6 +56,25 @@ def test_argument_checks_need_no_gpu(lib):
     buf = (ctypes.c_float * 64)()
     misaligned = ctypes.addressof(buf) + 4
     assert lib.avr_composite_fwd(misaligned, ctypes.addressof(buf), 1, 4, 1, 1.8, None, ctypes.addressof(buf), ctypes.addressof(buf), None) == -1
+
+
+def test_options_and_dispatch_counters_are_host_state(lib):
+    from avr_b200 import _lib
+    a = 1 << 20
+    assert lib.avr_set_option(b"AVR_NO_SUCH_SWITCH", 1, 0) == -1
+    L = ctypes.c_int()
+    assert lib.avr_composite_plan_info(1 << 20, 96, a, a, ctypes.byref(L), None, None) == 1 and L.value == 9
+    _lib.set_option("AVR_SPAN_L", 13)            # what AVR_SPAN_L=13 in the environment would do, without getenv per launch
+    assert lib.avr_composite_plan_info(1 << 20, 96, a, a, ctypes.byref(L), None, None) == 1 and L.value == 13
+    _lib.set_option("AVR_SPAN_L", None)
+    assert lib.avr_composite_plan_info(1 << 20, 96, a, a, ctypes.byref(L), None, None) == 1 and L.value == 9
+    _lib.dispatch_reset()
+    c = _lib.dispatch_counters()
+    assert set(c) == set(_lib.DISPATCH_NAMES) and not any(c.values())
+    # bad arguments of the signalled gather and of the wait are refused before any launch
+    assert lib.avr_gather_wait(None, 2, 1, None, None) == -1
+    assert lib.avr_gather_wait(a, 0, 1, None, None) == -1
+    assert lib.avr_composite_fwd_gather_signal(a, a, 96, 96, 1, 1.8, None, a, a, None, 2, 0, 0, None, 2, 0, 1, None, None) == -1
 
 
 def test_span_planner_is_host_logic(lib):

@@ -17,20 +17,20 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True, params=["default", "per_lane", "shared", "shared_staged", "shared_prefetch"])
-def kernel_variant(request, monkeypatch):
+def kernel_variant(request):
     """Every way the kernels are built (csrc/field_inputs.cu): a row's coordinate work done by each
     lane for itself or once per row and fetched by shuffles (AVR_FIELD_SHARE_POINT), output rows
     stored directly or staged in shared memory and sent by bulk copies (AVR_FIELD_STAGE), the next
     row of g_out prefetched or not (AVR_FIELD_BWD_PREFETCH)."""
+    from avr_b200 import _lib
     knobs = ("AVR_FIELD_SHARE_POINT", "AVR_FIELD_STAGE", "AVR_FIELD_BWD_PREFETCH")
-    if request.param == "default":          # what the library picks by itself
-        for k in knobs:
-            monkeypatch.delenv(k, raising=False)
-    else:
-        monkeypatch.setenv("AVR_FIELD_SHARE_POINT", "0" if request.param == "per_lane" else "1")
-        monkeypatch.setenv("AVR_FIELD_STAGE", "1" if request.param == "shared_staged" else "0")
-        monkeypatch.setenv("AVR_FIELD_BWD_PREFETCH", "1" if request.param == "shared_prefetch" else "0")
-    return request.param
+    if request.param != "default":          # "default": what the library picks by itself
+        _lib.set_option("AVR_FIELD_SHARE_POINT", 0 if request.param == "per_lane" else 1)
+        _lib.set_option("AVR_FIELD_STAGE", 1 if request.param == "shared_staged" else 0)
+        _lib.set_option("AVR_FIELD_BWD_PREFETCH", 1 if request.param == "shared_prefetch" else 0)
+    yield request.param
+    for k in knobs:
+        _lib.set_option(k, None)
 
 
 def _cfg(d):

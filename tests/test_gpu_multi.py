@@ -54,6 +54,33 @@ def _worker(rank, world, port, q, multicast):
             torch.cuda.synchronize()
             ok_fused = bool(torch.equal(rgb_f, rgb) and torch.equal(depth_f, depth)
                             and torch.equal(g_rgb, rgb_all) and torch.equal(g_depth, depth_all))
+            # (2b) six consecutive steps through the two slots with NO cross-rank barrier, uneven shards
+            # (6001 rays), a different image every step, the ranks deliberately out of step (odd ranks do
+            # extra work before launching, even ranks before reading), against the CPU oracle
+            import avr_oracle as O
+            r2 = 6001
+            z2 = torch.cat([z, z[:1]], 0)
+            x2 = torch.cat([x, x[:1]], 0)
+            lo2, hi2 = avr_dist.shard_bounds(r2, world, rank)
+            fg2 = avr_dist.FusedGather(hi2 - lo2, dev)
+            assert fg2.available, fg2.error
+            zs2 = z2[lo2:hi2].to(dev)
+            for step in range(6):
+                xi = x2.clone()
+                xi[..., :3] *= 1.0 / (step + 1)
+                if rank % 2 == 1:
+                    busy = ops.composite(x.to(dev), z.to(dev), True, 1.8, want_w=False)
+                out = fg2.composite_fwd(xi[lo2:hi2].to(dev), zs2, True, 1.8, want_w=False)
+                assert out is not None
+                if rank % 2 == 0:
+                    busy = ops.composite(x.to(dev), z.to(dev), True, 1.8, want_w=False)
+                a_rgb, a_depth = fg2.finish()
+                got_rgb, got_depth = a_rgb.cpu(), a_depth.cpu()      # read before the next launch (the contract)
+                want = O.composite_rgbs(z2.unsqueeze(0), xi.unsqueeze(0), True)
+                ok_fused = ok_fused and bool(torch.allclose(got_rgb, want[0][0], rtol=1e-5, atol=1e-6)
+                                             and torch.allclose(got_depth, want[1][0, :, 0], rtol=1e-5, atol=1e-6)
+                                             and torch.equal(got_rgb[lo2:hi2], out[0].cpu()))
+            ok_fused = ok_fused and not fg2.timed_out()
             # (3) copy-engine all-gather, double-buffered: three steps through two slots
             pg = avr_dist.PipelinedGather(hi - lo, dev)
             assert pg.available, pg.error

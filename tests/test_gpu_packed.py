@@ -203,13 +203,13 @@ def test_packed_span_tiling_matches_generic(name, dev):
 
 @pytest.mark.parametrize("variant", ["flat", "ray"])
 @pytest.mark.parametrize("case", ["c4_like", "empty_and_single", "empty_segments", "long", "scalar_bounds", "unaligned"])
-def test_packed_coarse_sampler_bit_exact(case, variant, dev, monkeypatch):
+def test_packed_coarse_sampler_bit_exact(case, variant, dev):
     """Packed coarse sampler (segment-of-32-rays flat kernel and the one-warp-per-ray kernel) against
     the oracle per bucket, bit for bit: ragged counts, empty rays, whole empty segments, rays longer
     than a warp step, scalar bounds, and u/z views off the 16-byte grid (the CPU suite walks the
     same per-lane code on the host: tests/test_host_kernel_cores.py)."""
-    from avr_b200 import ops
-    monkeypatch.setenv("AVR_COARSE_PACKED", variant)
+    from avr_b200 import _lib, ops
+    _lib.set_option("AVR_COARSE_PACKED", 1 if variant == "ray" else 0)
     g = torch.Generator().manual_seed(3)
     counts = {
         "c4_like": lambda: torch.randint(8, 257, (4099,), generator=g),
@@ -244,3 +244,4 @@ def test_packed_coarse_sampler_bit_exact(case, variant, dev, monkeypatch):
         f = far[rays] if far.numel() > 1 else far.expand(len(rays))
         want = O.coarse_z(n.unsqueeze(0), f.unsqueeze(0), k, u[idx].unsqueeze(0))[0]
         assert torch.equal(z[idx], want), (case, variant, k)
+    _lib.set_option("AVR_COARSE_PACKED", None)

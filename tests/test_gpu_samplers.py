@@ -13,15 +13,16 @@ pytestmark = pytest.mark.gpu
 def family(request):
     """Run through the kernel the library picks (8/16 lanes per ray for the hot shapes), the
     warp-per-ray register kernel, AND the general shared-memory kernel."""
-    import os
-
     import avr_b200
+    from avr_b200 import _lib
     lib = avr_b200.load_library()
     lib.avr_set_force_generic(1 if request.param == "generic" else 0)
     if request.param == "warp":
-        os.environ["AVR_IMPORTANCE_GRP"] = "0"
+        _lib.set_option("AVR_IMPORTANCE_GRP", 0)
+        _lib.set_option("AVR_IMPORTANCE_BINS", 0)
     yield request.param
-    os.environ.pop("AVR_IMPORTANCE_GRP", None)
+    _lib.set_option("AVR_IMPORTANCE_GRP", None)
+    _lib.set_option("AVR_IMPORTANCE_BINS", None)
     lib.avr_set_force_generic(0)
 
 

@@ -36,15 +36,11 @@ def synth_rgbs(n, dev, g):
     return x
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--rays", type=int, default=1 << 22)
-    ap.add_argument("--iters", type=int, default=5)
-    a = ap.parse_args()
-    dev = torch.device("cuda:0")
+def run(rays, iters, dev, warm=2):
+    """Yields one record per stage and a final one for the whole pipeline."""
     lib = avr_b200.load_library()
     g = torch.Generator(device=dev).manual_seed(0)
-    r = a.rays
+    r = rays
     counts = torch.randint(8, 257, (r,), device=dev, generator=g)
     offsets = torch.zeros(r + 1, dtype=torch.int64, device=dev)
     offsets[1:] = torch.cumsum(counts, 0)
@@ -61,7 +57,7 @@ def main():
     x_f = synth_rgbs(s + sf, dev, g)
     g_rgb, g_d = torch.randn(r, 3, device=dev, generator=g), torch.randn(r, device=dev, generator=g)
     dx = torch.empty_like(x_f)
-    sp = torch.cuda.current_stream().cuda_stream
+    sp = torch.cuda.current_stream(dev).cuda_stream
     state = {}
 
     def st_coarse():
@@ -88,32 +84,38 @@ def main():
         ("composite_fwd_packed (fine)", st_comp_f, 20 * (s + sf) + 24 * r),
         ("composite_bwd_packed (fine)", st_bwd, 36 * (s + sf) + 24 * r),
     ]
-    for _, fn, _ in stages:      # warm-up, also builds the state the later stages read
-        fn()
-    for _ in range(2):
+    for _ in range(1 + warm):    # warm-up, also builds the state the later stages read
         for _, fn, _ in stages:
             fn()
-    torch.cuda.synchronize()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(a.iters)]
-    for it in range(a.iters):
+    torch.cuda.synchronize(dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(iters)]
+    for it in range(iters):
         ev[it][0].record()
         for i, (_, fn, _) in enumerate(stages):
             fn()
             ev[it][i + 1].record()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     pk = peak()
     total_bytes = 0
     for i, (name, _, nbytes) in enumerate(stages):
-        ms = sum(ev[it][i].elapsed_time(ev[it][i + 1]) for it in range(a.iters)) / a.iters
+        ms = sum(ev[it][i].elapsed_time(ev[it][i + 1]) for it in range(iters)) / iters
         total_bytes += nbytes
-        print(json.dumps({"stage": name, "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1),
-                          "hbm_frac": round(nbytes / ms / 1e6 / pk, 4), "bytes": nbytes}), flush=True)
-    ms = sum(ev[it][0].elapsed_time(ev[it][-1]) for it in range(a.iters)) / a.iters
-    print(json.dumps({"pipeline": "coarse -> composite -> importance+merge -> composite fwd+bwd (packed, counts 8..256)",
-                      "rays": r, "coarse_samples": s, "fine_samples": sf, "ms": round(ms, 3),
-                      "rays_per_s": r / (ms * 1e-3), "composited_samples_per_s": (2 * s + sf) / (ms * 1e-3),
-                      "GBps": round(total_bytes / ms / 1e6, 1), "hbm_frac": round(total_bytes / ms / 1e6 / pk, 4)}),
-          flush=True)
+        yield {"stage": name, "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1),
+               "hbm_frac": round(nbytes / ms / 1e6 / pk, 4), "bytes": nbytes}
+    ms = sum(ev[it][0].elapsed_time(ev[it][-1]) for it in range(iters)) / iters
+    yield {"pipeline": "coarse -> composite -> importance+merge -> composite fwd+bwd (packed, counts 8..256)",
+           "rays": r, "coarse_samples": s, "fine_samples": sf, "ms": round(ms, 3),
+           "rays_per_s": r / (ms * 1e-3), "composited_samples_per_s": (2 * s + sf) / (ms * 1e-3),
+           "GBps": round(total_bytes / ms / 1e6, 1), "hbm_frac": round(total_bytes / ms / 1e6 / pk, 4)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=1 << 22)
+    ap.add_argument("--iters", type=int, default=5)
+    a = ap.parse_args()
+    for rec in run(a.rays, a.iters, torch.device("cuda:0")):
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":

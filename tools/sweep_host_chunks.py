@@ -12,7 +12,7 @@ for chunk in (4096, 8192, 16384, 32768, 65536, 131072, 262144):
     assert lib.avr_host_workspace_create(k, chunk, ctypes.byref(ws)) == 0
     def step():
         rc = lib.avr_composite_fwd_bwd_host(ws, hx.data_ptr(), hz.data_ptr(), hg.data_ptr(), hd.data_ptr(), rays, k, 1, 1.8,
-                                            o_rgb.data_ptr(), o_depth.data_ptr(), o_dx.data_ptr())
+                                            o_rgb.data_ptr(), o_depth.data_ptr(), None, o_dx.data_ptr())
         assert rc == 0
     step(); step()
     t0 = time.perf_counter()

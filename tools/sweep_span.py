@@ -41,9 +41,9 @@ def main():
         sp = torch.cuda.current_stream().cuda_stream
         ref = None
         for L, warps, stages in itertools.product(a.ls, a.warps, a.stages):
-            os.environ["AVR_SPAN_WARPS"] = str(warps)
-            os.environ["AVR_SPAN_STAGES"] = str(stages)
-            os.environ["AVR_SPAN_L"] = str(L) if L else ""
+            lib.avr_set_option(b"AVR_SPAN_WARPS", warps, 0)
+            lib.avr_set_option(b"AVR_SPAN_STAGES", stages, 0)
+            lib.avr_set_option(b"AVR_SPAN_L", L or 0, 0 if L else 1)
             Lc, rpt, mr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
             if not lib.avr_composite_plan_info(rays, k, x.data_ptr(), z.data_ptr(), ctypes.byref(Lc), ctypes.byref(rpt), ctypes.byref(mr)):
                 print(json.dumps({"k": k, "L": L, "skip": "no span plan"}))
