@@ -50,7 +50,7 @@ PROTOTYPES = {
     "avr_composite_bwd_packed": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_float, _P, _P, _P]),
     "avr_coarse_sample_fwd_packed": (c_int, [_P, _P, c_int, _P, _P, c_int64, c_int64, _P, _P]),
     "avr_importance_sample_packed": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int64, c_int, c_int,
-                                             _P, _P, _P]),
+                                             _P, _P, _P, _P, _P]),
     "avr_ray_points_fwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P]),
     "avr_ray_points_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P]),
     "avr_ray_points_fwd_packed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P]),

@@ -128,14 +128,14 @@ int avr_importance_sample(const float* weights, const float* z_coarse, const flo
 int avr_importance_sample_packed(const float* weights, const float* z_coarse, const float* u, const float* u2,
                                  const float* near, const float* far, int bound_stride, const int64_t* offsets,
                                  const int64_t* fine_offsets, int64_t R, int max_coarse, int max_fine,
-                                 float* z_fine, float* z_sorted, avr_stream_t stream) {
+                                 float* z_fine, float* z_sorted, float* cdf, int32_t* idx, avr_stream_t stream) {
   if (R < 0 || max_coarse < 1 || max_fine < 0 || (bound_stride != 0 && bound_stride != 1))
     return AVR_ERR_BAD_ARG;
   if (R == 0) return AVR_OK;
   if (!weights || !near || !far || !offsets || !fine_offsets || !u || !u2) return AVR_ERR_BAD_ARG;
   if (z_sorted && !z_coarse) return AVR_ERR_BAD_ARG;
   return launch_importance(weights, z_coarse, u, u2, nullptr, near, far, bound_stride, offsets, fine_offsets, R,
-                           max_coarse, max_fine, 0, 0.f, z_fine, z_sorted, nullptr, nullptr, !g_force_generic.load(), as_stream(stream));
+                           max_coarse, max_fine, 0, 0.f, z_fine, z_sorted, cdf, idx, !g_force_generic.load(), as_stream(stream));
 }
 
 int avr_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, avr_stream_t stream) {

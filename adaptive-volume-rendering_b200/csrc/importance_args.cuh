@@ -37,4 +37,9 @@ int launch_importance_grp(const ImportanceRegArgs& a, cudaStream_t stream);
 int launch_importance_grp_ragged(const ImportanceRegArgs& a, int max_coarse, int max_fine, bool* covers_all,
                                  cudaStream_t stream);
 
+// importance_bins.cu: the same shapes by bucket ranking instead of sorting networks
+int launch_importance_bins(const ImportanceRegArgs& a, cudaStream_t stream);
+int launch_importance_bins_ragged(const ImportanceRegArgs& a, int max_coarse, int max_fine, bool* covers_all,
+                                  cudaStream_t stream);
+
 }  // namespace avr

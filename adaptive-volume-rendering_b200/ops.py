@@ -320,8 +320,9 @@ def coarse_sample_packed(near, far, u, offsets):
 
 
 def importance_sample_packed(weights, z_coarse, near, far, u, u2, offsets, fine_offsets, max_coarse, max_fine,
-                             want_sorted=True):
-    """Packed sample_fine + merge: returns (z_fine (Sf,), z_sorted (S+Sf,) or None)."""
+                             want_sorted=True, want_cdf=False, want_idx=False):
+    """Packed sample_fine + merge: returns (z_fine (Sf,), z_sorted (S+Sf,) or None) — and, when asked
+    for, the cdf (S+R,: ray r's Kc_r+1 entries start at offsets[r]+r) and the int32 bin indices (Sf,)."""
     require_cuda(weights, u, u2, offsets, fine_offsets)
     weights, u, u2 = _f32c(weights.detach()), _f32c(u), _f32c(u2)
     z_coarse = _f32c(z_coarse.detach())
@@ -329,11 +330,15 @@ def importance_sample_packed(weights, z_coarse, near, far, u, u2, offsets, fine_
     near_c, far_c, stride = _bounds(near.detach(), far.detach(), r)
     z_fine = torch.empty_like(u)
     z_sorted = torch.empty(weights.numel() + u.numel(), dtype=torch.float32, device=u.device) if want_sorted else None
+    cdf = torch.zeros(weights.numel() + r, dtype=torch.float32, device=u.device) if want_cdf else None
+    idx = torch.zeros(u.numel(), dtype=torch.int32, device=u.device) if want_idx else None
     with torch.cuda.device(u.device):
         check(_lib.load().avr_importance_sample_packed(
             ptr(weights), ptr(z_coarse), ptr(u), ptr(u2), ptr(near_c), ptr(far_c), stride,
             ptr(offsets.contiguous()), ptr(fine_offsets.contiguous()), r, int(max_coarse), int(max_fine),
-            ptr(z_fine), ptr(z_sorted), _stream(u)), "avr_importance_sample_packed")
+            ptr(z_fine), ptr(z_sorted), ptr(cdf), ptr(idx), _stream(u)), "avr_importance_sample_packed")
+    if want_cdf or want_idx:
+        return z_fine, z_sorted, cdf, idx
     return z_fine, z_sorted
 
 

@@ -234,13 +234,19 @@ AVR_API int avr_coarse_sample_fwd_packed(const float* near, const float* far, in
  * samples from its Kc_r = offsets[r+1]-offsets[r] coarse weights (Kc_r >= 1 wherever
  * n_r > 0), and the merge has Kc_r + n_r entries at offsets[r] + fine_offsets[r].
  * max_coarse / max_fine: upper bounds on Kc_r / n_r over all rays (they size the
- * per-warp shared-memory tables; max_coarse + max_fine <= AVR_MAX_SORT). */
+ * per-warp shared-memory tables and pick the kernel classes; max_coarse + max_fine <=
+ * AVR_MAX_SORT).  PRECONDITION: they really are upper bounds — a ray with more samples than
+ * stated is processed at the stated shape (its tail ignored) without an error.
+ * cdf (may be NULL): the table each ray's search ran on, Kc_r + 1 entries per ray starting at
+ * offsets[r] + r (S + R floats in all); idx (may be NULL): int32 bin index per new sample, laid
+ * out like u — bit-exact with clamp_min(searchsorted(cdf_r, u_r, right=True) - 1, 0). */
 AVR_API int avr_importance_sample_packed(const float* weights, const float* z_coarse,
                                  const float* u, const float* u2,
                                  const float* near, const float* far, int bound_stride,
                                  const int64_t* offsets, const int64_t* fine_offsets,
                                  int64_t R, int max_coarse, int max_fine,
-                                 float* z_fine, float* z_sorted, avr_stream_t stream);
+                                 float* z_fine, float* z_sorted, float* cdf, int32_t* idx,
+                                 avr_stream_t stream);
 
 /* ------------------------------------------ ray setup / sample points / depth -- */
 

@@ -84,11 +84,15 @@ def test_packed_pipeline_vs_oracle(dev, family):
         assert_close(dz[idx] / scale[0], (wdz[0] / scale[0]).float(), rtol=1e-5, atol=2e-5, what=f"d_z k={k}")
 
 
+@pytest.mark.parametrize("kernels", ["bins", "networks"])
 @pytest.mark.parametrize("r,lo,hi", [(2000, 8, 128),     # few rays: one launch at the maximum shape
-                                     (6000, 1, 256),     # per-class ragged kernels (8/16 lanes per ray), n = 0 for k = 1
+                                     (6000, 1, 256),     # per-class ragged kernels (8..32 lanes per ray), n = 0 for k = 1
                                      (5000, 8, 300)])    # rays beyond the largest class box take the warp-per-ray classes
-def test_packed_importance_and_merge(r, lo, hi, dev):
-    from avr_b200 import ops
+def test_packed_importance_and_merge(r, lo, hi, kernels, dev):
+    """Both kernel families (bucket ranking, importance_bins.cu / sorting networks).  With the cdf and
+    the indices exported: indices bit-exact against searchsorted on the kernel's own cdf, per ray."""
+    from avr_b200 import _lib, ops
+    _lib.set_option("AVR_IMPORTANCE_BINS", 1 if kernels == "bins" else 0)
     counts, offsets, g = _ragged(r, lo, hi, seed=1, zero_some=False)
     fine_counts = counts // 2
     fine_offsets = torch.zeros(r + 1, dtype=torch.int64)
@@ -98,9 +102,13 @@ def test_packed_importance_and_merge(r, lo, hi, dev):
     w = torch.rand(int(offsets[-1]), generator=g) ** 6
     sf = int(fine_offsets[-1])
     uf, uf2 = torch.rand(sf, generator=g), torch.rand(sf, generator=g)
-    zf, zs = ops.importance_sample_packed(w.to(dev), zc.to(dev), near.to(dev), far.to(dev), uf.to(dev), uf2.to(dev),
-                                          offsets.to(dev), fine_offsets.to(dev), hi, hi // 2)
-    zf, zs = zf.cpu(), zs.cpu()
+    args = (w.to(dev), zc.to(dev), near.to(dev), far.to(dev), uf.to(dev), uf2.to(dev), offsets.to(dev), fine_offsets.to(dev),
+            hi, hi // 2)
+    zf, zs = ops.importance_sample_packed(*args)
+    zf2, zs2, kcdf, kidx = ops.importance_sample_packed(*args, want_cdf=True, want_idx=True)
+    _lib.set_option("AVR_IMPORTANCE_BINS", None)
+    assert torch.equal(zf, zf2) and torch.equal(zs, zs2)          # exporting the cdf changes nothing
+    zf, zs, kcdf, kidx = zf.cpu(), zs.cpu(), kcdf.cpu(), kidx.cpu()
     out_offsets = offsets + fine_offsets
     mismatched = 0
     for k, rays, idx in O.bucketed(offsets):
@@ -111,6 +119,11 @@ def test_packed_importance_and_merge(r, lo, hi, dev):
                                    uf[fidx].unsqueeze(0), uf2[fidx].unsqueeze(0), return_aux=True)
         same = zf[fidx] == want[0]
         mismatched += int((~same).sum())
+        # north_star: indices bit-exact given an identical CDF — the kernel's own table, entry by entry
+        cidx = (offsets[rays] + rays).unsqueeze(-1) + torch.arange(k + 1)
+        assert torch.equal(kidx[fidx].long(), O.cdf_search(kcdf[cidx], uf[fidx])), k
+        assert (kcdf[cidx][:, 0] == 0).all() and (kcdf[cidx][:, 1:] >= kcdf[cidx][:, :-1]).all()
+        assert_close(kcdf[cidx], cdf[0], rtol=1e-5, atol=1e-6, what=f"cdf k={k}")
         # the merge is the exact sort of the kernel's own samples
         assert torch.equal(zs[oidx], torch.sort(torch.cat([zc[idx], zf[fidx]], -1), -1).values), k
     assert mismatched <= max(2, int(2e-5 * sf))          # rare one-bin flips from the CDF's summation order

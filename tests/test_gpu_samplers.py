@@ -9,16 +9,19 @@ from conftest import assert_close, load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "warp", "generic"])
+@pytest.fixture(params=["auto", "grp", "warp", "generic"])
 def family(request):
-    """Run through the kernel the library picks (8/16 lanes per ray for the hot shapes), the
-    warp-per-ray register kernel, AND the general shared-memory kernel."""
+    """Run through the kernel the library picks (bucket ranking, importance_bins.cu, for the hot
+    shapes), the 8/16-lanes-per-ray sorting networks, the warp-per-ray register kernel, AND the
+    general shared-memory kernel."""
     import avr_b200
     from avr_b200 import _lib
     lib = avr_b200.load_library()
     lib.avr_set_force_generic(1 if request.param == "generic" else 0)
     if request.param == "warp":
         _lib.set_option("AVR_IMPORTANCE_GRP", 0)
+        _lib.set_option("AVR_IMPORTANCE_BINS", 0)
+    if request.param == "grp":
         _lib.set_option("AVR_IMPORTANCE_BINS", 0)
     yield request.param
     _lib.set_option("AVR_IMPORTANCE_GRP", None)
