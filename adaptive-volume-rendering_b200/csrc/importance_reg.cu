@@ -502,8 +502,9 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   // hot dense shapes: eight lanes per ray, shape as template constants (importance_grp.cu);
   // AVR_IMPORTANCE_GRP=0 keeps them on the warp-per-ray kernel (A/B experiments)
   if (!offsets) {
-    // bucket ranking (importance_bins.cu) when a merge is asked for; AVR_IMPORTANCE_BINS=0 keeps the networks
-    if (z_sorted && option(OPT_IMPORTANCE_BINS, 1)) {
+    // AVR_IMPORTANCE_BINS=1: bucket ranking (importance_bins.cu) instead of the sorting networks — exact and
+    // shape-agnostic, but measured 2x slower on B200 (profiles/r02_importance_bins.md), so it is opt-in
+    if (z_sorted && option(OPT_IMPORTANCE_BINS, 0)) {
       const int rc = launch_importance_bins(a, stream);
       if (rc == AVR_OK) count_dispatch(AVR_DISPATCH_IMPORTANCE_BINS);
       if (rc != AVR_ERR_UNSUPPORTED) return rc;
@@ -523,10 +524,10 @@ int launch_importance_reg(const float* weights, const float* z_coarse, const flo
   // the caller's maxima (AVR_PACKED_CLASSES=0: one launch, every ray at the maximum shape)
   if (offsets && R >= 4096) {
     if (option(OPT_PACKED_CLASSES, 1)) {
-      // rays of at most 256 coarse / 128 new samples: class kernels with 8..32 lanes per ray — bucket
-      // ranking (importance_bins.cu; also the one that exports cdf / idx for packed rays) or, with
-      // AVR_IMPORTANCE_BINS=0, the networks (importance_grp.cu)
-      const bool bins = z_sorted && a.n_depth == 0 && (option(OPT_IMPORTANCE_BINS, 1) || cdf || idx);
+      // rays of at most 256 coarse / 128 new samples: class kernels with 8..32 lanes per ray — the sorting
+      // networks (importance_grp.cu) or, with AVR_IMPORTANCE_BINS=1, bucket ranking (importance_bins.cu);
+      // a request for the cdf / the indices goes to the kernels that export them for packed rays
+      const bool bins = z_sorted && a.n_depth == 0 && option(OPT_IMPORTANCE_BINS, 0);
       const bool grp = !bins && a.n_depth == 0 && !cdf && !idx && option(OPT_IMPORTANCE_GRP, 1);
       if (bins || grp) {
         bool covers_all = false;

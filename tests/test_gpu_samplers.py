@@ -9,11 +9,11 @@ from conftest import assert_close, load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "grp", "warp", "generic"])
+@pytest.fixture(params=["auto", "bins", "warp", "generic"])
 def family(request):
-    """Run through the kernel the library picks (bucket ranking, importance_bins.cu, for the hot
-    shapes), the 8/16-lanes-per-ray sorting networks, the warp-per-ray register kernel, AND the
-    general shared-memory kernel."""
+    """Run through the kernel the library picks (8/16-lanes-per-ray sorting networks for the hot
+    shapes), the bucket-ranking kernel (importance_bins.cu, opt-in), the warp-per-ray register
+    kernel, AND the general shared-memory kernel."""
     import avr_b200
     from avr_b200 import _lib
     lib = avr_b200.load_library()
@@ -21,8 +21,8 @@ def family(request):
     if request.param == "warp":
         _lib.set_option("AVR_IMPORTANCE_GRP", 0)
         _lib.set_option("AVR_IMPORTANCE_BINS", 0)
-    if request.param == "grp":
-        _lib.set_option("AVR_IMPORTANCE_BINS", 0)
+    if request.param == "bins":
+        _lib.set_option("AVR_IMPORTANCE_BINS", 1)
     yield request.param
     _lib.set_option("AVR_IMPORTANCE_GRP", None)
     _lib.set_option("AVR_IMPORTANCE_BINS", None)
