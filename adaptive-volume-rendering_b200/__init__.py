@@ -16,12 +16,13 @@ from .renderers import (  # noqa: F401
     volume_integral,
     volume_integral_rgbs,
 )
-from . import ops, geometry, field  # noqa: F401
+from . import ops, geometry, field, march  # noqa: F401
+from .march import lstm_march  # noqa: F401
 from .field import FieldConfig, field_inputs, fuse_field_inputs  # noqa: F401
 from .dropin import accelerate, convert_renderer  # noqa: F401
 
 __all__ = [
     "AdaptiveVolumeRenderer", "VolumeRenderer", "sample_coarse", "sample_depth", "sample_fine",
     "volume_integral", "volume_integral_rgbs", "ops", "geometry", "field", "FieldConfig", "field_inputs",
-    "fuse_field_inputs", "accelerate", "convert_renderer", "AvrError", "load_library", "LIB_PATH",
+    "fuse_field_inputs", "lstm_march", "march", "accelerate", "convert_renderer", "AvrError", "load_library", "LIB_PATH",
 ]

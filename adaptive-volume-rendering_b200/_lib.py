@@ -60,6 +60,8 @@ PROTOTYPES = {
     "avr_depth_from_world": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P]),
     "avr_field_inputs_fwd": (c_int, [_P, _P]),
     "avr_field_inputs_bwd": (c_int, [_P, _P]),
+    "avr_lstm_march_fwd": (c_int, [_P, _P, _P]),
+    "avr_lstm_march_bwd": (c_int, [_P, _P, _P]),
     "avr_host_workspace_create": (c_int, [c_int, c_int64, ctypes.POINTER(c_void_p)]),
     "avr_host_workspace_destroy": (c_int, [_P]),
     "avr_composite_fwd_bwd_host": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P]),

@@ -21,7 +21,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libavr_b200.so")
 
-SOURCES = ["api.cu", "runtime.cu", "composite_generic.cu", "composite_span.cu", "samplers.cu", "importance_reg.cu", "importance_grp.cu", "importance_bins.cu", "composite_wray.cu", "composite_span_packed.cu", "geometry.cu", "field_inputs.cu"]
+SOURCES = ["api.cu", "runtime.cu", "composite_generic.cu", "composite_span.cu", "samplers.cu", "importance_reg.cu", "importance_grp.cu", "importance_bins.cu", "composite_wray.cu", "composite_span_packed.cu", "geometry.cu", "field_inputs.cu", "lstm_march.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -403,6 +403,41 @@ int avr_field_inputs_bwd(const avr_field_inputs* desc, avr_stream_t stream) {
   return launch_field_inputs_bwd(*desc, desc->NV / desc->NS, as_stream(stream));
 }
 
+/* ------------------------------------------ the adaptive renderer's LSTM ray march -- */
+
+static int check_march(const avr_field_inputs* f, const avr_lstm_march* m, bool backward) {
+  if (!f || !m || m->R < 0 || m->steps < 0 || m->rays_per_obj < 1) return AVR_ERR_BAD_ARG;
+  if (m->R == 0 || m->steps == 0) return AVR_OK;
+  if (f->NS != 1 || !f->features_only) return AVR_ERR_UNSUPPORTED;
+  if (f->C != 128 && f->C != 256 && f->C != 512) return AVR_ERR_UNSUPPORTED;
+  if (f->H < 1 || f->W < 1 || !f->poses || !f->focal || !f->c || !f->latent || !aligned16(f->latent)) return AVR_ERR_BAD_ARG;
+  if ((m->R + m->rays_per_obj - 1) / m->rays_per_obj > f->NV) return AVR_ERR_BAD_ARG;
+  if (!m->ros || !m->rds || !m->w_ih || !m->w_hh || !m->b_ih || !m->b_hh || !m->w_out || !m->b_out || !m->world)
+    return AVR_ERR_BAD_ARG;
+  if (!aligned16(m->w_ih)) return AVR_ERR_BAD_ARG;
+  const int saved = (m->feats ? 1 : 0) + (m->gates ? 1 : 0) + (m->cells ? 1 : 0) + (m->hidden ? 1 : 0);
+  if (backward) {
+    if (saved != 4 || !m->g_world || !m->d_gates || !m->d_dist) return AVR_ERR_BAD_ARG;
+    if (f->d_latent && !aligned16(f->d_latent)) return AVR_ERR_BAD_ARG;
+  } else {
+    if (!m->init_dist || (saved != 0 && saved != 4)) return AVR_ERR_BAD_ARG;
+    if (m->feats && !aligned16(m->feats)) return AVR_ERR_BAD_ARG;
+  }
+  return 1;
+}
+
+int avr_lstm_march_fwd(const avr_field_inputs* field, const avr_lstm_march* march, avr_stream_t stream) {
+  const int rc = check_march(field, march, false);
+  if (rc <= 0) return rc;
+  return launch_lstm_march(*field, *march, false, as_stream(stream));
+}
+
+int avr_lstm_march_bwd(const avr_field_inputs* field, const avr_lstm_march* march, avr_stream_t stream) {
+  const int rc = check_march(field, march, true);
+  if (rc <= 0) return rc;
+  return launch_lstm_march(*field, *march, true, as_stream(stream));
+}
+
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
 }  // extern "C"

@@ -128,10 +128,11 @@ AVR_FI float rot_row(const float* R, int i, float x, float y, float z) {
   return fi_add(fi_add(fi_mul(R[4 * i], x), fi_mul(R[4 * i + 1], y)), fi_mul(R[4 * i + 2], z));
 }
 
-AVR_FI FieldPoint field_point(const FieldInputsArgs& a, const FieldCursor& cur, const FieldView& w) {
+// The point (x, y, z) with view direction (dx, dy, dz) seen from view `w` (the LSTM march,
+// lstm_march.cu, calls this with points it holds in registers).
+AVR_FI FieldPoint field_point_xyz(const FieldInputsArgs& a, const FieldView& w, float x, float y, float z, float dx, float dy,
+                                  float dz) {
   FieldPoint p;
-  const float* q = a.xyz + (cur.obj * a.B + cur.b) * 3;
-  const float x = q[0], y = q[1], z = q[2];
   const float r0 = rot_row(w.R, 0, x, y, z), r1 = rot_row(w.R, 1, x, y, z), r2 = rot_row(w.R, 2, x, y, z);
   p.cam0 = fi_add(r0, w.R[3]);
   p.cam1 = fi_add(r1, w.R[7]);
@@ -141,8 +142,6 @@ AVR_FI FieldPoint field_point(const FieldInputsArgs& a, const FieldCursor& cur, 
   p.enc2 = a.normalize_z ? r2 : p.cam2;
   p.vrot0 = p.vrot1 = p.vrot2 = 0.f;
   if (a.use_viewdirs && !a.features_only) {
-    const float* d = a.viewdirs + (cur.obj * a.B + cur.b) * 3;
-    const float dx = d[0], dy = d[1], dz = d[2];
     p.vrot0 = rot_row(w.R, 0, dx, dy, dz);
     p.vrot1 = rot_row(w.R, 1, dx, dy, dz);
     p.vrot2 = rot_row(w.R, 2, dx, dy, dz);
@@ -167,6 +166,18 @@ AVR_FI FieldPoint field_point(const FieldInputsArgs& a, const FieldCursor& cur, 
   p.sw = fi_mul(wy, ex);
   p.se = fi_mul(wy, wx);
   return p;
+}
+
+AVR_FI FieldPoint field_point(const FieldInputsArgs& a, const FieldCursor& cur, const FieldView& w) {
+  const float* q = a.xyz + (cur.obj * a.B + cur.b) * 3;
+  float dx = 0.f, dy = 0.f, dz = 0.f;
+  if (a.use_viewdirs && !a.features_only) {
+    const float* d = a.viewdirs + (cur.obj * a.B + cur.b) * 3;
+    dx = d[0];
+    dy = d[1];
+    dz = d[2];
+  }
+  return field_point_xyz(a, w, q[0], q[1], q[2], dx, dy, dz);
 }
 
 AVR_FI float pick3(float v0, float v1, float v2, int d) { return d == 0 ? v0 : (d == 1 ? v1 : v2); }

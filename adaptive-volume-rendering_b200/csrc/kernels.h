@@ -105,6 +105,8 @@ int launch_depth_from_world(const float* ros, const float* rds, const float* dis
 using FieldInputsArgs = ::avr_field_inputs;
 int launch_field_inputs_fwd(const FieldInputsArgs& a, cudaStream_t stream);
 int launch_field_inputs_bwd(const FieldInputsArgs& a, int64_t SB, cudaStream_t stream);
+// lstm_march.cu — the adaptive renderer's LSTM ray march (renderers.py:411-435), SURVEY 8(f) row 4
+int launch_lstm_march(const FieldInputsArgs& f, const ::avr_lstm_march& m, bool backward, cudaStream_t stream);
 int launch_sort_rays_bwd(const float* g_out, const int32_t* perm, int64_t R, int K, float* d_in, cudaStream_t stream);
 int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t* perm, cudaStream_t stream);
 

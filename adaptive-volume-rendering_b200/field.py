@@ -192,18 +192,24 @@ def _check_supported(net) -> None:
         raise AvrError("fuse_field_inputs: configuration not implemented by the kernels (" + "; ".join(problems) + ")")
 
 
+def field_state(net):
+    """(launch constants, channels-last feature map) of a fused radiance field, refreshed when
+    ``encode`` has produced a new feature map.  Shared by the fused forward and the LSTM march."""
+    latent = net.encoder.latent
+    st = net._avr_field_state
+    if st.get("latent") is not latent:          # encode() ran: new feature map, new camera state
+        st["latent"] = latent
+        st["cfg"] = _config_of(net)
+        src = latent.detach() if net.stop_encoder_grad else latent
+        st["nhwc"] = src.permute(0, 2, 3, 1).contiguous()
+    return st["cfg"], st["nhwc"]
+
+
 def _fused_forward(self, xyz, coarse=True, viewdirs=None, far=False, return_features=False):
     """``NewPixelNeRFNet.forward`` (models.py:739-866) with lines 754-826 done by ``field_inputs``."""
     sb, b, _ = xyz.shape
-    latent = self.encoder.latent
-    st = self._avr_field_state
-    if st.get("latent") is not latent:          # encode() ran: new feature map, new camera state
-        st["latent"] = latent
-        st["cfg"] = _config_of(self)
-        src = latent.detach() if self.stop_encoder_grad else latent
-        st["nhwc"] = src.permute(0, 2, 3, 1).contiguous()
-    cfg = st["cfg"]
-    mlp_input = field_inputs(xyz, viewdirs, st["nhwc"], self.poses, self.focal, self.c, cfg, features_only=return_features)
+    cfg, nhwc = field_state(self)
+    mlp_input = field_inputs(xyz, viewdirs, nhwc, self.poses, self.focal, self.c, cfg, features_only=return_features)
     if return_features:
         return mlp_input                        # (SB*NS*B, latent), models.py:828-829
     mlp = self.mlp_coarse if (coarse or self.mlp_fine is None) else self.mlp_fine

@@ -198,8 +198,9 @@ def _forget_gate_init(cell: nn.LSTMCell):
 
 class AdaptiveVolumeRenderer(nn.Module):
     """LSTM ray-march to a surface estimate d, then a thin stratified slab [d-eps, d+eps]
-    composited with the fused kernels.  The march (renderers.py:411-435) is out of scope
-    and stays stock torch; the tail (:489-509) is the hot path: coarse sampling with
+    composited with the fused kernels.  The march (renderers.py:411-435)
+    is one persistent kernel when the radiance field allows it (``march``), the reference's loop
+    otherwise; the tail (:489-509) is the hot path: coarse sampling with
     per-ray bounds that carry grad, a gradient-routing sort, and compositing with d_z."""
 
     def __init__(self, num_feature_channels, raymarch_steps, epsilon, n_coarse, white_back):
@@ -215,6 +216,7 @@ class AdaptiveVolumeRenderer(nn.Module):
         _forget_gate_init(self.lstm)
         self.out_layer = nn.Linear(hidden_size, 1)
         self.counter = 0
+        self.fused_march = True      # False: always the reference's torch loop (A/B measurements)
 
     def forward(self, cam2world, intrinsics, xy_pix, phi, debug=False,
                 draws: Optional[Sequence[torch.Tensor]] = None):
@@ -229,15 +231,7 @@ class AdaptiveVolumeRenderer(nn.Module):
             u = None
         else:
             init, u = draws
-        world = ros + rds * init
-        state = None
-        for _ in range(self.steps):                                                     # :421-435
-            v = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), return_features=True)
-            state = self.lstm(v.reshape(-1, self.n_feature_channels), state)
-            if state[0].requires_grad:
-                state[0].register_hook(lambda x: x.clamp(min=-10, max=10))
-            signed_distance = self.out_layer(state[0]).view(sb, num_rays, 1)
-            world = world + rds * signed_distance
+        world = self.march(ros, rds, init, phi)                                         # :415-435
 
         out_c = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), coarse=True, return_features=False)
         rgb_coarse = out_c[..., :3].reshape(sb, num_rays, 3)                            # :485
@@ -262,6 +256,26 @@ class AdaptiveVolumeRenderer(nn.Module):
             print(f" color is {rgb[0][64][0]}")
             print(f" depth is {depth[0][64]}")
         return rgb_coarse, rgb, depth_coarse, depth
+
+    def march(self, ros, rds, init, phi):
+        """The LSTM ray march (renderers.py:415-435): one persistent kernel when ``phi``'s feature
+        fetch is the front-end kernels' (``fuse_field_inputs``, one source view per object);
+        otherwise — an arbitrary ``phi`` callable — the reference's loop around ``phi``."""
+        from . import march as _march
+
+        sb, num_rays, _ = ros.shape
+        if self.fused_march and _march.march_supported(phi, self.lstm, self.out_layer):
+            return _march.lstm_march(ros, rds, init, phi, self.lstm, self.out_layer, self.steps)
+        world = ros + rds * init
+        state = None
+        for _ in range(self.steps):
+            v = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), return_features=True)
+            state = self.lstm(v.reshape(-1, self.n_feature_channels), state)
+            if state[0].requires_grad:
+                state[0].register_hook(lambda x: x.clamp(min=-10, max=10))
+            signed_distance = self.out_layer(state[0]).view(sb, num_rays, 1)
+            world = world + rds * signed_distance
+        return world
 
     @classmethod
     def from_conf(cls, conf, white_back=False):

@@ -342,6 +342,57 @@ AVR_API int avr_field_inputs_fwd(const avr_field_inputs* desc, avr_stream_t stre
  * view directions through the projection, the encoding and the rigid transform). */
 AVR_API int avr_field_inputs_bwd(const avr_field_inputs* desc, avr_stream_t stream);
 
+/* ------------------------------------------ the adaptive renderer's LSTM ray march -- */
+
+/* AdaptiveVolumeRenderer's march loop (renderers.py:411-435; the same loop
+ * is Raymarcher.forward, :313-351) in ONE launch:
+ *     world_0 = ros + rds * init_dist
+ *     repeat `steps` times:  v = phi(world_t, return_features=True)      pixel-aligned encoder features,
+ *                                                                        models.py:757-761, 803-829
+ *                            (h, c) = LSTMCell(v, (h, c))               torch.nn.LSTMCell(C -> 16), gates i,f,g,o
+ *                            world_{t+1} = world_t + rds * Linear(h)     out_layer, 16 -> 1
+ * The feature fetch is described by an avr_field_inputs descriptor with features_only = 1 and NS == 1
+ * (one source view per object — the only case the reference's reshape at :423/:430 admits); its xyz /
+ * viewdirs / out pointers are ignored (the points live in registers), B is ignored.  C in {128, 256, 512}.
+ * All pointers are device pointers.  fp32 FMAs throughout (no tensor cores: the recurrence would amplify
+ * TF32 rounding beyond the 1e-5 bar). */
+typedef struct avr_lstm_march {
+  const float* ros;        /* (R, 3) ray origins                                        utils.py:315-336 */
+  const float* rds;        /* (R, 3) unit ray directions                                                  */
+  const float* init_dist;  /* (R)    the N(0.8, 0.05) draw of renderers.py:413 (made by the caller)       */
+  int64_t R;
+  int64_t rays_per_obj;    /* ray r belongs to object (= source view) r / rays_per_obj                    */
+  int steps;               /* raymarch_steps                                                              */
+  const float* w_ih;       /* (64, C)  lstm.weight_ih                                   renderers.py:371   */
+  const float* w_hh;       /* (64, 16) lstm.weight_hh                                                      */
+  const float* b_ih;       /* (64)     lstm.bias_ih                                                        */
+  const float* b_hh;       /* (64)     lstm.bias_hh                                                        */
+  const float* w_out;      /* (16)     out_layer.weight                                 renderers.py:377   */
+  const float* b_out;      /* (1)      out_layer.bias                                                      */
+  float* world;            /* (steps + 1, R, 3): world[t] = the point step t starts from; world[steps] is
+                              the march's result (forward writes, backward reads)                          */
+  /* saved by forward for backward; all four NULL = inference (nothing but `world` is written)            */
+  float* feats;            /* (steps, R, C)  the fetched features v_t (the weight-gradient GEMM reads them) */
+  float* gates;            /* (steps, R, 64) activated gates i, f, g, o                                     */
+  float* cells;            /* (steps, R, 16) c_t                                                            */
+  float* hidden;           /* (steps, R, 16) h_t                                                            */
+  /* backward only */
+  const float* g_world;    /* (R, 3)  dL / d world[steps]                                                   */
+  float* d_gates;          /* (steps, R, 64) dL / d (gate pre-activations)                                  */
+  float* d_dist;           /* (steps, R)     dL / d (signed distance of step t)                             */
+} avr_lstm_march;
+
+/* Forward march.  AVR_ERR_UNSUPPORTED for NS != 1 or a channel count other than 128 / 256 / 512. */
+AVR_API int avr_lstm_march_fwd(const avr_field_inputs* field, const avr_lstm_march* march, avr_stream_t stream);
+/* Backward through time, including the gradient clamp hook on the hidden state (renderers.py:427-428,
+ * clamp to [-10, 10]).  Writes d_gates and d_dist, adds the feature-map gradient into field->d_latent
+ * (NOT zeroed here; may be NULL) with vector atomics, and follows the gradient through the sample
+ * positions (d features / d point) from step to step.  The parameter gradients are plain GEMMs over
+ * the rows this writes (N = steps * R):  d w_ih = d_gates^T feats,  d w_hh = d_gates^T [0; hidden[:-1]],
+ * d b_ih = d b_hh = sum_N d_gates,  d w_out = d_dist^T hidden,  d b_out = sum_N d_dist  — left to the
+ * caller's BLAS (the Python host side uses torch.matmul). */
+AVR_API int avr_lstm_march_bwd(const avr_field_inputs* field, const avr_lstm_march* march, avr_stream_t stream);
+
 /* ------------------------------------------------ host-buffer (end to end) -- */
 
 /* One forward+backward compositing pass over HOST buffers (pinned for full speed):

@@ -289,3 +289,30 @@ def draw_volume_randoms(sb, r, n_coarse, n_fine, n_fine_depth, generator=None, d
         torch.rand(sb, r, ki, **kw),
         torch.randn(sb, r, n_fine_depth, **kw),
     )
+
+
+# --------------------------------------------------------------------------
+# the adaptive renderer's LSTM ray march.  renderers.py:411-435 (the same loop
+# is Raymarcher.forward, :313-351).
+# --------------------------------------------------------------------------
+def lstm_march(ros, rds, init_distance, phi, lstm, out_layer, steps: int, return_all: bool = False):
+    """``world_coords`` of the march: start at ``ros + rds * init_distance`` (:415), then ``steps``
+    times: features at the current point (``phi(..., return_features=True)``, :423), one
+    ``LSTMCell`` step (:425), the gradient clamp hook on the hidden state (:427-428), a signed
+    distance from ``out_layer`` (:430), advance along the ray (:432).
+
+    ros, rds (SB, R, 3); init_distance (SB, R, 1) — the reference draws it with
+    ``torch.zeros(...).normal_(0.8, 5e-2)`` on the CPU generator (:413); here it is an argument.
+    Returns world_coords[-1] (SB, R, 3), or the whole list with ``return_all``."""
+    sb, num_rays, _ = ros.shape
+    world = [ros + rds * init_distance]
+    states = [None]
+    for _ in range(steps):
+        v = phi(world[-1].reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), return_features=True)
+        state = lstm(v.reshape(-1, lstm.input_size), states[-1])
+        if state[0].requires_grad:
+            state[0].register_hook(lambda x: x.clamp(min=-10, max=10))
+        signed_distance = out_layer(state[0]).view(sb, num_rays, 1)
+        world.append(world[-1] + rds * signed_distance)
+        states.append(state)
+    return world if return_all else world[-1]

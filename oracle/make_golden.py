@@ -235,6 +235,44 @@ def case_adaptive_renderer(ref):
          **{f"ref_phi_grad_{i}": p.grad.clone() for i, p in enumerate(phi.parameters())})
 
 
+def case_adaptive_march(ref):
+    """the reference's AdaptiveVolumeRenderer (march loop :411-435 and
+    tail :489-509) around a radiance field that HAS a feature map — tests/field_stub.py's StubNet,
+    whose stock forward is oracle/field_oracle.py (pinned bit for bit to NewPixelNeRFNet.forward) —
+    so that the fused march kernel can be held to numbers the reference's renderer produced:
+    outputs, and gradients of the LSTM head, of the encoder's parameters (through the feature map,
+    i.e. d_latent) and of the MLPs (through the sample positions)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    from field_stub import StubNet
+    sb, r, steps = 2, 40, 4
+    cam2world, intrinsics, x_pix = camera_setup(sb, r, seed=13)
+    torch.manual_seed(14)
+    phi = StubNet()
+    g = torch.Generator().manual_seed(15)
+    images = torch.rand(sb, 1, 3, 20, 16, generator=g) * 2 - 1
+    src_pose = cam2world[:, :1].clone()                                   # the source view is the target view
+    phi.encode(images, src_pose, 22.0)
+    torch.manual_seed(16)
+    ren = ref.AdaptiveVolumeRenderer(128, raymarch_steps=steps, epsilon=0.15, n_coarse=20, white_back=True)
+    with torch.no_grad():                                                 # make the march move (default init barely does)
+        ren.out_layer.weight.mul_(3.0)
+    state = {k: v.clone() for k, v in ren.state_dict().items()}
+    torch.manual_seed(51)
+    rc, rgb, dc, depth = ren(cam2world, intrinsics, x_pix, phi)
+    loss = ((rgb - 0.3) ** 2).mean() + 0.1 * depth.mean() + ((rc - 0.2) ** 2).mean() + 0.05 * dc.mean()
+    loss.backward()
+    torch.manual_seed(51)
+    init = torch.zeros((sb, r, 1)).normal_(mean=0.8, std=5e-2)            # renderers.py:413
+    u = torch.rand(sb, r, 20)                                             # renderers.py:14 via :492
+    save("adaptive_march", cam2world=cam2world, intrinsics=intrinsics, x_pix=x_pix, images=images, src_pose=src_pose,
+         focal=22.0, init_distance=init, u_coarse=u, steps=steps,
+         ref_rgb_coarse=rc, ref_rgb=rgb, ref_depth_coarse=dc, ref_depth=depth, ref_loss=loss.detach(),
+         **{"state_" + k.replace(".", "__"): v for k, v in state.items()},
+         **{"phi_" + k.replace(".", "__"): v.clone() for k, v in phi.state_dict().items()},
+         **{"ref_grad_" + k.replace(".", "__"): p.grad.clone() for k, p in ren.named_parameters()},
+         **{"ref_phi_grad_" + k.replace(".", "__"): p.grad.clone() for k, p in phi.named_parameters()})
+
+
 def case_geometry(ref):
     """utils.get_world_rays / depth_from_world and the point generation of renderers.py:171-175,
     run by the reference's own utils module (star-imported into renderers, renderers.py:1)."""
@@ -442,6 +480,7 @@ def main():
     case_fine(ref)
     case_volume_renderer(ref)
     case_adaptive_renderer(ref)
+    case_adaptive_march(ref)
     case_geometry(ref)
     case_pixelnerf_replay(ref)
     case_field_inputs(ref)

@@ -132,3 +132,35 @@ def test_field_front_end_bit_exact_and_config(ref):
     net.use_global_encoder = True
     with pytest.raises(field.AvrError):
         field.fuse_field_inputs(net)
+
+
+def test_lstm_march_bit_exact(ref):
+    """oracle.lstm_march against the reference's own loop: Raymarcher.forward (renderers.py:313-351)
+    is the loop of AdaptiveVolumeRenderer (:411-435) followed by phi at the last point and
+    depth_from_world, so its outputs and its gradients pin the march forward and backward."""
+    from fields import TinyFeatureField
+    sb, r, ch, steps = 2, 30, 32, 4
+    cam2world, intrinsics, x_pix = camera_setup(sb, r, seed=8)
+    phi = TinyFeatureField(ch, seed=9)
+    torch.manual_seed(21)
+    rm = ref.Raymarcher(ch, steps)
+    torch.manual_seed(33)
+    rgb, _, depth, _ = rm(cam2world, intrinsics, x_pix, phi)
+    (rgb.sum() * 30 + depth.sum()).backward()
+    want = {k: p.grad.clone() for k, p in rm.named_parameters()}
+    want_phi = [p.grad.clone() for p in phi.parameters()]
+    for p in list(rm.parameters()) + list(phi.parameters()):
+        p.grad = None
+    torch.manual_seed(33)
+    init = torch.zeros((sb, r, 1)).normal_(mean=0.8, std=5e-2)          # renderers.py:320
+    ros, rds = O.world_rays(x_pix, intrinsics, cam2world)
+    world = O.lstm_march(ros, rds, init, phi, rm.lstm, rm.out_layer, steps)
+    out = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), coarse=True, return_features=False)
+    got_rgb = out[..., :3].reshape(sb, r, 3)
+    got_depth = O.camera_depth(world, cam2world).reshape(sb, r, -1)
+    assert torch.equal(got_rgb, rgb) and torch.equal(got_depth, depth)
+    (got_rgb.sum() * 30 + got_depth.sum()).backward()
+    for k, p in rm.named_parameters():
+        assert torch.equal(p.grad, want[k]), k
+    for p, w in zip(phi.parameters(), want_phi):
+        assert torch.equal(p.grad, w)
