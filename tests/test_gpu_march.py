@@ -41,6 +41,7 @@ def test_march_matches_oracle(sb, r, steps, g_scale, dev):
     phi = StubNet()
     cam2world, images, ros, rds, init = _scene(sb, r, seed=20 + steps)
     lstm, out_layer = _head(128, seed=4)
+    phi_d = copy.deepcopy(phi).to(dev)            # before encode(): the feature map is a non-leaf
     phi.encode(images, cam2world[:, :1], 22.0)
     g_out = torch.randn(sb, r, 3, generator=torch.Generator().manual_seed(5)) * g_scale
     # oracle: the reference's loop on the CPU
@@ -48,10 +49,28 @@ def test_march_matches_oracle(sb, r, steps, g_scale, dev):
     (world * g_out).sum().backward()
     want = {k: p.grad.clone() for k, p in list(lstm.named_parameters()) + list(out_layer.named_parameters())}
     want_conv = phi.encoder.conv.weight.grad.clone()
-
-    phi_d = copy.deepcopy(phi).to(dev)
-    for p in phi_d.parameters():
+    # the march feeds its own output back `steps` times: rounding differences grow from step to step
+    # (the reference's fp32 run itself drifts from an fp64 run of the same code).  Yardstick, as for
+    # the other ill-conditioned quantities of this suite: the same loop in fp64.
+    phi64, lstm64, out64 = copy.deepcopy(phi_d).cpu().double(), copy.deepcopy(lstm).double(), copy.deepcopy(out_layer).double()
+    for p in list(phi64.parameters()) + list(lstm64.parameters()) + list(out64.parameters()):
         p.grad = None
+    phi64.encode(images.double(), cam2world[:, :1].double(), 22.0)
+    world64 = O.lstm_march(ros.double(), rds.double(), init.double(), phi64, lstm64, out64, steps)
+    (world64 * g_out.double()).sum().backward()
+    want64 = {k: p.grad.clone() for k, p in list(lstm64.named_parameters()) + list(out64.named_parameters())}
+    want64_conv = phi64.encoder.conv.weight.grad.clone()
+
+    def held_to_fp64(got_t, ref32, ref64, what, floor):
+        """within the 1e-5 / 1e-6 bar of the fp32 oracle, or no further from fp64 than 4x the oracle's
+        own fp32 error (plus a floor for quantities the oracle happens to hit exactly)"""
+        got_t, ref32 = got_t.detach().cpu().double(), ref32.double()
+        scale = max(ref64.abs().max().item(), 1e-12)
+        ok = (got_t - ref32).abs() <= 1e-6 * scale + 1e-5 * ref32.abs()
+        own = ((ref32 - ref64).abs().max() / scale).item()
+        err = ((got_t - ref64).abs().max() / scale).item()
+        assert bool(ok.all()) or err <= 4 * own + floor, f"{what}: {err:.3g} of scale from fp64, the fp32 oracle {own:.3g}"
+
     lstm_d, out_d = copy.deepcopy(lstm).to(dev), copy.deepcopy(out_layer).to(dev)
     for p in list(lstm_d.parameters()) + list(out_d.parameters()):
         p.grad = None
@@ -59,13 +78,11 @@ def test_march_matches_oracle(sb, r, steps, g_scale, dev):
     avr_b200.fuse_field_inputs(phi_d)
     assert avr_b200.march.march_supported(phi_d, lstm_d, out_d)
     got = avr_b200.lstm_march(ros.to(dev), rds.to(dev), init.to(dev), phi_d, lstm_d, out_d, steps)
-    assert_close(got, world, rtol=2e-5, atol=2e-6, what="world_coords[-1]")
+    held_to_fp64(got, world, world64, "world_coords[-1]", 2e-6)
     (got * g_out.to(dev)).sum().backward()
     for k, p in list(lstm_d.named_parameters()) + list(out_d.named_parameters()):
-        scale = max(want[k].abs().max().item(), 1e-12)
-        assert_close(p.grad / scale, want[k] / scale, rtol=1e-4, atol=2e-5, what=f"grad {k}")
-    scale = want_conv.abs().max().item()
-    assert_close(phi_d.encoder.conv.weight.grad / scale, want_conv / scale, rtol=1e-4, atol=2e-5, what="grad encoder (d_latent)")
+        held_to_fp64(p.grad, want[k], want64[k], f"grad {k}", 2e-5)
+    held_to_fp64(phi_d.encoder.conv.weight.grad, want_conv, want64_conv, "grad encoder (d_latent)", 2e-5)
     if g_scale > 1:
         # the case exists to exercise the hook: without the clamp the gradients are different
         lstm2, out2 = copy.deepcopy(lstm), copy.deepcopy(out_layer)
@@ -107,6 +124,7 @@ def test_adaptive_renderer_with_fused_march_golden(dev):
         ren.fused_march = fused
         for p in list(ren.parameters()) + list(phi.parameters()):
             p.grad = None
+        phi.encode(g["images"].to(dev), g["src_pose"].to(dev), float(g["focal"]))      # a fresh graph per pass
         rc, rgb, dc, depth = ren(*args, draws=draws)
         assert_close(rc, g["ref_rgb_coarse"], rtol=1e-4, atol=1e-5, what="rgb_coarse")
         assert_close(dc, g["ref_depth_coarse"], rtol=1e-4, atol=1e-5, what="depth_coarse")

@@ -20,12 +20,18 @@ def test_volume_renderer_golden(name, dev):
     rc, rf, d0, d1 = ren(g["cam2world"].to(dev), g["intrinsics"].to(dev), g["x_pix"].to(dev), field, draws=draws)
     assert d0 is d1 and d0.shape == g["ref_depth"].shape
     assert_close(rc, g["ref_rgb_coarse"], rtol=1e-5, atol=2e-6, what="rgb_coarse")
-    # the fine pass sits behind a discontinuous resampling step (a CDF bin can flip on a 1-ulp
-    # difference of the field's output between CPU and GPU), so allow isolated outliers
+    # the fine pass sits behind a discontinuous resampling step: a CDF bin can flip on a 1-ulp
+    # difference of the field's output between CPU and GPU.  The sampler tests measure that rate
+    # at ~1e-5 per new sample (test_gpu_samplers.py), i.e. ~0.03 flipped samples in this fixture:
+    # at most ONE ray may differ, and a flipped sample moves by one coarse bin, (far - near) / Kc,
+    # which bounds what it can do to the depth (and, colours being in [0, 1], to the colour)
+    n_rays = g["ref_depth"].numel()
+    bin_width = 1.0 / kc
     for got, ref, what in ((rf, g["ref_rgb_fine"], "rgb_fine"), (d0, g["ref_depth"], "depth")):
         err = (got.cpu() - ref).abs()
-        assert (err <= 2e-5 + 1e-4 * ref.abs()).float().mean() >= 0.97, what
-        assert err.max() < 2e-2, what
+        bad_rays = (err > 2e-5 + 1e-4 * ref.abs()).reshape(n_rays, -1).any(-1)
+        assert int(bad_rays.sum()) <= 1, f"{what}: {int(bad_rays.sum())}/{n_rays} rays differ"
+        assert err.max() <= bin_width, what
     loss = ((rc - 0.3) ** 2).mean() + ((rf - 0.3) ** 2).mean() + 0.1 * d0.mean()
     assert abs(loss.item() - g["ref_loss"].item()) < 1e-4
     loss.backward()
@@ -123,7 +129,8 @@ def test_volume_renderer_pixelnerf_replay(dev):
     xyz_f = field.asked["fine"][0].reshape(r, 96, 3)
     ref_f = g["ref_xyz_fine"].reshape(r, 96, 3)
     same_ray = ((xyz_f - ref_f).abs() <= 3e-6 + 1e-5 * ref_f.abs()).all(-1).all(-1)
-    assert same_ray.float().mean() >= 0.97, f"only {int(same_ray.sum())}/{r} rays asked the field the reference's fine points"
+    # same budget as above: ~1e-5 flips per new sample x 16 x 512 rays = 0.08 expected; one ray allowed
+    assert int((~same_ray).sum()) <= 1, f"only {int(same_ray.sum())}/{r} rays asked the field the reference's fine points"
     assert d0 is d1 and d0.shape == g["ref_depth"].shape
     assert_close(rf[0][same_ray], g["ref_rgb_fine"][0][same_ray], rtol=1e-5, atol=2e-6, what="rgb_fine")
     assert_close(d0[0][same_ray], g["ref_depth"][0][same_ray], rtol=1e-5, atol=2e-6, what="depth")

@@ -35,7 +35,10 @@ class _Encoder(nn.Module):
 
     def __init__(self, sb, ch, h, w):
         super().__init__()
-        self.latent_param = nn.Parameter(torch.randn(sb, ch, h, w))
+        # smooth features (an encoder's output is; white noise would make the march chaotic and the
+        # fused-vs-loop agreement check meaningless)
+        self.latent_param = nn.Parameter(torch.nn.functional.interpolate(torch.randn(sb, ch, 6, 6), size=(h, w), mode="bicubic",
+                                                                         align_corners=True) * 0.3)
         self.latent = None
         self.register_buffer("latent_scaling", torch.tensor([w / (w - 1) * 2.0, h / (h - 1) * 2.0]))
 
