@@ -48,6 +48,20 @@ class SyntheticField(nn.Module):
         return torch.cat([torch.sigmoid(o[..., :3]), torch.relu(o[..., 3:4] * 20.0)], -1)
 
 
+class WideField(SyntheticField):
+    """Same contract, an MLP of PixelNeRF's width (five 512-wide layers: ~2 MFLOP per point against
+    ResnetFC's ~6, models.py:473-606) — the regime the renderer actually runs in."""
+
+    def __init__(self, hidden=512, layers=4):
+        super().__init__(hidden)
+        self.body = nn.Sequential(*[m for _ in range(layers) for m in (nn.Linear(hidden, hidden), nn.ReLU())])
+
+    def forward(self, xyz, viewdirs=None, coarse=True, return_features=False):
+        h = self.body(torch.sin(self.l1(torch.cat([xyz * 3.0, viewdirs], -1))))
+        o = self.l2(h)
+        return torch.cat([torch.sigmoid(o[..., :3]), torch.relu(o[..., 3:4] * 20.0)], -1)
+
+
 def camera(sb, r, dev):
     import math
     side = int(round(math.sqrt(r)))
@@ -144,8 +158,33 @@ def run(dev, iters=20, sizes=((1, 16384, "128x128 frame, SB=1"), (4, 512, "train
             rec["dropin_cuda_graph"] = {"error": f"{type(exc).__name__}: {exc}"}
         e, ref, fo = rec["dropin_eager"], rec["reference_eager_gpu"], rec["field_only"]
         rec["speedup_vs_reference_wall"] = round(ref["wall_ms"] / e["wall_ms"], 2)
-        rec["renderer_share_of_step"] = round(max(e["wall_ms"] - fo["wall_ms"], 0.0) / e["wall_ms"], 3)
+        # what the renderer itself costs (kernels + ctypes + torch.empty + Python autograd), per step
+        rec["renderer_ms"] = round(max(e["wall_ms"] - fo["wall_ms"], 0.0), 4)
+        rec["reference_renderer_ms"] = round(max(ref["wall_ms"] - fo["wall_ms"], 0.0), 4)
+        rec["renderer_share_of_step"] = round(rec["renderer_ms"] / e["wall_ms"], 3)
         rec["rays_per_s_wall"] = sb * r / (e["wall_ms"] * 1e-3)
+        if sb * r <= 4096:
+            # the same step around an MLP of PixelNeRF's width: the share of the boundary in a real step
+            wide = WideField().to(dev)
+            wparams = list(wide.parameters())
+
+            def wide_step(render):
+                for p in wparams:
+                    p.grad = None
+                if render:
+                    loss_of(renderer(c2w, intr, x_pix, wide)).backward()
+                else:
+                    tot = 0.0
+                    for k in (kc, kc + kf):
+                        pts = torch.empty(sb, r * k, 3, device=dev).uniform_(-1, 1)
+                        tot = tot + wide(pts, viewdirs=pts, coarse=True).mean()
+                    tot.backward()
+
+            a = _time(lambda: wide_step(True), max(iters // 2, 3), dev, warm=2)
+            b = _time(lambda: wide_step(False), max(iters // 2, 3), dev, warm=2)
+            rec["with_512_wide_mlp"] = {"dropin_eager": a, "field_only": b,
+                                        "renderer_share_of_step": round(max(a["wall_ms"] - b["wall_ms"], 0.0) / a["wall_ms"], 4)}
+            del wide
         out[label] = rec
     return out
 
