@@ -56,7 +56,11 @@ PROTOTYPES = {
     "avr_ray_points_fwd_packed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P]),
     "avr_ray_points_bwd_packed": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "avr_coarse_sample_points_fwd": (c_int, [_P, _P, c_int, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P]),
-    "avr_world_rays": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P]),
+    "avr_world_rays": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P]),
+    "avr_rays_coarse_sample_points_fwd": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int, _P, c_int64, c_int, _P, _P, _P, _P, _P,
+                                                  _P, _P]),
+    "avr_composite_fwd_camera": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P, _P]),
+    "avr_composite_bwd_camera": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
     "avr_depth_from_world": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P]),
     "avr_field_inputs_fwd": (c_int, [_P, _P]),
     "avr_field_inputs_bwd": (c_int, [_P, _P]),

@@ -156,6 +156,11 @@ int avr_sort_rays_bwd(const float* g_out, const int32_t* perm, int64_t R, int K,
 
 int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int white_back, float infinity,
                       float* w, float* rgb, float* depth, avr_stream_t stream) {
+  return avr_composite_fwd_camera(rgbs, z, nullptr, R, K, white_back, infinity, w, rgb, depth, stream);
+}
+
+int avr_composite_fwd_camera(const float* rgbs, const float* z, const float* depth_affine, int64_t R, int K,
+                             int white_back, float infinity, float* w, float* rgb, float* depth, avr_stream_t stream) {
   if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
   if (R == 0) return AVR_OK;
   if (!rgbs || !z || !rgb || !depth || !aligned16(rgbs)) return AVR_ERR_BAD_ARG;
@@ -163,7 +168,8 @@ int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int w
   SpanPlan plan;
   int64_t done = 0;
   if (!g_force_generic.load() && span_plan(R, K, rgbs, z, &plan) && (w == nullptr || aligned16(w))) {
-    int rc = launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, st);
+    int rc = launch_composite_fwd_span(plan, rgbs, z, K, white_back, infinity, w, rgb, depth, st, nullptr, 0, 0, false,
+                                       nullptr, depth_affine);
     if (rc != AVR_OK) return rc;
     count_dispatch(AVR_DISPATCH_FWD_SPAN);
     done = plan.main_rays;
@@ -172,7 +178,8 @@ int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int K, int w
     count_dispatch(g_force_generic.load() ? AVR_DISPATCH_FWD_GENERIC : AVR_DISPATCH_FWD_WRAY);
     auto rest = g_force_generic.load() ? launch_composite_fwd_generic : launch_composite_fwd_wray;
     return rest(rgbs + done * K * 4, z + done * K, nullptr, R - done, K, white_back, infinity,
-                w ? w + done * K : nullptr, rgb + done * 3, depth + done, st);
+                w ? w + done * K : nullptr, rgb + done * 3, depth + done, st,
+                depth_affine ? depth_affine + done * 2 : nullptr);
   }
   return AVR_OK;
 }
@@ -253,6 +260,12 @@ int avr_gather_push_rows(void* const* peer_gathered, int n_peers, int self, int6
 int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, const float* g_depth,
                       const float* g_w, int64_t R, int K, int white_back, float infinity, float* d_rgbs,
                       float* d_z, avr_stream_t stream) {
+  return avr_composite_bwd_camera(rgbs, z, nullptr, g_rgb, g_depth, g_w, R, K, white_back, infinity, d_rgbs, d_z, stream);
+}
+
+int avr_composite_bwd_camera(const float* rgbs, const float* z, const float* depth_affine, const float* g_rgb,
+                             const float* g_depth, const float* g_w, int64_t R, int K, int white_back, float infinity,
+                             float* d_rgbs, float* d_z, avr_stream_t stream) {
   if (R < 0 || K < 1) return AVR_ERR_BAD_ARG;
   if (R == 0) return AVR_OK;
   if (!rgbs || !z || !d_rgbs || !aligned16(rgbs) || !aligned16(d_rgbs)) return AVR_ERR_BAD_ARG;
@@ -264,7 +277,7 @@ int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, con
   // aligned.  g_w requests and the remaining shapes take the warp-per-ray kernel.
   if (!g_force_generic.load() && !g_w && span_plan(R, K, rgbs, z, &plan) &&
       (!d_z || (K > plan.L && aligned16(d_z)))) {
-    int rc = launch_composite_bwd_span(plan, rgbs, z, g_rgb, g_depth, K, white_back, infinity, d_rgbs, d_z, st);
+    int rc = launch_composite_bwd_span(plan, rgbs, z, g_rgb, g_depth, K, white_back, infinity, d_rgbs, d_z, st, depth_affine);
     if (rc != AVR_OK) return rc;
     count_dispatch(AVR_DISPATCH_BWD_SPAN);
     done = plan.main_rays;
@@ -274,7 +287,8 @@ int avr_composite_bwd(const float* rgbs, const float* z, const float* g_rgb, con
     auto rest = g_force_generic.load() ? launch_composite_bwd_generic : launch_composite_bwd_wray;
     return rest(rgbs + done * K * 4, z + done * K, nullptr, g_rgb ? g_rgb + done * 3 : nullptr,
                 g_depth ? g_depth + done : nullptr, g_w ? g_w + done * K : nullptr, R - done, K, white_back,
-                infinity, d_rgbs + done * K * 4, d_z ? d_z + done * K : nullptr, st);
+                infinity, d_rgbs + done * K * 4, d_z ? d_z + done * K : nullptr, st,
+                depth_affine ? depth_affine + done * 2 : nullptr);
   }
   return AVR_OK;
 }
@@ -293,7 +307,7 @@ int avr_composite_fwd_packed(const float* rgbs, const float* z, const int64_t* o
   }
   count_dispatch(g_force_generic.load() ? AVR_DISPATCH_FWD_GENERIC : AVR_DISPATCH_FWD_WRAY);
   auto fn = g_force_generic.load() ? launch_composite_fwd_generic : launch_composite_fwd_wray;
-  return fn(rgbs, z, offsets, R, 0, white_back, infinity, w, rgb, depth, as_stream(stream));
+  return fn(rgbs, z, offsets, R, 0, white_back, infinity, w, rgb, depth, as_stream(stream), nullptr);
 }
 
 int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* offsets, const float* g_rgb,
@@ -309,7 +323,7 @@ int avr_composite_bwd_packed(const float* rgbs, const float* z, const int64_t* o
   }
   count_dispatch(g_force_generic.load() ? AVR_DISPATCH_BWD_GENERIC : AVR_DISPATCH_BWD_WRAY);
   auto fn = g_force_generic.load() ? launch_composite_bwd_generic : launch_composite_bwd_wray;
-  return fn(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs, d_z, as_stream(stream));
+  return fn(rgbs, z, offsets, g_rgb, g_depth, g_w, R, 0, white_back, infinity, d_rgbs, d_z, as_stream(stream), nullptr);
 }
 
 /* ------------------------------------------ ray setup / sample points / depth -- */
@@ -355,11 +369,23 @@ int avr_ray_points_bwd_packed(const float* rds, const float* g_pts, const int64_
 }
 
 int avr_world_rays(const float* x_pix, const float* kinv, const float* cam2world, int64_t R, int64_t rays_per_cam,
-                   float* ros, float* rds, avr_stream_t stream) {
+                   float* ros, float* rds, float* depth_affine, avr_stream_t stream) {
   if (R < 0 || rays_per_cam < 1) return AVR_ERR_BAD_ARG;
   if (R == 0) return AVR_OK;
   if (!x_pix || !kinv || !cam2world || !ros || !rds || !aligned16(cam2world)) return AVR_ERR_BAD_ARG;
-  return launch_world_rays(x_pix, kinv, cam2world, R, rays_per_cam, ros, rds, as_stream(stream));
+  return launch_world_rays(x_pix, kinv, cam2world, R, rays_per_cam, ros, rds, depth_affine, as_stream(stream));
+}
+
+int avr_rays_coarse_sample_points_fwd(const float* x_pix, const float* intrinsics, const float* cam2world,
+                                      int64_t rays_per_cam, const float* near, const float* far, int bound_stride,
+                                      const float* u, int64_t R, int K, float* ros, float* rds, float* depth_affine,
+                                      float* z, float* pts, float* viewdirs, avr_stream_t stream) {
+  if (R < 0 || K < 1 || rays_per_cam < 1 || (bound_stride != 0 && bound_stride != 1)) return AVR_ERR_BAD_ARG;
+  if (R == 0) return AVR_OK;
+  if (!x_pix || !intrinsics || !cam2world || !near || !far || !u || !ros || !rds || !z || !pts || !aligned16(cam2world))
+    return AVR_ERR_BAD_ARG;
+  return launch_rays_coarse_points(x_pix, intrinsics, cam2world, rays_per_cam, near, far, bound_stride, u, R, K, ros, rds,
+                                   depth_affine, z, pts, viewdirs, as_stream(stream));
 }
 
 int avr_depth_from_world(const float* ros, const float* rds, const float* dist, const float* cam2world, int64_t R,

@@ -29,6 +29,17 @@ __device__ __forceinline__ Opacity opacity(float sigma, float delta) {
   return o;
 }
 
+// Camera depth folded into the compositing kernels (utils.depth_from_world at renderers.py:274-275,
+// 508-509): the depth of ros + rds * dist seen from the ray's camera is AFFINE in the composited
+// distance, depth = A * dist + B, with (A, B) per ray formed once by the ray-setup kernel
+// (geometry.cu).  `aff` == nullptr: the kernels return / differentiate the distance itself.
+__device__ __forceinline__ float cam_depth(const float* __restrict__ aff, int64_t ray, float dist) {
+  return aff ? fmaf(aff[2 * ray], dist, aff[2 * ray + 1]) : dist;
+}
+__device__ __forceinline__ float cam_depth_grad(const float* __restrict__ aff, int64_t ray, float g) {
+  return aff ? g * aff[2 * ray] : g;
+}
+
 // Streaming (read-once / write-once) global accesses: keep them out of L1.
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 v;

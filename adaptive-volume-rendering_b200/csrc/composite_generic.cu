@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128)
 composite_fwd_ray_kernel(const float4* __restrict__ rgbs, const float* __restrict__ z,
                          const int64_t* __restrict__ offsets, int64_t R, int K, int white_back,
                          float infinity, float* __restrict__ w_out, float* __restrict__ rgb_out,
-                         float* __restrict__ depth_out) {
+                         float* __restrict__ depth_out, const float* __restrict__ depth_affine) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
   RaySpan s = ray_span(offsets, r, K);
@@ -61,7 +61,7 @@ composite_fwd_ray_kernel(const float4* __restrict__ rgbs, const float* __restric
   rgb_out[r * 3 + 0] = ar;
   rgb_out[r * 3 + 1] = ag;
   rgb_out[r * 3 + 2] = ab;
-  depth_out[r] = ad;
+  depth_out[r] = cam_depth(depth_affine, r, ad);
 }
 
 // Backward, two sweeps per ray.  Sweep 1 (front to back) recomputes the transmittance
@@ -75,7 +75,7 @@ composite_bwd_ray_kernel(const float4* __restrict__ rgbs, const float* __restric
                          const int64_t* __restrict__ offsets, const float* __restrict__ g_rgb,
                          const float* __restrict__ g_depth, const float* __restrict__ g_w, int64_t R,
                          int K, int white_back, float infinity, float4* __restrict__ d_rgbs,
-                         float* __restrict__ d_z) {
+                         float* __restrict__ d_z, const float* __restrict__ depth_affine) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
   RaySpan s = ray_span(offsets, r, K);
@@ -97,7 +97,7 @@ composite_bwd_ray_kernel(const float4* __restrict__ rgbs, const float* __restric
   const float gr = g_rgb ? g_rgb[r * 3 + 0] : 0.f;
   const float gg = g_rgb ? g_rgb[r * 3 + 1] : 0.f;
   const float gb = g_rgb ? g_rgb[r * 3 + 2] : 0.f;
-  const float gd = g_depth ? g_depth[r] : 0.f;
+  const float gd = g_depth ? cam_depth_grad(depth_affine, r, g_depth[r]) : 0.f;
   const float gbg = white_back ? (gr + gg + gb) : 0.f;
   float Q = 0.f;
   float ddelta_next = 0.f;  // dL/ddelta_{k+1}
@@ -128,25 +128,25 @@ composite_bwd_ray_kernel(const float4* __restrict__ rgbs, const float* __restric
 
 int launch_composite_fwd_generic(const float* rgbs, const float* z, const int64_t* offsets, int64_t R,
                                  int K, int white_back, float infinity, float* w, float* rgb,
-                                 float* depth, cudaStream_t stream) {
+                                 float* depth, cudaStream_t stream, const float* depth_affine) {
   if (R == 0) return AVR_OK;
   const int threads = 128;
   const int64_t blocks = (R + threads - 1) / threads;
   composite_fwd_ray_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
-      reinterpret_cast<const float4*>(rgbs), z, offsets, R, K, white_back, infinity, w, rgb, depth);
+      reinterpret_cast<const float4*>(rgbs), z, offsets, R, K, white_back, infinity, w, rgb, depth, depth_affine);
   return check_launch();
 }
 
 int launch_composite_bwd_generic(const float* rgbs, const float* z, const int64_t* offsets,
                                  const float* g_rgb, const float* g_depth, const float* g_w, int64_t R,
                                  int K, int white_back, float infinity, float* d_rgbs, float* d_z,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, const float* depth_affine) {
   if (R == 0) return AVR_OK;
   const int threads = 128;
   const int64_t blocks = (R + threads - 1) / threads;
   composite_bwd_ray_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
       reinterpret_cast<const float4*>(rgbs), z, offsets, g_rgb, g_depth, g_w, R, K, white_back, infinity,
-      reinterpret_cast<float4*>(d_rgbs), d_z);
+      reinterpret_cast<float4*>(d_rgbs), d_z, depth_affine);
   return check_launch();
 }
 

@@ -535,8 +535,9 @@ static SpanArgs make_args(const SpanPlan& plan, int K, int white_back, float inf
 int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const float* z, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
                               cudaStream_t stream, void* const* peers, int n_peers, int64_t peer_row0,
-                              bool multicast, const GatherSignal* signal) {
+                              bool multicast, const GatherSignal* signal, const float* depth_affine) {
   SpanArgs a = make_args(plan, K, white_back, infinity);
+  a.depth_affine = depth_affine;
   if (n_peers > kMaxPeers) return AVR_ERR_UNSUPPORTED;
   if (signal && signal->n > 0) {
     if (signal->n > kMaxPeers || n_peers < 1) return AVR_ERR_UNSUPPORTED;
@@ -565,8 +566,9 @@ int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const flo
 
 int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
-                              float* d_z, cudaStream_t stream) {
+                              float* d_z, cudaStream_t stream, const float* depth_affine) {
   SpanArgs a = make_args(plan, K, white_back, infinity);
+  a.depth_affine = depth_affine;
   a.d_z = d_z;
   a.rgbs = rgbs;
   a.z = z;

@@ -38,12 +38,12 @@ __global__ void __launch_bounds__(kWrayWarps * 32)
 composite_fwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restrict__ z,
                           const int64_t* __restrict__ offsets, int64_t R, int K, int white_back,
                           float infinity, float* __restrict__ w_out, float* __restrict__ rgb_out,
-                          float* __restrict__ depth_out) {
+                          float* __restrict__ depth_out, const float* __restrict__ depth_affine) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * kWrayWarps;
   for (int64_t r = blockIdx.x * (int64_t)kWrayWarps + (threadIdx.x >> 5); r < R; r += warps) {
     const WraySpan s = wray_span(offsets, r, K);
-    wray_fwd_ray(rgbs, z, s.begin, s.count, r, white_back, infinity, w_out, rgb_out, depth_out, lane);
+    wray_fwd_ray(rgbs, z, s.begin, s.count, r, white_back, infinity, w_out, rgb_out, depth_out, lane, depth_affine);
   }
 }
 
@@ -52,16 +52,16 @@ composite_bwd_wray_kernel(const float4* __restrict__ rgbs, const float* __restri
                           const int64_t* __restrict__ offsets, const float* __restrict__ g_rgb,
                           const float* __restrict__ g_depth, const float* __restrict__ g_w, int64_t R, int K,
                           int white_back, float infinity, float4* __restrict__ d_rgbs,
-                          float* __restrict__ d_z) {
+                          float* __restrict__ d_z, const float* __restrict__ depth_affine) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * kWrayWarps;
   for (int64_t r = blockIdx.x * (int64_t)kWrayWarps + (threadIdx.x >> 5); r < R; r += warps) {
     const WraySpan s = wray_span(offsets, r, K);
     if (s.count == 0) continue;
     if (s.count <= 32 * kWrayMaxChunks) {
-      wray_bwd_ray<true>(rgbs, z, s.begin, s.count, r, g_rgb, g_depth, g_w, white_back, infinity, d_rgbs, d_z, lane);
+      wray_bwd_ray<true>(rgbs, z, s.begin, s.count, r, g_rgb, g_depth, g_w, white_back, infinity, d_rgbs, d_z, lane, depth_affine);
     } else {
-      wray_bwd_ray<false>(rgbs, z, s.begin, s.count, r, g_rgb, g_depth, g_w, white_back, infinity, d_rgbs, d_z, lane);
+      wray_bwd_ray<false>(rgbs, z, s.begin, s.count, r, g_rgb, g_depth, g_w, white_back, infinity, d_rgbs, d_z, lane, depth_affine);
     }
   }
 }
@@ -75,20 +75,21 @@ static unsigned wray_grid(int64_t R) {
 
 int launch_composite_fwd_wray(const float* rgbs, const float* z, const int64_t* offsets, int64_t R, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, const float* depth_affine) {
   if (R == 0) return AVR_OK;
   composite_fwd_wray_kernel<<<wray_grid(R), kWrayWarps * 32, 0, stream>>>(
-      reinterpret_cast<const float4*>(rgbs), z, offsets, R, K, white_back, infinity, w, rgb, depth);
+      reinterpret_cast<const float4*>(rgbs), z, offsets, R, K, white_back, infinity, w, rgb, depth, depth_affine);
   return check_launch();
 }
 
 int launch_composite_bwd_wray(const float* rgbs, const float* z, const int64_t* offsets, const float* g_rgb,
                               const float* g_depth, const float* g_w, int64_t R, int K, int white_back,
-                              float infinity, float* d_rgbs, float* d_z, cudaStream_t stream) {
+                              float infinity, float* d_rgbs, float* d_z, cudaStream_t stream,
+                              const float* depth_affine) {
   if (R == 0) return AVR_OK;
   composite_bwd_wray_kernel<<<wray_grid(R), kWrayWarps * 32, 0, stream>>>(
       reinterpret_cast<const float4*>(rgbs), z, offsets, g_rgb, g_depth, g_w, R, K, white_back, infinity,
-      reinterpret_cast<float4*>(d_rgbs), d_z);
+      reinterpret_cast<float4*>(d_rgbs), d_z, depth_affine);
   return check_launch();
 }
 

@@ -39,18 +39,91 @@ __device__ __forceinline__ float coarse_z(float near, float span, int j, float k
   return __fadd_rn(base, pow2 ? __fmul_rn(jit, inv_k) : __fdiv_rn(jit, kf));
 }
 
+// utils.get_world_rays for ray r: origin = pose[:3,3]; dir = R_pose * normalize(flip(K^-1 [x,y,1])).
+// intr: [n_cams,3,3] intrinsics, one per object (ray r uses camera r / rays_per_cam); the 3x3 inverse
+// (utils.py:263) is formed from the cofactors — 9 cached loads and ~30 flops.
+__device__ __forceinline__ Ray3 ray_from_pixel(const float* __restrict__ x_pix, const float* __restrict__ intr,
+                                               const float* __restrict__ c2w, int64_t r, int64_t rays_per_cam) {
+  const float* km = intr + (r / rays_per_cam) * 9;
+  const float a00 = km[0], a01 = km[1], a02 = km[2], a10 = km[3], a11 = km[4], a12 = km[5], a20 = km[6],
+              a21 = km[7], a22 = km[8];
+  const float c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+  const float idet = 1.0f / (a00 * c00 + a01 * c01 + a02 * c02);
+  const float ki[9] = {c00 * idet, (a02 * a21 - a01 * a22) * idet, (a01 * a12 - a02 * a11) * idet,
+                       c01 * idet, (a00 * a22 - a02 * a20) * idet, (a02 * a10 - a00 * a12) * idet,
+                       c02 * idet, (a01 * a20 - a00 * a21) * idet, (a00 * a11 - a01 * a10) * idet};
+  const float x = x_pix[r * 2 + 0], y = x_pix[r * 2 + 1];
+  // einsum('ij,kj->ki', K^-1, [x,y,1])  (utils.py:263)
+  float cx = ki[0] * x + ki[1] * y + ki[2];
+  float cy = ki[3] * x + ki[4] * y + ki[5];
+  float cz = ki[6] * x + ki[7] * y + ki[8];
+  // unproject negates x, then scales by z = -1 (utils.py:264-266, :312)
+  cx = -cx;
+  cx *= -1.0f; cy *= -1.0f; cz *= -1.0f;
+  const float nrm = sqrtf(cx * cx + cy * cy + cz * cz);   // torch.norm (utils.py:313)
+  cx = cx / nrm; cy = cy / nrm; cz = cz / nrm;
+  const float4* m = reinterpret_cast<const float4*>(c2w + r * 16);
+  const float4 r0 = m[0], r1 = m[1], r2 = m[2];
+  Ray3 q;
+  q.ox = r0.w; q.oy = r1.w; q.oz = r2.w;                                      // pose[:3, -1]
+  q.dx = r0.x * cx + r0.y * cy + r0.z * cz;                                   // pose @ [dir, 0]
+  q.dy = r1.x * cx + r1.y * cy + r1.z * cz;
+  q.dz = r2.x * cx + r2.y * cy + r2.z * cz;
+  return q;
+}
+
+// Row 2 of pose^-1 as (c02, c12, c22, c32) / det: camera z of a world point p is row . [p, 1]
+// (inverse(M)[2][j] = cofactor(M)[j][2] / det(M); the cofactors delete column 2 of M).
+struct PoseRow2 {
+  float x, y, z, w;
+};
+__device__ __forceinline__ PoseRow2 pose_inverse_row2(const float* __restrict__ c2w, int64_t r) {
+  const float4* mp = reinterpret_cast<const float4*>(c2w + r * 16);
+  const float4 a = mp[0], b = mp[1], c = mp[2], d = mp[3];
+  auto det3 = [](float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) {
+    return a0 * (b1 * c2 - b2 * c1) - a1 * (b0 * c2 - b2 * c0) + a2 * (b0 * c1 - b1 * c0);
+  };
+  const float c02 = det3(b.x, b.y, b.w, c.x, c.y, c.w, d.x, d.y, d.w);    // delete row 0, col 2, sign +
+  const float c12 = -det3(a.x, a.y, a.w, c.x, c.y, c.w, d.x, d.y, d.w);   // row 1, sign -
+  const float c22 = det3(a.x, a.y, a.w, b.x, b.y, b.w, d.x, d.y, d.w);    // row 2, sign +
+  const float c32 = -det3(a.x, a.y, a.w, b.x, b.y, b.w, c.x, c.y, c.w);   // row 3, sign -
+  const float det = a.z * c02 + b.z * c12 + c.z * c22 + d.z * c32;         // expansion along column 2
+  return PoseRow2{c02 / det, c12 / det, c22 / det, c32 / det};
+}
+
+// depth_from_world(o + d * dist) = A * dist + B  (utils.py:358-361 at renderers.py:274-275, 508-509):
+// what the compositing kernels need to return the camera depth themselves (avr_common.cuh cam_depth)
+__device__ __forceinline__ float2 depth_affine_of(const Ray3& q, const PoseRow2& w) {
+  return make_float2(-(w.x * q.dx + w.y * q.dy + w.z * q.dz), -(w.x * q.ox + w.y * q.oy + w.z * q.oz + w.w));
+}
+
 // One thread per 4 consecutive samples (K % 4 == 0 keeps them in one ray): 16 B of z (or u) in,
 // 48 B of points and 48 B of view directions out.  A thread's 48 bytes are contiguous but the
 // warp's stores would interleave at a 48-byte stride (half-filled sectors), so each warp
 // transposes its 1536 bytes through shared memory and writes three fully coalesced 512-byte rows
 // (the 48-byte stride is conflict-free for 16-byte shared-memory accesses).
 // kFromU: `zu` holds the uniforms; z is computed here (and stored) — the fused coarse sampler.
-template <bool kFromU>
+// kSetup: the rays themselves are formed here from pixels and poses (utils.get_world_rays), so the
+// renderer's first launch covers renderers.py:166-175; the thread that owns a ray's first samples
+// also stores its origin / direction (the fine pass and the adaptive tail read them) and the
+// camera-depth coefficients.  Every thread recomputes its ray's setup (~120 flops against the
+// 128 bytes it moves: the kernel stays HBM-bound) instead of sharing it across lanes.
+struct RaySetupArgs {
+  const float* x_pix;
+  const float* intr;
+  const float* c2w;
+  int64_t rays_per_cam;
+  float* ros_out;
+  float* rds_out;
+  float* affine_out;   // nullable
+};
+
+template <bool kFromU, bool kSetup>
 __global__ void __launch_bounds__(256)
 ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ rds, const float* __restrict__ zu,
                        const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
                        int64_t n_vec, int K, float* __restrict__ z_out, float* __restrict__ pts,
-                       float* __restrict__ viewdirs) {
+                       float* __restrict__ viewdirs, const RaySetupArgs rs) {
   __shared__ float4 s_stage[8][96];
   const int lane = threadIdx.x & 31;
   float4* sw = s_stage[threadIdx.x >> 5];
@@ -65,7 +138,21 @@ ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ 
     const int64_t i = (valid ? v : n_vec - 1) * 4;
     const int64_t r = i / K;
     const int j = (int)(i - r * K);
-    const Ray3 q = load_ray3(ros, rds, r);
+    Ray3 q;
+    if (kSetup) {
+      q = ray_from_pixel(rs.x_pix, rs.intr, rs.c2w, r, rs.rays_per_cam);
+      if (valid && j == 0) {
+        rs.ros_out[r * 3 + 0] = q.ox; rs.ros_out[r * 3 + 1] = q.oy; rs.ros_out[r * 3 + 2] = q.oz;
+        rs.rds_out[r * 3 + 0] = q.dx; rs.rds_out[r * 3 + 1] = q.dy; rs.rds_out[r * 3 + 2] = q.dz;
+        if (rs.affine_out) {
+          const float2 ab = depth_affine_of(q, pose_inverse_row2(rs.c2w, r));
+          rs.affine_out[r * 2 + 0] = ab.x;
+          rs.affine_out[r * 2 + 1] = ab.y;
+        }
+      }
+    } else {
+      q = load_ray3(ros, rds, r);
+    }
     float4 z4 = ldg_stream(reinterpret_cast<const float4*>(zu + i));
     if (kFromU) {
       const int64_t b = bound_stride ? r : 0;
@@ -105,19 +192,33 @@ ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ 
 }
 
 // any K / alignment: one thread per sample
-template <bool kFromU>
+template <bool kFromU, bool kSetup>
 __global__ void __launch_bounds__(256)
 ray_points_scalar_kernel(const float* __restrict__ ros, const float* __restrict__ rds, const float* __restrict__ zu,
                          const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
                          int64_t total, int K, float* __restrict__ z_out, float* __restrict__ pts,
-                         float* __restrict__ viewdirs) {
+                         float* __restrict__ viewdirs, const RaySetupArgs rs) {
   const float kf = (float)K;
   const bool pow2 = (K & (K - 1)) == 0;
   const float inv_k = 1.0f / kf;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t r = i / K;
-    const Ray3 q = load_ray3(ros, rds, r);
+    Ray3 q;
+    if (kSetup) {
+      q = ray_from_pixel(rs.x_pix, rs.intr, rs.c2w, r, rs.rays_per_cam);
+      if (i == r * K) {
+        rs.ros_out[r * 3 + 0] = q.ox; rs.ros_out[r * 3 + 1] = q.oy; rs.ros_out[r * 3 + 2] = q.oz;
+        rs.rds_out[r * 3 + 0] = q.dx; rs.rds_out[r * 3 + 1] = q.dy; rs.rds_out[r * 3 + 2] = q.dz;
+        if (rs.affine_out) {
+          const float2 ab = depth_affine_of(q, pose_inverse_row2(rs.c2w, r));
+          rs.affine_out[r * 2 + 0] = ab.x;
+          rs.affine_out[r * 2 + 1] = ab.y;
+        }
+      }
+    } else {
+      q = load_ray3(ros, rds, r);
+    }
     float z = zu[i];
     if (kFromU) {
       const int64_t b = bound_stride ? r : 0;
@@ -171,38 +272,22 @@ ray_points_bwd_kernel(const float* __restrict__ rds, const float* __restrict__ g
   }
 }
 
-// utils.get_world_rays: origin = pose[:3,3]; dir = R_pose * normalize(flip(K^-1 [x,y,1]))
-// intr: [n_cams,3,3] intrinsics, one per object (ray r uses camera r / rays_per_cam); the 3x3
-// inverse (utils.py:263) is formed per thread from the cofactors — 9 cached loads and ~30 flops.
+// utils.get_world_rays as a kernel of its own (the adaptive renderer marches before it samples),
+// optionally with the camera-depth coefficients of every ray.
 __global__ void __launch_bounds__(256)
 world_rays_kernel(const float* __restrict__ x_pix, const float* __restrict__ intr, const float* __restrict__ c2w,
-                  int64_t R, int64_t rays_per_cam, float* __restrict__ ros, float* __restrict__ rds) {
+                  int64_t R, int64_t rays_per_cam, float* __restrict__ ros, float* __restrict__ rds,
+                  float* __restrict__ affine) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += stride) {
-    const float* km = intr + (r / rays_per_cam) * 9;
-    const float a00 = km[0], a01 = km[1], a02 = km[2], a10 = km[3], a11 = km[4], a12 = km[5], a20 = km[6],
-                a21 = km[7], a22 = km[8];
-    const float c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
-    const float idet = 1.0f / (a00 * c00 + a01 * c01 + a02 * c02);
-    const float ki[9] = {c00 * idet, (a02 * a21 - a01 * a22) * idet, (a01 * a12 - a02 * a11) * idet,
-                         c01 * idet, (a00 * a22 - a02 * a20) * idet, (a02 * a10 - a00 * a12) * idet,
-                         c02 * idet, (a01 * a20 - a00 * a21) * idet, (a00 * a11 - a01 * a10) * idet};
-    const float x = x_pix[r * 2 + 0], y = x_pix[r * 2 + 1];
-    // einsum('ij,kj->ki', K^-1, [x,y,1])  (utils.py:263)
-    float cx = ki[0] * x + ki[1] * y + ki[2];
-    float cy = ki[3] * x + ki[4] * y + ki[5];
-    float cz = ki[6] * x + ki[7] * y + ki[8];
-    // unproject negates x, then scales by z = -1 (utils.py:264-266, :312)
-    cx = -cx;
-    cx *= -1.0f; cy *= -1.0f; cz *= -1.0f;
-    const float nrm = sqrtf(cx * cx + cy * cy + cz * cz);   // torch.norm (utils.py:313)
-    cx = cx / nrm; cy = cy / nrm; cz = cz / nrm;
-    const float4* m = reinterpret_cast<const float4*>(c2w + r * 16);
-    const float4 r0 = m[0], r1 = m[1], r2 = m[2];
-    ros[r * 3 + 0] = r0.w; ros[r * 3 + 1] = r1.w; ros[r * 3 + 2] = r2.w;      // pose[:3, -1]
-    rds[r * 3 + 0] = r0.x * cx + r0.y * cy + r0.z * cz;                          // pose @ [dir, 0]
-    rds[r * 3 + 1] = r1.x * cx + r1.y * cy + r1.z * cz;
-    rds[r * 3 + 2] = r2.x * cx + r2.y * cy + r2.z * cz;
+    const Ray3 q = ray_from_pixel(x_pix, intr, c2w, r, rays_per_cam);
+    ros[r * 3 + 0] = q.ox; ros[r * 3 + 1] = q.oy; ros[r * 3 + 2] = q.oz;
+    rds[r * 3 + 0] = q.dx; rds[r * 3 + 1] = q.dy; rds[r * 3 + 2] = q.dz;
+    if (affine) {
+      const float2 ab = depth_affine_of(q, pose_inverse_row2(c2w, r));
+      affine[r * 2 + 0] = ab.x;
+      affine[r * 2 + 1] = ab.y;
+    }
   }
 }
 
@@ -258,21 +343,42 @@ int launch_ray_points(const float* ros, const float* rds, const float* z_or_u, c
   if (total == 0) return AVR_OK;
   const bool vec = (K % 4 == 0) && aligned16(z_or_u) && aligned16(pts) && aligned16(viewdirs) && aligned16(z_out);
   const int max_blocks = num_sms() * 16;
+  const RaySetupArgs none{};
   if (vec) {
     const int64_t n_vec = total / 4;
     if (from_u) {
-      ray_points_vec4_kernel<true><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
-                                                                                  bound_stride, n_vec, K, z_out, pts, viewdirs);
+      ray_points_vec4_kernel<true, false><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
+          ros, rds, z_or_u, near, far, bound_stride, n_vec, K, z_out, pts, viewdirs, none);
     } else {
-      ray_points_vec4_kernel<false><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
-                                                                                   bound_stride, n_vec, K, z_out, pts, viewdirs);
+      ray_points_vec4_kernel<false, false><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
+          ros, rds, z_or_u, near, far, bound_stride, n_vec, K, z_out, pts, viewdirs, none);
     }
   } else if (from_u) {
-    ray_points_scalar_kernel<true><<<grid_1d(total, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
-                                                                                  bound_stride, total, K, z_out, pts, viewdirs);
+    ray_points_scalar_kernel<true, false><<<grid_1d(total, max_blocks), 256, 0, stream>>>(
+        ros, rds, z_or_u, near, far, bound_stride, total, K, z_out, pts, viewdirs, none);
   } else {
-    ray_points_scalar_kernel<false><<<grid_1d(total, max_blocks), 256, 0, stream>>>(ros, rds, z_or_u, near, far,
-                                                                                   bound_stride, total, K, z_out, pts, viewdirs);
+    ray_points_scalar_kernel<false, false><<<grid_1d(total, max_blocks), 256, 0, stream>>>(
+        ros, rds, z_or_u, near, far, bound_stride, total, K, z_out, pts, viewdirs, none);
+  }
+  return check_launch();
+}
+
+int launch_rays_coarse_points(const float* x_pix, const float* intr, const float* c2w, int64_t rays_per_cam,
+                              const float* near, const float* far, int bound_stride, const float* u, int64_t R, int K,
+                              float* ros, float* rds, float* depth_affine, float* z, float* pts, float* viewdirs,
+                              cudaStream_t stream) {
+  const int64_t total = R * (int64_t)K;
+  if (total == 0) return AVR_OK;
+  const bool vec = (K % 4 == 0) && aligned16(u) && aligned16(pts) && aligned16(viewdirs) && aligned16(z);
+  const int max_blocks = num_sms() * 16;
+  const RaySetupArgs rs{x_pix, intr, c2w, rays_per_cam, ros, rds, depth_affine};
+  if (vec) {
+    const int64_t n_vec = total / 4;
+    ray_points_vec4_kernel<true, true><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
+        nullptr, nullptr, u, near, far, bound_stride, n_vec, K, z, pts, viewdirs, rs);
+  } else {
+    ray_points_scalar_kernel<true, true><<<grid_1d(total, max_blocks), 256, 0, stream>>>(
+        nullptr, nullptr, u, near, far, bound_stride, total, K, z, pts, viewdirs, rs);
   }
   return check_launch();
 }
@@ -294,9 +400,10 @@ int launch_ray_points_packed(const float* ros, const float* rds, const float* z,
 }
 
 int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, int64_t R, int64_t rays_per_cam,
-                      float* ros, float* rds, cudaStream_t stream) {
+                      float* ros, float* rds, float* depth_affine, cudaStream_t stream) {
   if (R == 0) return AVR_OK;
-  world_rays_kernel<<<grid_1d(R, num_sms() * 16), 256, 0, stream>>>(x_pix, kinv, c2w, R, rays_per_cam, ros, rds);
+  world_rays_kernel<<<grid_1d(R, num_sms() * 16), 256, 0, stream>>>(x_pix, kinv, c2w, R, rays_per_cam, ros, rds,
+                                                                     depth_affine);
   return check_launch();
 }
 

@@ -20,21 +20,23 @@ int num_sms();                  // SMs of the current device (cached)
 void count_dispatch(int which); // AVR_DISPATCH_* of avr_b200.h
 
 // composite_generic.cu — any shape, dense (offsets == nullptr) or packed
+// depth_affine (nullable, [R,2]): `depth` / `g_depth` are the camera depth A*dist + B (avr_common.cuh)
 int launch_composite_fwd_generic(const float* rgbs, const float* z, const int64_t* offsets, int64_t R,
                                  int K, int white_back, float infinity, float* w, float* rgb,
-                                 float* depth, cudaStream_t stream);
+                                 float* depth, cudaStream_t stream, const float* depth_affine = nullptr);
 int launch_composite_bwd_generic(const float* rgbs, const float* z, const int64_t* offsets,
                                  const float* g_rgb, const float* g_depth, const float* g_w, int64_t R,
                                  int K, int white_back, float infinity, float* d_rgbs, float* d_z,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, const float* depth_affine = nullptr);
 
 // composite_wray.cu — warp per ray, coalesced; any shape, dense (offsets == nullptr) or packed
 int launch_composite_fwd_wray(const float* rgbs, const float* z, const int64_t* offsets, int64_t R, int K,
                               int white_back, float infinity, float* w, float* rgb, float* depth,
-                              cudaStream_t stream);
+                              cudaStream_t stream, const float* depth_affine = nullptr);
 int launch_composite_bwd_wray(const float* rgbs, const float* z, const int64_t* offsets, const float* g_rgb,
                               const float* g_depth, const float* g_w, int64_t R, int K, int white_back,
-                              float infinity, float* d_rgbs, float* d_z, cudaStream_t stream);
+                              float infinity, float* d_rgbs, float* d_z, cudaStream_t stream,
+                              const float* depth_affine = nullptr);
 
 // composite_span.cu — dense, TMA-staged blocked scan.  `span_plan` says whether a
 // shape is eligible and how many leading rays the span kernel covers (the caller
@@ -57,12 +59,13 @@ int launch_composite_fwd_span(const SpanPlan& plan, const float* rgbs, const flo
                               int white_back, float infinity, float* w, float* rgb, float* depth,
                               cudaStream_t stream, void* const* peers = nullptr, int n_peers = 0,
                               int64_t peer_row0 = 0, bool multicast = false,
-                              const GatherSignal* signal = nullptr);
+                              const GatherSignal* signal = nullptr, const float* depth_affine = nullptr);
 // runtime.cu: wait until flags[0..n) >= value (acquire, system scope); bounded spin
 int launch_gather_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* status, cudaStream_t stream);
 int launch_composite_bwd_span(const SpanPlan& plan, const float* rgbs, const float* z, const float* g_rgb,
                               const float* g_depth, int K, int white_back, float infinity, float* d_rgbs,
-                              float* d_z /* nullable; needs K > plan.L */, cudaStream_t stream);
+                              float* d_z /* nullable; needs K > plan.L */, cudaStream_t stream,
+                              const float* depth_affine = nullptr);
 
 // composite_span_packed.cu — packed layout, TMA-staged whole-ray tiles packed on the fly
 bool span_packed_eligible(const void* rgbs, const void* z, const void* w_or_null, const void* d_rgbs_or_null);
@@ -98,7 +101,12 @@ int launch_ray_points_bwd(const float* rds, const float* g_pts, int64_t R, int K
 int launch_ray_points_packed(const float* ros, const float* rds, const float* z, const int64_t* offsets, int64_t R,
                              float* pts, float* viewdirs, const float* g_pts, float* d_z, cudaStream_t stream);
 int launch_world_rays(const float* x_pix, const float* kinv, const float* c2w, int64_t R, int64_t rays_per_cam,
-                      float* ros, float* rds, cudaStream_t stream);
+                      float* ros, float* rds, float* depth_affine, cudaStream_t stream);
+// ray setup + stratified depths + sample points + view directions in one launch
+int launch_rays_coarse_points(const float* x_pix, const float* intr, const float* c2w, int64_t rays_per_cam,
+                              const float* near, const float* far, int bound_stride, const float* u, int64_t R, int K,
+                              float* ros, float* rds, float* depth_affine, float* z, float* pts, float* viewdirs,
+                              cudaStream_t stream);
 int launch_depth_from_world(const float* ros, const float* rds, const float* dist, const float* c2w, int64_t R,
                             float* depth, float* grad_row, cudaStream_t stream);
 // field_inputs.cu — radiance-field front end (models.py:754-826), SURVEY 8(f) row 3

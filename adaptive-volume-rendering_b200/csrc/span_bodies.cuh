@@ -27,6 +27,7 @@ struct SpanArgs {
   const float* g_depth;   // bwd (nullable)
   float* d_rgbs;          // bwd
   float* d_z;             // bwd (nullable): gradient w.r.t. the depths (adaptive renderer)
+  const float* depth_affine;  // nullable [R,2]: `depth` is the camera depth A*dist + B (see cam_depth)
   int64_t n_tiles;
   int K;
   int rays_per_tile;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void store_ray(const SpanArgs& a, int64_t ray, const 
   o3[0] = t.r + bg;
   o3[1] = t.g + bg;
   o3[2] = t.b + bg;
-  a.depth[ray] = t.d;
+  a.depth[ray] = cam_depth(a.depth_affine, ray, t.d);
 }
 
 // rays [lo, hi) were finished (and stored to a.rgb / a.depth) by THIS warp: forward them to every
@@ -210,7 +211,7 @@ __device__ __forceinline__ RayGrad load_ray_grad(const SpanArgs& a, int64_t ray)
     g.g = a.g_rgb[ray * 3 + 1];
     g.b = a.g_rgb[ray * 3 + 2];
   }
-  if (a.g_depth) g.d = a.g_depth[ray];
+  if (a.g_depth) g.d = cam_depth_grad(a.depth_affine, ray, a.g_depth[ray]);
   g.bg = a.white_back ? (g.r + g.g + g.b) : 0.f;
   return g;
 }

@@ -87,7 +87,8 @@ __device__ __forceinline__ void bwd_chunk(const ChunkIn& in, float e, float T, c
 __device__ __forceinline__ void wray_fwd_ray(const float4* __restrict__ rgbs, const float* __restrict__ z,
                                              int64_t begin, int64_t count, int64_t r, int white_back,
                                              float infinity, float* __restrict__ w_out,
-                                             float* __restrict__ rgb_out, float* __restrict__ depth_out, int lane) {
+                                             float* __restrict__ rgb_out, float* __restrict__ depth_out, int lane,
+                                             const float* __restrict__ depth_affine = nullptr) {
   float carry = 1.0f;
   float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, acc = 0.f;
   for (int64_t c0 = 0; c0 < count; c0 += 32) {
@@ -119,7 +120,7 @@ __device__ __forceinline__ void wray_fwd_ray(const float4* __restrict__ rgbs, co
     rgb_out[r * 3 + 0] = ar + bg;
     rgb_out[r * 3 + 1] = ag + bg;
     rgb_out[r * 3 + 2] = ab + bg;
-    depth_out[r] = ad;
+    depth_out[r] = cam_depth(depth_affine, r, ad);
   }
 }
 
@@ -130,13 +131,14 @@ __device__ __forceinline__ void wray_bwd_ray(const float4* __restrict__ rgbs, co
                                              int64_t begin, int64_t count, int64_t r,
                                              const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
                                              const float* __restrict__ g_w, int white_back, float infinity,
-                                             float4* __restrict__ d_rgbs, float* __restrict__ d_z, int lane) {
+                                             float4* __restrict__ d_rgbs, float* __restrict__ d_z, int lane,
+                                             const float* __restrict__ depth_affine = nullptr) {
   float* park = reinterpret_cast<float*>(d_rgbs);
   BwdRay g;
   g.gr = g_rgb ? g_rgb[r * 3 + 0] : 0.f;
   g.gg = g_rgb ? g_rgb[r * 3 + 1] : 0.f;
   g.gb = g_rgb ? g_rgb[r * 3 + 2] : 0.f;
-  g.gd = g_depth ? g_depth[r] : 0.f;
+  g.gd = g_depth ? cam_depth_grad(depth_affine, r, g_depth[r]) : 0.f;
   g.gbg = white_back ? (g.gr + g.gg + g.gb) : 0.f;
   const int n_chunks = (int)((count + 31) >> 5);
 

@@ -169,8 +169,9 @@ class SortRays(torch.autograd.Function):
 
 
 # -------------------------------------------------------------------------- composite
-def composite_fwd_raw(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool, infinity: float, want_w: bool = True):
-    require_cuda(rgbs, z)
+def composite_fwd_raw(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool, infinity: float, want_w: bool = True,
+                      depth_affine: Optional[torch.Tensor] = None):
+    require_cuda(rgbs, z, depth_affine)
     rgbs, z = _f32c(rgbs), _f32c(z)
     k = z.shape[-1]
     r = z.numel() // k
@@ -182,12 +183,22 @@ def composite_fwd_raw(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool, inf
     rgb = torch.empty(*lead, 3, dtype=torch.float32, device=dev)
     depth = torch.empty(*lead, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().avr_composite_fwd(ptr(rgbs), ptr(z), r, k, int(bool(white_back)), float(infinity),
-                                            ptr(w), ptr(rgb), ptr(depth), _stream(z)), "avr_composite_fwd")
+        check(_lib.load().avr_composite_fwd_camera(ptr(rgbs), ptr(z), ptr(_affine(depth_affine, r)), r, k,
+                                                   int(bool(white_back)), float(infinity), ptr(w), ptr(rgb), ptr(depth),
+                                                   _stream(z)), "avr_composite_fwd")
     return rgb, depth, w
 
 
-def composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back: bool, infinity: float, want_dz: bool):
+def _affine(depth_affine, r):
+    if depth_affine is None:
+        return None
+    a = _f32c(depth_affine)
+    if a.numel() != 2 * r:
+        raise _lib.AvrError(f"depth_affine holds {a.numel() // 2} rays, the batch {r}")
+    return a
+
+
+def composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back: bool, infinity: float, want_dz: bool, depth_affine=None):
     rgbs, z = _f32c(rgbs), _f32c(z)
     k = z.shape[-1]
     r = z.numel() // k
@@ -197,9 +208,9 @@ def composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back: bool, infinity: 
     d_rgbs = torch.empty_like(rgbs)
     d_z = torch.empty_like(z) if want_dz else None
     with torch.cuda.device(z.device):
-        check(_lib.load().avr_composite_bwd(ptr(rgbs), ptr(z), ptr(g_rgb), ptr(g_depth), ptr(g_w), r, k,
-                                            int(bool(white_back)), float(infinity), ptr(d_rgbs), ptr(d_z), _stream(z)),
-              "avr_composite_bwd")
+        check(_lib.load().avr_composite_bwd_camera(ptr(rgbs), ptr(z), ptr(_affine(depth_affine, r)), ptr(g_rgb), ptr(g_depth),
+                                                   ptr(g_w), r, k, int(bool(white_back)), float(infinity), ptr(d_rgbs),
+                                                   ptr(d_z), _stream(z)), "avr_composite_bwd")
     return d_rgbs, d_z
 
 
@@ -210,13 +221,13 @@ class Composite(torch.autograd.Function):
     with shape (..., K) (callers add the trailing 1 the reference has)."""
 
     @staticmethod
-    def forward(ctx, rgbs, z, white_back: bool, infinity: float, want_w: bool):
-        rgb, depth, w = composite_fwd_raw(rgbs, z, white_back, infinity, want_w)
+    def forward(ctx, rgbs, z, white_back: bool, infinity: float, want_w: bool, depth_affine=None):
+        rgb, depth, w = composite_fwd_raw(rgbs, z, white_back, infinity, want_w, depth_affine)
         # an output nobody differentiates through must reach backward as None, not as a tensor of
         # zeros: a materialised g_w would push every training step of VolumeRenderer's coarse pass
         # (w_c only feeds the detached sampler, renderers.py:36) off the span kernel (api.cu)
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(rgbs, z)
+        ctx.save_for_backward(rgbs, z, depth_affine)
         ctx.cfg = (bool(white_back), float(infinity))
         if w is None:
             w = rgb.new_empty(0)
@@ -225,22 +236,25 @@ class Composite(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_w):
-        rgbs, z = ctx.saved_tensors
+        rgbs, z, depth_affine = ctx.saved_tensors
         white_back, infinity = ctx.cfg
         if g_w is not None and g_w.numel() == 0:
             g_w = None
         if g_rgb is None and g_depth is None and g_w is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         want_dz = ctx.needs_input_grad[1]
-        d_rgbs, d_z = composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back, infinity, want_dz)
-        return (d_rgbs.view_as(rgbs) if ctx.needs_input_grad[0] else None), d_z, None, None, None
+        d_rgbs, d_z = composite_bwd_raw(rgbs, z, g_rgb, g_depth, g_w, white_back, infinity, want_dz, depth_affine)
+        return (d_rgbs.view_as(rgbs) if ctx.needs_input_grad[0] else None), d_z, None, None, None, None
 
 
 def composite(rgbs: torch.Tensor, z: torch.Tensor, white_back: bool = True, infinity: float = 1.8,
-              want_w: bool = True) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+              want_w: bool = True, depth_affine: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """Differentiable compositing of a (..., K, 4) = (r,g,b,sigma) buffer along z (..., K).
-    Returns rgb (...,3), depth (...), w (...,K) or None."""
-    rgb, depth, w = Composite.apply(rgbs, z, white_back, infinity, want_w)
+    Returns rgb (...,3), depth (...), w (...,K) or None.  With ``depth_affine`` (..., 2) — the
+    per-ray coefficients ``world_rays`` / ``rays_coarse_sample_points`` return — ``depth`` is the
+    camera depth of the composited point (utils.depth_from_world, renderers.py:274-275) instead
+    of the distance along the ray."""
+    rgb, depth, w = Composite.apply(rgbs, z, white_back, infinity, want_w, depth_affine)
     return rgb, depth, (w if want_w else None)
 
 
@@ -462,23 +476,53 @@ def coarse_sample_points(near, far, bound_stride: int, u: torch.Tensor, ros: tor
     return z, pts, vd
 
 
-def world_rays(xy_pix: torch.Tensor, intrinsics: torch.Tensor, cam2world: torch.Tensor):
-    """utils.get_world_rays (utils.py:309-336): xy_pix (SB,R,2), intrinsics (SB,3,3), cam2world
-    (SB,R,4,4) -> origins, unit directions (SB,R,3), all of it (including the 3x3 inverse of
-    utils.py:263) in one kernel.  Non-differentiable (the reference's poses and intrinsics are data)."""
-    require_cuda(xy_pix, intrinsics, cam2world)
-    sb, n = xy_pix.shape[0], xy_pix.shape[1]
+def _camera_inputs(xy_pix, intrinsics, cam2world):
+    sb = xy_pix.shape[0]
     x = _f32c(xy_pix.detach())
     c2w = _f32c(cam2world.detach())
     kinv = _f32c(intrinsics.detach().reshape(-1, 3, 3))
     if kinv.shape[0] != sb:
         kinv = _f32c(kinv.expand(sb, 3, 3))
+    return x, kinv, c2w
+
+
+def rays_coarse_sample_points(xy_pix, intrinsics, cam2world, near, far, bound_stride: int, u: torch.Tensor):
+    """renderers.py:166-175 in one launch: get_world_rays + sample_coarse + sample points + view
+    directions.  Returns ros, rds (SB,R,3), depth_affine (SB,R,2), z (SB,R,K), pts, viewdirs
+    (SB,R,K,3); non-differentiable (poses, intrinsics and VolumeRenderer's bounds are data)."""
+    require_cuda(xy_pix, intrinsics, cam2world, near, far, u)
+    sb, n = xy_pix.shape[0], xy_pix.shape[1]
+    x, kinv, c2w = _camera_inputs(xy_pix, intrinsics, cam2world)
+    u = _f32c(u)
+    k = u.shape[-1]
+    dev = x.device
+    ros = torch.empty(sb, n, 3, dtype=torch.float32, device=dev)
+    rds = torch.empty_like(ros)
+    aff = torch.empty(sb, n, 2, dtype=torch.float32, device=dev)
+    z = torch.empty_like(u)
+    pts = torch.empty(*u.shape, 3, dtype=torch.float32, device=dev)
+    vd = torch.empty_like(pts)
+    with torch.cuda.device(dev):
+        check(_lib.load().avr_rays_coarse_sample_points_fwd(ptr(x), ptr(kinv), ptr(c2w), n, ptr(near), ptr(far), bound_stride,
+                                                            ptr(u), sb * n, k, ptr(ros), ptr(rds), ptr(aff), ptr(z), ptr(pts),
+                                                            ptr(vd), _stream(x)), "avr_rays_coarse_sample_points_fwd")
+    return ros, rds, aff, z, pts, vd
+
+
+def world_rays(xy_pix: torch.Tensor, intrinsics: torch.Tensor, cam2world: torch.Tensor, want_affine: bool = False):
+    """utils.get_world_rays (utils.py:309-336): xy_pix (SB,R,2), intrinsics (SB,3,3), cam2world
+    (SB,R,4,4) -> origins, unit directions (SB,R,3), all of it (including the 3x3 inverse of
+    utils.py:263) in one kernel.  Non-differentiable (the reference's poses and intrinsics are data)."""
+    require_cuda(xy_pix, intrinsics, cam2world)
+    sb, n = xy_pix.shape[0], xy_pix.shape[1]
+    x, kinv, c2w = _camera_inputs(xy_pix, intrinsics, cam2world)
     ros = torch.empty(sb, n, 3, dtype=torch.float32, device=x.device)
     rds = torch.empty_like(ros)
+    aff = torch.empty(sb, n, 2, dtype=torch.float32, device=x.device) if want_affine else None
     with torch.cuda.device(x.device):
-        check(_lib.load().avr_world_rays(ptr(x), ptr(kinv), ptr(c2w), sb * n, n, ptr(ros), ptr(rds), _stream(x)),
+        check(_lib.load().avr_world_rays(ptr(x), ptr(kinv), ptr(c2w), sb * n, n, ptr(ros), ptr(rds), ptr(aff), _stream(x)),
               "avr_world_rays")
-    return ros, rds
+    return (ros, rds, aff) if want_affine else (ros, rds)
 
 
 class DepthFromWorld(torch.autograd.Function):

@@ -141,10 +141,8 @@ class VolumeRenderer(nn.Module):
         near, far = self.near.to(dev), self.far.to(dev)
         white_back = bool(self.white_back)
 
-        ros, rds = get_world_rays(x_pix, intrinsics, cam2world)                       # :166
-
-        # coarse pass: depths, sample points and the view-direction copy in one kernel  # :169-175
-        z_c, pts, vd = ops.coarse_sample_points(near, far, 0, u_c, ros, rds)
+        # ray setup, coarse depths, sample points and the view-direction copy in one kernel   # :166-175
+        ros, rds, aff, z_c, pts, vd = ops.rays_coarse_sample_points(x_pix, intrinsics, cam2world, near, far, 0, u_c)
         out = radiance_field(pts.view(sb, -1, 3), viewdirs=vd.view(sb, -1, 3), coarse=True)   # :173
         rgb_c, _dist_c, w_c = ops.composite(out.reshape(sb, num_rays, kc, 4), z_c, white_back, 1.8, want_w=True)  # :180
 
@@ -155,9 +153,9 @@ class VolumeRenderer(nn.Module):
         k = kc + self.n_fine
         pts, vd = ops.ray_points(ros, rds, z_s)                                       # :260-265
         out = radiance_field(pts.view(sb, -1, 3), viewdirs=vd.view(sb, -1, 3), coarse=False)  # :263
-        rgb_f, dist_f, _ = ops.composite(out.reshape(sb, num_rays, k, 4), z_s, white_back, 1.8, want_w=False)  # :270
-
-        depth = depth_from_world(ros, cam2world, rds=rds, dist=dist_f)                # :274-275
+        # the fine composite returns the camera depth of ros + rds * dist itself              # :270-275
+        rgb_f, depth, _ = ops.composite(out.reshape(sb, num_rays, k, 4), z_s, white_back, 1.8, want_w=False,
+                                        depth_affine=aff)
         return rgb_c, rgb_f, depth, depth
 
     @classmethod
@@ -224,7 +222,7 @@ class AdaptiveVolumeRenderer(nn.Module):
         dev = xy_pix.device
         if not xy_pix.is_cuda:
             raise AvrError("AdaptiveVolumeRenderer (avr_b200) needs CUDA inputs; there is no CPU fallback")
-        ros, rds = get_world_rays(xy_pix, intrinsics=intrinsics, cam2world=cam2world)   # :411
+        ros, rds, aff = ops.world_rays(xy_pix, intrinsics, cam2world, want_affine=True)  # :411
         if draws is None:
             # :413 draws the initial distance on the CPU generator, :14 (via :492) on the device
             init = torch.zeros((sb, num_rays, 1)).normal_(mean=0.8, std=5e-2).to(dev)
@@ -245,9 +243,9 @@ class AdaptiveVolumeRenderer(nn.Module):
         z_sorted, _ = ops.SortRays.apply(z)                                             # :494
         pts, vd = ops.ray_points(ros, rds, z_sorted)                                    # :496-498 (d_z flows back)
         out = phi(pts.view(sb, -1, 3), coarse=False, viewdirs=vd.view(sb, -1, 3), return_features=False)  # :499
-        rgb, dist, _ = ops.composite(out.reshape(sb, num_rays, self.n_coarse, 4), z_sorted,
-                                     bool(self.white_back), 1.8, want_w=False)          # :505
-        depth = depth_from_world(ros, cam2world, rds=rds, dist=dist)                    # :508-509
+        rgb, depth, _ = ops.composite(out.reshape(sb, num_rays, self.n_coarse, 4), z_sorted,
+                                      bool(self.white_back), 1.8, want_w=False, depth_affine=aff)  # :505-509
+        dist = depth
         if debug:
             print("now AVR")
             print(f" pixel location is {xy_pix[0][64]}")

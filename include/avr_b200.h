@@ -152,6 +152,19 @@ AVR_API int avr_composite_fwd(const float* rgbs, const float* z, int64_t R, int 
                       int white_back, float infinity,
                       float* w, float* rgb, float* depth, avr_stream_t stream);
 
+/* The same with utils.depth_from_world folded in (renderers.py:274-275, 508-509): `depth_affine`
+ * [R,2] holds, per ray, (A, B) with  camera depth of (ros + rds * dist) = A * dist + B  (written by
+ * avr_world_rays / avr_rays_coarse_sample_points_fwd); `depth` then receives that camera depth instead
+ * of the composited distance, and in the backward call `g_depth` is the gradient w.r.t. it.
+ * depth_affine == NULL: exactly avr_composite_fwd / avr_composite_bwd. */
+AVR_API int avr_composite_fwd_camera(const float* rgbs, const float* z, const float* depth_affine,
+                                     int64_t R, int K, int white_back, float infinity,
+                                     float* w, float* rgb, float* depth, avr_stream_t stream);
+AVR_API int avr_composite_bwd_camera(const float* rgbs, const float* z, const float* depth_affine,
+                                     const float* g_rgb, const float* g_depth, const float* g_w,
+                                     int64_t R, int K, int white_back, float infinity,
+                                     float* d_rgbs, float* d_z, avr_stream_t stream);
+
 /* Forward compositing with the output all-gather fused into the kernel's epilogue (multi-GPU):
  * besides rgb/depth, every ray's (r,g,b,depth) is stored as one float4 into row `row0 + ray` of
  * each of the `n_peers` buffers in `peer_gathered` (HOST array of DEVICE pointers, each a
@@ -277,9 +290,21 @@ AVR_API int avr_ray_points_bwd_packed(const float* rds, const float* g_pts, cons
  *   x_pix [R,2]; intrinsics [n_cams,3,3], ray r uses camera r / rays_per_cam (the 3x3 inverse of
  *   utils.py:263 is formed inside the kernel);
  *   cam2world [R,4,4] (one pose per ray, as the reference's callers expand it, train.py:83);
- *   ros, rds [R,3]. */
+ *   ros, rds [R,3];
+ *   depth_affine [R,2] (may be NULL): per ray (A, B) with depth_from_world(ros + rds * t) = A t + B,
+ *   for avr_composite_fwd_camera. */
 AVR_API int avr_world_rays(const float* x_pix, const float* intrinsics, const float* cam2world, int64_t R,
-                           int64_t rays_per_cam, float* ros, float* rds, avr_stream_t stream);
+                           int64_t rays_per_cam, float* ros, float* rds, float* depth_affine,
+                           avr_stream_t stream);
+/* VolumeRenderer's first launch, renderers.py:166-175 in one pass over the uniforms: ray setup
+ * (avr_world_rays) + sample_coarse + sample points + view directions.  Outputs ros, rds [R,3],
+ * depth_affine [R,2] (may be NULL), z [R,K], pts / viewdirs [R,K,3]; each bit-identical to the
+ * separate calls. */
+AVR_API int avr_rays_coarse_sample_points_fwd(const float* x_pix, const float* intrinsics, const float* cam2world,
+                                              int64_t rays_per_cam, const float* near, const float* far,
+                                              int bound_stride, const float* u, int64_t R, int K,
+                                              float* ros, float* rds, float* depth_affine,
+                                              float* z, float* pts, float* viewdirs, avr_stream_t stream);
 /* utils.depth_from_world (utils.py:358-361) of the composited point ros + rds * dist
  * (renderers.py:274-275, 508-509); dist == NULL: `ros` holds the world points themselves and
  * rds is ignored (renderers.py:486).  depth [R] = -(cam2world^-1 [p,1])_z.

@@ -132,3 +132,64 @@ def test_ray_points_packed(dev):
     gp = torch.randn(s, 3, generator=gen)
     pts.backward(gp.to(dev))
     assert_close(zd.grad, (gp * rds[seg]).sum(-1), rtol=1e-5, atol=1e-6, what="d_z")
+
+
+@pytest.mark.parametrize("k", [64, 20, 7])
+def test_rays_coarse_sample_points_is_the_three_calls_in_one(k, dev):
+    """VolumeRenderer's first launch (renderers.py:166-175): rays, coarse depths, points and view
+    directions from one kernel, each bit-identical to the separate kernels (and so to the goldens
+    those are held to), plus the camera-depth coefficients."""
+    from avr_b200 import ops
+    g = load_golden("geometry")
+    x_pix, intr, c2w = g["x_pix"].to(dev), g["intrinsics"].to(dev), g["cam2world"].to(dev)
+    u = torch.rand(2, 75, k, generator=torch.Generator().manual_seed(k)).to(dev)
+    near, far = torch.tensor([0.8], device=dev), torch.tensor([1.8], device=dev)
+    ros0, rds0, aff0 = ops.world_rays(x_pix, intr, c2w, want_affine=True)
+    z0, pts0, vd0 = ops.coarse_sample_points(near, far, 0, u, ros0, rds0)
+    ros, rds, aff, z, pts, vd = ops.rays_coarse_sample_points(x_pix, intr, c2w, near, far, 0, u)
+    for a, b, what in ((ros, ros0, "ros"), (rds, rds0, "rds"), (aff, aff0, "affine"), (z, z0, "z"), (pts, pts0, "pts"), (vd, vd0, "viewdirs")):
+        assert torch.equal(a, b), what
+    assert torch.equal(ros.cpu(), g["ref_ros"])
+    assert_close(rds, g["ref_rds"], rtol=1e-5, atol=1e-6, what="rds")
+    # depth_from_world(ros + rds * t) == A t + B   (utils.py:358-361)
+    depth = aff[..., 0] * g["dist"].to(dev) + aff[..., 1]
+    assert_close(depth, g["ref_depth"], rtol=1e-5, atol=2e-6, what="camera depth from the affine form")
+
+
+@pytest.mark.parametrize("r,k,want_dz", [(3000, 96, False), (1200, 20, True), (50, 64, False), (5, 7, True)])
+def test_composite_returns_the_camera_depth(r, k, want_dz, dev):
+    """utils.depth_from_world folded into the compositing kernels (renderers.py:270-275, 505-509):
+    the span kernels (3000 x 96, 1200 x 20 with d_z), the warp-per-ray kernels (tails / tiny batches)
+    and the generic kernels return A * dist + B and differentiate through it, against composite +
+    depth_from_world as separate steps."""
+    import avr_b200
+    from avr_b200 import ops
+    lib = avr_b200.load_library()
+    gen = torch.Generator().manual_seed(r + k)
+    z = torch.sort(0.8 + torch.rand(1, r, k, generator=gen), -1).values.to(dev)
+    x = torch.cat([torch.sigmoid(torch.randn(1, r, k, 3, generator=gen)), torch.relu(torch.randn(1, r, k, 1, generator=gen)) * 30], -1).to(dev)
+    x_pix = torch.rand(1, r, 2, generator=gen).to(dev)
+    from fields import camera_setup
+    c2w, intr, _ = (t.to(dev) for t in camera_setup(1, r, seed=4))
+    ros, rds, aff = ops.world_rays(x_pix, intr, c2w, want_affine=True)
+    g_rgb, g_d = torch.randn(1, r, 3, generator=gen).to(dev), torch.randn(1, r, generator=gen).to(dev)
+    for generic in (0, 1):
+        lib.avr_set_force_generic(generic)
+        try:
+            xa, za = x.clone().requires_grad_(True), z.clone().requires_grad_(want_dz)
+            rgb_a, depth_a, _ = ops.composite(xa, za, True, 1.8, want_w=False, depth_affine=aff)
+            torch.autograd.backward([rgb_a, depth_a], [g_rgb, g_d])
+            xb, zb = x.clone().requires_grad_(True), z.clone().requires_grad_(want_dz)
+            rgb_b, dist_b, _ = ops.composite(xb, zb, True, 1.8, want_w=False)
+            depth_b = ops.depth_from_world(ros, rds, dist_b, c2w)
+            torch.autograd.backward([rgb_b, depth_b], [g_rgb, g_d])
+        finally:
+            lib.avr_set_force_generic(0)
+        assert torch.equal(rgb_a, rgb_b)
+        assert_close(depth_a, depth_b, rtol=1e-5, atol=2e-6, what=f"camera depth (generic={generic})")
+        assert_close(xa.grad[..., :3], xb.grad[..., :3], rtol=1e-5, atol=2e-6, what="d_rgb")
+        assert_close(xa.grad[..., :-1, 3], xb.grad[..., :-1, 3], rtol=1e-5, atol=2e-6, what="d_sigma[:-1]")
+        assert_close(xa.grad[..., -1, 3] / 1e10, xb.grad[..., -1, 3] / 1e10, rtol=1e-5, atol=2e-6, what="d_sigma[-1] / 1e10")
+        if want_dz:
+            scale = zb.grad.abs().amax(-1, keepdim=True).clamp_min(1.0)
+            assert_close(za.grad / scale, zb.grad / scale, rtol=1e-5, atol=2e-5, what="d_z")
