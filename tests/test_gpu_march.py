@@ -88,6 +88,7 @@ def test_march_matches_oracle(sb, r, steps, g_scale, dev):
         lstm2, out2 = copy.deepcopy(lstm), copy.deepcopy(out_layer)
         for p in list(lstm2.parameters()) + list(out2.parameters()) + list(phi.parameters()):
             p.grad = None
+        phi.encode(images, cam2world[:, :1], 22.0)          # a fresh graph for the second backward
         w = ros + rds * init
         state = None
         for _ in range(steps):
