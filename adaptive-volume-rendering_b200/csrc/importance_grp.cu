@@ -126,7 +126,7 @@ __host__ __device__ inline int grp_ragged_class(int kc, int n) {
 // kRagged == true (packed layout): rays of class kClass, i.e. at most KC coarse and NI new
 // samples, padded to the box with masked lanes / +inf keys; the launch handles only its class
 // (warp-level filter over 32 consecutive rays), so a short ray never pays for the longest.
-template <int G, int KC, int NI, int ND, bool kRagged, int kClass>
+template <int G, int KC, int NI, int ND, bool kRagged, int kClass, bool kPrefetch = false>
 __global__ void __launch_bounds__(GrpCfg<G, KC, NI, ND>::WARPS * 32, GrpCfg<G, KC, NI, ND>::MIN_BLOCKS)
 importance_grp_kernel(const ImportanceRegArgs a) {
   using C = GrpCfg<G, KC, NI, ND>;
@@ -143,15 +143,19 @@ importance_grp_kernel(const ImportanceRegArgs a) {
   const LaneSigns sg = lane_signs(lane);
   const float inv_kc = 1.0f / (float)KC;  // KC is a power of two: x * inv_kc == x / KC bit for bit
 
-  // tree slots of this lane's cdf entries q = g*CW + i + 1 (breadth-first order, root = 1);
-  // the last entry q == KC is not part of the tree: it is dumped into the unused slot 0
-  int hidx[CW];
-#pragma unroll
-  for (int i = 0; i < CW; ++i) {
-    const int q = g * CW + i + 1;
-    const int tz = __ffs(q) - 1;
-    hidx[i] = (q < KC) ? (1 << (DEPTH - 1 - tz)) + (q >> (tz + 1)) : 0;
-  }
+  // tree slots of this lane's cdf entries q = g*CW + i + 1 (breadth-first order, root = 1):
+  // slot(q) = 2^(DEPTH-1-tz) + (q >> (tz+1)) with tz = trailing zeros of q.  For i < CW-1 the
+  // trailing zeros of q are those of i + 1 (g*CW has more), a compile-time constant, so the slot is
+  // linear in g and costs one IMAD where it is used; only the lane's LAST entry (q = (g+1)*CW) needs
+  // a run-time count, kept in one register.  q == KC is not part of the tree: it goes to the unused slot 0.
+  const int q_last = (g + 1) * CW;
+  const int tz_last = __ffs(q_last) - 1;
+  const int h_last = (q_last < KC) ? (1 << (DEPTH - 1 - tz_last)) + (q_last >> (tz_last + 1)) : 0;
+  auto tree_slot = [&](const int i) -> int {
+    if (i == CW - 1) return h_last;
+    const int tz = __ffs(i + 1) - 1;     // i is a constant after unrolling
+    return (1 << (DEPTH - 1 - tz)) + (g * (CW >> (tz + 1))) + ((i + 1) >> (tz + 1));
+  };
 
   // one ray per group: `live` == false marks a group without work of its own (it recomputes a
   // valid ray alongside the others and stores nothing)
@@ -221,13 +225,14 @@ importance_grp_kernel(const ImportanceRegArgs a) {
 #pragma unroll
     for (int d = G / 2; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     const float S = part;
-    // dense shapes divide like the reference (renderers.py:37); ragged rays multiply by 1/S (a lane
-    // owns up to 16 bins; <= 1 ulp per pdf entry, same rule as importance_reg.cu's run-time shapes)
-    const float rS = kRagged ? __fdiv_rn(1.0f, S) : 0.f;
+    // pdf = w / S (renderers.py:37) as w * (1/S) with a correctly rounded reciprocal: <= 1 ulp per
+    // entry, far inside the cdf's tolerance, and the search stays bit-exact with respect to the cdf
+    // the kernel exports (a true division is 16 instructions per entry on this ISA)
+    const float rS = __fdiv_rn(1.0f, S);
     float run = 0.f;
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
-      run += kRagged ? __fmul_rn(w[i], rS) : __fdiv_rn(w[i], S);
+      run += __fmul_rn(w[i], rS);
       w[i] = run;  // local inclusive prefix
     }
     float incl = run;
@@ -253,7 +258,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     for (int i = 0; i < CW; ++i) {
       float val = fmaxf(off + w[i], floor_prev);
       if (kRagged && g * CW + i >= kc) val = CUDART_INF_F;  // past the ray's last bin
-      tree[hidx[i]] = val;
+      tree[tree_slot(i)] = val;
       if (cdf_out) cdf_out[g * CW + i + 1] = val;
       last = val;
     }
@@ -270,18 +275,26 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       // node <- 2*node + (tree[node] <= u): after DEPTH probes node - KC counts the entries
       // cdf[1..KC-1] <= u; adding (cdf[KC] <= u) gives clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
       // (c <= u) is the complement of the sign bit of u - c (exact in sign: nothing is flushed).
+      // Held as shared-memory byte addresses a = base + 4 * node, so a probe step is LDS, one 3-input add
+      // (a <- 2a - base) and a predicated +4: four instructions.
       unsigned node[NIL > 0 ? NIL : 1];
       int bins[NIL > 0 ? NIL : 1];
+      const unsigned tbase = smem_u32(tree);
+      const unsigned neg_base = 0u - tbase;
 #pragma unroll
-      for (int q = 0; q < NIL; ++q) node[q] = 1;
+      for (int q = 0; q < NIL; ++q) node[q] = tbase + 4u;
 #pragma unroll
       for (int step = 0; step < DEPTH; ++step) {
 #pragma unroll
         for (int q = 0; q < NIL; ++q) {
-          const float d = __fsub_rn(uu[q], tree[node[q]]);
-          node[q] = 2 * node[q] + 1 - (__float_as_uint(d) >> 31);
+          float cv;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cv) : "r"(node[q]));
+          node[q] = node[q] + node[q] + neg_base;
+          if (cv <= uu[q]) node[q] += 4u;
         }
       }
+#pragma unroll
+      for (int q = 0; q < NIL; ++q) node[q] = (node[q] - tbase) >> 2;
 #pragma unroll
       for (int q = 0; q < NIL; ++q) {
         const float dl = __fsub_rn(uu[q], last);
@@ -394,7 +407,32 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     }
   } else {
     const int64_t n_wg = (a.R + RPW - 1) / RPW;
-    for (int64_t wg = blockIdx.x * (int64_t)kGrpWarps + warp; wg < n_wg; wg += (int64_t)gridDim.x * kGrpWarps) {
+    const int64_t wg_stride = (int64_t)gridDim.x * kGrpWarps;
+    const int64_t wg0 = blockIdx.x * (int64_t)kGrpWarps + warp;
+    // The chain load -> sum -> cdf -> search is one dependent sequence per ray and the kernel runs at
+    // 16-32 warps per SM: pull the NEXT group's inputs (contiguous: the warp's rays are consecutive)
+    // into L2 one iteration ahead, so that its loads are L2 hits.  No registers are held beyond one
+    // running pointer per stream: lane l owns line l of each of the group's chunks.
+    const char* pf_c = reinterpret_cast<const char*>(a.weights) + ((wg0 + wg_stride) * RPW * KC * 4 + lane * 128);
+    const char* pf_z = reinterpret_cast<const char*>(a.z_coarse) + ((wg0 + wg_stride) * RPW * KC * 4 + lane * 128);
+    const char* pf_u = reinterpret_cast<const char*>(a.u) + ((wg0 + wg_stride) * RPW * NI * 4 + lane * 128);
+    const char* pf_j = reinterpret_cast<const char*>(a.u2) + ((wg0 + wg_stride) * RPW * NI * 4 + lane * 128);
+    const int64_t step_c = wg_stride * RPW * KC * 4, step_u = wg_stride * RPW * NI * 4;
+    for (int64_t wg = wg0; wg < n_wg; wg += wg_stride) {
+      if (kPrefetch && wg + wg_stride < n_wg) {
+        if (lane * 128 < RPW * KC * 4) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_c));
+          if (do_sort) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_z));
+        }
+        if (NI > 0 && lane * 128 < RPW * NI * 4) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_u));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_j));
+        }
+        pf_c += step_c;
+        pf_z += step_c;
+        pf_u += step_u;
+        pf_j += step_u;
+      }
       const int64_t r_raw = wg * RPW + sub;
       process(r_raw < a.R ? r_raw : a.R - 1, r_raw < a.R);   // a dead group (last warp only) recomputes ray R-1
     }
@@ -409,7 +447,12 @@ static int launch_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
   int64_t blocks = (n_wg + C::WARPS - 1) / C::WARPS;
   const int64_t cap = (int64_t)num_sms() * C::MIN_BLOCKS * 4;  // a few waves for balance
   if (blocks > cap) blocks = cap;
-  importance_grp_kernel<G, KC, NI, ND, false, 0><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
+  // AVR_GRP_PREFETCH=0: without the L2 prefetch of the next group's inputs (A/B)
+  if (option(OPT_GRP_PREFETCH, 1)) {
+    importance_grp_kernel<G, KC, NI, ND, false, 0, true><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
+  } else {
+    importance_grp_kernel<G, KC, NI, ND, false, 0, false><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
+  }
   return check_launch();
 }
 
