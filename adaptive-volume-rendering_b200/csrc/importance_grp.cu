@@ -126,7 +126,7 @@ __host__ __device__ inline int grp_ragged_class(int kc, int n) {
 // kRagged == true (packed layout): rays of class kClass, i.e. at most KC coarse and NI new
 // samples, padded to the box with masked lanes / +inf keys; the launch handles only its class
 // (warp-level filter over 32 consecutive rays), so a short ray never pays for the longest.
-template <int G, int KC, int NI, int ND, bool kRagged, int kClass, bool kPrefetch = false>
+template <int G, int KC, int NI, int ND, bool kRagged, int kClass>
 __global__ void __launch_bounds__(GrpCfg<G, KC, NI, ND>::WARPS * 32, GrpCfg<G, KC, NI, ND>::MIN_BLOCKS)
 importance_grp_kernel(const ImportanceRegArgs a) {
   using C = GrpCfg<G, KC, NI, ND>;
@@ -408,31 +408,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
   } else {
     const int64_t n_wg = (a.R + RPW - 1) / RPW;
     const int64_t wg_stride = (int64_t)gridDim.x * kGrpWarps;
-    const int64_t wg0 = blockIdx.x * (int64_t)kGrpWarps + warp;
-    // The chain load -> sum -> cdf -> search is one dependent sequence per ray and the kernel runs at
-    // 16-32 warps per SM: pull the NEXT group's inputs (contiguous: the warp's rays are consecutive)
-    // into L2 one iteration ahead, so that its loads are L2 hits.  No registers are held beyond one
-    // running pointer per stream: lane l owns line l of each of the group's chunks.
-    const char* pf_c = reinterpret_cast<const char*>(a.weights) + ((wg0 + wg_stride) * RPW * KC * 4 + lane * 128);
-    const char* pf_z = reinterpret_cast<const char*>(a.z_coarse) + ((wg0 + wg_stride) * RPW * KC * 4 + lane * 128);
-    const char* pf_u = reinterpret_cast<const char*>(a.u) + ((wg0 + wg_stride) * RPW * NI * 4 + lane * 128);
-    const char* pf_j = reinterpret_cast<const char*>(a.u2) + ((wg0 + wg_stride) * RPW * NI * 4 + lane * 128);
-    const int64_t step_c = wg_stride * RPW * KC * 4, step_u = wg_stride * RPW * NI * 4;
-    for (int64_t wg = wg0; wg < n_wg; wg += wg_stride) {
-      if (kPrefetch && wg + wg_stride < n_wg) {
-        if (lane * 128 < RPW * KC * 4) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_c));
-          if (do_sort) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_z));
-        }
-        if (NI > 0 && lane * 128 < RPW * NI * 4) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_u));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_j));
-        }
-        pf_c += step_c;
-        pf_z += step_c;
-        pf_u += step_u;
-        pf_j += step_u;
-      }
+    for (int64_t wg = blockIdx.x * (int64_t)kGrpWarps + warp; wg < n_wg; wg += wg_stride) {
       const int64_t r_raw = wg * RPW + sub;
       process(r_raw < a.R ? r_raw : a.R - 1, r_raw < a.R);   // a dead group (last warp only) recomputes ray R-1
     }
@@ -447,12 +423,7 @@ static int launch_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
   int64_t blocks = (n_wg + C::WARPS - 1) / C::WARPS;
   const int64_t cap = (int64_t)num_sms() * C::MIN_BLOCKS * 4;  // a few waves for balance
   if (blocks > cap) blocks = cap;
-  // AVR_GRP_PREFETCH=0: without the L2 prefetch of the next group's inputs (A/B)
-  if (option(OPT_GRP_PREFETCH, 1)) {
-    importance_grp_kernel<G, KC, NI, ND, false, 0, true><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
-  } else {
-    importance_grp_kernel<G, KC, NI, ND, false, 0, false><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
-  }
+  importance_grp_kernel<G, KC, NI, ND, false, 0><<<(unsigned)blocks, C::WARPS * 32, 0, stream>>>(a);
   return check_launch();
 }
 

@@ -94,6 +94,42 @@ def _time(step, iters, dev, warm=5):
     return {"wall_ms": round(wall, 4), "device_ms": round(e0.elapsed_time(e1) / iters, 4)}
 
 
+def boundary_overhead(dev, calls=2000):
+    """Host cost of ONE call through the boundary on a batch too small to matter (96 rays x 64):
+    the ctypes call alone (outputs preallocated), the Python operator around it (argument checks,
+    three torch.empty, stream lookup), and a stock ATen op on the same tensor as the yardstick.
+    BASELINE.json's north_star names a torch C++ extension for this layer; the repo binds the C ABI
+    with ctypes instead — these numbers are what that choice costs."""
+    import avr_b200
+    from avr_b200 import ops
+    lib = avr_b200.load_library()
+    r, k = 96, 64
+    x = torch.rand(1, r, k, 4, device=dev)
+    z = torch.sort(0.8 + torch.rand(1, r, k, device=dev), -1).values
+    w, rgb, depth = torch.empty(1, r, k, device=dev), torch.empty(1, r, 3, device=dev), torch.empty(1, r, device=dev)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+
+    def raw():
+        lib.avr_composite_fwd(x.data_ptr(), z.data_ptr(), r, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(), depth.data_ptr(), sp)
+
+    def per_call(fn):
+        for _ in range(50):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            fn()
+        dt = time.perf_counter() - t0          # host time to ENQUEUE (the queue never fills at this size)
+        torch.cuda.synchronize(dev)
+        return round(dt / calls * 1e6, 2)
+
+    return {"ctypes_call_us": per_call(raw),
+            "python_operator_us": per_call(lambda: ops.composite_fwd_raw(x, z, True, 1.8, True)),
+            "autograd_function_us": per_call(lambda: ops.composite(x, z, True, 1.8, True)),
+            "aten_cumprod_us": per_call(lambda: torch.cumprod(z, -1)),
+            "aten_sort_us": per_call(lambda: torch.sort(z, -1))}
+
+
 def run(dev, iters=20, sizes=((1, 16384, "128x128 frame, SB=1"), (4, 512, "train.py batch, SB=4 x 512 rays"))):
     import avr_b200
     import avr_oracle as O
@@ -186,6 +222,7 @@ def run(dev, iters=20, sizes=((1, 16384, "128x128 frame, SB=1"), (4, 512, "train
                                         "renderer_share_of_step": round(max(a["wall_ms"] - b["wall_ms"], 0.0) / a["wall_ms"], 4)}
             del wide
         out[label] = rec
+    out["boundary_call_overhead"] = boundary_overhead(dev)
     return out
 
 
