@@ -472,19 +472,21 @@ int avr_lstm_march_bwd(const avr_field_inputs* field, const avr_lstm_march* marc
 // while chunk c computes, chunk c+1 uploads and chunk c-1 downloads (PCIe is full duplex).
 // Stream order inside a slot serialises the reuse of its buffers.
 struct avr_host_workspace {
-  static constexpr int kSlots = 3;
+  static constexpr int kMaxSlots = 8;
+  int n_slots = 3;   // AVR_HOST_SLOTS (2..8): chunks in flight
   struct Slot {
     float *rgbs = nullptr, *z = nullptr, *g_rgb = nullptr, *g_depth = nullptr;
     float *rgb = nullptr, *depth = nullptr, *d_rgbs = nullptr, *w = nullptr;
     cudaStream_t stream = nullptr;
-  } slots[kSlots];
+  } slots[kMaxSlots];
   int K = 0;
   int64_t chunk_rays = 0;
   int device = 0;
 };
 
 static void free_workspace(avr_host_workspace* ws) {
-  for (auto& sl : ws->slots) {
+  for (int i = 0; i < ws->n_slots; ++i) {
+    auto& sl = ws->slots[i];
     if (sl.stream) {
       cudaStreamSynchronize(sl.stream);
       cudaStreamDestroy(sl.stream);
@@ -514,7 +516,8 @@ static void free_workspace(avr_host_workspace* ws) {
 static int alloc_workspace(avr_host_workspace* ws) {
   const size_t nk = (size_t)ws->chunk_rays * ws->K;
   const size_t nr = (size_t)ws->chunk_rays;
-  for (auto& sl : ws->slots) {
+  for (int i = 0; i < ws->n_slots; ++i) {
+    auto& sl = ws->slots[i];
     AVR_RT(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     AVR_RT(cudaMalloc(&sl.rgbs, nk * 16));
     AVR_RT(cudaMalloc(&sl.z, nk * 4));
@@ -536,7 +539,7 @@ static int enqueue_host_pass(avr_host_workspace* ws, const float* rgbs, const fl
   const int64_t n_chunks = (R + chunk - 1) / chunk;
   int rc = AVR_OK;
   for (int64_t c = 0; c < n_chunks; ++c) {
-    auto& sl = ws->slots[c % avr_host_workspace::kSlots];
+    auto& sl = ws->slots[c % ws->n_slots];
     const int64_t r0 = c * chunk;
     const int64_t rn = (R - r0 < chunk) ? R - r0 : chunk;
     const size_t n = (size_t)rn * K;
@@ -566,8 +569,8 @@ static int run_host_pass(avr_host_workspace* ws, const float* rgbs, const float*
   AVR_RT(cudaGetDevice(&prev));
   if (prev != ws->device) AVR_RT(cudaSetDevice(ws->device));  // streams and buffers live on the workspace's device
   int rc = enqueue_host_pass(ws, rgbs, z, g_rgb, g_depth, R, white_back, infinity, rgb, depth, w, d_rgbs);
-  for (auto& sl : ws->slots) {
-    cudaError_t e = cudaStreamSynchronize(sl.stream);
+  for (int i = 0; i < ws->n_slots; ++i) {
+    cudaError_t e = cudaStreamSynchronize(ws->slots[i].stream);
     if (e != cudaSuccess && rc == AVR_OK) {
       set_last_cuda_error(e);
       (void)cudaGetLastError();
@@ -586,12 +589,15 @@ int avr_host_workspace_create(int K, int64_t chunk_rays, avr_host_workspace** ou
   int rc = avr_device_check();
   if (rc != AVR_OK) return rc;
   if (chunk_rays <= 0) {
-    int64_t target = (int64_t)(48ll << 20) / ((int64_t)K * 16);
+    const int64_t mib = option(OPT_HOST_CHUNK_MIB, 48);
+    int64_t target = (int64_t)((mib < 1 ? 1 : mib) << 20) / ((int64_t)K * 16);
     chunk_rays = target < 96 ? 96 : target;
   }
   auto* ws = new avr_host_workspace();
   ws->K = K;
   ws->chunk_rays = chunk_rays;
+  int ns = option(OPT_HOST_SLOTS, 3);
+  ws->n_slots = ns < 2 ? 2 : (ns > avr_host_workspace::kMaxSlots ? avr_host_workspace::kMaxSlots : ns);
   cudaGetDevice(&ws->device);
   rc = alloc_workspace(ws);
   if (rc != AVR_OK) {
