@@ -93,7 +93,9 @@ lstm_march_fwd_kernel(const FieldInputsArgs f, const MarchArgs m) {
   FieldView view;
   field_view_reset(&view);
 
-  for (int64_t grp = (int64_t)blockIdx.x * WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * WARPS) {
+  // groups are dealt CTA-major (consecutive groups to different CTAs): a training batch has fewer groups than
+  // the grid has warps, and every SM should get its share
+  for (int64_t grp = (int64_t)warp * gridDim.x + blockIdx.x; grp < n_groups; grp += (int64_t)gridDim.x * WARPS) {
     float wx[RB], wy[RB], wz[RB], dx[RB], dy[RB], dz[RB], h[RB], c[RB];
     int64_t ray[RB];
     bool live[RB];
@@ -222,7 +224,9 @@ lstm_march_bwd_kernel(const FieldInputsArgs f, const MarchArgs m) {
   field_view_reset(&view);
   const int j = lane & (kMarchHidden - 1);
 
-  for (int64_t grp = (int64_t)blockIdx.x * WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * WARPS) {
+  // groups are dealt CTA-major (consecutive groups to different CTAs): a training batch has fewer groups than
+  // the grid has warps, and every SM should get its share
+  for (int64_t grp = (int64_t)warp * gridDim.x + blockIdx.x; grp < n_groups; grp += (int64_t)gridDim.x * WARPS) {
     float gx[RB], gy[RB], gz[RB], dx[RB], dy[RB], dz[RB], gh[RB], gc[RB];
     int64_t ray[RB];
     bool live[RB];
