@@ -198,6 +198,114 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
   if (kLatent && CPL > 0) field_grad_flush<N>(a, lane, &grads);
 }
 
+// kRing variant of the above: the rows of g_out (2216 B each, read exactly once) reach the warp through a
+// two-stage shared-memory ring filled by 1-D bulk async copies (TMA, cp.async.bulk + mbarrier) one row
+// PAIR ahead — rows are 8-byte aligned, pairs starting at an even row are 16-byte aligned and a multiple
+// of 16 bytes long.  ncu had these kernels waiting on exactly those loads (4.6 long-scoreboard stall
+// cycles per issued instruction at 10-14 resident warps); a register prefetch (kPre) spilled.  The
+// ring costs no registers and the copy engine runs ahead across chunk boundaries.
+template <int CPL, bool kLatent, bool kPoint, bool kShare>
+__global__ void __launch_bounds__(kFieldWarps * 32, (kLatent && kPoint) ? 1 : 3)
+field_inputs_bwd_ring_kernel(const FieldInputsArgs a, int row_stride) {
+  extern __shared__ __align__(16) unsigned char s_ring_raw[];
+  static_assert(CPL > 0, "ring kernels exist for the cached channel counts");
+  constexpr int N = CPL;
+  constexpr int kChunk = FieldChunk<kShare>::value;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair_floats = 2 * row_stride;              // row_stride is even: a multiple of 16 bytes
+  const int stage_floats = (pair_floats + 3) & ~3;
+  float* ring = reinterpret_cast<float*>(s_ring_raw) + (size_t)warp * 2 * stage_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring_raw + (size_t)kFieldWarps * 2 * stage_floats * sizeof(float)) + warp * 2;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const int64_t rows = a.NV * a.B;
+  const int64_t n_chunks = (rows + kChunk - 1) / kChunk;
+  const int64_t warps = (int64_t)gridDim.x * kFieldWarps;
+  const FieldLaneCode lc = field_lane_code(a, lane);
+  FieldTapCache<N> taps;
+  FieldGradCache<N> grads;
+  FieldView view;
+  field_cache_reset(&taps);
+  field_grad_reset(&grads);
+  field_view_reset(&view);
+  // lane 0: request rows [ch*kChunk + 2*pp, +2) into `stage` (a single last row is read directly instead)
+  auto issue = [&](int64_t ch, int pp, int stage) {
+    const int64_t first_row = ch * kChunk + 2 * pp;
+    if (first_row + 2 <= rows) {
+      const uint32_t bytes = (uint32_t)pair_floats * 4u;
+      mbar_expect_tx(&bars[stage], bytes);
+      bulk_g2s(ring + (size_t)stage * stage_floats, a.g_out + first_row * row_stride, bytes, &bars[stage]);
+    }
+  };
+  int64_t ch = blockIdx.x * (int64_t)kFieldWarps + warp;
+  int64_t k = 0;  // row pairs this warp has consumed
+  if (lane == 0 && ch < n_chunks) issue(ch, 0, 0);
+  for (; ch < n_chunks; ch += warps) {
+    const int64_t first = ch * kChunk;
+    const int n = (int)(first + kChunk < rows ? kChunk : rows - first);
+    const int np = (n + 1) >> 1;
+    FieldPoint mine;
+    if (kShare) mine = point_of_my_row(a, first, lane, rows, &view);
+    FieldCursor cur = field_cursor_at(a, first);
+    for (int pp = 0; pp < np; ++pp, ++k) {
+      {  // one pair ahead, across chunk boundaries
+        int64_t c2 = ch;
+        int p2 = pp + 1;
+        if (p2 >= np) {
+          c2 = ch + warps;
+          p2 = 0;
+        }
+        __syncwarp();  // every lane is done with the stage pair k-1 used
+        if (lane == 0 && c2 < n_chunks) issue(c2, p2, (int)((k + 1) & 1));
+      }
+      const int stage = (int)(k & 1);
+      const int nrows = n - 2 * pp < 2 ? n - 2 * pp : 2;
+      if (nrows == 2) mbar_wait(&bars[stage], (uint32_t)((k >> 1) & 1));
+      const float* srow = ring + (size_t)stage * stage_floats;
+      for (int q = 0; q < nrows; ++q, field_cursor_next(a, &cur)) {
+        const int r = 2 * pp + q;
+        FieldPoint p;
+        if (kShare) {
+          p = point_from_lane<kPoint>(mine, r);
+        } else {
+          field_view_fill(a, cur, &view);
+          p = field_point(a, cur, view);
+        }
+        FieldRowGrad<N> rg;
+        FieldRowPartial s;
+        if (nrows == 2) {
+          s = field_bwd_row_lane<N, kLatent, kPoint, false>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads,
+                                                            srow + (size_t)q * row_stride);
+        } else {  // the single last row of all: straight from global memory
+          s = field_bwd_row_lane<N, kLatent, kPoint, false>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads);
+        }
+        if (kPoint) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            s.gix += __shfl_xor_sync(0xffffffffu, s.gix, d);
+            s.giy += __shfl_xor_sync(0xffffffffu, s.giy, d);
+            s.enc0 += __shfl_xor_sync(0xffffffffu, s.enc0, d);
+            s.enc1 += __shfl_xor_sync(0xffffffffu, s.enc1, d);
+            s.enc2 += __shfl_xor_sync(0xffffffffu, s.enc2, d);
+            s.vr0 += __shfl_xor_sync(0xffffffffu, s.vr0, d);
+            s.vr1 += __shfl_xor_sync(0xffffffffu, s.vr1, d);
+            s.vr2 += __shfl_xor_sync(0xffffffffu, s.vr2, d);
+          }
+          if (lane == 0) {
+            if (kShare) field_view_fill(a, cur, &view);
+            field_bwd_row_finish(a, cur, view, p, s);
+          }
+        }
+      }
+    }
+  }
+  if (kLatent) field_grad_flush<N>(a, lane, &grads);
+}
+
 // Experiment knobs (A/B measurements; defaults are what the measurements picked):
 //   AVR_FIELD_NOCACHE=1      every channel count takes the generic walk (no register caches)
 //   AVR_FIELD_BWD_SPLIT=0    feature-map and point gradients in ONE launch instead of two (234 registers,
@@ -205,6 +313,7 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
 //   AVR_FIELD_SHARE_POINT=x  per-row coordinate work shared out over the lanes (see point_from_lane)
 //   AVR_FIELD_STAGE=x        forward rows leave through shared memory and bulk copies (see kStage)
 //   AVR_FIELD_BWD_PREFETCH=x backward kernels that share the point work also prefetch the next row of g_out
+//   AVR_FIELD_BWD_RING=0     backward without the bulk-copy ring for g_out (see field_inputs_bwd_ring_kernel)
 static bool field_no_cache() { return option(OPT_FIELD_NOCACHE, 0) != 0; }
 static bool field_bwd_split() { return option(OPT_FIELD_BWD_SPLIT, 1) != 0; }
 // unset: the measured defaults (forward and feature-map backward share, the point backward does not:
@@ -220,9 +329,30 @@ static unsigned field_grid(int64_t rows, int chunk) {
   return (unsigned)(blocks > cap ? cap : blocks);
 }
 
+template <int CPL, bool kLatent, bool kPoint, bool kShare>
+static bool launch_bwd_ring(const FieldInputsArgs& a, int row_stride, cudaStream_t stream) {
+  if constexpr (CPL == 0) {
+    return false;
+  } else {
+    if (!option(OPT_FIELD_BWD_RING, 1) || (row_stride & 1) || !aligned16(a.g_out)) return false;
+    const int stage_floats = (2 * row_stride + 3) & ~3;
+    const size_t smem = (size_t)kFieldWarps * 2 * stage_floats * sizeof(float) + kFieldWarps * 2 * sizeof(uint64_t);
+    auto kern = field_inputs_bwd_ring_kernel<CPL, kLatent, kPoint, kShare>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    kern<<<field_grid(a.NV * a.B, FieldChunk<kShare>::value), kFieldWarps * 32, smem, stream>>>(a, row_stride);
+    return true;
+  }
+}
+
 template <int CPL, bool kLatent, bool kPoint>
 static void launch_bwd_kernel(const FieldInputsArgs& a, int row_stride, bool share, cudaStream_t stream) {
   const unsigned t = kFieldWarps * 32;
+  if (share ? launch_bwd_ring<CPL, kLatent, kPoint, true>(a, row_stride, stream)
+            : launch_bwd_ring<CPL, kLatent, kPoint, false>(a, row_stride, stream))
+    return;
   if (share && field_bwd_prefetch()) {
     field_inputs_bwd_kernel<CPL, kLatent, kPoint, true, true><<<field_grid(a.NV * a.B, FieldChunk<true>::value), t, 0, stream>>>(a, row_stride);
   } else if (share) {

@@ -488,14 +488,17 @@ AVR_FI void field_load_row_grad(const FieldInputsArgs& a, int64_t row, int lane,
 // sums of the point gradient (kPoint; zero otherwise).  `taps` is the forward tap cache (read only
 // when kPoint); with kPreloaded `rg` holds this lane's part of the row's upstream gradient,
 // otherwise it is read here, group by group.
+// `g_row_in` (may be null): where the row of g_out is to be read from instead of global memory — the
+// shared-memory ring of the kernels that prefetch it with bulk copies (any address space).
 template <int CPL, bool kLatent, bool kPoint, bool kPreloaded>
 AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
                                           int row_stride, const FieldLaneCode& lc, const FieldRowGrad<CPL>& rg,
-                                          FieldTapCache<CPL>* taps, FieldGradCache<CPL>* grads) {
+                                          FieldTapCache<CPL>* taps, FieldGradCache<CPL>* grads,
+                                          const float* g_row_in = nullptr) {
   const int64_t v = cur.v;
   FieldRowPartial s;
   field_partial_zero(&s);
-  const float* g_row = a.g_out + cur.row * row_stride;
+  const float* g_row = g_row_in ? g_row_in : a.g_out + cur.row * row_stride;
   if (kPoint) field_cache_fill<CPL>(a, p, v, lane, taps);
   if (kLatent && !(grads->x0 == p.x0 && grads->y0 == p.y0 && grads->v == v)) {  // warp-uniform
     field_grad_flush<CPL>(a, lane, grads);
@@ -521,6 +524,11 @@ AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldC
     float g[4];
     if (kPreloaded) {
       g[0] = rg.g[i][0]; g[1] = rg.g[i][1]; g[2] = rg.g[i][2]; g[3] = rg.g[i][3];
+    } else if (g_row_in) {  // staged row (shared memory): ordinary 8-byte loads, one group at a time
+      g[0] = g_row[4 * lane + 128 * i];
+      g[1] = g_row[4 * lane + 128 * i + 1];
+      g[2] = g_row[4 * lane + 128 * i + 2];
+      g[3] = g_row[4 * lane + 128 * i + 3];
     } else {  // `rg` is not touched: one group of four in flight at a time
       field_load2(g_row + 4 * lane + 128 * i, g);
       field_load2(g_row + 4 * lane + 128 * i + 2, g + 2);
