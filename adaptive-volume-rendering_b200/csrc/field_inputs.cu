@@ -334,7 +334,11 @@ static bool launch_bwd_ring(const FieldInputsArgs& a, int row_stride, cudaStream
   if constexpr (CPL == 0) {
     return false;
   } else {
-    if (!option(OPT_FIELD_BWD_RING, 1) || (row_stride & 1) || !aligned16(a.g_out)) return false;
+    // measured (profiles/r02_field_ring.md): the point gradient gains a third (0.343 -> 0.257 ms), the feature-map
+    // gradient nothing (0.146 -> 0.149 ms: it waits on its vector atomics, not on g_out), so by default only kernels
+    // that form the point gradient take the ring; AVR_FIELD_BWD_RING=2 forces it everywhere, 0 nowhere
+    const int mode = option(OPT_FIELD_BWD_RING, 1);
+    if (mode == 0 || (mode == 1 && !kPoint) || (row_stride & 1) || !aligned16(a.g_out)) return false;
     const int stage_floats = (2 * row_stride + 3) & ~3;
     const size_t smem = (size_t)kFieldWarps * 2 * stage_floats * sizeof(float) + kFieldWarps * 2 * sizeof(uint64_t);
     auto kern = field_inputs_bwd_ring_kernel<CPL, kLatent, kPoint, kShare>;
@@ -350,8 +354,9 @@ static bool launch_bwd_ring(const FieldInputsArgs& a, int row_stride, cudaStream
 template <int CPL, bool kLatent, bool kPoint>
 static void launch_bwd_kernel(const FieldInputsArgs& a, int row_stride, bool share, cudaStream_t stream) {
   const unsigned t = kFieldWarps * 32;
-  if (share ? launch_bwd_ring<CPL, kLatent, kPoint, true>(a, row_stride, stream)
-            : launch_bwd_ring<CPL, kLatent, kPoint, false>(a, row_stride, stream))
+  if (!(share && field_bwd_prefetch()) &&
+      (share ? launch_bwd_ring<CPL, kLatent, kPoint, true>(a, row_stride, stream)
+             : launch_bwd_ring<CPL, kLatent, kPoint, false>(a, row_stride, stream)))
     return;
   if (share && field_bwd_prefetch()) {
     field_inputs_bwd_kernel<CPL, kLatent, kPoint, true, true><<<field_grid(a.NV * a.B, FieldChunk<true>::value), t, 0, stream>>>(a, row_stride);
