@@ -462,6 +462,13 @@ def measure_other_configs(dev, peak, lib):
         return bench_dropin.run(dev, iters=10)
     guarded("c1_dropin_volume_renderer", c1)
 
+    # SURVEY 8(f) row 4, the adaptive renderer's LSTM ray march: one persistent kernel vs the reference's loop in torch
+    def march():
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_march
+        return bench_march.run(dev, iters=10)
+    guarded("lstm_ray_march_10_steps_c512", march)
+
     # SURVEY 8(f) row 3, the radiance field's front end (tools/bench_field.py: raw C-ABI launches over
     # rotating inputs larger than L2; 2048 rays x 96 samples, conf/default.conf's 512 + 42 wide rows)
     def field():

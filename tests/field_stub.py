@@ -100,3 +100,44 @@ class StubNet(torch.nn.Module):
         out = (self.mlp_coarse if coarse else self.mlp_fine)(x, combine_inner_dims=(self.num_views_per_obj, b))
         out = out.reshape(-1, b, 4)
         return torch.cat([torch.sigmoid(out[..., :3]), torch.relu(out[..., 3:4])], -1).reshape(xyz.shape[0], b, -1)
+
+
+class MapField(torch.nn.Module):
+    """A radiance field that is nothing but a feature map (a parameter, so d_latent has somewhere to
+    go) with the attributes the fused front end reads — for the LSTM march at 256 / 512 channels,
+    where StubNet's conv encoder would only slow the test down."""
+
+    use_encoder = use_xyz = use_code = use_viewdirs = normalize_z = True
+    use_global_encoder = use_code_viewdirs = stop_encoder_grad = False
+    d_out = 4
+    num_views_per_obj = 1
+
+    def __init__(self, sb, ch, h=12, w=10, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.encoder, self.code = _Encoder(), _Code()
+        smooth = torch.nn.functional.interpolate(torch.randn(sb, ch, 4, 4, generator=g), size=(h, w), mode="bicubic", align_corners=True)
+        self.map = torch.nn.Parameter(smooth * 0.4)
+        ls = torch.tensor([float(w), float(h)])
+        self.encoder.latent_scaling = ls / (ls - 1) * 2.0
+        self.mlp_coarse = self.mlp_fine = None
+
+    def place(self, cam2world, focal):
+        """Source view = the given poses (SB, 4, 4); call after .to(device)."""
+        dev = self.map.device
+        rot = cam2world[:, :3, :3].transpose(1, 2)
+        self.poses = torch.cat((rot, -torch.bmm(rot, cam2world[:, :3, 3:])), dim=-1).contiguous().to(dev)
+        h, w = self.map.shape[-2:]
+        self.image_shape = torch.tensor([4.0 * w, 4.0 * h], device=dev)
+        self.focal = torch.tensor([[focal, -focal]], device=dev)
+        self.c = (self.image_shape * 0.5).unsqueeze(0)
+        self.encoder.latent_scaling = self.encoder.latent_scaling.to(dev)
+        self.refresh()
+
+    def refresh(self):
+        self.encoder.latent = self.map * 1.0        # a non-leaf, like an encoder's output
+
+    def forward(self, xyz, coarse=True, viewdirs=None, far=False, return_features=False):
+        assert return_features
+        return FO.field_inputs(xyz, viewdirs, self.poses, self.focal, self.c, self.image_shape, self.encoder.latent,
+                               self.encoder.latent_scaling, self.code._freqs, self.code._phases, ns=1, features_only=True)

@@ -155,3 +155,53 @@ def test_march_falls_back_for_an_arbitrary_field(dev):
     phi = TinyFeatureField(32, seed=4).to(dev)
     ren = avr_b200.AdaptiveVolumeRenderer(32, raymarch_steps=2, epsilon=0.15, n_coarse=20, white_back=True).to(dev)
     assert not avr_b200.march.march_supported(phi, ren.lstm, ren.out_layer)
+
+
+@pytest.mark.parametrize("ch", [256, 512])
+def test_march_at_pixelnerf_channel_counts(ch, dev):
+    """conf/default.conf's 512 feature channels (and 256): the kernel against the SAME loop run by torch
+    on the GPU (fused front-end kernel for the features, torch's LSTMCell / Linear / autograd for the
+    rest — an independent implementation of everything the march kernels add), forward and every
+    gradient, with the fp64 CPU oracle as the yardstick for how far two fp32 runs may drift."""
+    import copy
+
+    import avr_b200
+    from field_stub import MapField
+    sb, r, steps = 2, 96, 5
+    cam2world, images, ros, rds, init = _scene(sb, r, seed=40)
+    phi = MapField(sb, ch, seed=41)
+    phi64 = copy.deepcopy(phi).double()
+    lstm, out_layer = _head(ch, seed=42, gain=2.0)
+    lstm64, out64 = copy.deepcopy(lstm).double(), copy.deepcopy(out_layer).double()
+    g_out = torch.randn(sb, r, 3, generator=torch.Generator().manual_seed(43))
+    # fp64 and fp32 oracle runs on the CPU
+    phi.place(cam2world[:, 0], 36.0)
+    world32 = O.lstm_march(ros, rds, init, phi, lstm, out_layer, steps)
+    (world32 * g_out).sum().backward()
+    phi64.place(cam2world[:, 0].double(), 36.0)
+    phi64.encoder.latent_scaling = phi64.encoder.latent_scaling.double()
+    phi64.image_shape, phi64.focal, phi64.c = phi64.image_shape.double(), phi64.focal.double(), phi64.c.double()
+    world64 = O.lstm_march(ros.double(), rds.double(), init.double(), phi64, lstm64, out64, steps)
+    (world64 * g_out.double()).sum().backward()
+    # the kernels
+    phi_d, lstm_d, out_d = MapField(sb, ch, seed=41).to(dev), copy.deepcopy(lstm).to(dev), copy.deepcopy(out_layer).to(dev)
+    for p in list(lstm_d.parameters()) + list(out_d.parameters()):
+        p.grad = None
+    phi_d.place(cam2world[:, 0].to(dev), 36.0)
+    avr_b200.fuse_field_inputs(phi_d)
+    assert avr_b200.march.march_supported(phi_d, lstm_d, out_d)
+    got = avr_b200.lstm_march(ros.to(dev), rds.to(dev), init.to(dev), phi_d, lstm_d, out_d, steps)
+    (got * g_out.to(dev)).sum().backward()
+
+    def held(got_t, ref32, ref64, what):
+        scale = max(ref64.abs().max().item(), 1e-12)
+        own = ((ref32.double() - ref64).abs().max() / scale).item()
+        err = ((got_t.detach().cpu().double() - ref64).abs().max() / scale).item()
+        assert err <= 4 * own + 2e-5, f"{what}: {err:.3g} of scale from fp64, the fp32 oracle {own:.3g}"
+
+    held(got, world32, world64, "world_coords[-1]")
+    for (k, p), (_, p32), (_, p64) in zip(list(lstm_d.named_parameters()) + list(out_d.named_parameters()),
+                                           list(lstm.named_parameters()) + list(out_layer.named_parameters()),
+                                           list(lstm64.named_parameters()) + list(out64.named_parameters())):
+        held(p.grad, p32.grad, p64.grad, f"grad {k}")
+    held(phi_d.map.grad, phi.map.grad, phi64.map.grad, "grad feature map (d_latent)")
