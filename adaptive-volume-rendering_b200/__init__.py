@@ -9,6 +9,7 @@ The kernels live in ``csrc/`` and are reached only through the C ABI in
 from ._lib import AvrError, LIB_PATH, load as load_library  # noqa: F401
 from .renderers import (  # noqa: F401
     AdaptiveVolumeRenderer,
+    Raymarcher,
     VolumeRenderer,
     sample_coarse,
     sample_depth,
@@ -22,7 +23,7 @@ from .field import FieldConfig, field_inputs, fuse_field_inputs  # noqa: F401
 from .dropin import accelerate, convert_renderer  # noqa: F401
 
 __all__ = [
-    "AdaptiveVolumeRenderer", "VolumeRenderer", "sample_coarse", "sample_depth", "sample_fine",
+    "AdaptiveVolumeRenderer", "Raymarcher", "VolumeRenderer", "sample_coarse", "sample_depth", "sample_fine",
     "volume_integral", "volume_integral_rgbs", "ops", "geometry", "field", "FieldConfig", "field_inputs",
     "fuse_field_inputs", "lstm_march", "march", "accelerate", "convert_renderer", "AvrError", "load_library", "LIB_PATH",
 ]

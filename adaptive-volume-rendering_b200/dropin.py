@@ -11,14 +11,19 @@ from __future__ import annotations
 
 from ._lib import AvrError
 from .field import fuse_field_inputs
-from .renderers import AdaptiveVolumeRenderer, VolumeRenderer
+from .renderers import AdaptiveVolumeRenderer, Raymarcher, VolumeRenderer
 
 
 def convert_renderer(renderer):
     """The avr_b200 renderer equivalent to a reference ``VolumeRenderer`` (renderers.py:121-289) or
     ``AdaptiveVolumeRenderer`` (renderers.py:360-509) instance.  avr_b200 renderers pass through."""
-    if isinstance(renderer, (VolumeRenderer, AdaptiveVolumeRenderer)):
+    if isinstance(renderer, (VolumeRenderer, AdaptiveVolumeRenderer, Raymarcher)):
         return renderer
+    if all(hasattr(renderer, a) for a in ("lstm", "out_layer", "steps")) and not hasattr(renderer, "epsilon"):
+        new = Raymarcher(renderer.n_feature_channels, renderer.steps)       # renderers.py:292-358
+        new.lstm, new.out_layer = renderer.lstm, renderer.out_layer          # shared, not copied
+        new.train(renderer.training)
+        return new
     if all(hasattr(renderer, a) for a in ("lstm", "out_layer", "steps", "epsilon", "n_coarse")):
         new = AdaptiveVolumeRenderer(renderer.n_feature_channels, renderer.steps, renderer.epsilon, renderer.n_coarse,
                                      renderer.white_back)

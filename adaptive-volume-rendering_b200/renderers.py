@@ -194,6 +194,67 @@ def _forget_gate_init(cell: nn.LSTMCell):
             p.data[n // 4: n // 2].fill_(1.0)
 
 
+def _lstm_march(module, ros, rds, init, phi):
+    """The LSTM ray march shared by ``Raymarcher`` (renderers.py:313-351) and ``AdaptiveVolumeRenderer``
+    (:415-435): one persistent kernel when ``phi``'s feature fetch is the front-end kernels'
+    (``fuse_field_inputs``, one source view per object); otherwise — an arbitrary ``phi`` callable —
+    the reference's loop around ``phi``."""
+    from . import march as _march
+
+    sb, num_rays, _ = ros.shape
+    if module.fused_march and _march.march_supported(phi, module.lstm, module.out_layer):
+        return _march.lstm_march(ros, rds, init, phi, module.lstm, module.out_layer, module.steps)
+    world = ros + rds * init
+    state = None
+    for _ in range(module.steps):
+        v = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), return_features=True)
+        state = module.lstm(v.reshape(-1, module.n_feature_channels), state)
+        if state[0].requires_grad:
+            state[0].register_hook(lambda x: x.clamp(min=-10, max=10))
+        signed_distance = module.out_layer(state[0]).view(sb, num_rays, 1)
+        world = world + rds * signed_distance
+    return world
+
+
+class Raymarcher(nn.Module):
+    """The reference's LSTM sphere tracer (renderers.py:292-358): march, then colour and depth at the
+    point reached — no sampling, no compositing.  Same constructor, ``from_conf(conf, raymarch_steps)``
+    and 4-tuple ``(rgb, None, depth, depth)``; parameters ``lstm.*`` / ``out_layer.*`` as in the
+    reference, so checkpoints load."""
+
+    def __init__(self, num_feature_channels, raymarch_steps):
+        super().__init__()
+        self.n_feature_channels = num_feature_channels
+        self.steps = raymarch_steps
+        hidden_size = 16
+        self.lstm = nn.LSTMCell(input_size=self.n_feature_channels, hidden_size=hidden_size)
+        _init_recurrent_weights(self.lstm)
+        _forget_gate_init(self.lstm)
+        self.out_layer = nn.Linear(hidden_size, 1)
+        self.counter = 0
+        self.fused_march = True
+
+    def forward(self, cam2world, intrinsics, xy_pix, phi, draws: Optional[Sequence[torch.Tensor]] = None):
+        sb, num_rays, _ = xy_pix.shape
+        if not xy_pix.is_cuda:
+            raise AvrError("Raymarcher (avr_b200) needs CUDA inputs; there is no CPU fallback")
+        ros, rds = get_world_rays(xy_pix, intrinsics=intrinsics, cam2world=cam2world)      # :318
+        if draws is None:       # :320 draws on the CPU generator
+            init = torch.zeros((sb, num_rays, 1)).normal_(mean=0.8, std=5e-2).to(xy_pix.device)
+        else:
+            (init,) = draws
+        world = _lstm_march(self, ros, rds, init, phi)                                      # :321-343
+        self.counter += 1
+        out = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), coarse=True, return_features=False)  # :346
+        rgb = out[..., :3].reshape(sb, num_rays, 3)
+        final_depth = depth_from_world(world, cam2world).reshape(sb, num_rays, -1)          # :349
+        return rgb, None, final_depth, final_depth
+
+    @classmethod
+    def from_conf(cls, conf, raymarch_steps):
+        return cls(num_feature_channels=conf.get_int("num_feature_channels", 512), raymarch_steps=raymarch_steps)
+
+
 class AdaptiveVolumeRenderer(nn.Module):
     """LSTM ray-march to a surface estimate d, then a thin stratified slab [d-eps, d+eps]
     composited with the fused kernels.  The march (renderers.py:411-435)
@@ -256,24 +317,8 @@ class AdaptiveVolumeRenderer(nn.Module):
         return rgb_coarse, rgb, depth_coarse, depth
 
     def march(self, ros, rds, init, phi):
-        """The LSTM ray march (renderers.py:415-435): one persistent kernel when ``phi``'s feature
-        fetch is the front-end kernels' (``fuse_field_inputs``, one source view per object);
-        otherwise — an arbitrary ``phi`` callable — the reference's loop around ``phi``."""
-        from . import march as _march
-
-        sb, num_rays, _ = ros.shape
-        if self.fused_march and _march.march_supported(phi, self.lstm, self.out_layer):
-            return _march.lstm_march(ros, rds, init, phi, self.lstm, self.out_layer, self.steps)
-        world = ros + rds * init
-        state = None
-        for _ in range(self.steps):
-            v = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), return_features=True)
-            state = self.lstm(v.reshape(-1, self.n_feature_channels), state)
-            if state[0].requires_grad:
-                state[0].register_hook(lambda x: x.clamp(min=-10, max=10))
-            signed_distance = self.out_layer(state[0]).view(sb, num_rays, 1)
-            world = world + rds * signed_distance
-        return world
+        """The LSTM ray march (renderers.py:415-435), see ``_lstm_march``."""
+        return _lstm_march(self, ros, rds, init, phi)
 
     @classmethod
     def from_conf(cls, conf, white_back=False):

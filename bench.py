@@ -421,6 +421,17 @@ def measure_other_configs(dev, peak, lib):
         return res
     guarded("c3_importance_64_to_128", c3)
 
+    # the north-star sentence as one number: every kernel of a VolumeRenderer render (sampling + compositing,
+    # forward and backward, conf/default.conf's 64 + 16 + 16 samples) over 2^20 rays (tools/bench_dense_pipeline.py)
+    def dense():
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_dense_pipeline
+        recs = list(bench_dense_pipeline.run(1 << 20, 3, dev, warm=1))
+        res = {rec["stage"]: {k: rec[k] for k in ("ms", "GBps", "hbm_frac")} for rec in recs if "stage" in rec}
+        res["pipeline"] = {k: v for k, v in recs[-1].items() if k != "pipeline"}
+        return res
+    guarded("sample_plus_composite_pipeline_2^20_rays_64+32", dense)
+
     # config 4: the whole ragged pipeline, 2^22 rays with 8..256 samples (tools/bench_packed_pipeline.py)
     def c4():
         sys.path.insert(0, os.path.join(ROOT, "tools"))

@@ -273,6 +273,40 @@ def case_adaptive_march(ref):
          **{"ref_phi_grad_" + k.replace(".", "__"): p.grad.clone() for k, p in phi.named_parameters()})
 
 
+def case_raymarcher(ref):
+    """The reference's Raymarcher (renderers.py:292-358: the LSTM march, then colour and depth at the point
+    reached) around the same kind of field as case_adaptive_march: outputs and the gradients of the LSTM
+    head, of the encoder (through the feature map) and of the coarse MLP."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    from field_stub import StubNet
+    sb, r, steps = 2, 33, 5
+    cam2world, intrinsics, x_pix = camera_setup(sb, r, seed=23)
+    torch.manual_seed(24)
+    phi = StubNet()
+    g = torch.Generator().manual_seed(25)
+    images = torch.rand(sb, 1, 3, 20, 16, generator=g) * 2 - 1
+    src_pose = cam2world[:, :1].clone()
+    phi.encode(images, src_pose, 22.0)
+    torch.manual_seed(26)
+    ren = ref.Raymarcher(128, steps)
+    with torch.no_grad():
+        ren.out_layer.weight.mul_(3.0)
+    state = {k: v.clone() for k, v in ren.state_dict().items()}
+    torch.manual_seed(52)
+    rgb, none, depth, depth2 = ren(cam2world, intrinsics, x_pix, phi)
+    assert none is None and depth is depth2
+    loss = ((rgb - 0.3) ** 2).mean() + 0.1 * depth.mean()
+    loss.backward()
+    torch.manual_seed(52)
+    init = torch.zeros((sb, r, 1)).normal_(mean=0.8, std=5e-2)            # renderers.py:320
+    save("raymarcher", cam2world=cam2world, intrinsics=intrinsics, x_pix=x_pix, images=images, src_pose=src_pose,
+         focal=22.0, init_distance=init, steps=steps, ref_rgb=rgb, ref_depth=depth, ref_loss=loss.detach(),
+         **{"state_" + k.replace(".", "__"): v for k, v in state.items()},
+         **{"phi_" + k.replace(".", "__"): v.clone() for k, v in phi.state_dict().items()},
+         **{"ref_grad_" + k.replace(".", "__"): p.grad.clone() for k, p in ren.named_parameters()},
+         **{"ref_phi_grad_" + k.replace(".", "__"): p.grad.clone() for k, p in phi.named_parameters() if p.grad is not None})
+
+
 def case_geometry(ref):
     """utils.get_world_rays / depth_from_world and the point generation of renderers.py:171-175,
     run by the reference's own utils module (star-imported into renderers, renderers.py:1)."""
@@ -481,6 +515,7 @@ def main():
     case_volume_renderer(ref)
     case_adaptive_renderer(ref)
     case_adaptive_march(ref)
+    case_raymarcher(ref)
     case_geometry(ref)
     case_pixelnerf_replay(ref)
     case_field_inputs(ref)

@@ -205,3 +205,44 @@ def test_march_at_pixelnerf_channel_counts(ch, dev):
                                            list(lstm64.named_parameters()) + list(out64.named_parameters())):
         held(p.grad, p32.grad, p64.grad, f"grad {k}")
     held(phi_d.map.grad, phi.map.grad, phi64.map.grad, "grad feature map (d_latent)")
+
+
+def test_raymarcher_golden(dev):
+    """The reference's third renderer, Raymarcher (renderers.py:292-358), as a drop-in on the march
+    kernels: outputs, the 4-tuple's shape conventions, parameter names and gradients against a fixture
+    the reference's own class produced (oracle/make_golden.py case_raymarcher)."""
+    import avr_b200
+    from ref_shim import Conf
+    g = load_golden("raymarcher")
+    steps = int(g["steps"])
+    phi = StubNet()
+    phi.load_state_dict({k[len("phi_"):].replace("__", "."): v for k, v in g.items() if k.startswith("phi_")})
+    phi = phi.to(dev)
+    avr_b200.fuse_field_inputs(phi)
+    ren = avr_b200.Raymarcher.from_conf(Conf(num_feature_channels=128), steps)
+    state = {k[len("state_"):].replace("__", "."): v for k, v in g.items() if k.startswith("state_")}
+    assert sorted(state) == sorted(ren.state_dict().keys())
+    ren.load_state_dict(state)
+    ren = ren.to(dev)
+    for fused in (True, False):
+        ren.fused_march = fused
+        for p in list(ren.parameters()) + list(phi.parameters()):
+            p.grad = None
+        phi.encode(g["images"].to(dev), g["src_pose"].to(dev), float(g["focal"]))
+        rgb, none, depth, depth2 = ren(g["cam2world"].to(dev), g["intrinsics"].to(dev), g["x_pix"].to(dev), phi,
+                                       draws=(g["init_distance"].to(dev),))
+        assert none is None and depth is depth2 and depth.shape == g["ref_depth"].shape
+        assert_close(rgb, g["ref_rgb"], rtol=1e-4, atol=1e-5, what="rgb")
+        assert_close(depth, g["ref_depth"], rtol=1e-4, atol=2e-5, what="depth")
+        loss = ((rgb - 0.3) ** 2).mean() + 0.1 * depth.mean()
+        assert abs(loss.item() - g["ref_loss"].item()) < 1e-5
+        loss.backward()
+        for k, p in ren.named_parameters():
+            ref = g["ref_grad_" + k.replace(".", "__")]
+            scale = max(ref.abs().max().item(), 1e-9)
+            assert_close(p.grad.cpu() / scale, ref / scale, rtol=1e-3, atol=5e-3, what=f"grad {k} (fused={fused})")
+        for k, p in phi.named_parameters():
+            key = "ref_phi_grad_" + k.replace(".", "__")
+            if key in g:
+                scale = max(g[key].abs().max().item(), 1e-9)
+                assert_close(p.grad.cpu() / scale, g[key] / scale, rtol=1e-3, atol=5e-3, what=f"phi grad {k} (fused={fused})")

@@ -102,6 +102,11 @@ def test_accelerate_switches_a_reference_model():
     assert isinstance(a, avr_b200.AdaptiveVolumeRenderer) and a.lstm is aren.lstm and a.out_layer is aren.out_layer
     assert (a.steps, a.epsilon, a.n_coarse, a.white_back, a.n_feature_channels) == (10, 0.15, 20, True, 512)
     assert model2.rf.forward.__func__.__name__ == "forward"             # untouched with fuse_field=False
+    # the third renderer, Raymarcher (renderers.py:292-358): same treatment
+    rm = ref.Raymarcher(512, 10)
+    m3 = avr_b200.convert_renderer(rm)
+    assert isinstance(m3, avr_b200.Raymarcher) and m3.lstm is rm.lstm and m3.out_layer is rm.out_layer and m3.steps == 10
+    assert sorted(m3.state_dict()) == sorted(rm.state_dict())
     # a field outside the kernels' family keeps its torch forward; the renderer is still switched
     other = models.make_new_model(conf)
     other.use_global_encoder = True
