@@ -127,3 +127,34 @@ def test_pixelnerf_replay_golden():
     assert_close(rc, g["ref_rgb_coarse"], what="rgb_coarse", **TIGHT)
     assert_close(rf, g["ref_rgb_fine"], what="rgb_fine", **TIGHT)
     assert_close(depth, g["ref_depth"], what="depth", rtol=2e-6, atol=5e-7)
+
+
+def test_raymarcher_golden_against_the_oracle_march():
+    """tests/golden/raymarcher.npz (the reference's Raymarcher, renderers.py:292-358) re-derived on the
+    CPU from oracle.lstm_march + the stub field: the fixture travels, and the oracle's loop is the
+    reference's (it is also pinned bit for bit where the reference can be imported)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from field_stub import StubNet
+    g = load_golden("raymarcher")
+    steps = int(g["steps"])
+    phi = StubNet()
+    phi.load_state_dict({k[len("phi_"):].replace("__", "."): v for k, v in g.items() if k.startswith("phi_")})
+    phi.encode(g["images"], g["src_pose"], float(g["focal"]))
+    lstm, out_layer = torch.nn.LSTMCell(128, 16), torch.nn.Linear(16, 1)
+    lstm.load_state_dict({k[len("state_lstm__"):]: v for k, v in g.items() if k.startswith("state_lstm__")})
+    out_layer.load_state_dict({k[len("state_out_layer__"):]: v for k, v in g.items() if k.startswith("state_out_layer__")})
+    ros, rds = O.world_rays(g["x_pix"], g["intrinsics"], g["cam2world"])
+    world = O.lstm_march(ros, rds, g["init_distance"], phi, lstm, out_layer, steps)
+    sb, r = g["x_pix"].shape[:2]
+    out = phi(world.reshape(sb, -1, 3), viewdirs=rds.reshape(sb, -1, 3), coarse=True, return_features=False)
+    rgb = out[..., :3].reshape(sb, r, 3)
+    depth = O.camera_depth(world, g["cam2world"]).reshape(sb, r, -1)
+    assert_close(rgb, g["ref_rgb"], rtol=2e-5, atol=2e-6, what="rgb")
+    assert_close(depth, g["ref_depth"], rtol=2e-5, atol=2e-6, what="depth")
+    (((rgb - 0.3) ** 2).mean() + 0.1 * depth.mean()).backward()
+    for mod, prefix in ((lstm, "lstm__"), (out_layer, "out_layer__")):
+        for name, p in mod.named_parameters():
+            ref = g["ref_grad_" + prefix + name]
+            scale = max(ref.abs().max().item(), 1e-9)
+            assert_close(p.grad / scale, ref / scale, rtol=1e-4, atol=2e-5, what=f"grad {prefix}{name}")
