@@ -1,9 +1,11 @@
 """CPU oracle for the ray-sampling + volume-compositing hot path.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is product code: only
-``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
-``--impl reference`` legs may import it, and only as the checker (or as the
-reported CPU baseline), never as the thing shipped.  The product path is the
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s baseline legs — the
+CPU baseline / ``--impl reference`` arm and the eager-GPU reference arm of
+``tools/bench_dropin.py`` (the reference's op sequence timed next to the
+kernels, as VERDICT r1 asked) — may import it, and only as the checker or as
+the reported baseline, never as the thing shipped.  The product path is the
 CUDA library behind ``include/avr_b200.h`` and fails loudly without it.
 
 What this is: a restatement, in plain torch-CPU ops, of the algorithm in the
