@@ -39,7 +39,7 @@ namespace avr {
 // ---- forward, any K (several boundaries per run possible) ----------------------------
 template <int L, bool kWriteW>
 __device__ __forceinline__ void fwd_tile_general(const SpanArgs& a, const Run& run, const float4* rg, float* zs,
-                                                 int64_t ray_base, int lane) {
+                                                 int64_t ray_base, int lane, float4* gather_ring = nullptr) {
   const int K = a.K;
   float wl[L];
   float Tl = 1.0f;
@@ -70,7 +70,7 @@ __device__ __forceinline__ void fwd_tile_general(const SpanArgs& a, const Run& r
       zk = z_after;
       if (last) {
         if (seen_head) {  // ray lies entirely inside this run: finished here
-          store_ray(a, ray_base + ray, s);
+          store_ray(a, ray_base + ray, s, gather_ring);
         } else {
           first_seg = s;
           first_seg_ray = ray;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void fwd_tile_general(const SpanArgs& a, const Run& r
     t.b = s_in.b + T_in * first_seg.b;
     t.d = s_in.d + T_in * first_seg.d;
     t.a = s_in.a + T_in * first_seg.a;
-    store_ray(a, ray_base + first_seg_ray, t);
+    store_ray(a, ray_base + first_seg_ray, t, gather_ring);
   }
   if (kWriteW) {
     __syncwarp();
@@ -213,6 +213,11 @@ __device__ __forceinline__ void bwd_tile_general(const SpanArgs& a, const Run& r
 // =====================================================================================
 // Kernels: per-warp tile pipeline around the bodies.
 // =====================================================================================
+// byte offset of the gather rings in a forward CTA's dynamic shared memory (16-byte aligned)
+__host__ __device__ inline int gather_ring_offset(int warps, int stages, int stage_bytes) {
+  return (warps * stages * stage_bytes + warps * stages * 8 + 15) & ~15;
+}
+
 template <int L, int NS>
 struct WarpPipe {
   using Cfg = SpanCfg<L>;
@@ -262,6 +267,10 @@ composite_fwd_span_kernel(const SpanArgs a) {
   // addresses); with the fused all-gather each warp takes a contiguous block of tiles instead,
   // so that the rays it finishes are consecutive and leave for the peers in 512-byte stores
   const bool gather = a.n_peers > 0;
+  // gather mode: this warp's ring of finished rays (r,g,b,depth), behind the stages and their barriers
+  float4* gring = gather ? reinterpret_cast<float4*>(smem + gather_ring_offset(warps, NS, WarpPipe<L, NS>::Cfg::kStageBytes)) +
+                               warp * kGatherRing
+                         : nullptr;
   const int64_t gw = (int64_t)blockIdx.x * warps + warp, n_warps = (int64_t)gridDim.x * warps;
   const int64_t per_warp = (a.n_tiles + n_warps - 1) / n_warps;
   const int64_t first = gather ? gw * per_warp : gw;
@@ -297,9 +306,9 @@ composite_fwd_span_kernel(const SpanArgs a) {
     float* zs = pipe.z_stage(st) + run.s0;
     const int64_t ray_base = tile * a.rays_per_tile;
     if (kSimple) {
-      fwd_tile_simple<L, kWriteW>(a, run, rg, zs, ray_base, lane);
+      fwd_tile_simple<L, kWriteW>(a, run, rg, zs, ray_base, lane, gring);
     } else {
-      fwd_tile_general<L, kWriteW>(a, run, rg, zs, ray_base, lane);
+      fwd_tile_general<L, kWriteW>(a, run, rg, zs, ray_base, lane, gring);
     }
     if (kWriteW) {
       fence_proxy_async_smem();
@@ -315,7 +324,7 @@ composite_fwd_span_kernel(const SpanArgs a) {
       const int64_t done = ray_base + n_cur / K;
       const int64_t upto = (i + 1 == n_my) ? done : flushed + ((done - flushed) & ~(int64_t)31);  // whole 512-byte rows
       if (upto > flushed) {
-        flush_rays_to_peers(a, flushed, upto, lane);
+        flush_rays_to_peers(a, flushed, upto, lane, gring);
         flushed = upto;
       }
     }
@@ -462,7 +471,8 @@ bool span_plan(int64_t R, int K, const void* rgbs, const void* z, SpanPlan* plan
 template <typename KernelT>
 static int span_launch(KernelT kernel, int L, int stage_bytes, int stages, const SpanArgs& a, cudaStream_t stream) {
   const int warps = warps_per_cta(L);
-  const int smem_bytes = warps * stages * stage_bytes + warps * stages * 8;
+  const int smem_bytes = a.n_peers > 0 ? gather_ring_offset(warps, stages, stage_bytes) + warps * kGatherRing * 16
+                                       : warps * stages * stage_bytes + warps * stages * 8;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) {
     set_last_cuda_error(e);

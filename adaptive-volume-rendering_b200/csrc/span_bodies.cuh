@@ -151,23 +151,29 @@ __device__ __forceinline__ float scan_rev_exclusive(int lane, float A, float B) 
   return lane == 31 ? 0.f : q;
 }
 
-__device__ __forceinline__ void store_ray(const SpanArgs& a, int64_t ray, const Sums& t) {
+// `gather_ring` (fused all-gather only, else null): the warp's 64-entry shared-memory ring of finished rays,
+// indexed by ray & 63 — what flush_rays_to_peers forwards, so that the peer stores need no trip through L2.
+constexpr int kGatherRing = 64;
+__device__ __forceinline__ void store_ray(const SpanArgs& a, int64_t ray, const Sums& t, float4* gather_ring = nullptr) {
   const float bg = a.white_back ? 1.0f - t.a : 0.f;
   float* o3 = a.rgb + ray * 3;
-  o3[0] = t.r + bg;
-  o3[1] = t.g + bg;
-  o3[2] = t.b + bg;
-  a.depth[ray] = cam_depth(a.depth_affine, ray, t.d);
+  const float r = t.r + bg, g = t.g + bg, b = t.b + bg, d = cam_depth(a.depth_affine, ray, t.d);
+  o3[0] = r;
+  o3[1] = g;
+  o3[2] = b;
+  a.depth[ray] = d;
+  if (gather_ring) gather_ring[ray & (kGatherRing - 1)] = make_float4(r, g, b, d);
 }
 
-// rays [lo, hi) were finished (and stored to a.rgb / a.depth) by THIS warp: forward them to every
-// peer's gathered buffer, lanes <-> consecutive rays.  Reads bypass L1 (the values were just
-// written by other lanes of the warp; __syncwarp orders them).
-__device__ __forceinline__ void flush_rays_to_peers(const SpanArgs& a, int64_t lo, int64_t hi, int lane) {
+// rays [lo, hi) were finished by THIS warp (hi - lo <= 64, the ring's size): forward them to every peer's
+// gathered buffer, lanes <-> consecutive rays, from the warp's shared-memory ring (the first version re-read
+// them from global memory with ld.cg: a store -> L2 -> load round trip of ~1.5 us every ~11 tiles, 7 % of
+// the forward kernel).  __syncwarp orders the ring writes of the other lanes before the reads.
+__device__ __forceinline__ void flush_rays_to_peers(const SpanArgs& a, int64_t lo, int64_t hi, int lane,
+                                                    const float4* gather_ring) {
   __syncwarp();
   for (int64_t ray = lo + lane; ray < hi; ray += 32) {
-    const float4 v = make_float4(__ldcg(a.rgb + ray * 3), __ldcg(a.rgb + ray * 3 + 1), __ldcg(a.rgb + ray * 3 + 2),
-                                 __ldcg(a.depth + ray));
+    const float4 v = gather_ring[ray & (kGatherRing - 1)];
     if (a.peers_multicast) {
       // the switch replicates the store into every rank's buffer (this rank's included): 16 B per ray
       // leave the GPU instead of 16 B per ray and peer
@@ -227,7 +233,7 @@ __device__ __forceinline__ RayGrad load_ray_grad(const SpanArgs& a, int64_t ray)
 // whatever stale shared memory they read only reaches aggregates nobody consumes.
 template <int L, bool kWriteW>
 __device__ __forceinline__ void fwd_tile_simple(const SpanArgs& a, const Run& run, const float4* rg, float* zs,
-                                                int64_t ray_base, int lane) {
+                                                int64_t ray_base, int lane, float4* gather_ring = nullptr) {
   const int p = run.end_pos;
   float wl[L];
   float Tl = 1.0f;
@@ -275,7 +281,7 @@ __device__ __forceinline__ void fwd_tile_simple(const SpanArgs& a, const Run& ru
     t.b = s_in.b + T_in * A.b;
     t.d = s_in.d + T_in * A.d;
     t.a = s_in.a + T_in * A.a;
-    store_ray(a, ray_base + run.ray0, t);
+    store_ray(a, ray_base + run.ray0, t, gather_ring);
   }
   if (kWriteW) {
     __syncwarp();  // every lane has finished reading z from this stage
