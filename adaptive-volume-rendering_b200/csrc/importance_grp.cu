@@ -45,6 +45,16 @@ struct GrpCfg {
   static constexpr int BUF_FLOATS = (P > M + G * PAD ? P : M + G * PAD);
   static constexpr int BUF_STRIDE = BUF_FLOATS + 8;
   static constexpr unsigned kInf0 = ((EPC >= 32 ? 0xffffffffu : ((1u << EPC) - 1u)) & ~((1u << CW) - 1u));
+  // quad layout of the merged keys (dense rays): register i of lane g holds key (i >> 2)*4G + 4g + (i & 3).
+  // A group of four registers is +inf on every lane iff its 4G keys lie inside the padding [KC, P - M).
+  static constexpr int QG = 4 * G;
+  static constexpr unsigned quad_inf_mask() {
+    unsigned m = 0;
+    for (int hi = 0; hi * 4 < EPT; ++hi)
+      if (hi * QG >= KC && (hi + 1) * QG <= P - M) m |= 0xfu << (4 * hi);
+    return m;
+  }
+  static constexpr unsigned kInfQ = quad_inf_mask();
   // warps per CTA: as many as the static shared-memory limit (48 KiB) allows, at most 8
   static constexpr int SMEM_PER_WARP = RPW * (TREE_STRIDE + BUF_STRIDE) * 4;
   static constexpr int WARPS = (8 * SMEM_PER_WARP <= 48 * 1024) ? 8 : 4;
@@ -53,6 +63,7 @@ struct GrpCfg {
   static_assert(G == 8 || G == 16 || G == 32, "group width");
   static_assert((KC & (KC - 1)) == 0 && KC % G == 0 && NI % G == 0 && ND % G == 0, "shape must split evenly over the group");
   static_assert(EPT <= 32 && BUF_STRIDE % 4 == 0 && TREE_STRIDE % 4 == 0, "layout");
+  static constexpr bool kQuadOK = (EPT % 4 == 0 && KC % QG == 0 && (P - M) % 4 == 0 && TOTAL % 4 == 0 && (EPF % 4 == 0 || PAD == 0));
 };
 
 // shared-memory bitonic sort of P keys by the G lanes of a group (all groups of the warp in
@@ -111,6 +122,33 @@ __device__ __forceinline__ void store_consecutive(float* dst, const float (&src)
   }
 }
 
+// A row of N*G floats split over the G lanes of a group as 16-byte pieces dealt round-robin: lane g takes
+// pieces g, g + G, ... — every instruction touches G*16 CONTIGUOUS bytes per ray (one LSU wavefront per 128
+// bytes; a lane-blocked split of 32 bytes per lane costs two).  Which new sample a lane draws is free: they
+// are sorted afterwards; the exports below use the same split.
+template <int N>
+__device__ __forceinline__ void load_dealt(float (&dst)[N], const float* row, int g, int G, bool vec_ok) {
+  if (N % 4 == 0 && N > 4 && vec_ok) {
+#pragma unroll
+    for (int q = 0; q < N; q += 4) {
+      const float4 p = *reinterpret_cast<const float4*>(row + 4 * g + q * G);
+      dst[q] = p.x; dst[(q + 1) % N] = p.y; dst[(q + 2) % N] = p.z; dst[(q + 3) % N] = p.w;
+    }
+  } else {
+    load_consecutive<N>(dst, row + g * N, vec_ok);
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_dealt(float* row, const float (&src)[N], int g, int G, bool vec_ok) {
+  if (N % 4 == 0 && N > 4 && vec_ok) {
+#pragma unroll
+    for (int q = 0; q < N; q += 4)
+      *reinterpret_cast<float4*>(row + 4 * g + q * G) = make_float4(src[q], src[(q + 1) % N], src[(q + 2) % N], src[(q + 3) % N]);
+  } else {
+    store_consecutive<N>(row + g * N, src, vec_ok);
+  }
+}
+
 // The class of a packed ray for the ragged kernels below: the smallest (KC, NI) box that holds
 // its kc coarse and n new samples, or -1 (empty ray, or larger than the largest box: those
 // rays take importance_reg.cu's per-class kernels).
@@ -132,6 +170,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
   using C = GrpCfg<G, KC, NI, ND>;
   constexpr int RPW = C::RPW, NIL = C::NIL, NDL = C::NDL, EPF = C::EPF, CW = C::CW, EPT = C::EPT, EPC = C::EPC;
   constexpr int DEPTH = C::DEPTH, PAD = C::PAD, kGrpWarps = C::WARPS;
+  constexpr bool kQuad = !kRagged && C::kQuadOK;  // layout of the merged keys (sort_net.cuh: merge_net)
   static_assert(!kRagged || ND == 0, "the packed entry point has no depth samples");
   __shared__ __align__(16) float s_tree[kGrpWarps][RPW][C::TREE_STRIDE];
   __shared__ __align__(16) float s_buf[kGrpWarps][RPW][C::BUF_STRIDE];
@@ -203,14 +242,25 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     } else {
       load_consecutive<CW>(w, a.weights + r * KC + g * CW, a.vecw != 0);
       if (NIL > 0) {
-        load_consecutive<(NIL > 0 ? NIL : 1)>(uu, a.u + r * NI + g * NIL, a.vec4 != 0);
-        load_consecutive<(NIL > 0 ? NIL : 1)>(jj, a.u2 + r * NI + g * NIL, a.vec4 != 0);
+        load_dealt<(NIL > 0 ? NIL : 1)>(uu, a.u + r * NI, g, G, a.vec4 != 0);
+        load_dealt<(NIL > 0 ? NIL : 1)>(jj, a.u2 + r * NI, g, G, a.vec4 != 0);
       }
       if (do_sort) {
         if (NDL > 0) load_consecutive<(NDL > 0 ? NDL : 1)>(nn, a.normals + r * ND + g * NDL, a.vecz != 0);
-        const float* zrow = a.z_coarse + r * KC;
+        const float* zrow = a.z_coarse + r * KC;  // quads: merged position q = (i >> 2)*4G + 4g + (i & 3)
+        if (!kQuad) {
 #pragma unroll
-        for (int i = 0; i < CW; ++i) x[i] = zrow[i * G + g];  // striped: merged position q = i*G + g
+          for (int i = 0; i < CW; ++i) x[i] = zrow[i * G + g];  // striped: merged position q = i*G + g
+        } else if (a.vecz) {
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 p = *reinterpret_cast<const float4*>(zrow + (i >> 2) * C::QG + 4 * g);
+            x[i] = p.x; x[i + 1] = p.y; x[i + 2] = p.z; x[i + 3] = p.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) x[i] = zrow[(i >> 2) * C::QG + 4 * g + (i & 3)];
+        }
       }
     }
 
@@ -269,8 +319,8 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     // ---- 2. this lane's new samples -----------------------------------------------------------
     float v[EPF];
     if (NIL > 0) {
-      int32_t* irow = (!kRagged && a.idx && live) ? a.idx + r * NI + g * NIL : nullptr;
-      float* frow = (a.z_fine && live) ? a.z_fine + fbase + g * NIL : nullptr;
+      int32_t* irow = (!kRagged && a.idx && live) ? a.idx + r * NI : nullptr;           // dense: the row, dealt as u was
+      float* frow = (a.z_fine && live) ? a.z_fine + fbase + (kRagged ? g * NIL : 0) : nullptr;
       const float kcf = (float)kc;
       // node <- 2*node + (tree[node] <= u): after DEPTH probes node - KC counts the entries
       // cdf[1..KC-1] <= u; adding (cdf[KC] <= u) gives clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
@@ -313,8 +363,8 @@ importance_grp_kernel(const ImportanceRegArgs a) {
           if (!has) v[q] = CUDART_INF_F;  // padding of the class box
         }
       } else {
-        if (irow) store_consecutive<(NIL > 0 ? NIL : 1)>(reinterpret_cast<float*>(irow), reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(bins), a.vec4 != 0);
-        if (frow) store_consecutive<(NIL > 0 ? NIL : 1)>(frow, reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(v), a.vec4 != 0);
+        if (irow) store_dealt<(NIL > 0 ? NIL : 1)>(reinterpret_cast<float*>(irow), reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(bins), g, G, a.vec4 != 0);
+        if (frow) store_dealt<(NIL > 0 ? NIL : 1)>(frow, reinterpret_cast<const float(&)[NIL > 0 ? NIL : 1]>(v), g, G, a.vec4 != 0);
       }
     }
     if (!do_sort) return;
@@ -343,43 +393,85 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       }
     }
     __syncwarp();
+    // key index of register i: quads (dense rays) or striped (packed rays, whose rows have no alignment)
+    auto key_index = [&](const int i) -> int { return kQuad ? (i >> 2) * C::QG + 4 * g + (i & 3) : i * G + g; };
+    if (kQuad) {
+      // groups of four registers: wholly coarse (loaded above), wholly padding, or — from key P - M on — the
+      // new samples in descending order, read back 16 bytes at a time
 #pragma unroll
-    for (int i = CW; i < EPT; ++i) {
-      if (i < EPC) {
-        x[i] = CUDART_INF_F;
-      } else {
-        const int idx = (i - EPC) * G + g;          // position in the descending new-sample sequence
-        x[i] = buf[idx + (idx / EPF) * PAD];
+      for (int i = CW; i < EPT; i += 4) {
+        const int q0 = (i >> 2) * C::QG + 4 * g;
+        float4 p = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+        if (!((C::kInfQ >> i) & 1u) && q0 >= C::P - C::M) {
+          const int idx = q0 - (C::P - C::M);
+          p = *reinterpret_cast<const float4*>(buf + idx + (idx / EPF) * PAD);
+        }
+        x[i] = p.x; x[i + 1] = p.y; x[i + 2] = p.z; x[i + 3] = p.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = CW; i < EPT; ++i) {
+        if (i < EPC) {
+          x[i] = CUDART_INF_F;
+        } else {
+          const int idx = (i - EPC) * G + g;          // position in the descending new-sample sequence
+          x[i] = buf[idx + (idx / EPF) * PAD];
+        }
       }
     }
     // coarse depths must be ascending for the merge (they are when they come from sample_coarse)
     bool unsorted = false;
+    if (kQuad) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
-      const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], lane & ~(G - 1));
-      if (g == G - 1) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
-      if ((!kRagged || i * G + g + 1 < kc) && x[i] > nx) unsorted = true;
+      for (int i = 0; i < CW; i += 4) {
+        // inside the lane's four, then its last against the next lane's first (the group's last lane: against
+        // lane 0's first of the next group of registers)
+        unsorted = unsorted || x[i] > x[i + 1] || x[i + 1] > x[i + 2] || x[i + 2] > x[i + 3];
+        float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
+        if (i + 4 < CW) {
+          const float first_next = __shfl_sync(0xffffffffu, x[(i + 4 < CW) ? i + 4 : i], lane & ~(G - 1));
+          if (g == G - 1) nx = first_next;
+        } else if (g == G - 1) {
+          nx = CUDART_INF_F;
+        }
+        unsorted = unsorted || x[i + 3] > nx;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
+        const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], lane & ~(G - 1));
+        if (g == G - 1) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
+        if ((!kRagged || i * G + g + 1 < kc) && x[i] > nx) unsorted = true;
+      }
     }
     if (__any_sync(0xffffffffu, unsorted)) {
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) buf[i * G + g] = x[i];
+      for (int i = 0; i < EPT; ++i) buf[key_index(i)] = x[i];
       sort_smem_grp(buf, C::P, g, G);
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) x[i] = buf[i * G + g];
+      for (int i = 0; i < EPT; ++i) x[i] = buf[key_index(i)];
     } else {
-      merge_striped<EPT, C::kInf0, G>(x, sg);
+      merge_net<EPT, (kQuad ? C::kInfQ : C::kInf0), G, kQuad>(x, sg);
     }
 
-    // ---- 5. store the first TOTAL keys: each group writes 32-byte segments of its row -------------
+    // ---- 5. store the first TOTAL keys: G*16 contiguous bytes per ray and instruction (quads), 4G (striped)
     if (live) {
       float* out = a.z_sorted + (kRagged ? cbase + fbase : r * C::TOTAL);
       const int total = kRagged ? kc + n : C::TOTAL;
+      if (kQuad && a.vecz) {
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        const int q = i * G + g;
-        if (q < total) out[q] = x[i];
+        for (int i = 0; i < EPT; i += 4) {
+          const int q0 = (i >> 2) * C::QG + 4 * g;
+          if (q0 < total) *reinterpret_cast<float4*>(out + q0) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          const int q = key_index(i);
+          if (q < total) out[q] = x[i];
+        }
       }
     }
   };

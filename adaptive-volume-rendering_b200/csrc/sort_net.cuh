@@ -94,16 +94,23 @@ __device__ __forceinline__ void sort_blocked(float (&v)[EPF], const LaneSigns& s
   }
 }
 
-// Ascending bitonic merge of G*EPT keys, striped layout: key index q = i*G + (lane % G).
+// Ascending bitonic merge of G*EPT keys.  Two register layouts (g = lane % G):
+//   striped (kQuad == false): key index q = i*G + g                       — a load/store of register i covers
+//                             G consecutive floats per ray;
+//   quads   (kQuad == true):  key index q = (i >> 2)*4G + 4g + (i & 3)    — a lane owns groups of FOUR
+//                             consecutive keys, so rows move with 16-byte accesses (G*16 contiguous bytes per
+//                             ray and instruction: the fewest LSU wavefronts a row can cost).
+// Index bits from the top: the high register bits (lane-local compare-exchanges), the lane bits (shuffles,
+// signed domain), then — quads only — the two low register bits.
 // kInf0: bit i set = register i is known to hold +inf on every lane (padding); comparators
 // with such an input reduce to nothing or to a register move, resolved at compile time.
-template <int EPT, unsigned kInf0, int G = 32>
-__device__ __forceinline__ void merge_striped(float (&x)[EPT], const LaneSigns& sg) {
+template <int EPT, unsigned kInf0, int G, bool kQuad>
+__device__ __forceinline__ void merge_net(float (&x)[EPT], const LaneSigns& sg) {
   constexpr int kTop = ilog2_c(G) - 1;  // highest lane bit inside a group
+  constexpr int kLow = kQuad ? 4 : 1;   // register strides below this one come after the lane bits
+  static_assert(!kQuad || EPT % 4 == 0, "quads need whole groups of four registers");
   unsigned infm = kInf0;
-#pragma unroll
-  for (int stride = (G / 2) * EPT; stride >= G; stride >>= 1) {
-    const int istride = stride / G;
+  auto local_stage = [&](const int istride) {
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
       if ((i & istride) == 0) {
@@ -119,7 +126,9 @@ __device__ __forceinline__ void merge_striped(float (&x)[EPT], const LaneSigns& 
         }
       }
     }
-  }
+  };
+#pragma unroll
+  for (int istride = EPT / 2; istride >= kLow; istride >>= 1) local_stage(istride);
 #pragma unroll
   for (int b = kTop; b >= 0; --b) {
     const float f = (b == kTop) ? sg.s[kTop] : sg.s[b + 1] * sg.s[b];
@@ -136,6 +145,13 @@ __device__ __forceinline__ void merge_striped(float (&x)[EPT], const LaneSigns& 
   for (int i = 0; i < EPT; ++i) {
     if (!((infm >> i) & 1u)) x[i] *= sg.s[0];
   }
+#pragma unroll
+  for (int istride = kLow / 2; istride >= 1; istride >>= 1) local_stage(istride);
+}
+
+template <int EPT, unsigned kInf0, int G = 32>
+__device__ __forceinline__ void merge_striped(float (&x)[EPT], const LaneSigns& sg) {
+  merge_net<EPT, kInf0, G, false>(x, sg);
 }
 
 }  // namespace avr
