@@ -549,9 +549,10 @@ int launch_importance_grp_ragged(const ImportanceRegArgs& a, int max_coarse, int
 // VolumeRenderer.from_conf's defaults (32 coarse, 8 + 8, renderers.py:279-289).
 int launch_importance_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
   if (a.offsets) return AVR_ERR_UNSUPPORTED;
-  // lanes per ray: 16 for the 128-sample shape (64 registers -> 32 resident warps/SM beats the
-  // fewer shuffle stages of 8 lanes at 118 registers: 0.77 vs 0.83 ms for 2^20 rays on B200);
-  // 8 for the small shapes.  AVR_GRP_G=8|16 overrides (experiments).
+  // lanes per ray: 8 for every shape.  The kernel is bound by LSU wavefronts (shuffles, shared memory and
+  // global accesses share one data pipe per SM), and 8 lanes per ray need 84 shuffles per two rays of the
+  // 128-sample shape where 16 lanes need 128; that outweighs 127 registers / 16 resident warps against 64 / 32
+  // (0.653 vs 0.695 ms for 2^20 rays on B200).  AVR_GRP_G=8|16 overrides (experiments).
   const int force_g = option(OPT_GRP_G, 0);
   if (force_g == 32 && a.Kc == 64 && a.n_imp == 128 && a.n_depth == 0) return launch_grp<32, 64, 128, 0>(a, stream);
 #define AVR_GRP_CASE(G_, KC_, NI_, ND_)                                        \
@@ -560,7 +561,7 @@ int launch_importance_grp(const ImportanceRegArgs& a, cudaStream_t stream) {
     if (force_g == 16) return launch_grp<16, KC_, NI_, ND_>(a, stream);        \
     return launch_grp<G_, KC_, NI_, ND_>(a, stream);                           \
   }
-  AVR_GRP_CASE(16, 64, 128, 0)
+  AVR_GRP_CASE(8, 64, 128, 0)
   AVR_GRP_CASE(8, 64, 16, 16)
   AVR_GRP_CASE(8, 64, 16, 0)
   AVR_GRP_CASE(8, 64, 64, 0)
