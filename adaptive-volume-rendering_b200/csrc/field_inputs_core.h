@@ -384,7 +384,8 @@ AVR_FI void field_grad_reset(FieldGradCache<CPL>* c) {
 
 AVR_FI void field_atomic_add4(float* dst, const float* v) {
 #if defined(__CUDACC__)
-  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+  // a reduction (REDG: fire and forget), not an atomic with a discarded result (ATOM ... RZ still waits for L2's answer)
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 #else
   for (int i = 0; i < 4; ++i) dst[i] += v[i];
 #endif

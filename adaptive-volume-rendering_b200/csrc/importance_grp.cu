@@ -331,10 +331,26 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       int bins[NIL > 0 ? NIL : 1];
       const unsigned tbase = smem_u32(tree);
       const unsigned neg_base = 0u - tbase;
+      // With four or more draws per lane the first two probe levels come from registers: the root and its two
+      // children are read once per ray (three broadcast reads) instead of twice per draw — the kernel is bound by
+      // LSU wavefronts, and a select plus a compare is cheaper than a shared-memory round trip.
+      constexpr int kRegLevels = (NIL >= 4 && DEPTH >= 3) ? 2 : 0;
+      if (kRegLevels == 2) {
+        const float n1 = tree[1], n2 = tree[2], n3 = tree[3];
 #pragma unroll
-      for (int q = 0; q < NIL; ++q) node[q] = tbase + 4u;
+        for (int q = 0; q < NIL; ++q) {
+          const bool right = n1 <= uu[q];
+          const float c = right ? n3 : n2;
+          unsigned nd = right ? tbase + 24u : tbase + 16u;   // node 4 + 2*right ...
+          if (c <= uu[q]) nd += 4u;                           // ... + (child <= u)
+          node[q] = nd;
+        }
+      } else {
 #pragma unroll
-      for (int step = 0; step < DEPTH; ++step) {
+        for (int q = 0; q < NIL; ++q) node[q] = tbase + 4u;
+      }
+#pragma unroll
+      for (int step = kRegLevels; step < DEPTH; ++step) {
 #pragma unroll
         for (int q = 0; q < NIL; ++q) {
           float cv;

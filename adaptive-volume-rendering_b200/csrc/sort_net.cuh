@@ -31,6 +31,37 @@ __device__ __forceinline__ LaneSigns lane_signs(int lane) {
   return g;
 }
 
+// Ascending sort of a lane's own EPF keys by the smallest known comparator networks (5 / 19 / 60 compare-exchanges
+// for 4 / 8 / 16 keys: Knuth, TAOCP 3, section 5.3.4; the lane-local phases of a bitonic sort need 6 / 24 / 80).
+// Each list was checked over all 2^EPF zero-one inputs (tools/check_sort_nets.py).
+template <int EPF>
+__device__ __forceinline__ bool presort_lane(float (&v)[EPF]) {
+#define AVR_CE(a, b) cmp_swap_asc(v[a], v[b]);
+  if constexpr (EPF == 4) {
+    AVR_CE(0, 2) AVR_CE(1, 3) AVR_CE(0, 1) AVR_CE(2, 3) AVR_CE(1, 2)
+    return true;
+  } else if constexpr (EPF == 8) {
+    AVR_CE(0, 2) AVR_CE(1, 3) AVR_CE(4, 6) AVR_CE(5, 7) AVR_CE(0, 4) AVR_CE(1, 5) AVR_CE(2, 6) AVR_CE(3, 7)
+    AVR_CE(0, 1) AVR_CE(2, 3) AVR_CE(4, 5) AVR_CE(6, 7) AVR_CE(2, 4) AVR_CE(3, 5) AVR_CE(1, 4) AVR_CE(3, 6)
+    AVR_CE(1, 2) AVR_CE(3, 4) AVR_CE(5, 6)
+    return true;
+  } else if constexpr (EPF == 16) {
+    AVR_CE(0, 13) AVR_CE(1, 12) AVR_CE(2, 15) AVR_CE(3, 14) AVR_CE(4, 8) AVR_CE(5, 6) AVR_CE(7, 11) AVR_CE(9, 10)
+    AVR_CE(0, 5) AVR_CE(1, 7) AVR_CE(2, 9) AVR_CE(3, 4) AVR_CE(6, 13) AVR_CE(8, 14) AVR_CE(10, 15) AVR_CE(11, 12)
+    AVR_CE(0, 1) AVR_CE(2, 3) AVR_CE(4, 5) AVR_CE(6, 8) AVR_CE(7, 9) AVR_CE(10, 11) AVR_CE(12, 13) AVR_CE(14, 15)
+    AVR_CE(0, 2) AVR_CE(1, 3) AVR_CE(4, 10) AVR_CE(5, 11) AVR_CE(6, 7) AVR_CE(8, 9) AVR_CE(12, 14) AVR_CE(13, 15)
+    AVR_CE(1, 2) AVR_CE(3, 12) AVR_CE(4, 6) AVR_CE(5, 7) AVR_CE(8, 10) AVR_CE(9, 11) AVR_CE(13, 14)
+    AVR_CE(1, 4) AVR_CE(2, 6) AVR_CE(5, 8) AVR_CE(7, 10) AVR_CE(9, 13) AVR_CE(11, 14)
+    AVR_CE(2, 4) AVR_CE(3, 6) AVR_CE(9, 12) AVR_CE(11, 13)
+    AVR_CE(3, 5) AVR_CE(6, 8) AVR_CE(7, 9) AVR_CE(10, 12)
+    AVR_CE(3, 4) AVR_CE(5, 6) AVR_CE(7, 8) AVR_CE(9, 10) AVR_CE(11, 12)
+    AVR_CE(6, 7) AVR_CE(8, 9)
+    return true;
+  }
+#undef AVR_CE
+  return false;
+}
+
 // Full bitonic sort of G*EPF keys, blocked layout: key index e = (lane % G)*EPF + r.
 // All comparators point the same way (the lower index keeps the minimum): each merge phase
 // opens with a "mirror" step (e <-> e ^ (size-1)) instead of alternating directions, so the
@@ -40,8 +71,11 @@ template <int EPF, int G = 32>
 __device__ __forceinline__ void sort_blocked(float (&v)[EPF], const LaneSigns& sg) {
   constexpr int M = G * EPF;
   int cur = -1;  // lane bit whose sign pattern the keys carry; -1 = true values (compile-time after unrolling)
+  constexpr bool presorted = (EPF == 4 || EPF == 8 || EPF == 16);  // the phases up to size EPF, by a smaller network
+  presort_lane<EPF>(v);
 #pragma unroll
   for (int size = 2; size <= M; size <<= 1) {
+    if (presorted && size <= EPF) continue;
     // mirror step
     if (size <= EPF) {
 #pragma unroll

@@ -114,3 +114,15 @@ def test_accelerate_switches_a_reference_model():
     assert isinstance(model3.renderer, avr_b200.VolumeRenderer) and other.forward.__func__.__name__ == "forward"
     with pytest.raises(avr_b200.AvrError):
         avr_b200.convert_renderer(torch.nn.Linear(2, 2))
+
+
+def test_lane_local_sorting_networks_sort_every_zero_one_input():
+    """csrc/sort_net.cuh presort_lane: the 5 / 19 / 60-comparator networks, parsed out of the header."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import check_sort_nets
+    found = dict(check_sort_nets.networks())
+    assert sorted(found) == [4, 8, 16] and [len(found[n]) for n in (4, 8, 16)] == [5, 19, 60]
+    for n, net in found.items():
+        assert check_sort_nets.sorts(n, net)
