@@ -17,6 +17,7 @@ namespace avr {
 constexpr bool kFieldBwdPrefetchDefault = false;  // measured: 0.200 vs 0.147 ms (spills under the 168-register cap)
 constexpr bool kFieldStageDefault = false;  // measured: 0.127 ms staged vs 0.118 ms direct (L2 merges the half sectors)
 constexpr int kFieldWarps = 4;
+constexpr int kFieldBwdAsyncDepth = 4;  // rows of g_out a warp keeps in flight in the feature-map gradient kernel
 // consecutive rows per warp visit (samples of one ray, same view): 32 when the lanes share out the
 // per-row coordinate work, 16 otherwise
 template <bool kShare>
@@ -306,6 +307,77 @@ field_inputs_bwd_ring_kernel(const FieldInputsArgs a, int row_stride) {
   if (kLatent) field_grad_flush<N>(a, lane, &grads);
 }
 
+// Feature-map gradient with a DEEP private prefetch of g_out.  ncu's source page has the plain kernel waiting on
+// exactly one instruction, the first use of a row's g_out (half of all stall samples): a warp has one row
+// (2 KB) in flight, 10.5 resident warps per SM hold 23 KB against the ~30 KB that cover HBM's latency at full
+// rate, and registers for a second row do not exist under the 168-register cap.  Here every lane copies ITS OWN
+// pieces of the next kDepth - 1 rows into a per-warp shared-memory ring with cp.async (8-byte copies: rows of
+// g_out are only 8-byte aligned; the staged groups are 16-byte aligned) and reads them back itself — no
+// barrier, no mbarrier, no cross-lane traffic, no registers held by loads in flight.
+template <int CPL, bool kShare, int kDepth, int kMinBlocks>
+__global__ void __launch_bounds__(kFieldWarps * 32, kMinBlocks)
+field_inputs_bwd_latent_async_kernel(const FieldInputsArgs a, int row_stride) {
+  extern __shared__ __align__(16) unsigned char s_ring_raw[];
+  static_assert(CPL > 0 && kDepth >= 2, "ring of the cached channel counts");
+  constexpr int N = CPL;
+  constexpr int kChunk = FieldChunk<kShare>::value;
+  constexpr int kRow = 128 * CPL;  // floats of a staged row: the channels only
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(s_ring_raw) + (size_t)warp * kDepth * kRow;
+  const int64_t rows = a.NV * a.B;
+  const int64_t n_chunks = (rows + kChunk - 1) / kChunk;
+  const int64_t warps = (int64_t)gridDim.x * kFieldWarps;
+  const int64_t ch0 = blockIdx.x * (int64_t)kFieldWarps + warp;
+  const FieldLaneCode lc = field_lane_code(a, lane);
+  FieldTapCache<N> taps;
+  FieldGradCache<N> grads;
+  FieldView view;
+  field_cache_reset(&taps);
+  field_grad_reset(&grads);
+  field_view_reset(&view);
+  // the k-th row this warp visits (only the very last chunk can be short, and nothing follows it)
+  auto issue = [&](const int64_t k) {
+    const int64_t chunk = ch0 + (k / kChunk) * warps;
+    const int64_t row = chunk * kChunk + (k % kChunk);
+    if (chunk < n_chunks && row < rows) {
+      const float* src = a.g_out + row * row_stride + 4 * lane;
+      const uint32_t dst = smem_u32(ring + (size_t)(k % kDepth) * kRow + 4 * lane);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 512u * i), "l"(src + 128 * i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 512u * i + 8u), "l"(src + 128 * i + 2) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // an empty group keeps the count uniform
+  };
+#pragma unroll
+  for (int j = 0; j < kDepth - 1; ++j) issue(j);
+  int64_t k = 0;
+  for (int64_t ch = ch0; ch < n_chunks; ch += warps) {
+    const int64_t first = ch * kChunk;
+    const int n = (int)(first + kChunk < rows ? kChunk : rows - first);
+    FieldPoint mine;
+    if (kShare) mine = point_of_my_row(a, first, lane, rows, &view);
+    FieldCursor cur = field_cursor_at(a, first);
+    for (int r = 0; r < n; ++r, ++k, field_cursor_next(a, &cur)) {
+      issue(k + kDepth - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory");
+      FieldPoint p;
+      if (kShare) {
+        p = point_from_lane<false>(mine, r);
+      } else {
+        field_view_fill(a, cur, &view);
+        p = field_point(a, cur, view);
+      }
+      FieldRowGrad<N> rg;
+      (void)field_bwd_row_lane<N, true, false, false, true>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads,
+                                                              ring + (size_t)(k % kDepth) * kRow);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  field_grad_flush<N>(a, lane, &grads);
+}
+
 // Experiment knobs (A/B measurements; defaults are what the measurements picked):
 //   AVR_FIELD_NOCACHE=1      every channel count takes the generic walk (no register caches)
 //   AVR_FIELD_BWD_SPLIT=0    feature-map and point gradients in ONE launch instead of two (234 registers,
@@ -351,9 +423,31 @@ static bool launch_bwd_ring(const FieldInputsArgs& a, int row_stride, cudaStream
   }
 }
 
+// feature-map gradient through the cp.async ring (AVR_FIELD_BWD_ASYNC=0: the plain kernel)
+template <int CPL, bool kShare>
+static bool launch_bwd_latent_async(const FieldInputsArgs& a, int row_stride, cudaStream_t stream) {
+  if constexpr (CPL == 0) {
+    return false;
+  } else {
+    // measured on B200 (2048 rays x 96 samples, 512 channels; profiles/r02_field_async.md): plain kernel 0.1458 ms;
+    // ring of 2 / 3 / 4 / 6 rows at three CTAs per SM (168 registers, ~100 B of spills) 0.135 / 0.140 / 0.137 /
+    // 0.151 ms; at two CTAs per SM (no spills) 3 / 4 / 6 / 8 rows: 0.131 / 0.125 / 0.131 / 0.128 ms -> 4 rows, two CTAs
+    if (!option(OPT_FIELD_BWD_ASYNC, 1) || (row_stride & 1) || (reinterpret_cast<uintptr_t>(a.g_out) & 7u)) return false;
+    constexpr int kDepth = kFieldBwdAsyncDepth;
+    auto kern = field_inputs_bwd_latent_async_kernel<CPL, kShare, kDepth, 2>;
+    const size_t smem = (size_t)kFieldWarps * kDepth * 128 * CPL * sizeof(float);
+    static_assert((size_t)kFieldWarps * kDepth * 128 * 4 * sizeof(float) <= 48 * 1024, "no opt-in shared memory needed");
+    kern<<<field_grid(a.NV * a.B, FieldChunk<kShare>::value), kFieldWarps * 32, smem, stream>>>(a, row_stride);
+    return true;
+  }
+}
+
 template <int CPL, bool kLatent, bool kPoint>
 static void launch_bwd_kernel(const FieldInputsArgs& a, int row_stride, bool share, cudaStream_t stream) {
   const unsigned t = kFieldWarps * 32;
+  if (kLatent && !kPoint &&
+      (share ? launch_bwd_latent_async<CPL, true>(a, row_stride, stream) : launch_bwd_latent_async<CPL, false>(a, row_stride, stream)))
+    return;
   if (!(share && field_bwd_prefetch()) &&
       (share ? launch_bwd_ring<CPL, kLatent, kPoint, true>(a, row_stride, stream)
              : launch_bwd_ring<CPL, kLatent, kPoint, false>(a, row_stride, stream)))

@@ -491,7 +491,8 @@ AVR_FI void field_load_row_grad(const FieldInputsArgs& a, int64_t row, int lane,
 // otherwise it is read here, group by group.
 // `g_row_in` (may be null): where the row of g_out is to be read from instead of global memory — the
 // shared-memory ring of the kernels that prefetch it with bulk copies (any address space).
-template <int CPL, bool kLatent, bool kPoint, bool kPreloaded>
+// kStaged16: `g_row_in` is a staged copy whose channel groups are 16-byte aligned (one LDS.128 per group).
+template <int CPL, bool kLatent, bool kPoint, bool kPreloaded, bool kStaged16 = false>
 AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldCursor& cur, const FieldPoint& p, int lane,
                                           int row_stride, const FieldLaneCode& lc, const FieldRowGrad<CPL>& rg,
                                           FieldTapCache<CPL>* taps, FieldGradCache<CPL>* grads,
@@ -525,6 +526,13 @@ AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldC
     float g[4];
     if (kPreloaded) {
       g[0] = rg.g[i][0]; g[1] = rg.g[i][1]; g[2] = rg.g[i][2]; g[3] = rg.g[i][3];
+    } else if (kStaged16) {
+#if defined(__CUDACC__)
+      const float4 gv = *reinterpret_cast<const float4*>(g_row + 4 * lane + 128 * i);
+      g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+#else
+      for (int q = 0; q < 4; ++q) g[q] = g_row[4 * lane + 128 * i + q];
+#endif
     } else if (g_row_in) {  // staged row (shared memory): ordinary 8-byte loads, one group at a time
       g[0] = g_row[4 * lane + 128 * i];
       g[1] = g_row[4 * lane + 128 * i + 1];

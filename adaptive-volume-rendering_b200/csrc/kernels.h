@@ -13,6 +13,7 @@ enum Opt {
   OPT_PACKED_SPAN, OPT_IMPORTANCE_GRP, OPT_PACKED_CLASSES, OPT_GRP_G,
   OPT_FIELD_NOCACHE, OPT_FIELD_BWD_SPLIT, OPT_FIELD_SHARE_POINT, OPT_FIELD_BWD_PREFETCH,
   OPT_FIELD_STAGE, OPT_IMPORTANCE_BINS, OPT_FIELD_BWD_RING, OPT_HOST_SLOTS, OPT_HOST_CHUNK_MIB,
+  OPT_FIELD_BWD_ASYNC,
   OPT_COUNT
 };
 int option(Opt o, int dflt);

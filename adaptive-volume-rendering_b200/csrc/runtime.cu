@@ -19,6 +19,7 @@ static const char* const kOptNames[OPT_COUNT] = {
     "AVR_PACKED_SPAN",     "AVR_IMPORTANCE_GRP",   "AVR_PACKED_CLASSES",     "AVR_GRP_G",
     "AVR_FIELD_NOCACHE",   "AVR_FIELD_BWD_SPLIT",  "AVR_FIELD_SHARE_POINT",  "AVR_FIELD_BWD_PREFETCH",
     "AVR_FIELD_STAGE",     "AVR_IMPORTANCE_BINS",  "AVR_FIELD_BWD_RING",    "AVR_HOST_SLOTS",         "AVR_HOST_CHUNK_MIB",
+    "AVR_FIELD_BWD_ASYNC",
 };
 constexpr int kUnset = INT_MIN;
 static std::atomic<int> g_opt[OPT_COUNT];

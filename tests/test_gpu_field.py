@@ -16,16 +16,19 @@ from field_stub import StubNet, ray_ordered_case
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["default", "no_ring", "ring_everywhere", "per_lane", "shared", "shared_staged", "shared_prefetch"])
+@pytest.fixture(autouse=True, params=["default", "no_ring", "ring_everywhere", "no_async", "per_lane", "shared", "shared_staged", "shared_prefetch"])
 def kernel_variant(request):
     """Every way the kernels are built (csrc/field_inputs.cu): a row's coordinate work done by each
     lane for itself or once per row and fetched by shuffles (AVR_FIELD_SHARE_POINT), output rows
     stored directly or staged in shared memory and sent by bulk copies (AVR_FIELD_STAGE), the next
-    row of g_out prefetched or not (AVR_FIELD_BWD_PREFETCH)."""
+    row of g_out prefetched or not (AVR_FIELD_BWD_PREFETCH), the feature-map gradient with its cp.async ring
+    for g_out (the default) or without (AVR_FIELD_BWD_ASYNC=0)."""
     from avr_b200 import _lib
-    knobs = ("AVR_FIELD_SHARE_POINT", "AVR_FIELD_STAGE", "AVR_FIELD_BWD_PREFETCH", "AVR_FIELD_BWD_RING")
+    knobs = ("AVR_FIELD_SHARE_POINT", "AVR_FIELD_STAGE", "AVR_FIELD_BWD_PREFETCH", "AVR_FIELD_BWD_RING", "AVR_FIELD_BWD_ASYNC")
     if request.param in ("no_ring", "ring_everywhere"):     # backward without / always with the bulk-copy ring for g_out
         _lib.set_option("AVR_FIELD_BWD_RING", 0 if request.param == "no_ring" else 2)
+    elif request.param == "no_async":
+        _lib.set_option("AVR_FIELD_BWD_ASYNC", 0)
     elif request.param != "default":        # "default": what the library picks by itself
         _lib.set_option("AVR_FIELD_SHARE_POINT", 0 if request.param == "per_lane" else 1)
         _lib.set_option("AVR_FIELD_STAGE", 1 if request.param == "shared_staged" else 0)
