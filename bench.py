@@ -426,7 +426,7 @@ def measure_other_configs(dev, peak, lib):
     def dense():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_dense_pipeline
-        recs = list(bench_dense_pipeline.run(1 << 20, 3, dev, warm=1))
+        recs = list(bench_dense_pipeline.run(1 << 20, 3, dev, warm=2))
         res = {rec["stage"]: {k: rec[k] for k in ("ms", "GBps", "hbm_frac")} for rec in recs if "stage" in rec}
         res["pipeline"] = {k: v for k, v in recs[-1].items() if k != "pipeline"}
         return res

@@ -86,6 +86,12 @@ def run(rays, iters, dev, warm=2):
         ("composite bwd, fine", s_bwd_f, r * (36 * k + 24)),
         ("composite bwd, coarse", s_bwd_c, r * (36 * kc + 12)),
     ]
+    # every stage drops its previous result BEFORE it runs, so the caching allocator hands the same block back
+    # (with two generations alive, a 1.2 - 2.4 GB result can cost a cudaMalloc inside the timed region: 53 ms
+    # instead of 0.48 ms for the fine points when this ran inside bench.py)
+    keys = (("ros", "rds", "aff", "z_c", "pts", "vd"), ("w_c",), ("z_s",), ("pts_f",), ("out",), ("dx_f",), ("dx_c",))
+    stages = [(name, (lambda fn=fn, ks=ks: ([st.pop(k_, None) for k_ in ks], fn())), nbytes)
+              for (name, fn, nbytes), ks in zip(stages, keys)]
     for _ in range(1 + warm):
         for _, fn, _ in stages:
             fn()
