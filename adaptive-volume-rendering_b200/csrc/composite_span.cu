@@ -333,7 +333,7 @@ composite_fwd_span_kernel(const SpanArgs a) {
   if (gather && a.n_signal > 0) signal_gather_done(a);
 }
 
-template <int L, int NS, bool kSimple, bool kDz>
+template <int L, int NS, bool kSimple, bool kDz, bool kCam = true>
 __global__ void __launch_bounds__(256)
 composite_bwd_span_kernel(const SpanArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -378,9 +378,9 @@ composite_bwd_span_kernel(const SpanArgs a) {
     // wait so their latency hides behind the tile load)
     RayGrad gA{0.f, 0.f, 0.f, 0.f, 0.f}, gB{0.f, 0.f, 0.f, 0.f, 0.f};
     if (run.nvalid > 0) {
-      gA = load_ray_grad(a, ray_base + run.ray0);
+      gA = load_ray_grad<kCam>(a, ray_base + run.ray0);
       const int ray_end = (run.s0 + run.nvalid - 1) / K;
-      gB = (ray_end != run.ray0) ? load_ray_grad(a, ray_base + ray_end) : gA;
+      gB = (ray_end != run.ray0) ? load_ray_grad<kCam>(a, ray_base + ray_end) : gA;
     }
     mbar_wait(&pipe.bars[st], (uint32_t)((i / NS) & 1));
     float4* rg = pipe.rgbs_stage(st) + run.s0;
@@ -512,6 +512,7 @@ template <int L, int NS>
 static int bwd_span_LN(const SpanArgs& a, bool simple, cudaStream_t stream) {
   constexpr int sb = SpanCfg<L>::kStageBytes;
   if (simple) {
+    if (!a.d_z && !a.depth_affine) return span_launch(composite_bwd_span_kernel<L, NS, true, false, false>, L, sb, NS, a, stream);
     return a.d_z ? span_launch(composite_bwd_span_kernel<L, NS, true, true>, L, sb, NS, a, stream)
                  : span_launch(composite_bwd_span_kernel<L, NS, true, false>, L, sb, NS, a, stream);
   }

@@ -358,8 +358,8 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
       const Run run = ragged_run(pipe.ends_stage(st), n_s, lane);
       RayGrad gA{0.f, 0.f, 0.f, 0.f, 0.f}, gB{0.f, 0.f, 0.f, 0.f, 0.f};
       if (run.nvalid > 0) {
-        gA = load_ray_grad(a.sp, cur.r0 + run.ray0);
-        gB = (run.end_pos >= 0 && run.end_pos + 1 < run.nvalid) ? load_ray_grad(a.sp, cur.r0 + run.ray0 + 1) : gA;
+        gA = load_ray_grad<false>(a.sp, cur.r0 + run.ray0);  // the packed entry points have no camera-depth map
+        gB = (run.end_pos >= 0 && run.end_pos + 1 < run.nvalid) ? load_ray_grad<false>(a.sp, cur.r0 + run.ray0 + 1) : gA;
       }
       float4* rg = pipe.rgbs_stage(st) + run.s0;
       float* zs = pipe.z_stage(st) + shift + run.s0;
