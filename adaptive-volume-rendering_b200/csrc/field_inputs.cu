@@ -335,32 +335,48 @@ field_inputs_bwd_latent_async_kernel(const FieldInputsArgs a, int row_stride) {
   field_cache_reset(&taps);
   field_grad_reset(&grads);
   field_view_reset(&view);
-  // the k-th row this warp visits (only the very last chunk can be short, and nothing follows it)
-  auto issue = [&](const int64_t k) {
-    const int64_t chunk = ch0 + (k / kChunk) * warps;
-    const int64_t row = chunk * kChunk + (k % kChunk);
-    if (chunk < n_chunks && row < rows) {
-      const float* src = a.g_out + row * row_stride + 4 * lane;
-      const uint32_t dst = smem_u32(ring + (size_t)(k % kDepth) * kRow + 4 * lane);
+  // prefetch cursor: the next row to request (rows of this warp's chunks, in the order it visits them), kept as a
+  // source pointer, a count of rows left in the cursor's chunk and a ring slot — no per-row index arithmetic
+  const float* pf_src = a.g_out + ch0 * kChunk * (int64_t)row_stride + 4 * lane;
+  const int64_t pf_jump = ((warps - 1) * kChunk) * (int64_t)row_stride;  // from the end of a chunk to this warp's next one
+  int64_t pf_chunk = ch0;
+  auto rows_in = [&](const int64_t chunk) -> int {
+    if (chunk >= n_chunks) return 0;
+    const int64_t first = chunk * kChunk;
+    return (int)(first + kChunk < rows ? kChunk : rows - first);
+  };
+  int pf_left = rows_in(pf_chunk);
+  uint32_t pf_dst = smem_u32(ring + 4 * lane);
+  const uint32_t ring_lo = pf_dst, ring_hi = pf_dst + (uint32_t)(kDepth * kRow * sizeof(float));
+  auto issue = [&]() {
+    if (pf_left > 0) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 512u * i), "l"(src + 128 * i) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 512u * i + 8u), "l"(src + 128 * i + 2) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_dst + 512u * i), "l"(pf_src + 128 * i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_dst + 512u * i + 8u), "l"(pf_src + 128 * i + 2) : "memory");
+      }
+      pf_src += row_stride;
+      if (--pf_left == 0) {
+        pf_chunk += warps;
+        pf_src += pf_jump;
+        pf_left = rows_in(pf_chunk);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // an empty group keeps the count uniform
+    pf_dst += (uint32_t)(kRow * sizeof(float));             // the slot advances with every group, used or not
+    if (pf_dst == ring_hi) pf_dst = ring_lo;
   };
 #pragma unroll
-  for (int j = 0; j < kDepth - 1; ++j) issue(j);
-  int64_t k = 0;
+  for (int j = 0; j < kDepth - 1; ++j) issue();
+  const float* rd = ring;  // the slot of the row being consumed
   for (int64_t ch = ch0; ch < n_chunks; ch += warps) {
     const int64_t first = ch * kChunk;
     const int n = (int)(first + kChunk < rows ? kChunk : rows - first);
     FieldPoint mine;
     if (kShare) mine = point_of_my_row(a, first, lane, rows, &view);
     FieldCursor cur = field_cursor_at(a, first);
-    for (int r = 0; r < n; ++r, ++k, field_cursor_next(a, &cur)) {
-      issue(k + kDepth - 1);
+    for (int r = 0; r < n; ++r, field_cursor_next(a, &cur)) {
+      issue();
       asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory");
       FieldPoint p;
       if (kShare) {
@@ -370,8 +386,9 @@ field_inputs_bwd_latent_async_kernel(const FieldInputsArgs a, int row_stride) {
         p = field_point(a, cur, view);
       }
       FieldRowGrad<N> rg;
-      (void)field_bwd_row_lane<N, true, false, false, true>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads,
-                                                              ring + (size_t)(k % kDepth) * kRow);
+      (void)field_bwd_row_lane<N, true, false, false, true>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads, rd);
+      rd += kRow;
+      if (rd == ring + kDepth * kRow) rd = ring;
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
