@@ -44,7 +44,7 @@ UNIT = "rays/s"
 
 # (rays, K) -> DRAM bytes per launch of composite_bwd_span_kernel<9,3> from the committed ncu --set full
 # capture (dram__bytes_read.sum + dram__bytes_write.sum; raw CSV under profiles/)
-NCU_TRAFFIC_BWD = {(1 << 20, 96): {"bytes": 2.031426e9 + 1.565985e9, "source": "profiles/r02_ncu_span.raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, composite_bwd_span_kernel<9,3,1,0>)"}}
+NCU_TRAFFIC_BWD = {(1 << 20, 96): {"bytes": 2.030070e9 + 1.564075e9, "source": "profiles/r02_ncu_span_final.raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, composite_bwd_span_kernel<9,3,1,0,0>)"}}
 
 WORKLOADS = {
     # name: (rays per GPU, samples per ray, description)
