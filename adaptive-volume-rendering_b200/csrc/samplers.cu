@@ -561,7 +561,9 @@ int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t*
   const int P = next_pow2(K);
   const int smem = kSamplerWarps * 2 * P * (int)sizeof(float);
   if (K % 4 == 0 && K <= 128 && aligned16(z_in) && aligned16(z_out) && aligned16(perm)) {
-    sort_rays_presorted_kernel<<<grid_for(R, kSamplerWarps * 32, num_sms() * 8), kSamplerWarps * 32, smem, stream>>>(
+    // a short streaming kernel: as many resident warps as the registers allow (48 -> 40 per SM), each with one
+    // 512-byte load in flight
+    sort_rays_presorted_kernel<<<grid_for(R, kSamplerWarps * 32, num_sms() * 16), kSamplerWarps * 32, smem, stream>>>(
         z_in, R, K, P, z_out, perm);
     return check_launch();
   }
