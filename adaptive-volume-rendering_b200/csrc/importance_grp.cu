@@ -1,18 +1,25 @@
-// Importance sampler + merge for the hot dense shapes, G = 8 lanes per ray (four rays per warp).
+// Importance sampler + merge for the hot dense shapes and the packed ray classes, G = 8 / 16 / 32 lanes per ray
+// (four / two / one ray per warp).
 //
 // Same algorithm as importance_reg.cu (cdf scan -> inverse-CDF search -> jitter -> register
 // bitonic sort of the new samples -> one bitonic merge with the ascending coarse depths;
 // renderers.py:27-66, 255-258), re-mapped so that more of it is lane-local:
-//   * a lane owns KC/8 coarse bins and (NI+ND)/8 new samples, so 22 of the 28 compare-exchange
+//   * a lane owns KC/G coarse bins and (NI+ND)/G new samples, so at G = 8 22 of the 28 compare-exchange
 //     stages of a 128-key sort (and 5 of the 8 merge stages) are register-to-register; only
-//     the stages over the 3 lane bits inside a group need a shuffle;
+//     the stages over the lane bits inside a group need a shuffle;
 //   * the per-ray fixed work (sum, scan, running max, bounds, addressing) is issued once per
-//     FOUR rays;
+//     32/G rays;
 //   * the cdf is searched as a perfect binary tree over cdf[1..KC-1] (log2 KC probes, stored
 //     breadth-first so a probe step's nodes are contiguous) plus one compare against the last
-//     entry, which stays in a register.
-// The kernel is issue-bound, not memory-bound; see DESIGN.md section 3.3 for the instruction
-// budget.  Shapes are template constants; anything else takes importance_reg.cu.
+//     entry, which stays in a register; with four or more draws per lane the first two levels
+//     come from registers.
+// What limits the kernel is the SM's LSU data pipe — shuffles, shared-memory and global accesses share
+// it, one 128-byte wavefront per cycle — and, once that is relieved, issue slots and the ALU pipe
+// together (profiles/r02_lsu_wavefronts.md).  Hence: dense rows move as 16-byte pieces DEALT over a
+// ray's lanes (G*16 contiguous bytes per ray and instruction), the merged keys live in a layout
+// where a lane owns groups of four consecutive keys (sort_net.cuh: merge_net<..., kQuad>), and every
+// dense shape runs at 8 lanes per ray.  Shapes are template constants; anything else takes
+// importance_reg.cu.
 #include <math_constants.h>
 
 #include <cstdlib>
