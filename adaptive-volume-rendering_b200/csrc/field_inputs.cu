@@ -51,6 +51,33 @@ __device__ __forceinline__ FieldPoint point_from_lane(const FieldPoint& m, int s
   return p;
 }
 
+// Sum the eight partials of a row over the warp by a transposing butterfly: in each of the first three steps a
+// lane hands half of its values to its partner and keeps the other half (4 + 2 + 1 shuffles), two more steps add
+// up the four lanes that then hold the same value, eight broadcasts give every lane every total: 17 shuffles and
+// 9 additions where one butterfly per value takes 40 and 40.
+__device__ __forceinline__ void field_partial_reduce(FieldRowPartial* s, int lane) {
+  const unsigned full = 0xffffffffu;
+  const float v[8] = {s->gix, s->giy, s->enc0, s->enc1, s->enc2, s->vr0, s->vr1, s->vr2};
+  const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
+  float k4[4], k2[2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) k4[j] = (u4 ? v[j + 4] : v[j]) + __shfl_xor_sync(full, u4 ? v[j] : v[j + 4], 16);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) k2[j] = (u3 ? k4[j + 2] : k4[j]) + __shfl_xor_sync(full, u3 ? k4[j] : k4[j + 2], 8);
+  float x = (u2 ? k2[1] : k2[0]) + __shfl_xor_sync(full, u2 ? k2[0] : k2[1], 4);
+  x += __shfl_xor_sync(full, x, 2);
+  x += __shfl_xor_sync(full, x, 1);
+  // value 4*b4 + 2*b3 + b2 ended up on the lanes with those bits: value j on lane 4*j
+  s->gix = __shfl_sync(full, x, 0);
+  s->giy = __shfl_sync(full, x, 4);
+  s->enc0 = __shfl_sync(full, x, 8);
+  s->enc1 = __shfl_sync(full, x, 12);
+  s->enc2 = __shfl_sync(full, x, 16);
+  s->vr0 = __shfl_sync(full, x, 20);
+  s->vr1 = __shfl_sync(full, x, 24);
+  s->vr2 = __shfl_sync(full, x, 28);
+}
+
 // the point of row min(first + lane, rows - 1), with this lane's own view constants
 __device__ __forceinline__ FieldPoint point_of_my_row(const FieldInputsArgs& a, int64_t first, int lane, int64_t rows,
                                                       FieldView* view) {
@@ -178,17 +205,7 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
         s = field_bwd_row_lane_generic<kLatent, kPoint>(a, cur, p, lane, row_stride, lc);
       }
       if (kPoint) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          s.gix += __shfl_xor_sync(0xffffffffu, s.gix, d);
-          s.giy += __shfl_xor_sync(0xffffffffu, s.giy, d);
-          s.enc0 += __shfl_xor_sync(0xffffffffu, s.enc0, d);
-          s.enc1 += __shfl_xor_sync(0xffffffffu, s.enc1, d);
-          s.enc2 += __shfl_xor_sync(0xffffffffu, s.enc2, d);
-          s.vr0 += __shfl_xor_sync(0xffffffffu, s.vr0, d);
-          s.vr1 += __shfl_xor_sync(0xffffffffu, s.vr1, d);
-          s.vr2 += __shfl_xor_sync(0xffffffffu, s.vr2, d);
-        }
+        field_partial_reduce(&s, lane);
         if (lane == 0) {
           if (kShare) field_view_fill(a, cur, &view);  // lane 0's view is that of ITS row of the chunk
           field_bwd_row_finish(a, cur, view, p, s);
@@ -285,17 +302,7 @@ field_inputs_bwd_ring_kernel(const FieldInputsArgs a, int row_stride) {
           s = field_bwd_row_lane<N, kLatent, kPoint, false>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads);
         }
         if (kPoint) {
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) {
-            s.gix += __shfl_xor_sync(0xffffffffu, s.gix, d);
-            s.giy += __shfl_xor_sync(0xffffffffu, s.giy, d);
-            s.enc0 += __shfl_xor_sync(0xffffffffu, s.enc0, d);
-            s.enc1 += __shfl_xor_sync(0xffffffffu, s.enc1, d);
-            s.enc2 += __shfl_xor_sync(0xffffffffu, s.enc2, d);
-            s.vr0 += __shfl_xor_sync(0xffffffffu, s.vr0, d);
-            s.vr1 += __shfl_xor_sync(0xffffffffu, s.vr1, d);
-            s.vr2 += __shfl_xor_sync(0xffffffffu, s.vr2, d);
-          }
+          field_partial_reduce(&s, lane);
           if (lane == 0) {
             if (kShare) field_view_fill(a, cur, &view);
             field_bwd_row_finish(a, cur, view, p, s);

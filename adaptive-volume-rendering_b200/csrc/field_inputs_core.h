@@ -285,9 +285,10 @@ AVR_FI void field_store2(float* dst, float x, float y) {
 #endif
 }
 
+// returns true when the cache was (re)filled
 template <int CPL>
-AVR_FI void field_cache_fill(const FieldInputsArgs& a, const FieldPoint& p, int64_t v, int lane, FieldTapCache<CPL>* c) {
-  if (c->x0 == p.x0 && c->y0 == p.y0 && c->v == v) return;  // warp-uniform
+AVR_FI bool field_cache_fill(const FieldInputsArgs& a, const FieldPoint& p, int64_t v, int lane, FieldTapCache<CPL>* c) {
+  if (c->x0 == p.x0 && c->y0 == p.y0 && c->v == v) return false;  // warp-uniform
   c->x0 = p.x0;
   c->y0 = p.y0;
   c->v = v;
@@ -305,6 +306,32 @@ AVR_FI void field_cache_fill(const FieldInputsArgs& a, const FieldPoint& p, int6
       } else {
         c->t[k][i][0] = c->t[k][i][1] = c->t[k][i][2] = c->t[k][i][3] = 0.f;
       }
+    }
+  }
+  return true;
+}
+
+// The point gradient only needs the four tap DIFFERENCES of a cell,
+//   t[0] = ne - nw (along x, north edge), t[1] = se - sw (along x, south edge),
+//   t[2] = sw - nw (along y, west edge),  t[3] = se - ne (along y, east edge),
+// formed once per cell change instead of once per row (consecutive samples of a ray stay in a cell for
+// three rows out of four): the backward kernels keep those in the same registers.
+template <int CPL>
+AVR_FI void field_diff_fill(const FieldInputsArgs& a, const FieldPoint& p, int64_t v, int lane, FieldTapCache<CPL>* c) {
+  if (!field_cache_fill<CPL>(a, p, v, lane, c)) return;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < CPL; ++i) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) {
+      const float nw = c->t[0][i][q], ne = c->t[1][i][q], sw = c->t[2][i][q], se = c->t[3][i][q];
+      c->t[0][i][q] = ne - nw;
+      c->t[1][i][q] = se - sw;
+      c->t[2][i][q] = sw - nw;
+      c->t[3][i][q] = se - ne;
     }
   }
 }
@@ -501,7 +528,7 @@ AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldC
   FieldRowPartial s;
   field_partial_zero(&s);
   const float* g_row = g_row_in ? g_row_in : a.g_out + cur.row * row_stride;
-  if (kPoint) field_cache_fill<CPL>(a, p, v, lane, taps);
+  if (kPoint) field_diff_fill<CPL>(a, p, v, lane, taps);  // `taps` holds the cell's tap differences here
   if (kLatent && !(grads->x0 == p.x0 && grads->y0 == p.y0 && grads->v == v)) {  // warp-uniform
     field_grad_flush<CPL>(a, lane, grads);
     grads->x0 = p.x0;
@@ -519,6 +546,7 @@ AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldC
   // bilinear weights again, split into their factors for the coordinate gradient
   const float wx = fi_sub(p.ix, (float)p.x0), ex = fi_sub(1.0f, wx);
   const float wy = fi_sub(p.iy, (float)p.y0), sy = fi_sub(1.0f, wy);
+  float dxn = 0.f, dxs = 0.f, dyw = 0.f, dye = 0.f;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -552,12 +580,17 @@ AVR_FI FieldRowPartial field_bwd_row_lane(const FieldInputsArgs& a, const FieldC
         grads->acc[2][i][q] = fi_fma(g[q], p.sw, grads->acc[2][i][q]);
         grads->acc[3][i][q] = fi_fma(g[q], p.se, grads->acc[3][i][q]);
       }
-      if (kPoint) {
-        const float t_nw = taps->t[0][i][q], t_ne = taps->t[1][i][q], t_sw = taps->t[2][i][q], t_se = taps->t[3][i][q];
-        s.gix += g[q] * ((t_ne - t_nw) * sy + (t_se - t_sw) * wy);
-        s.giy += g[q] * ((t_sw - t_nw) * ex + (t_se - t_ne) * wx);
+      if (kPoint) {  // four sums over the channels; the row's bilinear factors multiply them once, below
+        dxn += g[q] * taps->t[0][i][q];
+        dxs += g[q] * taps->t[1][i][q];
+        dyw += g[q] * taps->t[2][i][q];
+        dye += g[q] * taps->t[3][i][q];
       }
     }
+  }
+  if (kPoint) {
+    s.gix = dxn * sy + dxs * wy;
+    s.giy = dyw * ex + dye * wx;
   }
   if (kPoint) field_code_grad_lane(lc, p, g_row + a.C, lane, &s);
   return s;
