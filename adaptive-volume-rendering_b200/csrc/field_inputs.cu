@@ -53,9 +53,10 @@ __device__ __forceinline__ FieldPoint point_from_lane(const FieldPoint& m, int s
 
 // Sum the eight partials of a row over the warp by a transposing butterfly: in each of the first three steps a
 // lane hands half of its values to its partner and keeps the other half (4 + 2 + 1 shuffles), two more steps add
-// up the four lanes that then hold the same value, eight broadcasts give every lane every total: 17 shuffles and
-// 9 additions where one butterfly per value takes 40 and 40.
-__device__ __forceinline__ void field_partial_reduce(FieldRowPartial* s, int lane) {
+// up the four lanes that then hold the same value: 9 shuffles and
+// 9 additions where one butterfly per value takes 40 and 40.  The totals of the row go to `row_totals[0..8)`
+// (shared memory; order gix, giy, enc0..2, vr0..2).
+__device__ __forceinline__ void field_partial_reduce(const FieldRowPartial* s, int lane, float* row_totals) {
   const unsigned full = 0xffffffffu;
   const float v[8] = {s->gix, s->giy, s->enc0, s->enc1, s->enc2, s->vr0, s->vr1, s->vr2};
   const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
@@ -67,15 +68,28 @@ __device__ __forceinline__ void field_partial_reduce(FieldRowPartial* s, int lan
   float x = (u2 ? k2[1] : k2[0]) + __shfl_xor_sync(full, u2 ? k2[0] : k2[1], 4);
   x += __shfl_xor_sync(full, x, 2);
   x += __shfl_xor_sync(full, x, 1);
-  // value 4*b4 + 2*b3 + b2 ended up on the lanes with those bits: value j on lane 4*j
-  s->gix = __shfl_sync(full, x, 0);
-  s->giy = __shfl_sync(full, x, 4);
-  s->enc0 = __shfl_sync(full, x, 8);
-  s->enc1 = __shfl_sync(full, x, 12);
-  s->enc2 = __shfl_sync(full, x, 16);
-  s->vr0 = __shfl_sync(full, x, 20);
-  s->vr1 = __shfl_sync(full, x, 24);
-  s->vr2 = __shfl_sync(full, x, 28);
+  // value 4*b4 + 2*b3 + b2 ended up on the lanes with those bits: value j on lanes 4j .. 4j+3
+  if ((lane & 3) == 0) row_totals[lane >> 2] = x;
+}
+
+// End of a chunk: lane l finishes row first + l (chain rule through the projection and the rigid transform,
+// atomics over the object's views) from the totals its row left in the warp's table — every lane at once, instead
+// of lane 0 alone after every row while 31 lanes wait.
+__device__ __forceinline__ void field_chunk_finish(const FieldInputsArgs& a, int64_t first, int n, int lane,
+                                                   float (*totals)[8], FieldView* view) {
+  __syncwarp();
+  if (lane < n) {
+    const float4 t0 = *reinterpret_cast<const float4*>(&totals[lane][0]);
+    const float4 t1 = *reinterpret_cast<const float4*>(&totals[lane][4]);
+    FieldRowPartial s;
+    s.gix = t0.x; s.giy = t0.y; s.enc0 = t0.z; s.enc1 = t0.w;
+    s.enc2 = t1.x; s.vr0 = t1.y; s.vr1 = t1.z; s.vr2 = t1.w;
+    const FieldCursor mc = field_cursor_at(a, first + lane);
+    field_view_fill(a, mc, view);
+    const FieldPoint mp = field_point(a, mc, *view);
+    field_bwd_row_finish(a, mc, *view, mp, s);
+  }
+  __syncwarp();  // the next chunk overwrites the table
 }
 
 // the point of row min(first + lane, rows - 1), with this lane's own view constants
@@ -167,6 +181,7 @@ field_inputs_fwd_kernel(const FieldInputsArgs a, int row_stride) {
 template <int CPL, bool kLatent, bool kPoint, bool kShare, bool kPre>
 __global__ void __launch_bounds__(kFieldWarps * 32, (kLatent && kPoint) ? 1 : 3)
 field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
+  __shared__ __align__(16) float s_tot[kPoint ? kFieldWarps : 1][32][8];  // per warp: the rows' reduced partial sums
   constexpr int N = CPL > 0 ? CPL : 1;
   constexpr int kChunk = FieldChunk<kShare>::value;
   const int lane = threadIdx.x & 31;
@@ -204,14 +219,9 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
       } else {
         s = field_bwd_row_lane_generic<kLatent, kPoint>(a, cur, p, lane, row_stride, lc);
       }
-      if (kPoint) {
-        field_partial_reduce(&s, lane);
-        if (lane == 0) {
-          if (kShare) field_view_fill(a, cur, &view);  // lane 0's view is that of ITS row of the chunk
-          field_bwd_row_finish(a, cur, view, p, s);
-        }
-      }
+      if (kPoint) field_partial_reduce(&s, lane, s_tot[threadIdx.x >> 5][r]);
     }
+    if (kPoint) field_chunk_finish(a, first, n, lane, s_tot[threadIdx.x >> 5], &view);
   }
   if (kLatent && CPL > 0) field_grad_flush<N>(a, lane, &grads);
 }
@@ -225,6 +235,7 @@ field_inputs_bwd_kernel(const FieldInputsArgs a, int row_stride) {
 template <int CPL, bool kLatent, bool kPoint, bool kShare>
 __global__ void __launch_bounds__(kFieldWarps * 32, (kLatent && kPoint) ? 1 : 3)
 field_inputs_bwd_ring_kernel(const FieldInputsArgs a, int row_stride) {
+  __shared__ __align__(16) float s_tot[kPoint ? kFieldWarps : 1][32][8];  // per warp: the rows' reduced partial sums
   extern __shared__ __align__(16) unsigned char s_ring_raw[];
   static_assert(CPL > 0, "ring kernels exist for the cached channel counts");
   constexpr int N = CPL;
@@ -301,15 +312,10 @@ field_inputs_bwd_ring_kernel(const FieldInputsArgs a, int row_stride) {
         } else {  // the single last row of all: straight from global memory
           s = field_bwd_row_lane<N, kLatent, kPoint, false>(a, cur, p, lane, row_stride, lc, rg, &taps, &grads);
         }
-        if (kPoint) {
-          field_partial_reduce(&s, lane);
-          if (lane == 0) {
-            if (kShare) field_view_fill(a, cur, &view);
-            field_bwd_row_finish(a, cur, view, p, s);
-          }
-        }
+        if (kPoint) field_partial_reduce(&s, lane, s_tot[warp][r]);
       }
     }
+    if (kPoint) field_chunk_finish(a, first, n, lane, s_tot[warp], &view);
   }
   if (kLatent) field_grad_flush<N>(a, lane, &grads);
 }
