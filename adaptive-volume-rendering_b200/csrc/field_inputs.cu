@@ -418,8 +418,8 @@ field_inputs_bwd_latent_async_kernel(const FieldInputsArgs a, int row_stride) {
 //   AVR_FIELD_BWD_RING=0     backward without the bulk-copy ring for g_out (see field_inputs_bwd_ring_kernel)
 static bool field_no_cache() { return option(OPT_FIELD_NOCACHE, 0) != 0; }
 static bool field_bwd_split() { return option(OPT_FIELD_BWD_SPLIT, 1) != 0; }
-// unset: the measured defaults (forward and feature-map backward share, the point backward does not:
-// 0.346 vs 0.362 ms); 0 / 1 force every kernel one way
+// unset: the measured defaults (every kernel shares; the point backward did not while lane 0 finished each row by
+// itself, 0.346 vs 0.362 ms — with the per-chunk finish sharing wins, 0.195 vs 0.218 ms); 0 / 1 force every kernel one way
 static bool field_share_point(bool dflt) { return option(OPT_FIELD_SHARE_POINT, dflt ? 1 : 0) != 0; }
 static bool field_bwd_prefetch() { return option(OPT_FIELD_BWD_PREFETCH, kFieldBwdPrefetchDefault ? 1 : 0) != 0; }
 static bool field_stage_rows() { return option(OPT_FIELD_STAGE, kFieldStageDefault ? 1 : 0) != 0; }
@@ -499,7 +499,7 @@ static void launch_bwd_variant(const FieldInputsArgs& a, int row_stride, cudaStr
     return;
   }
   if (latent) launch_bwd_kernel<CPL, true, false>(a, row_stride, field_share_point(true), stream);
-  if (point) launch_bwd_kernel<CPL, false, true>(a, row_stride, field_share_point(false), stream);
+  if (point) launch_bwd_kernel<CPL, false, true>(a, row_stride, field_share_point(true), stream);
 }
 
 int launch_field_inputs_bwd(const FieldInputsArgs& a, int64_t SB, cudaStream_t stream) {
