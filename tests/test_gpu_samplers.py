@@ -203,3 +203,37 @@ def test_importance_full_size_properties(dev):
     assert (zs[..., 1:] >= zs[..., :-1]).all()
     # exactly the sorted multiset of the inputs
     assert torch.equal(zs, torch.sort(torch.cat([zc, out["z_fine"]], -1), -1).values)
+
+
+@pytest.mark.parametrize("kc,n,nd", [(64, 128, 0), (64, 16, 16), (32, 8, 8)])
+def test_importance_unaligned_inputs_take_the_scalar_paths(kc, n, nd, dev):
+    """The hot dense shapes move their rows with 16-byte accesses when the pointers allow it; inputs that
+    start 4 bytes off a 16-byte boundary take the scalar loads / stores (and the lane-blocked split of the
+    draws) and must give the same bits."""
+    from avr_b200 import ops
+    g = torch.Generator().manual_seed(kc + n)
+    r = 301
+    near = torch.tensor([0.8], device=dev)
+    far = torch.tensor([1.8], device=dev)
+
+    def off(t):  # the same values in a contiguous tensor whose storage starts one float later
+        flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=dev)
+        flat[1:] = t.to(dev).reshape(-1)
+        v = flat[1:].view(t.shape)
+        assert v.data_ptr() % 16 == 4 and v.is_contiguous()
+        return v
+
+    w = torch.rand(1, r, kc, generator=g) ** 6
+    u, u2 = torch.rand(1, r, n, generator=g), torch.rand(1, r, n, generator=g)
+    nrm = torch.randn(1, r, nd, generator=g) if nd else None
+    zc = O.coarse_z(near.cpu().expand(1, r).contiguous(), far.cpu().expand(1, r).contiguous(), kc, torch.rand(1, r, kc, generator=g))
+    kw = dict(depth_std=0.01, want_fine=True, want_sorted=True, want_cdf=True, want_idx=True)
+    ref = ops.importance_sample(w.to(dev), near, far, u.to(dev), u2.to(dev), z_coarse=zc.to(dev),
+                                normals=None if nrm is None else nrm.to(dev), **kw)
+    for which in ("w", "u", "z", "all"):
+        a = ops.importance_sample(off(w) if which in ("w", "all") else w.to(dev), near, far,
+                                  off(u) if which in ("u", "all") else u.to(dev), off(u2) if which in ("u", "all") else u2.to(dev),
+                                  z_coarse=off(zc) if which in ("z", "all") else zc.to(dev),
+                                  normals=None if nrm is None else (off(nrm) if which in ("z", "all") else nrm.to(dev)), **kw)
+        for k in ("z_sorted", "z_fine", "idx", "cdf"):
+            assert torch.equal(a[k], ref[k]), (which, k)
