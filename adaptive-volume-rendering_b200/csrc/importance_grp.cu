@@ -203,6 +203,9 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     return (1 << (DEPTH - 1 - tz)) + (g * (CW >> (tz + 1))) + ((i + 1) >> (tz + 1));
   };
 
+  // packed layout: lengths of the coarse and the new-sample streams (the last offsets)
+  const int64_t total_c = kRagged ? a.offsets[a.R] : 0, total_f = kRagged ? a.fine_offsets[a.R] : 0;
+
   // one ray per group: `live` == false marks a group without work of its own (it recomputes a
   // valid ray alongside the others and stores nothing)
   auto process = [&](const int64_t r, const bool live) {
@@ -222,7 +225,29 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     // ---- loads: everything this lane needs of its ray --------------------------------------
     float w[CW], uu[NIL > 0 ? NIL : 1], jj[NIL > 0 ? NIL : 1], nn[NDL > 0 ? NDL : 1];
     float x[EPT];
-    if (kRagged) {
+    if (kRagged && __all_sync(0xffffffffu, cbase + KC <= total_c && fbase + NI <= total_f)) {
+      // the whole class box lies inside the packed streams (every ray but the last few of a launch): plain loads
+      // at constant offsets from one pointer per stream.  What they fetch past the ray's own counts belongs to
+      // the following rays and is masked where it is used (selects: a NaN there goes nowhere).
+      const float* wrow = a.weights + cbase + g * CW;
+#pragma unroll
+      for (int i = 0; i < CW; ++i) w[i] = wrow[i];
+      const float* urow = a.u + fbase + g * NIL;
+      const float* jrow = a.u2 + fbase + g * NIL;
+#pragma unroll
+      for (int q = 0; q < NIL; ++q) {
+        uu[q] = urow[q];
+        jj[q] = jrow[q];
+      }
+      if (do_sort) {
+        const float* zrow = a.z_coarse + cbase + g;
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          const float zv = zrow[i * G];
+          x[i] = i * G + g < kc ? zv : CUDART_INF_F;
+        }
+      }
+    } else if (kRagged) {
       // clamped unconditional loads; entries past the ray's counts are masked where they are used
       const float* wrow = a.weights + cbase;
 #pragma unroll
@@ -460,11 +485,14 @@ importance_grp_kernel(const ImportanceRegArgs a) {
         unsorted = unsorted || x[i + 3] > nx;
       }
     } else {
+      // key i*G + g + 1 sits in register i of the next lane — for the group's last lane in register i + 1 of its
+      // first: that lane offers x[i + 1] instead, so one rotating shuffle per register serves both
+      const int next_lane = (lane & ~(G - 1)) | ((g + 1) & (G - 1));
 #pragma unroll
       for (int i = 0; i < CW; ++i) {
-        float nx = __shfl_down_sync(0xffffffffu, x[i], 1);
-        const float first_next = __shfl_sync(0xffffffffu, x[(i + 1 < CW) ? i + 1 : i], lane & ~(G - 1));
-        if (g == G - 1) nx = (i + 1 < CW) ? first_next : CUDART_INF_F;
+        const float offer = (g == 0 && i + 1 < CW) ? x[(i + 1 < CW) ? i + 1 : i] : x[i];
+        float nx = __shfl_sync(0xffffffffu, offer, next_lane);
+        if (i + 1 == CW && g == G - 1) nx = CUDART_INF_F;
         if ((!kRagged || i * G + g + 1 < kc) && x[i] > nx) unsorted = true;
       }
     }
@@ -493,6 +521,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
           const int q = key_index(i);
+          if (!kQuad && i * G >= C::TOTAL) continue;  // striped: registers wholly past the largest row
           if (q < total) out[q] = x[i];
         }
       }
