@@ -208,18 +208,19 @@ importance_grp_kernel(const ImportanceRegArgs a) {
 
   // one ray per group: `live` == false marks a group without work of its own (it recomputes a
   // valid ray alongside the others and stores nothing)
-  auto process = [&](const int64_t r, const bool live) {
+  auto process = [&](const int64_t r, const bool live, const int64_t cbase_in, const int kc_in, const int64_t fbase_in,
+                     const int n_in) {
     const int64_t bi = a.bound_stride ? r : 0;
     const float near = a.near[bi], far = a.far[bi];
     const float span = __fsub_rn(far, near);
     // ragged: this ray's counts and its slices of the packed streams
     int kc = KC, n = NI;
     int64_t cbase = r * KC, fbase = r * NI;
-    if (kRagged) {
-      cbase = a.offsets[r];
-      kc = (int)(a.offsets[r + 1] - cbase);
-      fbase = a.fine_offsets[r];
-      n = (int)(a.fine_offsets[r + 1] - fbase);
+    if (kRagged) {  // handed over by the lane that classified the ray: no second trip to the offsets
+      cbase = cbase_in;
+      kc = kc_in;
+      fbase = fbase_in;
+      n = n_in;
     }
 
     // ---- loads: everything this lane needs of its ray --------------------------------------
@@ -354,6 +355,11 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       int32_t* irow = (!kRagged && a.idx && live) ? a.idx + r * NI : nullptr;           // dense: the row, dealt as u was
       float* frow = (a.z_fine && live) ? a.z_fine + fbase + (kRagged ? g * NIL : 0) : nullptr;
       const float kcf = (float)kc;
+      // ragged rays divide by their own count (renderers.py:45).  1 <= kc <= 256, so y = RN(1/kc) and Markstein's
+      // sequence q0 = RN(a*y); r = fma(-kc, q0, a); q = fma(r, y, q0) give the correctly rounded a/kc for every
+      // numerator whose intermediates stay normal (coarse_packed_core.h has the same shortcut and its CPU walk);
+      // anything else — no draw of torch.rand gets there — divides the IEEE way.
+      const float rkc = kRagged ? __frcp_rn(kcf) : 0.f;
       // node <- 2*node + (tree[node] <= u): after DEPTH probes node - KC counts the entries
       // cdf[1..KC-1] <= u; adding (cdf[KC] <= u) gives clamp_min(searchsorted(cdf, u, right=True) - 1, 0).
       // (c <= u) is the complement of the sign bit of u - c (exact in sign: nothing is flushed).
@@ -398,7 +404,18 @@ importance_grp_kernel(const ImportanceRegArgs a) {
         const float dl = __fsub_rn(uu[q], last);
         const int bin = (int)(node[q] - KC) + 1 - (int)(__float_as_uint(dl) >> 31);
         const float num = __fadd_rn((float)bin, jj[q]);                    // renderers.py:45
-        const float t = kRagged ? __fdiv_rn(num, kcf) : __fmul_rn(num, inv_kc);
+        float t;
+        if (kRagged) {
+          const float an = fabsf(num);
+          if ((an >= 0x1p-90f && an < 0x1p100f) || an == 0.f) {
+            const float q0 = __fmul_rn(num, rkc);
+            t = __fmaf_rn(__fmaf_rn(-kcf, q0, num), rkc, q0);
+          } else {
+            t = __fdiv_rn(num, kcf);
+          }
+        } else {
+          t = __fmul_rn(num, inv_kc);
+        }
         const float val = __fadd_rn(near, __fmul_rn(span, t));              // :46
         bins[q] = bin;
         v[q] = val;
@@ -534,19 +551,27 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     for (int64_t base = (blockIdx.x * (int64_t)kGrpWarps + warp) * 32; base < a.R; base += step) {
       const int64_t rr = base + lane;
       bool mine = false;
+      int64_t c_lane = 0, f_lane = 0;
+      int kc_lane = 0, n_lane = 0;
       if (rr < a.R) {
-        const int kc = (int)(a.offsets[rr + 1] - a.offsets[rr]);
-        const int n = (int)(a.fine_offsets[rr + 1] - a.fine_offsets[rr]);
-        mine = grp_ragged_class(kc, n) == kClass;
+        c_lane = a.offsets[rr];
+        f_lane = a.fine_offsets[rr];
+        kc_lane = (int)(a.offsets[rr + 1] - c_lane);
+        n_lane = (int)(a.fine_offsets[rr + 1] - f_lane);
+        mine = grp_ragged_class(kc_lane, n_lane) == kClass;
       }
       unsigned todo = __ballot_sync(0xffffffffu, mine);
       while (todo) {
-        const unsigned pick = __fns(todo, 0, sub + 1);        // the (sub+1)-th match, if there is one
-        const bool live = pick != 0xffffffffu;
-        const int64_t r = base + (live ? (int)pick : __ffs(todo) - 1);
+        unsigned mine_on = todo;                              // the (sub+1)-th match, if there is one
+#pragma unroll
+        for (int k = 1; k < RPW; ++k)
+          if (k <= sub) mine_on &= mine_on - 1;
+        const bool live = mine_on != 0u;
+        const int src = __ffs(live ? mine_on : todo) - 1;
 #pragma unroll
         for (int k = 0; k < RPW; ++k) todo &= todo - 1;       // (x & (x-1)) of 0 stays 0
-        process(r, live);
+        process(base + src, live, __shfl_sync(0xffffffffu, c_lane, src), __shfl_sync(0xffffffffu, kc_lane, src),
+                __shfl_sync(0xffffffffu, f_lane, src), __shfl_sync(0xffffffffu, n_lane, src));
       }
     }
   } else {
@@ -554,7 +579,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     const int64_t wg_stride = (int64_t)gridDim.x * kGrpWarps;
     for (int64_t wg = blockIdx.x * (int64_t)kGrpWarps + warp; wg < n_wg; wg += wg_stride) {
       const int64_t r_raw = wg * RPW + sub;
-      process(r_raw < a.R ? r_raw : a.R - 1, r_raw < a.R);   // a dead group (last warp only) recomputes ray R-1
+      process(r_raw < a.R ? r_raw : a.R - 1, r_raw < a.R, 0, 0, 0, 0);   // a dead group (last warp only) recomputes ray R-1
     }
   }
 }
