@@ -8,10 +8,21 @@
 // Layout of the work.  A warp owns a SEGMENT = 32 consecutive rays, i.e. one contiguous slice
 // [offsets[r0], offsets[r0+32]) of the packed u / z streams.  The 33 offsets (relative to the
 // segment start) and the rays' parameters go to shared memory once; after that the segment is
-// processed as a flat stream, four consecutive samples (one 16-byte access) per lane and step,
-// each lane finding its ray by a 5-probe search of the 33 offsets.  Rays of any length,
-// including empty ones, cost nothing beyond their samples: no lane idles on a short ray and
-// there is one dependent global-load chain per 32 rays instead of one per ray.
+// processed as a flat stream, four consecutive samples (one 16-byte access) per lane and step.
+// Rays of any length, including empty ones, cost nothing beyond their samples: no lane idles on a
+// short ray and there is one dependent global-load chain per 32 rays instead of one per ray.
+//
+// Finding the ray of a group.  The 32 groups a warp handles in one step ("a row") are 128
+// consecutive samples, so they touch few rays: two votes over the lanes' own offsets give the ray
+// of the row's first and last sample, and a lane only counts the ray starts in between that lie at
+// or before its group (a warp-uniform loop, usually zero to two steps; rows with many short rays
+// take the 5-probe search of the 33 offsets instead).
+//
+// Inside a group.  A group lies in one ray (A) or crosses into the next one (B); as long as B
+// reaches the group's end the four samples are computed without a branch, each selecting its
+// ray's constants.  Everything else (rays shorter than the rest of a group, empty rays in between,
+// partial groups at the segment's ends, unaligned streams, numerators outside the division
+// shortcut's range) takes the general walk, sample by sample.
 //
 // Division.  z = near + span*(j/K) + (u*span)/K has two IEEE divisions per sample
 // (renderers.py:12, :14).  K is constant along a ray, so y = RN(1/K) is formed once per ray and
@@ -57,10 +68,11 @@ struct CoarseRay {
   float near, span, kf, rcp;  // rcp == 0 marks a ray that divides the IEEE way
 };
 
+constexpr int kRowWalk = 4;  // ray starts a lane counts one by one before it prefers the search
+
 struct CoarseSegment {
-  int rel[kSegRays + 1];  // offsets relative to the segment start; rel[32] = segment length
-  int pad[3];
-  CoarseRay ray[kSegRays];
+  int rel[kSegRays + 4];  // offsets relative to the segment start; rel[32] = segment length; rel[33..35] = INT_MAX
+  CoarseRay ray[kSegRays + 1];  // ray[32]: a stand-in (rcp == 0) so that "the ray after k" always exists
 };
 
 // a / K given y = RN(1/K): Markstein's correction, the correctly rounded quotient under the
@@ -104,6 +116,12 @@ AVR_HD bool coarse_segment_build(int lane, int64_t r0, int64_t R, const int64_t*
   const bool ok = rel >= 0 && cnt >= 0 && (end - seg_begin) < (int64_t)0x7ffffff0;  // head + len + 3 stays an int
   seg->rel[lane] = (int)rel;
   if (lane == kSegRays - 1) seg->rel[kSegRays] = (int)(end - seg_begin);
+  if (lane == 0) {
+    seg->rel[kSegRays + 1] = seg->rel[kSegRays + 2] = seg->rel[kSegRays + 3] = 0x7fffffff;
+    CoarseRay none;
+    none.near = none.span = none.kf = none.rcp = 0.f;
+    seg->ray[kSegRays] = none;
+  }
   CoarseRay p;
   const int64_t b = bound_stride ? (r < R ? r : R - 1) : 0;
   p.near = near[b];
@@ -157,9 +175,8 @@ AVR_HD CoarseGroup coarse_group_load(int g, int head, int seg_len, const float* 
   return c;
 }
 
-AVR_HD void coarse_group_finish(const CoarseGroup& c, int g, const CoarseSegment* seg, float* za) {
-  if (c.hi <= c.lo) return;
-  int k = coarse_segment_find(seg, c.lo);
+// the general walk of a group, sample by sample, starting from the ray k of its first slot
+AVR_HD void coarse_group_walk(const CoarseGroup& c, int g, int k, const CoarseSegment* seg, float* za) {
   CoarseRay p = seg->ray[k];
   int rb = seg->rel[k], re = seg->rel[k + 1];
   float out[4];
@@ -192,22 +209,109 @@ AVR_HD void coarse_group_finish(const CoarseGroup& c, int g, const CoarseSegment
   }
 }
 
-// `vec_ok`: u and z are 16-byte aligned.  Two groups per lane are in flight per step (both
-// loads are issued before either is consumed).
+// A group whose first slot lies in ray k.  Whole groups inside ray k, or crossing into a ray k+1
+// that reaches the group's end, are computed branch-free; the rest takes coarse_group_walk.
+AVR_HD void coarse_group_finish(const CoarseGroup& c, int g, int k, const CoarseSegment* seg, float* za) {
+  const int rb = seg->rel[k], re = seg->rel[k + 1], re2 = seg->rel[k + 2];
+  const CoarseRay A = seg->ray[k], B = seg->ray[k + 1];
+  const int end4 = c.i0 + 4;
+  // (no short-circuit: lanes whose group crosses into B must not leave the others behind and run the block twice)
+  const bool two_rays = c.full & (A.rcp != 0.f) & ((re >= end4) | ((re2 >= end4) & (B.rcp != 0.f)));
+  if (two_rays) {
+    const float ja = (float)(c.i0 - rb), jb = (float)(c.i0 - re);  // sample numbers of slot 0 in A / in B (exact)
+    const int to_b = re - c.i0;                                     // slots to_b.. of the group lie in B
+    float nr[4], sp[4], kf[4], rc[4], jf[4], jit[4];
+    bool fast = true;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) {
+      const bool in_b = q >= to_b;
+      nr[q] = in_b ? B.near : A.near;
+      sp[q] = in_b ? B.span : A.span;
+      kf[q] = in_b ? B.kf : A.kf;
+      rc[q] = in_b ? B.rcp : A.rcp;
+      jf[q] = f_add(in_b ? jb : ja, (float)q);
+      jit[q] = f_mul(c.u[q], sp[q]);
+      const float aj = fabsf(jit[q]);
+      fast = fast & (aj >= 0x1p-90f) & (aj < 0x1p100f);  // zero draws (one in 2^24) walk
+    }
+    if (fast) {
+      float out[4];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int q = 0; q < 4; ++q) {
+        const float bin = div_markstein(jf[q], kf[q], rc[q]);
+        const float t = div_markstein(jit[q], kf[q], rc[q]);
+        out[q] = f_add(f_add(nr[q], f_mul(sp[q], bin)), t);
+      }
+#if defined(__CUDACC__)
+      __stcs(reinterpret_cast<float4*>(za + 4 * g), make_float4(out[0], out[1], out[2], out[3]));
+#else
+      for (int q = 0; q < 4; ++q) za[4 * g + q] = out[q];
+#endif
+      return;
+    }
+  }
+  coarse_group_walk(c, g, k, seg, za);
+}
+
+// number of rays of the segment that start at or before sample i: a vote over the lanes' own offsets
+// (every lane of the warp calls it with the same i); the host walk counts the table instead
+AVR_HD int coarse_starts_le(const CoarseSegment* seg, int my_rel, int i) {
+#if defined(__CUDACC__)
+  (void)seg;
+  return __popc(__ballot_sync(0xffffffffu, my_rel <= i));
+#else
+  (void)my_rel;
+  int n = 0;
+  for (int l = 0; l < kSegRays; ++l) n += seg->rel[l] <= i;
+  return n;
+#endif
+}
+
+// One row: groups g_row .. g_row+31, lane `lane` owning group g_row + lane (`on`: it exists and was loaded).
+// Every lane of the warp enters (the votes), lanes without a group leave after them.
+AVR_HD void coarse_row_finish(const CoarseGroup& c, bool on, int lane, int my_rel, int g_row, int head, int seg_len,
+                              const CoarseSegment* seg, float* za) {
+  int i_first = 4 * g_row - head, i_last = 4 * (g_row + 31) - head + 3;
+  i_first = i_first < 0 ? 0 : i_first;
+  i_last = i_last < seg_len ? i_last : seg_len - 1;
+  const int k_first = coarse_starts_le(seg, my_rel, i_first) - 1;  // rel[0] == 0: at least one
+  const int k_last = coarse_starts_le(seg, my_rel, i_last) - 1;
+  if (!on || c.hi <= c.lo) return;
+  int k;
+  if (k_last - k_first <= kRowWalk) {
+    k = k_first;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int b = k_first + 1; b <= k_last; ++b) k += seg->rel[b] <= c.lo ? 1 : 0;  // rel is non-decreasing
+  } else {
+    k = coarse_segment_find(seg, c.lo);
+  }
+  coarse_group_finish(c, g_row + lane, k, seg, za);
+}
+
+// `vec_ok`: u and z are 16-byte aligned.  Two rows are in flight per step (both loads are issued
+// before either is consumed).
 AVR_HD void coarse_segment_run(int lane, const CoarseSegment* seg, int64_t seg_begin, const float* u, float* z,
                                bool vec_ok) {
   const int seg_len = seg->rel[kSegRays];
+  const int my_rel = seg->rel[lane];
   const int head = (int)(seg_begin & 3);  // samples between the 16-byte boundary below and the segment
   const int n_groups = (head + seg_len + 3) >> 2;
   const float* ua = u + (seg_begin - head);
   float* za = z + (seg_begin - head);
-  for (int g = lane; g < n_groups; g += 64) {
-    const bool two = g + 32 < n_groups;
-    const CoarseGroup c0 = coarse_group_load(g, head, seg_len, ua, vec_ok);
-    CoarseGroup c1 = c0;
-    if (two) c1 = coarse_group_load(g + 32, head, seg_len, ua, vec_ok);
-    coarse_group_finish(c0, g, seg, za);
-    if (two) coarse_group_finish(c1, g + 32, seg, za);
+  for (int g_row = 0; g_row < n_groups; g_row += 64) {  // the same trip count on every lane
+    const int g = g_row + lane;
+    const bool on0 = g < n_groups, on1 = g + 32 < n_groups;
+    CoarseGroup c0 = CoarseGroup(), c1 = CoarseGroup();
+    if (on0) c0 = coarse_group_load(g, head, seg_len, ua, vec_ok);
+    if (on1) c1 = coarse_group_load(g + 32, head, seg_len, ua, vec_ok);
+    coarse_row_finish(c0, on0, lane, my_rel, g_row, head, seg_len, seg, za);
+    if (g_row + 32 < n_groups) coarse_row_finish(c1, on1, lane, my_rel, g_row + 32, head, seg_len, seg, za);
   }
 }
 
