@@ -13,10 +13,9 @@
 // short ray and there is one dependent global-load chain per 32 rays instead of one per ray.
 //
 // Finding the ray of a group.  The 32 groups a warp handles in one step ("a row") are 128
-// consecutive samples, so they touch few rays: two votes over the lanes' own offsets give the ray
-// of the row's first and last sample, and a lane only counts the ray starts in between that lie at
-// or before its group (a warp-uniform loop, usually zero to two steps; rows with many short rays
-// take the 5-probe search of the 33 offsets instead).
+// consecutive samples, so they touch few rays: a vote over the lanes' own offsets gives the ray of
+// the row's first sample, and a lane adds how many of the next two ray starts lie at or before its
+// group (rows that hold more than two ray starts take the 5-probe search of the 33 offsets).
 //
 // Inside a group.  A group lies in one ray (A) or crosses into the next one (B); as long as B
 // reaches the group's end the four samples are computed without a branch, each selecting its
@@ -67,8 +66,6 @@ constexpr int kMarksteinMaxCount = (1 << 24) - 2;  // above: float(K) may have a
 struct CoarseRay {
   float near, span, kf, rcp;  // rcp == 0 marks a ray that divides the IEEE way
 };
-
-constexpr int kRowWalk = 4;  // ray starts a lane counts one by one before it prefers the search
 
 struct CoarseSegment {
   int rel[kSegRays + 4];  // offsets relative to the segment start; rel[32] = segment length; rel[33..35] = INT_MAX
@@ -160,7 +157,6 @@ AVR_HD CoarseGroup coarse_group_load(int g, int head, int seg_len, const float* 
   c.lo = c.i0 < 0 ? 0 : c.i0;
   c.hi = c.i0 + 4 < seg_len ? c.i0 + 4 : seg_len;
   c.full = vec_ok && (c.hi - c.lo == 4);
-  c.u[0] = c.u[1] = c.u[2] = c.u[3] = 0.f;
   if (c.full) {
 #if defined(__CUDACC__)
     const float4 q = __ldcs(reinterpret_cast<const float4*>(ua + 4 * g));
@@ -169,6 +165,7 @@ AVR_HD CoarseGroup coarse_group_load(int g, int head, int seg_len, const float* 
     for (int q = 0; q < 4; ++q) c.u[q] = ua[4 * g + q];
 #endif
   } else {
+    c.u[0] = c.u[1] = c.u[2] = c.u[3] = 0.f;
     for (int q = 0; q < 4; ++q)
       if (c.i0 + q >= c.lo && c.i0 + q < c.hi) c.u[q] = ua[4 * g + q];
   }
@@ -221,7 +218,6 @@ AVR_HD void coarse_group_finish(const CoarseGroup& c, int g, int k, const Coarse
     const float ja = (float)(c.i0 - rb), jb = (float)(c.i0 - re);  // sample numbers of slot 0 in A / in B (exact)
     const int to_b = re - c.i0;                                     // slots to_b.. of the group lie in B
     float nr[4], sp[4], kf[4], rc[4], jf[4], jit[4];
-    bool fast = true;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -231,11 +227,15 @@ AVR_HD void coarse_group_finish(const CoarseGroup& c, int g, int k, const Coarse
       sp[q] = in_b ? B.span : A.span;
       kf[q] = in_b ? B.kf : A.kf;
       rc[q] = in_b ? B.rcp : A.rcp;
-      jf[q] = f_add(in_b ? jb : ja, (float)q);
+      const float ja_q = f_add(ja, (float)q), jb_q = f_add(jb, (float)q);  // exact
+      jf[q] = in_b ? jb_q : ja_q;
       jit[q] = f_mul(c.u[q], sp[q]);
-      const float aj = fabsf(jit[q]);
-      fast = fast & (aj >= 0x1p-90f) & (aj < 0x1p100f);  // zero draws (one in 2^24) walk
     }
+    // the division shortcut's range for all four numerators at once (a NaN passes and stays a NaN); zero draws
+    // (one in 2^24) walk
+    const float a0 = fabsf(jit[0]), a1 = fabsf(jit[1]), a2 = fabsf(jit[2]), a3 = fabsf(jit[3]);
+    const float amin = fminf(fminf(a0, a1), fminf(a2, a3)), amax = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+    const bool fast = (amin >= 0x1p-90f) & (amax < 0x1p100f);
     if (fast) {
       float out[4];
 #if defined(__CUDACC__)
@@ -279,15 +279,13 @@ AVR_HD void coarse_row_finish(const CoarseGroup& c, bool on, int lane, int my_re
   i_first = i_first < 0 ? 0 : i_first;
   i_last = i_last < seg_len ? i_last : seg_len - 1;
   const int k_first = coarse_starts_le(seg, my_rel, i_first) - 1;  // rel[0] == 0: at least one
-  const int k_last = coarse_starts_le(seg, my_rel, i_last) - 1;
+  // the next three ray starts (warp-uniform reads; past the table's 33 offsets they are INT_MAX): when the third
+  // lies beyond the row, a group's ray is k_first plus the starts among the first two at or before the group
+  const int s1 = seg->rel[k_first + 1], s2 = seg->rel[k_first + 2], s3 = seg->rel[k_first + 3];
   if (!on || c.hi <= c.lo) return;
   int k;
-  if (k_last - k_first <= kRowWalk) {
-    k = k_first;
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-    for (int b = k_first + 1; b <= k_last; ++b) k += seg->rel[b] <= c.lo ? 1 : 0;  // rel is non-decreasing
+  if (s3 > i_last) {
+    k = k_first + (s1 <= c.lo ? 1 : 0) + (s2 <= c.lo ? 1 : 0);  // rel is non-decreasing
   } else {
     k = coarse_segment_find(seg, c.lo);
   }
@@ -307,7 +305,8 @@ AVR_HD void coarse_segment_run(int lane, const CoarseSegment* seg, int64_t seg_b
   for (int g_row = 0; g_row < n_groups; g_row += 64) {  // the same trip count on every lane
     const int g = g_row + lane;
     const bool on0 = g < n_groups, on1 = g + 32 < n_groups;
-    CoarseGroup c0 = CoarseGroup(), c1 = CoarseGroup();
+    CoarseGroup c0, c1;
+    c0.lo = c0.hi = c1.lo = c1.hi = 0;
     if (on0) c0 = coarse_group_load(g, head, seg_len, ua, vec_ok);
     if (on1) c1 = coarse_group_load(g + 32, head, seg_len, ua, vec_ok);
     coarse_row_finish(c0, on0, lane, my_rel, g_row, head, seg_len, seg, za);

@@ -77,7 +77,10 @@ coarse_fwd_dense_kernel(const float* __restrict__ near, const float* __restrict_
 // packed, flat: a warp owns 32 consecutive rays = one contiguous slice of the packed streams and
 // walks it four samples per lane at a time (coarse_packed_core.h has the per-lane code and the
 // reasoning; the same code runs on the host in the CPU test suite)
-__global__ void __launch_bounds__(kSamplerWarps * 32)
+#ifndef AVR_COARSE_FLAT_BLOCKS
+#define AVR_COARSE_FLAT_BLOCKS 8  // resident CTAs per SM the register budget is cut for (8 x 4 warps: 64 registers)
+#endif
+__global__ void __launch_bounds__(kSamplerWarps * 32, AVR_COARSE_FLAT_BLOCKS)
 coarse_fwd_packed_flat_kernel(const float* __restrict__ near, const float* __restrict__ far, int bound_stride,
                               const float* __restrict__ u, const int64_t* __restrict__ offsets, int64_t R,
                               float* __restrict__ z, int vec_ok) {
