@@ -151,19 +151,36 @@ struct CoarseGroup {
   float u[4];
 };
 
-AVR_HD CoarseGroup coarse_group_load(int g, int head, int seg_len, const float* ua, bool vec_ok) {
+// The draws of a whole, vector-loadable group: requested as soon as its index is known (a warp has
+// AVR_COARSE_ROWS such loads per lane in flight; with AVR_COARSE_AHEAD those of the NEXT step, issued before
+// the current step is computed).  Anything else is left to coarse_group_load.
+struct CoarseDraws {
+  float u[4];
+};
+
+AVR_HD CoarseDraws coarse_group_request(int g, int n_groups, int head, int seg_len, const float* ua, bool vec_ok) {
+  CoarseDraws d;
+  d.u[0] = d.u[1] = d.u[2] = d.u[3] = 0.f;
+  const int i0 = 4 * g - head;
+  if (vec_ok && g < n_groups && i0 >= 0 && i0 + 4 <= seg_len) {
+#if defined(__CUDACC__)
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(ua + 4 * g));
+    d.u[0] = q.x; d.u[1] = q.y; d.u[2] = q.z; d.u[3] = q.w;
+#else
+    for (int q = 0; q < 4; ++q) d.u[q] = ua[4 * g + q];
+#endif
+  }
+  return d;
+}
+
+AVR_HD CoarseGroup coarse_group_load(int g, int head, int seg_len, const float* ua, bool vec_ok, const CoarseDraws& req) {
   CoarseGroup c;
   c.i0 = 4 * g - head;
   c.lo = c.i0 < 0 ? 0 : c.i0;
   c.hi = c.i0 + 4 < seg_len ? c.i0 + 4 : seg_len;
   c.full = vec_ok && (c.hi - c.lo == 4);
   if (c.full) {
-#if defined(__CUDACC__)
-    const float4 q = __ldcs(reinterpret_cast<const float4*>(ua + 4 * g));
-    c.u[0] = q.x; c.u[1] = q.y; c.u[2] = q.z; c.u[3] = q.w;
-#else
-    for (int q = 0; q < 4; ++q) c.u[q] = ua[4 * g + q];
-#endif
+    for (int q = 0; q < 4; ++q) c.u[q] = req.u[q];
   } else {
     c.u[0] = c.u[1] = c.u[2] = c.u[3] = 0.f;
     for (int q = 0; q < 4; ++q)
@@ -271,10 +288,10 @@ AVR_HD int coarse_starts_le(const CoarseSegment* seg, int my_rel, int i) {
 #endif
 }
 
-// One row: groups g_row .. g_row+31, lane `lane` owning group g_row + lane (`on`: it exists and was loaded).
-// Every lane of the warp enters (the votes), lanes without a group leave after them.
-AVR_HD void coarse_row_finish(const CoarseGroup& c, bool on, int lane, int my_rel, int g_row, int head, int seg_len,
-                              const CoarseSegment* seg, float* za) {
+// One row: groups g_row .. g_row+31, lane `lane` owning group g_row + lane (the draws of a whole group arrive
+// in `req`).  Every lane of the warp enters (the vote), lanes without a group leave after it.
+AVR_HD void coarse_row_finish(const CoarseDraws& req, int lane, int my_rel, int g_row, int n_groups, int head,
+                              int seg_len, const CoarseSegment* seg, const float* ua, float* za, bool vec_ok) {
   int i_first = 4 * g_row - head, i_last = 4 * (g_row + 31) - head + 3;
   i_first = i_first < 0 ? 0 : i_first;
   i_last = i_last < seg_len ? i_last : seg_len - 1;
@@ -282,35 +299,67 @@ AVR_HD void coarse_row_finish(const CoarseGroup& c, bool on, int lane, int my_re
   // the next three ray starts (warp-uniform reads; past the table's 33 offsets they are INT_MAX): when the third
   // lies beyond the row, a group's ray is k_first plus the starts among the first two at or before the group
   const int s1 = seg->rel[k_first + 1], s2 = seg->rel[k_first + 2], s3 = seg->rel[k_first + 3];
-  if (!on || c.hi <= c.lo) return;
+  const int g = g_row + lane;
+  if (g >= n_groups) return;
+  const CoarseGroup c = coarse_group_load(g, head, seg_len, ua, vec_ok, req);
+  if (c.hi <= c.lo) return;
   int k;
   if (s3 > i_last) {
     k = k_first + (s1 <= c.lo ? 1 : 0) + (s2 <= c.lo ? 1 : 0);  // rel is non-decreasing
   } else {
     k = coarse_segment_find(seg, c.lo);
   }
-  coarse_group_finish(c, g_row + lane, k, seg, za);
+  coarse_group_finish(c, g, k, seg, za);
 }
 
-// `vec_ok`: u and z are 16-byte aligned.  Two rows are in flight per step (both loads are issued
-// before either is consumed).
+#ifndef AVR_COARSE_ROWS
+#define AVR_COARSE_ROWS 3   // rows (16-byte loads per lane) per step
+#endif
+#ifndef AVR_COARSE_AHEAD
+#define AVR_COARSE_AHEAD 0  // 1: the next step's draws are requested before the current step is computed
+#endif
+
+// `vec_ok`: u and z are 16-byte aligned.
 AVR_HD void coarse_segment_run(int lane, const CoarseSegment* seg, int64_t seg_begin, const float* u, float* z,
                                bool vec_ok) {
+  constexpr int NR = AVR_COARSE_ROWS;
   const int seg_len = seg->rel[kSegRays];
   const int my_rel = seg->rel[lane];
   const int head = (int)(seg_begin & 3);  // samples between the 16-byte boundary below and the segment
   const int n_groups = (head + seg_len + 3) >> 2;
   const float* ua = u + (seg_begin - head);
   float* za = z + (seg_begin - head);
-  for (int g_row = 0; g_row < n_groups; g_row += 64) {  // the same trip count on every lane
-    const int g = g_row + lane;
-    const bool on0 = g < n_groups, on1 = g + 32 < n_groups;
-    CoarseGroup c0, c1;
-    c0.lo = c0.hi = c1.lo = c1.hi = 0;
-    if (on0) c0 = coarse_group_load(g, head, seg_len, ua, vec_ok);
-    if (on1) c1 = coarse_group_load(g + 32, head, seg_len, ua, vec_ok);
-    coarse_row_finish(c0, on0, lane, my_rel, g_row, head, seg_len, seg, za);
-    if (g_row + 32 < n_groups) coarse_row_finish(c1, on1, lane, my_rel, g_row + 32, head, seg_len, seg, za);
+  CoarseDraws cur[NR], nxt[NR];
+  if (AVR_COARSE_AHEAD) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int r = 0; r < NR; ++r) cur[r] = coarse_group_request(lane + 32 * r, n_groups, head, seg_len, ua, vec_ok);
+  }
+  for (int g_row = 0; g_row < n_groups; g_row += 32 * NR) {  // the same trip count on every lane
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int r = 0; r < NR; ++r) {
+      if (AVR_COARSE_AHEAD) {
+        nxt[r] = coarse_group_request(g_row + 32 * (NR + r) + lane, n_groups, head, seg_len, ua, vec_ok);
+      } else {
+        cur[r] = coarse_group_request(g_row + 32 * r + lane, n_groups, head, seg_len, ua, vec_ok);
+      }
+    }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int r = 0; r < NR; ++r) {
+      if (r == 0 || g_row + 32 * r < n_groups)
+        coarse_row_finish(cur[r], lane, my_rel, g_row + 32 * r, n_groups, head, seg_len, seg, ua, za, vec_ok);
+    }
+    if (AVR_COARSE_AHEAD) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int r = 0; r < NR; ++r) cur[r] = nxt[r];
+    }
   }
 }
 
