@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--stages", type=int, nargs="+", default=[3, 4])
     ap.add_argument("--ls", type=int, nargs="+", default=[0])
     ap.add_argument("--peak", type=float, default=6456.2)
+    ap.add_argument("--no-w", action="store_true", help="forward without the weights output (the fine pass of a render)")
     a = ap.parse_args()
     lib = avr_b200.load_library()
     dev = torch.device("cuda:0")
@@ -50,7 +51,7 @@ def main():
                 continue
 
             def fwd():
-                rc = lib.avr_composite_fwd(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, w.data_ptr(), rgb.data_ptr(), depth.data_ptr(), sp)
+                rc = lib.avr_composite_fwd(x.data_ptr(), z.data_ptr(), rays, k, 1, 1.8, None if a.no_w else w.data_ptr(), rgb.data_ptr(), depth.data_ptr(), sp)
                 assert rc == 0, (rc, lib.avr_last_cuda_error())
 
             def bwd():
@@ -58,7 +59,7 @@ def main():
                 assert rc == 0, (rc, lib.avr_last_cuda_error())
 
             res = {"k": k, "L": Lc.value, "rays_per_tile": rpt.value, "warps": warps, "stages": stages}
-            for name, fn, bpr in (("fwd", fwd, 24 * k + 16), ("bwd", bwd, 36 * k + 16)):
+            for name, fn, bpr in (("fwd", fwd, (20 if a.no_w else 24) * k + 16), ("bwd", bwd, 36 * k + 16)):
                 try:
                     for _ in range(3):
                         fn()
