@@ -233,12 +233,14 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       const float* wrow = a.weights + cbase + g * CW;
 #pragma unroll
       for (int i = 0; i < CW; ++i) w[i] = wrow[i];
-      const float* urow = a.u + fbase + g * NIL;
-      const float* jrow = a.u2 + fbase + g * NIL;
+      // draws striped over the group (lane g takes samples g, g + G, ...: G consecutive floats per instruction;
+      // which lane draws which sample is free, they are sorted afterwards)
+      const float* urow = a.u + fbase + g;
+      const float* jrow = a.u2 + fbase + g;
 #pragma unroll
       for (int q = 0; q < NIL; ++q) {
-        uu[q] = urow[q];
-        jj[q] = jrow[q];
+        uu[q] = urow[q * G];
+        jj[q] = jrow[q * G];
       }
       if (do_sort) {
         const float* zrow = a.z_coarse + cbase + g;
@@ -258,7 +260,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       }
 #pragma unroll
       for (int q = 0; q < NIL; ++q) {
-        const int e = g * NIL + q;
+        const int e = q * G + g;
         const int ec = n > 0 ? (e < n ? e : n - 1) : 0;
         uu[q] = n > 0 ? a.u[fbase + ec] : 0.f;
         jj[q] = n > 0 ? a.u2[fbase + ec] : 0.f;
@@ -353,7 +355,7 @@ importance_grp_kernel(const ImportanceRegArgs a) {
     float v[EPF];
     if (NIL > 0) {
       int32_t* irow = (!kRagged && a.idx && live) ? a.idx + r * NI : nullptr;           // dense: the row, dealt as u was
-      float* frow = (a.z_fine && live) ? a.z_fine + fbase + (kRagged ? g * NIL : 0) : nullptr;
+      float* frow = (a.z_fine && live) ? a.z_fine + fbase + (kRagged ? g : 0) : nullptr;
       const float kcf = (float)kc;
       // ragged rays divide by their own count (renderers.py:45).  1 <= kc <= 256, so y = RN(1/kc) and Markstein's
       // sequence q0 = RN(a*y); r = fma(-kc, q0, a); q = fma(r, y, q0) give the correctly rounded a/kc for every
@@ -423,8 +425,8 @@ importance_grp_kernel(const ImportanceRegArgs a) {
       if (kRagged) {
 #pragma unroll
         for (int q = 0; q < NIL; ++q) {
-          const bool has = g * NIL + q < n;
-          if (frow && has) frow[q] = v[q];
+          const bool has = q * G + g < n;
+          if (frow && has) frow[q * G] = v[q];
           if (!has) v[q] = CUDART_INF_F;  // padding of the class box
         }
       } else {
