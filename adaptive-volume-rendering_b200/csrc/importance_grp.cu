@@ -65,8 +65,15 @@ struct GrpCfg {
   // warps per CTA: as many as the static shared-memory limit (48 KiB) allows, at most 8
   static constexpr int SMEM_PER_WARP = RPW * (TREE_STRIDE + BUF_STRIDE) * 4;
   static constexpr int WARPS = (8 * SMEM_PER_WARP <= 48 * 1024) ? 8 : 4;
-  // register budget: 64/thread where the per-lane arrays are small, 128 otherwise
-  static constexpr int MIN_BLOCKS = (EPT <= 16 && (G >= 16 || EPF <= 4)) ? (32 / WARPS) : (16 / WARPS);
+  // register budget: 64/thread (32 resident warps) where the per-lane arrays are small; otherwise 80 (24 warps) —
+  // the dense shapes fit that without a spill, and the 64 -> 128 kernel runs 0.628 -> 0.605 ms against the former
+  // 128 / 16 warps (95 registers / 20 warps: 0.606, 72 / 28 warps with 16 B spilled: 0.625, 64 with 44 B: 0.638)
+  // ... and 48 (40 warps, 12 B spilled) for the largest ragged class, one ray per warp: 1.239 -> 1.212 ms on config 4's
+  // distribution (24 warps at 78 registers: 1.283, 48 warps at 40 registers: 1.281)
+  // (the second largest class, two rays per warp: 24 / 32 / 40 warps within 1 %)
+  static constexpr int MIN_BLOCKS = (G == 32 && KC == 256)                 ? (40 / WARPS)
+                                    : (EPT <= 16 && (G >= 16 || EPF <= 4)) ? (32 / WARPS)
+                                                                           : (24 / WARPS);
   static_assert(G == 8 || G == 16 || G == 32, "group width");
   static_assert((KC & (KC - 1)) == 0 && KC % G == 0 && NI % G == 0 && ND % G == 0, "shape must split evenly over the group");
   static_assert(EPT <= 32 && BUF_STRIDE % 4 == 0 && TREE_STRIDE % 4 == 0, "layout");
