@@ -71,7 +71,10 @@ struct GrpCfg {
   // ... and 48 (40 warps, 12 B spilled) for the largest ragged class, one ray per warp: 1.239 -> 1.212 ms on config 4's
   // distribution (24 warps at 78 registers: 1.283, 48 warps at 40 registers: 1.281)
   // (the second largest class, two rays per warp: 24 / 32 / 40 warps within 1 %)
+  // conf/default.conf's shape (64 -> 16 + 16): 48 registers / 40 warps without a spill, 0.239 -> 0.233 ms with the merge
+  // (24 warps: 0.268, 48 warps at 40 registers with 36 B spilled: 0.248)
   static constexpr int MIN_BLOCKS = (G == 32 && KC == 256)                 ? (40 / WARPS)
+                                    : (G == 8 && KC == 64 && NI == 16)     ? (40 / WARPS)
                                     : (EPT <= 16 && (G >= 16 || EPF <= 4)) ? (32 / WARPS)
                                                                            : (24 / WARPS);
   static_assert(G == 8 || G == 16 || G == 32, "group width");
