@@ -24,6 +24,7 @@
 //     instruction latency, so 12 resident warps/SM (2 x 8.6 KB each) beat 8 with a third slot.
 #include <climits>
 #include <cstdlib>
+#include <type_traits>
 
 #include "avr_common.cuh"
 #include "kernels.h"
@@ -202,11 +203,12 @@ __device__ __forceinline__ void patch_z_tail(const PkPipe& pipe, int st, const P
 
 // The lane's run inside a ragged tile: which ray its first sample belongs to and where (if
 // anywhere) that ray ends inside the run.  ends[i] = end of the tile's i-th ray, INT_MAX padded.
+template <int L>
 __device__ __forceinline__ Run ragged_run(const int* ends, int n_s, int lane) {
   Run run;
-  run.s0 = lane * kPkL;
+  run.s0 = lane * L;
   const int rem = n_s - run.s0;
-  run.nvalid = rem < 0 ? 0 : (rem > kPkL ? kPkL : rem);
+  run.nvalid = rem < 0 ? 0 : (rem > L ? L : rem);
   int cnt = 0;  // rays ending at or before s0
 #pragma unroll
   for (int step = 16; step > 0; step >>= 1) {
@@ -218,11 +220,33 @@ __device__ __forceinline__ Run ragged_run(const int* ends, int n_s, int lane) {
   const int end = ends[cnt];
   run.ray0 = cnt;
   run.k0 = run.s0 - start;
-  const int to_head = (run.k0 == 0) ? 0 : (end == INT_MAX ? kPkL : end - run.s0);
+  const int to_head = (run.k0 == 0) ? 0 : (end == INT_MAX ? L : end - run.s0);
   run.carry_len = to_head < run.nvalid ? to_head : run.nvalid;
   const int e = (end == INT_MAX) ? INT_MAX : end - 1 - run.s0;
   run.end_pos = e < run.nvalid ? e : -1;
   return run;
+}
+
+// Samples per lane for ONE tile.  The greedy packing of whole rays leaves a tile 77 % full on config 4's
+// distribution (322 of 416 samples), and a tile body costs its L samples per lane whatever the fill.  The forward
+// kernels therefore walk a tile of at most 288 samples with 9 samples per lane (odd: conflict-free; every tiled
+// ray has more than kPkL samples, so a run still holds at most one ray boundary): 0.616 -> 0.586 ms on 2^20 rays of
+// 8..256 samples.  More bodies lose to their code size — {7, 9, 11, 13}: forward 0.89 ms, backward 0.88 -> 1.80 ms;
+// the backward kernel, whose body is twice as long, is slower even with two (0.876 -> 0.924 ms) and keeps one.
+#ifndef AVR_PK_L2
+#define AVR_PK_L2 9
+#endif
+template <bool kTwoBodies, typename F>
+__device__ __forceinline__ void with_run_length(int n_s, F&& body) {
+  if (kTwoBodies && kPkL == 13 && AVR_PK_L2 < 13) {
+    if (n_s <= 32 * AVR_PK_L2) {
+      body(std::integral_constant<int, AVR_PK_L2>());
+    } else {
+      body(std::integral_constant<int, 13>());
+    }
+  } else {
+    body(std::integral_constant<int, kPkL>());
+  }
 }
 
 template <bool kWriteW>
@@ -272,10 +296,13 @@ composite_fwd_span_packed_kernel(const PackedArgs a) {
       const int shift = (int)(cur.sb & 3);
       mbar_wait(&pipe.bars[st], (uint32_t)((cur_tile / kPkStages) & 1));
       patch_z_tail(pipe, st, a, cur, lane);
-      const Run run = ragged_run(pipe.ends_stage(st), n_s, lane);
-      const float4* rg = pipe.rgbs_stage(st) + run.s0;
-      float* zs = pipe.z_stage(st) + shift + run.s0;
-      fwd_tile_simple<kPkL, kWriteW>(a.sp, run, rg, zs, cur.r0, lane);
+      with_run_length<true>(n_s, [&](auto len) {
+        constexpr int L = decltype(len)::value;
+        const Run run = ragged_run<L>(pipe.ends_stage(st), n_s, lane);
+        const float4* rg = pipe.rgbs_stage(st) + run.s0;
+        float* zs = pipe.z_stage(st) + shift + run.s0;
+        fwd_tile_simple<L, kWriteW>(a.sp, run, rg, zs, cur.r0, lane);
+      });
       if (kWriteW) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -355,15 +382,18 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
       const int shift = (int)(cur.sb & 3);
       mbar_wait(&pipe.bars[st], (uint32_t)((cur_tile / kPkStages) & 1));
       patch_z_tail(pipe, st, a, cur, lane);
-      const Run run = ragged_run(pipe.ends_stage(st), n_s, lane);
-      RayGrad gA{0.f, 0.f, 0.f, 0.f, 0.f}, gB{0.f, 0.f, 0.f, 0.f, 0.f};
-      if (run.nvalid > 0) {
-        gA = load_ray_grad<false>(a.sp, cur.r0 + run.ray0);  // the packed entry points have no camera-depth map
-        gB = (run.end_pos >= 0 && run.end_pos + 1 < run.nvalid) ? load_ray_grad<false>(a.sp, cur.r0 + run.ray0 + 1) : gA;
-      }
-      float4* rg = pipe.rgbs_stage(st) + run.s0;
-      float* zs = pipe.z_stage(st) + shift + run.s0;
-      bwd_tile_simple<kPkL, false>(a.sp, run, rg, zs, gA, gB, lane);
+      with_run_length<false>(n_s, [&](auto len) {
+        constexpr int L = decltype(len)::value;
+        const Run run = ragged_run<L>(pipe.ends_stage(st), n_s, lane);
+        RayGrad gA{0.f, 0.f, 0.f, 0.f, 0.f}, gB{0.f, 0.f, 0.f, 0.f, 0.f};
+        if (run.nvalid > 0) {
+          gA = load_ray_grad<false>(a.sp, cur.r0 + run.ray0);  // the packed entry points have no camera-depth map
+          gB = (run.end_pos >= 0 && run.end_pos + 1 < run.nvalid) ? load_ray_grad<false>(a.sp, cur.r0 + run.ray0 + 1) : gA;
+        }
+        float4* rg = pipe.rgbs_stage(st) + run.s0;
+        float* zs = pipe.z_stage(st) + shift + run.s0;
+        bwd_tile_simple<L, false>(a.sp, run, rg, zs, gA, gB, lane);
+      });
       if (kOutByTma) {
         fence_proxy_async_smem();
         __syncwarp();
