@@ -173,38 +173,46 @@ __device__ __forceinline__ int z_bulk_elems(int64_t sb, int n_s, int64_t S) {
   return end > zb ? (int)(end - zb) : 0;
 }
 
-// all lanes: publish the tile's ray ends, lane 0: issue the bulk loads
-__device__ __forceinline__ void issue_tile(const PkPipe& pipe, int st, const PackedArgs& a, const Item& it,
-                                           int rel_end, int lane) {
+// all lanes: publish the tile's ray ends, lane 0: issue the bulk loads (n_s samples of rgbs, n_z >= n_s of z: a
+// tile that leaves its last ray open also needs the depth after its last sample)
+__device__ __forceinline__ void issue_tile_n(const PkPipe& pipe, int st, const PackedArgs& a, int64_t sb, int n_s,
+                                             int n_z, int rel_end, int lane) {
   pipe.ends_stage(st)[lane] = rel_end;
   __syncwarp();
   if (lane == 0) {
     if (!kOutByTma) fence_proxy_async_smem();  // generic reads/writes of this slot precede the async refill
-    const int n_s = (int)it.n_s;
-    const int shift = (int)(it.sb & 3);
-    const int zel = z_bulk_elems(it.sb, n_s, a.S);
+    const int shift = (int)(sb & 3);
+    const int zel = z_bulk_elems(sb, n_z, a.S);
     const uint32_t rb = (uint32_t)n_s * 16u, zbytes = (uint32_t)zel * 4u;
     mbar_expect_tx(&pipe.bars[st], rb + zbytes);
-    bulk_g2s(pipe.rgbs_stage(st), a.sp.rgbs + it.sb * 4, rb, &pipe.bars[st]);
-    if (zel > 0) bulk_g2s(pipe.z_stage(st), a.sp.z + (it.sb - shift), zbytes, &pipe.bars[st]);
+    bulk_g2s(pipe.rgbs_stage(st), a.sp.rgbs + sb * 4, rb, &pipe.bars[st]);
+    if (zel > 0) bulk_g2s(pipe.z_stage(st), a.sp.z + (sb - shift), zbytes, &pipe.bars[st]);
   }
 }
+__device__ __forceinline__ void issue_tile(const PkPipe& pipe, int st, const PackedArgs& a, const Item& it,
+                                           int rel_end, int lane) {
+  issue_tile_n(pipe, st, a, it.sb, (int)it.n_s, (int)it.n_s, rel_end, lane);
+}
 
-// after the mbarrier wait: fetch the (<= 3) tile samples of z the bulk copy could not cover
-__device__ __forceinline__ void patch_z_tail(const PkPipe& pipe, int st, const PackedArgs& a, const Item& it, int lane) {
-  const int n_s = (int)it.n_s;
-  const int shift = (int)(it.sb & 3);
-  const int64_t zb = it.sb - shift;
-  const int64_t covered = zb + z_bulk_elems(it.sb, n_s, a.S);
+// after the mbarrier wait: fetch the (<= 4) staged elements of z the bulk copy could not cover
+__device__ __forceinline__ void patch_z_tail_n(const PkPipe& pipe, int st, const PackedArgs& a, int64_t sb, int n_z, int lane) {
+  const int shift = (int)(sb & 3);
+  const int64_t zb = sb - shift;
+  const int64_t covered = zb + z_bulk_elems(sb, n_z, a.S);
   const int64_t gi = covered + lane;
-  if (gi < it.sb + n_s) pipe.z_stage(st)[gi - zb] = a.sp.z[gi];  // at most 3 lanes (warp-uniform loop-free)
+  if (gi < sb + n_z && gi < a.S) pipe.z_stage(st)[gi - zb] = a.sp.z[gi];  // a few lanes (warp-uniform loop-free)
   __syncwarp();
+}
+__device__ __forceinline__ void patch_z_tail(const PkPipe& pipe, int st, const PackedArgs& a, const Item& it, int lane) {
+  patch_z_tail_n(pipe, st, a, it.sb, (int)it.n_s, lane);
 }
 
 // The lane's run inside a ragged tile: which ray its first sample belongs to and where (if
 // anywhere) that ray ends inside the run.  ends[i] = end of the tile's i-th ray, INT_MAX padded.
+// first_k0: position of the tile's first sample inside its ray (> 0 only in the streaming forward kernel, whose
+// tiles may begin inside a ray)
 template <int L>
-__device__ __forceinline__ Run ragged_run(const int* ends, int n_s, int lane) {
+__device__ __forceinline__ Run ragged_run(const int* ends, int n_s, int lane, int first_k0 = 0) {
   Run run;
   run.s0 = lane * L;
   const int rem = n_s - run.s0;
@@ -216,7 +224,7 @@ __device__ __forceinline__ Run ragged_run(const int* ends, int n_s, int lane) {
   }
   if (ends[cnt] <= run.s0) ++cnt;   // cnt in [0, 32]
   if (cnt > 31) cnt = 31;           // idle lanes only
-  const int start = cnt > 0 ? ends[cnt - 1] : 0;
+  const int start = cnt > 0 ? ends[cnt - 1] : -first_k0;
   const int end = ends[cnt];
   run.ray0 = cnt;
   run.k0 = run.s0 - start;
@@ -418,6 +426,255 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
   if (kOutByTma && lane == 0) bulk_wait_all<0>();
 }
 
+// ---- streaming forward -----------------------------------------------------------------
+// The kernels above pack WHOLE rays into a tile, which leaves a 416-sample tile 77 % full on config 4's counts and
+// cuts it short at every ray of <= kPkL samples.  The forward pass does not need whole rays: the warp walks its
+// sample range front to back, so a ray may continue from one tile into the next with its transmittance and partial
+// sums carried in registers.  A tile is then exactly kPkC consecutive samples unless it has to stop at a ray end
+// (before a short ray, after 32 ray ends, at the end of the warp's range) — only tiles that stop at a ray end are
+// partial, so every run of an open tile is full and the tile bodies' "no valid sample after the last ray end" rule
+// still holds.  (The backward pass needs the transmittance from the ray's start AND the reverse scan from its end;
+// it keeps whole-ray tiles.)
+#ifndef AVR_PK_STREAM
+#define AVR_PK_STREAM 1
+#endif
+
+struct StreamItem {
+  int64_t r0;     // ray of the item's first sample
+  int64_t sb;     // first sample
+  int64_t n_ray;  // kItemRay: samples of the short ray
+  int n_s;        // tile: samples
+  int first_k0;   // tile: position of its first sample inside ray r0 (> 0: the ray continues from the tile before)
+  bool open;      // tile: its last sample does not end a ray
+  int kind;
+};
+
+// What starts at sample k_in of ray r (k_in > 0: inside a ray a tile left open).  Updates (r, k_in) to the state
+// after the item; `rel_end` returns the lane's ray end relative to the tile start (INT_MAX unless the ray ends
+// inside the tile).
+__device__ __forceinline__ StreamItem next_stream_item(const Window& w, int64_t& r, int64_t& k_in, int64_t rb, int lane,
+                                                       int& rel_end) {
+  StreamItem it;
+  it.r0 = r;
+  it.sb = w.ostart + k_in;
+  it.kind = kItemNone;
+  it.n_ray = 0;
+  it.n_s = 0;
+  it.first_k0 = 0;
+  it.open = false;
+  rel_end = INT_MAX;
+  if (r >= rb) return it;
+  const bool valid = (r + lane < rb);
+  const int64_t rel64 = valid ? (w.oend - it.sb) : (int64_t)INT_MAX;
+  const int rel = rel64 > (int64_t)INT_MAX ? INT_MAX : (int)rel64;
+  int64_t prev64 = __shfl_up_sync(0xffffffffu, rel64, 1);
+  if (lane == 0) prev64 = -k_in;
+  const int64_t cnt = rel64 - prev64;                       // the ray's length
+  const bool bad = !valid || cnt <= kPkL;                  // cannot be part of a tile
+  const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+  const int first_bad = badmask ? (__ffs(badmask) - 1) : 32;
+  if (first_bad == 0) {  // ray r is short (k_in == 0: a ray a tile left open is long)
+    it.kind = kItemRay;
+    it.n_ray = __shfl_sync(0xffffffffu, rel64, 0);
+    r += 1;
+    k_in = 0;
+    return it;
+  }
+  const int limit = __shfl_sync(0xffffffffu, rel, first_bad - 1);  // end of the last ray a tile may take
+  const int n_s = limit < kPkC ? limit : kPkC;
+  const bool closed = lane < first_bad && rel <= n_s;
+  const int nr_closed = __popc(__ballot_sync(0xffffffffu, closed));
+  const int last_end = __shfl_sync(0xffffffffu, rel, nr_closed > 0 ? nr_closed - 1 : 0);
+  it.kind = kItemTile;
+  it.n_s = n_s;
+  it.first_k0 = k_in > (int64_t)INT_MAX ? INT_MAX : (int)k_in;
+  it.open = nr_closed == 0 || last_end < n_s;
+  rel_end = closed ? rel : INT_MAX;
+  k_in = it.open ? (nr_closed > 0 ? (int64_t)(n_s - last_end) : k_in + n_s) : 0;
+  r += nr_closed;
+  return it;
+}
+
+// fwd_tile_simple (span_bodies.cuh) with a ray carried in from the tile before (cT, cS: its transmittance and
+// partial sums up to this tile; identity when the tile starts at a ray head) and out to the next one.
+template <int L, bool kWriteW>
+__device__ __forceinline__ void fwd_tile_stream(const SpanArgs& a, const Run& run, const float4* rg, float* zs,
+                                                int64_t ray_base, int lane, bool carried_in, bool open, int n_s,
+                                                float& cT, Sums& cS) {
+  const int p = run.end_pos;
+  float wl[L];
+  float Tl = 1.0f;
+  Sums A = zero_sums(), B = zero_sums();
+  float zk = zs[0];
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    const bool last = (j == p);
+    const bool in_a = (j <= p);
+    const float4 c = rg[j];
+    const float z_after = zs[j + 1];
+    const float zn = last ? a.infinity : z_after;
+    const float delta = last ? kLastDelta : zn - zk;
+    const Opacity o = opacity(c.w, delta);
+    const float w = o.alpha * Tl;
+    wl[j] = w;
+    if (in_a) {
+      A.r += w * c.x;
+      A.g += w * c.y;
+      A.b += w * c.z;
+      A.d += w * zn;
+      A.a += w;
+    } else {
+      B.r += w * c.x;
+      B.g += w * c.y;
+      B.b += w * c.z;
+      B.d += w * zn;
+      B.a += w;
+    }
+    Tl = last ? 1.0f : Tl * o.t;
+    zk = z_after;
+  }
+  const bool head0 = (run.k0 == 0);
+  float T_in = Tl;
+  Sums s_in = B;
+  scan_fwd_exclusive(lane, head0 || p >= 0 || run.nvalid == 0, T_in, s_in);
+  if (head0) {
+    T_in = 1.0f;
+    s_in = zero_sums();
+  } else if (carried_in && run.ray0 == 0) {  // still inside the ray the tile before left open
+    s_in.r = cS.r + cT * s_in.r;
+    s_in.g = cS.g + cT * s_in.g;
+    s_in.b = cS.b + cT * s_in.b;
+    s_in.d = cS.d + cT * s_in.d;
+    s_in.a = cS.a + cT * s_in.a;
+    T_in = cT * T_in;
+  }
+  if (p >= 0) {
+    Sums t;
+    t.r = s_in.r + T_in * A.r;
+    t.g = s_in.g + T_in * A.g;
+    t.b = s_in.b + T_in * A.b;
+    t.d = s_in.d + T_in * A.d;
+    t.a = s_in.a + T_in * A.a;
+    store_ray(a, ray_base + run.ray0, t);
+  }
+  // what the open ray has gathered up to the tile's end: the last lane's run after its ray end, if it has one,
+  // else everything that entered the lane composed with the whole run
+  if (open) {
+    const int ll = (n_s - 1) / L;
+    const bool fresh = p >= 0;
+    const float oT = fresh ? Tl : T_in * Tl;
+    Sums o;
+    o.r = fresh ? B.r : s_in.r + T_in * B.r;
+    o.g = fresh ? B.g : s_in.g + T_in * B.g;
+    o.b = fresh ? B.b : s_in.b + T_in * B.b;
+    o.d = fresh ? B.d : s_in.d + T_in * B.d;
+    o.a = fresh ? B.a : s_in.a + T_in * B.a;
+    cT = __shfl_sync(0xffffffffu, oT, ll);
+    cS.r = __shfl_sync(0xffffffffu, o.r, ll);
+    cS.g = __shfl_sync(0xffffffffu, o.g, ll);
+    cS.b = __shfl_sync(0xffffffffu, o.b, ll);
+    cS.d = __shfl_sync(0xffffffffu, o.d, ll);
+    cS.a = __shfl_sync(0xffffffffu, o.a, ll);
+  } else {
+    cT = 1.0f;
+    cS = zero_sums();
+  }
+  if (kWriteW) {
+    __syncwarp();  // every lane has finished reading z from this stage
+#pragma unroll
+    for (int j = 0; j < L; ++j) zs[j] = (p < 0 || j <= p) ? wl[j] * T_in : wl[j];
+  }
+}
+
+template <bool kWriteW>
+__global__ void __launch_bounds__(kPkWarps * 32)
+composite_fwd_stream_packed_kernel(const PackedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PkPipe pipe;
+  pipe.init(smem, warp, lane);
+
+  const int64_t gw = (int64_t)blockIdx.x * kPkWarps + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * kPkWarps;
+  const int64_t ra = warp_lower_bound(a.offsets, a.R, (a.S / n_warps) * gw + min(gw, a.S % n_warps), lane);
+  const int64_t rb = (gw + 1 == n_warps)
+                         ? a.R
+                         : warp_lower_bound(a.offsets, a.R, (a.S / n_warps) * (gw + 1) + min(gw + 1, a.S % n_warps), lane);
+  const float4* rgbs4 = reinterpret_cast<const float4*>(a.sp.rgbs);
+
+  int64_t tiles = 0;  // tiles issued so far (tile t lives in stage t % NS, parity (t / NS) & 1)
+  int rel_end;
+  int64_t r = ra, k_in = 0;  // the walk's position: sample k_in of ray r
+  Window win = load_window(a.offsets, r, rb, lane);
+  StreamItem cur = next_stream_item(win, r, k_in, rb, lane, rel_end);
+  int64_t cur_tile = -1;
+  if (cur.kind == kItemTile) {
+    cur_tile = tiles++;
+    issue_tile_n(pipe, (int)(cur_tile % kPkStages), a, cur.sb, cur.n_s, cur.n_s + 1, rel_end, lane);
+  }
+  win = load_window(a.offsets, r, rb, lane);
+  float cT = 1.0f;  // the ray the previous tile left open
+  Sums cS = zero_sums();
+
+  while (cur.kind != kItemNone) {
+    // ---- prepare the next item (its window was loaded one iteration ago) and start its loads
+    StreamItem nxt = next_stream_item(win, r, k_in, rb, lane, rel_end);
+    int64_t nxt_tile = -1;
+    if (nxt.kind == kItemTile) {
+      nxt_tile = tiles++;
+      if (kOutByTma && kWriteW && lane == 0) bulk_wait_read<1>();  // the store that last read this stage is done
+      issue_tile_n(pipe, (int)(nxt_tile % kPkStages), a, nxt.sb, nxt.n_s, nxt.n_s + 1, rel_end, lane);
+    }
+    if (nxt.kind != kItemNone) win = load_window(a.offsets, r, rb, lane);
+
+    // ---- process the current item
+    if (cur.kind == kItemTile) {
+      const int st = (int)(cur_tile % kPkStages);
+      const int n_s = cur.n_s;
+      const int shift = (int)(cur.sb & 3);
+      mbar_wait(&pipe.bars[st], (uint32_t)((cur_tile / kPkStages) & 1));
+      patch_z_tail_n(pipe, st, a, cur.sb, n_s + 1, lane);
+      with_run_length<true>(n_s, [&](auto len) {
+        constexpr int L = decltype(len)::value;
+        const Run run = ragged_run<L>(pipe.ends_stage(st), n_s, lane, cur.first_k0);
+        const float4* rg = pipe.rgbs_stage(st) + run.s0;
+        float* zs = pipe.z_stage(st) + shift + run.s0;
+        fwd_tile_stream<L, kWriteW>(a.sp, run, rg, zs, cur.r0, lane, cur.first_k0 > 0, cur.open, n_s, cT, cS);
+      });
+      if (kWriteW) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        // aligned interior by bulk store, up to 3 samples at either end by ordinary stores
+        int a0 = (4 - shift) & 3;
+        if (a0 > n_s) a0 = n_s;
+        const int len = (n_s - a0) & ~3;
+        const float* zt = pipe.z_stage(st) + shift;  // tile sample s at zt[s]
+        float* wg = a.sp.w + cur.sb;
+        if (kOutByTma) {
+          if (lane == 0 && len > 0) bulk_s2g(wg + a0, zt + a0, (uint32_t)len * 4u);
+          if (lane == 0) bulk_commit();
+        } else {  // coalesced 16-byte stores: the stage is free again when this iteration ends
+          const float4* src4 = reinterpret_cast<const float4*>(zt + a0);
+          float4* dst4 = reinterpret_cast<float4*>(wg + a0);
+          for (int v = lane; v < (len >> 2); v += 32) dst4[v] = src4[v];
+        }
+        if (lane < a0) wg[lane] = zt[lane];
+        const int t0 = a0 + len;
+        if (t0 + lane < n_s) wg[t0 + lane] = zt[t0 + lane];
+        if (!kOutByTma) __syncwarp();
+      } else {
+        __syncwarp();
+      }
+    } else {
+      wray_fwd_ray(rgbs4, a.sp.z, cur.sb, cur.n_ray, cur.r0, a.sp.white_back, a.sp.infinity, a.sp.w, a.sp.rgb,
+                   a.sp.depth, lane);
+    }
+    cur = nxt;
+    cur_tile = nxt_tile;
+  }
+  if (kOutByTma && kWriteW && lane == 0) bulk_wait_all<0>();
+}
+
 // ---- host side -----------------------------------------------------------------------
 bool span_packed_eligible(const void* rgbs, const void* z, const void* w_or_null, const void* d_rgbs_or_null) {
   if (!option(OPT_PACKED_SPAN, 1)) return false;
@@ -464,8 +721,13 @@ int launch_composite_fwd_span_packed(const float* rgbs, const float* z, const in
   a.offsets = offsets;
   a.R = R;
   a.S = S;
+#if AVR_PK_STREAM
+  return w ? packed_launch(composite_fwd_stream_packed_kernel<true>, a, stream)
+           : packed_launch(composite_fwd_stream_packed_kernel<false>, a, stream);
+#else
   return w ? packed_launch(composite_fwd_span_packed_kernel<true>, a, stream)
            : packed_launch(composite_fwd_span_packed_kernel<false>, a, stream);
+#endif
 }
 
 int launch_composite_bwd_span_packed(const float* rgbs, const float* z, const int64_t* offsets,

@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--rays", type=int, default=1 << 20)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--what", nargs="+", default=["coarse", "importance", "packed", "geometry", "adaptive"])
+    ap.add_argument("--min-count", type=int, default=8, help="packed: shortest ray (BASELINE.json config 4: 8)")
     ap.add_argument("--warmup", type=int, default=3, help="untimed launches per kernel (1 for ncu captures)")
     a = ap.parse_args()
     global WARMUP
@@ -158,7 +159,7 @@ def main():
         del x, z, zs, perm, gz
     if "packed" in a.what:
         rp = min(r, 1 << 20)
-        counts = torch.randint(8, 257, (rp,), device=dev, generator=g)
+        counts = torch.randint(a.min_count, 257, (rp,), device=dev, generator=g)
         offsets = torch.zeros(rp + 1, dtype=torch.int64, device=dev)
         offsets[1:] = torch.cumsum(counts, 0)
         s = int(offsets[-1])
