@@ -10,12 +10,15 @@
 //   * walking its range, the warp packs consecutive rays greedily into tiles of at most
 //     C = 32*L samples (at most 32 rays): the next 32 ray ends are read with one coalesced
 //     load one iteration ahead, a ballot finds how many fit;
-//   * a tile only takes rays with more than L samples, so a lane's run holds at most one
-//     ray boundary and the branch-free "simple" tile bodies apply unchanged; the per-lane
-//     run description (ray, boundary position) is found per tile by a 6-step search of the
-//     tile's ray-end table in shared memory;
-//   * rays a tile cannot take — count <= L (incl. empty rays) or count > C — are composited
+//   * a tile only takes a ray whose last sample falls into another lane's run than the last
+//     sample of the ray before it (any ray longer than L; in the backward kernel also a shorter
+//     one unless it is unlucky, and then it opens the next tile), so a lane's run holds at most one ray boundary and the
+//     branch-free "simple" tile bodies apply unchanged; the per-lane run description (ray,
+//     boundary position) is found per tile by a 6-step search of the tile's ray-end table in
+//     shared memory;
+//   * rays a tile cannot take — empty ones, and in the backward kernel count > C — are composited
 //     by the same warp with the warp-per-ray routine straight from global memory;
+//   * the forward kernels do not need whole rays in a tile: see "streaming forward" below;
 //   * z and w slices start at arbitrary sample offsets: the stage keeps the global 16-byte
 //     phase (bulk copies cover the aligned interior, up to 3 elements at either end go
 //     through ordinary loads/stores);
@@ -42,6 +45,9 @@ namespace avr {
 #endif
 #ifndef AVR_PK_STAGES
 #define AVR_PK_STAGES 2
+#endif
+#ifndef AVR_PK_L2
+#define AVR_PK_L2 9  // run length of the forward kernels' second body (small tiles)
 #endif
 constexpr int kPkL = AVR_PK_L;   // samples per lane (odd: conflict-free shared-memory runs)
 constexpr int kPkC = 32 * kPkL;  // samples per tile
@@ -104,6 +110,18 @@ __device__ __forceinline__ Window load_window(const int64_t* __restrict__ offset
   return w;
 }
 
+// The tile bodies allow ONE ray end per lane run.  Rays longer than a run guarantee that; a shorter ray still fits
+// when its last sample and the last sample of the ray before it fall into different runs (always true for the
+// first ray of a tile).  `rel`: the lane's ray end relative to the tile start, >= 1.  Checked for both run lengths
+// the kernels use.  (Short rays used to leave the tiles altogether: each cut a tile short and went through the
+// warp-per-ray routine — 4.5 % of the kernels' time on counts 8..256, where 2.4 % of the rays have <= 13 samples.)
+__device__ __forceinline__ bool ends_share_a_run(int rel, int lane) {
+  const int run_a = (rel - 1) / kPkL, run_b = (rel - 1) / AVR_PK_L2;
+  int prev_a = __shfl_up_sync(0xffffffffu, run_a, 1), prev_b = __shfl_up_sync(0xffffffffu, run_b, 1);
+  if (lane == 0) prev_a = prev_b = -1;
+  return run_a == prev_a || run_b == prev_b;
+}
+
 // Decide what the next work item starting at ray r is.  `rel_end` returns the lane's ray end
 // relative to the item start (INT_MAX for lanes past it); meaningful for tiles.
 __device__ __forceinline__ Item next_item(const Window& w, int64_t r, int64_t rb, int lane, int& rel_end) {
@@ -121,7 +139,8 @@ __device__ __forceinline__ Item next_item(const Window& w, int64_t r, int64_t rb
   int prev = __shfl_up_sync(0xffffffffu, rel, 1);
   if (lane == 0) prev = 0;
   const int cnt = rel - prev;
-  const bool ok = valid && rel <= kPkC && cnt > kPkL;
+  const bool shares = ends_share_a_run(rel, lane);  // (shuffles: every lane, before any short-circuit)
+  const bool ok = valid && rel <= kPkC && cnt >= 1 && !shares;
   const unsigned mask = __ballot_sync(0xffffffffu, ok);
   const int nr = (mask == 0xffffffffu) ? 32 : (__ffs(~mask) - 1);  // leading rays that fit
   if (nr == 0) {  // first ray is too short or too long for a tile: composite it on its own
@@ -241,9 +260,6 @@ __device__ __forceinline__ Run ragged_run(const int* ends, int n_s, int lane, in
 // ray has more than kPkL samples, so a run still holds at most one ray boundary): 0.616 -> 0.586 ms on 2^20 rays of
 // 8..256 samples.  More bodies lose to their code size — {7, 9, 11, 13}: forward 0.89 ms, backward 0.88 -> 1.80 ms;
 // the backward kernel, whose body is twice as long, is slower even with two (0.876 -> 0.924 ms) and keeps one.
-#ifndef AVR_PK_L2
-#define AVR_PK_L2 9
-#endif
 template <bool kTwoBodies, typename F>
 __device__ __forceinline__ void with_run_length(int n_s, F&& body) {
   if (kTwoBodies && kPkL == 13 && AVR_PK_L2 < 13) {
@@ -470,7 +486,9 @@ __device__ __forceinline__ StreamItem next_stream_item(const Window& w, int64_t&
   int64_t prev64 = __shfl_up_sync(0xffffffffu, rel64, 1);
   if (lane == 0) prev64 = -k_in;
   const int64_t cnt = rel64 - prev64;                       // the ray's length
-  const bool bad = !valid || cnt <= kPkL;                  // cannot be part of a tile
+  // cannot be (the next) part of a tile.  (The backward kernel's finer rule, ends_share_a_run, buys nothing here:
+  // with tiles that stay full across rays the forward kernels run at the HBM roofline either way, 0.536 vs 0.541 ms.)
+  const bool bad = !valid || cnt <= kPkL;
   const unsigned badmask = __ballot_sync(0xffffffffu, bad);
   const int first_bad = badmask ? (__ffs(badmask) - 1) : 32;
   if (first_bad == 0) {  // ray r is short (k_in == 0: a ray a tile left open is long)
