@@ -572,7 +572,7 @@ int launch_sort_rays(const float* z_in, int64_t R, int K, float* z_out, int32_t*
   if (K % 4 == 0 && K <= 128 && aligned16(z_in) && aligned16(z_out) && aligned16(perm)) {
     // a short streaming kernel: as many resident warps as the registers allow (48 -> 40 per SM), each with one
     // 512-byte load in flight
-    sort_rays_presorted_kernel<<<grid_for(R, kSamplerWarps * 32, grid_cap(16)), kSamplerWarps * 32, smem, stream>>>(
+    sort_rays_presorted_kernel<<<grid_for(R, kSamplerWarps * 32, 1 << 24), kSamplerWarps * 32, smem, stream>>>(
         z_in, R, K, P, z_out, perm);
     return check_launch();
   }
