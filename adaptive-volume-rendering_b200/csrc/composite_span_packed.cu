@@ -427,9 +427,11 @@ composite_bwd_span_packed_kernel(const PackedArgs a) {
         }
       } else {
         __syncwarp();
-        const float4* src4 = pipe.rgbs_stage(st);
-        float4* dst4 = d4 + cur.sb;
-        for (int v = lane; v < n_s; v += 32) dst4[v] = src4[v];  // 512-byte coalesced rows
+        const float4* src4 = pipe.rgbs_stage(st) + lane;
+        float4* dst4 = d4 + cur.sb + lane;
+#pragma unroll
+        for (int it = 0; it < kPkL; ++it)  // 512-byte coalesced rows at constant offsets from two pointers
+          if (it * 32 + lane < n_s) dst4[it * 32] = src4[it * 32];
         __syncwarp();
       }
     } else if (cur.n_s > 0) {
